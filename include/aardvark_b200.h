@@ -1,0 +1,292 @@
+/*
+ * aardvark_b200.h -- C ABI of the B200-native haplotype-comparison hot path.
+ *
+ * This header is the drop-in boundary for ONE path of PacificBiosciences/aardvark
+ * (v0.10.5): the per-cluster solvers that `aardvark compare` / `aardvark merge`
+ * call from their rayon loops.  The reference has no FFI today; the two pure
+ * functions below are its de-facto operator interface, and each entry point here
+ * names the reference interface it replaces (paths relative to the reference):
+ *
+ *   solve_compare_region(&CompareRegion, &ReferenceGenome, CompareConfig, ..)
+ *       -> anyhow::Result<CompareBenchmark>          src/waffle_solver.rs:122-124
+ *       call site (rayon par_iter)                   src/main.rs:251-268
+ *   solve_merge_region(&MultiRegion, &ReferenceGenome, MergeConfig)
+ *       -> anyhow::Result<MergeBenchmark>            src/merge_solver.rs:110
+ *       call site (rayon par_iter)                   src/main.rs:463-478
+ *   wfa_ed(&[u8], &[u8]) -> usize                    src/util/sequence_alignment.rs:9-13
+ *
+ * Because the reference materialises ALL regions before solving
+ * (src/main.rs:217-232, :434-443), the per-region call is replaced by ONE
+ * batched call over a flat SoA/CSR description of every region.
+ *
+ * Plain C: pointers + sizes only, no torch/CUDA types.  All pointers are HOST
+ * pointers unless a function says otherwise; the library owns all device
+ * memory.  Nothing allocated by the library is freed by the caller.
+ *
+ * Two libraries implement (subsets of) this header with identical struct
+ * layouts so that outputs can be compared bit for bit:
+ *   aardvark_b200/csrc  -> libaardvark_b200.so   (CUDA sm_100a; the product)
+ *   oracle/             -> liboracle.so          (CPU restatement; TEST ONLY)
+ */
+#ifndef AARDVARK_B200_H
+#define AARDVARK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ enums */
+
+/* VariantType, same discriminants as src/data_types/variants.rs:6-31 */
+enum {
+    AVK_VT_SNV = 0,
+    AVK_VT_INSERTION = 1,
+    AVK_VT_DELETION = 2,
+    AVK_VT_INDEL = 3,
+    AVK_VT_SV_INSERTION = 4,
+    AVK_VT_SV_DELETION = 5,
+    AVK_VT_SV_DUPLICATION = 6,
+    AVK_VT_SV_INVERSION = 7,
+    AVK_VT_SV_BREAKEND = 8,
+    AVK_VT_TR_CONTRACTION = 9,
+    AVK_VT_TR_EXPANSION = 10,
+    AVK_VT_UNKNOWN = 11,
+    AVK_N_VARIANT_TYPES = 12
+};
+
+/* PhasedZygosity, declaration order of src/data_types/phase_enums.rs:33-46 */
+enum {
+    AVK_ZYG_UNKNOWN = 0,
+    AVK_ZYG_HOM_REF = 1,
+    AVK_ZYG_UNPHASED_HET = 2,
+    AVK_ZYG_PHASED_HET01 = 3,
+    AVK_ZYG_PHASED_HET10 = 4,
+    AVK_ZYG_HOM_ALT = 5
+};
+
+/* Classification, src/data_types/variant_metrics.rs:11-22 */
+enum {
+    AVK_CLASS_UNKNOWN = 0,
+    AVK_CLASS_TP = 1,
+    AVK_CLASS_FN = 2,
+    AVK_CLASS_FP = 3
+};
+
+/* MergeClassification, src/data_types/merge_benchmark.rs:7-20 */
+enum {
+    AVK_MERGE_DIFFERENT = 0,
+    AVK_MERGE_NO_CONFLICT = 1,
+    AVK_MERGE_MAJORITY_AGREE = 2,
+    AVK_MERGE_CONFLICT_SELECTION = 3,
+    AVK_MERGE_BASEPAIR_IDENTICAL = 4
+};
+
+/* GroupMetrics flattened to 22 u64 (src/data_types/grouped_metrics.rs:149-161,
+ * summary_metrics.rs:5-14,82-91).  Each SummaryMetrics block is
+ * {truth_tp, truth_fn, query_tp, query_fp}. */
+enum {
+    AVK_M_GT = 0,            /* +0 tp +1 fn +2 qtp +3 qfp */
+    AVK_M_GT_TRUTH_FN_GT = 4,
+    AVK_M_GT_QUERY_FP_GT = 5,
+    AVK_M_HAP = 6,
+    AVK_M_WEIGHTED_HAP = 10,
+    AVK_M_BASEPAIR = 14,
+    AVK_M_RECORD_BP = 18,
+    AVK_N_METRICS = 22
+};
+/* group index into per-region metric rows: 0 = joint, 1 + VariantType = that type */
+#define AVK_N_GROUPS (1 + AVK_N_VARIANT_TYPES)
+
+/* Per-region status.  0 = Ok(..); anything else is the reference's Err(..)
+ * (counted as an "error block", src/main.rs:259-262) or an input the reference
+ * would panic on.  The GPU library adds AVK_ST_WORKSPACE for its own limits. */
+enum {
+    AVK_ST_OK = 0,
+    AVK_ST_BAD_ZYGOSITY = 1,      /* HomRef/Unknown zygosity: reference panics (query_optimizer.rs:315) */
+    AVK_ST_NO_RESULT = 2,         /* "no results found" / "No result found for problem" */
+    AVK_ST_TRUTH_FP = 3,          /* expected < observed (waffle_solver.rs:322, grouped_metrics.rs:197) */
+    AVK_ST_TP_UNDERFLOW = 4,      /* ensure!(truth_tp >= basepair tp) waffle_solver.rs:492-493 */
+    AVK_ST_BAD_INPUT = 5,         /* malformed batch entry (window outside contig, empty allele, ...) */
+    AVK_ST_WORKSPACE = 6          /* GPU only: search exceeded the largest workspace tier */
+};
+
+/* Library-level return codes */
+enum {
+    AVK_OK = 0,
+    AVK_ERR_INVALID = -1,
+    AVK_ERR_CUDA = -2,
+    AVK_ERR_NO_REFERENCE = -3,
+    AVK_ERR_OOM = -4
+};
+
+/* ------------------------------------------------------------- input batch */
+
+/* Variant fields read on the path (src/data_types/variants.rs:73-91): position,
+ * allele0, allele1, variant_type, raw_allele_space; zygosity is the parallel
+ * Vec<PhasedZygosity>.  allele0 is stored at allele_pool[allele_off ..+a0_len],
+ * allele1 directly after it.  Alleles are raw bytes and compared as raw bytes
+ * (src/dwfa/dynamic_wfa.rs:118). */
+typedef struct avk_variant_table {
+    uint64_t n_variants;
+    const uint32_t *position;          /* 0-based, contigs < 2^32 bp */
+    const uint8_t *variant_type;       /* AVK_VT_* */
+    const uint8_t *zygosity;           /* AVK_ZYG_* */
+    const uint32_t *raw_allele_space;  /* pre-trim max allele length (RECORD_BP) */
+    const uint32_t *allele_off;
+    const uint32_t *a0_len;
+    const uint32_t *a1_len;
+    const uint8_t *allele_pool;
+    uint64_t allele_pool_len;
+} avk_variant_table;
+
+/* A batch of regions, each with n_inputs variant lists.  Compare uses
+ * n_inputs == 2 (input 0 = truth, input 1 = query: compare_region.rs:102-118);
+ * merge uses n_inputs >= 2 (multi_region.rs:9-18).  List (r, k) is the variant
+ * index range [var_off[r*n_inputs+k], var_off[r*n_inputs+k+1]); every list is
+ * position-sorted (region_generation.rs:373). */
+typedef struct avk_region_batch {
+    uint64_t n_regions;
+    uint32_t n_inputs;
+    const uint64_t *region_id;   /* [n_regions] */
+    const uint32_t *contig;      /* [n_regions] index given to avk_set_reference */
+    const uint32_t *start;       /* [n_regions] Coordinates.start (0-based) */
+    const uint32_t *end;         /* [n_regions] Coordinates.end (exclusive) */
+    const uint64_t *var_off;     /* [n_regions*n_inputs + 1] */
+    avk_variant_table variants;
+} avk_region_batch;
+
+/* CompareConfig, src/waffle_solver.rs:94-115 */
+typedef struct avk_compare_cfg {
+    uint32_t max_branch_factor;      /* default 50 */
+    uint32_t enable_exact_shortcut;  /* default 0 */
+    uint32_t enable_sequences;       /* fill the sequence bundle outputs */
+    uint32_t reserved;
+} avk_compare_cfg;
+
+/* MergeConfig, src/merge_solver.rs:62-84 */
+typedef struct avk_merge_cfg {
+    uint32_t max_branch_factor;
+    uint32_t no_conflict_enabled;
+    uint32_t majority_voting_enabled;
+    int32_t conflict_selection;      /* -1 = None */
+} avk_merge_cfg;
+
+/* ------------------------------------------------------------ output (SoA) */
+
+/* CompareBenchmark (src/data_types/compare_benchmark.rs:9-33) as caller-owned
+ * arrays.  Any pointer may be NULL to skip that output, except status. */
+typedef struct avk_compare_out {
+    int32_t *status;          /* [n_regions] AVK_ST_* */
+    uint32_t *ed1;            /* [n_regions] bm_edit_distance_h1 */
+    uint32_t *ed2;            /* [n_regions] bm_edit_distance_h2 */
+    uint64_t *region_metrics; /* [n_regions][AVK_N_GROUPS][AVK_N_METRICS] GroupTypeMetrics */
+    uint16_t *type_mask;      /* [n_regions] bit t set <=> variant_metrics has key t */
+    /* per variant, indexed like the variant table (VariantMetrics,
+     * variant_metrics.rs:25-35): truth entries as computed, query entries
+     * already toggled (compare_benchmark.rs:109-123) */
+    uint8_t *var_expected;    /* [n_variants] */
+    uint8_t *var_observed;    /* [n_variants] */
+    uint8_t *var_class;       /* [n_variants] AVK_CLASS_* */
+    /* reduction over all status==0 regions: what SummaryWriter::
+     * add_comparison_benchmark accumulates (writers/summary.rs:146-158) */
+    uint64_t *totals;         /* [AVK_N_GROUPS][AVK_N_METRICS] */
+    uint16_t *totals_mask;    /* [1] */
+    uint64_t *solved_blocks;  /* [1] */
+    uint64_t *error_blocks;   /* [1] */
+    /* optional stratified reduction: region r belongs to strata
+     * strat_idx[strat_off[r] .. strat_off[r+1]) (containment_regions) */
+    const uint64_t *strat_off;   /* [n_regions+1] or NULL */
+    const uint32_t *strat_idx;
+    uint32_t n_strata;
+    uint32_t pad0;
+    uint64_t *strat_totals;   /* [n_strata][AVK_N_GROUPS][AVK_N_METRICS] */
+    /* optional SequenceBundle (compare_benchmark.rs:159-185): 5 strings per
+     * region in the order ref, truth1, truth2, query1, query2.  String s of
+     * region r is written at seq_pool[seq_off[r*5+s]] with length seq_len[r*5+s];
+     * seq_off is an INPUT computed by avk_compare_seq_offsets. */
+    const uint64_t *seq_off;  /* [n_regions*5 + 1] */
+    uint32_t *seq_len;        /* [n_regions*5] */
+    uint8_t *seq_pool;
+} avk_compare_out;
+
+/* MergeBenchmark (src/data_types/merge_benchmark.rs:57-62) */
+typedef struct avk_merge_out {
+    int32_t *status;       /* [n_regions] */
+    uint8_t *classification; /* [n_regions] AVK_MERGE_* */
+    uint8_t *n_indices;    /* [n_regions] number of valid entries in indices row */
+    uint8_t *indices;      /* [n_regions][n_inputs] ascending input indices (or the selected index) */
+} avk_merge_out;
+
+/* Work counters (DESIGN.md "algorithmic work"): filled by both libraries when
+ * non-NULL so that roofline numerators come from the same definition. */
+typedef struct avk_work_counters {
+    uint64_t alignments;     /* finalize() calls (global EDs) */
+    uint64_t cells;          /* sum over alignments/updates of wavefront entries touched */
+    uint64_t matched_bases;  /* bases walked by extend() */
+    uint64_t search_pops;    /* optimize_sequences pops */
+    uint64_t exact_pops;     /* optimize_gt_alleles pops */
+} avk_work_counters;
+
+/* ------------------------------------------------------ GPU library (product) */
+
+typedef struct avk_ctx avk_ctx;
+
+/* Create a context bound to one CUDA device (one process per GPU). */
+int avk_create(int device, avk_ctx **out);
+void avk_destroy(avk_ctx *ctx);
+const char *avk_last_error(const avk_ctx *ctx);
+
+/* Replaces ReferenceGenome::from_fasta + get_full_chromosome
+ * (src/main.rs:94, src/waffle_solver.rs:131): uploads the contigs once; they
+ * stay resident in HBM for every later batch. */
+int avk_set_reference(avk_ctx *ctx, uint32_t n_contigs,
+                      const uint8_t *const *seqs, const uint64_t *lens);
+
+/* Replaces the par_iter over solve_compare_region (src/main.rs:251-268). */
+int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch,
+                      const avk_compare_cfg *cfg, avk_compare_out *out);
+
+/* Replaces the par_iter over solve_merge_region (src/main.rs:463-478). */
+int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch,
+                    const avk_merge_cfg *cfg, avk_merge_out *out);
+
+/* Batched global edit distance == wfa_ed (src/util/sequence_alignment.rs:9-13).
+ * Pair p aligns pool[a_off[p]..+a_len[p]] against pool[b_off[p]..+b_len[p]]. */
+int avk_wfa_ed_batch(avk_ctx *ctx, uint64_t n_pairs, const uint8_t *pool, uint64_t pool_len,
+                     const uint64_t *a_off, const uint32_t *a_len,
+                     const uint64_t *b_off, const uint32_t *b_len, uint32_t *ed_out);
+
+/* Upper-bound layout for the optional sequence bundle: fills
+ * seq_off[n_regions*5+1]; returns the pool size in *pool_len. Host only. */
+int avk_compare_seq_offsets(const avk_region_batch *batch, uint64_t *seq_off, uint64_t *pool_len);
+
+/* Device-resident variants used by bench.py (`value`, inputs already in HBM):
+ * upload once, run many times, download once. */
+int avk_compare_upload(avk_ctx *ctx, const avk_region_batch *batch);
+int avk_compare_run_resident(avk_ctx *ctx, const avk_compare_cfg *cfg);
+int avk_compare_download(avk_ctx *ctx, avk_compare_out *out);
+/* Milliseconds spent in the phases of the last resident run (CUDA events on the
+ * library's stream): [0] alt_ed kernel, [1] search kernel(s), [2] heavy ED kernel,
+ * [3] finalize/reduce, [4] total. */
+int avk_last_timings(avk_ctx *ctx, float *ms5);
+int avk_last_work(avk_ctx *ctx, avk_work_counters *out);
+/* Number of kernel launches issued by the library since avk_create. */
+uint64_t avk_launch_count(const avk_ctx *ctx);
+
+/* ------------------------------------------------------ CPU oracle (tests only) */
+
+int orc_compare_batch(const avk_region_batch *batch, const uint8_t *const *contigs,
+                      const uint64_t *contig_lens, uint32_t n_contigs,
+                      const avk_compare_cfg *cfg, avk_compare_out *out,
+                      int n_threads, avk_work_counters *work);
+int orc_merge_batch(const avk_region_batch *batch, const uint8_t *const *contigs,
+                    const uint64_t *contig_lens, uint32_t n_contigs,
+                    const avk_merge_cfg *cfg, avk_merge_out *out,
+                    int n_threads, avk_work_counters *work);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AARDVARK_B200_H */
