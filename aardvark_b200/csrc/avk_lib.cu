@@ -1,0 +1,700 @@
+// avk_lib.cu -- kernels and the C ABI of libaardvark_b200.so (include/aardvark_b200.h).
+//
+// Kernels (all sm_100a, no tensor cores -- integer DP):
+//   k_alt_ed       per-variant ED(allele0, allele1)           variants.rs:413-415 (alt_ed)
+//   k_compare      one warp per cluster, persistent warps     waffle_solver.rs:122-284
+//   k_merge        one warp per cluster                       merge_solver.rs:110-200
+//   k_wfa_ed       one warp per alignment                     util/sequence_alignment.rs:9-13
+//   k_reduce       sum of per-region metrics                  writers/summary.rs:146-158
+//
+// There is NO CPU fallback in this library: every entry point either runs the CUDA path or
+// returns an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "avk_solver.cuh"
+
+using namespace avk;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return (e_ == cudaErrorMemoryAllocation) ? AVK_ERR_OOM : AVK_ERR_CUDA;                 \
+        }                                                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ kernels
+
+__device__ __forceinline__ void flush_work(const WorkAcc &w, unsigned long long *out) {
+    if (lane_id() == 0 && out) {
+        atomicAdd(out + 0, w.alignments); atomicAdd(out + 1, w.cells); atomicAdd(out + 2, w.matched);
+        atomicAdd(out + 3, w.search_pops); atomicAdd(out + 4, w.exact_pops);
+    }
+}
+
+// alt_ed: 32 variants per warp pass; SNVs are answered by their lane, everything else is aligned
+// warp-cooperatively (prefix shortcut for pure insertions/deletions, WFA otherwise).
+__global__ void __launch_bounds__(256) k_alt_ed(DevBatch b, u64 n_variants, u32 *alt_ed, int *scratch, int scratch_ints,
+                                                unsigned long long *work_out) {
+    const int lane = lane_id();
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int *wf = scratch + warp * (u64)scratch_ints;
+    WorkAcc w; w.clear();
+    for (u64 base = warp * 32; base < n_variants; base += n_warps * 32) {
+        const u64 v = base + lane;
+        bool coop = false;
+        if (v < n_variants) {
+            const u32 l0 = b.l0[v], l1 = b.l1[v];
+            if (l0 == 1 && l1 == 1) alt_ed[v] = (b.pool[b.aoff[v]] != b.pool[b.aoff[v] + 1]) ? 1u : 0u;
+            else coop = true;
+        }
+        unsigned m = __ballot_sync(AVK_FULL, coop);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const u64 vv = base + src;
+            const int l0 = (int)b.l0[vv], l1 = (int)b.l1[vv];
+            const u8 *a0 = b.pool + b.aoff[vv];
+            const u8 *a1 = a0 + l0;
+            int ed;
+            const int mn = min(l0, l1);
+            if (mn == 0) ed = max(l0, l1);
+            else if (2 * max(l0, l1) + 3 > scratch_ints) ed = 0;   // cannot happen: host sizes scratch by the max allele
+            else {
+                const int p = warp_lcp(a0, l0, a1, l1);
+                if (p == mn) ed = max(l0, l1) - mn;                // one allele is a prefix of the other
+                else {
+                    ed = wfa_ed_warp(a0, l0, a1, l1, wf, (scratch_ints - 3) / 2, w);
+                    if (ed < 0) ed = 0;
+                }
+            }
+            if (lane == 0) alt_ed[vv] = (u32)ed;
+        }
+    }
+    flush_work(w, work_out);
+}
+
+__global__ void __launch_bounds__(256) k_wfa_ed(u64 n_pairs, const u8 *pool, const u64 *a_off, const u32 *a_len,
+                                                const u64 *b_off, const u32 *b_len, u32 *ed_out, int *scratch,
+                                                int scratch_ints, u32 *counter, unsigned long long *work_out) {
+    const int lane = lane_id();
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int *wf = scratch + warp * (u64)scratch_ints;
+    WorkAcc w; w.clear();
+    for (;;) {
+        u32 p = 0;
+        if (lane == 0) p = atomicAdd(counter, 1u);
+        p = __shfl_sync(AVK_FULL, p, 0);
+        if (p >= n_pairs) break;
+        const int ed = wfa_ed_warp(pool + a_off[p], (int)a_len[p], pool + b_off[p], (int)b_len[p], wf, (scratch_ints - 3) / 2, w);
+        if (lane == 0) ed_out[p] = (u32)ed;
+    }
+    flush_work(w, work_out);
+}
+
+__device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const DevCompareOut &out, u64 r, bool metrics_only) {
+    const int lane = lane_id();
+    u64 *gm = out.region_metrics + r * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
+    for (int i = lane; i < AVK_N_GROUPS * AVK_N_METRICS; i += 32) gm[i] = 0;
+    if (!metrics_only) {
+        const u64 v0 = b.var_off[r * 2], v1 = b.var_off[r * 2 + 2];
+        for (u64 v = v0 + lane; v < v1; v += 32) { out.vexp[v] = 0; out.vobs[v] = 0; out.vcls[v] = AVK_CLASS_UNKNOWN; }
+        if (lane == 0) { out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = 0; }
+        if (out.seq_off && lane < 5) out.seq_len[r * 5 + lane] = 0;
+    }
+    __syncwarp();
+}
+
+// Persistent warps pull clusters from a global counter.  A cluster whose search does not fit this
+// tier's per-warp arena is appended to fail_list and re-run by the next (larger) tier.
+__global__ void __launch_bounds__(256) k_compare(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, const u32 *work_list,
+                                                 u32 n_work, u32 *counter, u8 *arena_base, long long arena_bytes,
+                                                 u32 *fail_list, u32 *fail_count, int last_tier,
+                                                 unsigned long long *work_out) {
+    const int lane = lane_id();
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    WorkAcc w; w.clear();
+    RegionSolver s(b, w);
+    s.arena = arena_base + warp * (u64)arena_bytes;
+    s.arena_bytes = arena_bytes;
+    for (;;) {
+        u32 idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1u);
+        idx = __shfl_sync(AVK_FULL, idx, 0);
+        if (idx >= n_work) break;
+        const u64 r = work_list ? work_list[idx] : idx;
+        zero_region_outputs(b, out, r, true);
+        int rc = s.solve_compare(r, cfg, out);
+        __syncwarp();
+        if (rc == SOLVE_WORKSPACE) {
+            if (!last_tier) {
+                if (lane == 0) fail_list[atomicAdd(fail_count, 1u)] = (u32)r;
+                continue;
+            }
+            rc = AVK_ST_WORKSPACE;
+        }
+        if (rc != AVK_ST_OK) zero_region_outputs(b, out, r, false);
+        if (lane == 0) out.status[r] = rc;
+    }
+    flush_work(w, work_out);
+}
+
+__global__ void __launch_bounds__(256) k_merge(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, const u32 *work_list, u32 n_work,
+                                               u32 *counter, u8 *arena_base, long long arena_bytes, u32 *fail_list,
+                                               u32 *fail_count, int last_tier, unsigned long long *work_out) {
+    const int lane = lane_id();
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    WorkAcc w; w.clear();
+    RegionSolver s(b, w);
+    s.arena = arena_base + warp * (u64)arena_bytes;
+    s.arena_bytes = arena_bytes;
+    const u32 K = b.n_inputs;
+    for (;;) {
+        u32 idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1u);
+        idx = __shfl_sync(AVK_FULL, idx, 0);
+        if (idx >= n_work) break;
+        const u64 r = work_list ? work_list[idx] : idx;
+        int rc = s.solve_merge(r, cfg, out);
+        __syncwarp();
+        if (rc == SOLVE_WORKSPACE) {
+            if (!last_tier) {
+                if (lane == 0) fail_list[atomicAdd(fail_count, 1u)] = (u32)r;
+                continue;
+            }
+            rc = AVK_ST_WORKSPACE;
+        }
+        if (lane == 0) {
+            out.status[r] = rc;
+            if (rc != AVK_ST_OK) {
+                out.cls[r] = AVK_MERGE_DIFFERENT; out.n_idx[r] = 0;
+                for (u32 k = 0; k < K; ++k) out.idx[r * K + k] = 0xFF;
+            }
+        }
+    }
+    flush_work(w, work_out);
+}
+
+// SummaryWriter::add_comparison_benchmark (writers/summary.rs:146-158): thread j sums column j of the
+// [n][286] metric rows (coalesced across the block), one atomicAdd per column per block.
+#define RED_COLS (AVK_N_GROUPS * AVK_N_METRICS)
+__global__ void __launch_bounds__(288) k_reduce(u64 n, const int *status, const u64 *region_metrics, const uint16_t *type_mask,
+                                                unsigned long long *totals, u32 *totals_mask, unsigned long long *solved,
+                                                unsigned long long *errors, const u64 *strat_off, const u32 *strat_idx,
+                                                unsigned long long *strat_totals) {
+    const int j = threadIdx.x;
+    unsigned long long acc = 0, ok = 0, bad = 0;
+    u32 mask = 0;
+    for (u64 r = blockIdx.x; r < n; r += gridDim.x) {
+        const bool good = status[r] == AVK_ST_OK;
+        if (j == 0) { if (good) { ok += 1; mask |= type_mask[r]; } else bad += 1; }
+        if (!good || j >= RED_COLS) continue;
+        const unsigned long long v = region_metrics[r * RED_COLS + j];
+        acc += v;
+        if (strat_off && v) {
+            for (u64 s = strat_off[r]; s < strat_off[r + 1]; ++s) atomicAdd(strat_totals + (u64)strat_idx[s] * RED_COLS + j, v);
+        }
+    }
+    if (j < RED_COLS && acc) atomicAdd(totals + j, acc);
+    if (j == 0) { atomicAdd(solved, ok); atomicAdd(errors, bad); atomicOr(totals_mask, mask); }
+}
+
+// ------------------------------------------------------------------------------------ context
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Tier {
+    long long arena_bytes;
+    int warps;
+};
+
+struct avk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    // reference
+    std::vector<DevBuf> contig_bufs;
+    std::vector<u64> contig_lens;
+    DevBuf d_contig_ptr, d_contig_len;
+    // batch buffers
+    DevBuf region_id, contig, start, end, var_off, pos, vtype, zyg, raw, aoff, l0, l1, pool, alt_ed;
+    // outputs
+    DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, strat_off, strat_idx, strat_totals,
+        seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx;
+    // workspace
+    DevBuf scratch, arena, counters, fail_a, fail_b, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    // resident batch
+    bool have_batch = false;
+    u64 n_regions = 0, n_variants = 0;
+    u32 n_inputs = 0;
+    u32 max_allele = 1;
+    bool resident_has_seq = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[5] = {0, 0, 0, 0, 0};
+    avk_work_counters last_work = {0, 0, 0, 0, 0};
+    std::vector<Tier> tiers;
+};
+
+static int ensure(avk_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return AVK_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return AVK_ERR_OOM;
+    }
+    b.cap = want;
+    return AVK_OK;
+}
+#define ENSURE(buf, bytes)                        \
+    do {                                          \
+        int rc_ = ensure(ctx, buf, (bytes));      \
+        if (rc_ != AVK_OK) return rc_;            \
+    } while (0)
+
+static int upload(avk_ctx *ctx, DevBuf &b, const void *src, size_t bytes) {
+    int rc = ensure(ctx, b, bytes);
+    if (rc != AVK_OK) return rc;
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return AVK_OK;
+}
+#define UPLOAD(buf, src, bytes)                          \
+    do {                                                 \
+        int rc_ = upload(ctx, buf, (src), (bytes));      \
+        if (rc_ != AVK_OK) return rc_;                   \
+    } while (0)
+
+extern "C" int avk_create(int device, avk_ctx **out) {
+    if (!out) return AVK_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return AVK_ERR_CUDA;
+    avk_ctx *ctx = new avk_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return AVK_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    const int sm = ctx->sm_count;
+    // workspace tiers: (bytes per warp, warps).  Clusters that overflow a tier are re-run in the next.
+    ctx->tiers = {{48LL << 10, sm * 32}, {2LL << 20, sm * 8}, {64LL << 20, sm}, {2048LL << 20, 8}};
+    *out = ctx;
+    return AVK_OK;
+}
+
+extern "C" void avk_destroy(avk_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_contig_ptr, &ctx->d_contig_len, &ctx->region_id, &ctx->contig, &ctx->start, &ctx->end, &ctx->var_off,
+                      &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
+                      &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
+                      &ctx->totals, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->scratch, &ctx->arena, &ctx->counters, &ctx->fail_a, &ctx->fail_b,
+                      &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *avk_last_error(const avk_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" uint64_t avk_launch_count(const avk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int avk_set_reference(avk_ctx *ctx, uint32_t n_contigs, const uint8_t *const *seqs, const uint64_t *lens) {
+    if (!ctx || (n_contigs && (!seqs || !lens))) return AVK_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
+    ctx->contig_bufs.assign(n_contigs, DevBuf());
+    ctx->contig_lens.assign(lens, lens + n_contigs);
+    std::vector<const u8 *> ptrs(n_contigs);
+    for (uint32_t c = 0; c < n_contigs; ++c) {
+        // 64 bytes of slack so that vectorised tail reads stay inside the allocation
+        ENSURE(ctx->contig_bufs[c], lens[c] + 64);
+        if (lens[c]) CK(cudaMemcpyAsync(ctx->contig_bufs[c].p, seqs[c], lens[c], cudaMemcpyHostToDevice, ctx->stream));
+        ptrs[c] = (const u8 *)ctx->contig_bufs[c].p;
+    }
+    UPLOAD(ctx->d_contig_ptr, ptrs.data(), sizeof(u8 *) * n_contigs);
+    UPLOAD(ctx->d_contig_len, lens, sizeof(u64) * n_contigs);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AVK_OK;
+}
+
+static int validate_batch(avk_ctx *ctx, const avk_region_batch *b, bool compare) {
+    if (!b) { ctx->err = "null batch"; return AVK_ERR_INVALID; }
+    if (compare ? b->n_inputs != 2 : (b->n_inputs < 1 || b->n_inputs > 32)) { ctx->err = "unsupported n_inputs"; return AVK_ERR_INVALID; }
+    if (b->n_regions >= (1ull << 32) - 1 || b->variants.n_variants >= (1ull << 32) || b->variants.allele_pool_len >= (1ull << 32)) {
+        ctx->err = "batch too large for 32-bit indices; split it";
+        return AVK_ERR_INVALID;
+    }
+    if (b->n_regions && (!b->region_id || !b->contig || !b->start || !b->end || !b->var_off)) { ctx->err = "null region arrays"; return AVK_ERR_INVALID; }
+    if (b->n_regions && b->var_off[b->n_regions * b->n_inputs] != b->variants.n_variants) { ctx->err = "var_off does not cover the variant table"; return AVK_ERR_INVALID; }
+    return AVK_OK;
+}
+
+static int upload_batch(avk_ctx *ctx, const avk_region_batch *b) {
+    if (ctx->contig_bufs.empty()) { ctx->err = "avk_set_reference has not been called"; return AVK_ERR_NO_REFERENCE; }
+    const u64 n = b->n_regions, nv = b->variants.n_variants;
+    const avk_variant_table &t = b->variants;
+    UPLOAD(ctx->region_id, b->region_id, 8 * n);
+    UPLOAD(ctx->contig, b->contig, 4 * n);
+    UPLOAD(ctx->start, b->start, 4 * n);
+    UPLOAD(ctx->end, b->end, 4 * n);
+    UPLOAD(ctx->var_off, b->var_off, 8 * (n * b->n_inputs + 1));
+    UPLOAD(ctx->pos, t.position, 4 * nv);
+    UPLOAD(ctx->vtype, t.variant_type, nv);
+    UPLOAD(ctx->zyg, t.zygosity, nv);
+    UPLOAD(ctx->raw, t.raw_allele_space, 4 * nv);
+    UPLOAD(ctx->aoff, t.allele_off, 4 * nv);
+    UPLOAD(ctx->l0, t.a0_len, 4 * nv);
+    UPLOAD(ctx->l1, t.a1_len, 4 * nv);
+    UPLOAD(ctx->pool, t.allele_pool, t.allele_pool_len);
+    ENSURE(ctx->alt_ed, 4 * nv);
+    u32 mx = 1;
+    for (u64 i = 0; i < nv; ++i) mx = std::max(mx, std::max(t.a0_len[i], t.a1_len[i]));
+    ctx->max_allele = mx;
+    ctx->n_regions = n; ctx->n_variants = nv; ctx->n_inputs = b->n_inputs;
+    ctx->have_batch = true;
+    return AVK_OK;
+}
+
+static DevBatch dev_batch(avk_ctx *ctx) {
+    DevBatch d;
+    d.n_regions = ctx->n_regions; d.n_inputs = ctx->n_inputs;
+    d.region_id = (const u64 *)ctx->region_id.p; d.contig = (const u32 *)ctx->contig.p;
+    d.start = (const u32 *)ctx->start.p; d.end = (const u32 *)ctx->end.p; d.var_off = (const u64 *)ctx->var_off.p;
+    d.pos = (const u32 *)ctx->pos.p; d.vtype = (const u8 *)ctx->vtype.p; d.zyg = (const u8 *)ctx->zyg.p;
+    d.raw = (const u32 *)ctx->raw.p; d.aoff = (const u32 *)ctx->aoff.p; d.l0 = (const u32 *)ctx->l0.p; d.l1 = (const u32 *)ctx->l1.p;
+    d.pool = (const u8 *)ctx->pool.p;
+    d.contig_ptr = (const u8 *const *)ctx->d_contig_ptr.p; d.contig_len = (const u64 *)ctx->d_contig_len.p;
+    d.n_contigs = (u32)ctx->contig_lens.size();
+    d.alt_ed = (const u32 *)ctx->alt_ed.p;
+    return d;
+}
+
+// counters layout (u32): [0] work counter, [1] fail count A, [2] fail count B
+static int run_alt_ed(avk_ctx *ctx, const DevBatch &db) {
+    if (ctx->n_variants == 0) return AVK_OK;
+    const int blocks = ctx->sm_count * 4, threads = 256;
+    const int warps = blocks * threads / 32;
+    const int scratch_ints = 2 * (int)ctx->max_allele + 8;
+    ENSURE(ctx->scratch, (size_t)warps * scratch_ints * 4);
+    k_alt_ed<<<blocks, threads, 0, ctx->stream>>>(db, ctx->n_variants, (u32 *)ctx->alt_ed.p, (int *)ctx->scratch.p, scratch_ints,
+                                                   (unsigned long long *)ctx->work_ctr.p);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return AVK_OK;
+}
+
+// Runs a tiered per-cluster kernel; `launch` is called with (work_list, n_work, arena, arena_bytes, fail_list, last, grid).
+template <class F>
+static int run_tiers(avk_ctx *ctx, u64 n, F launch) {
+    if (n == 0) return AVK_OK;
+    ENSURE(ctx->fail_a, 4 * n);
+    ENSURE(ctx->fail_b, 4 * n);
+    u32 *counters = (u32 *)ctx->counters.p;
+    const u32 *work_list = nullptr;
+    u32 n_work = (u32)n;
+    u32 *fail_lists[2] = {(u32 *)ctx->fail_a.p, (u32 *)ctx->fail_b.p};
+    for (size_t t = 0; t < ctx->tiers.size() && n_work > 0; ++t) {
+        const bool last = t + 1 == ctx->tiers.size();
+        Tier tier = ctx->tiers[t];
+        int warps = (int)std::min<u64>((u64)tier.warps, ((u64)n_work + 0) < 8 ? 8 : (u64)n_work);
+        warps = (warps + 7) / 8 * 8;
+        ENSURE(ctx->arena, (size_t)warps * (size_t)tier.arena_bytes);
+        CK(cudaMemsetAsync(counters, 0, 16, ctx->stream));
+        u32 *fail_list = fail_lists[t & 1];
+        launch(work_list, n_work, (u8 *)ctx->arena.p, tier.arena_bytes, fail_list, counters + 1, last ? 1 : 0, warps / 8);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        if (last) break;
+        u32 host_counters[4];
+        CK(cudaMemcpyAsync(host_counters, counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_work = host_counters[1];
+        work_list = fail_list;
+    }
+    return AVK_OK;
+}
+
+static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, const u64 *strat_off_dev,
+                              const u32 *strat_idx_dev, u32 n_strata) {
+    const u64 n = ctx->n_regions, nv = ctx->n_variants;
+    ENSURE(ctx->status, 4 * n); ENSURE(ctx->ed1, 4 * n); ENSURE(ctx->ed2, 4 * n);
+    ENSURE(ctx->region_metrics, 8ull * RED_COLS * n);
+    ENSURE(ctx->type_mask, 2 * n);
+    ENSURE(ctx->vexp, nv); ENSURE(ctx->vobs, nv); ENSURE(ctx->vcls, nv);
+    ENSURE(ctx->totals, 8 * RED_COLS + 64);
+    ENSURE(ctx->counters, 64);
+    ENSURE(ctx->work_ctr, 64);
+    if (n_strata) ENSURE(ctx->strat_totals, 8ull * RED_COLS * n_strata);
+    CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
+    CK(cudaMemsetAsync(ctx->totals.p, 0, 8 * RED_COLS + 64, ctx->stream));
+    if (n_strata) CK(cudaMemsetAsync(ctx->strat_totals.p, 0, 8ull * RED_COLS * n_strata, ctx->stream));
+    DevBatch db = dev_batch(ctx);
+    DevCompareOut out;
+    out.status = (int *)ctx->status.p; out.ed1 = (u32 *)ctx->ed1.p; out.ed2 = (u32 *)ctx->ed2.p;
+    out.region_metrics = (u64 *)ctx->region_metrics.p; out.type_mask = (uint16_t *)ctx->type_mask.p;
+    out.vexp = (u8 *)ctx->vexp.p; out.vobs = (u8 *)ctx->vobs.p; out.vcls = (u8 *)ctx->vcls.p;
+    out.seq_off = want_seq ? (const u64 *)ctx->seq_off.p : nullptr;
+    out.seq_len = (u32 *)ctx->seq_len.p; out.seq_pool = (u8 *)ctx->seq_pool.p;
+    avk_compare_cfg c = *cfg;
+    unsigned long long *work = (unsigned long long *)ctx->work_ctr.p;
+
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = run_alt_ed(ctx, db);
+    if (rc != AVK_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = run_tiers(ctx, n, [&](const u32 *wl, u32 nw, u8 *arena, long long ab, u32 *fl, u32 *fc, int last, int blocks) {
+        k_compare<<<blocks, 256, 0, ctx->stream>>>(db, out, c, wl, nw, (u32 *)ctx->counters.p, arena, ab, fl, fc, last, work);
+    });
+    if (rc != AVK_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (n) {
+        unsigned long long *tot = (unsigned long long *)ctx->totals.p;
+        k_reduce<<<std::min<u64>(n, (u64)ctx->sm_count * 8), 288, 0, ctx->stream>>>(
+            n, out.status, out.region_metrics, out.type_mask, tot, (u32 *)(tot + RED_COLS), tot + RED_COLS + 1, tot + RED_COLS + 2,
+            strat_off_dev, strat_idx_dev, (unsigned long long *)ctx->strat_totals.p);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    return AVK_OK;
+}
+
+static int fetch_timings(avk_ctx *ctx) {
+    CK(cudaEventSynchronize(ctx->ev[4]));
+    cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->last_ms[2], ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->last_ms[3], ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->last_ms[4], ctx->ev[0], ctx->ev[4]);
+    unsigned long long w[8];
+    CK(cudaMemcpyAsync(w, ctx->work_ctr.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_work.alignments = w[0]; ctx->last_work.cells = w[1]; ctx->last_work.matched_bases = w[2];
+    ctx->last_work.search_pops = w[3]; ctx->last_work.exact_pops = w[4];
+    return AVK_OK;
+}
+
+#define DL(dst, buf, bytes)                                                                                     \
+    do {                                                                                                        \
+        if ((dst) && (bytes)) CK(cudaMemcpyAsync((dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream)); \
+    } while (0)
+
+static int download_compare(avk_ctx *ctx, avk_compare_out *out, bool want_seq, u64 seq_pool_len) {
+    const u64 n = ctx->n_regions, nv = ctx->n_variants;
+    DL(out->status, ctx->status, 4 * n);
+    DL(out->ed1, ctx->ed1, 4 * n);
+    DL(out->ed2, ctx->ed2, 4 * n);
+    DL(out->region_metrics, ctx->region_metrics, 8ull * RED_COLS * n);
+    DL(out->type_mask, ctx->type_mask, 2 * n);
+    DL(out->var_expected, ctx->vexp, nv);
+    DL(out->var_observed, ctx->vobs, nv);
+    DL(out->var_class, ctx->vcls, nv);
+    unsigned long long tot[RED_COLS + 8];
+    CK(cudaMemcpyAsync(tot, ctx->totals.p, 8 * RED_COLS + 64, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->strat_totals && out->n_strata) DL(out->strat_totals, ctx->strat_totals, 8ull * RED_COLS * out->n_strata);
+    if (want_seq) {
+        DL(out->seq_len, ctx->seq_len, 4 * 5 * n);
+        DL(out->seq_pool, ctx->seq_pool, seq_pool_len);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out->totals) memcpy(out->totals, tot, 8 * RED_COLS);
+    if (out->totals_mask) *out->totals_mask = (uint16_t)(tot[RED_COLS] & 0xffff);
+    if (out->solved_blocks) *out->solved_blocks = tot[RED_COLS + 1];
+    if (out->error_blocks) *out->error_blocks = tot[RED_COLS + 2];
+    return AVK_OK;
+}
+
+static int prepare_outputs_on_device(avk_ctx *ctx, const avk_compare_out *out, bool &want_seq, u64 &seq_pool_len) {
+    const u64 n = ctx->n_regions;
+    want_seq = out->seq_off && out->seq_len && out->seq_pool;
+    seq_pool_len = 0;
+    if (want_seq) {
+        seq_pool_len = out->seq_off[n * 5];
+        UPLOAD(ctx->seq_off, out->seq_off, 8 * (n * 5 + 1));
+        ENSURE(ctx->seq_len, 4 * 5 * n);
+        ENSURE(ctx->seq_pool, seq_pool_len);
+        CK(cudaMemsetAsync(ctx->seq_len.p, 0, 4 * 5 * n + 4, ctx->stream));
+    }
+    if (out->strat_off && out->strat_totals && out->n_strata) {
+        UPLOAD(ctx->strat_off, out->strat_off, 8 * (n + 1));
+        UPLOAD(ctx->strat_idx, out->strat_idx, 4 * out->strat_off[n]);
+    }
+    return AVK_OK;
+}
+
+extern "C" int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = validate_batch(ctx, batch, true);
+    if (rc != AVK_OK) return rc;
+    rc = upload_batch(ctx, batch);
+    if (rc != AVK_OK) return rc;
+    bool want_seq; u64 seq_pool_len;
+    rc = prepare_outputs_on_device(ctx, out, want_seq, seq_pool_len);
+    if (rc != AVK_OK) return rc;
+    const bool strat = out->strat_off && out->strat_totals && out->n_strata;
+    rc = run_compare_device(ctx, cfg, want_seq, strat ? (const u64 *)ctx->strat_off.p : nullptr,
+                            strat ? (const u32 *)ctx->strat_idx.p : nullptr, strat ? out->n_strata : 0);
+    if (rc != AVK_OK) return rc;
+    rc = download_compare(ctx, out, want_seq, seq_pool_len);
+    if (rc != AVK_OK) return rc;
+    return fetch_timings(ctx);
+}
+
+extern "C" int avk_compare_upload(avk_ctx *ctx, const avk_region_batch *batch) {
+    if (!ctx) return AVK_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = validate_batch(ctx, batch, true);
+    if (rc != AVK_OK) return rc;
+    rc = upload_batch(ctx, batch);
+    if (rc != AVK_OK) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AVK_OK;
+}
+
+extern "C" int avk_compare_run_resident(avk_ctx *ctx, const avk_compare_cfg *cfg) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!cfg || !ctx->have_batch || ctx->n_inputs != 2) { ctx->err = "no resident compare batch"; return AVK_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = run_compare_device(ctx, cfg, false, nullptr, nullptr, 0);
+    if (rc != AVK_OK) return rc;
+    return fetch_timings(ctx);
+}
+
+extern "C" int avk_compare_download(avk_ctx *ctx, avk_compare_out *out) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!out || !ctx->have_batch) { ctx->err = "no resident batch"; return AVK_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    return download_compare(ctx, out, false, 0);
+}
+
+extern "C" int avk_last_timings(avk_ctx *ctx, float *ms5) {
+    if (!ctx || !ms5) return AVK_ERR_INVALID;
+    memcpy(ms5, ctx->last_ms, sizeof(ctx->last_ms));
+    return AVK_OK;
+}
+extern "C" int avk_last_work(avk_ctx *ctx, avk_work_counters *out) {
+    if (!ctx || !out) return AVK_ERR_INVALID;
+    *out = ctx->last_work;
+    return AVK_OK;
+}
+
+extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, const avk_merge_cfg *cfg, avk_merge_out *out) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = validate_batch(ctx, batch, false);
+    if (rc != AVK_OK) return rc;
+    rc = upload_batch(ctx, batch);
+    if (rc != AVK_OK) return rc;
+    const u64 n = ctx->n_regions;
+    const u32 K = ctx->n_inputs;
+    ENSURE(ctx->status, 4 * n); ENSURE(ctx->m_cls, n); ENSURE(ctx->m_nidx, n); ENSURE(ctx->m_idx, n * K);
+    ENSURE(ctx->counters, 64); ENSURE(ctx->work_ctr, 64);
+    CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
+    DevBatch db = dev_batch(ctx);
+    DevMergeOut mo;
+    mo.status = (int *)ctx->status.p; mo.cls = (u8 *)ctx->m_cls.p; mo.n_idx = (u8 *)ctx->m_nidx.p; mo.idx = (u8 *)ctx->m_idx.p;
+    avk_merge_cfg c = *cfg;
+    unsigned long long *work = (unsigned long long *)ctx->work_ctr.p;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = run_alt_ed(ctx, db);
+    if (rc != AVK_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = run_tiers(ctx, n, [&](const u32 *wl, u32 nw, u8 *arena, long long ab, u32 *fl, u32 *fc, int last, int blocks) {
+        k_merge<<<blocks, 256, 0, ctx->stream>>>(db, mo, c, wl, nw, (u32 *)ctx->counters.p, arena, ab, fl, fc, last, work);
+    });
+    if (rc != AVK_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    DL(out->status, ctx->status, 4 * n);
+    DL(out->classification, ctx->m_cls, n);
+    DL(out->n_indices, ctx->m_nidx, n);
+    DL(out->indices, ctx->m_idx, n * K);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return fetch_timings(ctx);
+}
+
+extern "C" int avk_wfa_ed_batch(avk_ctx *ctx, uint64_t n_pairs, const uint8_t *pool, uint64_t pool_len, const uint64_t *a_off,
+                                const uint32_t *a_len, const uint64_t *b_off, const uint32_t *b_len, uint32_t *ed_out) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (n_pairs && (!pool || !a_off || !a_len || !b_off || !b_len || !ed_out)) { ctx->err = "null argument"; return AVK_ERR_INVALID; }
+    if (n_pairs >= (1ull << 32) - 1) { ctx->err = "too many pairs"; return AVK_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    if (n_pairs == 0) return AVK_OK;
+    u32 mx = 1;
+    for (u64 i = 0; i < n_pairs; ++i) {
+        if (a_off[i] + a_len[i] > pool_len || b_off[i] + b_len[i] > pool_len) { ctx->err = "pair outside pool"; return AVK_ERR_INVALID; }
+        mx = std::max(mx, std::max(a_len[i], b_len[i]));
+    }
+    UPLOAD(ctx->pair_pool, pool, pool_len);
+    UPLOAD(ctx->pair_a_off, a_off, 8 * n_pairs);
+    UPLOAD(ctx->pair_b_off, b_off, 8 * n_pairs);
+    UPLOAD(ctx->pair_a_len, a_len, 4 * n_pairs);
+    UPLOAD(ctx->pair_b_len, b_len, 4 * n_pairs);
+    ENSURE(ctx->pair_ed, 4 * n_pairs);
+    ENSURE(ctx->counters, 64); ENSURE(ctx->work_ctr, 64);
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+    CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
+    const int scratch_ints = 2 * (int)mx + 8;
+    int warps = (int)std::min<u64>((u64)ctx->sm_count * 32, (n_pairs + 7) / 8 * 8);
+    warps = (warps + 7) / 8 * 8;
+    ENSURE(ctx->scratch, (size_t)warps * scratch_ints * 4);
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    k_wfa_ed<<<warps / 8, 256, 0, ctx->stream>>>(n_pairs, (const u8 *)ctx->pair_pool.p, (const u64 *)ctx->pair_a_off.p,
+                                                  (const u32 *)ctx->pair_a_len.p, (const u64 *)ctx->pair_b_off.p,
+                                                  (const u32 *)ctx->pair_b_len.p, (u32 *)ctx->pair_ed.p, (int *)ctx->scratch.p,
+                                                  scratch_ints, (u32 *)ctx->counters.p, (unsigned long long *)ctx->work_ctr.p);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(cudaMemcpyAsync(ed_out, ctx->pair_ed.p, 4 * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return fetch_timings(ctx);
+}
+
+// Host-only: upper-bound layout of the sequence bundle (ref = window; haplotype <= window + sum of ALT lengths of its side).
+extern "C" int avk_compare_seq_offsets(const avk_region_batch *b, uint64_t *seq_off, uint64_t *pool_len) {
+    if (!b || !seq_off || b->n_inputs != 2) return AVK_ERR_INVALID;
+    u64 off = 0;
+    for (u64 r = 0; r < b->n_regions; ++r) {
+        const u64 win = b->end[r] > b->start[r] ? b->end[r] - b->start[r] : 0;
+        u64 alt[2] = {0, 0};
+        for (int k = 0; k < 2; ++k)
+            for (u64 v = b->var_off[r * 2 + k]; v < b->var_off[r * 2 + k + 1]; ++v) alt[k] += b->variants.a1_len[v];
+        const u64 sizes[5] = {win, win + alt[0], win + alt[0], win + alt[1], win + alt[1]};
+        for (int s = 0; s < 5; ++s) { seq_off[r * 5 + s] = off; off += sizes[s]; }
+    }
+    seq_off[b->n_regions * 5] = off;
+    if (pool_len) *pool_len = off;
+    return AVK_OK;
+}

@@ -1,0 +1,225 @@
+"""ctypes binding of libaardvark_b200.so (the CUDA product) + the host-side operator mirror.
+
+`Solver` is the drop-in for the two call sites the reference parallelises with rayon:
+
+    solve_compare_region(&CompareRegion, &ReferenceGenome, CompareConfig, ..)  src/waffle_solver.rs:122-124
+    solve_merge_region(&MultiRegion, &ReferenceGenome, MergeConfig)            src/merge_solver.rs:110
+
+Because the reference materialises all regions first (src/main.rs:217-232), the natural
+unit here is the batch: `Solver.compare_batch(RegionBatch)`; the single-region calls
+exist for parity with the reference's tests.  There is NO CPU fallback: if the shared
+library is missing or no CUDA device is present, construction raises.
+"""
+import ctypes as C
+import os
+import subprocess
+from typing import List, Sequence
+
+import numpy as np
+
+from . import abi
+from .batch import CompareOutputs, MergeOutputs, RegionBatch, seq_offsets
+from .results import unpack_compare, unpack_merge
+from .types import CompareConfig, CompareRegion, MergeConfig, MultiRegion, RegionError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libaardvark_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--shared", "-Xcompiler", "-fPIC"]
+
+_LIB = None
+
+
+class AvkError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("avk_lib.cu", "avk_solver.cuh", "avk_device.cuh")]
+    srcs.append(os.path.join(_HERE, "..", "include", "aardvark_b200.h"))
+    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= max(os.path.getmtime(s) for s in srcs):
+        return SO_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, srcs[0]]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"], env=env)
+    return SO_PATH
+
+
+def load():
+    """Load the product library; raises loudly when it is not built (no fallback path exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO_PATH):
+        raise AvkError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                       "aardvark_b200 has no CPU fallback")
+    lib = C.CDLL(SO_PATH)
+    vp = C.c_void_p
+    lib.avk_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.avk_destroy.argtypes = [vp]
+    lib.avk_last_error.restype = C.c_char_p
+    lib.avk_last_error.argtypes = [vp]
+    lib.avk_launch_count.restype = C.c_uint64
+    lib.avk_launch_count.argtypes = [vp]
+    lib.avk_set_reference.argtypes = [vp, C.c_uint32, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint64)]
+    lib.avk_compare_batch.argtypes = [vp, C.POINTER(abi.RegionBatch), C.POINTER(abi.CompareCfg), C.POINTER(abi.CompareOut)]
+    lib.avk_merge_batch.argtypes = [vp, C.POINTER(abi.RegionBatch), C.POINTER(abi.MergeCfg), C.POINTER(abi.MergeOut)]
+    lib.avk_wfa_ed_batch.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                     C.POINTER(C.c_uint32)]
+    lib.avk_compare_seq_offsets.argtypes = [C.POINTER(abi.RegionBatch), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.avk_compare_upload.argtypes = [vp, C.POINTER(abi.RegionBatch)]
+    lib.avk_compare_run_resident.argtypes = [vp, C.POINTER(abi.CompareCfg)]
+    lib.avk_compare_download.argtypes = [vp, C.POINTER(abi.CompareOut)]
+    lib.avk_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.avk_last_work.argtypes = [vp, C.POINTER(abi.WorkCounters)]
+    _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "avk_create", "avk_destroy", "avk_last_error", "avk_set_reference", "avk_compare_batch", "avk_merge_batch",
+    "avk_wfa_ed_batch", "avk_compare_seq_offsets", "avk_compare_upload", "avk_compare_run_resident",
+    "avk_compare_download", "avk_last_timings", "avk_last_work", "avk_launch_count",
+]
+
+
+def compare_cfg(cfg: CompareConfig) -> abi.CompareCfg:
+    return abi.CompareCfg(cfg.max_branch_factor, int(cfg.enable_exact_shortcut), int(cfg.enable_sequences), 0)
+
+
+def merge_cfg(cfg: MergeConfig) -> abi.MergeCfg:
+    return abi.MergeCfg(cfg.max_branch_factor, int(cfg.no_conflict_enabled), int(cfg.majority_voting_enabled),
+                        -1 if cfg.conflict_selection is None else int(cfg.conflict_selection))
+
+
+class Solver:
+    """One context per process / GPU.  The reference genome stays resident in HBM
+    (ReferenceGenome::from_fasta once per run, src/main.rs:94)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.avk_create(device, C.byref(self._ctx))
+        if rc != 0:
+            self._ctx = None
+            raise AvkError(f"avk_create(device={device}) failed with {rc}: no usable CUDA device "
+                           "(aardvark_b200 has no CPU fallback)")
+        self.contig_index = {}
+        self._contigs = []
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.avk_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise AvkError(f"{what} failed ({rc}): {self._lib.avk_last_error(self._ctx).decode()}")
+
+    # -- reference ---------------------------------------------------------------------
+    def set_reference(self, contigs, names: Sequence[str] = None):
+        """contigs: list of bytes / uint8 arrays (raw bases, compared as raw bytes)."""
+        arrs = [np.frombuffer(c, dtype=np.uint8) if isinstance(c, (bytes, bytearray)) else np.ascontiguousarray(c, dtype=np.uint8)
+                for c in contigs]
+        self._contigs = arrs
+        ptrs = (C.POINTER(C.c_uint8) * len(arrs))(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in arrs])
+        lens = (C.c_uint64 * len(arrs))(*[a.size for a in arrs])
+        self._check(self._lib.avk_set_reference(self._ctx, len(arrs), ptrs, lens), "avk_set_reference")
+        names = list(names) if names is not None else [str(i) for i in range(len(arrs))]
+        self.contig_index = {n: i for i, n in enumerate(names)}
+
+    # -- batched operators --------------------------------------------------------------
+    def compare_batch(self, batch: RegionBatch, cfg: CompareConfig = None, out: CompareOutputs = None, **out_kwargs):
+        cfg = cfg or CompareConfig(enable_sequences=False)
+        if out is None:
+            if cfg.enable_sequences and "seq_off" not in out_kwargs:
+                off, plen = seq_offsets(batch)
+                out_kwargs.update(seq_off=off, seq_pool_len=plen)
+            out = CompareOutputs(batch, **out_kwargs)
+        cb, cc, co = batch.to_c(), compare_cfg(cfg), out.to_c()
+        self._check(self._lib.avk_compare_batch(self._ctx, C.byref(cb), C.byref(cc), C.byref(co)), "avk_compare_batch")
+        return out
+
+    def merge_batch(self, batch: RegionBatch, cfg: MergeConfig = None) -> MergeOutputs:
+        cfg = cfg or MergeConfig()
+        out = MergeOutputs(batch)
+        cb, cc, co = batch.to_c(), merge_cfg(cfg), out.to_c()
+        self._check(self._lib.avk_merge_batch(self._ctx, C.byref(cb), C.byref(cc), C.byref(co)), "avk_merge_batch")
+        return out
+
+    def wfa_ed_batch(self, pairs) -> np.ndarray:
+        """Batched wfa_ed (src/util/sequence_alignment.rs:9-13) over [(a, b)] byte pairs."""
+        pool = bytearray()
+        a_off, a_len, b_off, b_len = [], [], [], []
+        for a, b in pairs:
+            a_off.append(len(pool)); a_len.append(len(a)); pool += a
+            b_off.append(len(pool)); b_len.append(len(b)); pool += b
+        pool_a = np.frombuffer(bytes(pool) if pool else b"\0", dtype=np.uint8)
+        ao, bo = np.array(a_off, dtype=np.uint64), np.array(b_off, dtype=np.uint64)
+        al, bl = np.array(a_len, dtype=np.uint32), np.array(b_len, dtype=np.uint32)
+        ed = np.zeros(max(len(a_off), 1), dtype=np.uint32)
+        self._check(self._lib.avk_wfa_ed_batch(self._ctx, len(a_off), abi.ptr(pool_a), len(pool), abi.ptr(ao), abi.ptr(al),
+                                                abi.ptr(bo), abi.ptr(bl), abi.ptr(ed)), "avk_wfa_ed_batch")
+        return ed[:len(a_off)]
+
+    # -- resident mode (bench: inputs already in HBM) --------------------------------------
+    def upload(self, batch: RegionBatch):
+        cb = batch.to_c()
+        self._check(self._lib.avk_compare_upload(self._ctx, C.byref(cb)), "avk_compare_upload")
+
+    def run_resident(self, cfg: CompareConfig = None):
+        cc = compare_cfg(cfg or CompareConfig(enable_sequences=False))
+        self._check(self._lib.avk_compare_run_resident(self._ctx, C.byref(cc)), "avk_compare_run_resident")
+
+    def download(self, out: CompareOutputs):
+        co = out.to_c()
+        self._check(self._lib.avk_compare_download(self._ctx, C.byref(co)), "avk_compare_download")
+        return out
+
+    def last_timings_ms(self):
+        buf = (C.c_float * 5)()
+        self._lib.avk_last_timings(self._ctx, buf)
+        return dict(zip(("alt_ed", "search", "heavy_ed", "reduce", "total"), (float(x) for x in buf)))
+
+    def last_work(self):
+        wc = abi.WorkCounters()
+        self._lib.avk_last_work(self._ctx, C.byref(wc))
+        return wc.as_dict()
+
+    def launch_count(self) -> int:
+        return int(self._lib.avk_launch_count(self._ctx))
+
+    # -- the reference's per-region operators ------------------------------------------------
+    def solve_compare_regions(self, regions: Sequence[CompareRegion], cfg: CompareConfig = None) -> List:
+        cfg = cfg or CompareConfig()
+        batch = RegionBatch.from_compare_regions(regions, self.contig_index)
+        out = self.compare_batch(batch, cfg)
+        return unpack_compare(batch, out)
+
+    def solve_compare_region(self, region: CompareRegion, cfg: CompareConfig = None):
+        """Ok(CompareBenchmark) or raises RegionError (the reference's per-region Err)."""
+        res = self.solve_compare_regions([region], cfg)[0]
+        if isinstance(res, RegionError):
+            raise res
+        return res
+
+    def solve_merge_regions(self, regions: Sequence[MultiRegion], cfg: MergeConfig = None) -> List:
+        batch = RegionBatch.from_multi_regions(regions, self.contig_index)
+        return unpack_merge(batch, self.merge_batch(batch, cfg))
+
+    def solve_merge_region(self, region: MultiRegion, cfg: MergeConfig = None):
+        res = self.solve_merge_regions([region], cfg)[0]
+        if isinstance(res, RegionError):
+            raise res
+        return res

@@ -969,11 +969,16 @@ static void load_list(const avk_region_batch *b, uint64_t r, uint32_t k, std::ve
     }
 }
 
-static bool list_valid(const std::vector<Var> &v, const std::vector<uint8_t> &z) {
+// Inputs the reference never produces (its region builder guarantees them) are
+// rejected identically by the oracle and the CUDA library: empty alleles, unknown enum codes, a variant
+// outside its window, a list that is not position-sorted.
+static bool list_valid(const std::vector<Var> &v, const std::vector<uint8_t> &z, uint64_t start, uint64_t end) {
     for (size_t i = 0; i < v.size(); ++i) {
         if (v[i].l0 == 0 || v[i].l1 == 0) return false;
         if (v[i].type >= AVK_N_VARIANT_TYPES) return false;
         if (z[i] > AVK_ZYG_HOM_ALT) return false;
+        if (v[i].pos < start || (uint64_t)v[i].pos + v[i].l0 > end) return false;
+        if (i > 0 && v[i - 1].pos > v[i].pos) return false;
     }
     return true;
 }
@@ -1012,7 +1017,7 @@ int orc_compare_batch(const avk_region_batch *b, const uint8_t *const *contigs, 
             Benchmark res;
             int st;
             uint32_t c = b->contig[r];
-            if (c >= n_contigs || !list_valid(tv, tz) || !list_valid(qv, qz)) st = AVK_ST_BAD_INPUT;
+            if (c >= n_contigs || b->end[r] > 0x7fff0000u || !list_valid(tv, tz, b->start[r], b->end[r]) || !list_valid(qv, qz, b->start[r], b->end[r])) st = AVK_ST_BAD_INPUT;
             else st = solve_compare_region(contigs[c], contig_lens[c], b->start[r], b->end[r], tv, tz, qv, qz, *cfg, res);
             out->status[r] = st;
             const uint64_t t0 = b->var_off[r * 2], q0 = b->var_off[r * 2 + 1], q1 = b->var_off[r * 2 + 2];
@@ -1110,8 +1115,8 @@ int orc_merge_batch(const avk_region_batch *b, const uint8_t *const *contigs, co
         std::vector<std::vector<uint8_t>> zygs(K);
 #pragma omp for schedule(dynamic, 64)
         for (int64_t r = 0; r < n; ++r) {
-            bool ok = b->contig[r] < n_contigs;
-            for (uint32_t k = 0; k < K; ++k) { load_list(b, r, k, vars[k], zygs[k]); ok = ok && list_valid(vars[k], zygs[k]); }
+            bool ok = b->contig[r] < n_contigs && b->end[r] <= 0x7fff0000u;
+            for (uint32_t k = 0; k < K; ++k) { load_list(b, r, k, vars[k], zygs[k]); ok = ok && list_valid(vars[k], zygs[k], b->start[r], b->end[r]); }
             uint8_t cls = AVK_MERGE_DIFFERENT;
             std::vector<uint8_t> idx;
             int st = ok ? solve_merge_region(contigs[b->contig[r]], contig_lens[b->contig[r]], b->start[r], b->end[r], vars, zygs, *cfg, cls, idx)

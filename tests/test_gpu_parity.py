@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the reference's own
+golden vectors and (b) the CPU oracle on seeded synthetic batches.  Bit-exact (integer work)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle_py as orc
+from aardvark_b200 import abi, synth
+from aardvark_b200.batch import CompareOutputs, RegionBatch, seq_offsets
+from aardvark_b200.lib import Solver, compare_cfg, merge_cfg
+from aardvark_b200.results import unpack_compare, unpack_merge
+from aardvark_b200.types import CompareConfig, CompareRegion, MergeConfig
+from golden_cases import COMPARE_CASES, ED_CASES, MERGE_CASES, MOCK_CHR1
+from test_oracle_golden import check_compare_case
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def solver():
+    s = Solver(0)
+    yield s
+    s.close()
+
+
+def test_native_library_is_loaded(solver):
+    maps = open("/proc/self/maps").read()
+    assert "libaardvark_b200.so" in maps
+
+
+def test_wfa_ed_golden(solver):  # dynamic_wfa.rs:289-403, sequence_alignment.rs:57-116
+    ed = solver.wfa_ed_batch([(a, b) for a, b, _ in ED_CASES])
+    assert list(ed) == [e for _, _, e in ED_CASES]
+
+
+def test_wfa_ed_big_golden(solver):  # dynamic_wfa.rs:452-468: ED 5278
+    g = json.load(open(os.path.join(HERE, "golden", "dwfa_big_early_termination.json")))
+    c1, s23 = g["c1"].encode(), g["seq_23"].encode()
+    ed = solver.wfa_ed_batch([(s23, c1), (c1, s23), (c1, c1)])
+    assert list(ed) == [5278, 5278, 0]
+
+
+def test_wfa_ed_random_vs_oracle(solver):
+    rng = np.random.default_rng(7)
+    pairs = []
+    for _ in range(400):
+        n = int(rng.integers(0, 300))
+        a = synth.ACGT[rng.integers(0, 4, size=n)].copy()
+        b = a.copy()
+        for _ in range(int(rng.integers(0, 12))):
+            if b.size == 0:
+                break
+            k = int(rng.integers(0, b.size))
+            op = rng.integers(0, 3)
+            if op == 0:
+                b[k] = synth.ACGT[rng.integers(0, 4)]
+            elif op == 1:
+                b = np.delete(b, slice(k, k + int(rng.integers(1, 20))))
+            else:
+                b = np.insert(b, k, synth.ACGT[rng.integers(0, 4, size=int(rng.integers(1, 20)))])
+        pairs.append((a.tobytes(), b.tobytes()))
+    pairs.append((b"", b""))
+    ed = solver.wfa_ed_batch(pairs)
+    assert list(ed) == [orc.wfa_ed(a, b) for a, b in pairs]
+
+
+@pytest.mark.parametrize("name,region,exp", COMPARE_CASES, ids=[c[0] for c in COMPARE_CASES])
+def test_solve_compare_region_golden(solver, name, region, exp):  # waffle_solver.rs:896-1247
+    solver.set_reference([MOCK_CHR1], ["mock_chr1"])
+    bench = solver.solve_compare_region(region, CompareConfig())
+    check_compare_case(bench, exp)
+
+
+def _both_compare(solver, batch, contigs, cfg, **kw):
+    gpu = solver.compare_batch(batch, cfg, **kw)
+    cpu = orc.compare_batch(batch, contigs, compare_cfg(cfg), **kw)
+    return gpu, cpu
+
+
+def test_compare_golden_batch_vs_oracle(solver):
+    """BASELINE config 1: the reference's unit-test clusters as one batch, all outputs incl. sequences."""
+    solver.set_reference([MOCK_CHR1], ["mock_chr1"])
+    regions = [CompareRegion(i, r.coordinates, r.truth_variants, r.truth_zygosity, r.query_variants, r.query_zygosity)
+               for i, (_, r, _) in enumerate(COMPARE_CASES)]
+    batch = RegionBatch.from_compare_regions(regions, solver.contig_index)
+    off, plen = seq_offsets(batch)
+    for shortcut in (False, True):
+        cfg = CompareConfig(enable_sequences=True, enable_exact_shortcut=shortcut)
+        gpu, cpu = _both_compare(solver, batch, [MOCK_CHR1], cfg, seq_off=off, seq_pool_len=plen)
+        assert gpu.diff(cpu) == []
+
+
+@pytest.mark.parametrize("name,region,cfg,expected", MERGE_CASES, ids=[c[0] for c in MERGE_CASES])
+def test_solve_merge_region_golden(solver, name, region, cfg, expected):  # merge_solver.rs:242-348
+    solver.set_reference([MOCK_CHR1], ["mock_chr1"])
+    assert solver.solve_merge_region(region, cfg).merge_classification == expected
+
+
+@pytest.mark.parametrize("seed", [20, 21, 22])
+def test_compare_synthetic_vs_oracle(solver, seed):
+    """chr20-shaped synthetic batch (configs[1] at 1/50 scale): every output array bit-exact."""
+    ref, batch = synth.workload_chr20(scale=0.02, seed=seed)
+    solver.set_reference([ref])
+    strat_off = np.arange(batch.n_regions + 1, dtype=np.uint64)
+    strat_idx = (np.arange(batch.n_regions) % 3).astype(np.uint32)
+    kw = dict(strat_off=strat_off, strat_idx=strat_idx, n_strata=3)
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False), **kw)
+    assert gpu.diff(cpu) == []
+    assert int(gpu.solved_blocks[0]) == batch.n_regions
+    # size-independent property: the reduction is the sum of the per-region rows
+    assert (gpu.totals == gpu.region_metrics.sum(axis=0)).all()
+    assert (gpu.strat_totals.sum(axis=0) == gpu.totals).all()
+
+
+def test_compare_synthetic_sequences_and_branch_factor(solver):
+    ref, batch = synth.workload_chr20(scale=0.005, seed=5)
+    solver.set_reference([ref])
+    off, plen = seq_offsets(batch)
+    for mbf in (50, 2, 1):
+        cfg = CompareConfig(enable_sequences=True, max_branch_factor=mbf)
+        gpu, cpu = _both_compare(solver, batch, [ref], cfg, seq_off=off, seq_pool_len=plen)
+        assert gpu.diff(cpu) == []
+
+
+def test_compare_dense_clusters_vs_oracle(solver):
+    """Dense het clusters (deep searches, workspace-tier escalation, auto-fail logic)."""
+    p = synth.SynthParams(n_variants=3000, dense_frac=0.9, dense_mean=6.0, het_frac=0.95, phased_frac=0.2,
+                          p_repr=0.05, p_gt_err=0.05, p_fn=0.05, p_fp=0.05)
+    ref, batch = synth.workload_compare(60_000, p, seed=11)
+    solver.set_reference([ref])
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False))
+    assert gpu.diff(cpu) == []
+
+
+def test_compare_sv_vs_oracle(solver):
+    """SV / long-indel shaped batch (configs[3] scaled down): wide wavefronts, long windows."""
+    p = synth.SynthParams(n_variants=300, sv_events=60, sv_max=1500, flank=1000)
+    ref, batch = synth.workload_compare(400_000, p, seed=4)
+    solver.set_reference([ref])
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False))
+    assert gpu.diff(cpu) == []
+
+
+def test_compare_edge_cases_vs_oracle(solver):
+    """Empty batch, malformed regions, unsupported zygosity, non-ACGT bytes."""
+    from aardvark_b200.types import Coordinates, PhasedZygosity as Z, Variant
+    ref = b"ACGTNNNNacgtACGTRYKMACGTACGTACGTACGTACGT"
+    solver.set_reference([ref], ["c"])
+    empty = RegionBatch.from_compare_regions([], {"c": 0})
+    out = solver.compare_batch(empty, CompareConfig(enable_sequences=False))
+    assert int(out.solved_blocks[0]) == 0 and int(out.error_blocks[0]) == 0
+    v = lambda p, a, b: Variant(0, abi.VT_SNV, p, a, b)
+    regions = [
+        CompareRegion(0, Coordinates("c", 0, 20), [v(5, b"N", b"n")], [Z.PhasedHet01], [v(5, b"N", b"n")], [Z.UnphasedHeterozygous]),
+        CompareRegion(1, Coordinates("c", 0, 20), [v(9, b"c", b"C")], [Z.HomozygousAlternate], [v(9, b"c", b"G")], [Z.HomozygousAlternate]),
+        CompareRegion(2, Coordinates("c", 0, 20), [v(5, b"N", b"A")], [Z.HomozygousReference], [], []),   # reference panics
+        CompareRegion(3, Coordinates("c", 0, 20), [v(25, b"A", b"C")], [Z.PhasedHet01], [], []),           # outside window
+        CompareRegion(4, Coordinates("c", 10, 400), [v(12, b"A", b"C")], [Z.PhasedHet01], [], []),         # window past contig
+        CompareRegion(5, Coordinates("c", 0, 40), [], [], [v(30, b"A", b"C"), v(30, b"A", b"G"), v(30, b"A", b"T")],
+                      [Z.UnphasedHeterozygous] * 3),
+    ]
+    batch = RegionBatch.from_compare_regions(regions, {"c": 0})
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False))
+    assert gpu.diff(cpu) == []
+    assert list(gpu.status[:5]) == [0, 0, abi.ST_BAD_ZYGOSITY, abi.ST_BAD_INPUT, abi.ST_BAD_INPUT]
+    assert int(gpu.error_blocks[0]) == 3
+
+
+def test_merge_synthetic_vs_oracle(solver):
+    ref, batch = synth.workload_merge(150_000, 400, n_sets=5, seed=38)
+    solver.set_reference([ref])
+    for cfg in (MergeConfig(majority_voting_enabled=True), MergeConfig(no_conflict_enabled=True),
+                MergeConfig(conflict_selection=2), MergeConfig()):
+        gpu = solver.merge_batch(batch, cfg)
+        cpu = orc.merge_batch(batch, [ref], merge_cfg(cfg))
+        assert gpu.diff(cpu) == []
+
+
+def test_resident_mode_matches_batch_mode(solver):
+    ref, batch = synth.workload_chr20(scale=0.004, seed=3)
+    solver.set_reference([ref])
+    a = solver.compare_batch(batch, CompareConfig(enable_sequences=False))
+    solver.upload(batch)
+    solver.run_resident(CompareConfig(enable_sequences=False))
+    solver.run_resident(CompareConfig(enable_sequences=False))   # idempotent
+    b = solver.download(CompareOutputs(batch))
+    assert a.diff(b) == []
+    assert solver.launch_count() > 0
+    w = solver.last_work()
+    assert w["search_pops"] > 0 and w["alignments"] > 0
