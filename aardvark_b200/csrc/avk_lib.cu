@@ -207,6 +207,19 @@ __global__ void __launch_bounds__(288) k_reduce(u64 n, const int *status, const 
     if (j == 0) { atomicAdd(solved, ok); atomicAdd(errors, bad); atomicOr(totals_mask, mask); }
 }
 
+// INT32 ALU peak probe for the integer roofline: 8 independent chains of
+// add / xor / max per thread, the instruction mix of the wavefront recurrence (IADD3, LOP3, IMNMX).
+__global__ void __launch_bounds__(256) k_int_peak(int iters, int *sink) {
+    int a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const int k = blockIdx.x | 1;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = max(a0 + k, a1) ^ i; a1 = max(a1 + k, a2) ^ i; a2 = max(a2 + k, a3) ^ i; a3 = max(a3 + k, a4) ^ i;
+        a4 = max(a4 + k, a5) ^ i; a5 = max(a5 + k, a6) ^ i; a6 = max(a6 + k, a7) ^ i; a7 = max(a7 + k, a0) ^ i;
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x7fffffff) sink[0] = a0;
+}
+
 // ------------------------------------------------------------------------------------ context
 
 struct DevBuf {
@@ -591,6 +604,28 @@ extern "C" int avk_compare_download(avk_ctx *ctx, avk_compare_out *out) {
     if (!out || !ctx->have_batch) { ctx->err = "no resident batch"; return AVK_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     return download_compare(ctx, out, false, 0);
+}
+
+// Measured INT32 throughput in integer ops per second (3 ops per chain step: add, max, xor).
+extern "C" int avk_int_peak(avk_ctx *ctx, double *ops_per_s) {
+    if (!ctx || !ops_per_s) return AVK_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ENSURE(ctx->counters, 64);
+    const int iters = 1 << 15, blocks = ctx->sm_count * 16, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_int_peak<<<blocks, threads, 0, ctx->stream>>>(iters, (int *)ctx->counters.p);
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    *ops_per_s = (double)blocks * threads * (double)iters * 8.0 * 3.0 / (best * 1e-3);
+    return AVK_OK;
 }
 
 extern "C" int avk_last_timings(avk_ctx *ctx, float *ms5) {

@@ -77,6 +77,7 @@ def load():
     lib.avk_compare_download.argtypes = [vp, C.POINTER(abi.CompareOut)]
     lib.avk_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     lib.avk_last_work.argtypes = [vp, C.POINTER(abi.WorkCounters)]
+    lib.avk_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     _LIB = lib
     return lib
 
@@ -84,7 +85,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "avk_create", "avk_destroy", "avk_last_error", "avk_set_reference", "avk_compare_batch", "avk_merge_batch",
     "avk_wfa_ed_batch", "avk_compare_seq_offsets", "avk_compare_upload", "avk_compare_run_resident",
-    "avk_compare_download", "avk_last_timings", "avk_last_work", "avk_launch_count",
+    "avk_compare_download", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak",
 ]
 
 
@@ -196,6 +197,11 @@ class Solver:
         wc = abi.WorkCounters()
         self._lib.avk_last_work(self._ctx, C.byref(wc))
         return wc.as_dict()
+
+    def int_peak_ops_per_s(self) -> float:
+        v = C.c_double(0)
+        self._check(self._lib.avk_int_peak(self._ctx, C.byref(v)), "avk_int_peak")
+        return float(v.value)
 
     def launch_count(self) -> int:
         return int(self._lib.avk_launch_count(self._ctx))

@@ -272,6 +272,9 @@ int avk_compare_download(avk_ctx *ctx, avk_compare_out *out);
  * [3] finalize/reduce, [4] total. */
 int avk_last_timings(avk_ctx *ctx, float *ms5);
 int avk_last_work(avk_ctx *ctx, avk_work_counters *out);
+/* INT32 ALU throughput probe (add/max/xor chains), integer ops per second: the measured
+ * denominator of the integer roofline, obtained the way MEASURED_PEAKS.json obtains HBM GB/s. */
+int avk_int_peak(avk_ctx *ctx, double *ops_per_s);
 /* Number of kernel launches issued by the library since avk_create. */
 uint64_t avk_launch_count(const avk_ctx *ctx);
 
