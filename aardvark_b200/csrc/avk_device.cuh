@@ -2,14 +2,18 @@
 //
 // One warp owns one cluster (or one alignment).  All 32 lanes execute these
 // functions together with warp-uniform scalar arguments; lanes split either
-//   * the BASES of one diagonal (32 bytes per step, __ballot_sync + __ffs), or
+//   * the BASES of one diagonal (4 bytes per lane, 128 bytes per warp step:
+//     unaligned 32-bit loads built with funnel shifts, XOR, __ffs, __ballot_sync), or
 //   * the DIAGONALS of one wavefront (one diagonal per lane),
 // whichever the wavefront width calls for.  Nothing here uses tensor cores:
-// this is integer DP, bounded by the INT32 ALU pipe.
+// this is integer DP, bounded by the INT32 ALU pipe and latency.
+//
+// Sequences are raw bytes (the reference compares raw bytes, dynamic_wfa.rs:118, so
+// N / IUPAC / soft-masked bases stay distinct symbols).  Every sequence buffer the
+// primitives read has >= 8 readable bytes of slack after its logical end.
 //
 // Semantics follow the reference exactly (paths relative to the reference repo):
 //   DWFALite::{extend,increase_edit_distance,update,finalize}  src/dwfa/dynamic_wfa.rs:68-245
-//   HaplotypeTracker / HaplotypeDWFA                            src/dwfa/haplotype_dwfa.rs:46-227
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,46 +28,62 @@ namespace avk {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-// ---- work counters (DESIGN.md "algorithmic work") ------------------------------------------
+// ---- work counters (DESIGN.md "algorithmic work"), per warp, flushed once at kernel end -----------
 struct WorkAcc {
-    unsigned long long alignments, cells, matched, search_pops, exact_pops;
-    __device__ void clear() { alignments = cells = matched = search_pops = exact_pops = 0; }
+    u64 cells, matched;
+    u32 alignments, search_pops, exact_pops;
+    __device__ __forceinline__ void clear() { alignments = cells = matched = search_pops = exact_pops = 0; }
 };
 
-// ---- byte copy ------------------------------------------------------------------------------
-// dst/src may live in shared or global memory (generic pointers).
-__device__ __forceinline__ void warp_copy(u8 *dst, const u8 *src, int n) {
-    const int lane = lane_id();
-    // head bytes until dst is 4-byte aligned, then words when src is equally aligned
-    if (n >= 64 && (((uintptr_t)dst ^ (uintptr_t)src) & 3) == 0) {
-        int head = (4 - ((uintptr_t)dst & 3)) & 3;
-        if (lane < head) dst[lane] = src[lane];
-        const u32 *s4 = (const u32 *)(src + head);
-        u32 *d4 = (u32 *)(dst + head);
-        int nw = (n - head) >> 2;
-        for (int i = lane; i < nw; i += 32) d4[i] = s4[i];
-        int done = head + (nw << 2);
-        if (done + lane < n) dst[done + lane] = src[done + lane];
-    } else {
-        for (int i = lane; i < n; i += 32) dst[i] = src[i];
-    }
+// ---- unaligned 32-bit load: two aligned loads + funnel shift ---------------------------------
+__device__ __forceinline__ u32 ld4u(const u8 *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const u32 *w = (const u32 *)(a & ~(uintptr_t)3);
+    const u32 sh = ((u32)a & 3u) * 8u;
+    return __funnelshift_r(w[0], w[1], sh);   // sh == 0 returns w[0]; w[1] is inside the slack
 }
 
-// ---- longest common prefix, lanes across bases ----------------------------------------------
-// number of equal bytes of a[0..na) and b[0..nb) from the start; warp-uniform result.
-__device__ __forceinline__ int warp_lcp(const u8 *a, int na, const u8 *b, int nb) {
+// ---- byte copy, any alignment, generic pointers (shared or global) ---------------------------
+__device__ __noinline__ void warp_copy(u8 *dst, const u8 *src, int n) {
+    const int lane = lane_id();
+    if (n < 16) {
+        if (lane < n) dst[lane] = src[lane];
+        return;
+    }
+    const int head = (int)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (lane < head) dst[lane] = src[lane];
+    u32 *d4 = (u32 *)(dst + head);
+    const u8 *s = src + head;
+    const int nw = (n - head) >> 2;
+    #pragma unroll 1
+    for (int i = lane; i < nw; i += 32) d4[i] = ld4u(s + 4 * i);
+    const int done = head + (nw << 2);
+    if (done + lane < n) dst[done + lane] = src[done + lane];
+}
+
+// ---- longest common prefix, lanes across bases (128 bytes per step) --------------------------
+// number of equal leading bytes of a[0..na) and b[0..nb); warp-uniform result.
+__device__ __noinline__ int warp_lcp(const u8 *a, int na, const u8 *b, int nb) {
     const int lane = lane_id();
     const int maxn = min(na, nb);
     int total = 0;
+    #pragma unroll 1
     while (total < maxn) {
-        int k = total + lane;
-        bool eq = (k < maxn) && (a[k] == b[k]);
-        unsigned m = __ballot_sync(AVK_FULL, eq);
-        if (m == AVK_FULL) { total += 32; continue; }
-        total += __ffs(~m) - 1;
+        const int k = total + 4 * lane;
+        int good = 0;   // equal bytes in this lane's word, capped by the bytes that exist
+        const int valid = min(4, maxn - k);
+        if (valid > 0) {
+            const u32 x = ld4u(a + k) ^ ld4u(b + k);
+            good = x ? ((__ffs(x) - 1) >> 3) : 4;
+            good = min(good, valid);
+        }
+        const unsigned m = __ballot_sync(AVK_FULL, good == 4);
+        if (m == AVK_FULL) { total += 128; continue; }
+        const int f = __ffs(~m) - 1;
+        total += 4 * f + __shfl_sync(AVK_FULL, good, f);
         break;
     }
-    return total;
+    return min(total, maxn);
 }
 
 // ---- DWFA -----------------------------------------------------------------------------------
@@ -76,15 +96,16 @@ struct Reach {
 };
 
 // extend(): dynamic_wfa.rs:94-130.  Narrow wavefronts: one warp-wide LCP per diagonal.
-// Wide wavefronts: one diagonal per lane; lanes that are still matching after a few
-// bytes are finished with a warp-wide LCP so that one long run does not serialise the warp.
-__device__ __forceinline__ Reach dwfa_extend(int *wf, int ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
+// Wide wavefronts: one diagonal per lane, one word compare each; lanes whose first word matched
+// completely are finished with a warp-wide LCP so that one long run does not serialise the warp.
+__device__ __noinline__ Reach dwfa_extend(int *wf, int ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
     const int lane = lane_id();
     const int n = 2 * ed + 1;
     int mb = -1, mo = -1;
     bool full = false;
     int matched = 0;
-    if (n <= 4) {
+    if (n <= 3) {
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) {
             int d = wf[i];
             int boff = d + ed - i;
@@ -96,17 +117,24 @@ __device__ __forceinline__ Reach dwfa_extend(int *wf, int ed, const u8 *A, int l
             full = full || (boff >= la && d >= lb);
         }
     } else {
+        #pragma unroll 1
         for (int base = 0; base < n; base += 32) {
             const int i = base + lane;
             const bool act = i < n;
             int d = act ? wf[i] : 0;
             int boff = d + ed - i;
             const int d0 = d;
-            int cnt = 0;
-            if (act) {
-                while (cnt < 4 && boff < la && d < lb && A[boff] == B[d]) { ++d; ++boff; ++cnt; }
+            bool more = false;
+            if (act && boff < la && d < lb) {
+                const int valid = min(4, min(la - boff, lb - d));
+                const u32 x = ld4u(A + boff) ^ ld4u(B + d);
+                int good = x ? ((__ffs(x) - 1) >> 3) : 4;
+                good = min(good, valid);
+                d += good; boff += good;
+                more = (good == 4) && boff < la && d < lb;
             }
-            unsigned m = __ballot_sync(AVK_FULL, act && cnt == 4 && boff < la && d < lb);
+            unsigned m = __ballot_sync(AVK_FULL, more);
+            #pragma unroll 1
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
@@ -128,8 +156,8 @@ __device__ __forceinline__ Reach dwfa_extend(int *wf, int ed, const u8 *A, int l
         matched = __reduce_add_sync(AVK_FULL, matched);
     }
     __syncwarp();
-    w.cells += (unsigned)n;
-    w.matched += (unsigned)matched;
+    w.cells += (u32)n;
+    w.matched += (u32)matched;
     Reach r;
     r.max_base = mb; r.max_other = mo; r.full = full;
     return r;
@@ -138,10 +166,11 @@ __device__ __forceinline__ Reach dwfa_extend(int *wf, int ed, const u8 *A, int l
 // increase_edit_distance() without the re-extend: dynamic_wfa.rs:152-168, in place.
 // new[i] = max(old[i], old[i-1]+1, old[i-2]+1) over the entries that exist; chunks are
 // processed from the top so that every read of old[] precedes the write that replaces it.
-__device__ __forceinline__ void dwfa_grow(int *wf, int old_ed) {
+__device__ __noinline__ void dwfa_grow(int *wf, int old_ed) {
     const int lane = lane_id();
     const int n_old = 2 * old_ed + 1;
     const int n_new = n_old + 2;
+    #pragma unroll 1
     for (int base = ((n_new - 1) >> 5) << 5; base >= 0; base -= 32) {
         const int i = base + lane;
         int v = 0;
@@ -159,8 +188,9 @@ __device__ __forceinline__ void dwfa_grow(int *wf, int old_ed) {
 enum { DWFA_OK = 0, DWFA_MAX_ED = 1 };
 
 // update(): dynamic_wfa.rs:68-84.  *ed is left incremented when the cap is hit (:146-149).
-__device__ __forceinline__ int dwfa_update(int *wf, int *ed, int max_ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
+__device__ __noinline__ int dwfa_update(int *wf, int *ed, int max_ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
     Reach r = dwfa_extend(wf, *ed, A, la, B, lb, w);
+    #pragma unroll 1
     while (!(r.max_base >= la) && !(r.max_other >= lb)) {
         *ed += 1;
         if (*ed > max_ed) return DWFA_MAX_ED;
@@ -171,9 +201,10 @@ __device__ __forceinline__ int dwfa_update(int *wf, int *ed, int max_ed, const u
 }
 
 // finalize(): dynamic_wfa.rs:183-198
-__device__ __forceinline__ int dwfa_finalize(int *wf, int *ed, int max_ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
+__device__ __noinline__ int dwfa_finalize(int *wf, int *ed, int max_ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
     w.alignments += 1;
     Reach r = dwfa_extend(wf, *ed, A, la, B, lb, w);
+    #pragma unroll 1
     while (!r.full) {
         *ed += 1;
         if (*ed > max_ed) return DWFA_MAX_ED;
@@ -185,12 +216,41 @@ __device__ __forceinline__ int dwfa_finalize(int *wf, int *ed, int max_ed, const
 
 // wfa_ed(): src/util/sequence_alignment.rs:9-13.  wf holds 2*max_ed+3 ints; returns -1 if the
 // distance would exceed max_ed (callers size the buffer from a proven bound, so -1 is a bug trap).
-__device__ __forceinline__ int wfa_ed_warp(const u8 *A, int la, const u8 *B, int lb, int *wf, int max_ed, WorkAcc &w) {
+__device__ __noinline__ int wfa_ed_warp(const u8 *A, int la, const u8 *B, int lb, int *wf, int max_ed, WorkAcc &w) {
     if (lane_id() == 0) wf[0] = 0;
     __syncwarp();
     int ed = 0;
     if (dwfa_finalize(wf, &ed, max_ed, A, la, B, lb, w) != DWFA_OK) return -1;
     return ed;
+}
+
+// ---- TMA bulk copy of a reference window into shared memory ------------------------------------
+// cp.async.bulk (1-D bulk tensor-less TMA, SASS UBLKCP) + mbarrier completion.  src/dst 16-byte
+// aligned, bytes a multiple of 16.  One mbarrier per warp; `phase` toggles per use.
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __noinline__ void tma_window_load(u8 *smem_dst, const u8 *gsrc, u32 bytes, u64 *mbar, u32 &phase) {
+    // order this warp's earlier generic-proxy accesses to the window before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane_id() == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+    }
+    u32 done = 0;
+    #pragma unroll 1
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
+    }
+    phase ^= 1u;
+    __syncwarp();
 }
 
 }  // namespace avk

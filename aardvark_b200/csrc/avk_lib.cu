@@ -34,8 +34,11 @@ using namespace avk;
 
 __device__ __forceinline__ void flush_work(const WorkAcc &w, unsigned long long *out) {
     if (lane_id() == 0 && out) {
-        atomicAdd(out + 0, w.alignments); atomicAdd(out + 1, w.cells); atomicAdd(out + 2, w.matched);
-        atomicAdd(out + 3, w.search_pops); atomicAdd(out + 4, w.exact_pops);
+        if (w.alignments) atomicAdd(out + 0, (unsigned long long)w.alignments);
+        if (w.cells) atomicAdd(out + 1, (unsigned long long)w.cells);
+        if (w.matched) atomicAdd(out + 2, (unsigned long long)w.matched);
+        if (w.search_pops) atomicAdd(out + 3, (unsigned long long)w.search_pops);
+        if (w.exact_pops) atomicAdd(out + 4, (unsigned long long)w.exact_pops);
     }
 }
 
@@ -113,61 +116,96 @@ __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const Dev
     __syncwarp();
 }
 
-// Persistent warps pull clusters from a global counter.  A cluster whose search does not fit this
-// tier's per-warp arena is appended to fail_list and re-run by the next (larger) tier.
-__global__ void __launch_bounds__(256) k_compare(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, const u32 *work_list,
-                                                 u32 n_work, u32 *counter, u8 *arena_base, long long arena_bytes,
-                                                 u32 *fail_list, u32 *fail_count, int last_tier,
-                                                 unsigned long long *work_out) {
+extern __shared__ __align__(128) u8 avk_dyn_smem[];
+
+// Work distribution of one workspace tier.  ctrs[0] = work counter of this launch, ctrs[1] = number of
+// clusters that did not fit (appended to fail_list, re-run by the next tier).  n_work is read from
+// device memory when n_work_ptr is set, so that tiers can be chained without a host round trip.
+struct TierArgs {
+    const u32 *work_list;
+    const u32 *n_work_ptr;
+    u32 n_work;
+    u32 *ctrs;
+    u8 *arena_base;        // global tiers
+    long long arena_bytes; // per warp
+    u32 *fail_list;
+    int last_tier;
+    unsigned long long *work_out;
+};
+
+// Persistent warps pull clusters from a global counter; one warp solves one cluster at a time.
+// SMEM tiers keep the warp's whole workspace (staged reference window, search nodes, queue) in
+// shared memory; global tiers take the clusters that do not fit.
+// Per-CTA shared state: the batch descriptor and one solver object per warp (never a local-memory frame).
+template <bool SMEM>
+__device__ __forceinline__ RegionSolver &init_solver(const DevBatch &b, const TierArgs &t, DevBatch &sb, RegionSolver *sol) {
+    if (threadIdx.x == 0) sb = b;
+    __syncthreads();
+    RegionSolver &s = sol[threadIdx.x >> 5];
+    if (lane_id() == 0) {
+        s.bp = &sb;
+        s.work.clear();
+        s.tma_phase = 0;
+        s.stage = SMEM;
+        s.arena_bytes = t.arena_bytes;
+        if (SMEM) {
+            s.arena = avk_dyn_smem + (threadIdx.x >> 5) * t.arena_bytes;
+            mbar_init((u64 *)s.arena);
+        } else {
+            s.arena = t.arena_base + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (u64)t.arena_bytes;
+        }
+    }
+    __syncwarp();
+    return s;
+}
+
+template <bool SMEM, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, TierArgs t) {
+    __shared__ DevBatch sb;
+    __shared__ RegionSolver sol[8];
     const int lane = lane_id();
-    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    WorkAcc w; w.clear();
-    RegionSolver s(b, w);
-    s.arena = arena_base + warp * (u64)arena_bytes;
-    s.arena_bytes = arena_bytes;
+    RegionSolver &s = init_solver<SMEM>(b, t, sb, sol);
+    const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
     for (;;) {
         u32 idx = 0;
-        if (lane == 0) idx = atomicAdd(counter, 1u);
+        if (lane == 0) idx = atomicAdd(t.ctrs, 1u);
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
-        const u64 r = work_list ? work_list[idx] : idx;
-        zero_region_outputs(b, out, r, true);
+        const u64 r = t.work_list ? t.work_list[idx] : idx;
         int rc = s.solve_compare(r, cfg, out);
         __syncwarp();
         if (rc == SOLVE_WORKSPACE) {
-            if (!last_tier) {
-                if (lane == 0) fail_list[atomicAdd(fail_count, 1u)] = (u32)r;
+            if (!t.last_tier) {
+                if (lane == 0) t.fail_list[atomicAdd(t.ctrs + 1, 1u)] = (u32)r;
                 continue;
             }
             rc = AVK_ST_WORKSPACE;
         }
-        if (rc != AVK_ST_OK) zero_region_outputs(b, out, r, false);
+        if (rc != AVK_ST_OK) zero_region_outputs(sb, out, r, false);
         if (lane == 0) out.status[r] = rc;
     }
-    flush_work(w, work_out);
+    flush_work(s.work, t.work_out);
 }
 
-__global__ void __launch_bounds__(256) k_merge(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, const u32 *work_list, u32 n_work,
-                                               u32 *counter, u8 *arena_base, long long arena_bytes, u32 *fail_list,
-                                               u32 *fail_count, int last_tier, unsigned long long *work_out) {
+template <bool SMEM, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) k_merge(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, TierArgs t) {
+    __shared__ DevBatch sb;
+    __shared__ RegionSolver sol[8];
     const int lane = lane_id();
-    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    WorkAcc w; w.clear();
-    RegionSolver s(b, w);
-    s.arena = arena_base + warp * (u64)arena_bytes;
-    s.arena_bytes = arena_bytes;
+    RegionSolver &s = init_solver<SMEM>(b, t, sb, sol);
     const u32 K = b.n_inputs;
+    const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
     for (;;) {
         u32 idx = 0;
-        if (lane == 0) idx = atomicAdd(counter, 1u);
+        if (lane == 0) idx = atomicAdd(t.ctrs, 1u);
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
-        const u64 r = work_list ? work_list[idx] : idx;
+        const u64 r = t.work_list ? t.work_list[idx] : idx;
         int rc = s.solve_merge(r, cfg, out);
         __syncwarp();
         if (rc == SOLVE_WORKSPACE) {
-            if (!last_tier) {
-                if (lane == 0) fail_list[atomicAdd(fail_count, 1u)] = (u32)r;
+            if (!t.last_tier) {
+                if (lane == 0) t.fail_list[atomicAdd(t.ctrs + 1, 1u)] = (u32)r;
                 continue;
             }
             rc = AVK_ST_WORKSPACE;
@@ -180,7 +218,7 @@ __global__ void __launch_bounds__(256) k_merge(DevBatch b, DevMergeOut out, avk_
             }
         }
     }
-    flush_work(w, work_out);
+    flush_work(s.work, t.work_out);
 }
 
 // SummaryWriter::add_comparison_benchmark (writers/summary.rs:146-158): thread j sums column j of the
@@ -227,11 +265,6 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-struct Tier {
-    long long arena_bytes;
-    int warps;
-};
-
 struct avk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -258,7 +291,9 @@ struct avk_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
     avk_work_counters last_work = {0, 0, 0, 0, 0};
-    std::vector<Tier> tiers;
+    u32 tier_fail[3] = {0, 0, 0};
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float tier_ms[3] = {0, 0, 0};
 };
 
 static int ensure(avk_ctx *ctx, DevBuf &b, size_t bytes) {
@@ -307,9 +342,7 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     for (auto &e : ctx->ev) cudaEventCreate(&e);
-    const int sm = ctx->sm_count;
-    // workspace tiers: (bytes per warp, warps).  Clusters that overflow a tier are re-run in the next.
-    ctx->tiers = {{48LL << 10, sm * 32}, {2LL << 20, sm * 8}, {64LL << 20, sm}, {2048LL << 20, 8}};
+    for (auto &e : ctx->tev) cudaEventCreate(&e);
     *out = ctx;
     return AVK_OK;
 }
@@ -419,35 +452,92 @@ static int run_alt_ed(avk_ctx *ctx, const DevBatch &db) {
     return AVK_OK;
 }
 
-// Runs a tiered per-cluster kernel; `launch` is called with (work_list, n_work, arena, arena_bytes, fail_list, last, grid).
+// Workspace tiers.  Tiers 0-1 keep the per-warp workspace in shared memory (3 CTAs x 8 warps x 9 KB,
+// then 1 CTA x 8 warps x 28 KB per SM); tiers 2+ use global memory for the rare clusters whose search
+// does not fit.  Tiers 0-2 are launched back to back: each reads its work count from the previous
+// tier's fail counter in device memory, so the common case needs no host round trip.
+struct LaunchCfg {
+    bool smem;
+    int min_ctas;          // CTAs per SM the kernel is compiled for
+    long long arena_bytes; // per warp
+    int ctas;              // grid size (persistent)
+};
+
 template <class F>
 static int run_tiers(avk_ctx *ctx, u64 n, F launch) {
     if (n == 0) return AVK_OK;
+    const int sm = ctx->sm_count;
     ENSURE(ctx->fail_a, 4 * n);
     ENSURE(ctx->fail_b, 4 * n);
-    u32 *counters = (u32 *)ctx->counters.p;
-    const u32 *work_list = nullptr;
-    u32 n_work = (u32)n;
+    ENSURE(ctx->counters, 256);
+    u32 *ctrs = (u32 *)ctx->counters.p;
+    CK(cudaMemsetAsync(ctrs, 0, 256, ctx->stream));
     u32 *fail_lists[2] = {(u32 *)ctx->fail_a.p, (u32 *)ctx->fail_b.p};
-    for (size_t t = 0; t < ctx->tiers.size() && n_work > 0; ++t) {
-        const bool last = t + 1 == ctx->tiers.size();
-        Tier tier = ctx->tiers[t];
-        int warps = (int)std::min<u64>((u64)tier.warps, ((u64)n_work + 0) < 8 ? 8 : (u64)n_work);
-        warps = (warps + 7) / 8 * 8;
-        ENSURE(ctx->arena, (size_t)warps * (size_t)tier.arena_bytes);
-        CK(cudaMemsetAsync(counters, 0, 16, ctx->stream));
-        u32 *fail_list = fail_lists[t & 1];
-        launch(work_list, n_work, (u8 *)ctx->arena.p, tier.arena_bytes, fail_list, counters + 1, last ? 1 : 0, warps / 8);
+    const LaunchCfg chain[3] = {{true, 3, 8192, sm * 3}, {true, 1, 27648, sm}, {false, 1, 2LL << 20, sm}};
+    ENSURE(ctx->arena, (size_t)chain[2].ctas * 8 * (size_t)chain[2].arena_bytes);
+    CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+    for (int t = 0; t < 3; ++t) {
+        TierArgs a;
+        a.work_list = t == 0 ? nullptr : fail_lists[(t - 1) & 1];
+        a.n_work_ptr = t == 0 ? nullptr : ctrs + 2 * (t - 1) + 1;
+        a.n_work = (u32)n;
+        a.ctrs = ctrs + 2 * t;
+        a.arena_base = (u8 *)ctx->arena.p;
+        a.arena_bytes = chain[t].arena_bytes;
+        a.fail_list = fail_lists[t & 1];
+        a.last_tier = 0;
+        a.work_out = (unsigned long long *)ctx->work_ctr.p;
+        int ctas = chain[t].ctas;
+        if (t == 0) ctas = (int)std::min<u64>((u64)ctas, (n + 7) / 8);
+        launch(chain[t], a, ctas);
         ctx->launches += 1;
         CK(cudaGetLastError());
-        if (last) break;
-        u32 host_counters[4];
-        CK(cudaMemcpyAsync(host_counters, counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->tev[t + 1], ctx->stream));
+    }
+    u32 host_ctrs[8];
+    CK(cudaMemcpyAsync(host_ctrs, ctrs, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tier_fail[0] = host_ctrs[1]; ctx->tier_fail[1] = host_ctrs[3]; ctx->tier_fail[2] = host_ctrs[5];
+    for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
+    u32 n_work = host_ctrs[5];
+    int prev = 2;
+    // rare: clusters that overflow 2 MB per warp; host-synchronised escalation
+    const LaunchCfg big[2] = {{false, 1, 64LL << 20, (sm + 7) / 8}, {false, 1, 2048LL << 20, 1}};
+    for (int t = 0; t < 2 && n_work > 0; ++t) {
+        ENSURE(ctx->arena, (size_t)big[t].ctas * 8 * (size_t)big[t].arena_bytes);
+        CK(cudaMemsetAsync(ctrs + 8, 0, 8, ctx->stream));
+        TierArgs a;
+        a.work_list = fail_lists[prev & 1];
+        a.n_work_ptr = nullptr;
+        a.n_work = n_work;
+        a.ctrs = ctrs + 8;
+        a.arena_base = (u8 *)ctx->arena.p;
+        a.arena_bytes = big[t].arena_bytes;
+        a.fail_list = fail_lists[(prev + 1) & 1];
+        a.last_tier = t == 1;
+        a.work_out = (unsigned long long *)ctx->work_ctr.p;
+        launch(big[t], a, big[t].ctas);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host_ctrs, ctrs + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        n_work = host_counters[1];
-        work_list = fail_list;
+        n_work = host_ctrs[1];
+        prev += 1;
     }
     return AVK_OK;
+}
+
+template <bool SMEM, int MIN_CTAS>
+static void launch_compare(avk_ctx *ctx, const DevBatch &db, const DevCompareOut &out, const avk_compare_cfg &c, const TierArgs &a, int ctas) {
+    const size_t smem = SMEM ? (size_t)a.arena_bytes * 8 : 0;
+    if (SMEM) cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_compare<SMEM, MIN_CTAS><<<ctas, 256, smem, ctx->stream>>>(db, out, c, a);
+}
+template <bool SMEM, int MIN_CTAS>
+static void launch_merge(avk_ctx *ctx, const DevBatch &db, const DevMergeOut &out, const avk_merge_cfg &c, const TierArgs &a, int ctas) {
+    const size_t smem = SMEM ? (size_t)a.arena_bytes * 8 : 0;
+    if (SMEM) cudaFuncSetAttribute(k_merge<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_merge<SMEM, MIN_CTAS><<<ctas, 256, smem, ctx->stream>>>(db, out, c, a);
 }
 
 static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, const u64 *strat_off_dev,
@@ -478,8 +568,10 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     int rc = run_alt_ed(ctx, db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = run_tiers(ctx, n, [&](const u32 *wl, u32 nw, u8 *arena, long long ab, u32 *fl, u32 *fc, int last, int blocks) {
-        k_compare<<<blocks, 256, 0, ctx->stream>>>(db, out, c, wl, nw, (u32 *)ctx->counters.p, arena, ab, fl, fc, last, work);
+    rc = run_tiers(ctx, n, [&](const LaunchCfg &lc, const TierArgs &a, int ctas) {
+        if (lc.smem && lc.min_ctas == 3) launch_compare<true, 3>(ctx, db, out, c, a, ctas);
+        else if (lc.smem) launch_compare<true, 1>(ctx, db, out, c, a, ctas);
+        else launch_compare<false, 1>(ctx, db, out, c, a, ctas);
     });
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -633,6 +725,18 @@ extern "C" int avk_last_timings(avk_ctx *ctx, float *ms5) {
     memcpy(ms5, ctx->last_ms, sizeof(ctx->last_ms));
     return AVK_OK;
 }
+// Diagnostics: how many clusters overflowed workspace tiers 0, 1, 2 in the last run.
+extern "C" int avk_last_tier_overflow(avk_ctx *ctx, uint32_t *out3) {
+    if (!ctx || !out3) return AVK_ERR_INVALID;
+    for (int i = 0; i < 3; ++i) out3[i] = ctx->tier_fail[i];
+    return AVK_OK;
+}
+// Diagnostics: device milliseconds of workspace tiers 0, 1, 2 in the last run.
+extern "C" int avk_last_tier_ms(avk_ctx *ctx, float *out3) {
+    if (!ctx || !out3) return AVK_ERR_INVALID;
+    for (int i = 0; i < 3; ++i) out3[i] = ctx->tier_ms[i];
+    return AVK_OK;
+}
 extern "C" int avk_last_work(avk_ctx *ctx, avk_work_counters *out) {
     if (!ctx || !out) return AVK_ERR_INVALID;
     *out = ctx->last_work;
@@ -661,8 +765,10 @@ extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, cons
     rc = run_alt_ed(ctx, db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = run_tiers(ctx, n, [&](const u32 *wl, u32 nw, u8 *arena, long long ab, u32 *fl, u32 *fc, int last, int blocks) {
-        k_merge<<<blocks, 256, 0, ctx->stream>>>(db, mo, c, wl, nw, (u32 *)ctx->counters.p, arena, ab, fl, fc, last, work);
+    rc = run_tiers(ctx, n, [&](const LaunchCfg &lc, const TierArgs &a, int ctas) {
+        if (lc.smem && lc.min_ctas == 3) launch_merge<true, 3>(ctx, db, mo, c, a, ctas);
+        else if (lc.smem) launch_merge<true, 1>(ctx, db, mo, c, a, ctas);
+        else launch_merge<false, 1>(ctx, db, mo, c, a, ctas);
     });
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));

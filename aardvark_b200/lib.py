@@ -85,7 +85,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "avk_create", "avk_destroy", "avk_last_error", "avk_set_reference", "avk_compare_batch", "avk_merge_batch",
     "avk_wfa_ed_batch", "avk_compare_seq_offsets", "avk_compare_upload", "avk_compare_run_resident",
-    "avk_compare_download", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak",
+    "avk_compare_download", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak", "avk_last_tier_overflow", "avk_last_tier_ms",
 ]
 
 
@@ -202,6 +202,16 @@ class Solver:
         v = C.c_double(0)
         self._check(self._lib.avk_int_peak(self._ctx, C.byref(v)), "avk_int_peak")
         return float(v.value)
+
+    def last_tier_overflow(self):
+        buf = (C.c_uint32 * 3)()
+        self._lib.avk_last_tier_overflow(self._ctx, buf)
+        return [int(x) for x in buf]
+
+    def last_tier_ms(self):
+        buf = (C.c_float * 3)()
+        self._lib.avk_last_tier_ms(self._ctx, buf)
+        return [float(x) for x in buf]
 
     def launch_count(self) -> int:
         return int(self._lib.avk_launch_count(self._ctx))

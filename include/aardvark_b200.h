@@ -272,6 +272,10 @@ int avk_compare_download(avk_ctx *ctx, avk_compare_out *out);
  * [3] finalize/reduce, [4] total. */
 int avk_last_timings(avk_ctx *ctx, float *ms5);
 int avk_last_work(avk_ctx *ctx, avk_work_counters *out);
+/* Diagnostics: clusters that overflowed workspace tiers 0, 1, 2 in the last run. */
+int avk_last_tier_overflow(avk_ctx *ctx, uint32_t *out3);
+/* Diagnostics: device milliseconds spent in workspace tiers 0, 1, 2 in the last run. */
+int avk_last_tier_ms(avk_ctx *ctx, float *out3);
 /* INT32 ALU throughput probe (add/max/xor chains), integer ops per second: the measured
  * denominator of the integer roofline, obtained the way MEASURED_PEAKS.json obtains HBM GB/s. */
 int avk_int_peak(avk_ctx *ctx, double *ops_per_s);
