@@ -1,19 +1,29 @@
 // avk_device.cuh -- warp-cooperative device primitives of the haplotype-comparison path.
 //
-// One warp owns one cluster (or one alignment).  All 32 lanes execute these
-// functions together with warp-uniform scalar arguments; lanes split either
-//   * the BASES of one diagonal (4 bytes per lane, 128 bytes per warp step:
-//     unaligned 32-bit loads built with funnel shifts, XOR, __ffs, __ballot_sync), or
+// One warp owns one cluster (or one alignment).  All 32 lanes execute these functions together
+// with warp-uniform scalar arguments; lanes split either
+//   * the BASES of one diagonal (4 bytes per lane, 128 bytes per warp step: unaligned 32-bit
+//     loads built with funnel shifts, XOR, __ffs, __ballot_sync), or
 //   * the DIAGONALS of one wavefront (one diagonal per lane),
-// whichever the wavefront width calls for.  Nothing here uses tensor cores:
-// this is integer DP, bounded by the INT32 ALU pipe and latency.
+// whichever the wavefront width calls for.  No tensor cores: this is integer DP.
 //
-// Sequences are raw bytes (the reference compares raw bytes, dynamic_wfa.rs:118, so
-// N / IUPAC / soft-masked bases stay distinct symbols).  Every sequence buffer the
-// primitives read has >= 8 readable bytes of slack after its logical end.
+// Memory spaces.  Mem<true> addresses the CTA's dynamic shared memory with 32-bit byte offsets
+// (LDS/STS, no generic-address arithmetic); Mem<false> uses 64-bit global addresses.  Every kernel
+// is instantiated for one of the two, so the hot shared-memory tier never touches a generic pointer.
 //
-// Semantics follow the reference exactly (paths relative to the reference repo):
-//   DWFALite::{extend,increase_edit_distance,update,finalize}  src/dwfa/dynamic_wfa.rs:68-245
+// Virtual sequences.  A haplotype is "the reference with ALT alleles spliced in", and most of it
+// IS reference.  A sequence is therefore kept as a materialised prefix (up to the end of its last
+// spliced ALT) plus an implicit tail that reads the reference window directly:
+//       byte x  =  x < mlen ? data[x] : tail[x - mlen]          for x < len
+// Appending reference (HaplotypeTracker::copy_reference) costs nothing, clones copy only the
+// prefix, and when both sequences of a comparison read the same reference bytes the match is
+// known without touching memory.  Logical content is exactly the reference's Vec<u8>.
+//
+// Sequences are raw bytes (the reference compares raw bytes, dynamic_wfa.rs:118, so N / IUPAC /
+// soft-masked bases stay distinct symbols).  Every buffer has >= 8 readable bytes of slack.
+//
+// Semantics follow DWFALite::{extend,increase_edit_distance,update,finalize}
+// (src/dwfa/dynamic_wfa.rs:68-245) exactly.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,56 +34,70 @@ typedef uint8_t u8;
 typedef uint32_t u32;
 typedef uint64_t u64;
 
+extern __shared__ __align__(128) u8 avk_dyn_smem[];
+
 namespace avk {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-// ---- work counters (DESIGN.md "algorithmic work"), per warp, flushed once at kernel end -----------
-struct WorkAcc {
-    u64 cells, matched;
-    u32 alignments, search_pops, exact_pops;
-    __device__ __forceinline__ void clear() { alignments = cells = matched = search_pops = exact_pops = 0; }
+template <bool SMEM> struct Mem;
+template <> struct Mem<true> {
+    typedef u32 addr;
+    static __device__ __forceinline__ u8 *p(addr a) { return avk_dyn_smem + a; }
 };
+template <> struct Mem<false> {
+    typedef u64 addr;
+    static __device__ __forceinline__ u8 *p(addr a) { return (u8 *)a; }
+};
+#define LD8(a) (*(const u8 *)M::p(a))
+#define LD32(a) (*(const u32 *)M::p(a))
+#define LDI(a) (*(const int *)M::p(a))
+#define LD64(a) (*(const u64 *)M::p(a))
+#define ST8(a, v) (*(u8 *)M::p(a) = (u8)(v))
+#define ST32(a, v) (*(u32 *)M::p(a) = (u32)(v))
+#define ST64(a, v) (*(u64 *)M::p(a) = (u64)(v))
 
-// ---- unaligned 32-bit load: two aligned loads + funnel shift ---------------------------------
-__device__ __forceinline__ u32 ld4u(const u8 *p) {
-    const uintptr_t a = (uintptr_t)p;
-    const u32 *w = (const u32 *)(a & ~(uintptr_t)3);
-    const u32 sh = ((u32)a & 3u) * 8u;
-    return __funnelshift_r(w[0], w[1], sh);   // sh == 0 returns w[0]; w[1] is inside the slack
+// ---- work counters (DESIGN.md "algorithmic work"); live in the arena header ---------------------
+enum { WK_CELLS = 16, WK_MATCHED = 24, WK_ALIGN = 32, WK_SPOPS = 36, WK_XPOPS = 40, ARENA_HDR = 48 };
+
+// ---- unaligned 32-bit load: two aligned loads + funnel shift ------------------------------------
+template <bool SMEM>
+__device__ __forceinline__ u32 ld4u(typename Mem<SMEM>::addr a) {
+    typedef Mem<SMEM> M;
+    const typename M::addr w = a & ~(typename M::addr)3;
+    return __funnelshift_r(LD32(w), LD32(w + 4), ((u32)a & 3u) * 8u);   // shift 0 returns the first word
 }
 
-// ---- byte copy, any alignment, generic pointers (shared or global) ---------------------------
-__device__ __noinline__ void warp_copy(u8 *dst, const u8 *src, int n) {
+// ---- byte copy, any alignment ---------------------------------------------------------------------
+template <bool SMEM>
+__device__ __noinline__ void warp_copy(typename Mem<SMEM>::addr dst, typename Mem<SMEM>::addr src, int n) {
+    typedef Mem<SMEM> M;
     const int lane = lane_id();
-    if (n < 16) {
-        if (lane < n) dst[lane] = src[lane];
+    if (n <= 32) {
+        if (lane < n) ST8(dst + lane, LD8(src + lane));
         return;
     }
-    const int head = (int)((4 - ((uintptr_t)dst & 3)) & 3);
-    if (lane < head) dst[lane] = src[lane];
-    u32 *d4 = (u32 *)(dst + head);
-    const u8 *s = src + head;
+    const int head = (int)((4u - ((u32)dst & 3u)) & 3u);
+    if (lane < head) ST8(dst + lane, LD8(src + lane));
     const int nw = (n - head) >> 2;
-    #pragma unroll 1
-    for (int i = lane; i < nw; i += 32) d4[i] = ld4u(s + 4 * i);
+#pragma unroll 1
+    for (int i = lane; i < nw; i += 32) ST32(dst + head + 4 * i, ld4u<SMEM>(src + head + 4 * i));
     const int done = head + (nw << 2);
-    if (done + lane < n) dst[done + lane] = src[done + lane];
+    if (done + lane < n) ST8(dst + done + lane, LD8(src + done + lane));
 }
 
-// ---- longest common prefix, lanes across bases (128 bytes per step) --------------------------
-// number of equal leading bytes of a[0..na) and b[0..nb); warp-uniform result.
-__device__ __noinline__ int warp_lcp(const u8 *a, int na, const u8 *b, int nb) {
+// ---- longest common prefix of two physical byte ranges (128 bytes per step) -----------------------
+template <bool SMEM>
+__device__ __forceinline__ int raw_lcp(typename Mem<SMEM>::addr a, typename Mem<SMEM>::addr b, int maxn) {
     const int lane = lane_id();
-    const int maxn = min(na, nb);
     int total = 0;
-    #pragma unroll 1
+#pragma unroll 1
     while (total < maxn) {
         const int k = total + 4 * lane;
         int good = 0;   // equal bytes in this lane's word, capped by the bytes that exist
         const int valid = min(4, maxn - k);
         if (valid > 0) {
-            const u32 x = ld4u(a + k) ^ ld4u(b + k);
+            const u32 x = ld4u<SMEM>(a + k) ^ ld4u<SMEM>(b + k);
             good = x ? ((__ffs(x) - 1) >> 3) : 4;
             good = min(good, valid);
         }
@@ -86,65 +110,102 @@ __device__ __noinline__ int warp_lcp(const u8 *a, int na, const u8 *b, int nb) {
     return min(total, maxn);
 }
 
-// ---- DWFA -----------------------------------------------------------------------------------
-// State: ed, wavefront wf[0 .. 2*ed] (int32, bases consumed in `other`), kept by the caller.
-// baseline offset of entry i is wf[i] + ed - i (dynamic_wfa.rs:114).
+// ---- virtual sequence ---------------------------------------------------------------------------------
+template <bool SMEM>
+struct VSeq {
+    typename Mem<SMEM>::addr data;   // materialised prefix
+    typename Mem<SMEM>::addr tail;   // address of the byte at logical offset mlen (a reference position)
+    int mlen;                        // materialised bytes
+    int len;                         // logical length
+    __device__ __forceinline__ typename Mem<SMEM>::addr at(int x) const { return x < mlen ? data + x : tail + (x - mlen); }
+    __device__ __forceinline__ int run(int x, int cap) const { return x < mlen ? mlen - x : cap; }   // bytes left in this piece
+};
+
+// number of equal leading bytes of A[ia..] and B[ib..]; warp-uniform.  At most three pieces.
+template <bool SMEM>
+__device__ __noinline__ int vs_lcp(const VSeq<SMEM> A, int ia, const VSeq<SMEM> B, int ib) {
+    const int maxn = min(A.len - ia, B.len - ib);
+    int total = 0;
+#pragma unroll 1
+    while (total < maxn) {
+        const int xa = ia + total, xb = ib + total;
+        const int n = min(min(A.run(xa, maxn), B.run(xb, maxn)), maxn - total);
+        const typename Mem<SMEM>::addr pa = A.at(xa), pb = B.at(xb);
+        if (pa == pb) { total += n; continue; }   // both read the same reference bytes: equal by construction
+        const int m = raw_lcp<SMEM>(pa, pb, n);
+        total += m;
+        if (m < n) break;
+    }
+    return total;
+}
+
+// ---- DWFA -------------------------------------------------------------------------------------------
+// State: ed, wavefront wf[0 .. 2*ed] (int32, bases consumed in `other` == B), kept by the caller.
+// baseline (A) offset of entry i is wf[i] + ed - i (dynamic_wfa.rs:114).
 struct Reach {
     int max_base;   // max_i (wf[i] + ed - i)     (maximum_baseline_distance :201-208)
     int max_other;  // max_i wf[i]                (maximum_other_distance    :212-215)
     bool full;      // any i: base >= la && other >= lb (reached_full_diagonal :237-245)
 };
 
-// extend(): dynamic_wfa.rs:94-130.  Narrow wavefronts: one warp-wide LCP per diagonal.
-// Wide wavefronts: one diagonal per lane, one word compare each; lanes whose first word matched
-// completely are finished with a warp-wide LCP so that one long run does not serialise the warp.
-__device__ __noinline__ Reach dwfa_extend(int *wf, int ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
+// extend(): dynamic_wfa.rs:94-130.  Narrow wavefronts: one warp-wide LCP per diagonal.  Wide
+// wavefronts: one diagonal per lane, one word compare each; lanes whose word matched completely are
+// finished with a warp-wide LCP so that one long run does not serialise the warp.
+template <bool SMEM>
+__device__ __noinline__ Reach dwfa_extend(typename Mem<SMEM>::addr wf, int ed, const VSeq<SMEM> A, const VSeq<SMEM> B,
+                                          typename Mem<SMEM>::addr wk) {
+    typedef Mem<SMEM> M;
     const int lane = lane_id();
     const int n = 2 * ed + 1;
+    const int la = A.len, lb = B.len;
     int mb = -1, mo = -1;
     bool full = false;
     int matched = 0;
     if (n <= 3) {
-        #pragma unroll 1
+#pragma unroll 1
         for (int i = 0; i < n; ++i) {
-            int d = wf[i];
+            int d = LDI(wf + 4 * i);
             int boff = d + ed - i;
             int ext = 0;
-            if (boff < la && d < lb) ext = warp_lcp(A + boff, la - boff, B + d, lb - d);
+            if (boff < la && d < lb) ext = vs_lcp<SMEM>(A, boff, B, d);
             d += ext; boff += ext; matched += ext;
-            if (ext && lane == 0) wf[i] = d;
+            if (ext && lane == 0) ST32(wf + 4 * i, d);
             mb = max(mb, boff); mo = max(mo, d);
             full = full || (boff >= la && d >= lb);
         }
     } else {
-        #pragma unroll 1
+#pragma unroll 1
         for (int base = 0; base < n; base += 32) {
             const int i = base + lane;
             const bool act = i < n;
-            int d = act ? wf[i] : 0;
+            int d = act ? LDI(wf + 4 * i) : 0;
             int boff = d + ed - i;
             const int d0 = d;
             bool more = false;
             if (act && boff < la && d < lb) {
-                const int valid = min(4, min(la - boff, lb - d));
-                const u32 x = ld4u(A + boff) ^ ld4u(B + d);
-                int good = x ? ((__ffs(x) - 1) >> 3) : 4;
-                good = min(good, valid);
+                const int lim = min(la - boff, lb - d);
+                const int valid = min(min(4, lim), min(A.run(boff, 4), B.run(d, 4)));
+                const typename M::addr pa = A.at(boff), pb = B.at(d);
+                int good = valid;
+                if (pa != pb) {
+                    const u32 x = ld4u<SMEM>(pa) ^ ld4u<SMEM>(pb);
+                    good = min(x ? ((__ffs(x) - 1) >> 3) : 4, valid);
+                }
                 d += good; boff += good;
-                more = (good == 4) && boff < la && d < lb;
+                more = (good == valid) && good < lim;
             }
             unsigned m = __ballot_sync(AVK_FULL, more);
-            #pragma unroll 1
+#pragma unroll 1
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
                 const int dd = __shfl_sync(AVK_FULL, d, src);
                 const int bb = __shfl_sync(AVK_FULL, boff, src);
-                const int ext = warp_lcp(A + bb, la - bb, B + dd, lb - dd);
+                const int ext = vs_lcp<SMEM>(A, bb, B, dd);
                 if (lane == src) { d += ext; boff += ext; }
             }
             if (act) {
-                if (d != d0) wf[i] = d;
+                if (d != d0) ST32(wf + 4 * i, d);
                 matched += d - d0;
                 mb = max(mb, boff); mo = max(mo, d);
                 full = full || (boff >= la && d >= lb);
@@ -156,100 +217,97 @@ __device__ __noinline__ Reach dwfa_extend(int *wf, int ed, const u8 *A, int la, 
         matched = __reduce_add_sync(AVK_FULL, matched);
     }
     __syncwarp();
-    w.cells += (u32)n;
-    w.matched += (u32)matched;
+    if (lane == 0) { ST64(wk + WK_CELLS, LD64(wk + WK_CELLS) + (u64)n); ST64(wk + WK_MATCHED, LD64(wk + WK_MATCHED) + (u64)matched); }
     Reach r;
     r.max_base = mb; r.max_other = mo; r.full = full;
     return r;
 }
 
 // increase_edit_distance() without the re-extend: dynamic_wfa.rs:152-168, in place.
-// new[i] = max(old[i], old[i-1]+1, old[i-2]+1) over the entries that exist; chunks are
-// processed from the top so that every read of old[] precedes the write that replaces it.
-__device__ __noinline__ void dwfa_grow(int *wf, int old_ed) {
+// new[i] = max(old[i], old[i-1]+1, old[i-2]+1) over the entries that exist; chunks are processed from
+// the top so that every read of old[] precedes the write that replaces it.
+template <bool SMEM>
+__device__ __noinline__ void dwfa_grow(typename Mem<SMEM>::addr wf, int old_ed) {
+    typedef Mem<SMEM> M;
     const int lane = lane_id();
     const int n_old = 2 * old_ed + 1;
     const int n_new = n_old + 2;
-    #pragma unroll 1
+#pragma unroll 1
     for (int base = ((n_new - 1) >> 5) << 5; base >= 0; base -= 32) {
         const int i = base + lane;
         int v = 0;
         if (i < n_new) {
-            if (i < n_old) v = wf[i];
-            if (i >= 1 && i - 1 < n_old) v = max(v, wf[i - 1] + 1);
-            if (i >= 2 && i - 2 < n_old) v = max(v, wf[i - 2] + 1);
+            if (i < n_old) v = LDI(wf + 4 * i);
+            if (i >= 1 && i - 1 < n_old) v = max(v, LDI(wf + 4 * (i - 1)) + 1);
+            if (i >= 2 && i - 2 < n_old) v = max(v, LDI(wf + 4 * (i - 2)) + 1);
         }
         __syncwarp();
-        if (i < n_new) wf[i] = v;
+        if (i < n_new) ST32(wf + 4 * i, v);
     }
     __syncwarp();
 }
 
 enum { DWFA_OK = 0, DWFA_MAX_ED = 1 };
 
-// update(): dynamic_wfa.rs:68-84.  *ed is left incremented when the cap is hit (:146-149).
-__device__ __noinline__ int dwfa_update(int *wf, int *ed, int max_ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
-    Reach r = dwfa_extend(wf, *ed, A, la, B, lb, w);
-    #pragma unroll 1
-    while (!(r.max_base >= la) && !(r.max_other >= lb)) {
-        *ed += 1;
-        if (*ed > max_ed) return DWFA_MAX_ED;
-        dwfa_grow(wf, *ed - 1);
-        r = dwfa_extend(wf, *ed, A, la, B, lb, w);
+// update() (dynamic_wfa.rs:68-84) when !to_full, finalize() (:183-198) when to_full.
+// *ed is left incremented when the cap is hit (:146-149).
+template <bool SMEM>
+__device__ __noinline__ int dwfa_run(typename Mem<SMEM>::addr wf, int *ed, int max_ed, const VSeq<SMEM> A, const VSeq<SMEM> B,
+                                     bool to_full, typename Mem<SMEM>::addr wk) {
+    int e = *ed;
+    Reach r = dwfa_extend<SMEM>(wf, e, A, B, wk);
+#pragma unroll 1
+    while (to_full ? !r.full : (!(r.max_base >= A.len) && !(r.max_other >= B.len))) {
+        e += 1;
+        *ed = e;
+        if (e > max_ed) return DWFA_MAX_ED;
+        dwfa_grow<SMEM>(wf, e - 1);
+        r = dwfa_extend<SMEM>(wf, e, A, B, wk);
     }
     return DWFA_OK;
 }
 
-// finalize(): dynamic_wfa.rs:183-198
-__device__ __noinline__ int dwfa_finalize(int *wf, int *ed, int max_ed, const u8 *A, int la, const u8 *B, int lb, WorkAcc &w) {
-    w.alignments += 1;
-    Reach r = dwfa_extend(wf, *ed, A, la, B, lb, w);
-    #pragma unroll 1
-    while (!r.full) {
-        *ed += 1;
-        if (*ed > max_ed) return DWFA_MAX_ED;
-        dwfa_grow(wf, *ed - 1);
-        r = dwfa_extend(wf, *ed, A, la, B, lb, w);
-    }
-    return DWFA_OK;
-}
-
-// wfa_ed(): src/util/sequence_alignment.rs:9-13.  wf holds 2*max_ed+3 ints; returns -1 if the
-// distance would exceed max_ed (callers size the buffer from a proven bound, so -1 is a bug trap).
-__device__ __noinline__ int wfa_ed_warp(const u8 *A, int la, const u8 *B, int lb, int *wf, int max_ed, WorkAcc &w) {
-    if (lane_id() == 0) wf[0] = 0;
+// wfa_ed(): src/util/sequence_alignment.rs:9-13.  wf holds 2*max_ed+3 ints; returns -1 if the distance
+// would exceed max_ed (callers size the buffer from a proven bound, so -1 is a bug trap).
+template <bool SMEM>
+__device__ __noinline__ int wfa_ed_warp(const VSeq<SMEM> A, const VSeq<SMEM> B, typename Mem<SMEM>::addr wf, int max_ed,
+                                        typename Mem<SMEM>::addr wk) {
+    typedef Mem<SMEM> M;
+    if (lane_id() == 0) { ST32(wf, 0); ST32(wk + WK_ALIGN, LD32(wk + WK_ALIGN) + 1); }
     __syncwarp();
     int ed = 0;
-    if (dwfa_finalize(wf, &ed, max_ed, A, la, B, lb, w) != DWFA_OK) return -1;
+    if (dwfa_run<SMEM>(wf, &ed, max_ed, A, B, true, wk) != DWFA_OK) return -1;
     return ed;
 }
 
-// ---- TMA bulk copy of a reference window into shared memory ------------------------------------
-// cp.async.bulk (1-D bulk tensor-less TMA, SASS UBLKCP) + mbarrier completion.  src/dst 16-byte
-// aligned, bytes a multiple of 16.  One mbarrier per warp; `phase` toggles per use.
+// ---- TMA bulk copy of a reference window into shared memory -------------------------------------------
+// cp.async.bulk (1-D bulk TMA, SASS UBLKCP) + mbarrier completion.  src/dst 16-byte aligned, bytes a
+// multiple of 16.  One mbarrier per warp (arena bytes [0,8)); `phase` toggles per use.
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(u64 *mbar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+__device__ __forceinline__ void mbar_init(u32 mbar_off) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(avk_dyn_smem + mbar_off)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-__device__ __noinline__ void tma_window_load(u8 *smem_dst, const u8 *gsrc, u32 bytes, u64 *mbar, u32 &phase) {
+__device__ __noinline__ void tma_window_load(u32 dst_off, const u8 *gsrc, u32 bytes, u32 mbar_off, u32 *phase) {
     // order this warp's earlier generic-proxy accesses to the window before the async-proxy write
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
+    const u32 mbar = smem_u32(avk_dyn_smem + mbar_off);
     if (lane_id() == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+                     ::"r"(smem_u32(avk_dyn_smem + dst_off)), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
     }
+    const u32 ph = *phase;
     u32 done = 0;
-    #pragma unroll 1
+#pragma unroll 1
     while (!done) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
+                     : "=r"(done) : "r"(mbar), "r"(ph) : "memory");
     }
-    phase ^= 1u;
+    *phase = ph ^ 1u;
     __syncwarp();
 }
 

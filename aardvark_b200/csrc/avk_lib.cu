@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,25 +33,44 @@ using namespace avk;
 
 // ------------------------------------------------------------------------------------ kernels
 
-__device__ __forceinline__ void flush_work(const WorkAcc &w, unsigned long long *out) {
+// Flush the per-warp work counters kept in an arena / scratch header (WK_* offsets) to the global totals.
+template <bool SMEM>
+__device__ __forceinline__ void flush_work(typename Mem<SMEM>::addr hdr, unsigned long long *out) {
+    typedef Mem<SMEM> M;
     if (lane_id() == 0 && out) {
-        if (w.alignments) atomicAdd(out + 0, (unsigned long long)w.alignments);
-        if (w.cells) atomicAdd(out + 1, (unsigned long long)w.cells);
-        if (w.matched) atomicAdd(out + 2, (unsigned long long)w.matched);
-        if (w.search_pops) atomicAdd(out + 3, (unsigned long long)w.search_pops);
-        if (w.exact_pops) atomicAdd(out + 4, (unsigned long long)w.exact_pops);
+        const u64 cells = LD64(hdr + WK_CELLS), matched = LD64(hdr + WK_MATCHED);
+        const u32 al = LD32(hdr + WK_ALIGN), sp = LD32(hdr + WK_SPOPS), xp = LD32(hdr + WK_XPOPS);
+        if (al) atomicAdd(out + 0, (unsigned long long)al);
+        if (cells) atomicAdd(out + 1, (unsigned long long)cells);
+        if (matched) atomicAdd(out + 2, (unsigned long long)matched);
+        if (sp) atomicAdd(out + 3, (unsigned long long)sp);
+        if (xp) atomicAdd(out + 4, (unsigned long long)xp);
     }
+}
+template <bool SMEM>
+__device__ __forceinline__ void clear_work(typename Mem<SMEM>::addr hdr) {
+    typedef Mem<SMEM> M;
+    const int lane = lane_id();
+    if (lane < 8) ST32(hdr + 16 + 4 * lane, 0);
+    __syncwarp();
+}
+
+// per-warp scratch of the two alignment kernels: [ARENA_HDR bytes header | wavefront ints]
+__device__ __forceinline__ VSeq<false> plain_seq(const u8 *p, int n) {
+    VSeq<false> v;
+    v.data = (u64)(uintptr_t)p; v.tail = v.data + (u64)n; v.mlen = n; v.len = n;
+    return v;
 }
 
 // alt_ed: 32 variants per warp pass; SNVs are answered by their lane, everything else is aligned
 // warp-cooperatively (prefix shortcut for pure insertions/deletions, WFA otherwise).
-__global__ void __launch_bounds__(256) k_alt_ed(DevBatch b, u64 n_variants, u32 *alt_ed, int *scratch, int scratch_ints,
+__global__ void __launch_bounds__(256) k_alt_ed(DevBatch b, u64 n_variants, u32 *alt_ed, u8 *scratch, int scratch_ints,
                                                 unsigned long long *work_out) {
     const int lane = lane_id();
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
-    int *wf = scratch + warp * (u64)scratch_ints;
-    WorkAcc w; w.clear();
+    const u64 hdr = (u64)(uintptr_t)(scratch + warp * ((u64)scratch_ints * 4 + ARENA_HDR));
+    clear_work<false>(hdr);
     for (u64 base = warp * 32; base < n_variants; base += n_warps * 32) {
         const u64 v = base + lane;
         bool coop = false;
@@ -72,35 +92,36 @@ __global__ void __launch_bounds__(256) k_alt_ed(DevBatch b, u64 n_variants, u32 
             if (mn == 0) ed = max(l0, l1);
             else if (2 * max(l0, l1) + 3 > scratch_ints) ed = 0;   // cannot happen: host sizes scratch by the max allele
             else {
-                const int p = warp_lcp(a0, l0, a1, l1);
+                const int p = raw_lcp<false>((u64)(uintptr_t)a0, (u64)(uintptr_t)a1, mn);
                 if (p == mn) ed = max(l0, l1) - mn;                // one allele is a prefix of the other
                 else {
-                    ed = wfa_ed_warp(a0, l0, a1, l1, wf, (scratch_ints - 3) / 2, w);
+                    ed = wfa_ed_warp<false>(plain_seq(a0, l0), plain_seq(a1, l1), hdr + ARENA_HDR, (scratch_ints - 3) / 2, hdr);
                     if (ed < 0) ed = 0;
                 }
             }
             if (lane == 0) alt_ed[vv] = (u32)ed;
         }
     }
-    flush_work(w, work_out);
+    flush_work<false>(hdr, work_out);
 }
 
 __global__ void __launch_bounds__(256) k_wfa_ed(u64 n_pairs, const u8 *pool, const u64 *a_off, const u32 *a_len,
-                                                const u64 *b_off, const u32 *b_len, u32 *ed_out, int *scratch,
+                                                const u64 *b_off, const u32 *b_len, u32 *ed_out, u8 *scratch,
                                                 int scratch_ints, u32 *counter, unsigned long long *work_out) {
     const int lane = lane_id();
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int *wf = scratch + warp * (u64)scratch_ints;
-    WorkAcc w; w.clear();
+    const u64 hdr = (u64)(uintptr_t)(scratch + warp * ((u64)scratch_ints * 4 + ARENA_HDR));
+    clear_work<false>(hdr);
     for (;;) {
         u32 p = 0;
         if (lane == 0) p = atomicAdd(counter, 1u);
         p = __shfl_sync(AVK_FULL, p, 0);
         if (p >= n_pairs) break;
-        const int ed = wfa_ed_warp(pool + a_off[p], (int)a_len[p], pool + b_off[p], (int)b_len[p], wf, (scratch_ints - 3) / 2, w);
+        const int ed = wfa_ed_warp<false>(plain_seq(pool + a_off[p], (int)a_len[p]), plain_seq(pool + b_off[p], (int)b_len[p]),
+                                          hdr + ARENA_HDR, (scratch_ints - 3) / 2, hdr);
         if (lane == 0) ed_out[p] = (u32)ed;
     }
-    flush_work(w, work_out);
+    flush_work<false>(hdr, work_out);
 }
 
 __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const DevCompareOut &out, u64 r, bool metrics_only) {
@@ -115,8 +136,6 @@ __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const Dev
     }
     __syncwarp();
 }
-
-extern __shared__ __align__(128) u8 avk_dyn_smem[];
 
 // Work distribution of one workspace tier.  ctrs[0] = work counter of this launch, ctrs[1] = number of
 // clusters that did not fit (appended to fail_list, re-run by the next tier).  n_work is read from
@@ -138,33 +157,31 @@ struct TierArgs {
 // shared memory; global tiers take the clusters that do not fit.
 // Per-CTA shared state: the batch descriptor and one solver object per warp (never a local-memory frame).
 template <bool SMEM>
-__device__ __forceinline__ RegionSolver &init_solver(const DevBatch &b, const TierArgs &t, DevBatch &sb, RegionSolver *sol) {
+__device__ __forceinline__ RegionSolver<SMEM> &init_solver(const DevBatch &b, const TierArgs &t, DevBatch &sb, RegionSolver<SMEM> *sol) {
+    typedef typename Mem<SMEM>::addr addr;
     if (threadIdx.x == 0) sb = b;
     __syncthreads();
-    RegionSolver &s = sol[threadIdx.x >> 5];
+    RegionSolver<SMEM> &s = sol[threadIdx.x >> 5];
+    addr arena;
+    if (SMEM) arena = (addr)((threadIdx.x >> 5) * (u32)t.arena_bytes);
+    else arena = (addr)(uintptr_t)(t.arena_base + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (u64)t.arena_bytes);
     if (lane_id() == 0) {
         s.bp = &sb;
-        s.work.clear();
         s.tma_phase = 0;
-        s.stage = SMEM;
-        s.arena_bytes = t.arena_bytes;
-        if (SMEM) {
-            s.arena = avk_dyn_smem + (threadIdx.x >> 5) * t.arena_bytes;
-            mbar_init((u64 *)s.arena);
-        } else {
-            s.arena = t.arena_base + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (u64)t.arena_bytes;
-        }
+        s.arena_bytes = (u32)t.arena_bytes;
+        s.arena = arena;
+        if (SMEM) mbar_init((u32)arena);
     }
-    __syncwarp();
+    clear_work<SMEM>(arena);
     return s;
 }
 
 template <bool SMEM, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, TierArgs t) {
     __shared__ DevBatch sb;
-    __shared__ RegionSolver sol[8];
+    __shared__ RegionSolver<SMEM> sol[8];
     const int lane = lane_id();
-    RegionSolver &s = init_solver<SMEM>(b, t, sb, sol);
+    RegionSolver<SMEM> &s = init_solver<SMEM>(b, t, sb, sol);
     const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
     for (;;) {
         u32 idx = 0;
@@ -184,15 +201,15 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompar
         if (rc != AVK_ST_OK) zero_region_outputs(sb, out, r, false);
         if (lane == 0) out.status[r] = rc;
     }
-    flush_work(s.work, t.work_out);
+    flush_work<SMEM>(s.arena, t.work_out);
 }
 
 template <bool SMEM, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS) k_merge(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, TierArgs t) {
     __shared__ DevBatch sb;
-    __shared__ RegionSolver sol[8];
+    __shared__ RegionSolver<SMEM> sol[8];
     const int lane = lane_id();
-    RegionSolver &s = init_solver<SMEM>(b, t, sb, sol);
+    RegionSolver<SMEM> &s = init_solver<SMEM>(b, t, sb, sol);
     const u32 K = b.n_inputs;
     const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
     for (;;) {
@@ -218,7 +235,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_merge(DevBatch b, DevMergeOut
             }
         }
     }
-    flush_work(s.work, t.work_out);
+    flush_work<SMEM>(s.arena, t.work_out);
 }
 
 // SummaryWriter::add_comparison_benchmark (writers/summary.rs:146-158): thread j sums column j of the
@@ -443,9 +460,9 @@ static int run_alt_ed(avk_ctx *ctx, const DevBatch &db) {
     if (ctx->n_variants == 0) return AVK_OK;
     const int blocks = ctx->sm_count * 4, threads = 256;
     const int warps = blocks * threads / 32;
-    const int scratch_ints = 2 * (int)ctx->max_allele + 8;
-    ENSURE(ctx->scratch, (size_t)warps * scratch_ints * 4);
-    k_alt_ed<<<blocks, threads, 0, ctx->stream>>>(db, ctx->n_variants, (u32 *)ctx->alt_ed.p, (int *)ctx->scratch.p, scratch_ints,
+    const int scratch_ints = (2 * (int)ctx->max_allele + 8 + 3) / 4 * 4;
+    ENSURE(ctx->scratch, (size_t)warps * ((size_t)scratch_ints * 4 + ARENA_HDR));
+    k_alt_ed<<<blocks, threads, 0, ctx->stream>>>(db, ctx->n_variants, (u32 *)ctx->alt_ed.p, (u8 *)ctx->scratch.p, scratch_ints,
                                                    (unsigned long long *)ctx->work_ctr.p);
     ctx->launches += 1;
     CK(cudaGetLastError());
@@ -473,7 +490,9 @@ static int run_tiers(avk_ctx *ctx, u64 n, F launch) {
     u32 *ctrs = (u32 *)ctx->counters.p;
     CK(cudaMemsetAsync(ctrs, 0, 256, ctx->stream));
     u32 *fail_lists[2] = {(u32 *)ctx->fail_a.p, (u32 *)ctx->fail_b.p};
-    const LaunchCfg chain[3] = {{true, 3, 8192, sm * 3}, {true, 1, 27648, sm}, {false, 1, 2LL << 20, sm}};
+    const char *env_ctas = getenv("AVK_S0_CTAS_PER_SM");   // tuning knob (default 3)
+    const int s0_ctas = env_ctas ? atoi(env_ctas) : 3;
+    const LaunchCfg chain[3] = {{true, 3, 8192, sm * s0_ctas}, {true, 1, 27648, sm}, {false, 1, 2LL << 20, sm}};
     ENSURE(ctx->arena, (size_t)chain[2].ctas * 8 * (size_t)chain[2].arena_bytes);
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     for (int t = 0; t < 3; ++t) {
@@ -803,15 +822,15 @@ extern "C" int avk_wfa_ed_batch(avk_ctx *ctx, uint64_t n_pairs, const uint8_t *p
     ENSURE(ctx->counters, 64); ENSURE(ctx->work_ctr, 64);
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
-    const int scratch_ints = 2 * (int)mx + 8;
+    const int scratch_ints = (2 * (int)mx + 8 + 3) / 4 * 4;
     int warps = (int)std::min<u64>((u64)ctx->sm_count * 32, (n_pairs + 7) / 8 * 8);
     warps = (warps + 7) / 8 * 8;
-    ENSURE(ctx->scratch, (size_t)warps * scratch_ints * 4);
+    ENSURE(ctx->scratch, (size_t)warps * ((size_t)scratch_ints * 4 + ARENA_HDR));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     k_wfa_ed<<<warps / 8, 256, 0, ctx->stream>>>(n_pairs, (const u8 *)ctx->pair_pool.p, (const u64 *)ctx->pair_a_off.p,
                                                   (const u32 *)ctx->pair_a_len.p, (const u64 *)ctx->pair_b_off.p,
-                                                  (const u32 *)ctx->pair_b_len.p, (u32 *)ctx->pair_ed.p, (int *)ctx->scratch.p,
+                                                  (const u32 *)ctx->pair_b_len.p, (u32 *)ctx->pair_ed.p, (u8 *)ctx->scratch.p,
                                                   scratch_ints, (u32 *)ctx->counters.p, (unsigned long long *)ctx->work_ctr.p);
     ctx->launches += 1;
     CK(cudaGetLastError());

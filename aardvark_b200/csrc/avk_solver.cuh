@@ -7,18 +7,18 @@
 //                                     add_record_basepair_stats :455-522, generate_allele_sequence :726-778
 //   RegionSolver::solve_merge()    <- solve_merge_region      src/merge_solver.rs:110-223
 //
-// The sequential best-first searches of the reference are replayed exactly: the same
-// (unique) priority keys, the same node-id assignment, the same quotas and prunes, so the
-// same equal-cost solution is reported.  What differs is the machine mapping: a warp keeps
-// the whole problem of one cluster in a private workspace ("arena": shared memory in the
-// common tiers, global memory for the rare oversized cluster):
+// The sequential best-first searches of the reference are replayed exactly: the same (unique)
+// priority keys, the same node-id assignment, the same quotas and prunes, so the same equal-cost
+// solution is reported.  What differs is the machine mapping: a warp keeps the whole problem of one
+// cluster in a private workspace ("arena": shared memory in the common tiers, global memory for the
+// rare oversized cluster):
 //   * the reference window, staged once with a TMA bulk copy,
 //   * the cluster's variants in merged processing order and their allele bytes,
-//   * the search nodes (haplotype sequences + wavefronts), the key array of the queue,
+//   * the search nodes (materialised haplotype prefixes + wavefronts) and the key array of the queue,
 //   * the metric rows being accumulated.
-// Pops are a warp-wide scan + REDUX min over the unsorted key array, clones are warp-wide
-// copies, scoring is the warp-cooperative DWFA of avk_device.cuh.  The solver object itself
-// lives in shared memory (one per warp), never in a local-memory stack frame.
+// Pops are a warp-wide scan + REDUX min over the unsorted key array, clones are warp-wide copies,
+// scoring is the warp-cooperative DWFA of avk_device.cuh over virtual sequences.  The solver object
+// lives in shared memory (one per warp); all arena accesses use Mem<SMEM> addresses.
 #pragma once
 #include "avk_device.cuh"
 #include "../../include/aardvark_b200.h"
@@ -62,205 +62,216 @@ enum { SOLVE_OK = 0, SOLVE_WORKSPACE = -1 };   // internal; positive values are 
 
 __device__ __forceinline__ int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-struct HapState {   // HaplotypeDWFA scalars (haplotype_dwfa.rs:17-24,145-154)
-    int t_ref_pos, q_ref_pos, t_len, q_len, t_skip, q_skip, ed, pad;
-};
-
-// One variant of the cluster, in merged processing order (order_variants, query_optimizer.rs:372-381).
-struct VInfo {
-    u32 pos, l0, l1;
-    u32 aoff;      // offset of allele0 in alle_base (allele1 follows it)
-    u32 alt_ed;    // ED(allele0, allele1)  (variants.rs:413-415)
-    u32 raw;       // raw_allele_space
-    u32 gv;        // index in the batch variant table
-    u8 type, zyg, is_truth, slot;   // slot = metric-row slot of this variant's type
-};
+// One variant of the cluster in merged processing order (order_variants, query_optimizer.rs:372-381):
+// 32-byte record in the arena.
+enum { VI_POS = 0, VI_L0 = 4, VI_L1 = 8, VI_AOFF = 12, VI_ALTED = 16, VI_RAW = 20, VI_GV = 24, VI_FLAGS = 28, VI_SIZE = 32 };
+// flags: type | zyg << 8 | is_truth << 16 | slot << 24
+// optimize node: ints {id, depth, hap0[9], hap1[9]}; hap = {t_ref_pos, q_ref_pos, t_mlen, q_mlen, t_mref, q_mref, t_skip, q_skip, ed}
+enum { ON_ID = 0, ON_DEPTH = 4, ON_HAP = 8, ON_HAPSZ = 36, ON_HDR = 80 };
+enum { H_TRP = 0, H_QRP = 4, H_TML = 8, H_QML = 12, H_TMR = 16, H_QMR = 20, H_TSK = 24, H_QSK = 28, H_ED = 32 };
+// exact node: ints {id, errors, depth, t_ref_pos, q_ref_pos, t_mlen, q_mlen, t_mref, q_mref, d}
+enum { XN_ID = 0, XN_ERR = 4, XN_DEPTH = 8, XN_TRP = 12, XN_QRP = 16, XN_TML = 20, XN_QML = 24, XN_TMR = 28, XN_QMR = 32, XN_D = 36, XN_HDR = 48 };
+// sequence descriptors written by build_hap_seq: {mlen, cur, failed, n_alt}
+enum { SD_MLEN = 0, SD_CUR = 4, SD_FAILED = 8, SD_NALT = 12, SD_SIZE = 16 };
 
 static __device__ __forceinline__ bool type_supported(int t) {   // SUPPORTED_VARIANT_TYPES waffle_solver.rs:82-91
     return t == AVK_VT_SNV || t == AVK_VT_INSERTION || t == AVK_VT_DELETION || t == AVK_VT_INDEL ||
            t == AVK_VT_TR_CONTRACTION || t == AVK_VT_TR_EXPANSION || t == AVK_VT_SV_DELETION || t == AVK_VT_SV_INSERTION;
 }
 
+template <bool SMEM>
 struct RegionSolver {
+    typedef Mem<SMEM> M;
+    typedef typename M::addr addr;
+    typedef VSeq<SMEM> VS;
+
     // ---- problem (warp-uniform) ----
     const DevBatch *bp;
-    WorkAcc work;
-    const u8 *ref;        // ref[pos] addresses absolute contig positions (staged window or global contig)
-    const u8 *alle_base;  // allele bytes (staged copy or the global pool)
+    addr arena;           // this warp's workspace (shared-memory offset or global address)
+    u32 arena_bytes;
+    addr ref_base;        // byte of absolute contig position p is at ref_base + p (staged window or global contig)
+    addr alle_base;       // allele bytes (staged copy or the global pool)
     int start, end;       // region window
     int nv[2];
     int N;
     int mbf;
-    bool stage;           // shared-memory tier: stage window + alleles into the arena
-    // ---- arena ----
-    u8 *arena;
-    long long arena_bytes;
-    VInfo *vinfo;         // [N]
-    int *bucket;          // [N+1]
-    u8 *res_alle;         // [res_cap][Npad] bit0 hap1 ALT, bit1 hap2 ALT (by order index)
-    int *res_num;         // [res_cap][6] ed1 ed2 tvs1 tvs2 qvs1 qvs2
-    u8 *hap_alle;         // [Npad] input alleles of exact_gt by order index
-    u8 *cur_obs;          // [2][Npad]
-    u8 *best_obs;         // [2][Npad]
-    u64 *mrows;           // [1 + n_slots][22] metric rows: joint, then one per distinct variant type
-    u32 *slot_cnt;        // [n_slots][2] number of truth / query variants of that type
-    u64 *slot_tot;        // [n_slots][2] zygosity-weighted raw allele space of that type (RECORD_BP)
-    u8 slot_type[AVK_N_VARIANT_TYPES];
-    int n_slots;
-    u8 *dyn;              // start of the re-partitionable part
-    long long dyn_bytes;
-    int Npad, seq_cap, wf_cap;
-    int n_res, res_cap;
-    int region_off;       // first arena byte after the mbarrier (+ staged window)
     u32 tma_phase;        // mbarrier parity of the next window load
-    // queue + slots (partitioned per phase)
-    u64 *qkeys;
-    u32 *qslot;
-    u32 *freel;
-    u8 *nodes;
+    // ---- arena layout ----
+    addr vinfo;           // [N] VI_* records
+    addr bucket;          // [N+1] int
+    addr res_alle;        // [res_cap][Npad] bit0 hap1 ALT, bit1 hap2 ALT (by order index)
+    addr res_num;         // [res_cap][6] int: ed1 ed2 tvs1 tvs2 qvs1 qvs2
+    addr hap_alle;        // [Npad] input alleles of exact_gt by order index
+    addr cur_obs;         // [2][Npad]
+    addr best_obs;        // [2][Npad]
+    addr mrows;           // [1 + n_slots][22] u64 metric rows: joint, then one per distinct variant type
+    addr slot_cnt;        // [n_slots][2] u32 number of truth / query variants of that type
+    addr slot_tot;        // [n_slots][2] u64 zygosity-weighted raw allele space of that type (RECORD_BP)
+    addr sdesc;           // [3] SD_* sequence descriptors (T, Q, F)
+    addr dyn;             // start of the re-partitionable part
+    u32 dyn_bytes;
+    int Npad, seq_cap, wf_cap;
+    int n_res, res_cap, n_slots;
+    int region_off;       // first arena byte after the header (+ staged window)
+    int ed_overflow;
+    u8 slot_type[AVK_N_VARIANT_TYPES];
+    // queue + node slots (partitioned per phase)
+    addr qkeys, qslot, freel, nodes;
     int stride, max_slots, qn, nfree;
 
     // ------------------------------------------------------------------ helpers
+    __device__ __forceinline__ addr vi(int oi) const { return vinfo + (u32)(VI_SIZE * oi); }
     __device__ __forceinline__ int sync_pos(int oi) const {   // query_optimizer.rs:258-265
-        return (oi == N - 1) ? end : (int)vinfo[oi + 1].pos;
+        return (oi == N - 1) ? end : (int)LD32(vi(oi + 1) + VI_POS);
     }
+    __device__ __forceinline__ addr wk() const { return arena; }   // work counters live in the arena header
 
-    // Start of a region: in shared-memory tiers the reference window is staged into the arena with a
-    // TMA bulk copy (cp.async.bulk, 16-byte aligned superset of [start, end)), and `ref` is rebased so
-    // that ref[pos] still addresses absolute contig positions.  Bytes [0,16) of the arena hold the
-    // warp's mbarrier and are never touched by generic stores.
+    // Start of a region: in shared-memory tiers the reference window is staged into the arena with a TMA
+    // bulk copy (cp.async.bulk, 16-byte aligned superset of [start, end)), and ref_base is set so that
+    // ref_base + pos still addresses absolute contig positions.
     __device__ __noinline__ bool begin_region(const u8 *contig) {
-        region_off = 16;
-        ref = contig;
-        if (!stage) return true;
+        region_off = ARENA_HDR;
+        if (!SMEM) { ref_base = (addr)(uintptr_t)contig; return true; }
         const int a0 = start & ~15;
         const int bytes = align_up(end - a0 + 16, 16);        // >= 16 bytes of slack for ld4u
-        if (16LL + bytes + 2048 > arena_bytes) return false;
-        u8 *win = arena + 16;
-        tma_window_load(win, contig + a0, (u32)bytes, (u64 *)arena, tma_phase);
-        ref = win - a0;
-        region_off = 16 + bytes;
+        if ((u32)(ARENA_HDR + bytes + 2048) > arena_bytes) return false;
+        tma_window_load((u32)arena + ARENA_HDR, contig + a0, (u32)bytes, (u32)arena, &tma_phase);
+        ref_base = arena + ARENA_HDR - (u32)a0;
+        region_off = ARENA_HDR + bytes;
         return true;
     }
 
     // per-lane partial validation of one variant list (same rules as the oracle's list_valid)
-    __device__ __noinline__ bool validate_list(u64 v0, int n, int &sum_l1, int &b0, int &sum_alle) const {
+    __device__ __noinline__ bool validate_list(u64 v0, int n, int *sums) const {
         const DevBatch &b = *bp;
         bool invalid = false;
-        #pragma unroll 1
+        int s_l1 = 0, s_b0 = 0, s_al = 0, mx = 0;
+#pragma unroll 1
         for (int i = lane_id(); i < n; i += 32) {
             const u64 gv = v0 + i;
             const u32 l0 = b.l0[gv], l1 = b.l1[gv], p = b.pos[gv];
             invalid = invalid || l0 == 0 || l1 == 0 || b.vtype[gv] >= AVK_N_VARIANT_TYPES || b.zyg[gv] > AVK_ZYG_HOM_ALT;
             invalid = invalid || (long long)p < start || (long long)p + l0 > (long long)end;
             if (i > 0) invalid = invalid || b.pos[gv - 1] > p;
-            sum_l1 += (int)min(l1, 1u << 24);
-            b0 += (int)min(max(l0, l1), 1u << 24);
-            sum_alle += (int)min(l0, 1u << 24) + (int)min(l1, 1u << 24);
+            s_l1 += (int)min(l1, 1u << 24);
+            s_b0 += (int)min(max(l0, l1), 1u << 24);
+            s_al += (int)min(l0, 1u << 24) + (int)min(l1, 1u << 24);
+            mx = max(mx, (int)min(p + l0, 0x7fffffffu));
         }
+        sums[0] += s_l1; sums[1] += s_b0; sums[2] += s_al; sums[3] = max(sums[3], mx);
         return invalid;
     }
 
-    // Validate and load one (truth list, query list) pair of region r: lays out the arena, fills vinfo
-    // in merged order, stages the allele bytes, assigns metric-row slots.
-    __device__ __noinline__ int setup_pair(u64 r, u32 ki, u32 kj, bool want_metrics, bool &bad) {
+    // Validate and load one (truth list, query list) pair of region r: lays out the arena, fills the
+    // variant records in merged order, stages the allele bytes, assigns metric-row slots.
+    __device__ __noinline__ int setup_pair(u64 r, u32 ki, u32 kj, bool want_metrics) {
         const DevBatch &b = *bp;
         const int lane = lane_id();
         const u32 K = b.n_inputs;
         const u64 v0[2] = {b.var_off[r * K + ki], b.var_off[r * K + kj]};
-        nv[0] = (int)(b.var_off[r * K + ki + 1] - v0[0]);
-        nv[1] = (int)(b.var_off[r * K + kj + 1] - v0[1]);
-        N = nv[0] + nv[1];
-        int sum_l1 = 0, b0 = 0, sum_alle = 0;
-        bool invalid = false;
-        #pragma unroll 1
-        for (int side = 0; side < 2; ++side) invalid = validate_list(v0[side], nv[side], sum_l1, b0, sum_alle) || invalid;
-        bad = __any_sync(AVK_FULL, invalid);
-        if (bad) return SOLVE_OK;
-        sum_l1 = __reduce_add_sync(AVK_FULL, sum_l1);
-        b0 = __reduce_add_sync(AVK_FULL, b0);
-        sum_alle = __reduce_add_sync(AVK_FULL, sum_alle);
+        const int n0 = (int)(b.var_off[r * K + ki + 1] - v0[0]), n1 = (int)(b.var_off[r * K + kj + 1] - v0[1]);
+        nv[0] = n0; nv[1] = n1;
+        const int n = n0 + n1;
+        N = n;
+        int sums[4] = {0, 0, 0, start};
+        bool invalid = validate_list(v0[0], n0, sums);
+        invalid = validate_list(v0[1], n1, sums) || invalid;
+        if (__any_sync(AVK_FULL, invalid)) return AVK_ST_BAD_INPUT;
+        const int sum_l1 = __reduce_add_sync(AVK_FULL, sums[0]);
+        const int b0 = __reduce_add_sync(AVK_FULL, sums[1]);
+        const int sum_alle = __reduce_add_sync(AVK_FULL, sums[2]);
+        const int max_end = __reduce_max_sync(AVK_FULL, sums[3]);
 
         // ---- layout of the fixed part
-        const int W = end - start;
-        Npad = align_up(max(N, 1), 16);
-        seq_cap = align_up(W + sum_l1 + 16, 16);
+        const int npad = align_up(max(n, 1), 16);
+        Npad = npad;
+        seq_cap = align_up((max_end - start) + sum_l1 + 16, 16);   // materialised prefix: up to the last variant end + all ALTs
         wf_cap = align_up(2 * b0 + 3, 4);
         // room for equal-best results: all of them (<= max_branch_factor) when the arena is large,
         // a handful in the small shared-memory tiers (more than that escalates to the next tier)
-        res_cap = (arena_bytes >= (256 << 10)) ? mbf : min(mbf, 8);
-        long long off = region_off;
-        vinfo = (VInfo *)(arena + off); off += (long long)sizeof(VInfo) * max(N, 1);
-        u8 *alle_buf = arena + off;
-        if (stage) off += align_up(sum_alle + 16, 16);
-        bucket = (int *)(arena + off); off += align_up(4 * (N + 1), 16);
-        res_alle = arena + off; off += (long long)res_cap * Npad;
-        res_num = (int *)(arena + off); off += align_up(res_cap * 6 * 4, 16);
-        hap_alle = arena + off; off += Npad;
-        cur_obs = arena + off; off += 2 * Npad;
-        best_obs = arena + off; off += 2 * Npad;
+        const int rcap = (arena_bytes >= (256u << 10)) ? mbf : min(mbf, 8);
+        res_cap = rcap;
+        u32 off = (u32)region_off;
+        vinfo = arena + off; off += (u32)(VI_SIZE * max(n, 1));
+        const addr alle_buf = arena + off;
+        if (SMEM) off += (u32)align_up(sum_alle + 16, 16);
+        bucket = arena + off; off += (u32)align_up(4 * (n + 1), 16);
+        res_alle = arena + off; off += (u32)(rcap * npad);
+        res_num = arena + off; off += (u32)align_up(rcap * 24, 16);
+        hap_alle = arena + off; off += (u32)npad;
+        cur_obs = arena + off; off += (u32)(2 * npad);
+        best_obs = arena + off; off += (u32)(2 * npad);
+        sdesc = arena + off; off += 3 * SD_SIZE;
         if (off + 1024 > arena_bytes) return SOLVE_WORKSPACE;
 
         // ---- merged order: stable, truth before query on equal positions
-        #pragma unroll 1
+#pragma unroll 1
         for (int side = 0; side < 2; ++side) {
-            const int other = side ^ 1;
-            #pragma unroll 1
-            for (int i = lane; i < nv[side]; i += 32) {
-                const u64 gv = v0[side] + i;
+            const int nm = side ? n1 : n0, no = side ? n0 : n1;
+            const u64 vm = v0[side], vo = v0[side ^ 1];
+#pragma unroll 1
+            for (int i = lane; i < nm; i += 32) {
+                const u64 gv = vm + i;
                 const u32 p = b.pos[gv];
-                int lo = 0, hi = nv[other];
-                #pragma unroll 1
+                int lo = 0, hi = no;
+#pragma unroll 1
                 while (lo < hi) {
                     const int m = (lo + hi) >> 1;
-                    const u32 pm = b.pos[v0[other] + m];
+                    const u32 pm = b.pos[vo + m];
                     const bool before = side == 0 ? (pm < p) : (pm <= p);
                     if (before) lo = m + 1; else hi = m;
                 }
-                VInfo v;
-                v.pos = p; v.l0 = b.l0[gv]; v.l1 = b.l1[gv]; v.aoff = b.aoff[gv]; v.alt_ed = b.alt_ed[gv]; v.raw = b.raw[gv];
-                v.gv = (u32)gv; v.type = b.vtype[gv]; v.zyg = b.zyg[gv]; v.is_truth = side == 0; v.slot = 0;
-                vinfo[i + lo] = v;
+                const addr rec = vi(i + lo);
+                ST32(rec + VI_POS, p); ST32(rec + VI_L0, b.l0[gv]); ST32(rec + VI_L1, b.l1[gv]); ST32(rec + VI_AOFF, b.aoff[gv]);
+                ST32(rec + VI_ALTED, b.alt_ed[gv]); ST32(rec + VI_RAW, b.raw[gv]); ST32(rec + VI_GV, (u32)gv);
+                ST32(rec + VI_FLAGS, (u32)b.vtype[gv] | ((u32)b.zyg[gv] << 8) | ((side == 0 ? 1u : 0u) << 16));
             }
         }
         __syncwarp();
-        // ---- stage allele bytes (shared-memory tiers) and assign metric-row slots
-        alle_base = b.pool;
-        if (stage) {
+        // ---- stage allele bytes (shared-memory tiers)
+        alle_base = (addr)(uintptr_t)b.pool;
+        if (SMEM) {
             int acc = 0;
-            #pragma unroll 1
-            for (int oi = 0; oi < N; ++oi) {
-                const int n = (int)(vinfo[oi].l0 + vinfo[oi].l1);
-                warp_copy(alle_buf + acc, b.pool + vinfo[oi].aoff, n);
+#pragma unroll 1
+            for (int oi = 0; oi < n; ++oi) {
+                const int na = (int)(LD32(vi(oi) + VI_L0) + LD32(vi(oi) + VI_L1));
+                const u8 *src = b.pool + LD32(vi(oi) + VI_AOFF);
+#pragma unroll 1
+                for (int i = lane; i < na; i += 32) ST8(alle_buf + acc + i, src[i]);
                 __syncwarp();
-                if (lane == 0) vinfo[oi].aoff = (u32)acc;
-                acc += n;
+                if (lane == 0) ST32(vi(oi) + VI_AOFF, acc);
+                acc += na;
             }
             alle_base = alle_buf;
         }
-        n_slots = 0;
+        int ns = 0;
         if (want_metrics) {
             u32 seen = 0;
-            #pragma unroll 1
-            for (int oi = 0; oi < N; ++oi) seen |= 1u << vinfo[oi].type;
-            n_slots = __popc(seen);
+#pragma unroll 1
+            for (int oi = 0; oi < n; ++oi) seen |= 1u << (LD32(vi(oi) + VI_FLAGS) & 0xff);
+            ns = __popc(seen);
             if (lane == 0) {
                 int k = 0;
-                #pragma unroll 1
+#pragma unroll 1
                 for (int t = 0; t < AVK_N_VARIANT_TYPES; ++t) if (seen & (1u << t)) slot_type[k++] = (u8)t;
-                #pragma unroll 1
-                for (int oi = 0; oi < N; ++oi) vinfo[oi].slot = (u8)__popc(seen & ((1u << vinfo[oi].type) - 1));
             }
-            mrows = (u64 *)(arena + ((off + 7) / 8 * 8)); off = (off + 7) / 8 * 8 + 8LL * AVK_N_METRICS * (1 + n_slots);
-            slot_tot = (u64 *)(arena + off); off += 16LL * max(n_slots, 1);
-            slot_cnt = (u32 *)(arena + off); off += 16LL * max(n_slots, 1);
+#pragma unroll 1
+            for (int oi = lane; oi < n; oi += 32) {
+                const u32 f = LD32(vi(oi) + VI_FLAGS);
+                ST32(vi(oi) + VI_FLAGS, f | ((u32)__popc(seen & ((1u << (f & 0xff)) - 1)) << 24));
+            }
+            off = (off + 7u) & ~7u;
+            mrows = arena + off; off += (u32)(8 * AVK_N_METRICS * (1 + ns));
+            slot_tot = arena + off; off += (u32)(16 * max(ns, 1));
+            slot_cnt = arena + off; off += (u32)(16 * max(ns, 1));
             if (off + 512 > arena_bytes) return SOLVE_WORKSPACE;
-            #pragma unroll 1
-            for (int i = lane; i < AVK_N_METRICS * (1 + n_slots); i += 32) mrows[i] = 0;
-            #pragma unroll 1
-            for (int i = lane; i < 2 * n_slots; i += 32) { slot_cnt[i] = 0; slot_tot[i] = 0; }
+#pragma unroll 1
+            for (int i = lane; i < AVK_N_METRICS * (1 + ns); i += 32) ST64(mrows + 8 * i, 0);
+#pragma unroll 1
+            for (int i = lane; i < 2 * ns; i += 32) { ST32(slot_cnt + 4 * i, 0); ST64(slot_tot + 8 * i, 0); }
         }
-        off = (off + 15) / 16 * 16;
+        n_slots = ns;
+        off = (off + 15u) & ~15u;
         dyn = arena + off;
         dyn_bytes = arena_bytes - off;
         __syncwarp();
@@ -270,416 +281,400 @@ struct RegionSolver {
     // Partition the dynamic part into queue arrays + node slots of `stride_` bytes.
     __device__ __noinline__ bool partition(int stride_, int min_slots) {
         stride = stride_;
-        int ms = (int)min(dyn_bytes / (stride + 16), 60000LL);
+        int ms = (int)min(dyn_bytes / (u32)(stride_ + 16), 60000u);
         if (ms < min_slots) return false;
-        long long off = 0;
-        qkeys = (u64 *)(dyn + off); off += (long long)ms * 8;
-        qslot = (u32 *)(dyn + off); off += (long long)ms * 4;
-        freel = (u32 *)(dyn + off); off += (long long)ms * 4;
-        off = (off + 15) / 16 * 16;
-        if (off + (long long)ms * stride > dyn_bytes) ms = (int)((dyn_bytes - off) / stride);
+        u32 off = 0;
+        qkeys = dyn + off; off += (u32)ms * 8;
+        qslot = dyn + off; off += (u32)ms * 4;
+        freel = dyn + off; off += (u32)ms * 4;
+        off = (off + 15u) & ~15u;
+        if (off + (u32)ms * (u32)stride_ > dyn_bytes) ms = (int)((dyn_bytes - off) / (u32)stride_);
         if (ms < min_slots) return false;
         max_slots = ms;
         nodes = dyn + off;
-        #pragma unroll 1
-        for (int i = lane_id(); i < ms; i += 32) freel[i] = (u32)(ms - 1 - i);
+#pragma unroll 1
+        for (int i = lane_id(); i < ms; i += 32) ST32(freel + 4 * i, ms - 1 - i);
         nfree = ms;
         qn = 0;
         __syncwarp();
         return true;
     }
+    __device__ __forceinline__ addr node(int s) const { return nodes + (u32)s * (u32)stride; }
     __device__ __forceinline__ int alloc_slot() {   // warp-uniform; -1 when exhausted
-        if (nfree == 0) return -1;
-        nfree -= 1;
-        return (int)freel[nfree];
+        const int nf = nfree;
+        if (nf == 0) return -1;
+        nfree = nf - 1;
+        return (int)LD32(freel + 4 * (nf - 1));
     }
     __device__ __forceinline__ void free_slot(int s) {
-        if (lane_id() == 0) freel[nfree] = (u32)s;
-        nfree += 1;
+        const int nf = nfree;
+        if (lane_id() == 0) ST32(freel + 4 * nf, s);
+        nfree = nf + 1;
         __syncwarp();
     }
     __device__ __forceinline__ void push(u64 key, int slot) {
-        if (lane_id() == 0) { qkeys[qn] = key; qslot[qn] = (u32)slot; }
-        qn += 1;
+        const int n = qn;
+        if (lane_id() == 0) { ST64(qkeys + 8 * n, key); ST32(qslot + 4 * n, slot); }
+        qn = n + 1;
         __syncwarp();
     }
     // pop the minimum key: warp-parallel scan, then two REDUX min-reductions (high word, low word)
     // and a ballot to locate the owner -- keys are unique, so exactly one lane matches.
-    __device__ __noinline__ int pop(u64 &key_out) {
+    __device__ __noinline__ int pop(u32 *key_hi) {
         const int lane = lane_id();
         const int n = qn;
         u64 best = ~0ull;
         int bi = 0;
-        #pragma unroll 1
-        for (int i = lane; i < n; i += 32) { const u64 k = qkeys[i]; if (k < best) { best = k; bi = i; } }
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) { const u64 k = LD64(qkeys + 8 * i); if (k < best) { best = k; bi = i; } }
         const u32 hi = (u32)(best >> 32), lo = (u32)best;
         const u32 mhi = __reduce_min_sync(AVK_FULL, hi);
         const u32 mlo = __reduce_min_sync(AVK_FULL, hi == mhi ? lo : 0xffffffffu);
         const int owner = __ffs(__ballot_sync(AVK_FULL, hi == mhi && lo == mlo)) - 1;
         bi = __shfl_sync(AVK_FULL, bi, owner);
-        const int slot = (int)qslot[bi];
+        const int slot = (int)LD32(qslot + 4 * bi);
         __syncwarp();
-        if (lane == 0) { qkeys[bi] = qkeys[n - 1]; qslot[bi] = qslot[n - 1]; }
+        if (lane == 0) { ST64(qkeys + 8 * bi, LD64(qkeys + 8 * (n - 1))); ST32(qslot + 4 * bi, LD32(qslot + 4 * (n - 1))); }
         qn = n - 1;
         __syncwarp();
-        key_out = ((u64)mhi << 32) | mlo;
+        *key_hi = mhi;
         return slot;
     }
 
-    // ------------------------------------------------------------------ tracker ops
-    // copy_reference(): haplotype_dwfa.rs:218-227
-    __device__ __forceinline__ bool copy_ref(u8 *seq, int &len, int &ref_pos, int to) {
-        if (ref_pos < to) {
-            const int n = to - ref_pos;
-            if (len + n > seq_cap) return false;
-            warp_copy(seq + len, ref + ref_pos, n);
-            len += n;
-            ref_pos = to;
-        }
-        return true;
-    }
-    // HaplotypeTracker::extend_variant(): haplotype_dwfa.rs:175-212.  false on capacity overflow.
-    __device__ __noinline__ bool track_variant(u8 *seq, int &len, int &ref_pos, int &skip, const VInfo &v, bool alt, int sync,
-                                                  bool &success) {
-        const int vpos = (int)v.pos;
-        if (!copy_ref(seq, len, ref_pos, vpos)) return false;
-        success = true;
+    // ------------------------------------------------------------------ tracker
+    // HaplotypeTracker::extend_variant() (haplotype_dwfa.rs:175-212) on one side of one haplotype.
+    // copy_reference (:218-227) only moves ref_pos; bytes are materialised when an ALT is spliced.
+    // returns 1 success / 0 incompatible (skipped) / -1 capacity overflow
+    __device__ __forceinline__ int track(addr data, int &ref_pos, int &mlen, int &mref, int &skip, addr rec, bool alt, int sync) {
+        const int vpos = (int)LD32(rec + VI_POS);
+        if (ref_pos < vpos) ref_pos = vpos;
+        int success = 1;
         if (alt) {
             if (ref_pos <= vpos) {
-                const int l1 = (int)v.l1;
-                if (len + l1 > seq_cap) return false;
-                warp_copy(seq + len, alle_base + v.aoff + v.l0, l1);
-                len += l1;
-                ref_pos = vpos + (int)v.l0;
+                const int l0 = (int)LD32(rec + VI_L0), l1 = (int)LD32(rec + VI_L1);
+                const int nref = vpos - mref;
+                if (mlen + nref + l1 > seq_cap) return -1;
+                if (nref > 0) warp_copy<SMEM>(data + mlen, ref_base + mref, nref);
+                warp_copy<SMEM>(data + mlen + nref, alle_base + LD32(rec + VI_AOFF) + l0, l1);
+                mlen += nref + l1;
+                ref_pos = vpos + l0;
+                mref = ref_pos;
             } else {
-                skip += (int)v.alt_ed;   // edit_distance(allele0, allele1) :199
-                success = false;
+                skip += (int)LD32(rec + VI_ALTED);   // edit_distance(allele0, allele1) :199
+                success = 0;
             }
         }
-        return copy_ref(seq, len, ref_pos, sync);
+        if (ref_pos < sync) ref_pos = sync;
+        return success;
+    }
+    __device__ __forceinline__ VS make_vs(addr data, int mlen, int mref, int ref_pos) const {
+        VS v;
+        v.data = data; v.tail = ref_base + mref; v.mlen = mlen; v.len = mlen + (ref_pos - mref);
+        return v;
     }
 
     // ================================================================== optimize_sequences
-    // node layout: int hdr[20] {id, depth, HapState h[2] (8 ints each), 2 pad}; u8 alle[Npad];
-    //              u8 seq[4][seq_cap] (h0 truth, h0 query, h1 truth, h1 query); int wf[2][wf_cap]
-    __device__ __forceinline__ int opt_stride() const { return 80 + Npad + 4 * seq_cap + 8 * wf_cap; }
-    __device__ __forceinline__ int *n_hdr(int s) const { return (int *)(nodes + (long long)s * stride); }
-    __device__ __forceinline__ u8 *n_alle(int s) const { return nodes + (long long)s * stride + 80; }
-    __device__ __forceinline__ u8 *n_seq(int s, int k) const { return nodes + (long long)s * stride + 80 + Npad + (long long)k * seq_cap; }
-    __device__ __forceinline__ int *n_wf(int s, int h) const { return (int *)(nodes + (long long)s * stride + 80 + Npad + 4LL * seq_cap) + (long long)h * wf_cap; }
+    // node: hdr[80] | alle[Npad] | seq[4][seq_cap] (h0 truth, h0 query, h1 truth, h1 query) | wf[2][wf_cap] ints
+    __device__ __forceinline__ int opt_stride() const { return ON_HDR + Npad + 4 * seq_cap + 8 * wf_cap; }
+    __device__ __forceinline__ addr n_seq(addr nb, int k) const { return nb + (u32)(ON_HDR + Npad + k * seq_cap); }
+    __device__ __forceinline__ addr n_wf(addr nb, int h) const { return nb + (u32)(ON_HDR + Npad + 4 * seq_cap + h * 4 * wf_cap); }
 
-    __device__ __noinline__ void opt_clone(int dst, int src) {
+    __device__ __noinline__ void opt_clone(addr dst, addr src) {
         const int lane = lane_id();
-        int *hs = n_hdr(src), *hd = n_hdr(dst);
-        const int depth = hs[1];
-        const int tl0 = hs[2 + 2], ql0 = hs[2 + 3], ed0 = hs[2 + 6], tl1 = hs[10 + 2], ql1 = hs[10 + 3], ed1 = hs[10 + 6];
-        if (lane < 20) hd[lane] = hs[lane];
-        warp_copy(n_alle(dst), n_alle(src), depth);
-        warp_copy(n_seq(dst, 0), n_seq(src, 0), tl0);
-        warp_copy(n_seq(dst, 1), n_seq(src, 1), ql0);
-        warp_copy(n_seq(dst, 2), n_seq(src, 2), tl1);
-        warp_copy(n_seq(dst, 3), n_seq(src, 3), ql1);
-        {
-            const int *ws = n_wf(src, 0); int *wd = n_wf(dst, 0);
-            #pragma unroll 1
-            for (int i = lane; i < 2 * ed0 + 1; i += 32) wd[i] = ws[i];
-            ws = n_wf(src, 1); wd = n_wf(dst, 1);
-            #pragma unroll 1
-            for (int i = lane; i < 2 * ed1 + 1; i += 32) wd[i] = ws[i];
+        const int depth = LDI(src + ON_DEPTH);
+        if (lane < 20) ST32(dst + 4 * lane, LD32(src + 4 * lane));
+        warp_copy<SMEM>(dst + ON_HDR, src + ON_HDR, depth);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const addr hb = src + ON_HAP + ON_HAPSZ * h;
+            warp_copy<SMEM>(n_seq(dst, 2 * h), n_seq(src, 2 * h), LDI(hb + H_TML));
+            warp_copy<SMEM>(n_seq(dst, 2 * h + 1), n_seq(src, 2 * h + 1), LDI(hb + H_QML));
+            const int nwf = 2 * LDI(hb + H_ED) + 1;
+            const addr ws = n_wf(src, h), wd = n_wf(dst, h);
+#pragma unroll 1
+            for (int i = lane; i < nwf; i += 32) ST32(wd + 4 * i, LD32(ws + 4 * i));
         }
         __syncwarp();
     }
 
-    // HaplotypeDWFA::extend_variant (haplotype_dwfa.rs:46-67) on hap h of node s.
-    __device__ __noinline__ int opt_extend_hap(int s, int h, const VInfo &v, bool alt, int sync) {
-        HapState *sp = (HapState *)(n_hdr(s) + 2 + 8 * h);
-        HapState st = *sp;
-        u8 *tseq = n_seq(s, 2 * h), *qseq = n_seq(s, 2 * h + 1);
-        bool success;
-        bool ok;
-        if (v.is_truth) {
-            ok = copy_ref(qseq, st.q_len, st.q_ref_pos, sync);
-            ok = ok && track_variant(tseq, st.t_len, st.t_ref_pos, st.t_skip, v, alt, sync, success);
+    // HaplotypeDWFA::extend_variant (haplotype_dwfa.rs:46-67) on hap h of node nb; finalize_dwfa (:84-95) when rec == 0.
+    __device__ __noinline__ int opt_extend_hap(addr nb, int h, addr rec, bool alt, int sync, bool finalize) {
+        const addr hb = nb + ON_HAP + ON_HAPSZ * h;
+        int t_rp = LDI(hb + H_TRP), q_rp = LDI(hb + H_QRP), t_ml = LDI(hb + H_TML), q_ml = LDI(hb + H_QML);
+        int t_mr = LDI(hb + H_TMR), q_mr = LDI(hb + H_QMR), t_sk = LDI(hb + H_TSK), q_sk = LDI(hb + H_QSK), ed = LDI(hb + H_ED);
+        if (finalize) {
+            t_rp = max(t_rp, end); q_rp = max(q_rp, end);
+        } else if (LD32(rec + VI_FLAGS) & 0x10000u) {   // truth variant: query first copies reference to the sync point
+            q_rp = max(q_rp, sync);
+            if (track(n_seq(nb, 2 * h), t_rp, t_ml, t_mr, t_sk, rec, alt, sync) < 0) return SOLVE_WORKSPACE;
         } else {
-            ok = copy_ref(tseq, st.t_len, st.t_ref_pos, sync);
-            ok = ok && track_variant(qseq, st.q_len, st.q_ref_pos, st.q_skip, v, alt, sync, success);
+            t_rp = max(t_rp, sync);
+            if (track(n_seq(nb, 2 * h + 1), q_rp, q_ml, q_mr, q_sk, rec, alt, sync) < 0) return SOLVE_WORKSPACE;
         }
-        if (!ok) return SOLVE_WORKSPACE;
         __syncwarp();
-        int *wf = n_wf(s, h);
-        const int rc = dwfa_update(wf, &st.ed, (wf_cap - 3) / 2, tseq, st.t_len, qseq, st.q_len, work);
-        if (rc != DWFA_OK) return SOLVE_WORKSPACE;   // ED bound exceeded: never expected (DESIGN.md)
-        if (lane_id() == 0) *sp = st;
-        __syncwarp();
-        return SOLVE_OK;
-    }
-    __device__ __noinline__ int opt_extend(int s, int oi, bool a1_alt, bool a2_alt) {   // ComparisonNode::extend_variant :443-451
-        const VInfo v = vinfo[oi];
-        const int sync = sync_pos(oi);
-        int rc = opt_extend_hap(s, 0, v, a1_alt, sync);
-        if (rc) return rc;
-        rc = opt_extend_hap(s, 1, v, a2_alt, sync);
-        if (rc) return rc;
-        if (lane_id() == 0) { n_alle(s)[oi] = (u8)((a1_alt ? 1 : 0) | (a2_alt ? 2 : 0)); n_hdr(s)[1] = oi + 1; }
-        __syncwarp();
-        return SOLVE_OK;
-    }
-    __device__ __forceinline__ u32 opt_cost(int s) const {
-        const int *h = n_hdr(s);
-        return (u32)(h[2 + 6] + h[2 + 4] + h[2 + 5] + h[10 + 6] + h[10 + 4] + h[10 + 5]);
-    }
-    __device__ __noinline__ int opt_finalize_hap(int s, int h) {   // finalize_dwfa: haplotype_dwfa.rs:84-95
-        HapState *sp = (HapState *)(n_hdr(s) + 2 + 8 * h);
-        HapState st = *sp;
-        u8 *tseq = n_seq(s, 2 * h), *qseq = n_seq(s, 2 * h + 1);
-        if (!copy_ref(tseq, st.t_len, st.t_ref_pos, end)) return SOLVE_WORKSPACE;
-        if (!copy_ref(qseq, st.q_len, st.q_ref_pos, end)) return SOLVE_WORKSPACE;
-        __syncwarp();
-        int *wf = n_wf(s, h);
+        const VS T = make_vs(n_seq(nb, 2 * h), t_ml, t_mr, t_rp), Q = make_vs(n_seq(nb, 2 * h + 1), q_ml, q_mr, q_rp);
         const int cap = (wf_cap - 3) / 2;
-        if (dwfa_update(wf, &st.ed, cap, tseq, st.t_len, qseq, st.q_len, work) != DWFA_OK) return SOLVE_WORKSPACE;
-        if (dwfa_finalize(wf, &st.ed, cap, tseq, st.t_len, qseq, st.q_len, work) != DWFA_OK) return SOLVE_WORKSPACE;
-        if (lane_id() == 0) *sp = st;
+        int rc = dwfa_run<SMEM>(n_wf(nb, h), &ed, cap, T, Q, false, wk());
+        if (rc == DWFA_OK && finalize) rc = dwfa_run<SMEM>(n_wf(nb, h), &ed, cap, T, Q, true, wk());
+        if (rc != DWFA_OK) return SOLVE_WORKSPACE;   // ED bound exceeded: never expected (DESIGN.md)
+        if (lane_id() == 0) {
+            ST32(hb + H_TRP, t_rp); ST32(hb + H_QRP, q_rp); ST32(hb + H_TML, t_ml); ST32(hb + H_QML, q_ml);
+            ST32(hb + H_TMR, t_mr); ST32(hb + H_QMR, q_mr); ST32(hb + H_TSK, t_sk); ST32(hb + H_QSK, q_sk); ST32(hb + H_ED, ed);
+            if (finalize) ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
+        }
         __syncwarp();
         return SOLVE_OK;
+    }
+    // ComparisonNode::extend_variant :443-451 followed by the push; returns the node's new cost via *cost
+    __device__ __noinline__ int opt_extend(addr nb, int oi, bool a1_alt, bool a2_alt, u32 *cost) {
+        const addr rec = vi(oi);
+        const int sync = sync_pos(oi);
+        int rc = opt_extend_hap(nb, 0, rec, a1_alt, sync, false);
+        if (rc) return rc;
+        rc = opt_extend_hap(nb, 1, rec, a2_alt, sync, false);
+        if (rc) return rc;
+        if (lane_id() == 0) { ST8(nb + ON_HDR + oi, (a1_alt ? 1 : 0) | (a2_alt ? 2 : 0)); ST32(nb + ON_DEPTH, oi + 1); }
+        __syncwarp();
+        *cost = opt_cost(nb);
+        return SOLVE_OK;
+    }
+    __device__ __forceinline__ u32 opt_cost(addr nb) const {
+        const addr h0 = nb + ON_HAP, h1 = nb + ON_HAP + ON_HAPSZ;
+        return (u32)(LDI(h0 + H_ED) + LDI(h0 + H_TSK) + LDI(h0 + H_QSK) + LDI(h1 + H_ED) + LDI(h1 + H_TSK) + LDI(h1 + H_QSK));
     }
 
-    // Runs the best-first search.  Results (all equal-best, in finalisation order) go to
-    // res_alle/res_num.  stop_at_nonzero: merge only needs "is the minimum cost zero"
-    // (merge_solver.rs:142-143); costs never decrease along a path, so the search may stop at
-    // the first popped node whose cost is > 0.
+    // Runs the best-first search.  Results (all equal-best, in finalisation order) go to res_alle/res_num.
+    // stop_at_nonzero: merge only needs "is the minimum cost zero" (merge_solver.rs:142-143); costs never
+    // decrease along a path, so the search may stop at the first popped node whose cost is > 0.
     __device__ __noinline__ int optimize(bool stop_at_nonzero) {
         const int lane = lane_id();
-        if (!partition(opt_stride(), min(N + 3, 48))) return SOLVE_WORKSPACE;   // cheap early escalation
-        #pragma unroll 1
-        for (int i = lane; i <= N; i += 32) bucket[i] = 0;
+        const int n = N;
+        if (!partition(opt_stride(), min(n + 3, 48))) return SOLVE_WORKSPACE;   // cheap early escalation
+#pragma unroll 1
+        for (int i = lane; i <= n; i += 32) ST32(bucket + 4 * i, 0);
         n_res = 0;
+        int nres = 0;
         u32 best = 0xffffffffu;
-        u32 next_id = 0;
-        {   // root (query_optimizer.rs:184-192)
+        u32 next_id = 1;
+        {   // root (query_optimizer.rs:184-192): id 0, both haplotypes at region start, wavefront [0]
             const int s = alloc_slot();
-            int *hdr = n_hdr(s);
-            if (lane < 20) hdr[lane] = (lane == 2 || lane == 3 || lane == 10 || lane == 11) ? start : 0;
-            if (lane == 0) { n_wf(s, 0)[0] = 0; n_wf(s, 1)[0] = 0; }
+            const addr nb = node(s);
+            if (lane < 20) {
+                const int k = lane - 2;   // hap field index (0..17) once past id/depth
+                const bool at_start = lane >= 2 && ((k % 9) == 0 || (k % 9) == 1 || (k % 9) == 4 || (k % 9) == 5);
+                ST32(nb + 4 * lane, at_start ? start : 0);
+            }
+            if (lane == 0) { ST32(n_wf(nb, 0), 0); ST32(n_wf(nb, 1), 0); }
             __syncwarp();
-            next_id = 1;
             push(0ull, s);
         }
-        #pragma unroll 1
+#pragma unroll 1
         while (qn > 0) {
-            u64 key;
-            const int s = pop(key);
-            work.search_pops += 1;
-            const u32 cost = (u32)(key >> 32);
-            if (stop_at_nonzero && cost > 0) return SOLVE_OK;   // nothing cheaper is left; n_res tells if a zero-cost result exists
+            u32 cost;
+            const int s = pop(&cost);
+            if (lane == 0) ST32(wk() + WK_SPOPS, LD32(wk() + WK_SPOPS) + 1);
+            if (stop_at_nonzero && cost > 0) break;        // nothing cheaper is left; n_res tells if a zero-cost result exists
             if (cost > best) { free_slot(s); continue; }                       // :204 strict
-            int *hdr = n_hdr(s);
-            const int oi = hdr[1];
-            const int bc = bucket[oi];
+            const addr nb = node(s);
+            const int oi = LDI(nb + ON_DEPTH);
+            const int bc = LDI(bucket + 4 * oi);
             if (bc >= mbf) { free_slot(s); continue; }                         // :222
-            if (lane == 0) bucket[oi] = bc + 1;
+            if (lane == 0) ST32(bucket + 4 * oi, bc + 1);
             __syncwarp();
-            if (oi == N) {                                                     // :227-247
-                int rc = opt_finalize_hap(s, 0);
+            if (oi == n) {                                                     // :227-247
+                int rc = opt_extend_hap(nb, 0, 0, false, 0, true);
                 if (rc) return rc;
-                rc = opt_finalize_hap(s, 1);
+                rc = opt_extend_hap(nb, 1, 0, false, 0, true);
                 if (rc) return rc;
-                const u32 c = opt_cost(s);
-                if (c < best) { best = c; n_res = 0; }
-                if (c == best && n_res >= res_cap) return SOLVE_WORKSPACE;
+                const u32 c = opt_cost(nb);
+                if (c < best) { best = c; nres = 0; }
                 if (c == best) {
-                    warp_copy(res_alle + (long long)n_res * Npad, n_alle(s), N);
-                    if (lane == 0) {
-                        int *rn = res_num + n_res * 6;
-                        rn[0] = hdr[2 + 6]; rn[1] = hdr[10 + 6]; rn[2] = hdr[2 + 4]; rn[3] = hdr[10 + 4]; rn[4] = hdr[2 + 5]; rn[5] = hdr[10 + 5];
+                    if (nres >= res_cap) return SOLVE_WORKSPACE;
+                    warp_copy<SMEM>(res_alle + (u32)(nres * Npad), nb + ON_HDR, n);
+                    if (lane < 6) {   // ed1 ed2 tvs1 tvs2 qvs1 qvs2
+                        const int fld = lane < 2 ? H_ED : (lane < 4 ? H_TSK : H_QSK);
+                        ST32(res_num + (u32)(nres * 24 + 4 * lane), LD32(nb + ON_HAP + ON_HAPSZ * (lane & 1) + fld));
                     }
                     __syncwarp();
-                    n_res += 1;
+                    nres += 1;
                 }
                 free_slot(s);
                 continue;
             }
-            const int z = vinfo[oi].zyg;
-            const bool is_truth = vinfo[oi].is_truth;
+            const u32 flags = LD32(vi(oi) + VI_FLAGS);
+            const int z = (flags >> 8) & 0xff;
+            const bool is_truth = (flags & 0x10000u) != 0;
             const bool het = (z == AVK_ZYG_UNPHASED_HET || z == AVK_ZYG_PHASED_HET01 || z == AVK_ZYG_PHASED_HET10);
-            if (het && (!is_truth || z == AVK_ZYG_UNPHASED_HET)) {             // :269-293
-                const int s2 = alloc_slot();
+            if (!het && z != AVK_ZYG_HOM_ALT) return AVK_ST_BAD_ZYGOSITY;      // assert_eq! :315
+            const bool two = het && (!is_truth || z == AVK_ZYG_UNPHASED_HET);  // :269: both orientations, new ids
+            int s2 = -1;
+            if (two) {
+                s2 = alloc_slot();
                 if (s2 < 0) return SOLVE_WORKSPACE;
-                opt_clone(s2, s);
+                opt_clone(node(s2), nb);
                 // first child (REF, ALT) gets the lower id, second (ALT, REF) the next one
-                if (lane == 0) { n_hdr(s2)[0] = (int)next_id; hdr[0] = (int)(next_id + 1); }
+                if (lane == 0) { ST32(node(s2) + ON_ID, next_id); ST32(nb + ON_ID, next_id + 1); }
                 __syncwarp();
-                int rc = opt_extend(s2, oi, false, true);
-                if (rc) return rc;
-                push(((u64)opt_cost(s2) << 32) | next_id, s2);
-                rc = opt_extend(s, oi, true, false);
-                if (rc) return rc;
-                push(((u64)opt_cost(s) << 32) | (next_id + 1), s);
                 next_id += 2;
-            } else if (het) {                                                  // :294-312 phased truth het, id kept
-                const bool a1 = (z == AVK_ZYG_PHASED_HET10);
-                const int rc = opt_extend(s, oi, a1, !a1);
+            }
+            // child order: (REF, ALT) then (ALT, REF) for a split; the single fixed orientation otherwise
+            // (phased truth het :294-312, hom-alt :313-327) keeps the node id.
+#pragma unroll 1
+            for (int k = two ? 0 : 1; k < 2; ++k) {
+                const int sl = (two && k == 0) ? s2 : s;
+                bool a1, a2;
+                if (two) { a1 = k == 1; a2 = k == 0; }
+                else if (het) { a1 = (z == AVK_ZYG_PHASED_HET10); a2 = !a1; }
+                else { a1 = true; a2 = true; }
+                u32 c;
+                const int rc = opt_extend(node(sl), oi, a1, a2, &c);
                 if (rc) return rc;
-                push(((u64)opt_cost(s) << 32) | (u32)hdr[0], s);
-            } else {
-                if (z != AVK_ZYG_HOM_ALT) return AVK_ST_BAD_ZYGOSITY;          // assert_eq! :315
-                const int rc = opt_extend(s, oi, true, true);
-                if (rc) return rc;
-                push(((u64)opt_cost(s) << 32) | (u32)hdr[0], s);
+                push(((u64)c << 32) | LD32(node(sl) + ON_ID), sl);
             }
         }
-        if (n_res == 0) return AVK_ST_NO_RESULT;                               // :331
+        n_res = nres;
+        if (nres == 0 && !stop_at_nonzero) return AVK_ST_NO_RESULT;            // :331
         return SOLVE_OK;
     }
 
     // ================================================================== optimize_gt_alleles
-    // node layout: int hdr[8] {id, errors, depth, t_ref_pos, q_ref_pos, t_len, q_len, d}; u8 alle[Npad];
-    //              u8 seq[2][seq_cap].  DWFA max ED is 0 (exact_gt_optimizer.rs:380), so the wavefront is the
-    //              single matched length d and "alive" means one sequence is a prefix of the other.
-    __device__ __forceinline__ int ex_stride() const { return 32 + Npad + 2 * seq_cap; }
-    __device__ __forceinline__ u8 *x_alle(int s) const { return nodes + (long long)s * stride + 32; }
-    __device__ __forceinline__ u8 *x_seq(int s, int k) const { return nodes + (long long)s * stride + 32 + Npad + (long long)k * seq_cap; }
+    // node: hdr[48] | alle[Npad] | seq[2][seq_cap].  DWFA max ED is 0 (exact_gt_optimizer.rs:380), so the wavefront
+    // is the single matched length d and "alive" means one sequence is a prefix of the other.
+    __device__ __forceinline__ int ex_stride() const { return XN_HDR + Npad + 2 * seq_cap; }
+    __device__ __forceinline__ addr x_seq(addr nb, int k) const { return nb + (u32)(XN_HDR + Npad + k * seq_cap); }
 
-    __device__ __noinline__ void ex_clone(int dst, int src) {
+    __device__ __noinline__ void ex_clone(addr dst, addr src) {
         const int lane = lane_id();
-        int *hs = n_hdr(src), *hd = n_hdr(dst);
-        const int depth = hs[2], tl = hs[5], ql = hs[6];
-        if (lane < 8) hd[lane] = hs[lane];
-        warp_copy(x_alle(dst), x_alle(src), depth);
-        warp_copy(x_seq(dst, 0), x_seq(src, 0), tl);
-        warp_copy(x_seq(dst, 1), x_seq(src, 1), ql);
+        if (lane < 10) ST32(dst + 4 * lane, LD32(src + 4 * lane));
+        warp_copy<SMEM>(dst + XN_HDR, src + XN_HDR, LDI(src + XN_DEPTH));
+        warp_copy<SMEM>(x_seq(dst, 0), x_seq(src, 0), LDI(src + XN_TML));
+        warp_copy<SMEM>(x_seq(dst, 1), x_seq(src, 1), LDI(src + XN_QML));
         __syncwarp();
     }
-    // ExactMatchNode::extend_variant (exact_gt_optimizer.rs:395-414): returns 1 keep / 0 drop / <0 error
-    __device__ __noinline__ int ex_extend(int s, int oi, bool alt, bool is_error) {
-        int *hdr = n_hdr(s);
-        int t_ref_pos = hdr[3], q_ref_pos = hdr[4], t_len = hdr[5], q_len = hdr[6], d = hdr[7];
-        const int errors = hdr[1];
-        u8 *tseq = x_seq(s, 0), *qseq = x_seq(s, 1);
-        const VInfo v = vinfo[oi];
-        const int sync = sync_pos(oi);
-        bool success, ok;
-        int skip = 0;
-        if (v.is_truth) {
-            ok = copy_ref(qseq, q_len, q_ref_pos, sync);
-            ok = ok && track_variant(tseq, t_len, t_ref_pos, skip, v, alt, sync, success);
+    // ExactMatchNode::extend_variant (exact_gt_optimizer.rs:395-414), or finalize_dwfas (:421-434) when finalize.
+    // returns 1 keep (alive / exact) / 0 drop / <0 error
+    __device__ __noinline__ int ex_extend(addr nb, int oi, bool alt, bool is_error, bool finalize) {
+        int t_rp = LDI(nb + XN_TRP), q_rp = LDI(nb + XN_QRP), t_ml = LDI(nb + XN_TML), q_ml = LDI(nb + XN_QML);
+        int t_mr = LDI(nb + XN_TMR), q_mr = LDI(nb + XN_QMR), d = LDI(nb + XN_D);
+        int skip = 0, success = 1;
+        if (finalize) {
+            t_rp = max(t_rp, end); q_rp = max(q_rp, end);
         } else {
-            ok = copy_ref(tseq, t_len, t_ref_pos, sync);
-            ok = ok && track_variant(qseq, q_len, q_ref_pos, skip, v, alt, sync, success);
+            const addr rec = vi(oi);
+            const int sync = sync_pos(oi);
+            if (LD32(rec + VI_FLAGS) & 0x10000u) {
+                q_rp = max(q_rp, sync);
+                success = track(x_seq(nb, 0), t_rp, t_ml, t_mr, skip, rec, alt, sync);
+            } else {
+                t_rp = max(t_rp, sync);
+                success = track(x_seq(nb, 1), q_rp, q_ml, q_mr, skip, rec, alt, sync);
+            }
+            if (success < 0) return SOLVE_WORKSPACE;
         }
-        if (!ok) return SOLVE_WORKSPACE;
         __syncwarp();
         // DWFA update with max ED 0: extend the single diagonal, then require an end to be reached
-        const int ext = warp_lcp(tseq + d, t_len - d, qseq + d, q_len - d);
-        work.cells += 1; work.matched += (u32)ext;
+        const VS T = make_vs(x_seq(nb, 0), t_ml, t_mr, t_rp), Q = make_vs(x_seq(nb, 1), q_ml, q_mr, q_rp);
+        const int ext = (d < T.len && d < Q.len) ? vs_lcp<SMEM>(T, d, Q, d) : 0;
         d += ext;
-        const bool alive = (d >= t_len) || (d >= q_len);
+        const bool alive = finalize ? ((d >= T.len) && (d >= Q.len))    // update ok + finalize ok <=> sequences equal
+                                    : ((d >= T.len) || (d >= Q.len));
         if (lane_id() == 0) {
-            hdr[1] = errors + (is_error ? 1 : 0);
-            hdr[2] = oi + 1;
-            hdr[3] = t_ref_pos; hdr[4] = q_ref_pos; hdr[5] = t_len; hdr[6] = q_len; hdr[7] = d;
-            x_alle(s)[oi] = alt ? AL_ALT : AL_REF;
+            ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1); ST64(wk() + WK_MATCHED, LD64(wk() + WK_MATCHED) + (u64)ext);
+            if (finalize) ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
+            else {
+                if (is_error) ST32(nb + XN_ERR, LD32(nb + XN_ERR) + 1);
+                ST32(nb + XN_DEPTH, oi + 1);
+                ST8(nb + XN_HDR + oi, alt ? AL_ALT : AL_REF);
+            }
+            ST32(nb + XN_TRP, t_rp); ST32(nb + XN_QRP, q_rp); ST32(nb + XN_TML, t_ml); ST32(nb + XN_QML, q_ml);
+            ST32(nb + XN_TMR, t_mr); ST32(nb + XN_QMR, q_mr); ST32(nb + XN_D, d);
         }
         __syncwarp();
         return (success && alive) ? 1 : 0;
     }
-    __device__ __forceinline__ u64 ex_key(int s) const {   // (Reverse(errors), set - errors, Reverse(id)) :372,452-458
-        const int *hdr = n_hdr(s);
-        const u64 errors = (u64)hdr[1];
-        const u64 good = (u64)(hdr[2] - hdr[1]);
-        return (errors << 48) | ((0xffffull - good) << 32) | (u32)hdr[0];
+    __device__ __forceinline__ u64 ex_key(addr nb) const {   // (Reverse(errors), set - errors, Reverse(id)) :372,452-458
+        const u64 errors = (u64)LD32(nb + XN_ERR);
+        const u64 good = (u64)(LD32(nb + XN_DEPTH) - LD32(nb + XN_ERR));
+        return (errors << 48) | ((0xffffull - good) << 32) | LD32(nb + XN_ID);
     }
 
     // in: hap_alle[oi] (AL_REF / AL_ALT by order index).  out: obs[oi], *errors.
-    __device__ __noinline__ int exact_gt(u8 *obs, int *errors_out) {
+    __device__ __noinline__ int exact_gt(addr obs, int *errors_out) {
         const int lane = lane_id();
-        if (N >= 0xffff) return SOLVE_WORKSPACE;
-        if (!partition(ex_stride(), min(N + 3, 48))) return SOLVE_WORKSPACE;
-        u32 next_id = 0;
+        const int n = N;
+        if (n >= 0xffff) return SOLVE_WORKSPACE;
+        if (!partition(ex_stride(), min(n + 3, 48))) return SOLVE_WORKSPACE;
+        u32 next_id = 1;
         int best_err = 0x7fffffff;
         bool have_best = false;
         int min_sync = 0, af_index = 0, af_counts = 0;
         {
             const int s = alloc_slot();
-            int *hdr = n_hdr(s);
-            if (lane < 8) hdr[lane] = (lane == 3 || lane == 4) ? start : 0;
+            const addr nb = node(s);
+            if (lane < 10) ST32(nb + 4 * lane, (lane == 3 || lane == 4 || lane == 7 || lane == 8) ? start : 0);
             __syncwarp();
-            next_id = 1;
-            push(ex_key(s), s);
+            push(ex_key(nb), s);
         }
-        #pragma unroll 1
+#pragma unroll 1
         while (qn > 0) {
-            u64 key;
-            const int s = pop(key);
-            work.exact_pops += 1;
-            int *hdr = n_hdr(s);
-            const int errors = hdr[1];
+            u32 khi;
+            const int s = pop(&khi);
+            if (lane == 0) ST32(wk() + WK_XPOPS, LD32(wk() + WK_XPOPS) + 1);
+            const addr nb = node(s);
+            const int errors = LDI(nb + XN_ERR);
             if (errors >= best_err) { free_slot(s); continue; }                // :169 non-strict
-            const int oi = hdr[2];
-            if (oi == N) {                                                     // :180-192
-                int t_ref_pos = hdr[3], q_ref_pos = hdr[4], t_len = hdr[5], q_len = hdr[6], d = hdr[7];
-                u8 *tseq = x_seq(s, 0), *qseq = x_seq(s, 1);
-                if (!copy_ref(tseq, t_len, t_ref_pos, end)) return SOLVE_WORKSPACE;
-                if (!copy_ref(qseq, q_len, q_ref_pos, end)) return SOLVE_WORKSPACE;
-                __syncwarp();
-                const int ext = warp_lcp(tseq + d, t_len - d, qseq + d, q_len - d);
-                work.cells += 1; work.matched += (u32)ext; work.alignments += 1;
-                d += ext;
-                const bool exact = (d >= t_len) && (d >= q_len);   // update ok + finalize ok <=> sequences equal
+            const int oi = LDI(nb + XN_DEPTH);
+            if (oi == n) {                                                     // :180-192
+                const int exact = ex_extend(nb, oi, false, false, true);
+                if (exact < 0) return exact;
                 if (exact && errors < best_err) {
                     best_err = errors;
                     have_best = true;
-                    warp_copy(obs, x_alle(s), N);
+                    warp_copy<SMEM>(obs, nb + XN_HDR, n);
                     __syncwarp();
                 }
                 free_slot(s);
                 continue;
             }
             if (oi < min_sync) { free_slot(s); continue; }                     // :194-197
-            if (hdr[5] == hdr[6] && hdr[3] == hdr[4]) {                        // is_synchronized (alive => ed == 0) :206-217
-                min_sync = oi; af_counts = 0; af_index = oi;
+            {   // is_synchronized (:206-217): alive => ed == 0; equal logical lengths and reference positions
+                const int t_rp = LDI(nb + XN_TRP), q_rp = LDI(nb + XN_QRP);
+                const int tl = LDI(nb + XN_TML) + (t_rp - LDI(nb + XN_TMR)), ql = LDI(nb + XN_QML) + (q_rp - LDI(nb + XN_QMR));
+                if (tl == ql && t_rp == q_rp) { min_sync = oi; af_counts = 0; af_index = oi; }
             }
-            const int al = hap_alle[oi];
-            if (al == AL_REF) {                                                // :257-273 move, id kept
-                const int keep = ex_extend(s, oi, false, false);
-                if (keep < 0) return keep;
-                if (keep) push(ex_key(s), s); else free_slot(s);
-            } else {                                                           // :274-306 clone twice
-                // (REF, error) first with id next_id; then (ALT, no error) unless auto-failed
-                const bool do_alt = !(oi < af_index);
-                int s_alt = -1;
-                if (do_alt) {
-                    s_alt = alloc_slot();
-                    if (s_alt < 0) return SOLVE_WORKSPACE;
-                    ex_clone(s_alt, s);
-                }
-                if (lane == 0) hdr[0] = (int)next_id;
+            const bool is_alt = LD8(hap_alle + oi) == AL_ALT;
+            // REF allele: move, id kept (:257-273).  ALT allele: (REF, error) with id next_id, then (ALT, no error)
+            // with the following id unless auto-failed (:274-306).
+            const bool do_alt = is_alt && !(oi < af_index);
+            int s_alt = -1;
+            if (do_alt) {
+                s_alt = alloc_slot();
+                if (s_alt < 0) return SOLVE_WORKSPACE;
+                ex_clone(node(s_alt), nb);
+            }
+            if (is_alt) {
+                if (lane == 0) { ST32(nb + XN_ID, next_id); if (do_alt) ST32(node(s_alt) + XN_ID, next_id + 1); }
                 __syncwarp();
-                next_id += 1;
-                int keep = ex_extend(s, oi, false, true);
+                next_id += do_alt ? 2 : 1;
+            }
+#pragma unroll 1
+            for (int k = 0; k < (do_alt ? 2 : 1); ++k) {
+                const int sl = k ? s_alt : s;
+                const int keep = ex_extend(node(sl), oi, k == 1, is_alt && k == 0, false);
                 if (keep < 0) return keep;
-                if (keep) push(ex_key(s), s); else free_slot(s);
-                if (do_alt) {
-                    if (lane == 0) n_hdr(s_alt)[0] = (int)next_id;
-                    __syncwarp();
-                    next_id += 1;
-                    keep = ex_extend(s_alt, oi, true, false);
-                    if (keep < 0) return keep;
-                    if (keep) push(ex_key(s_alt), s_alt); else free_slot(s_alt);
-                }
+                if (keep) push(ex_key(node(sl)), sl); else free_slot(sl);
             }
             af_counts += 1;                                                    // :310-339
             if (af_counts >= 500) {
-                if (af_index >= N) return AVK_ST_NO_RESULT;   // the reference would index out of bounds here
+                if (af_index >= n) return AVK_ST_NO_RESULT;   // the reference would index out of bounds here
                 int w = 0;
-                const int n = qn;
-                #pragma unroll 1
-                for (int i = 0; i < n; ++i) {
-                    const int sl = (int)qslot[i];
-                    const u8 a = x_alle(sl)[af_index];
-                    const bool set = n_hdr(sl)[2] > af_index;
-                    if (!set || a == AL_REF) {
-                        if (lane == 0 && w != i) { qkeys[w] = qkeys[i]; qslot[w] = qslot[i]; }
+                const int cnt = qn;
+#pragma unroll 1
+                for (int i = 0; i < cnt; ++i) {
+                    const int sl = (int)LD32(qslot + 4 * i);
+                    const bool set = LDI(node(sl) + XN_DEPTH) > af_index;
+                    if (!set || LD8(node(sl) + XN_HDR + af_index) == AL_REF) {
+                        if (lane == 0 && w != i) { ST64(qkeys + 8 * w, LD64(qkeys + 8 * i)); ST32(qslot + 4 * w, sl); }
                         w += 1;
                     } else {
                         free_slot(sl);
@@ -697,52 +692,82 @@ struct RegionSolver {
     }
 
     // ================================================================== waffle solver
-    // generate_allele_sequence(): waffle_solver.rs:726-778.  side 0 truth / 1 query, hap 0/1, alleles from
-    // result r; type_filter < 0 keeps every variant.  Returns length (or -1), failed ED, #ALT spliced.
-    __device__ __noinline__ int build_hap_seq(u8 *dst, int side, int hap, int r, int type_filter, int &failed, int &n_alt) {
-        const u8 *ra = res_alle + (long long)r * Npad;
-        int cur = start, len = 0;
-        failed = 0; n_alt = 0;
-        #pragma unroll 1
-        for (int oi = 0; oi < N; ++oi) {
-            const VInfo v = vinfo[oi];
-            if ((v.is_truth ? 0 : 1) != side) continue;
-            if (!((ra[oi] >> hap) & 1)) continue;                 // REF allele: skipped entirely (:738-741)
-            if (type_filter >= 0 && v.type != type_filter) continue;
-            const int vpos = (int)v.pos;
-            if (vpos < cur) { failed += (int)v.alt_ed; continue; }   // :745-753
-            if (!copy_ref(dst, len, cur, vpos)) return -1;
-            const int l1 = (int)v.l1;
-            if (len + l1 > seq_cap) return -1;
-            warp_copy(dst + len, alle_base + v.aoff + v.l0, l1);
-            len += l1;
-            cur = vpos + (int)v.l0;
+    // generate_allele_sequence(): waffle_solver.rs:726-778 as a virtual sequence in buffer `k` (0 T, 1 Q, 2 F).
+    // side 0 truth / 1 query, hap 0/1, alleles from result r; type_filter < 0 keeps every variant.
+    // Fills sdesc[k] = {mlen, cur, failed ED, #ALT spliced}; returns 0, -1 (capacity) or -2 (variant past the window).
+    __device__ __noinline__ int build_hap_seq(int k, int side, int hap, int r, int type_filter) {
+        const addr dst = dyn + (u32)(k * seq_cap);
+        const addr ra = res_alle + (u32)(r * Npad);
+        int cur = start, mlen = 0, failed = 0, n_alt = 0;
+        const int n = N;
+#pragma unroll 1
+        for (int oi = 0; oi < n; ++oi) {
+            const addr rec = vi(oi);
+            const u32 f = LD32(rec + VI_FLAGS);
+            if ((int)((f >> 16) & 1) == side) continue;           // is_truth == 1 <=> side 0
+            if (!((LD8(ra + oi) >> hap) & 1)) continue;           // REF allele: skipped entirely (:738-741)
+            if (type_filter >= 0 && (int)(f & 0xff) != type_filter) continue;
+            const int vpos = (int)LD32(rec + VI_POS);
+            if (vpos < cur) { failed += (int)LD32(rec + VI_ALTED); continue; }   // :745-753
+            const int l0 = (int)LD32(rec + VI_L0), l1 = (int)LD32(rec + VI_L1);
+            const int nref = vpos - cur;
+            if (mlen + nref + l1 > seq_cap) return -1;
+            if (nref > 0) warp_copy<SMEM>(dst + mlen, ref_base + cur, nref);
+            warp_copy<SMEM>(dst + mlen + nref, alle_base + LD32(rec + VI_AOFF) + l0, l1);
+            mlen += nref + l1;
+            cur = vpos + l0;
             n_alt += 1;
         }
         if (cur > end) return -2;
-        if (!copy_ref(dst, len, cur, end)) return -1;
+        if (lane_id() == 0) {
+            const addr sd = sdesc + (u32)(k * SD_SIZE);
+            ST32(sd + SD_MLEN, mlen); ST32(sd + SD_CUR, cur); ST32(sd + SD_FAILED, failed); ST32(sd + SD_NALT, n_alt);
+        }
         __syncwarp();
-        return len;
+        return 0;
+    }
+    // virtual sequence of buffer k (k < 0: the reference window itself)
+    __device__ __forceinline__ VS seq_vs(int k) const {
+        VS v;
+        if (k < 0) { v.data = 0; v.tail = ref_base + start; v.mlen = 0; v.len = end - start; return v; }
+        const addr sd = sdesc + (u32)(k * SD_SIZE);
+        const int mlen = LDI(sd + SD_MLEN), cur = LDI(sd + SD_CUR);
+        v.data = dyn + (u32)(k * seq_cap); v.tail = ref_base + cur; v.mlen = mlen; v.len = mlen + (end - cur);
+        return v;
+    }
+    // global edit distance between two sequence buffers, with overflow trap
+    __device__ __noinline__ u64 ed_between(int ka, int kb) {
+        const int e = wfa_ed_warp<SMEM>(seq_vs(ka), seq_vs(kb), dyn + (u32)(3 * seq_cap), (wf_cap - 3) / 2, wk());
+        if (e < 0) { ed_overflow = 1; return 0; }
+        return (u64)e;
+    }
+    // copy a sequence buffer to the optional sequence-bundle output
+    __device__ __noinline__ void emit_seq(const DevCompareOut &out, u64 r, int s, int k) {
+        const VS v = seq_vs(k);
+        u8 *dst = out.seq_pool + out.seq_off[r * 5 + s];
+#pragma unroll 1
+        for (int i = lane_id(); i < v.len; i += 32) dst[i] = LD8(v.at(i));
+        if (lane_id() == 0) out.seq_len[r * 5 + s] = (u32)v.len;
     }
 
-    // GroupMetrics::add_truth_zygosity (grouped_metrics.rs:183-227); col 0 = truth columns, 2 = query columns
-    // (the query pass lands in the query columns through add_swap_benchmark, :268-277).  lane 0 only.
-    static __device__ __forceinline__ void gm_add(u64 *g, int col, u64 w, int exp, int obs) {
+    // GroupMetrics::add_truth_zygosity (grouped_metrics.rs:183-227) on row g; col 0 = truth columns, 2 = query
+    // columns (the query pass lands in the query columns through add_swap_benchmark, :268-277).  lane 0 only.
+    __device__ __noinline__ void gm_add(addr g, int col, u64 w, int exp, int obs) {
+        const int mn = min(exp, obs);
+        ST64(g + 8 * (AVK_M_HAP + col), LD64(g + 8 * (AVK_M_HAP + col)) + (u64)mn);
+        ST64(g + 8 * (AVK_M_WEIGHTED_HAP + col), LD64(g + 8 * (AVK_M_WEIGHTED_HAP + col)) + (u64)mn * w);
         if (exp == obs) {
-            g[AVK_M_HAP + col] += exp; g[AVK_M_WEIGHTED_HAP + col] += exp * w; g[AVK_M_GT + col] += 1;
+            ST64(g + 8 * (AVK_M_GT + col), LD64(g + 8 * (AVK_M_GT + col)) + 1);
         } else {
-            g[AVK_M_HAP + col] += obs; g[AVK_M_HAP + col + 1] += (exp - obs);
-            g[AVK_M_WEIGHTED_HAP + col] += obs * w; g[AVK_M_WEIGHTED_HAP + col + 1] += (u64)(exp - obs) * w;
-            g[AVK_M_GT + col + 1] += 1;
-            if (obs > 0) g[(col == 0) ? AVK_M_GT_TRUTH_FN_GT : AVK_M_GT_QUERY_FP_GT] += 1;
+            ST64(g + 8 * (AVK_M_HAP + col + 1), LD64(g + 8 * (AVK_M_HAP + col + 1)) + (u64)(exp - obs));
+            ST64(g + 8 * (AVK_M_WEIGHTED_HAP + col + 1), LD64(g + 8 * (AVK_M_WEIGHTED_HAP + col + 1)) + (u64)(exp - obs) * w);
+            ST64(g + 8 * (AVK_M_GT + col + 1), LD64(g + 8 * (AVK_M_GT + col + 1)) + 1);
+            const int gt = (col == 0) ? AVK_M_GT_TRUTH_FN_GT : AVK_M_GT_QUERY_FP_GT;
+            if (obs > 0) ST64(g + 8 * gt, LD64(g + 8 * gt) + 1);
         }
     }
-
-    // global ED with overflow trap (the wavefront buffer is sized from the proven bound b0)
-    __device__ __noinline__ int ed_checked(bool &ovf, const u8 *A, int la, const u8 *B, int lb, int *wf, int cap) {
-        const int e = wfa_ed_warp(A, la, B, lb, wf, cap, work);
-        if (e < 0) { ovf = true; return 0; }
-        return e;
+    __device__ __forceinline__ void add4(addr g, u64 a, u64 b2, u64 c, u64 d) {   // lane 0 only
+        ST64(g, LD64(g) + a); ST64(g + 8, LD64(g + 8) + b2); ST64(g + 16, LD64(g + 16) + c); ST64(g + 24, LD64(g + 24) + d);
     }
 
     __device__ int solve_compare(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out);
@@ -750,7 +775,8 @@ struct RegionSolver {
 };
 
 // solve_compare_region(): returns AVK_ST_* (>= 0) or SOLVE_WORKSPACE
-__device__ int RegionSolver::solve_compare(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out) {
+template <bool SMEM>
+__device__ int RegionSolver<SMEM>::solve_compare(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out) {
     const DevBatch &b = *bp;
     const int lane = lane_id();
     const u32 c = b.contig[r];
@@ -760,41 +786,44 @@ __device__ int RegionSolver::solve_compare(u64 r, const avk_compare_cfg &cfg, co
     mbf = (int)cfg.max_branch_factor;
     if (mbf <= 0) return AVK_ST_BAD_INPUT;
     if (!begin_region(b.contig_ptr[c])) return SOLVE_WORKSPACE;
-    bool bad;
-    int rc = setup_pair(r, 0, 1, true, bad);
+    int rc = setup_pair(r, 0, 1, true);
     if (rc) return rc;
-    if (bad) return AVK_ST_BAD_INPUT;
-    const int W = end - start;
+    const int n = N, npad = Npad;
 
     rc = optimize(false);
     if (rc) return rc;
 
     int best_r = 0;
-    const bool shortcut = cfg.enable_exact_shortcut &&
-        (res_num[0] + res_num[1] + res_num[2] + res_num[3] + res_num[4] + res_num[5] == 0);   // :171
+    bool shortcut = false;
+    if (cfg.enable_exact_shortcut) {                                       // :171
+        int s = 0;
+#pragma unroll 1
+        for (int k = 0; k < 6; ++k) s += LDI(res_num + 4 * k);
+        shortcut = s == 0;
+    }
     if (!shortcut) {
         // ---- exact-GT scoring of every equal-best solution; first minimum wins (:169-265)
         int best_total = 0x7fffffff;
-        #pragma unroll 1
+#pragma unroll 1
         for (int ri = 0; ri < n_res; ++ri) {
             int total = 0;
-            #pragma unroll 1
+#pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                const u8 *ra = res_alle + (long long)ri * Npad;
-                #pragma unroll 1
-                for (int i = lane; i < N; i += 32) hap_alle[i] = ((ra[i] >> h) & 1) ? AL_ALT : AL_REF;
+                const addr ra = res_alle + (u32)(ri * npad);
+#pragma unroll 1
+                for (int i = lane; i < n; i += 32) ST8(hap_alle + i, ((LD8(ra + i) >> h) & 1) ? AL_ALT : AL_REF);
                 __syncwarp();
                 int errs = 0;
-                const int *rnum = res_num + ri * 6;
-                if (rnum[h] + rnum[2 + h] + rnum[4 + h] == 0) {
-                    // ED 0 and nothing skipped on this haplotype: the zero-flip path of optimize_gt_alleles
-                    // replays exactly these tracker steps, stays alive, is popped first (fewest errors, most
-                    // set alleles) and finalises with 0 errors, after which every other node is pruned
-                    // (errors >= best, exact_gt_optimizer.rs:169).  Its result is the input alleles.
-                    warp_copy(cur_obs + h * Npad, hap_alle, N);
+                const addr rnum = res_num + (u32)(ri * 24);
+                if (LDI(rnum + 4 * h) + LDI(rnum + 4 * (2 + h)) + LDI(rnum + 4 * (4 + h)) == 0) {
+                    // ED 0 and nothing skipped on this haplotype: the zero-flip path of optimize_gt_alleles replays
+                    // exactly these tracker steps, stays alive, is popped first (fewest errors, most set alleles)
+                    // and finalises with 0 errors, after which every other node is pruned (errors >= best,
+                    // exact_gt_optimizer.rs:169).  Its result is the input alleles.
+                    warp_copy<SMEM>(cur_obs + (u32)(h * npad), hap_alle, n);
                     __syncwarp();
                 } else {
-                    rc = exact_gt(cur_obs + h * Npad, &errs);
+                    rc = exact_gt(cur_obs + (u32)(h * npad), &errs);
                     if (rc) return rc;
                 }
                 total += errs;
@@ -802,189 +831,157 @@ __device__ int RegionSolver::solve_compare(u64 r, const avk_compare_cfg &cfg, co
             if (total < best_total) {
                 best_total = total;
                 best_r = ri;
-                warp_copy(best_obs, cur_obs, 2 * Npad);
+                warp_copy<SMEM>(best_obs, cur_obs, 2 * npad);
                 __syncwarp();
             }
         }
     }
-    const u8 *ra = res_alle + (long long)best_r * Npad;
-    u64 *gm = mrows;   // joint row; type rows follow at gm + 22 * (1 + slot)
+    const addr ra = res_alle + (u32)(best_r * npad);
+    const addr rnb = res_num + (u32)(best_r * 24);
+    const addr gm = mrows;   // joint row; type rows follow at gm + 176 * (1 + slot)
 
     // ---- per-variant expected/observed (:226-258); lanes across variants
-    #pragma unroll 1
-    for (int oi = lane; oi < N; oi += 32) {
-        const VInfo v = vinfo[oi];
+#pragma unroll 1
+    for (int oi = lane; oi < n; oi += 32) {
+        const u32 f = LD32(vi(oi) + VI_FLAGS);
+        const bool is_truth = (f & 0x10000u) != 0;
         int exp_, obs_;
         if (shortcut) {   // generate_exact_match(): counts come from the RAW zygosities (:544-557)
-            exp_ = (v.zyg == AVK_ZYG_HOM_ALT) ? 2 : 1;
+            exp_ = (((f >> 8) & 0xff) == AVK_ZYG_HOM_ALT) ? 2 : 1;
             obs_ = exp_;
         } else {
-            exp_ = (ra[oi] & 1) + ((ra[oi] >> 1) & 1);
-            obs_ = (best_obs[oi] == AL_ALT ? 1 : 0) + (best_obs[Npad + oi] == AL_ALT ? 1 : 0);
+            const int a = LD8(ra + oi);
+            exp_ = (a & 1) + ((a >> 1) & 1);
+            obs_ = (LD8(best_obs + oi) == AL_ALT ? 1 : 0) + (LD8(best_obs + npad + oi) == AL_ALT ? 1 : 0);
         }
-        const int cls = (exp_ == obs_) ? AVK_CLASS_TP : (v.is_truth ? AVK_CLASS_FN : AVK_CLASS_FP);
-        out.vexp[v.gv] = (u8)(v.is_truth ? exp_ : obs_);     // query entries are toggled (compare_benchmark.rs:109-123)
-        out.vobs[v.gv] = (u8)(v.is_truth ? obs_ : exp_);
-        out.vcls[v.gv] = (u8)cls;
-        hap_alle[oi] = (u8)(exp_ | (obs_ << 4));             // reuse as scratch for the metric pass below
+        const int cls = (exp_ == obs_) ? AVK_CLASS_TP : (is_truth ? AVK_CLASS_FN : AVK_CLASS_FP);
+        const u32 gv = LD32(vi(oi) + VI_GV);
+        out.vexp[gv] = (u8)(is_truth ? exp_ : obs_);     // query entries are toggled (compare_benchmark.rs:109-123)
+        out.vobs[gv] = (u8)(is_truth ? obs_ : exp_);
+        out.vcls[gv] = (u8)cls;
+        ST8(hap_alle + oi, exp_ | (obs_ << 4));          // scratch for the metric pass below
     }
     __syncwarp();
-    // ---- GT / HAP / WEIGHTED_HAP (+ add_swap_benchmark :269), accumulated in the arena by lane 0
+    // ---- GT / HAP / WEIGHTED_HAP (+ add_swap_benchmark :269) and RECORD_BP totals, accumulated by lane 0
     if (lane == 0) {
-        #pragma unroll 1
-        for (int oi = 0; oi < N; ++oi) {
-            const VInfo v = vinfo[oi];
-            const int exp_ = hap_alle[oi] & 15, obs_ = hap_alle[oi] >> 4;
-            const int col = v.is_truth ? 0 : 2;
-            gm_add(gm, col, v.alt_ed, exp_, obs_);
-            gm_add(gm + AVK_N_METRICS * (1 + v.slot), col, v.alt_ed, exp_, obs_);
-            slot_cnt[2 * v.slot + (v.is_truth ? 0 : 1)] += 1;
+#pragma unroll 1
+        for (int oi = 0; oi < n; ++oi) {
+            const addr rec = vi(oi);
+            const u32 f = LD32(rec + VI_FLAGS);
+            const int exp_ = LD8(hap_alle + oi) & 15, obs_ = LD8(hap_alle + oi) >> 4;
+            const int side = (f & 0x10000u) ? 0 : 1, slot = (int)(f >> 24);
+            const u64 w = LD32(rec + VI_ALTED);
+            gm_add(gm, 2 * side, w, exp_, obs_);
+            gm_add(gm + (u32)(8 * AVK_N_METRICS * (1 + slot)), 2 * side, w, exp_, obs_);
+            const addr cnt = slot_cnt + (u32)(4 * (2 * slot + side));
+            ST32(cnt, LD32(cnt) + 1);
+            const addr tot = slot_tot + (u32)(8 * (2 * slot + side));
+            ST64(tot, LD64(tot) + (u64)((((f >> 8) & 0xff) == AVK_ZYG_HOM_ALT) ? 2 : 1) * LD32(rec + VI_RAW));
         }
     }
     __syncwarp();
 
     // ---- basepair metrics: three sequence buffers + one wavefront in the dynamic part
-    const long long need = 3LL * seq_cap + 4LL * wf_cap + 16;
-    if (need > dyn_bytes) return SOLVE_WORKSPACE;
-    u8 *bufT = dyn, *bufQ = dyn + seq_cap, *bufF = dyn + 2LL * seq_cap;
-    int *wf = (int *)(dyn + 3LL * seq_cap);
-    const int ed_cap = (wf_cap - 3) / 2;
-    const u8 *R = ref + start;
+    if ((u32)(3 * seq_cap + 4 * wf_cap + 16) > dyn_bytes) return SOLVE_WORKSPACE;
     const bool want_seq = out.seq_off && cfg.enable_sequences;
-    bool ed_overflow = false;
+    ed_overflow = 0;
     u32 mask = 0;
-    #pragma unroll 1
+#pragma unroll 1
     for (int k = 0; k < n_slots; ++k) mask |= 1u << slot_type[k];
 
     int status = AVK_ST_OK;
-    if (shortcut) {
-        // generate_exact_match(): :559-598
-        u64 js = 0;
-        #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            int failed, n_alt;
-            const int lt = build_hap_seq(bufT, 0, h, 0, -1, failed, n_alt);
-            if (lt < 0) return lt == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
-            js += (u64)ed_checked(ed_overflow, R, W, bufT, lt, wf, ed_cap);
-            if (want_seq) {
-                const int lq = build_hap_seq(bufQ, 1, h, 0, -1, failed, n_alt);
-                if (lq < 0) return lq == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
-                warp_copy(out.seq_pool + out.seq_off[r * 5 + 1 + h], bufT, lt);
-                warp_copy(out.seq_pool + out.seq_off[r * 5 + 3 + h], bufQ, lq);
-                if (lane == 0) { out.seq_len[r * 5 + 1 + h] = (u32)lt; out.seq_len[r * 5 + 3 + h] = (u32)lq; }
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int rsel = shortcut ? 0 : best_r;
+        // truth / query haplotypes (buffers 0 / 1)
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            const int brc = build_hap_seq(side, side, h, rsel, -1);
+            if (brc) return brc == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
+            if (want_seq) emit_seq(out, r, 1 + 2 * side + h, side);
+        }
+        const int altT = LDI(sdesc + SD_NALT), altQ = LDI(sdesc + SD_SIZE + SD_NALT);
+        const u64 failT = (u64)LDI(sdesc + SD_FAILED), failQ = (u64)LDI(sdesc + SD_SIZE + SD_FAILED);
+        // X = ED(ref, truth), Y = ED(ref, query), Z = ED(truth, query).  A haplotype without a spliced ALT IS the
+        // reference window; Z is the optimizer's finalised (exact Levenshtein) distance of this haplotype pair.
+        const u64 X = altT ? ed_between(-1, 0) : 0;
+        if (shortcut) {   // generate_exact_match(): :559-598 -- joint gets 2 * ED(ref, truth) on both sides
+            if (lane == 0) add4(gm + 8 * AVK_M_BASEPAIR, 2 * X, 0, 2 * X, 0);
+            continue;
+        }
+        const u64 Z = (u64)LDI(rnb + 4 * h);
+        const u64 Y = (Z == 0) ? X : (altQ ? ed_between(-1, 1) : 0);
+        const u64 tp = X + Y - Z;                    // (2X + 2Y - 2Z) / 2  :644
+        if (lane == 0) add4(gm + 8 * AVK_M_BASEPAIR, tp, 2 * X - tp + 2 * failT, tp, 2 * Y - tp + 2 * failQ);
+        // per supported type that occurs in the cluster (absent types only ever receive zeros, :395-444)
+#pragma unroll 1
+        for (int k = 0; k < n_slots; ++k) {
+            const int ft = slot_type[k];
+            if (!type_supported(ft)) continue;
+#pragma unroll 1
+            for (int side = 1; side >= 0; --side) {   // query filter (:395-410) then truth filter (:422-437)
+                const int nf = (int)LD32(slot_cnt + (u32)(4 * (2 * k + side)));
+                if (nf == 0) continue;
+                u64 f_tp, f_bad;
+                if (nf == nv[side]) {                 // filtered == full haplotype
+                    f_tp = tp; f_bad = side ? (2 * Y - tp + 2 * failQ) : (2 * X - tp + 2 * failT);
+                } else {
+                    const int brc = build_hap_seq(2, side, h, best_r, ft);
+                    if (brc) return brc == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
+                    const bool altF = LDI(sdesc + 2 * SD_SIZE + SD_NALT) != 0;
+                    const u64 failF = (u64)LDI(sdesc + 2 * SD_SIZE + SD_FAILED);
+                    // side 1: (ref, truth, F): Xa = X, Yf = ED(ref, F), Zf = ED(truth, F); side 0 mirrored
+                    const u64 other_ref = side ? X : Y;          // ED(ref, unfiltered other haplotype)
+                    const bool alt_other = side ? (altT != 0) : (altQ != 0);
+                    u64 Ef = 0, Zf = other_ref;
+                    if (altF) {
+                        Ef = ed_between(-1, 2);
+                        Zf = alt_other ? (side ? ed_between(0, 2) : ed_between(2, 1)) : Ef;
+                    }
+                    f_tp = other_ref + Ef - Zf;
+                    f_bad = 2 * Ef - f_tp + 2 * failF;
+                }
+                if (lane == 0) {
+                    const addr g = gm + (u32)(8 * (AVK_N_METRICS * (1 + k) + AVK_M_BASEPAIR + 2 * side));
+                    ST64(g, LD64(g) + f_tp); ST64(g + 8, LD64(g + 8) + f_bad);
+                }
             }
         }
+    }
+    __syncwarp();
+    if (shortcut) {
+        // generate_exact_match(): per-variant basepair credit (:573-598); no RECORD_BP, no all-8-types fill
         if (lane == 0) {
-            gm[AVK_M_BASEPAIR + 0] += 2 * js; gm[AVK_M_BASEPAIR + 2] += 2 * js;
-            #pragma unroll 1
-            for (int oi = 0; oi < N; ++oi) {
-                const VInfo v = vinfo[oi];
-                const u64 dd = 2ull * v.alt_ed * (u64)((v.zyg == AVK_ZYG_HOM_ALT) ? 2 : 1);
-                gm[AVK_N_METRICS * (1 + v.slot) + AVK_M_BASEPAIR + (v.is_truth ? 0 : 2)] += dd;
+#pragma unroll 1
+            for (int oi = 0; oi < n; ++oi) {
+                const addr rec = vi(oi);
+                const u32 f = LD32(rec + VI_FLAGS);
+                const u64 dd = 2ull * LD32(rec + VI_ALTED) * (u64)((((f >> 8) & 0xff) == AVK_ZYG_HOM_ALT) ? 2 : 1);
+                const addr g = gm + (u32)(8 * (AVK_N_METRICS * (1 + (f >> 24)) + AVK_M_BASEPAIR + ((f & 0x10000u) ? 0 : 2)));
+                ST64(g, LD64(g) + dd);
             }
         }
     } else {
-        // add_basepair_stats(): :335-449
-        #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            int failT, failQ, altT, altQ;
-            const int lt = build_hap_seq(bufT, 0, h, best_r, -1, failT, altT);
-            if (lt < 0) return lt == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
-            const int lq = build_hap_seq(bufQ, 1, h, best_r, -1, failQ, altQ);
-            if (lq < 0) return lq == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
-            if (want_seq) {
-                warp_copy(out.seq_pool + out.seq_off[r * 5 + 1 + h], bufT, lt);
-                warp_copy(out.seq_pool + out.seq_off[r * 5 + 3 + h], bufQ, lq);
-                if (lane == 0) { out.seq_len[r * 5 + 1 + h] = (u32)lt; out.seq_len[r * 5 + 3 + h] = (u32)lq; }
-            }
-            // X = ED(ref, truth), Y = ED(ref, query), Z = ED(truth, query); a haplotype without a
-            // spliced ALT IS the reference window, so its distances are known without aligning.
-            u64 X, Y, Z;
-            const int *rnb = res_num + best_r * 6;
-            X = altT ? (u64)ed_checked(ed_overflow, R, W, bufT, lt, wf, ed_cap) : 0;
-            if (rnb[h] == 0) {          // optimizer ED(truth, query) == 0 on this haplotype: identical sequences
-                Y = X; Z = 0;
-            } else {
-                Y = altQ ? (u64)ed_checked(ed_overflow, R, W, bufQ, lq, wf, ed_cap) : 0;
-                if (!altT) Z = Y; else if (!altQ) Z = X; else Z = (u64)rnb[h];   // Z is the optimizer's finalised ED
-            }
-            const u64 tp = X + Y - Z;                    // (2X + 2Y - 2Z) / 2  :644
-            if (lane == 0) {
-                gm[AVK_M_BASEPAIR + 0] += tp; gm[AVK_M_BASEPAIR + 1] += 2 * X - tp + 2 * (u64)failT;
-                gm[AVK_M_BASEPAIR + 2] += tp; gm[AVK_M_BASEPAIR + 3] += 2 * Y - tp + 2 * (u64)failQ;
-            }
-            // per supported type that occurs in the cluster (absent types only ever receive zeros, :395-444)
-            #pragma unroll 1
-            for (int k = 0; k < n_slots; ++k) {
-                const int ft = slot_type[k];
-                if (!type_supported(ft)) continue;
-                const int ntf = (int)slot_cnt[2 * k], nqf = (int)slot_cnt[2 * k + 1];
-                u64 q_tp = 0, q_fp = 0, t_tp = 0, t_fn = 0;
-                if (nqf > 0) {                                           // :395-410
-                    if (nqf == nv[1]) { q_tp = tp; q_fp = 2 * Y - tp + 2 * (u64)failQ; }   // filtered == full query
-                    else {
-                        int failF, altF;
-                        const int lf = build_hap_seq(bufF, 1, h, best_r, ft, failF, altF);
-                        if (lf < 0) return lf == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
-                        u64 Yf, Zf;
-                        if (!altF) { Yf = 0; Zf = X; }
-                        else {
-                            Yf = (u64)ed_checked(ed_overflow, R, W, bufF, lf, wf, ed_cap);
-                            Zf = altT ? (u64)ed_checked(ed_overflow, bufT, lt, bufF, lf, wf, ed_cap) : Yf;
-                        }
-                        const u64 tpf = X + Yf - Zf;
-                        q_tp = tpf; q_fp = 2 * Yf - tpf + 2 * (u64)failF;
-                    }
-                }
-                if (ntf > 0) {                                           // :422-437
-                    if (ntf == nv[0]) { t_tp = tp; t_fn = 2 * X - tp + 2 * (u64)failT; }
-                    else {
-                        int failF, altF;
-                        const int lf = build_hap_seq(bufF, 0, h, best_r, ft, failF, altF);
-                        if (lf < 0) return lf == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
-                        u64 Xf, Zf;
-                        if (!altF) { Xf = 0; Zf = Y; }
-                        else {
-                            Xf = (u64)ed_checked(ed_overflow, R, W, bufF, lf, wf, ed_cap);
-                            Zf = altQ ? (u64)ed_checked(ed_overflow, bufF, lf, bufQ, lq, wf, ed_cap) : Xf;
-                        }
-                        const u64 tpf = Xf + Y - Zf;
-                        t_tp = tpf; t_fn = 2 * Xf - tpf + 2 * (u64)failF;
-                    }
-                }
-                if (lane == 0) {
-                    u64 *g = gm + AVK_N_METRICS * (1 + k) + AVK_M_BASEPAIR;
-                    g[0] += t_tp; g[1] += t_fn; g[2] += q_tp; g[3] += q_fp;
-                }
-            }
-        }
         // every supported type gets a (possibly all-zero) entry (:444)
         mask |= (1u << AVK_VT_SNV) | (1u << AVK_VT_INSERTION) | (1u << AVK_VT_DELETION) | (1u << AVK_VT_INDEL) |
                 (1u << AVK_VT_TR_CONTRACTION) | (1u << AVK_VT_TR_EXPANSION) | (1u << AVK_VT_SV_DELETION) | (1u << AVK_VT_SV_INSERTION);
-        __syncwarp();
-        // add_record_basepair_stats(): :455-522 (wrapping u64 like a release build).  Types without
-        // variants have zero totals and zero basepair counts, so their record rows stay zero.
+        // add_record_basepair_stats(): :455-522 (wrapping u64 like a release build).  Types without variants have
+        // zero totals and zero basepair counts, so their record rows stay zero.
         if (lane == 0) {
             u64 truth_total = 0, query_total = 0;
-            u64 *tq = slot_tot;
-            #pragma unroll 1
-            for (int oi = 0; oi < N; ++oi) {
-                const VInfo v = vinfo[oi];
-                const u64 cnt = (u64)((v.zyg == AVK_ZYG_HOM_ALT) ? 2 : 1) * v.raw;
-                tq[2 * v.slot + (v.is_truth ? 0 : 1)] += cnt;
-                if (v.is_truth) truth_total += cnt; else query_total += cnt;
-            }
-            const u64 tfn = gm[AVK_M_BASEPAIR + 1], qfp = gm[AVK_M_BASEPAIR + 3];
+#pragma unroll 1
+            for (int k = 0; k < n_slots; ++k) { truth_total += LD64(slot_tot + 16 * k); query_total += LD64(slot_tot + 16 * k + 8); }
+            const addr bp_ = gm + 8 * AVK_M_BASEPAIR;
+            const u64 tfn = LD64(bp_ + 8), qfp = LD64(bp_ + 24);
             const u64 ttp = 2 * truth_total - tfn, qtp = 2 * query_total - qfp;
-            if (!(ttp >= gm[AVK_M_BASEPAIR + 0]) || !(qtp >= gm[AVK_M_BASEPAIR + 2])) status = AVK_ST_TP_UNDERFLOW;
+            if (!(ttp >= LD64(bp_)) || !(qtp >= LD64(bp_ + 16))) status = AVK_ST_TP_UNDERFLOW;
             else {
-                gm[AVK_M_RECORD_BP + 0] += ttp; gm[AVK_M_RECORD_BP + 1] += tfn; gm[AVK_M_RECORD_BP + 2] += qtp; gm[AVK_M_RECORD_BP + 3] += qfp;
-                #pragma unroll 1
+                add4(gm + 8 * AVK_M_RECORD_BP, ttp, tfn, qtp, qfp);
+#pragma unroll 1
                 for (int k = 0; k < n_slots; ++k) {
-                    u64 *g = gm + AVK_N_METRICS * (1 + k);
-                    const u64 fn_ = g[AVK_M_BASEPAIR + 1], fp_ = g[AVK_M_BASEPAIR + 3];
-                    g[AVK_M_RECORD_BP + 0] += 2 * tq[2 * k] - fn_; g[AVK_M_RECORD_BP + 1] += fn_;
-                    g[AVK_M_RECORD_BP + 2] += 2 * tq[2 * k + 1] - fp_; g[AVK_M_RECORD_BP + 3] += fp_;
+                    const addr g = gm + (u32)(8 * AVK_N_METRICS * (1 + k));
+                    const u64 fn_ = LD64(g + 8 * (AVK_M_BASEPAIR + 1)), fp_ = LD64(g + 8 * (AVK_M_BASEPAIR + 3));
+                    add4(g + 8 * AVK_M_RECORD_BP, 2 * LD64(slot_tot + 16 * k) - fn_, fn_, 2 * LD64(slot_tot + 16 * k + 8) - fp_, fp_);
                 }
             }
         }
@@ -998,35 +995,32 @@ __device__ int RegionSolver::solve_compare(u64 r, const avk_compare_cfg &cfg, co
         u64 *dst = out.region_metrics + r * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
         // type -> slot lookup in a register: 4 bits per type, 15 = absent
         u64 lut = ~0ull;
-        #pragma unroll 1
+#pragma unroll 1
         for (int k = 0; k < n_slots; ++k) lut = (lut & ~(15ull << (4 * slot_type[k]))) | ((u64)k << (4 * slot_type[k]));
-        #pragma unroll 1
+#pragma unroll 1
         for (int i = lane; i < AVK_N_GROUPS * AVK_N_METRICS; i += 32) {
             const int g = i / AVK_N_METRICS, m = i - g * AVK_N_METRICS;
             u64 v = 0;
-            if (g == 0) v = gm[m];
+            if (g == 0) v = LD64(gm + 8 * m);
             else {
                 const int k = (int)((lut >> (4 * (g - 1))) & 15);
-                if (k != 15) v = gm[AVK_N_METRICS * (1 + k) + m];
+                if (k != 15) v = LD64(gm + (u32)(8 * (AVK_N_METRICS * (1 + k) + m)));
             }
             dst[i] = v;
         }
     }
-    if (want_seq) {
-        warp_copy(out.seq_pool + out.seq_off[r * 5], R, W);
-        if (lane == 0) out.seq_len[r * 5] = (u32)W;
-    }
+    if (want_seq) emit_seq(out, r, 0, -1);
     if (lane == 0) {
-        const int *rn = res_num + best_r * 6;
-        out.ed1[r] = shortcut ? 0u : (u32)rn[0];
-        out.ed2[r] = shortcut ? 0u : (u32)rn[1];
+        out.ed1[r] = shortcut ? 0u : (u32)LDI(rnb);
+        out.ed2[r] = shortcut ? 0u : (u32)LDI(rnb + 4);
         out.type_mask[r] = (uint16_t)mask;
     }
     return AVK_ST_OK;
 }
 
 // solve_merge_region(): merge_solver.rs:110-200
-__device__ int RegionSolver::solve_merge(u64 r, const avk_merge_cfg &cfg, const DevMergeOut &out) {
+template <bool SMEM>
+__device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, const DevMergeOut &out) {
     const DevBatch &b = *bp;
     const int lane = lane_id();
     const u32 K = b.n_inputs;
@@ -1038,11 +1032,11 @@ __device__ int RegionSolver::solve_merge(u64 r, const avk_merge_cfg &cfg, const 
     if (mbf <= 0 || K > 32) return AVK_ST_BAD_INPUT;
     {
         bool invalid = false;
-        int d0 = 0, d1 = 0, d2 = 0;
-        #pragma unroll 1
+        int sums[4] = {0, 0, 0, 0};
+#pragma unroll 1
         for (u32 k = 0; k < K; ++k) {
             const u64 v0 = b.var_off[r * K + k];
-            invalid = validate_list(v0, (int)(b.var_off[r * K + k + 1] - v0), d0, d1, d2) || invalid;
+            invalid = validate_list(v0, (int)(b.var_off[r * K + k + 1] - v0), sums) || invalid;
         }
         if (__any_sync(AVK_FULL, invalid)) return AVK_ST_BAD_INPUT;
     }
@@ -1051,7 +1045,7 @@ __device__ int RegionSolver::solve_merge(u64 r, const avk_merge_cfg &cfg, const 
     long long delta = 0;
     bool unknown = false;
     if ((u32)lane < K) {
-        #pragma unroll 1
+#pragma unroll 1
         for (u64 gv = b.var_off[r * K + lane]; gv < b.var_off[r * K + lane + 1]; ++gv) {
             const int z = b.zyg[gv];
             unknown = unknown || z == AVK_ZYG_UNKNOWN;
@@ -1062,22 +1056,25 @@ __device__ int RegionSolver::solve_merge(u64 r, const avk_merge_cfg &cfg, const 
     if (__any_sync(AVK_FULL, unknown)) return AVK_ST_BAD_ZYGOSITY;
     u32 match_row = ((u32)lane < K) ? (1u << lane) : 0;   // lane i holds match_sets[i] as a bit mask
     bool all_identical = true, no_conflict = true;
-    #pragma unroll 1
+#pragma unroll 1
     for (u32 i = 0; i < K; ++i) {
-        #pragma unroll 1
+#pragma unroll 1
         for (u32 j = i + 1; j < K; ++j) {
             const long long di = __shfl_sync(AVK_FULL, delta, i), dj = __shfl_sync(AVK_FULL, delta, j);
             bool exact = false;
             const bool empty_i = b.var_off[r * K + i + 1] == b.var_off[r * K + i];
             const bool empty_j = b.var_off[r * K + j + 1] == b.var_off[r * K + j];
             if (di == dj) {                                              // :135-143
-                bool bad;
-                int rc = setup_pair(r, i, j, false, bad);
+                int rc = setup_pair(r, i, j, false);
                 if (rc) return rc;
-                if (bad) return AVK_ST_BAD_INPUT;
                 rc = optimize(true);
                 if (rc) return rc;
-                exact = n_res > 0 && (res_num[0] + res_num[1] + res_num[2] + res_num[3] + res_num[4] + res_num[5] == 0);
+                if (n_res > 0) {
+                    int s = 0;
+#pragma unroll 1
+                    for (int k = 0; k < 6; ++k) s += LDI(res_num + 4 * k);
+                    exact = s == 0;
+                }
             }
             all_identical = all_identical && exact;
             no_conflict = no_conflict && (empty_i || empty_j || exact);   // :155-157
@@ -1107,7 +1104,6 @@ __device__ int RegionSolver::solve_merge(u64 r, const avk_merge_cfg &cfg, const 
         int n = 0;
         if (sel >= 0) { out.idx[r * K + 0] = (u8)sel; n = 1; }
         else for (u32 k = 0; k < K; ++k) if (idx_mask & (1u << k)) out.idx[r * K + (n++)] = (u8)k;
-        #pragma unroll 1
         for (u32 k = n; k < K; ++k) out.idx[r * K + k] = 0xFF;
         out.n_idx[r] = (u8)n;
     }
