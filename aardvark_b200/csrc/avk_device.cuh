@@ -290,16 +290,19 @@ __device__ __forceinline__ void mbar_init(u32 mbar_off) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-__device__ __noinline__ void tma_window_load(u32 dst_off, const u8 *gsrc, u32 bytes, u32 mbar_off, u32 *phase) {
+__device__ __forceinline__ void tma_window_issue(u32 dst_off, const u8 *gsrc, u32 bytes, u32 mbar_off) {
     // order this warp's earlier generic-proxy accesses to the window before the async-proxy write
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    const u32 mbar = smem_u32(avk_dyn_smem + mbar_off);
     if (lane_id() == 0) {
+        const u32 mbar = smem_u32(avk_dyn_smem + mbar_off);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(avk_dyn_smem + dst_off)), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
     }
+}
+__device__ __forceinline__ void tma_window_wait(u32 mbar_off, u32 *phase) {
+    const u32 mbar = smem_u32(avk_dyn_smem + mbar_off);
     const u32 ph = *phase;
     u32 done = 0;
 #pragma unroll 1

@@ -137,24 +137,25 @@ __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const Dev
     __syncwarp();
 }
 
-// Work distribution of one workspace tier.  ctrs[0] = work counter of this launch, ctrs[1] = number of
-// clusters that did not fit (appended to fail_list, re-run by the next tier).  n_work is read from
-// device memory when n_work_ptr is set, so that tiers can be chained without a host round trip.
+// Work distribution of one stage.  work_ctr = work counter of this launch, fail_ctr = number of clusters
+// that did not fit (appended to fail_list, re-run by a later stage).  n_work is read from device memory
+// when n_work_ptr is set, so that stages can be chained without a host round trip.
 struct TierArgs {
     const u32 *work_list;
     const u32 *n_work_ptr;
     u32 n_work;
-    u32 *ctrs;
+    u32 *work_ctr;
+    u32 *fail_ctr;
     u8 *arena_base;        // global tiers
     long long arena_bytes; // per warp
     u32 *fail_list;
     int last_tier;
     unsigned long long *work_out;
+    u8 *blobs;             // split tier: [n_regions][RB_SIZE] search results handed to the score kernel
 };
 
-// Persistent warps pull clusters from a global counter; one warp solves one cluster at a time.
-// SMEM tiers keep the warp's whole workspace (staged reference window, search nodes, queue) in
-// shared memory; global tiers take the clusters that do not fit.
+enum { MODE_FUSED = 0, MODE_SEARCH = 1, MODE_SCORE = 2 };
+
 // Per-CTA shared state: the batch descriptor and one solver object per warp (never a local-memory frame).
 template <bool SMEM>
 __device__ __forceinline__ RegionSolver<SMEM> &init_solver(const DevBatch &b, const TierArgs &t, DevBatch &sb, RegionSolver<SMEM> *sol) {
@@ -168,6 +169,7 @@ __device__ __forceinline__ RegionSolver<SMEM> &init_solver(const DevBatch &b, co
     if (lane_id() == 0) {
         s.bp = &sb;
         s.tma_phase = 0;
+        s.tma_pending = 0;
         s.arena_bytes = (u32)t.arena_bytes;
         s.arena = arena;
         if (SMEM) mbar_init((u32)arena);
@@ -176,7 +178,14 @@ __device__ __forceinline__ RegionSolver<SMEM> &init_solver(const DevBatch &b, co
     return s;
 }
 
-template <bool SMEM, int MIN_CTAS>
+// Persistent warps pull clusters from a global counter; one warp solves one cluster at a time.
+// SMEM stages keep the warp's whole workspace (staged reference window, variants, search nodes, queue, metric
+// rows) in shared memory; global stages take the clusters that do not fit.
+// MODE_FUSED runs solve_compare_region end to end.  The common tier is split into MODE_SEARCH (optimize_sequences ->
+// result blob) and MODE_SCORE (blob -> exact-GT, metrics, outputs): ncu shows the fused solver is bound by
+// instruction fetch (its executed path does not stay resident in the SM instruction cache), and two kernels of
+// half the footprint each run faster than one.
+template <bool SMEM, int MIN_CTAS, int MODE>
 __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, TierArgs t) {
     __shared__ DevBatch sb;
     __shared__ RegionSolver<SMEM> sol[8];
@@ -185,15 +194,27 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompar
     const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
     for (;;) {
         u32 idx = 0;
-        if (lane == 0) idx = atomicAdd(t.ctrs, 1u);
+        if (lane == 0) idx = atomicAdd(t.work_ctr, 1u);
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
         const u64 r = t.work_list ? t.work_list[idx] : idx;
-        int rc = s.solve_compare(r, cfg, out);
+        u8 *blob = t.blobs + r * (u64)RB_SIZE;
+        int rc;
+        if (MODE == MODE_SEARCH) {
+            rc = s.compare_search_to_blob(r, cfg, blob);
+            __syncwarp();
+            if (rc == SOLVE_OK) continue;                        // the score kernel finishes this cluster
+            if (lane == 0) *(int *)(blob + RB_NRES) = (rc == SOLVE_WORKSPACE) ? RB_FUSED : RB_DONE;
+        } else if (MODE == MODE_SCORE) {
+            if (*(const int *)(blob + RB_NRES) <= 0) continue;   // handled elsewhere
+            rc = s.compare_score_from_blob(r, cfg, out, blob);
+        } else {
+            rc = s.solve_compare(r, cfg, out);
+        }
         __syncwarp();
         if (rc == SOLVE_WORKSPACE) {
             if (!t.last_tier) {
-                if (lane == 0) t.fail_list[atomicAdd(t.ctrs + 1, 1u)] = (u32)r;
+                if (lane == 0) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
                 continue;
             }
             rc = AVK_ST_WORKSPACE;
@@ -214,7 +235,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_merge(DevBatch b, DevMergeOut
     const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
     for (;;) {
         u32 idx = 0;
-        if (lane == 0) idx = atomicAdd(t.ctrs, 1u);
+        if (lane == 0) idx = atomicAdd(t.work_ctr, 1u);
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
         const u64 r = t.work_list ? t.work_list[idx] : idx;
@@ -222,7 +243,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_merge(DevBatch b, DevMergeOut
         __syncwarp();
         if (rc == SOLVE_WORKSPACE) {
             if (!t.last_tier) {
-                if (lane == 0) t.fail_list[atomicAdd(t.ctrs + 1, 1u)] = (u32)r;
+                if (lane == 0) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
                 continue;
             }
             rc = AVK_ST_WORKSPACE;
@@ -298,7 +319,7 @@ struct avk_ctx {
     DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, strat_off, strat_idx, strat_totals,
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx;
     // workspace
-    DevBuf scratch, arena, counters, fail_a, fail_b, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    DevBuf blobs, scratch, arena, counters, fail_a, fail_b, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     // resident batch
     bool have_batch = false;
     u64 n_regions = 0, n_variants = 0;
@@ -372,7 +393,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->scratch, &ctx->arena, &ctx->counters, &ctx->fail_a, &ctx->fail_b,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->counters, &ctx->fail_a, &ctx->fail_b,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
@@ -469,19 +490,26 @@ static int run_alt_ed(avk_ctx *ctx, const DevBatch &db) {
     return AVK_OK;
 }
 
-// Workspace tiers.  Tiers 0-1 keep the per-warp workspace in shared memory (3 CTAs x 8 warps x 9 KB,
-// then 1 CTA x 8 warps x 28 KB per SM); tiers 2+ use global memory for the rare clusters whose search
-// does not fit.  Tiers 0-2 are launched back to back: each reads its work count from the previous
-// tier's fail counter in device memory, so the common case needs no host round trip.
-struct LaunchCfg {
+// Workspace stages.  The common tier keeps the per-warp workspace in shared memory; for compare it is split into a
+// search kernel and a score kernel (see k_compare).  Clusters whose search does not fit go down a chain of fused
+// stages: 8 warps x 27 KB of shared memory per SM, then global-memory arenas.  The first stages are launched back
+// to back: each reads its work count from an earlier stage's fail counter in device memory, so the common case
+// needs no host round trip.
+struct Stage {
+    int mode;              // MODE_*
     bool smem;
     int min_ctas;          // CTAs per SM the kernel is compiled for
     long long arena_bytes; // per warp
     int ctas;              // grid size (persistent)
+    int in_list;           // -1: all regions; else index of the fail list to consume (0 = A, 1 = B)
+    int in_ctr;            // counter index holding that list's length
+    int work_ctr;          // counter index of this launch's work counter
+    int fail_list;         // fail list to append to
+    int fail_ctr;          // counter index of that list's length
 };
 
 template <class F>
-static int run_tiers(avk_ctx *ctx, u64 n, F launch) {
+static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F launch) {
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
     ENSURE(ctx->fail_a, 4 * n);
@@ -490,67 +518,78 @@ static int run_tiers(avk_ctx *ctx, u64 n, F launch) {
     u32 *ctrs = (u32 *)ctx->counters.p;
     CK(cudaMemsetAsync(ctrs, 0, 256, ctx->stream));
     u32 *fail_lists[2] = {(u32 *)ctx->fail_a.p, (u32 *)ctx->fail_b.p};
-    const char *env_ctas = getenv("AVK_S0_CTAS_PER_SM");   // tuning knob (default 3)
-    const int s0_ctas = env_ctas ? atoi(env_ctas) : 3;
-    const LaunchCfg chain[3] = {{true, 3, 8192, sm * s0_ctas}, {true, 1, 27648, sm}, {false, 1, 2LL << 20, sm}};
-    ENSURE(ctx->arena, (size_t)chain[2].ctas * 8 * (size_t)chain[2].arena_bytes);
+    size_t garena = 0;
+    for (const Stage &st : stages) if (!st.smem) garena = std::max(garena, (size_t)st.ctas * 8 * (size_t)st.arena_bytes);
+    if (garena) ENSURE(ctx->arena, garena);
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
-    for (int t = 0; t < 3; ++t) {
+    int ev = 1;
+    for (size_t i = 0; i < stages.size(); ++i) {
+        const Stage &st = stages[i];
         TierArgs a;
-        a.work_list = t == 0 ? nullptr : fail_lists[(t - 1) & 1];
-        a.n_work_ptr = t == 0 ? nullptr : ctrs + 2 * (t - 1) + 1;
+        a.work_list = st.in_list < 0 ? nullptr : fail_lists[st.in_list];
+        a.n_work_ptr = st.in_list < 0 ? nullptr : ctrs + st.in_ctr;
         a.n_work = (u32)n;
-        a.ctrs = ctrs + 2 * t;
+        a.work_ctr = ctrs + st.work_ctr;
+        a.fail_ctr = ctrs + st.fail_ctr;
         a.arena_base = (u8 *)ctx->arena.p;
-        a.arena_bytes = chain[t].arena_bytes;
-        a.fail_list = fail_lists[t & 1];
+        a.arena_bytes = st.arena_bytes;
+        a.fail_list = fail_lists[st.fail_list];
         a.last_tier = 0;
         a.work_out = (unsigned long long *)ctx->work_ctr.p;
-        int ctas = chain[t].ctas;
-        if (t == 0) ctas = (int)std::min<u64>((u64)ctas, (n + 7) / 8);
-        launch(chain[t], a, ctas);
+        a.blobs = (u8 *)ctx->blobs.p;
+        int ctas = st.ctas;
+        if (st.in_list < 0) ctas = (int)std::min<u64>((u64)ctas, (n + 7) / 8);
+        launch(st, a, ctas);
         ctx->launches += 1;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->tev[t + 1], ctx->stream));
+        if (ev < 4 && (i + 1 == stages.size() || stages[i + 1].mode != MODE_SCORE)) CK(cudaEventRecord(ctx->tev[ev++], ctx->stream));
     }
-    u32 host_ctrs[8];
-    CK(cudaMemcpyAsync(host_ctrs, ctrs, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    while (ev < 4) CK(cudaEventRecord(ctx->tev[ev++], ctx->stream));
+    const Stage &lastst = stages.back();
+    u32 host_ctrs[16];
+    CK(cudaMemcpyAsync(host_ctrs, ctrs, 64, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->tier_fail[0] = host_ctrs[1]; ctx->tier_fail[1] = host_ctrs[3]; ctx->tier_fail[2] = host_ctrs[5];
     for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
-    u32 n_work = host_ctrs[5];
-    int prev = 2;
+    {   // diagnostics: overflow counts of the (up to) three chained tiers
+        int k = 0;
+        for (const Stage &st : stages) if (st.mode != MODE_SEARCH && k < 3) ctx->tier_fail[k++] = host_ctrs[st.fail_ctr];
+        while (k < 3) ctx->tier_fail[k++] = 0;
+    }
+    u32 n_work = host_ctrs[lastst.fail_ctr];
+    int cur_list = lastst.fail_list;
     // rare: clusters that overflow 2 MB per warp; host-synchronised escalation
-    const LaunchCfg big[2] = {{false, 1, 64LL << 20, (sm + 7) / 8}, {false, 1, 2048LL << 20, 1}};
+    const Stage big[2] = {{MODE_FUSED, false, 1, 64LL << 20, (sm + 7) / 8, 0, 0, 0, 0, 0}, {MODE_FUSED, false, 1, 2048LL << 20, 1, 0, 0, 0, 0, 0}};
     for (int t = 0; t < 2 && n_work > 0; ++t) {
         ENSURE(ctx->arena, (size_t)big[t].ctas * 8 * (size_t)big[t].arena_bytes);
-        CK(cudaMemsetAsync(ctrs + 8, 0, 8, ctx->stream));
+        CK(cudaMemsetAsync(ctrs + 32, 0, 8, ctx->stream));
         TierArgs a;
-        a.work_list = fail_lists[prev & 1];
+        a.work_list = fail_lists[cur_list];
         a.n_work_ptr = nullptr;
         a.n_work = n_work;
-        a.ctrs = ctrs + 8;
+        a.work_ctr = ctrs + 32;
+        a.fail_ctr = ctrs + 33;
         a.arena_base = (u8 *)ctx->arena.p;
         a.arena_bytes = big[t].arena_bytes;
-        a.fail_list = fail_lists[(prev + 1) & 1];
+        a.fail_list = fail_lists[cur_list ^ 1];
         a.last_tier = t == 1;
         a.work_out = (unsigned long long *)ctx->work_ctr.p;
+        a.blobs = (u8 *)ctx->blobs.p;
         launch(big[t], a, big[t].ctas);
         ctx->launches += 1;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(host_ctrs, ctrs + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(host_ctrs, ctrs + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         n_work = host_ctrs[1];
-        prev += 1;
+        cur_list ^= 1;
     }
     return AVK_OK;
 }
 
-template <bool SMEM, int MIN_CTAS>
+template <bool SMEM, int MIN_CTAS, int MODE>
 static void launch_compare(avk_ctx *ctx, const DevBatch &db, const DevCompareOut &out, const avk_compare_cfg &c, const TierArgs &a, int ctas) {
     const size_t smem = SMEM ? (size_t)a.arena_bytes * 8 : 0;
-    if (SMEM) cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_compare<SMEM, MIN_CTAS><<<ctas, 256, smem, ctx->stream>>>(db, out, c, a);
+    if (SMEM) cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_compare<SMEM, MIN_CTAS, MODE><<<ctas, 256, smem, ctx->stream>>>(db, out, c, a);
 }
 template <bool SMEM, int MIN_CTAS>
 static void launch_merge(avk_ctx *ctx, const DevBatch &db, const DevMergeOut &out, const avk_merge_cfg &c, const TierArgs &a, int ctas) {
@@ -587,10 +626,20 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     int rc = run_alt_ed(ctx, db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = run_tiers(ctx, n, [&](const LaunchCfg &lc, const TierArgs &a, int ctas) {
-        if (lc.smem && lc.min_ctas == 3) launch_compare<true, 3>(ctx, db, out, c, a, ctas);
-        else if (lc.smem) launch_compare<true, 1>(ctx, db, out, c, a, ctas);
-        else launch_compare<false, 1>(ctx, db, out, c, a, ctas);
+    ENSURE(ctx->blobs, (size_t)n * RB_SIZE);
+    const int sm = ctx->sm_count;
+    const std::vector<Stage> stages = {
+        // mode, smem, min_ctas, arena, ctas, in_list, in_ctr, work_ctr, fail_list, fail_ctr
+        {MODE_SEARCH, true, 3, 8192, sm * 3, -1, 0, 0, 0, 1},
+        {MODE_SCORE, true, 4, 5120, sm * 4, -1, 0, 2, 0, 1},
+        {MODE_FUSED, true, 1, 27648, sm, 0, 1, 3, 1, 4},
+        {MODE_FUSED, false, 1, 2LL << 20, sm, 1, 4, 5, 0, 6},
+    };
+    rc = run_stages(ctx, n, stages, [&](const Stage &st, const TierArgs &a, int ctas) {
+        if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(ctx, db, out, c, a, ctas);
+        else if (st.mode == MODE_SCORE) launch_compare<true, 4, MODE_SCORE>(ctx, db, out, c, a, ctas);
+        else if (st.smem) launch_compare<true, 1, MODE_FUSED>(ctx, db, out, c, a, ctas);
+        else launch_compare<false, 1, MODE_FUSED>(ctx, db, out, c, a, ctas);
     });
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -784,9 +833,15 @@ extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, cons
     rc = run_alt_ed(ctx, db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = run_tiers(ctx, n, [&](const LaunchCfg &lc, const TierArgs &a, int ctas) {
-        if (lc.smem && lc.min_ctas == 3) launch_merge<true, 3>(ctx, db, mo, c, a, ctas);
-        else if (lc.smem) launch_merge<true, 1>(ctx, db, mo, c, a, ctas);
+    const int sm = ctx->sm_count;
+    const std::vector<Stage> stages = {
+        {MODE_FUSED, true, 3, 8192, sm * 3, -1, 0, 0, 0, 1},
+        {MODE_FUSED, true, 1, 27648, sm, 0, 1, 3, 1, 4},
+        {MODE_FUSED, false, 1, 2LL << 20, sm, 1, 4, 5, 0, 6},
+    };
+    rc = run_stages(ctx, n, stages, [&](const Stage &st, const TierArgs &a, int ctas) {
+        if (st.smem && st.min_ctas == 3) launch_merge<true, 3>(ctx, db, mo, c, a, ctas);
+        else if (st.smem) launch_merge<true, 1>(ctx, db, mo, c, a, ctas);
         else launch_merge<false, 1>(ctx, db, mo, c, a, ctas);
     });
     if (rc != AVK_OK) return rc;

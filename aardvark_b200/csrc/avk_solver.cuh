@@ -72,7 +72,7 @@ enum { H_TRP = 0, H_QRP = 4, H_TML = 8, H_QML = 12, H_TMR = 16, H_QMR = 20, H_TS
 // exact node: ints {id, errors, depth, t_ref_pos, q_ref_pos, t_mlen, q_mlen, t_mref, q_mref, d}
 enum { XN_ID = 0, XN_ERR = 4, XN_DEPTH = 8, XN_TRP = 12, XN_QRP = 16, XN_TML = 20, XN_QML = 24, XN_TMR = 28, XN_QMR = 32, XN_D = 36, XN_HDR = 48 };
 // sequence descriptors written by build_hap_seq: {mlen, cur, failed, n_alt}
-enum { SD_MLEN = 0, SD_CUR = 4, SD_FAILED = 8, SD_NALT = 12, SD_SIZE = 16 };
+enum { SD_MLEN = 0, SD_CUR = 4, SD_FAILED = 8, SD_NALT = 12, SD_LAST = 16, SD_SIZE = 32 };   // SD_LAST: order index of the last spliced ALT
 
 static __device__ __forceinline__ bool type_supported(int t) {   // SUPPORTED_VARIANT_TYPES waffle_solver.rs:82-91
     return t == AVK_VT_SNV || t == AVK_VT_INSERTION || t == AVK_VT_DELETION || t == AVK_VT_INDEL ||
@@ -96,6 +96,7 @@ struct RegionSolver {
     int N;
     int mbf;
     u32 tma_phase;        // mbarrier parity of the next window load
+    int tma_pending;      // a window load has been issued and not yet waited for
     // ---- arena layout ----
     addr vinfo;           // [N] VI_* records
     addr bucket;          // [N+1] int
@@ -135,7 +136,8 @@ struct RegionSolver {
         const int a0 = start & ~15;
         const int bytes = align_up(end - a0 + 16, 16);        // >= 16 bytes of slack for ld4u
         if ((u32)(ARENA_HDR + bytes + 2048) > arena_bytes) return false;
-        tma_window_load((u32)arena + ARENA_HDR, contig + a0, (u32)bytes, (u32)arena, &tma_phase);
+        tma_window_issue((u32)arena + ARENA_HDR, contig + a0, (u32)bytes, (u32)arena);   // waited for at the end of setup_pair
+        tma_pending = 1;
         ref_base = arena + ARENA_HDR - (u32)a0;
         region_off = ARENA_HDR + bytes;
         return true;
@@ -274,6 +276,7 @@ struct RegionSolver {
         off = (off + 15u) & ~15u;
         dyn = arena + off;
         dyn_bytes = arena_bytes - off;
+        if (SMEM && tma_pending) { tma_window_wait((u32)arena, &tma_phase); tma_pending = 0; }
         __syncwarp();
         return SOLVE_OK;
     }
@@ -414,8 +417,27 @@ struct RegionSolver {
         __syncwarp();
         const VS T = make_vs(n_seq(nb, 2 * h), t_ml, t_mr, t_rp), Q = make_vs(n_seq(nb, 2 * h + 1), q_ml, q_mr, q_rp);
         const int cap = (wf_cap - 3) / 2;
-        int rc = dwfa_run<SMEM>(n_wf(nb, h), &ed, cap, T, Q, false, wk());
-        if (rc == DWFA_OK && finalize) rc = dwfa_run<SMEM>(n_wf(nb, h), &ed, cap, T, Q, true, wk());
+        int rc = DWFA_OK;
+        bool done = false;
+        if (ed == 0) {
+            // Fast path of DWFALite::update for the single diagonal: both sequences are reading the SAME reference
+            // bytes from offset d on (aligned implicit tails), so the run extends to the end of the shorter one.
+            const int d = LDI(n_wf(nb, h));
+            if (d >= t_ml && d >= q_ml && T.tail + (u32)(d - t_ml) == Q.tail + (u32)(d - q_ml)) {
+                const int nd = max(d, min(T.len, Q.len));
+                if (lane_id() == 0) {
+                    ST32(n_wf(nb, h), nd);
+                    ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1); ST64(wk() + WK_MATCHED, LD64(wk() + WK_MATCHED) + (u64)(nd - d));
+                }
+                __syncwarp();
+                done = !finalize || T.len == Q.len;     // finalize: the diagonal is at the end of both <=> equal lengths
+                if (done && finalize && lane_id() == 0) ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1);
+            }
+        }
+        if (!done) {
+            rc = dwfa_run<SMEM>(n_wf(nb, h), &ed, cap, T, Q, false, wk());
+            if (rc == DWFA_OK && finalize) rc = dwfa_run<SMEM>(n_wf(nb, h), &ed, cap, T, Q, true, wk());
+        }
         if (rc != DWFA_OK) return SOLVE_WORKSPACE;   // ED bound exceeded: never expected
         if (lane_id() == 0) {
             ST32(hb + H_TRP, t_rp); ST32(hb + H_QRP, q_rp); ST32(hb + H_TML, t_ml); ST32(hb + H_QML, q_ml);
@@ -574,7 +596,11 @@ struct RegionSolver {
         __syncwarp();
         // DWFA update with max ED 0: extend the single diagonal, then require an end to be reached
         const VS T = make_vs(x_seq(nb, 0), t_ml, t_mr, t_rp), Q = make_vs(x_seq(nb, 1), q_ml, q_mr, q_rp);
-        const int ext = (d < T.len && d < Q.len) ? vs_lcp<SMEM>(T, d, Q, d) : 0;
+        int ext = 0;
+        if (d < T.len && d < Q.len) {
+            if (d >= t_ml && d >= q_ml && T.tail + (u32)(d - t_ml) == Q.tail + (u32)(d - q_ml)) ext = min(T.len, Q.len) - d;   // aligned tails
+            else ext = vs_lcp<SMEM>(T, d, Q, d);
+        }
         d += ext;
         const bool alive = finalize ? ((d >= T.len) && (d >= Q.len))    // update ok + finalize ok <=> sequences equal
                                     : ((d >= T.len) || (d >= Q.len));
@@ -698,7 +724,7 @@ struct RegionSolver {
     __device__ __noinline__ int build_hap_seq(int k, int side, int hap, int r, int type_filter) {
         const addr dst = dyn + (u32)(k * seq_cap);
         const addr ra = res_alle + (u32)(r * Npad);
-        int cur = start, mlen = 0, failed = 0, n_alt = 0;
+        int cur = start, mlen = 0, failed = 0, n_alt = 0, last = 0;
         const int n = N;
 #pragma unroll 1
         for (int oi = 0; oi < n; ++oi) {
@@ -717,11 +743,12 @@ struct RegionSolver {
             mlen += nref + l1;
             cur = vpos + l0;
             n_alt += 1;
+            last = oi;
         }
         if (cur > end) return -2;
         if (lane_id() == 0) {
             const addr sd = sdesc + (u32)(k * SD_SIZE);
-            ST32(sd + SD_MLEN, mlen); ST32(sd + SD_CUR, cur); ST32(sd + SD_FAILED, failed); ST32(sd + SD_NALT, n_alt);
+            ST32(sd + SD_MLEN, mlen); ST32(sd + SD_CUR, cur); ST32(sd + SD_FAILED, failed); ST32(sd + SD_NALT, n_alt); ST32(sd + SD_LAST, last);
         }
         __syncwarp();
         return 0;
@@ -734,6 +761,22 @@ struct RegionSolver {
         const int mlen = LDI(sd + SD_MLEN), cur = LDI(sd + SD_CUR);
         v.data = dyn + (u32)(k * seq_cap); v.tail = ref_base + cur; v.mlen = mlen; v.len = mlen + (end - cur);
         return v;
+    }
+    // ED(reference window, buffer k).  A haplotype whose only spliced ALT is a single-base substitution has the
+    // window's length and differs from it in at most that one position, so the distance is 0 or 1 without aligning.
+    __device__ __forceinline__ u64 ed_to_ref(int k) {
+        const addr sd = sdesc + (u32)(k * SD_SIZE);
+        if (LDI(sd + SD_NALT) == 1) {
+            const addr rec = vi(LDI(sd + SD_LAST));
+            if (LD32(rec + VI_L0) == 1 && LD32(rec + VI_L1) == 1) {
+                if (lane_id() == 0) {
+                    ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
+                    ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1);
+                }
+                return LD8(alle_base + LD32(rec + VI_AOFF) + 1) != LD8(ref_base + LD32(rec + VI_POS)) ? 1u : 0u;
+            }
+        }
+        return ed_between(-1, k);
     }
     // global edit distance between two sequence buffers, with overflow trap
     __device__ __noinline__ u64 ed_between(int ka, int kb) {
@@ -771,14 +814,21 @@ struct RegionSolver {
     }
 
     __device__ int solve_compare(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out);
+    __device__ int compare_prepare(u64 r, const avk_compare_cfg &cfg, bool want_metrics);
+    __device__ int compare_search_to_blob(u64 r, const avk_compare_cfg &cfg, u8 *blob);
+    __device__ int compare_score_from_blob(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out, const u8 *blob);
+    __device__ int compare_score(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out);
     __device__ int solve_merge(u64 r, const avk_merge_cfg &cfg, const DevMergeOut &out);
 };
 
-// solve_compare_region(): returns AVK_ST_* (>= 0) or SOLVE_WORKSPACE
+// Hand-off record between the search kernel and the score kernel of the common tier (N <= 16, <= 8 results).
+enum { RB_NRES = 0, RB_ALLE = 16, RB_NUM = 16 + 8 * 16, RB_SIZE = 16 + 8 * 16 + 8 * 24 };
+enum { RB_FUSED = -1, RB_DONE = -2 };   // n_res values: handled by a fused tier / already final (error status written)
+
+// Loads region r and lays out the arena (first half of solve_compare_region, waffle_solver.rs:122-148).
 template <bool SMEM>
-__device__ int RegionSolver<SMEM>::solve_compare(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out) {
+__device__ int RegionSolver<SMEM>::compare_prepare(u64 r, const avk_compare_cfg &cfg, bool want_metrics) {
     const DevBatch &b = *bp;
-    const int lane = lane_id();
     const u32 c = b.contig[r];
     start = (int)b.start[r];
     end = (int)b.end[r];
@@ -786,12 +836,60 @@ __device__ int RegionSolver<SMEM>::solve_compare(u64 r, const avk_compare_cfg &c
     mbf = (int)cfg.max_branch_factor;
     if (mbf <= 0) return AVK_ST_BAD_INPUT;
     if (!begin_region(b.contig_ptr[c])) return SOLVE_WORKSPACE;
-    int rc = setup_pair(r, 0, 1, true);
-    if (rc) return rc;
-    const int n = N, npad = Npad;
+    return setup_pair(r, 0, 1, want_metrics);
+}
 
+// Search phase -> result blob (split tier).  Returns SOLVE_OK with the blob filled, or a status.
+template <bool SMEM>
+__device__ int RegionSolver<SMEM>::compare_search_to_blob(u64 r, const avk_compare_cfg &cfg, u8 *blob) {
+    int rc = compare_prepare(r, cfg, false);
+    if (rc) return rc;
+    if (N > 16) return SOLVE_WORKSPACE;
     rc = optimize(false);
     if (rc) return rc;
+    const int lane = lane_id();
+    const int nres = n_res;
+#pragma unroll 1
+    for (int i = lane; i < nres * 16; i += 32) blob[RB_ALLE + i] = LD8(res_alle + (u32)((i >> 4) * Npad + (i & 15)));
+#pragma unroll 1
+    for (int i = lane; i < nres * 6; i += 32) ((int *)(blob + RB_NUM))[i] = LDI(res_num + 4 * i);
+    if (lane == 0) *(int *)(blob + RB_NRES) = nres;
+    return SOLVE_OK;
+}
+
+// Score phase from a result blob (split tier).
+template <bool SMEM>
+__device__ int RegionSolver<SMEM>::compare_score_from_blob(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out, const u8 *blob) {
+    int rc = compare_prepare(r, cfg, true);
+    if (rc) return rc;
+    const int lane = lane_id();
+    const int nres = *(const int *)(blob + RB_NRES);
+    if (nres > res_cap) return SOLVE_WORKSPACE;
+#pragma unroll 1
+    for (int i = lane; i < nres * 16; i += 32) ST8(res_alle + (u32)((i >> 4) * Npad + (i & 15)), blob[RB_ALLE + i]);
+#pragma unroll 1
+    for (int i = lane; i < nres * 6; i += 32) ST32(res_num + 4 * i, ((const int *)(blob + RB_NUM))[i]);
+    n_res = nres;
+    __syncwarp();
+    return compare_score(r, cfg, out);
+}
+
+// solve_compare_region(): returns AVK_ST_* (>= 0) or SOLVE_WORKSPACE
+template <bool SMEM>
+__device__ int RegionSolver<SMEM>::solve_compare(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out) {
+    int rc = compare_prepare(r, cfg, true);
+    if (rc) return rc;
+    rc = optimize(false);
+    if (rc) return rc;
+    return compare_score(r, cfg, out);
+}
+
+// Second half of solve_compare_region (waffle_solver.rs:168-284): the equal-best results are in res_alle/res_num.
+template <bool SMEM>
+__device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out) {
+    const int lane = lane_id();
+    const int n = N, npad = Npad;
+    int rc;
 
     int best_r = 0;
     bool shortcut = false;
@@ -904,13 +1002,13 @@ __device__ int RegionSolver<SMEM>::solve_compare(u64 r, const avk_compare_cfg &c
         const u64 failT = (u64)LDI(sdesc + SD_FAILED), failQ = (u64)LDI(sdesc + SD_SIZE + SD_FAILED);
         // X = ED(ref, truth), Y = ED(ref, query), Z = ED(truth, query).  A haplotype without a spliced ALT IS the
         // reference window; Z is the optimizer's finalised (exact Levenshtein) distance of this haplotype pair.
-        const u64 X = altT ? ed_between(-1, 0) : 0;
+        const u64 X = altT ? ed_to_ref(0) : 0;
         if (shortcut) {   // generate_exact_match(): :559-598 -- joint gets 2 * ED(ref, truth) on both sides
             if (lane == 0) add4(gm + 8 * AVK_M_BASEPAIR, 2 * X, 0, 2 * X, 0);
             continue;
         }
         const u64 Z = (u64)LDI(rnb + 4 * h);
-        const u64 Y = (Z == 0) ? X : (altQ ? ed_between(-1, 1) : 0);
+        const u64 Y = (Z == 0) ? X : (altQ ? ed_to_ref(1) : 0);
         const u64 tp = X + Y - Z;                    // (2X + 2Y - 2Z) / 2  :644
         if (lane == 0) add4(gm + 8 * AVK_M_BASEPAIR, tp, 2 * X - tp + 2 * failT, tp, 2 * Y - tp + 2 * failQ);
         // per supported type that occurs in the cluster (absent types only ever receive zeros, :395-444)
@@ -935,7 +1033,7 @@ __device__ int RegionSolver<SMEM>::solve_compare(u64 r, const avk_compare_cfg &c
                     const bool alt_other = side ? (altT != 0) : (altQ != 0);
                     u64 Ef = 0, Zf = other_ref;
                     if (altF) {
-                        Ef = ed_between(-1, 2);
+                        Ef = ed_to_ref(2);
                         Zf = alt_other ? (side ? ed_between(0, 2) : ed_between(2, 1)) : Ef;
                     }
                     f_tp = other_ref + Ef - Zf;
