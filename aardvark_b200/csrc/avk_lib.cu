@@ -152,6 +152,7 @@ struct TierArgs {
     int last_tier;
     unsigned long long *work_out;
     u8 *blobs;             // split tier: [n_regions][RB_SIZE] search results handed to the score kernel
+    int n_lo, n_hi;        // stages that scan all regions only take clusters with n_lo <= #variants <= n_hi
 };
 
 enum { MODE_FUSED = 0, MODE_SEARCH = 1, MODE_SCORE = 2 };
@@ -198,6 +199,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompar
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
         const u64 r = t.work_list ? t.work_list[idx] : idx;
+        if (!t.work_list) {   // self-selection by cluster size: the size classes run concurrently on separate streams
+            const int nvar = (int)(sb.var_off[r * 2 + 2] - sb.var_off[r * 2]);
+            if (nvar < t.n_lo || nvar > t.n_hi) continue;
+        }
         u8 *blob = t.blobs + r * (u64)RB_SIZE;
         int rc;
         if (MODE == MODE_SEARCH) {
@@ -239,6 +244,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_merge(DevBatch b, DevMergeOut
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
         const u64 r = t.work_list ? t.work_list[idx] : idx;
+        if (!t.work_list) {
+            const int nvar = (int)(sb.var_off[r * K + K] - sb.var_off[r * K]);
+            if (nvar < t.n_lo || nvar > t.n_hi) continue;
+        }
         int rc = s.solve_merge(r, cfg, out);
         __syncwarp();
         if (rc == SOLVE_WORKSPACE) {
@@ -331,6 +340,8 @@ struct avk_ctx {
     avk_work_counters last_work = {0, 0, 0, 0, 0};
     u32 tier_fail[3] = {0, 0, 0};
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     float tier_ms[3] = {0, 0, 0};
 };
 
@@ -381,6 +392,9 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->tev) cudaEventCreate(&e);
+    for (auto &st : ctx->side) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (auto &e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ctx;
     return AVK_OK;
 }
@@ -501,11 +515,14 @@ struct Stage {
     int min_ctas;          // CTAs per SM the kernel is compiled for
     long long arena_bytes; // per warp
     int ctas;              // grid size (persistent)
+    int warps;             // warps per CTA
     int in_list;           // -1: all regions; else index of the fail list to consume (0 = A, 1 = B)
     int in_ctr;            // counter index holding that list's length
     int work_ctr;          // counter index of this launch's work counter
     int fail_list;         // fail list to append to
     int fail_ctr;          // counter index of that list's length
+    int stream;            // 0 main; 1, 2: side streams of the concurrent first group
+    int n_lo, n_hi;        // cluster-size class (stages scanning all regions)
 };
 
 template <class F>
@@ -519,12 +536,23 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
     CK(cudaMemsetAsync(ctrs, 0, 256, ctx->stream));
     u32 *fail_lists[2] = {(u32 *)ctx->fail_a.p, (u32 *)ctx->fail_b.p};
     size_t garena = 0;
-    for (const Stage &st : stages) if (!st.smem) garena = std::max(garena, (size_t)st.ctas * 8 * (size_t)st.arena_bytes);
+    for (const Stage &st : stages) if (!st.smem) garena = std::max(garena, (size_t)st.ctas * st.warps * (size_t)st.arena_bytes);
     if (garena) ENSURE(ctx->arena, garena);
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     int ev = 1;
+    bool forked = false, joined = false;
     for (size_t i = 0; i < stages.size(); ++i) {
         const Stage &st = stages[i];
+        cudaStream_t strm = st.stream == 0 ? ctx->stream : ctx->side[st.stream - 1];
+        if (st.stream != 0 && !forked) {   // side streams start after everything queued so far on the main stream
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            for (int k = 0; k < 2; ++k) CK(cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0));
+            forked = true;
+        }
+        if (forked && !joined && st.in_list >= 0) {   // first chained stage: wait for the concurrent group
+            for (int k = 0; k < 2; ++k) { CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); }
+            joined = true;
+        }
         TierArgs a;
         a.work_list = st.in_list < 0 ? nullptr : fail_lists[st.in_list];
         a.n_work_ptr = st.in_list < 0 ? nullptr : ctrs + st.in_ctr;
@@ -537,12 +565,16 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
         a.last_tier = 0;
         a.work_out = (unsigned long long *)ctx->work_ctr.p;
         a.blobs = (u8 *)ctx->blobs.p;
+        a.n_lo = st.n_lo; a.n_hi = st.n_hi;
         int ctas = st.ctas;
-        if (st.in_list < 0) ctas = (int)std::min<u64>((u64)ctas, (n + 7) / 8);
-        launch(st, a, ctas);
+        if (st.in_list < 0) ctas = (int)std::min<u64>((u64)ctas, (n + st.warps - 1) / st.warps);
+        launch(st, a, ctas, strm);
         ctx->launches += 1;
         CK(cudaGetLastError());
-        if (ev < 4 && (i + 1 == stages.size() || stages[i + 1].mode != MODE_SCORE)) CK(cudaEventRecord(ctx->tev[ev++], ctx->stream));
+        if (ev < 3 && st.stream == 0 && stages[i].mode != MODE_SEARCH && (i + 1 < stages.size())) CK(cudaEventRecord(ctx->tev[ev++], ctx->stream));
+    }
+    if (forked && !joined) {
+        for (int k = 0; k < 2; ++k) { CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); }
     }
     while (ev < 4) CK(cudaEventRecord(ctx->tev[ev++], ctx->stream));
     const Stage &lastst = stages.back();
@@ -558,9 +590,9 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
     u32 n_work = host_ctrs[lastst.fail_ctr];
     int cur_list = lastst.fail_list;
     // rare: clusters that overflow 2 MB per warp; host-synchronised escalation
-    const Stage big[2] = {{MODE_FUSED, false, 1, 64LL << 20, (sm + 7) / 8, 0, 0, 0, 0, 0}, {MODE_FUSED, false, 1, 2048LL << 20, 1, 0, 0, 0, 0, 0}};
+    const Stage big[2] = {{MODE_FUSED, false, 1, 64LL << 20, (sm + 7) / 8, 8, 0, 0, 0, 0, 0, 0, 0, 0x7fffffff}, {MODE_FUSED, false, 1, 2048LL << 20, 1, 8, 0, 0, 0, 0, 0, 0, 0, 0x7fffffff}};
     for (int t = 0; t < 2 && n_work > 0; ++t) {
-        ENSURE(ctx->arena, (size_t)big[t].ctas * 8 * (size_t)big[t].arena_bytes);
+        ENSURE(ctx->arena, (size_t)big[t].ctas * big[t].warps * (size_t)big[t].arena_bytes);
         CK(cudaMemsetAsync(ctrs + 32, 0, 8, ctx->stream));
         TierArgs a;
         a.work_list = fail_lists[cur_list];
@@ -574,7 +606,8 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
         a.last_tier = t == 1;
         a.work_out = (unsigned long long *)ctx->work_ctr.p;
         a.blobs = (u8 *)ctx->blobs.p;
-        launch(big[t], a, big[t].ctas);
+        a.n_lo = 0; a.n_hi = 0x7fffffff;
+        launch(big[t], a, big[t].ctas, ctx->stream);
         ctx->launches += 1;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(host_ctrs, ctrs + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -586,16 +619,16 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
 }
 
 template <bool SMEM, int MIN_CTAS, int MODE>
-static void launch_compare(avk_ctx *ctx, const DevBatch &db, const DevCompareOut &out, const avk_compare_cfg &c, const TierArgs &a, int ctas) {
-    const size_t smem = SMEM ? (size_t)a.arena_bytes * 8 : 0;
+static void launch_compare(avk_ctx *ctx, const DevBatch &db, const DevCompareOut &out, const avk_compare_cfg &c, const TierArgs &a, int ctas, int warps, cudaStream_t strm) {
+    const size_t smem = SMEM ? (size_t)a.arena_bytes * warps : 0;
     if (SMEM) cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_compare<SMEM, MIN_CTAS, MODE><<<ctas, 256, smem, ctx->stream>>>(db, out, c, a);
+    k_compare<SMEM, MIN_CTAS, MODE><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
 }
 template <bool SMEM, int MIN_CTAS>
-static void launch_merge(avk_ctx *ctx, const DevBatch &db, const DevMergeOut &out, const avk_merge_cfg &c, const TierArgs &a, int ctas) {
-    const size_t smem = SMEM ? (size_t)a.arena_bytes * 8 : 0;
+static void launch_merge(avk_ctx *ctx, const DevBatch &db, const DevMergeOut &out, const avk_merge_cfg &c, const TierArgs &a, int ctas, int warps, cudaStream_t strm) {
+    const size_t smem = SMEM ? (size_t)a.arena_bytes * warps : 0;
     if (SMEM) cudaFuncSetAttribute(k_merge<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_merge<SMEM, MIN_CTAS><<<ctas, 256, smem, ctx->stream>>>(db, out, c, a);
+    k_merge<SMEM, MIN_CTAS><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
 }
 
 static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, const u64 *strat_off_dev,
@@ -628,18 +661,21 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     ENSURE(ctx->blobs, (size_t)n * RB_SIZE);
     const int sm = ctx->sm_count;
+    const int INF = 0x7fffffff;
     const std::vector<Stage> stages = {
-        // mode, smem, min_ctas, arena, ctas, in_list, in_ctr, work_ctr, fail_list, fail_ctr
-        {MODE_SEARCH, true, 3, 8192, sm * 3, -1, 0, 0, 0, 1},
-        {MODE_SCORE, true, 4, 5120, sm * 4, -1, 0, 2, 0, 1},
-        {MODE_FUSED, true, 1, 27648, sm, 0, 1, 3, 1, 4},
-        {MODE_FUSED, false, 1, 2LL << 20, sm, 1, 4, 5, 0, 6},
+        // mode, smem, min_ctas, arena, ctas, warps, in_list, in_ctr, work_ctr, fail_list, fail_ctr, stream, n_lo, n_hi
+        {MODE_SEARCH, true, 3, 8192, sm * 3, 8, -1, 0, 0, 0, 1, 0, 0, INF},
+        {MODE_SCORE, true, 4, 5120, sm * 4, 8, -1, 0, 2, 0, 1, 0, 0, INF},
+        // chain for clusters that did not fit the common tier
+        {MODE_FUSED, true, 1, 27648, sm, 8, 0, 1, 3, 1, 4, 0, 0, INF},
+        {MODE_FUSED, false, 1, 2LL << 20, sm, 8, 1, 4, 5, 0, 6, 0, 0, INF},
     };
-    rc = run_stages(ctx, n, stages, [&](const Stage &st, const TierArgs &a, int ctas) {
-        if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(ctx, db, out, c, a, ctas);
-        else if (st.mode == MODE_SCORE) launch_compare<true, 4, MODE_SCORE>(ctx, db, out, c, a, ctas);
-        else if (st.smem) launch_compare<true, 1, MODE_FUSED>(ctx, db, out, c, a, ctas);
-        else launch_compare<false, 1, MODE_FUSED>(ctx, db, out, c, a, ctas);
+    rc = run_stages(ctx, n, stages, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
+        if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(ctx, db, out, c, a, ctas, st.warps, strm);
+        else if (st.mode == MODE_SCORE) launch_compare<true, 4, MODE_SCORE>(ctx, db, out, c, a, ctas, st.warps, strm);
+        else if (st.smem && st.min_ctas == 2) launch_compare<true, 2, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);
+        else if (st.smem) launch_compare<true, 1, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);
+        else launch_compare<false, 1, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);
     });
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -834,15 +870,16 @@ extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, cons
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     const int sm = ctx->sm_count;
+    const int INF = 0x7fffffff;
     const std::vector<Stage> stages = {
-        {MODE_FUSED, true, 3, 8192, sm * 3, -1, 0, 0, 0, 1},
-        {MODE_FUSED, true, 1, 27648, sm, 0, 1, 3, 1, 4},
-        {MODE_FUSED, false, 1, 2LL << 20, sm, 1, 4, 5, 0, 6},
+        {MODE_FUSED, true, 3, 8192, sm * 3, 8, -1, 0, 0, 0, 1, 0, 0, INF},
+        {MODE_FUSED, true, 1, 27648, sm, 8, 0, 1, 3, 1, 4, 0, 0, INF},
+        {MODE_FUSED, false, 1, 2LL << 20, sm, 8, 1, 4, 5, 0, 6, 0, 0, INF},
     };
-    rc = run_stages(ctx, n, stages, [&](const Stage &st, const TierArgs &a, int ctas) {
-        if (st.smem && st.min_ctas == 3) launch_merge<true, 3>(ctx, db, mo, c, a, ctas);
-        else if (st.smem) launch_merge<true, 1>(ctx, db, mo, c, a, ctas);
-        else launch_merge<false, 1>(ctx, db, mo, c, a, ctas);
+    rc = run_stages(ctx, n, stages, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
+        if (st.smem && st.min_ctas == 3) launch_merge<true, 3>(ctx, db, mo, c, a, ctas, st.warps, strm);
+        else if (st.smem) launch_merge<true, 1>(ctx, db, mo, c, a, ctas, st.warps, strm);
+        else launch_merge<false, 1>(ctx, db, mo, c, a, ctas, st.warps, strm);
     });
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
