@@ -153,6 +153,9 @@ struct TierArgs {
     unsigned long long *work_out;
     u8 *blobs;             // split tier: [n_regions][RB_SIZE] search results handed to the score kernel
     int n_lo, n_hi;        // stages that scan all regions only take clusters with n_lo <= #variants <= n_hi
+    u32 *heavy_list;       // optional: clusters whose FIRST partition already needs more than heavy_bytes go here
+    u32 *heavy_ctr;
+    u32 heavy_bytes;
 };
 
 enum { MODE_FUSED = 0, MODE_SEARCH = 1, MODE_SCORE = 2 };
@@ -219,7 +222,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompar
         __syncwarp();
         if (rc == SOLVE_WORKSPACE) {
             if (!t.last_tier) {
-                if (lane == 0) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
+                if (lane == 0) {
+                    if (t.heavy_list && s.last_need > t.heavy_bytes) t.heavy_list[atomicAdd(t.heavy_ctr, 1u)] = (u32)r;
+                    else t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
+                }
                 continue;
             }
             rc = AVK_ST_WORKSPACE;
@@ -328,7 +334,7 @@ struct avk_ctx {
     DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, strat_off, strat_idx, strat_totals,
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx;
     // workspace
-    DevBuf blobs, scratch, arena, counters, fail_a, fail_b, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    DevBuf blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     // resident batch
     bool have_batch = false;
     u64 n_regions = 0, n_variants = 0;
@@ -341,7 +347,7 @@ struct avk_ctx {
     u32 tier_fail[3] = {0, 0, 0};
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, dbg[3] = {nullptr, nullptr, nullptr};
     float tier_ms[3] = {0, 0, 0};
 };
 
@@ -392,9 +398,14 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->tev) cudaEventCreate(&e);
-    for (auto &st : ctx->side) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (auto &st : ctx->side) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi);
+    }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (auto &e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : ctx->dbg) cudaEventCreate(&e);
     *out = ctx;
     return AVK_OK;
 }
@@ -407,7 +418,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->counters, &ctx->fail_a, &ctx->fail_b,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
@@ -566,6 +577,7 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
         a.work_out = (unsigned long long *)ctx->work_ctr.p;
         a.blobs = (u8 *)ctx->blobs.p;
         a.n_lo = st.n_lo; a.n_hi = st.n_hi;
+        a.heavy_list = nullptr; a.heavy_ctr = nullptr; a.heavy_bytes = 0;
         int ctas = st.ctas;
         if (st.in_list < 0) ctas = (int)std::min<u64>((u64)ctas, (n + st.warps - 1) / st.warps);
         launch(st, a, ctas, strm);
@@ -621,14 +633,91 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
 template <bool SMEM, int MIN_CTAS, int MODE>
 static void launch_compare(avk_ctx *ctx, const DevBatch &db, const DevCompareOut &out, const avk_compare_cfg &c, const TierArgs &a, int ctas, int warps, cudaStream_t strm) {
     const size_t smem = SMEM ? (size_t)a.arena_bytes * warps : 0;
-    if (SMEM) cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // function attributes are set once per instantiation (the call may synchronise the device)
+    static size_t configured = 0;
+    if (configured < smem + 1) {
+        if (SMEM) cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+        configured = 228 * 1024;
+    }
     k_compare<SMEM, MIN_CTAS, MODE><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
 }
 template <bool SMEM, int MIN_CTAS>
 static void launch_merge(avk_ctx *ctx, const DevBatch &db, const DevMergeOut &out, const avk_merge_cfg &c, const TierArgs &a, int ctas, int warps, cudaStream_t strm) {
     const size_t smem = SMEM ? (size_t)a.arena_bytes * warps : 0;
-    if (SMEM) cudaFuncSetAttribute(k_merge<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool configured = false;
+    if (!configured) {
+        if (SMEM) cudaFuncSetAttribute(k_merge<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+        configured = true;
+    }
     k_merge<SMEM, MIN_CTAS><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
+}
+
+// The compare pipeline (one stream): search kernel (all clusters) -> score kernel -> fused 27 KB shared-memory stage
+// for the clusters that did not fit the common tier (list A) -> fused 2 MB global-arena stage (list B) -> rare
+// host-synchronised bigger arenas (list D).  Every stage reads its work count from the previous stage's overflow
+// counter in device memory, so the common case needs no host round trip.
+// counters (u32): 0 search work, 1 |A|, 2 score work, 4 S1 work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
+template <class F>
+static int run_compare_pipeline(avk_ctx *ctx, u64 n, F launch) {
+    if (n == 0) return AVK_OK;
+    const int sm = ctx->sm_count;
+    const int INF = 0x7fffffff;
+    ENSURE(ctx->fail_a, 4 * n); ENSURE(ctx->fail_b, 4 * n); ENSURE(ctx->fail_c, 4 * n); ENSURE(ctx->fail_d, 4 * n); ENSURE(ctx->fail_h, 4 * n);
+    ENSURE(ctx->counters, 256);
+    ENSURE(ctx->blobs, (size_t)n * RB_SIZE);
+    u32 *ctrs = (u32 *)ctx->counters.p;
+    u32 *LA = (u32 *)ctx->fail_a.p, *LB = (u32 *)ctx->fail_b.p, *LC = (u32 *)ctx->fail_c.p, *LD = (u32 *)ctx->fail_d.p;
+    CK(cudaMemsetAsync(ctrs, 0, 256, ctx->stream));
+    ENSURE(ctx->arena, (size_t)sm * 8 * (size_t)(2LL << 20));
+    ENSURE(ctx->arena2, (size_t)sm * 2 * (size_t)(2LL << 20));
+    auto args = [&](const u32 *list, int in_ctr, int work_ctr, u32 *fail_list, int fail_ctr, long long arena_bytes, u8 *garena) {
+        TierArgs a;
+        a.work_list = list; a.n_work_ptr = list ? ctrs + in_ctr : nullptr; a.n_work = (u32)n;
+        a.work_ctr = ctrs + work_ctr; a.fail_ctr = ctrs + fail_ctr; a.fail_list = fail_list;
+        a.arena_base = garena; a.arena_bytes = arena_bytes; a.last_tier = 0;
+        a.work_out = (unsigned long long *)ctx->work_ctr.p; a.blobs = (u8 *)ctx->blobs.p; a.n_lo = 0; a.n_hi = INF;
+        a.heavy_list = nullptr; a.heavy_ctr = nullptr; a.heavy_bytes = 0;
+        return a;
+    };
+    const Stage SEARCH = {MODE_SEARCH, true, 3, 8192, sm * 3, 8}, SCORE = {MODE_SCORE, true, 4, 5120, sm * 4, 8};
+    const Stage S1 = {MODE_FUSED, true, 1, 27648, sm, 8}, G0 = {MODE_FUSED, false, 1, 2LL << 20, sm, 8};
+    CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+    {
+        TierArgs a = args(nullptr, 0, 0, LA, 1, SEARCH.arena_bytes, nullptr);
+        launch(SEARCH, a, (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8), ctx->stream);
+    }
+    CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+    launch(SCORE, args(nullptr, 0, 2, LA, 1, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->stream);   // overflows join A
+    CK(cudaEventRecord(ctx->tev[2], ctx->stream));
+    launch(S1, args(LA, 1, 4, LB, 5, S1.arena_bytes, nullptr), S1.ctas, ctx->stream);             // A -> B   (8 warps x 27 KB per SM)
+    launch(G0, args(LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p), G0.ctas, ctx->stream);  // B -> D   (2 MB global arenas)
+    CK(cudaEventRecord(ctx->tev[3], ctx->stream));
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    u32 h[16];
+    CK(cudaMemcpyAsync(h, ctrs, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
+    ctx->tier_fail[0] = h[1]; ctx->tier_fail[1] = h[5]; ctx->tier_fail[2] = h[7];
+    // rare: clusters that overflow 2 MB per warp (list D); host-synchronised escalation
+    const Stage big[2] = {{MODE_FUSED, false, 1, 64LL << 20, (sm + 7) / 8, 8}, {MODE_FUSED, false, 1, 2048LL << 20, 1, 8}};
+    const u32 *cur = LD;
+    u32 *other = LC;
+    u32 n_work = h[7];
+    for (int t = 0; t < 2 && n_work > 0; ++t) {
+        ENSURE(ctx->arena, (size_t)big[t].ctas * big[t].warps * (size_t)big[t].arena_bytes);
+        CK(cudaMemsetAsync(ctrs + 32, 0, 8, ctx->stream));
+        TierArgs a = args(cur, 0, 32, other, 33, big[t].arena_bytes, (u8 *)ctx->arena.p);
+        a.n_work_ptr = nullptr; a.n_work = n_work; a.last_tier = t == 1;
+        launch(big[t], a, big[t].ctas, ctx->stream);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h, ctrs + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_work = h[1];
+        const u32 *tmp = cur; cur = other; other = (u32 *)tmp;
+    }
+    return AVK_OK;
 }
 
 static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, const u64 *strat_off_dev,
@@ -653,24 +742,12 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     out.seq_off = want_seq ? (const u64 *)ctx->seq_off.p : nullptr;
     out.seq_len = (u32 *)ctx->seq_len.p; out.seq_pool = (u8 *)ctx->seq_pool.p;
     avk_compare_cfg c = *cfg;
-    unsigned long long *work = (unsigned long long *)ctx->work_ctr.p;
 
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = run_alt_ed(ctx, db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    ENSURE(ctx->blobs, (size_t)n * RB_SIZE);
-    const int sm = ctx->sm_count;
-    const int INF = 0x7fffffff;
-    const std::vector<Stage> stages = {
-        // mode, smem, min_ctas, arena, ctas, warps, in_list, in_ctr, work_ctr, fail_list, fail_ctr, stream, n_lo, n_hi
-        {MODE_SEARCH, true, 3, 8192, sm * 3, 8, -1, 0, 0, 0, 1, 0, 0, INF},
-        {MODE_SCORE, true, 4, 5120, sm * 4, 8, -1, 0, 2, 0, 1, 0, 0, INF},
-        // chain for clusters that did not fit the common tier
-        {MODE_FUSED, true, 1, 27648, sm, 8, 0, 1, 3, 1, 4, 0, 0, INF},
-        {MODE_FUSED, false, 1, 2LL << 20, sm, 8, 1, 4, 5, 0, 6, 0, 0, INF},
-    };
-    rc = run_stages(ctx, n, stages, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
+    rc = run_compare_pipeline(ctx, n, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
         if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(ctx, db, out, c, a, ctas, st.warps, strm);
         else if (st.mode == MODE_SCORE) launch_compare<true, 4, MODE_SCORE>(ctx, db, out, c, a, ctas, st.warps, strm);
         else if (st.smem && st.min_ctas == 2) launch_compare<true, 2, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);
@@ -864,7 +941,6 @@ extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, cons
     DevMergeOut mo;
     mo.status = (int *)ctx->status.p; mo.cls = (u8 *)ctx->m_cls.p; mo.n_idx = (u8 *)ctx->m_nidx.p; mo.idx = (u8 *)ctx->m_idx.p;
     avk_merge_cfg c = *cfg;
-    unsigned long long *work = (unsigned long long *)ctx->work_ctr.p;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = run_alt_ed(ctx, db);
     if (rc != AVK_OK) return rc;

@@ -115,6 +115,7 @@ struct RegionSolver {
     int n_res, res_cap, n_slots;
     int region_off;       // first arena byte after the header (+ staged window)
     int ed_overflow;
+    u32 last_need;        // arena bytes the failed partition() would have needed (0: overflow happened later)
     u8 slot_type[AVK_N_VARIANT_TYPES];
     // queue + node slots (partitioned per phase)
     addr qkeys, qslot, freel, nodes;
@@ -285,7 +286,7 @@ struct RegionSolver {
     __device__ __noinline__ bool partition(int stride_, int min_slots) {
         stride = stride_;
         int ms = (int)min(dyn_bytes / (u32)(stride_ + 16), 60000u);
-        if (ms < min_slots) return false;
+        if (ms < min_slots) { last_need = (arena_bytes - dyn_bytes) + (u32)min_slots * (u32)(stride_ + 16) + 64; return false; }
         u32 off = 0;
         qkeys = dyn + off; off += (u32)ms * 8;
         qslot = dyn + off; off += (u32)ms * 4;
@@ -835,6 +836,7 @@ __device__ int RegionSolver<SMEM>::compare_prepare(u64 r, const avk_compare_cfg 
     if (c >= b.n_contigs || b.start[r] > b.end[r] || (u64)b.end[r] > b.contig_len[c] || b.end[r] > 0x7fff0000u) return AVK_ST_BAD_INPUT;
     mbf = (int)cfg.max_branch_factor;
     if (mbf <= 0) return AVK_ST_BAD_INPUT;
+    last_need = 0;
     if (!begin_region(b.contig_ptr[c])) return SOLVE_WORKSPACE;
     return setup_pair(r, 0, 1, want_metrics);
 }
