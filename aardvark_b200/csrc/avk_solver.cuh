@@ -377,6 +377,38 @@ struct RegionSolver {
         return v;
     }
 
+    // Queue garbage collection, used when no node slot is free.  It removes exactly the nodes the search would
+    // discard WITHOUT side effects the moment they are popped, so the replayed search is unchanged:
+    //   optimize_sequences : cost > best            (query_optimizer.rs:204, checked before the bucket quota)
+    //   optimize_gt_alleles: errors >= best         (exact_gt_optimizer.rs:169, first check after the pop), or
+    //                        depth < min_allele_sync for unfinished nodes (:194-197; finished nodes are handled
+    //                        before that check and are kept)
+    // key_hi of an optimize entry is its cost; an exact entry carries errors in key bits 48..63.
+    __device__ __noinline__ int gc_queue(bool exact, u32 best, int min_sync, int n_total) {
+        int w = 0;
+        const int cnt = qn;
+#pragma unroll 1
+        for (int i = 0; i < cnt; ++i) {
+            const u64 key = LD64(qkeys + 8 * i);
+            const int sl = (int)LD32(qslot + 4 * i);
+            bool dead;
+            if (!exact) dead = (u32)(key >> 32) > best;
+            else {
+                const int depth = LDI(node(sl) + XN_DEPTH);
+                dead = (u32)(key >> 48) >= best || (depth != n_total && depth < min_sync);
+            }
+            if (!dead) {
+                if (lane_id() == 0 && w != i) { ST64(qkeys + 8 * w, key); ST32(qslot + 4 * w, sl); }
+                w += 1;
+            } else {
+                free_slot(sl);
+            }
+            __syncwarp();
+        }
+        qn = w;
+        return cnt - w;
+    }
+
     // ================================================================== optimize_sequences
     // node: hdr[80] | alle[Npad] | seq[4][seq_cap] (h0 truth, h0 query, h1 truth, h1 query) | wf[2][wf_cap] ints
     __device__ __forceinline__ int opt_stride() const { return ON_HDR + Npad + 4 * seq_cap + 8 * wf_cap; }
@@ -533,6 +565,7 @@ struct RegionSolver {
             int s2 = -1;
             if (two) {
                 s2 = alloc_slot();
+                if (s2 < 0 && gc_queue(false, best, 0, n) > 0) s2 = alloc_slot();
                 if (s2 < 0) return SOLVE_WORKSPACE;
                 opt_clone(node(s2), nb);
                 // first child (REF, ALT) gets the lower id, second (ALT, REF) the next one
@@ -676,6 +709,7 @@ struct RegionSolver {
             int s_alt = -1;
             if (do_alt) {
                 s_alt = alloc_slot();
+                if (s_alt < 0 && gc_queue(true, (u32)min(best_err, 0xffff), min_sync, n) > 0) s_alt = alloc_slot();
                 if (s_alt < 0) return SOLVE_WORKSPACE;
                 ex_clone(node(s_alt), nb);
             }
