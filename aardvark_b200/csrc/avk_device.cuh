@@ -301,6 +301,19 @@ __device__ __forceinline__ void tma_window_issue(u32 dst_off, const u8 *gsrc, u3
                      ::"r"(smem_u32(avk_dyn_smem + dst_off)), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
     }
 }
+// two bulk copies (reference window + cluster digest) completing on one mbarrier
+__device__ __forceinline__ void tma_issue2(u32 dst0, const u8 *src0, u32 bytes0, u32 dst1, const u8 *src1, u32 bytes1, u32 mbar_off) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane_id() == 0) {
+        const u32 mbar = smem_u32(avk_dyn_smem + mbar_off);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes0 + bytes1) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(avk_dyn_smem + dst0)), "l"(src0), "r"(bytes0), "r"(mbar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(avk_dyn_smem + dst1)), "l"(src1), "r"(bytes1), "r"(mbar) : "memory");
+    }
+}
 __device__ __forceinline__ void tma_window_wait(u32 mbar_off, u32 *phase) {
     const u32 mbar = smem_u32(avk_dyn_smem + mbar_off);
     const u32 ph = *phase;

@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_scan.cuh>
+
 #include "avk_solver.cuh"
 
 using namespace avk;
@@ -122,6 +124,108 @@ __global__ void __launch_bounds__(256) k_wfa_ed(u64 n_pairs, const u8 *pool, con
         if (lane == 0) ed_out[p] = (u32)ed;
     }
     flush_work<false>(hdr, work_out);
+}
+
+// ---- cluster digests (compare path) -------------------------------------------------------------------------
+// k_prep_size / scan / k_prep_fill turn every cluster into one contiguous, 16-byte aligned blob:
+//   [PH_* header 64 B][N variant records of 32 B in merged processing order][allele bytes]
+// i.e. everything RegionSolver::setup_pair derives (validation, order_variants, per-type metric slots).  The solver
+// kernels then fetch a cluster with one TMA bulk copy instead of re-deriving it with dependent global loads.
+__global__ void __launch_bounds__(256) k_prep_size(DevBatch b, u64 n, u64 *sizes) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    if (r == n) { sizes[r] = 0; return; }
+    const u64 v0 = b.var_off[r * 2], v1 = b.var_off[r * 2 + 2];
+    u64 alle = 0;
+    for (u64 v = v0; v < v1; ++v) alle += (u64)min(b.l0[v], 1u << 24) + (u64)min(b.l1[v], 1u << 24);
+    sizes[r] = (PH_SIZE + VI_SIZE * (v1 - v0) + alle + 16 + 15) & ~15ull;
+}
+
+__global__ void __launch_bounds__(256) k_prep_fill(DevBatch b, u64 n, const u64 *offs, u8 *digest) {
+    const int lane = lane_id();
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 r = warp; r < n; r += n_warps) {
+        u8 *dig = digest + offs[r];
+        int *hdr = (int *)dig;
+        const long long start = b.start[r], end = b.end[r];
+        const u64 v0[2] = {b.var_off[r * 2], b.var_off[r * 2 + 1]};
+        const int cnt[2] = {(int)(b.var_off[r * 2 + 1] - v0[0]), (int)(b.var_off[r * 2 + 2] - v0[1])};
+        const int N = cnt[0] + cnt[1];
+        // validation (same rules as the oracle's list_valid) + the sums that size the solver workspace
+        bool invalid = false;
+        int s_l1 = 0, s_b0 = 0, s_al = 0, mx = (int)min(start, 0x7fffffffLL);
+        for (int side = 0; side < 2; ++side) {
+            for (int i = lane; i < cnt[side]; i += 32) {
+                const u64 gv = v0[side] + i;
+                const u32 l0 = b.l0[gv], l1 = b.l1[gv], p = b.pos[gv];
+                invalid = invalid || l0 == 0 || l1 == 0 || b.vtype[gv] >= AVK_N_VARIANT_TYPES || b.zyg[gv] > AVK_ZYG_HOM_ALT;
+                invalid = invalid || (long long)p < start || (long long)p + l0 > end;
+                if (i > 0) invalid = invalid || b.pos[gv - 1] > p;
+                s_l1 += (int)min(l1, 1u << 24);
+                s_b0 += (int)min(max(l0, l1), 1u << 24);
+                s_al += (int)min(l0, 1u << 24) + (int)min(l1, 1u << 24);
+                mx = max(mx, (int)min(p + l0, 0x7fffffffu));
+            }
+        }
+        invalid = __any_sync(AVK_FULL, invalid);
+        s_l1 = __reduce_add_sync(AVK_FULL, s_l1); s_b0 = __reduce_add_sync(AVK_FULL, s_b0);
+        s_al = __reduce_add_sync(AVK_FULL, s_al); mx = __reduce_max_sync(AVK_FULL, mx);
+        if (invalid) {
+            if (lane < PH_SIZE / 4) hdr[lane] = lane == 0 ? AVK_ST_BAD_INPUT : 0;
+            continue;
+        }
+        // merged order: stable, truth before query on equal positions (order_variants, query_optimizer.rs:372-381)
+        u8 *recs = dig + PH_SIZE;
+        for (int side = 0; side < 2; ++side) {
+            const int nm = cnt[side], no = cnt[side ^ 1];
+            const u64 vm = v0[side], vo = v0[side ^ 1];
+            for (int i = lane; i < nm; i += 32) {
+                const u64 gv = vm + i;
+                const u32 p = b.pos[gv];
+                int lo = 0, hi = no;
+                while (lo < hi) {
+                    const int m = (lo + hi) >> 1;
+                    const u32 pm = b.pos[vo + m];
+                    const bool before = side == 0 ? (pm < p) : (pm <= p);
+                    if (before) lo = m + 1; else hi = m;
+                }
+                u32 *rec = (u32 *)(recs + (size_t)VI_SIZE * (i + lo));
+                rec[VI_POS / 4] = p; rec[VI_L0 / 4] = b.l0[gv]; rec[VI_L1 / 4] = b.l1[gv]; rec[VI_AOFF / 4] = b.aoff[gv];
+                rec[VI_ALTED / 4] = b.alt_ed[gv]; rec[VI_RAW / 4] = b.raw[gv]; rec[VI_GV / 4] = (u32)gv;
+                rec[VI_FLAGS / 4] = (u32)b.vtype[gv] | ((u32)b.zyg[gv] << 8) | ((side == 0 ? 1u : 0u) << 16);
+            }
+        }
+        __syncwarp();
+        // allele bytes in merged order; VI_AOFF becomes the offset inside the digest's allele area
+        u8 *alle = recs + (size_t)VI_SIZE * N;
+        u32 seen = 0;
+        int acc = 0;
+        for (int oi = 0; oi < N; ++oi) {
+            u32 *rec = (u32 *)(recs + (size_t)VI_SIZE * oi);
+            const int na = (int)(rec[VI_L0 / 4] + rec[VI_L1 / 4]);
+            const u8 *src = b.pool + rec[VI_AOFF / 4];
+            for (int i = lane; i < na; i += 32) alle[acc + i] = src[i];
+            seen |= 1u << (rec[VI_FLAGS / 4] & 0xff);
+            __syncwarp();
+            if (lane == 0) rec[VI_AOFF / 4] = (u32)acc;
+            acc += na;
+        }
+        __syncwarp();
+        // metric-row slots: one per distinct variant type, in type order
+        for (int oi = lane; oi < N; oi += 32) {
+            u32 *rec = (u32 *)(recs + (size_t)VI_SIZE * oi);
+            const u32 f = rec[VI_FLAGS / 4];
+            rec[VI_FLAGS / 4] = f | ((u32)__popc(seen & ((1u << (f & 0xff)) - 1)) << 24);
+        }
+        if (lane == 0) {
+            hdr[PH_STATUS / 4] = AVK_ST_OK; hdr[PH_N / 4] = N; hdr[PH_N0 / 4] = cnt[0]; hdr[PH_N1 / 4] = cnt[1];
+            hdr[PH_SUM_L1 / 4] = s_l1; hdr[PH_B0 / 4] = s_b0; hdr[PH_SUM_ALLE / 4] = s_al; hdr[PH_MAX_END / 4] = mx;
+            hdr[PH_NSLOTS / 4] = __popc(seen);
+            int k = 0;
+            for (int t = 0; t < AVK_N_VARIANT_TYPES; ++t) if (seen & (1u << t)) dig[PH_SLOT_TYPE + (k++)] = (u8)t;
+        }
+    }
 }
 
 __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const DevCompareOut &out, u64 r, bool metrics_only) {
@@ -334,12 +438,13 @@ struct avk_ctx {
     DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, strat_off, strat_idx, strat_totals,
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx;
     // workspace
-    DevBuf blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     // resident batch
     bool have_batch = false;
     u64 n_regions = 0, n_variants = 0;
     u32 n_inputs = 0;
     u32 max_allele = 1;
+    u64 pool_len = 0;
     bool resident_has_seq = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
@@ -418,7 +523,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
@@ -480,8 +585,13 @@ static int upload_batch(avk_ctx *ctx, const avk_region_batch *b) {
     UPLOAD(ctx->pool, t.allele_pool, t.allele_pool_len);
     ENSURE(ctx->alt_ed, 4 * nv);
     u32 mx = 1;
-    for (u64 i = 0; i < nv; ++i) mx = std::max(mx, std::max(t.a0_len[i], t.a1_len[i]));
+    u64 sum_alle = 0;
+    for (u64 i = 0; i < nv; ++i) {
+        mx = std::max(mx, std::max(t.a0_len[i], t.a1_len[i]));
+        sum_alle += (u64)std::min(t.a0_len[i], 1u << 24) + (u64)std::min(t.a1_len[i], 1u << 24);
+    }
     ctx->max_allele = mx;
+    ctx->pool_len = sum_alle;   // bytes the cluster digests need for alleles
     ctx->n_regions = n; ctx->n_variants = nv; ctx->n_inputs = b->n_inputs;
     ctx->have_batch = true;
     return AVK_OK;
@@ -498,6 +608,8 @@ static DevBatch dev_batch(avk_ctx *ctx) {
     d.contig_ptr = (const u8 *const *)ctx->d_contig_ptr.p; d.contig_len = (const u64 *)ctx->d_contig_len.p;
     d.n_contigs = (u32)ctx->contig_lens.size();
     d.alt_ed = (const u32 *)ctx->alt_ed.p;
+    d.digest = (const u8 *)ctx->digest.p;
+    d.digest_off = (const u64 *)ctx->digest_offs.p;
     return d;
 }
 
@@ -652,6 +764,21 @@ static void launch_merge(avk_ctx *ctx, const DevBatch &db, const DevMergeOut &ou
     k_merge<SMEM, MIN_CTAS><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
 }
 
+static int run_prepare(avk_ctx *ctx, const DevBatch &db) {
+    const u64 n = ctx->n_regions;
+    if (n == 0) return AVK_OK;
+    u64 *sizes = (u64 *)ctx->digest_sizes.p, *offs = (u64 *)ctx->digest_offs.p;
+    k_prep_size<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(db, n, sizes);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sizes, offs, (int)(n + 1), ctx->stream);
+    ENSURE(ctx->scan_tmp, tmp_bytes);
+    cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, sizes, offs, (int)(n + 1), ctx->stream);
+    k_prep_fill<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, n, offs, (u8 *)ctx->digest.p);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return AVK_OK;
+}
+
 // The compare pipeline (one stream): search kernel (all clusters) -> score kernel -> fused 27 KB shared-memory stage
 // for the clusters that did not fit the common tier (list A) -> fused 2 MB global-arena stage (list B) -> rare
 // host-synchronised bigger arenas (list D).  Every stage reads its work count from the previous stage's overflow
@@ -734,6 +861,10 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->totals.p, 0, 8 * RED_COLS + 64, ctx->stream));
     if (n_strata) CK(cudaMemsetAsync(ctx->strat_totals.p, 0, 8ull * RED_COLS * n_strata, ctx->stream));
+    // digest buffers are sized from a host-side upper bound, so no device round trip is needed
+    ENSURE(ctx->digest, (size_t)n * (PH_SIZE + 32) + (size_t)VI_SIZE * nv + (size_t)ctx->pool_len + 256);
+    ENSURE(ctx->digest_sizes, 8 * (n + 1));
+    ENSURE(ctx->digest_offs, 8 * (n + 1));
     DevBatch db = dev_batch(ctx);
     DevCompareOut out;
     out.status = (int *)ctx->status.p; out.ed1 = (u32 *)ctx->ed1.p; out.ed2 = (u32 *)ctx->ed2.p;
@@ -745,6 +876,8 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
 
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = run_alt_ed(ctx, db);
+    if (rc != AVK_OK) return rc;
+    rc = run_prepare(ctx, db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     rc = run_compare_pipeline(ctx, n, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {

@@ -39,7 +39,14 @@ struct DevBatch {
     const u64 *contig_len;
     u32 n_contigs;
     const u32 *alt_ed;   // per variant, filled by k_alt_ed
+    // compare only: per-cluster "digest" written by k_prep_fill (header + variant records in merged order + alleles)
+    const u8 *digest;
+    const u64 *digest_off;   // [n_regions + 1]
 };
+
+// digest header (64 bytes), then N VI_* records, then the allele bytes (VI_AOFF is relative to their start)
+enum { PH_STATUS = 0, PH_N = 4, PH_N0 = 8, PH_N1 = 12, PH_SUM_L1 = 16, PH_B0 = 20, PH_SUM_ALLE = 24, PH_MAX_END = 28,
+       PH_NSLOTS = 32, PH_SLOT_TYPE = 36, PH_SIZE = 64 };
 
 struct DevCompareOut {
     int *status;
@@ -278,6 +285,73 @@ struct RegionSolver {
         dyn = arena + off;
         dyn_bytes = arena_bytes - off;
         if (SMEM && tma_pending) { tma_window_wait((u32)arena, &tma_phase); tma_pending = 0; }
+        __syncwarp();
+        return SOLVE_OK;
+    }
+
+    // Compare path: load the cluster digest prepared by k_prep_fill (one TMA bulk copy in shared-memory tiers; read in
+    // place from global memory otherwise) and lay out the rest of the arena.  Replaces setup_pair() + begin_region()
+    // for solve_compare_region; the digest holds exactly what setup_pair computes.
+    __device__ __noinline__ int load_cluster(u64 r, const u8 *contig, bool want_metrics) {
+        const DevBatch &b = *bp;
+        const int lane = lane_id();
+        const u64 d0 = b.digest_off[r];
+        const u32 dbytes = (u32)(b.digest_off[r + 1] - d0);
+        const u8 *dig = b.digest + d0;
+        u32 off = ARENA_HDR;
+        addr hdr;
+        if (SMEM) {
+            const int a0 = start & ~15;
+            const u32 wbytes = (u32)align_up(end - a0 + 16, 16);        // >= 16 bytes of slack for ld4u
+            if (ARENA_HDR + wbytes + dbytes + 1024 > arena_bytes) { last_need = ARENA_HDR + wbytes + dbytes + 4096; return SOLVE_WORKSPACE; }
+            tma_issue2((u32)arena + ARENA_HDR, contig + a0, wbytes, (u32)arena + ARENA_HDR + wbytes, dig, dbytes, (u32)arena);
+            tma_window_wait((u32)arena, &tma_phase);
+            ref_base = arena + ARENA_HDR - (u32)a0;
+            hdr = arena + ARENA_HDR + wbytes;
+            off = ARENA_HDR + wbytes + dbytes;
+        } else {
+            ref_base = (addr)(uintptr_t)contig;
+            hdr = (addr)(uintptr_t)dig;
+        }
+        const int st = LDI(hdr + PH_STATUS);
+        if (st) return st;
+        const int n = LDI(hdr + PH_N);
+        N = n; nv[0] = LDI(hdr + PH_N0); nv[1] = LDI(hdr + PH_N1);
+        const int npad = align_up(max(n, 1), 16);
+        Npad = npad;
+        seq_cap = align_up((LDI(hdr + PH_MAX_END) - start) + LDI(hdr + PH_SUM_L1) + 16, 16);
+        wf_cap = align_up(2 * LDI(hdr + PH_B0) + 3, 4);
+        const int rcap = (arena_bytes >= (256u << 10)) ? mbf : min(mbf, 8);
+        res_cap = rcap;
+        vinfo = hdr + PH_SIZE;
+        alle_base = vinfo + (u32)(VI_SIZE * n);
+        bucket = arena + off; off += (u32)align_up(4 * (n + 1), 16);
+        res_alle = arena + off; off += (u32)(rcap * npad);
+        res_num = arena + off; off += (u32)align_up(rcap * 24, 16);
+        hap_alle = arena + off; off += (u32)npad;
+        cur_obs = arena + off; off += (u32)(2 * npad);
+        best_obs = arena + off; off += (u32)(2 * npad);
+        sdesc = arena + off; off += 3 * SD_SIZE;
+        int ns = 0;
+        if (want_metrics) {
+            ns = LDI(hdr + PH_NSLOTS);
+            if (lane < ns) slot_type[lane] = LD8(hdr + PH_SLOT_TYPE + lane);
+            off = (off + 7u) & ~7u;
+            mrows = arena + off; off += (u32)(8 * AVK_N_METRICS * (1 + ns));
+            slot_tot = arena + off; off += (u32)(16 * max(ns, 1));
+            slot_cnt = arena + off; off += (u32)(16 * max(ns, 1));
+        }
+        if (off + 512 > arena_bytes) { last_need = off + 4096; return SOLVE_WORKSPACE; }
+        if (want_metrics) {
+#pragma unroll 1
+            for (int i = lane; i < AVK_N_METRICS * (1 + ns); i += 32) ST64(mrows + 8 * i, 0);
+#pragma unroll 1
+            for (int i = lane; i < 2 * ns; i += 32) { ST32(slot_cnt + 4 * i, 0); ST64(slot_tot + 8 * i, 0); }
+        }
+        n_slots = ns;
+        off = (off + 15u) & ~15u;
+        dyn = arena + off;
+        dyn_bytes = arena_bytes - off;
         __syncwarp();
         return SOLVE_OK;
     }
@@ -871,8 +945,7 @@ __device__ int RegionSolver<SMEM>::compare_prepare(u64 r, const avk_compare_cfg 
     mbf = (int)cfg.max_branch_factor;
     if (mbf <= 0) return AVK_ST_BAD_INPUT;
     last_need = 0;
-    if (!begin_region(b.contig_ptr[c])) return SOLVE_WORKSPACE;
-    return setup_pair(r, 0, 1, want_metrics);
+    return load_cluster(r, b.contig_ptr[c], want_metrics);
 }
 
 // Search phase -> result blob (split tier).  Returns SOLVE_OK with the blob filled, or a status.
