@@ -1017,7 +1017,7 @@ extern "C" int avk_int_peak(avk_ctx *ctx, double *ops_per_s) {
     if (!ctx || !ops_per_s) return AVK_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     ENSURE(ctx->counters, 64);
-    const int iters = 1 << 15, blocks = ctx->sm_count * 16, threads = 256;
+    const int iters = 1 << 13, blocks = ctx->sm_count * 16, threads = 256;
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));

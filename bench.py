@@ -94,7 +94,7 @@ class ClockSampler:
 
 def pinned_copy(arr):
     import torch
-    t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    t = torch.from_numpy(np.array(arr, copy=True)).pin_memory()
     return t.numpy()
 
 

@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aardvark_b200 import synth
 from aardvark_b200.lib import Solver
 from aardvark_b200.types import CompareConfig

@@ -1,5 +1,5 @@
 import sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from aardvark_b200 import synth, abi
 from aardvark_b200.lib import Solver
