@@ -206,8 +206,10 @@ def main():
     out = CompareOutputs(pbatch, region_metrics=False)
     for f in ("status", "ed1", "ed2", "type_mask", "var_expected", "var_observed", "var_class"):
         setattr(out, f, pinned_copy(getattr(out, f)))
-    for _ in range(2):
+    for _ in range(3):
         solver.compare_batch(pbatch, cfg, out=out)
+        if world > 1:
+            gather_compare_outputs(out, pbatch.n_regions, pbatch.n_variants)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
