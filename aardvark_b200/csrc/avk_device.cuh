@@ -74,10 +74,12 @@ __device__ __noinline__ void warp_copy(typename Mem<SMEM>::addr dst, typename Me
     typedef Mem<SMEM> M;
     const int lane = lane_id();
     if (n <= 32) {
+        __syncwarp();
         if (lane < n) ST8(dst + lane, LD8(src + lane));
         return;
     }
     const int head = (int)((4u - ((u32)dst & 3u)) & 3u);
+    __syncwarp();
     if (lane < head) ST8(dst + lane, LD8(src + lane));
     const int nw = (n - head) >> 2;
 #pragma unroll 1
@@ -169,6 +171,7 @@ __device__ __noinline__ Reach dwfa_extend(typename Mem<SMEM>::addr wf, int ed, c
             int ext = 0;
             if (boff < la && d < lb) ext = vs_lcp<SMEM>(A, boff, B, d);
             d += ext; boff += ext; matched += ext;
+            __syncwarp();
             if (ext && lane == 0) ST32(wf + 4 * i, d);
             mb = max(mb, boff); mo = max(mo, d);
             full = full || (boff >= la && d >= lb);
@@ -273,6 +276,7 @@ template <bool SMEM>
 __device__ __noinline__ int wfa_ed_warp(const VSeq<SMEM> A, const VSeq<SMEM> B, typename Mem<SMEM>::addr wf, int max_ed,
                                         typename Mem<SMEM>::addr wk) {
     typedef Mem<SMEM> M;
+    __syncwarp();
     if (lane_id() == 0) { ST32(wf, 0); ST32(wk + WK_ALIGN, LD32(wk + WK_ALIGN) + 1); }
     __syncwarp();
     int ed = 0;
@@ -314,16 +318,14 @@ __device__ __forceinline__ void tma_issue2(u32 dst0, const u8 *src0, u32 bytes0,
                      ::"r"(smem_u32(avk_dyn_smem + dst1)), "l"(src1), "r"(bytes1), "r"(mbar) : "memory");
     }
 }
-__device__ __forceinline__ void tma_window_wait(u32 mbar_off, u32 *phase) {
+__device__ __forceinline__ void tma_window_wait(u32 mbar_off, u32 phase) {
     const u32 mbar = smem_u32(avk_dyn_smem + mbar_off);
-    const u32 ph = *phase;
     u32 done = 0;
 #pragma unroll 1
     while (!done) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(mbar), "r"(ph) : "memory");
+                     : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
     }
-    *phase = ph ^ 1u;
     __syncwarp();
 }
 

@@ -260,6 +260,7 @@ struct RegionSolver {
 #pragma unroll 1
             for (int oi = 0; oi < n; ++oi) seen |= 1u << (LD32(vi(oi) + VI_FLAGS) & 0xff);
             ns = __popc(seen);
+            __syncwarp();
             if (lane == 0) {
                 int k = 0;
 #pragma unroll 1
@@ -284,7 +285,13 @@ struct RegionSolver {
         off = (off + 15u) & ~15u;
         dyn = arena + off;
         dyn_bytes = arena_bytes - off;
-        if (SMEM && tma_pending) { tma_window_wait((u32)arena, &tma_phase); tma_pending = 0; }
+        if (SMEM && tma_pending) {
+            const u32 ph = tma_phase;
+            tma_window_wait((u32)arena, ph);
+            __syncwarp();
+            if (lane == 0) { tma_phase = ph ^ 1u; tma_pending = 0; }
+            __syncwarp();
+        }
         __syncwarp();
         return SOLVE_OK;
     }
@@ -304,8 +311,12 @@ struct RegionSolver {
             const int a0 = start & ~15;
             const u32 wbytes = (u32)align_up(end - a0 + 16, 16);        // >= 16 bytes of slack for ld4u
             if (ARENA_HDR + wbytes + dbytes + 1024 > arena_bytes) { last_need = ARENA_HDR + wbytes + dbytes + 4096; return SOLVE_WORKSPACE; }
+            const u32 ph = tma_phase;
             tma_issue2((u32)arena + ARENA_HDR, contig + a0, wbytes, (u32)arena + ARENA_HDR + wbytes, dig, dbytes, (u32)arena);
-            tma_window_wait((u32)arena, &tma_phase);
+            tma_window_wait((u32)arena, ph);
+            __syncwarp();
+            if (lane == 0) tma_phase = ph ^ 1u;
+            __syncwarp();
             ref_base = arena + ARENA_HDR - (u32)a0;
             hdr = arena + ARENA_HDR + wbytes;
             off = ARENA_HDR + wbytes + dbytes;
@@ -335,6 +346,7 @@ struct RegionSolver {
         int ns = 0;
         if (want_metrics) {
             ns = LDI(hdr + PH_NSLOTS);
+            __syncwarp();
             if (lane < ns) slot_type[lane] = LD8(hdr + PH_SLOT_TYPE + lane);
             off = (off + 7u) & ~7u;
             mrows = arena + off; off += (u32)(8 * AVK_N_METRICS * (1 + ns));
@@ -358,42 +370,48 @@ struct RegionSolver {
 
     // Partition the dynamic part into queue arrays + node slots of `stride_` bytes.
     __device__ __noinline__ bool partition(int stride_, int min_slots) {
-        stride = stride_;
         int ms = (int)min(dyn_bytes / (u32)(stride_ + 16), 60000u);
         if (ms < min_slots) { last_need = (arena_bytes - dyn_bytes) + (u32)min_slots * (u32)(stride_ + 16) + 64; return false; }
         u32 off = 0;
-        qkeys = dyn + off; off += (u32)ms * 8;
-        qslot = dyn + off; off += (u32)ms * 4;
-        freel = dyn + off; off += (u32)ms * 4;
+        const addr qk = dyn + off; off += (u32)ms * 8;
+        const addr qs = dyn + off; off += (u32)ms * 4;
+        const addr fl = dyn + off; off += (u32)ms * 4;
         off = (off + 15u) & ~15u;
+        __syncwarp();
+        if (lane_id() == 0) { stride = stride_; qkeys = qk; qslot = qs; freel = fl; }
+        __syncwarp();
         if (off + (u32)ms * (u32)stride_ > dyn_bytes) ms = (int)((dyn_bytes - off) / (u32)stride_);
         if (ms < min_slots) return false;
-        max_slots = ms;
-        nodes = dyn + off;
+        __syncwarp();
+        if (lane_id() == 0) { max_slots = ms; nodes = dyn + off; nfree = ms; qn = 0; }
+        __syncwarp();
 #pragma unroll 1
         for (int i = lane_id(); i < ms; i += 32) ST32(freel + 4 * i, ms - 1 - i);
-        nfree = ms;
-        qn = 0;
         __syncwarp();
         return true;
     }
     __device__ __forceinline__ addr node(int s) const { return nodes + (u32)s * (u32)stride; }
+    // The solver object is shared by the 32 lanes of its warp: every lane reads a field, lane 0 alone writes it,
+    // with __syncwarp() between the reads and the write (no lane may observe a half-updated counter).
     __device__ __forceinline__ int alloc_slot() {   // warp-uniform; -1 when exhausted
         const int nf = nfree;
         if (nf == 0) return -1;
-        nfree = nf - 1;
-        return (int)LD32(freel + 4 * (nf - 1));
+        const int s = (int)LD32(freel + 4 * (nf - 1));
+        __syncwarp();
+        if (lane_id() == 0) nfree = nf - 1;
+        __syncwarp();
+        return s;
     }
     __device__ __forceinline__ void free_slot(int s) {
         const int nf = nfree;
-        if (lane_id() == 0) ST32(freel + 4 * nf, s);
-        nfree = nf + 1;
+        __syncwarp();
+        if (lane_id() == 0) { ST32(freel + 4 * nf, s); nfree = nf + 1; }
         __syncwarp();
     }
     __device__ __forceinline__ void push(u64 key, int slot) {
         const int n = qn;
-        if (lane_id() == 0) { ST64(qkeys + 8 * n, key); ST32(qslot + 4 * n, slot); }
-        qn = n + 1;
+        __syncwarp();
+        if (lane_id() == 0) { ST64(qkeys + 8 * n, key); ST32(qslot + 4 * n, slot); qn = n + 1; }
         __syncwarp();
     }
     // pop the minimum key: warp-parallel scan, then two REDUX min-reductions (high word, low word)
@@ -412,8 +430,7 @@ struct RegionSolver {
         bi = __shfl_sync(AVK_FULL, bi, owner);
         const int slot = (int)LD32(qslot + 4 * bi);
         __syncwarp();
-        if (lane == 0) { ST64(qkeys + 8 * bi, LD64(qkeys + 8 * (n - 1))); ST32(qslot + 4 * bi, LD32(qslot + 4 * (n - 1))); }
-        qn = n - 1;
+        if (lane == 0) { ST64(qkeys + 8 * bi, LD64(qkeys + 8 * (n - 1))); ST32(qslot + 4 * bi, LD32(qslot + 4 * (n - 1))); qn = n - 1; }
         __syncwarp();
         *key_hi = mhi;
         return slot;
@@ -479,7 +496,9 @@ struct RegionSolver {
             }
             __syncwarp();
         }
-        qn = w;
+        __syncwarp();
+        if (lane_id() == 0) qn = w;
+        __syncwarp();
         return cnt - w;
     }
 
@@ -492,6 +511,7 @@ struct RegionSolver {
     __device__ __noinline__ void opt_clone(addr dst, addr src) {
         const int lane = lane_id();
         const int depth = LDI(src + ON_DEPTH);
+        __syncwarp();
         if (lane < 20) ST32(dst + 4 * lane, LD32(src + 4 * lane));
         warp_copy<SMEM>(dst + ON_HDR, src + ON_HDR, depth);
 #pragma unroll 1
@@ -532,6 +552,7 @@ struct RegionSolver {
             const int d = LDI(n_wf(nb, h));
             if (d >= t_ml && d >= q_ml && T.tail + (u32)(d - t_ml) == Q.tail + (u32)(d - q_ml)) {
                 const int nd = max(d, min(T.len, Q.len));
+                __syncwarp();
                 if (lane_id() == 0) {
                     ST32(n_wf(nb, h), nd);
                     ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1); ST64(wk() + WK_MATCHED, LD64(wk() + WK_MATCHED) + (u64)(nd - d));
@@ -546,6 +567,7 @@ struct RegionSolver {
             if (rc == DWFA_OK && finalize) rc = dwfa_run<SMEM>(n_wf(nb, h), &ed, cap, T, Q, true, wk());
         }
         if (rc != DWFA_OK) return SOLVE_WORKSPACE;   // ED bound exceeded: never expected
+        __syncwarp();
         if (lane_id() == 0) {
             ST32(hb + H_TRP, t_rp); ST32(hb + H_QRP, q_rp); ST32(hb + H_TML, t_ml); ST32(hb + H_QML, q_ml);
             ST32(hb + H_TMR, t_mr); ST32(hb + H_QMR, q_mr); ST32(hb + H_TSK, t_sk); ST32(hb + H_QSK, q_sk); ST32(hb + H_ED, ed);
@@ -562,6 +584,7 @@ struct RegionSolver {
         if (rc) return rc;
         rc = opt_extend_hap(nb, 1, rec, a2_alt, sync, false);
         if (rc) return rc;
+        __syncwarp();
         if (lane_id() == 0) { ST8(nb + ON_HDR + oi, (a1_alt ? 1 : 0) | (a2_alt ? 2 : 0)); ST32(nb + ON_DEPTH, oi + 1); }
         __syncwarp();
         *cost = opt_cost(nb);
@@ -588,11 +611,13 @@ struct RegionSolver {
         {   // root (query_optimizer.rs:184-192): id 0, both haplotypes at region start, wavefront [0]
             const int s = alloc_slot();
             const addr nb = node(s);
+            __syncwarp();
             if (lane < 20) {
                 const int k = lane - 2;   // hap field index (0..17) once past id/depth
                 const bool at_start = lane >= 2 && ((k % 9) == 0 || (k % 9) == 1 || (k % 9) == 4 || (k % 9) == 5);
                 ST32(nb + 4 * lane, at_start ? start : 0);
             }
+            __syncwarp();
             if (lane == 0) { ST32(n_wf(nb, 0), 0); ST32(n_wf(nb, 1), 0); }
             __syncwarp();
             push(0ull, s);
@@ -601,6 +626,7 @@ struct RegionSolver {
         while (qn > 0) {
             u32 cost;
             const int s = pop(&cost);
+            __syncwarp();
             if (lane == 0) ST32(wk() + WK_SPOPS, LD32(wk() + WK_SPOPS) + 1);
             if (stop_at_nonzero && cost > 0) break;        // nothing cheaper is left; n_res tells if a zero-cost result exists
             if (cost > best) { free_slot(s); continue; }                       // :204 strict
@@ -608,6 +634,7 @@ struct RegionSolver {
             const int oi = LDI(nb + ON_DEPTH);
             const int bc = LDI(bucket + 4 * oi);
             if (bc >= mbf) { free_slot(s); continue; }                         // :222
+            __syncwarp();
             if (lane == 0) ST32(bucket + 4 * oi, bc + 1);
             __syncwarp();
             if (oi == n) {                                                     // :227-247
@@ -643,6 +670,7 @@ struct RegionSolver {
                 if (s2 < 0) return SOLVE_WORKSPACE;
                 opt_clone(node(s2), nb);
                 // first child (REF, ALT) gets the lower id, second (ALT, REF) the next one
+                __syncwarp();
                 if (lane == 0) { ST32(node(s2) + ON_ID, next_id); ST32(nb + ON_ID, next_id + 1); }
                 __syncwarp();
                 next_id += 2;
@@ -675,6 +703,7 @@ struct RegionSolver {
 
     __device__ __noinline__ void ex_clone(addr dst, addr src) {
         const int lane = lane_id();
+        __syncwarp();
         if (lane < 10) ST32(dst + 4 * lane, LD32(src + 4 * lane));
         warp_copy<SMEM>(dst + XN_HDR, src + XN_HDR, LDI(src + XN_DEPTH));
         warp_copy<SMEM>(x_seq(dst, 0), x_seq(src, 0), LDI(src + XN_TML));
@@ -712,6 +741,7 @@ struct RegionSolver {
         d += ext;
         const bool alive = finalize ? ((d >= T.len) && (d >= Q.len))    // update ok + finalize ok <=> sequences equal
                                     : ((d >= T.len) || (d >= Q.len));
+        __syncwarp();
         if (lane_id() == 0) {
             ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1); ST64(wk() + WK_MATCHED, LD64(wk() + WK_MATCHED) + (u64)ext);
             if (finalize) ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
@@ -745,6 +775,7 @@ struct RegionSolver {
         {
             const int s = alloc_slot();
             const addr nb = node(s);
+            __syncwarp();
             if (lane < 10) ST32(nb + 4 * lane, (lane == 3 || lane == 4 || lane == 7 || lane == 8) ? start : 0);
             __syncwarp();
             push(ex_key(nb), s);
@@ -753,6 +784,7 @@ struct RegionSolver {
         while (qn > 0) {
             u32 khi;
             const int s = pop(&khi);
+            __syncwarp();
             if (lane == 0) ST32(wk() + WK_XPOPS, LD32(wk() + WK_XPOPS) + 1);
             const addr nb = node(s);
             const int errors = LDI(nb + XN_ERR);
@@ -788,6 +820,7 @@ struct RegionSolver {
                 ex_clone(node(s_alt), nb);
             }
             if (is_alt) {
+                __syncwarp();
                 if (lane == 0) { ST32(nb + XN_ID, next_id); if (do_alt) ST32(node(s_alt) + XN_ID, next_id + 1); }
                 __syncwarp();
                 next_id += do_alt ? 2 : 1;
@@ -816,7 +849,9 @@ struct RegionSolver {
                     }
                     __syncwarp();
                 }
-                qn = w;
+                __syncwarp();
+                if (lane == 0) qn = w;
+                __syncwarp();
                 af_index += 1;
                 af_counts = 0;
             }
@@ -855,6 +890,7 @@ struct RegionSolver {
             last = oi;
         }
         if (cur > end) return -2;
+        __syncwarp();
         if (lane_id() == 0) {
             const addr sd = sdesc + (u32)(k * SD_SIZE);
             ST32(sd + SD_MLEN, mlen); ST32(sd + SD_CUR, cur); ST32(sd + SD_FAILED, failed); ST32(sd + SD_NALT, n_alt); ST32(sd + SD_LAST, last);
@@ -878,6 +914,7 @@ struct RegionSolver {
         if (LDI(sd + SD_NALT) == 1) {
             const addr rec = vi(LDI(sd + SD_LAST));
             if (LD32(rec + VI_L0) == 1 && LD32(rec + VI_L1) == 1) {
+                __syncwarp();
                 if (lane_id() == 0) {
                     ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
                     ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1);
@@ -1070,6 +1107,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
     }
     __syncwarp();
     // ---- GT / HAP / WEIGHTED_HAP (+ add_swap_benchmark :269) and RECORD_BP totals, accumulated by lane 0
+    __syncwarp();
     if (lane == 0) {
 #pragma unroll 1
         for (int oi = 0; oi < n; ++oi) {
@@ -1148,6 +1186,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
                     f_tp = other_ref + Ef - Zf;
                     f_bad = 2 * Ef - f_tp + 2 * failF;
                 }
+                __syncwarp();
                 if (lane == 0) {
                     const addr g = gm + (u32)(8 * (AVK_N_METRICS * (1 + k) + AVK_M_BASEPAIR + 2 * side));
                     ST64(g, LD64(g) + f_tp); ST64(g + 8, LD64(g + 8) + f_bad);
@@ -1158,6 +1197,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
     __syncwarp();
     if (shortcut) {
         // generate_exact_match(): per-variant basepair credit (:573-598); no RECORD_BP, no all-8-types fill
+        __syncwarp();
         if (lane == 0) {
 #pragma unroll 1
             for (int oi = 0; oi < n; ++oi) {
@@ -1174,6 +1214,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
                 (1u << AVK_VT_TR_CONTRACTION) | (1u << AVK_VT_TR_EXPANSION) | (1u << AVK_VT_SV_DELETION) | (1u << AVK_VT_SV_INSERTION);
         // add_record_basepair_stats(): :455-522 (wrapping u64 like a release build).  Types without variants have
         // zero totals and zero basepair counts, so their record rows stay zero.
+        __syncwarp();
         if (lane == 0) {
             u64 truth_total = 0, query_total = 0;
 #pragma unroll 1
@@ -1217,6 +1258,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
         }
     }
     if (want_seq) emit_seq(out, r, 0, -1);
+    __syncwarp();
     if (lane == 0) {
         out.ed1[r] = shortcut ? 0u : (u32)LDI(rnb);
         out.ed2[r] = shortcut ? 0u : (u32)LDI(rnb + 4);
@@ -1306,6 +1348,7 @@ __device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, 
     } else if (cfg.majority_voting_enabled && first_maj != 0) { cls = AVK_MERGE_MAJORITY_AGREE; idx_mask = first_maj; }
     else if (cfg.conflict_selection >= 0) { cls = AVK_MERGE_CONFLICT_SELECTION; sel = cfg.conflict_selection; }
     else cls = AVK_MERGE_DIFFERENT;
+    __syncwarp();
     if (lane == 0) {
         out.cls[r] = (u8)cls;
         int n = 0;

@@ -145,6 +145,16 @@ def test_compare_sv_vs_oracle(solver):
     assert gpu.diff(cpu) == []
 
 
+def test_compare_large_sv_vs_oracle(solver):
+    """Multi-kbp events: wavefronts thousands of diagonals wide, workspaces in the 2 MB / 64 MB global tiers."""
+    p = synth.SynthParams(n_variants=40, sv_events=12, sv_min=1500, sv_max=5000, flank=1000)
+    ref, batch = synth.workload_compare(300_000, p, seed=44)
+    solver.set_reference([ref])
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False))
+    assert gpu.diff(cpu) == []
+    assert int(gpu.error_blocks[0]) == 0
+
+
 def test_compare_edge_cases_vs_oracle(solver):
     """Empty batch, malformed regions, unsupported zygosity, non-ACGT bytes."""
     from aardvark_b200.types import Coordinates, PhasedZygosity as Z, Variant
