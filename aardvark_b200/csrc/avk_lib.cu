@@ -256,6 +256,8 @@ struct TierArgs {
     int last_tier;
     unsigned long long *work_out;
     u8 *blobs;             // split tier: [n_regions][RB_SIZE] search results handed to the score kernel
+    u8 *spill_base;        // shared-memory stages: per-warp node spill area in global memory (may be NULL)
+    u32 spill_bytes;       // per warp
     int n_lo, n_hi;        // stages that scan all regions only take clusters with n_lo <= #variants <= n_hi
     u32 *heavy_list;       // optional: clusters whose FIRST partition already needs more than heavy_bytes go here
     u32 *heavy_ctr;
@@ -280,6 +282,11 @@ __device__ __forceinline__ RegionSolver<SMEM> &init_solver(const DevBatch &b, co
         s.tma_pending = 0;
         s.arena_bytes = (u32)t.arena_bytes;
         s.arena = arena;
+        s.spill_base = nullptr; s.spill_bytes = 0;
+        if (SMEM && t.spill_base) {
+            s.spill_base = t.spill_base + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (u64)t.spill_bytes;
+            s.spill_bytes = t.spill_bytes;
+        }
         if (SMEM) mbar_init((u32)arena);
     }
     clear_work<SMEM>(arena);
@@ -688,6 +695,7 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
         a.last_tier = 0;
         a.work_out = (unsigned long long *)ctx->work_ctr.p;
         a.blobs = (u8 *)ctx->blobs.p;
+        a.spill_base = nullptr; a.spill_bytes = 0;
         a.n_lo = st.n_lo; a.n_hi = st.n_hi;
         a.heavy_list = nullptr; a.heavy_ctr = nullptr; a.heavy_bytes = 0;
         int ctas = st.ctas;
@@ -796,13 +804,14 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, F launch) {
     u32 *LA = (u32 *)ctx->fail_a.p, *LB = (u32 *)ctx->fail_b.p, *LC = (u32 *)ctx->fail_c.p, *LD = (u32 *)ctx->fail_d.p;
     CK(cudaMemsetAsync(ctrs, 0, 256, ctx->stream));
     ENSURE(ctx->arena, (size_t)sm * 8 * (size_t)(2LL << 20));
-    ENSURE(ctx->arena2, (size_t)sm * 2 * (size_t)(2LL << 20));
+    ENSURE(ctx->arena2, (size_t)sm * 8 * (size_t)(1u << 20));
     auto args = [&](const u32 *list, int in_ctr, int work_ctr, u32 *fail_list, int fail_ctr, long long arena_bytes, u8 *garena) {
         TierArgs a;
         a.work_list = list; a.n_work_ptr = list ? ctrs + in_ctr : nullptr; a.n_work = (u32)n;
         a.work_ctr = ctrs + work_ctr; a.fail_ctr = ctrs + fail_ctr; a.fail_list = fail_list;
         a.arena_base = garena; a.arena_bytes = arena_bytes; a.last_tier = 0;
         a.work_out = (unsigned long long *)ctx->work_ctr.p; a.blobs = (u8 *)ctx->blobs.p; a.n_lo = 0; a.n_hi = INF;
+        a.spill_base = nullptr; a.spill_bytes = 0;
         a.heavy_list = nullptr; a.heavy_ctr = nullptr; a.heavy_bytes = 0;
         return a;
     };
@@ -816,7 +825,11 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, F launch) {
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
     launch(SCORE, args(nullptr, 0, 2, LA, 1, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->stream);   // overflows join A
     CK(cudaEventRecord(ctx->tev[2], ctx->stream));
-    launch(S1, args(LA, 1, 4, LB, 5, S1.arena_bytes, nullptr), S1.ctas, ctx->stream);             // A -> B   (8 warps x 27 KB per SM)
+    {
+        TierArgs a = args(LA, 1, 4, LB, 5, S1.arena_bytes, nullptr);
+        a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;   // dense clusters keep running here: cold nodes spill to HBM
+        launch(S1, a, S1.ctas, ctx->stream);                                                      // A -> B   (8 warps x 27 KB per SM)
+    }
     launch(G0, args(LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p), G0.ctas, ctx->stream);  // B -> D   (2 MB global arenas)
     CK(cudaEventRecord(ctx->tev[3], ctx->stream));
     ctx->launches += 4;

@@ -126,7 +126,11 @@ struct RegionSolver {
     u8 slot_type[AVK_N_VARIANT_TYPES];
     // queue + node slots (partitioned per phase)
     addr qkeys, qslot, freel, nodes;
-    int stride, max_slots, qn, nfree;
+    int stride, max_slots, qn, nfree, qcap;
+    // node spill area in global memory (shared-memory tiers; 0 bytes = none)
+    u8 *spill_base;
+    u32 spill_bytes;
+    int spill_cap, spill_used, spill_nfree;
 
     // ------------------------------------------------------------------ helpers
     __device__ __forceinline__ addr vi(int oi) const { return vinfo + (u32)(VI_SIZE * oi); }
@@ -199,7 +203,7 @@ struct RegionSolver {
         wf_cap = align_up(2 * b0 + 3, 4);
         // room for equal-best results: all of them (<= max_branch_factor) when the arena is large,
         // a handful in the small shared-memory tiers (more than that escalates to the next tier)
-        const int rcap = (arena_bytes >= (256u << 10)) ? mbf : min(mbf, 8);
+        const int rcap = (arena_bytes >= (16u << 10)) ? mbf : min(mbf, 8);
         res_cap = rcap;
         u32 off = (u32)region_off;
         vinfo = arena + off; off += (u32)(VI_SIZE * max(n, 1));
@@ -332,7 +336,7 @@ struct RegionSolver {
         Npad = npad;
         seq_cap = align_up((LDI(hdr + PH_MAX_END) - start) + LDI(hdr + PH_SUM_L1) + 16, 16);
         wf_cap = align_up(2 * LDI(hdr + PH_B0) + 3, 4);
-        const int rcap = (arena_bytes >= (256u << 10)) ? mbf : min(mbf, 8);
+        const int rcap = (arena_bytes >= (16u << 10)) ? mbf : min(mbf, 8);
         res_cap = rcap;
         vinfo = hdr + PH_SIZE;
         alle_base = vinfo + (u32)(VI_SIZE * n);
@@ -368,22 +372,30 @@ struct RegionSolver {
         return SOLVE_OK;
     }
 
-    // Partition the dynamic part into queue arrays + node slots of `stride_` bytes.
+    // Partition the dynamic part into queue arrays + node slots of `stride_` bytes.  When the warp has a spill area
+    // in global memory (shared-memory tiers), the queue may hold more entries than there are node slots: nodes that
+    // are far down the queue are evicted to the spill area and brought back when they are popped.
     __device__ __noinline__ bool partition(int stride_, int min_slots) {
-        int ms = (int)min(dyn_bytes / (u32)(stride_ + 16), 60000u);
-        if (ms < min_slots) { last_need = (arena_bytes - dyn_bytes) + (u32)min_slots * (u32)(stride_ + 16) + 64; return false; }
+        const int scap = (spill_bytes > 32768u) ? (int)min((spill_bytes - 16384u) / (u32)stride_, 4096u) : 0;   // spillable nodes (after the id free list)
+        const int extra = min(scap, 384);                       // queue entries beyond the resident slots
+        const u32 per = (u32)stride_ + 16u;
+        if (dyn_bytes < 12u * (u32)extra + 64u) return false;
+        int ms = (int)min((dyn_bytes - 12u * (u32)extra - 16u) / per, 60000u);
+        if (ms < min_slots) { last_need = (arena_bytes - dyn_bytes) + (u32)min_slots * per + 12u * (u32)extra + 64; return false; }
+        const int qc = ms + extra;
         u32 off = 0;
-        const addr qk = dyn + off; off += (u32)ms * 8;
-        const addr qs = dyn + off; off += (u32)ms * 4;
+        const addr qk = dyn + off; off += (u32)qc * 8;
+        const addr qs = dyn + off; off += (u32)qc * 4;
         const addr fl = dyn + off; off += (u32)ms * 4;
         off = (off + 15u) & ~15u;
-        __syncwarp();
-        if (lane_id() == 0) { stride = stride_; qkeys = qk; qslot = qs; freel = fl; }
-        __syncwarp();
         if (off + (u32)ms * (u32)stride_ > dyn_bytes) ms = (int)((dyn_bytes - off) / (u32)stride_);
         if (ms < min_slots) return false;
         __syncwarp();
-        if (lane_id() == 0) { max_slots = ms; nodes = dyn + off; nfree = ms; qn = 0; }
+        if (lane_id() == 0) {
+            stride = stride_; qkeys = qk; qslot = qs; freel = fl;
+            max_slots = ms; qcap = qc; nodes = dyn + off; nfree = ms; qn = 0;
+            spill_cap = scap; spill_used = 0; spill_nfree = 0;
+        }
         __syncwarp();
 #pragma unroll 1
         for (int i = lane_id(); i < ms; i += 32) ST32(freel + 4 * i, ms - 1 - i);
@@ -391,31 +403,91 @@ struct RegionSolver {
         return true;
     }
     __device__ __forceinline__ addr node(int s) const { return nodes + (u32)s * (u32)stride; }
+    // spill area layout (global, per warp): [u32 free_ids[4096]] [nodes of `stride` bytes]
+    __device__ __forceinline__ u8 *spill_node(u32 id) const { return spill_base + 16384 + (size_t)id * (size_t)stride; }
+    // field of a queued node that may be resident (slot < 0x80000000) or spilled
+    __device__ __forceinline__ u32 qnode_ld32(u32 v, int off) const {
+        return (v & 0x80000000u) ? *(const u32 *)(spill_node(v & 0x7fffffffu) + off) : LD32(node((int)v) + off);
+    }
+    __device__ __forceinline__ u32 qnode_ld8(u32 v, int off) const {
+        return (v & 0x80000000u) ? (u32)spill_node(v & 0x7fffffffu)[off] : (u32)LD8(node((int)v) + off);
+    }
     // The solver object is shared by the 32 lanes of its warp: every lane reads a field, lane 0 alone writes it,
     // with __syncwarp() between the reads and the write (no lane may observe a half-updated counter).
-    __device__ __forceinline__ int alloc_slot() {   // warp-uniform; -1 when exhausted
-        const int nf = nfree;
-        if (nf == 0) return -1;
-        const int s = (int)LD32(freel + 4 * (nf - 1));
-        __syncwarp();
-        if (lane_id() == 0) nfree = nf - 1;
-        __syncwarp();
-        return s;
-    }
     __device__ __forceinline__ void free_slot(int s) {
         const int nf = nfree;
         __syncwarp();
         if (lane_id() == 0) { ST32(freel + 4 * nf, s); nfree = nf + 1; }
         __syncwarp();
     }
-    __device__ __forceinline__ void push(u64 key, int slot) {
+    __device__ __forceinline__ void free_spill(u32 id) {
+        const int nf = spill_nfree;
+        __syncwarp();
+        if (lane_id() == 0) { ((u32 *)spill_base)[nf] = id; spill_nfree = nf + 1; }
+        __syncwarp();
+    }
+    // release whatever a queue entry refers to
+    __device__ __forceinline__ void free_entry(u32 v) {
+        if (v & 0x80000000u) free_spill(v & 0x7fffffffu); else free_slot((int)v);
+    }
+    // Evict the queued resident node with the LARGEST key (popped last) to the spill area; returns its slot or -1.
+    __device__ __noinline__ int evict_one() {
+        const int lane = lane_id();
         const int n = qn;
+        if (spill_cap == 0) return -1;
+        u64 worst = 0;
+        int wi = -1;
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
+            if (LD32(qslot + 4 * i) & 0x80000000u) continue;
+            const u64 k = LD64(qkeys + 8 * i);
+            if (wi < 0 || k > worst) { worst = k; wi = i; }
+        }
+        const u32 hi = wi < 0 ? 0u : (u32)(worst >> 32), lo = wi < 0 ? 0u : (u32)worst;
+        if (!__any_sync(AVK_FULL, wi >= 0)) return -1;
+        const u32 mhi = __reduce_max_sync(AVK_FULL, hi);
+        const u32 mlo = __reduce_max_sync(AVK_FULL, (wi >= 0 && hi == mhi) ? lo : 0u);
+        const int owner = __ffs(__ballot_sync(AVK_FULL, wi >= 0 && hi == mhi && lo == mlo)) - 1;
+        wi = __shfl_sync(AVK_FULL, wi, owner);
+        u32 id;
+        const int nf = spill_nfree;
+        if (nf > 0) id = ((const u32 *)spill_base)[nf - 1];
+        else if (spill_used < spill_cap) id = (u32)spill_used;
+        else return -1;
+        const int slot = (int)LD32(qslot + 4 * wi);
+        u32 *dst = (u32 *)spill_node(id);
+        const addr src = node(slot);
+        const int words = stride >> 2;
+#pragma unroll 1
+        for (int i = lane; i < words; i += 32) dst[i] = LD32(src + 4 * i);
+        __syncwarp();
+        if (lane == 0) {
+            ST32(qslot + 4 * wi, 0x80000000u | id);
+            if (nf > 0) spill_nfree = nf - 1; else spill_used = spill_used + 1;
+        }
+        __syncwarp();
+        return slot;
+    }
+    __device__ __noinline__ int alloc_slot() {   // warp-uniform; -1 when exhausted
+        const int nf = nfree;
+        if (nf == 0) return evict_one();
+        const int s = (int)LD32(freel + 4 * (nf - 1));
+        __syncwarp();
+        if (lane_id() == 0) nfree = nf - 1;
+        __syncwarp();
+        return s;
+    }
+    __device__ __forceinline__ bool push(u64 key, int slot) {
+        const int n = qn;
+        if (n >= qcap) return false;
         __syncwarp();
         if (lane_id() == 0) { ST64(qkeys + 8 * n, key); ST32(qslot + 4 * n, slot); qn = n + 1; }
         __syncwarp();
+        return true;
     }
-    // pop the minimum key: warp-parallel scan, then two REDUX min-reductions (high word, low word)
-    // and a ballot to locate the owner -- keys are unique, so exactly one lane matches.
+    // pop the minimum key: warp-parallel scan, then two REDUX min-reductions (high word, low word) and a ballot to
+    // locate the owner -- keys are unique, so exactly one lane matches.  A spilled node is brought back into a slot.
+    // returns the slot, or -1 if no slot could be made available.
     __device__ __noinline__ int pop(u32 *key_hi) {
         const int lane = lane_id();
         const int n = qn;
@@ -428,11 +500,22 @@ struct RegionSolver {
         const u32 mlo = __reduce_min_sync(AVK_FULL, hi == mhi ? lo : 0xffffffffu);
         const int owner = __ffs(__ballot_sync(AVK_FULL, hi == mhi && lo == mlo)) - 1;
         bi = __shfl_sync(AVK_FULL, bi, owner);
-        const int slot = (int)LD32(qslot + 4 * bi);
+        const u32 v = LD32(qslot + 4 * bi);
         __syncwarp();
         if (lane == 0) { ST64(qkeys + 8 * bi, LD64(qkeys + 8 * (n - 1))); ST32(qslot + 4 * bi, LD32(qslot + 4 * (n - 1))); qn = n - 1; }
         __syncwarp();
         *key_hi = mhi;
+        if (!(v & 0x80000000u)) return (int)v;
+        const int slot = alloc_slot();
+        if (slot < 0) return -1;
+        const u32 id = v & 0x7fffffffu;
+        const u32 *src = (const u32 *)spill_node(id);
+        const addr dst = node(slot);
+        const int words = stride >> 2;
+#pragma unroll 1
+        for (int i = lane; i < words; i += 32) ST32(dst + 4 * i, src[i]);
+        __syncwarp();
+        free_spill(id);
         return slot;
     }
 
@@ -481,18 +564,19 @@ struct RegionSolver {
 #pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
             const u64 key = LD64(qkeys + 8 * i);
-            const int sl = (int)LD32(qslot + 4 * i);
+            const u32 sl = LD32(qslot + 4 * i);
             bool dead;
             if (!exact) dead = (u32)(key >> 32) > best;
             else {
-                const int depth = LDI(node(sl) + XN_DEPTH);
+                const int depth = (int)qnode_ld32(sl, XN_DEPTH);
                 dead = (u32)(key >> 48) >= best || (depth != n_total && depth < min_sync);
             }
             if (!dead) {
+                __syncwarp();
                 if (lane_id() == 0 && w != i) { ST64(qkeys + 8 * w, key); ST32(qslot + 4 * w, sl); }
                 w += 1;
             } else {
-                free_slot(sl);
+                free_entry(sl);
             }
             __syncwarp();
         }
@@ -601,7 +685,8 @@ struct RegionSolver {
     __device__ __noinline__ int optimize(bool stop_at_nonzero) {
         const int lane = lane_id();
         const int n = N;
-        if (!partition(opt_stride(), min(n + 3, 48))) return SOLVE_WORKSPACE;   // cheap early escalation
+        // without a spill area: cheap early escalation when the search obviously will not fit
+        if (!partition(opt_stride(), spill_bytes ? 6 : min(n + 3, 48))) return SOLVE_WORKSPACE;
 #pragma unroll 1
         for (int i = lane; i <= n; i += 32) ST32(bucket + 4 * i, 0);
         n_res = 0;
@@ -620,12 +705,13 @@ struct RegionSolver {
             __syncwarp();
             if (lane == 0) { ST32(n_wf(nb, 0), 0); ST32(n_wf(nb, 1), 0); }
             __syncwarp();
-            push(0ull, s);
+            if (!push(0ull, s)) return SOLVE_WORKSPACE;
         }
 #pragma unroll 1
         while (qn > 0) {
             u32 cost;
             const int s = pop(&cost);
+            if (s < 0) return SOLVE_WORKSPACE;
             __syncwarp();
             if (lane == 0) ST32(wk() + WK_SPOPS, LD32(wk() + WK_SPOPS) + 1);
             if (stop_at_nonzero && cost > 0) break;        // nothing cheaper is left; n_res tells if a zero-cost result exists
@@ -687,7 +773,7 @@ struct RegionSolver {
                 u32 c;
                 const int rc = opt_extend(node(sl), oi, a1, a2, &c);
                 if (rc) return rc;
-                push(((u64)c << 32) | LD32(node(sl) + ON_ID), sl);
+                if (!push(((u64)c << 32) | LD32(node(sl) + ON_ID), sl)) return SOLVE_WORKSPACE;
             }
         }
         n_res = nres;
@@ -767,7 +853,7 @@ struct RegionSolver {
         const int lane = lane_id();
         const int n = N;
         if (n >= 0xffff) return SOLVE_WORKSPACE;
-        if (!partition(ex_stride(), min(n + 3, 48))) return SOLVE_WORKSPACE;
+        if (!partition(ex_stride(), spill_bytes ? 6 : min(n + 3, 48))) return SOLVE_WORKSPACE;
         u32 next_id = 1;
         int best_err = 0x7fffffff;
         bool have_best = false;
@@ -778,12 +864,13 @@ struct RegionSolver {
             __syncwarp();
             if (lane < 10) ST32(nb + 4 * lane, (lane == 3 || lane == 4 || lane == 7 || lane == 8) ? start : 0);
             __syncwarp();
-            push(ex_key(nb), s);
+            if (!push(ex_key(nb), s)) return SOLVE_WORKSPACE;
         }
 #pragma unroll 1
         while (qn > 0) {
             u32 khi;
             const int s = pop(&khi);
+            if (s < 0) return SOLVE_WORKSPACE;
             __syncwarp();
             if (lane == 0) ST32(wk() + WK_XPOPS, LD32(wk() + WK_XPOPS) + 1);
             const addr nb = node(s);
@@ -830,7 +917,7 @@ struct RegionSolver {
                 const int sl = k ? s_alt : s;
                 const int keep = ex_extend(node(sl), oi, k == 1, is_alt && k == 0, false);
                 if (keep < 0) return keep;
-                if (keep) push(ex_key(node(sl)), sl); else free_slot(sl);
+                if (keep) { if (!push(ex_key(node(sl)), sl)) return SOLVE_WORKSPACE; } else free_slot(sl);
             }
             af_counts += 1;                                                    // :310-339
             if (af_counts >= 500) {
@@ -839,13 +926,13 @@ struct RegionSolver {
                 const int cnt = qn;
 #pragma unroll 1
                 for (int i = 0; i < cnt; ++i) {
-                    const int sl = (int)LD32(qslot + 4 * i);
-                    const bool set = LDI(node(sl) + XN_DEPTH) > af_index;
-                    if (!set || LD8(node(sl) + XN_HDR + af_index) == AL_REF) {
+                    const u32 sl = LD32(qslot + 4 * i);
+                    const bool set = (int)qnode_ld32(sl, XN_DEPTH) > af_index;
+                    if (!set || qnode_ld8(sl, XN_HDR + af_index) == AL_REF) {
                         if (lane == 0 && w != i) { ST64(qkeys + 8 * w, LD64(qkeys + 8 * i)); ST32(qslot + 4 * w, sl); }
                         w += 1;
                     } else {
-                        free_slot(sl);
+                        free_entry(sl);
                     }
                     __syncwarp();
                 }
