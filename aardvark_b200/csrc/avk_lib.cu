@@ -241,6 +241,89 @@ __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const Dev
     __syncwarp();
 }
 
+// ---- closed form for the commonest cluster shape ------------------------------------------------------------
+// One truth SNV and one query SNV at the same position with the same ALT base (!= the reference base) and the same
+// number of ALT copies: ~60 % of a small-variant WGS comparison.  What solve_compare_region computes for it follows
+// from the search itself (query_optimizer.rs:203-328): the orientation(s) in which both haplotypes spell identical
+// sequences finalise with cost 0 after at most four pops at the last depth (hence max_branch_factor >= 4), every
+// other orientation spells ref-vs-alt on some haplotype and costs more, so each equal-best result has ED 0, no skipped
+// variant and expected == observed == ALT copies for both records.  Metrics: gt/hap/weighted_hap TP on both sides
+// (grouped_metrics.rs:183-227), basepair X = Y = ED(ref, alt hap) = 1 per ALT haplotype, Z = 0
+// (waffle_solver.rs:639-648), record basepair 2 * copies * raw_allele_space (:455-522; needs raw >= 1, else the
+// general path reports the underflow).  Everything else -- including these shapes with the hidden exact shortcut or
+// the sequence bundle requested -- goes to the search kernels through `work_list`.
+__global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, u64 n, u32 *work_list,
+                                                        u32 *work_ctr) {
+    const int lane = lane_id();
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const bool enabled = !cfg.enable_exact_shortcut && !(out.seq_off && cfg.enable_sequences) && cfg.max_branch_factor >= 4;
+    const u32 supported = (1u << AVK_VT_SNV) | (1u << AVK_VT_INSERTION) | (1u << AVK_VT_DELETION) | (1u << AVK_VT_INDEL) |
+                          (1u << AVK_VT_TR_CONTRACTION) | (1u << AVK_VT_TR_EXPANSION) | (1u << AVK_VT_SV_DELETION) | (1u << AVK_VT_SV_INSERTION);
+    for (u64 base = warp * 32; base < n; base += n_warps * 32) {
+        const u64 r = base + lane;
+        bool simple = false;
+        u32 copies = 0, gvT = 0, gvQ = 0, wT = 0, wQ = 0, rawT = 0, rawQ = 0;
+        if (r < n && enabled) {
+            const u8 *dig = b.digest + b.digest_off[r];
+            const int4 h = *(const int4 *)dig;                         // status, N, nT, nQ
+            const u32 c = b.contig[r];
+            if (h.x == AVK_ST_OK && h.y == 2 && h.z == 1 && h.w == 1 && c < b.n_contigs && b.start[r] <= b.end[r] &&
+                (u64)b.end[r] <= b.contig_len[c] && b.end[r] <= 0x7fff0000u) {
+                const uint4 t0 = *(const uint4 *)(dig + PH_SIZE), t1 = *(const uint4 *)(dig + PH_SIZE + 16);
+                const uint4 q0 = *(const uint4 *)(dig + PH_SIZE + VI_SIZE), q1 = *(const uint4 *)(dig + PH_SIZE + VI_SIZE + 16);
+                // t0 = {pos, l0, l1, aoff}, t1 = {alt_ed, raw, gv, flags}
+                const u32 zT = (t1.w >> 8) & 0xff, zQ = (q1.w >> 8) & 0xff;
+                const u32 cT = zT == AVK_ZYG_HOM_ALT ? 2u : (zT >= AVK_ZYG_UNPHASED_HET ? 1u : 0u);
+                const u32 cQ = zQ == AVK_ZYG_HOM_ALT ? 2u : (zQ >= AVK_ZYG_UNPHASED_HET ? 1u : 0u);
+                if ((t1.w & 0x100ffu) == (0x10000u | AVK_VT_SNV) && (q1.w & 0x100ffu) == AVK_VT_SNV && t0.x == q0.x &&
+                    t0.y == 1 && t0.z == 1 && q0.y == 1 && q0.z == 1 && cT != 0 && cT == cQ && t1.y >= 1 && q1.y >= 1) {
+                    const u8 *alle = dig + PH_SIZE + 2 * VI_SIZE;
+                    const u8 altT = alle[t0.w + 1], altQ = alle[q0.w + 1];
+                    simple = altT == altQ && altT != b.contig_ptr[c][t0.x];
+                    copies = cT; gvT = t1.z; gvQ = q1.z; wT = t1.x; wQ = q1.x; rawT = t1.y; rawQ = q1.y;
+                }
+            }
+        }
+        // everything else: compact list for the search / score kernels (cluster order kept inside a warp's chunk)
+        const u32 rest = __ballot_sync(AVK_FULL, r < n && !simple);
+        u32 pos0 = 0;
+        if (lane == 0 && rest) pos0 = atomicAdd(work_ctr, (u32)__popc(rest));
+        pos0 = __shfl_sync(AVK_FULL, pos0, 0);
+        if (r < n && !simple) work_list[pos0 + __popc(rest & ((1u << lane) - 1))] = (u32)r;
+        if (simple) {
+            out.status[r] = AVK_ST_OK; out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = (uint16_t)supported;
+            out.vexp[gvT] = (u8)copies; out.vobs[gvT] = (u8)copies; out.vcls[gvT] = AVK_CLASS_TP;
+            out.vexp[gvQ] = (u8)copies; out.vobs[gvQ] = (u8)copies; out.vcls[gvQ] = AVK_CLASS_TP;
+        }
+        // metric rows [13][22], written by the whole warp per cluster: joint row == SNV row, the rest zero
+        u32 todo = __ballot_sync(AVK_FULL, simple);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const u64 cp = __shfl_sync(AVK_FULL, copies, src);
+            const u64 vwT = __shfl_sync(AVK_FULL, wT, src), vwQ = __shfl_sync(AVK_FULL, wQ, src);
+            const u64 vrT = __shfl_sync(AVK_FULL, rawT, src), vrQ = __shfl_sync(AVK_FULL, rawQ, src);
+            u64 *dst = out.region_metrics + (base + src) * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
+#pragma unroll 1
+            for (int i = lane; i < AVK_N_GROUPS * AVK_N_METRICS; i += 32) {
+                const int g = i / AVK_N_METRICS, m = i - g * AVK_N_METRICS;
+                u64 v = 0;
+                if (g == 0 || g == 1 + AVK_VT_SNV) {
+                    if (m == AVK_M_GT || m == AVK_M_GT + 2) v = 1;
+                    else if (m == AVK_M_HAP || m == AVK_M_HAP + 2) v = cp;
+                    else if (m == AVK_M_WEIGHTED_HAP) v = cp * vwT;
+                    else if (m == AVK_M_WEIGHTED_HAP + 2) v = cp * vwQ;
+                    else if (m == AVK_M_BASEPAIR || m == AVK_M_BASEPAIR + 2) v = 2 * cp;
+                    else if (m == AVK_M_RECORD_BP) v = 2 * cp * vrT;
+                    else if (m == AVK_M_RECORD_BP + 2) v = 2 * cp * vrQ;
+                }
+                dst[i] = v;
+            }
+        }
+    }
+}
+
 // Work distribution of one stage.  work_ctr = work counter of this launch, fail_ctr = number of clusters
 // that did not fit (appended to fail_list, re-run by a later stage).  n_work is read from device memory
 // when n_work_ptr is set, so that stages can be chained without a host round trip.
@@ -791,9 +874,9 @@ static int run_prepare(avk_ctx *ctx, const DevBatch &db) {
 // for the clusters that did not fit the common tier (list A) -> fused 2 MB global-arena stage (list B) -> rare
 // host-synchronised bigger arenas (list D).  Every stage reads its work count from the previous stage's overflow
 // counter in device memory, so the common case needs no host round trip.
-// counters (u32): 0 search work, 1 |A|, 2 score work, 4 S1 work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
-template <class F>
-static int run_compare_pipeline(avk_ctx *ctx, u64 n, F launch) {
+// counters (u32): 12 |W| (clusters without a closed form), 0 search work, 1 |A|, 2 score work, 4 S1 work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
+template <class P, class F>
+static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
     const int INF = 0x7fffffff;
@@ -818,12 +901,14 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, F launch) {
     const Stage SEARCH = {MODE_SEARCH, true, 3, 8192, sm * 3, 8}, SCORE = {MODE_SCORE, true, 4, 5120, sm * 4, 8};
     const Stage S1 = {MODE_FUSED, true, 1, 27648, sm, 8}, G0 = {MODE_FUSED, false, 1, 2LL << 20, sm, 8};
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+    u32 *LW = (u32 *)ctx->fail_h.p;
+    simple(LW, ctrs + 12);                                                                        // closed-form clusters; the rest -> W
     {
-        TierArgs a = args(nullptr, 0, 0, LA, 1, SEARCH.arena_bytes, nullptr);
+        TierArgs a = args(LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr);
         launch(SEARCH, a, (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8), ctx->stream);
     }
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
-    launch(SCORE, args(nullptr, 0, 2, LA, 1, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->stream);   // overflows join A
+    launch(SCORE, args(LW, 12, 2, LA, 1, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->stream);   // overflows join A
     CK(cudaEventRecord(ctx->tev[2], ctx->stream));
     {
         TierArgs a = args(LA, 1, 4, LB, 5, S1.arena_bytes, nullptr);
@@ -832,7 +917,7 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, F launch) {
     }
     launch(G0, args(LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p), G0.ctas, ctx->stream);  // B -> D   (2 MB global arenas)
     CK(cudaEventRecord(ctx->tev[3], ctx->stream));
-    ctx->launches += 4;
+    ctx->launches += 5;
     CK(cudaGetLastError());
     u32 h[16];
     CK(cudaMemcpyAsync(h, ctrs, 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -893,7 +978,9 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     rc = run_prepare(ctx, db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = run_compare_pipeline(ctx, n, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
+    rc = run_compare_pipeline(ctx, n, [&](u32 *list, u32 *ctr) {
+        k_compare_simple<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, out, c, n, list, ctr);
+    }, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
         if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(ctx, db, out, c, a, ctas, st.warps, strm);
         else if (st.mode == MODE_SCORE) launch_compare<true, 4, MODE_SCORE>(ctx, db, out, c, a, ctas, st.warps, strm);
         else if (st.smem && st.min_ctas == 2) launch_compare<true, 2, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);

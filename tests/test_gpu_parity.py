@@ -180,6 +180,47 @@ def test_compare_edge_cases_vs_oracle(solver):
     assert int(gpu.error_blocks[0]) == 3
 
 
+def test_compare_single_snv_pairs_closed_form_vs_oracle(solver):
+    """One truth + one query SNV: every zygosity pair, equal / different ALT, ALT == reference base, allele0 that
+    disagrees with the reference, odd type labels and raw_allele_space 0 -- the shapes around k_compare_simple's
+    closed form -- under branch factors 1..50, the exact shortcut and the sequence bundle."""
+    import itertools
+    from aardvark_b200.types import Coordinates, PhasedZygosity as Z, Variant, VariantType
+    rng = np.random.default_rng(11)
+    ref = bytes(synth.ACGT[rng.integers(0, 4, size=4000)])
+    solver.set_reference([ref], ["c"])
+    zygs = [Z.Unknown, Z.HomozygousReference, Z.UnphasedHeterozygous, Z.PhasedHet01, Z.PhasedHet10, Z.HomozygousAlternate]
+    regions, zero_raw = [], []
+    rid = 0
+    for zt, zq in itertools.product(zygs, zygs):
+        for shape in range(7):
+            p = 60 + 7 * (rid % 500)
+            r0 = ref[p:p + 1]
+            alts = [b for b in (b"A", b"C", b"G", b"T") if b != r0]
+            ta, qa, t0, q0, tp, qp = alts[0], alts[0], r0, r0, p, p
+            tt = qt = VariantType.Snv
+            if shape == 1: qa = alts[1]            # different ALT
+            if shape == 2: ta = qa = r0            # ALT == reference base
+            if shape == 3: t0 = q0 = alts[2]       # allele0 disagrees with the reference
+            if shape == 4: qp = p + 1; q0 = ref[qp:qp + 1]; qa = [b for b in (b"A", b"C", b"G", b"T") if b != q0][0]
+            if shape == 5: qt = VariantType.Indel  # odd label on a 1 -> 1 substitution
+            if shape == 6: zero_raw.append(rid)
+            regions.append(CompareRegion(rid, Coordinates("c", p - 50, p + 52), [Variant(0, tt, tp, t0, ta)], [zt],
+                                         [Variant(0, qt, qp, q0, qa)], [zq]))
+            rid += 1
+    batch = RegionBatch.from_compare_regions(regions, {"c": 0})
+    for r in zero_raw:   # raw_allele_space 0 on the truth record: the record-basepair underflow check must still fire
+        batch.raw_allele_space[int(batch.var_off[2 * r])] = 0
+    off, plen = seq_offsets(batch)
+    for mbf in (1, 2, 3, 4, 50):
+        gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False, max_branch_factor=mbf))
+        assert gpu.diff(cpu) == [], f"max_branch_factor={mbf}"
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False, enable_exact_shortcut=True))
+    assert gpu.diff(cpu) == []
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=True), seq_off=off, seq_pool_len=plen)
+    assert gpu.diff(cpu) == []
+
+
 def test_merge_synthetic_vs_oracle(solver):
     ref, batch = synth.workload_merge(150_000, 400, n_sets=5, seed=38)
     solver.set_reference([ref])
