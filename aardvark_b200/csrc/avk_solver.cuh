@@ -849,7 +849,10 @@ struct RegionSolver {
     }
 
     // in: hap_alle[oi] (AL_REF / AL_ALT by order index).  out: obs[oi], *errors.
-    __device__ __noinline__ int exact_gt(addr obs, int *errors_out) {
+    // `budget`: the caller only cares about results with fewer than `budget` errors.  Nodes are popped in
+    // non-decreasing error order, so the search stops at the first popped node that reaches the budget and reports
+    // *errors_out = budget ("at least").
+    __device__ __noinline__ int exact_gt(addr obs, int *errors_out, int budget) {
         const int lane = lane_id();
         const int n = N;
         if (n >= 0xffff) return SOLVE_WORKSPACE;
@@ -875,6 +878,7 @@ struct RegionSolver {
             if (lane == 0) ST32(wk() + WK_XPOPS, LD32(wk() + WK_XPOPS) + 1);
             const addr nb = node(s);
             const int errors = LDI(nb + XN_ERR);
+            if (errors >= budget && !have_best) { *errors_out = budget; return SOLVE_OK; }
             if (errors >= best_err) { free_slot(s); continue; }                // :169 non-strict
             const int oi = LDI(nb + XN_DEPTH);
             if (oi == n) {                                                     // :180-192
@@ -1133,33 +1137,41 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
         shortcut = s == 0;
     }
     if (!shortcut) {
-        // ---- exact-GT scoring of every equal-best solution; first minimum wins (:169-265)
+        // ---- exact-GT scoring of every equal-best solution; first minimum wins (:169-265).
+        // A haplotype with ED 0 and nothing skipped scores 0 errors: the zero-flip path of optimize_gt_alleles replays
+        // exactly the optimizer's tracker steps, stays alive, is popped first (fewest errors, most set alleles) and
+        // finalises with 0 errors, after which every other node is pruned (exact_gt_optimizer.rs:169).  Any other
+        // haplotype scores at least 1: its zero-flip path ends in unequal sequences or a skipped variant.  Only a
+        // strictly smaller total replaces the current first minimum, so a solution whose lower bound already reaches
+        // it is not searched at all, and a search stops once it has used up what is left of the budget.
         int best_total = 0x7fffffff;
 #pragma unroll 1
         for (int ri = 0; ri < n_res; ++ri) {
+            const addr ra = res_alle + (u32)(ri * npad);
+            const addr rnum = res_num + (u32)(ri * 24);
+            const bool zero0 = LDI(rnum) + LDI(rnum + 8) + LDI(rnum + 16) == 0;
+            const bool zero1 = LDI(rnum + 4) + LDI(rnum + 12) + LDI(rnum + 20) == 0;
+            if ((zero0 ? 0 : 1) + (zero1 ? 0 : 1) >= best_total) continue;
             int total = 0;
+            bool lost = false;
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                const addr ra = res_alle + (u32)(ri * npad);
+            for (int h = 0; h < 2 && !lost; ++h) {
 #pragma unroll 1
                 for (int i = lane; i < n; i += 32) ST8(hap_alle + i, ((LD8(ra + i) >> h) & 1) ? AL_ALT : AL_REF);
                 __syncwarp();
                 int errs = 0;
-                const addr rnum = res_num + (u32)(ri * 24);
-                if (LDI(rnum + 4 * h) + LDI(rnum + 4 * (2 + h)) + LDI(rnum + 4 * (4 + h)) == 0) {
-                    // ED 0 and nothing skipped on this haplotype: the zero-flip path of optimize_gt_alleles replays
-                    // exactly these tracker steps, stays alive, is popped first (fewest errors, most set alleles)
-                    // and finalises with 0 errors, after which every other node is pruned (errors >= best,
-                    // exact_gt_optimizer.rs:169).  Its result is the input alleles.
+                if (h ? zero1 : zero0) {
                     warp_copy<SMEM>(cur_obs + (u32)(h * npad), hap_alle, n);
                     __syncwarp();
                 } else {
-                    rc = exact_gt(cur_obs + (u32)(h * npad), &errs);
+                    const int budget = best_total - total - ((h == 0 && !zero1) ? 1 : 0);
+                    rc = exact_gt(cur_obs + (u32)(h * npad), &errs, budget);
                     if (rc) return rc;
+                    lost = errs >= budget;
                 }
                 total += errs;
             }
-            if (total < best_total) {
+            if (!lost && total < best_total) {
                 best_total = total;
                 best_r = ri;
                 warp_copy<SMEM>(best_obs, cur_obs, 2 * npad);
