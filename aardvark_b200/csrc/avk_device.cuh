@@ -58,7 +58,8 @@ template <> struct Mem<false> {
 #define ST64(a, v) (*(u64 *)M::p(a) = (u64)(v))
 
 // ---- work counters (DESIGN.md "algorithmic work"); live in the arena header ---------------------
-enum { WK_CELLS = 16, WK_MATCHED = 24, WK_ALIGN = 32, WK_SPOPS = 36, WK_XPOPS = 40, ARENA_HDR = 48 };
+enum { WK_COOP = 8, WK_CELLS = 16, WK_MATCHED = 24, WK_ALIGN = 32, WK_SPOPS = 36, WK_XPOPS = 40, ARENA_HDR = 48 };
+// WK_COOP != 0: the warp is the master warp of a k_compare_coop CTA and may hand wide wavefronts to the whole CTA
 
 // ---- unaligned 32-bit load: two aligned loads + funnel shift ------------------------------------
 template <bool SMEM>
@@ -250,17 +251,162 @@ __device__ __noinline__ void dwfa_grow(typename Mem<SMEM>::addr wf, int old_ed) 
     __syncwarp();
 }
 
+
 enum { DWFA_OK = 0, DWFA_MAX_ED = 1 };
+
+// ---- CTA-cooperative DWFA for wide wavefronts (SV / long-indel clusters) -------------------------------------
+// A 10 kbp event means an edit distance of ~10^4: 10^8 wavefront cells in ONE alignment, far too much for one warp.
+// In k_compare_coop one master warp runs the solver; when a wavefront reaches COOP_MIN_ED it posts the alignment as
+// a job and all COOP_THREADS threads of the CTA advance it together: wavefront ping-ponged in shared memory, one
+// diagonal per thread (thread-serial word compares), grow + extend fused so that a step costs one barrier
+// (__syncthreads_or doubles as the termination vote).  Same recurrence and stop rules as dwfa_grow/dwfa_extend.
+enum { COOP_THREADS = 512, COOP_MIN_ED = 48, COOP_JOB_BYTES = 128, DWFA_COOP_SPILL = 2 };
+struct CoopJob {
+    u64 wf;                                  // the node's wavefront ints (global memory)
+    u64 a_data, a_tail, b_data, b_tail;
+    int a_mlen, a_len, b_mlen, b_len;
+    int ed, max_ed, to_full, status, exit_, cap_ints;
+    unsigned long long matched, cells;
+};
+static_assert(sizeof(CoopJob) <= COOP_JOB_BYTES, "CoopJob must fit its slot");
+
+__device__ __forceinline__ int lcp_thread(const VSeq<false> &A, int ia, const VSeq<false> &B, int ib) {
+    typedef Mem<false> M;
+    const int maxn = min(A.len - ia, B.len - ib);
+    int total = 0;
+#pragma unroll 1
+    while (total < maxn) {
+        const int xa = ia + total, xb = ib + total;
+        const int n = min(min(A.run(xa, maxn), B.run(xb, maxn)), maxn - total);
+        const u64 pa = A.at(xa), pb = B.at(xb);
+        if (pa == pb) { total += n; continue; }
+        int k = 0;
+#pragma unroll 1
+        while (k < n) {
+            const u32 x = ld4u<false>(pa + k) ^ ld4u<false>(pb + k);
+            const int good = min(x ? ((__ffs(x) - 1) >> 3) : 4, n - k);
+            k += good;
+            if (x && good < 4) break;
+        }
+        total += k;
+        if (k < n) break;
+    }
+    return total;
+}
+
+// executed by every thread of the CTA; the job is in CoopJob at the start of dynamic shared memory
+__device__ __noinline__ void coop_dwfa_body() {
+    CoopJob &J = *(CoopJob *)avk_dyn_smem;
+    int *cur = (int *)(avk_dyn_smem + COOP_JOB_BYTES), *nxt = cur + J.cap_ints;
+    const int tid = threadIdx.x, T = blockDim.x;
+    VSeq<false> A, B;
+    A.data = J.a_data; A.tail = J.a_tail; A.mlen = J.a_mlen; A.len = J.a_len;
+    B.data = J.b_data; B.tail = J.b_tail; B.mlen = J.b_mlen; B.len = J.b_len;
+    const int la = A.len, lb = B.len, max_ed = J.max_ed, e_cap = (J.cap_ints - 3) / 2;
+    const bool to_full = J.to_full != 0;
+    int *gw = (int *)(uintptr_t)J.wf;
+    int e = J.ed, status = DWFA_OK;
+    unsigned long long matched = 0, cells = 0;
+    bool flag = false;
+#pragma unroll 1
+    for (int i = tid; i < 2 * e + 1; i += T) {           // extend() of the wavefront as it stands
+        int d = gw[i];
+        int boff = d + e - i;
+        if (boff < la && d < lb) { const int ext = lcp_thread(A, boff, B, d); d += ext; boff += ext; matched += ext; }
+        cur[i] = d;
+        flag = flag || (to_full ? (boff >= la && d >= lb) : (boff >= la || d >= lb));
+    }
+    cells += 2 * e + 1;
+    int stop = __syncthreads_or(flag);
+#pragma unroll 1
+    while (!stop) {
+        e += 1;
+        if (e > max_ed) { status = DWFA_MAX_ED; break; }                 // *ed stays incremented, wavefront not grown
+        if (e > e_cap) { status = DWFA_COOP_SPILL; e -= 1; break; }      // does not fit shared memory: back to the warp path
+        const int n = 2 * e + 1, n_old = n - 2;
+        flag = false;
+#pragma unroll 1
+        for (int i = tid; i < n; i += T) {
+            int d = 0;                                                   // increase_edit_distance(): dynamic_wfa.rs:152-168
+            if (i < n_old) d = cur[i];
+            if (i >= 1 && i - 1 < n_old) d = max(d, cur[i - 1] + 1);
+            if (i >= 2 && i - 2 < n_old) d = max(d, cur[i - 2] + 1);
+            int boff = d + e - i;
+            if (boff < la && d < lb) { const int ext = lcp_thread(A, boff, B, d); d += ext; boff += ext; matched += ext; }
+            nxt[i] = d;
+            flag = flag || (to_full ? (boff >= la && d >= lb) : (boff >= la || d >= lb));
+        }
+        cells += n;
+        stop = __syncthreads_or(flag);
+        int *t = cur; cur = nxt; nxt = t;
+    }
+    const int n_out = 2 * (status == DWFA_MAX_ED ? e - 1 : e) + 1;
+#pragma unroll 1
+    for (int i = tid; i < n_out; i += T) gw[i] = cur[i];
+    if (matched) atomicAdd(&J.matched, matched);
+    if (tid == 0) { J.ed = e; J.status = status; J.cells = cells; }
+    __threadfence_block();
+    __syncthreads();
+}
+
+// master warp: post the job, work on it with everybody else, collect the result
+__device__ __noinline__ int dwfa_run_coop(u64 wf, int *ed, int max_ed, const VSeq<false> A, const VSeq<false> B, bool to_full, u64 wk) {
+    typedef Mem<false> M;
+    CoopJob &J = *(CoopJob *)avk_dyn_smem;
+    __syncwarp();
+    if (lane_id() == 0) {
+        J.wf = wf; J.a_data = A.data; J.a_tail = A.tail; J.b_data = B.data; J.b_tail = B.tail;
+        J.a_mlen = A.mlen; J.a_len = A.len; J.b_mlen = B.mlen; J.b_len = B.len;
+        J.ed = *ed; J.max_ed = max_ed; J.to_full = to_full ? 1 : 0; J.status = 0; J.exit_ = 0; J.matched = 0; J.cells = 0;
+    }
+    __threadfence();                                   // the wavefront ints were written by this warp through global memory
+    __syncwarp();
+    asm volatile("bar.sync 1, %0;" ::"r"((int)COOP_THREADS) : "memory");
+    coop_dwfa_body();
+    const int st = J.status;
+    *ed = J.ed;
+    if (lane_id() == 0) { ST64(wk + WK_CELLS, LD64(wk + WK_CELLS) + J.cells); ST64(wk + WK_MATCHED, LD64(wk + WK_MATCHED) + J.matched); }
+    __syncwarp();
+    return st;
+}
+// helper warps of k_compare_coop
+__device__ __forceinline__ void coop_helper_loop() {
+    CoopJob &J = *(CoopJob *)avk_dyn_smem;
+    for (;;) {
+        asm volatile("bar.sync 1, %0;" ::"r"((int)COOP_THREADS) : "memory");
+        if (J.exit_) return;
+        coop_dwfa_body();
+    }
+}
+__device__ __forceinline__ void coop_release_helpers() {   // master warp, all lanes
+    CoopJob &J = *(CoopJob *)avk_dyn_smem;
+    __syncwarp();
+    if (lane_id() == 0) J.exit_ = 1;
+    __syncwarp();
+    asm volatile("bar.sync 1, %0;" ::"r"((int)COOP_THREADS) : "memory");
+}
 
 // update() (dynamic_wfa.rs:68-84) when !to_full, finalize() (:183-198) when to_full.
 // *ed is left incremented when the cap is hit (:146-149).
 template <bool SMEM>
 __device__ __noinline__ int dwfa_run(typename Mem<SMEM>::addr wf, int *ed, int max_ed, const VSeq<SMEM> A, const VSeq<SMEM> B,
                                      bool to_full, typename Mem<SMEM>::addr wk) {
+    typedef Mem<SMEM> M;
     int e = *ed;
+    bool coop = !SMEM && LD32(wk + WK_COOP) != 0;
     Reach r = dwfa_extend<SMEM>(wf, e, A, B, wk);
 #pragma unroll 1
     while (to_full ? !r.full : (!(r.max_base >= A.len) && !(r.max_other >= B.len))) {
+        if constexpr (!SMEM) {
+            if (coop && e >= COOP_MIN_ED) {            // wide wavefront: the whole CTA takes over from here
+                const int rc = dwfa_run_coop(wf, &e, max_ed, A, B, to_full, wk);
+                *ed = e;
+                if (rc != DWFA_COOP_SPILL) return rc;
+                coop = false;                          // wavefront outgrew shared memory: finish on the warp path
+                r = dwfa_extend<SMEM>(wf, e, A, B, wk);
+                continue;
+            }
+        }
         e += 1;
         *ed = e;
         if (e > max_ed) return DWFA_MAX_ED;

@@ -53,7 +53,7 @@ template <bool SMEM>
 __device__ __forceinline__ void clear_work(typename Mem<SMEM>::addr hdr) {
     typedef Mem<SMEM> M;
     const int lane = lane_id();
-    if (lane < 8) ST32(hdr + 16 + 4 * lane, 0);
+    if (lane < 10) ST32(hdr + 8 + 4 * lane, 0);   // WK_COOP and the counters
     __syncwarp();
 }
 
@@ -339,6 +339,7 @@ struct TierArgs {
     int last_tier;
     unsigned long long *work_out;
     u8 *blobs;             // split tier: [n_regions][RB_SIZE] search results handed to the score kernel
+    int wide_b0;           // global stages: hand clusters with an edit-distance bound >= wide_b0 to the next (cooperative) stage
     u8 *spill_base;        // shared-memory stages: per-warp node spill area in global memory (may be NULL)
     u32 spill_bytes;       // per warp
     int n_lo, n_hi;        // stages that scan all regions only take clusters with n_lo <= #variants <= n_hi
@@ -347,7 +348,7 @@ struct TierArgs {
     u32 heavy_bytes;
 };
 
-enum { MODE_FUSED = 0, MODE_SEARCH = 1, MODE_SCORE = 2 };
+enum { MODE_FUSED = 0, MODE_SEARCH = 1, MODE_SCORE = 2, MODE_COOP = 3 };
 
 // Per-CTA shared state: the batch descriptor and one solver object per warp (never a local-memory frame).
 template <bool SMEM>
@@ -366,6 +367,7 @@ __device__ __forceinline__ RegionSolver<SMEM> &init_solver(const DevBatch &b, co
         s.arena_bytes = (u32)t.arena_bytes;
         s.arena = arena;
         s.spill_base = nullptr; s.spill_bytes = 0;
+        s.wide_b0 = t.wide_b0;
         if (SMEM && t.spill_base) {
             s.spill_base = t.spill_base + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (u64)t.spill_bytes;
             s.spill_bytes = t.spill_bytes;
@@ -428,6 +430,48 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompar
         if (lane == 0) out.status[r] = rc;
     }
     flush_work<SMEM>(s.arena, t.work_out);
+}
+
+// SV / long-indel clusters (workspace beyond 2 MB): one cluster per CTA.  Warp 0 runs the solver on a global arena;
+// the other warps wait at a named barrier and join in whenever a wavefront gets wide (avk_device.cuh, dwfa_run_coop).
+__global__ void __launch_bounds__(COOP_THREADS, 1) k_compare_coop(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, TierArgs t, int cap_ints) {
+    __shared__ DevBatch sb;
+    __shared__ RegionSolver<false> sol1;
+    if (threadIdx.x == 0) { sb = b; ((CoopJob *)avk_dyn_smem)->cap_ints = cap_ints; ((CoopJob *)avk_dyn_smem)->exit_ = 0; }
+    __syncthreads();
+    if (threadIdx.x >= 32) { coop_helper_loop(); return; }
+    const int lane = lane_id();
+    RegionSolver<false> &s = sol1;
+    const u64 arena = (u64)(uintptr_t)(t.arena_base + (u64)blockIdx.x * (u64)t.arena_bytes);
+    if (lane == 0) {
+        s.bp = &sb; s.tma_phase = 0; s.tma_pending = 0;
+        s.arena_bytes = (u32)(t.arena_bytes > 0xfffffff0LL ? 0xfffffff0LL : t.arena_bytes); s.arena = arena;
+        s.spill_base = nullptr; s.spill_bytes = 0; s.wide_b0 = 0;
+    }
+    clear_work<false>(arena);
+    if (lane == 0) *(u32 *)(uintptr_t)(arena + WK_COOP) = 1u;
+    __syncwarp();
+    const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
+    for (;;) {
+        u32 idx = 0;
+        if (lane == 0) idx = atomicAdd(t.work_ctr, 1u);
+        idx = __shfl_sync(AVK_FULL, idx, 0);
+        if (idx >= n_work) break;
+        const u64 r = t.work_list ? t.work_list[idx] : idx;
+        int rc = s.solve_compare(r, cfg, out);
+        __syncwarp();
+        if (rc == SOLVE_WORKSPACE) {
+            if (!t.last_tier) {
+                if (lane == 0) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
+                continue;
+            }
+            rc = AVK_ST_WORKSPACE;
+        }
+        if (rc != AVK_ST_OK) zero_region_outputs(sb, out, r, false);
+        if (lane == 0) out.status[r] = rc;
+    }
+    flush_work<false>(arena, t.work_out);
+    coop_release_helpers();
 }
 
 template <bool SMEM, int MIN_CTAS>
@@ -915,7 +959,11 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
         a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;   // dense clusters keep running here: cold nodes spill to HBM
         launch(S1, a, S1.ctas, ctx->stream);                                                      // A -> B   (8 warps x 27 KB per SM)
     }
-    launch(G0, args(LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p), G0.ctas, ctx->stream);  // B -> D   (2 MB global arenas)
+    {
+        TierArgs a = args(LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p);
+        a.wide_b0 = 256;                                                                          // SV-sized events: cooperative tier
+        launch(G0, a, G0.ctas, ctx->stream);                                                      // B -> D   (2 MB global arenas)
+    }
     CK(cudaEventRecord(ctx->tev[3], ctx->stream));
     ctx->launches += 5;
     CK(cudaGetLastError());
@@ -925,7 +973,8 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
     ctx->tier_fail[0] = h[1]; ctx->tier_fail[1] = h[5]; ctx->tier_fail[2] = h[7];
     // rare: clusters that overflow 2 MB per warp (list D); host-synchronised escalation
-    const Stage big[2] = {{MODE_FUSED, false, 1, 64LL << 20, (sm + 7) / 8, 8}, {MODE_FUSED, false, 1, 2048LL << 20, 1, 8}};
+    // (SV-sized events).  64 MB: one cluster per CTA, wide wavefronts advanced by the whole CTA; 2 GB: last resort.
+    const Stage big[2] = {{MODE_COOP, false, 1, 64LL << 20, sm, 1}, {MODE_FUSED, false, 1, 2048LL << 20, 1, 8}};
     const u32 *cur = LD;
     u32 *other = LC;
     u32 n_work = h[7];
@@ -981,7 +1030,14 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     rc = run_compare_pipeline(ctx, n, [&](u32 *list, u32 *ctr) {
         k_compare_simple<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, out, c, n, list, ctr);
     }, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
-        if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(ctx, db, out, c, a, ctas, st.warps, strm);
+        if (st.mode == MODE_COOP) {
+            const int cap_ints = 26000;                                  // wavefronts up to ED 12998 stay in shared memory
+            const size_t smem = COOP_JOB_BYTES + 2 * sizeof(int) * (size_t)cap_ints;
+            static bool configured = false;
+            if (!configured) { cudaFuncSetAttribute(k_compare_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+            k_compare_coop<<<ctas, COOP_THREADS, smem, strm>>>(db, out, c, a, cap_ints);
+        }
+        else if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(ctx, db, out, c, a, ctas, st.warps, strm);
         else if (st.mode == MODE_SCORE) launch_compare<true, 4, MODE_SCORE>(ctx, db, out, c, a, ctas, st.warps, strm);
         else if (st.smem && st.min_ctas == 2) launch_compare<true, 2, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);
         else if (st.smem) launch_compare<true, 1, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);

@@ -96,6 +96,7 @@ struct RegionSolver {
     const DevBatch *bp;
     addr arena;           // this warp's workspace (shared-memory offset or global address)
     u32 arena_bytes;
+    int wide_b0;          // global tiers: clusters whose edit-distance bound reaches this go on to the cooperative tier (0 = keep)
     addr ref_base;        // byte of absolute contig position p is at ref_base + p (staged window or global contig)
     addr alle_base;       // allele bytes (staged copy or the global pool)
     int start, end;       // region window
@@ -330,6 +331,7 @@ struct RegionSolver {
         }
         const int st = LDI(hdr + PH_STATUS);
         if (st) return st;
+        if (!SMEM && wide_b0 && LDI(hdr + PH_B0) >= wide_b0) return SOLVE_WORKSPACE;   // wide wavefronts: cooperative tier
         const int n = LDI(hdr + PH_N);
         N = n; nv[0] = LDI(hdr + PH_N0); nv[1] = LDI(hdr + PH_N1);
         const int npad = align_up(max(n, 1), 16);

@@ -270,8 +270,11 @@ def main():
                          "traffic": traffic, "kernel": "k_compare", "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "peak_source": peak_src,
                          "note": "integer DP: the binding roof is the INT32 ALU pipe / latency, see int_roofline"},
+            # executed on the device (closed forms and pruned searches do less than the reference algorithm);
+            # replaced below by the reference algorithm's own counts when the CPU leg runs
             "int_roofline": {"achieved_gops": int_ops / (k_ms * 1e-3) / 1e9, "peak_gops": int_peak / 1e9,
                              "frac": int_ops / (k_ms * 1e-3) / int_peak, "algorithmic_int_ops": int_ops,
+                             "ops_counted_by": "device counters (work actually executed)",
                              "cells": work["cells"], "matched_bases": work["matched_bases"],
                              "search_pops": work["search_pops"], "exact_pops": work["exact_pops"],
                              "peak_source": "measured live (avk_int_peak: add/max/xor chains)"},
@@ -290,6 +293,15 @@ def main():
                 cpu_out = orc.compare_batch(batch, [ref], compare_cfg(cfg), n_threads=threads, region_metrics=False)
                 dt = time.perf_counter() - t0
                 best = dt if best is None else min(best, dt)
+            # algorithmic work = what the reference algorithm computes, counted by the CPU restatement
+            _, cw = orc.compare_batch(batch, [ref], compare_cfg(cfg), n_threads=threads, region_metrics=False, work=True)
+            ref_ops = 6 * cw["cells"] + 4 * ((cw["matched_bases"] + 15) // 16)
+            ir = line["int_roofline"]
+            ir.update({"device_executed": {k: ir[k] for k in ("algorithmic_int_ops", "cells", "matched_bases", "search_pops", "exact_pops")},
+                       "achieved_gops": ref_ops / (k_ms * 1e-3) / 1e9, "frac": ref_ops / (k_ms * 1e-3) / int_peak,
+                       "algorithmic_int_ops": ref_ops, "cells": cw["cells"], "matched_bases": cw["matched_bases"],
+                       "search_pops": cw["search_pops"], "exact_pops": cw["exact_pops"],
+                       "ops_counted_by": "CPU restatement of the reference algorithm (6*cells + 4*ceil(matched/16))"})
             line["cpu_baseline"] = {"value": batch.n_regions / best, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"rank 0's whole batch ({batch.n_regions} clusters), best of {reps}, "
                                               "OpenMP dynamic over clusters, solve phase only",
