@@ -79,7 +79,9 @@ enum { H_TRP = 0, H_QRP = 4, H_TML = 8, H_QML = 12, H_TMR = 16, H_QMR = 20, H_TS
 // exact node: ints {id, errors, depth, t_ref_pos, q_ref_pos, t_mlen, q_mlen, t_mref, q_mref, d}
 enum { XN_ID = 0, XN_ERR = 4, XN_DEPTH = 8, XN_TRP = 12, XN_QRP = 16, XN_TML = 20, XN_QML = 24, XN_TMR = 28, XN_QMR = 32, XN_D = 36, XN_HDR = 48 };
 // sequence descriptors written by build_hap_seq: {mlen, cur, failed, n_alt}
-enum { SD_MLEN = 0, SD_CUR = 4, SD_FAILED = 8, SD_NALT = 12, SD_LAST = 16, SD_SIZE = 32 };   // SD_LAST: order index of the last spliced ALT
+enum { SD_MLEN = 0, SD_CUR = 4, SD_FAILED = 8, SD_NALT = 12, SD_CLOSED = 16, SD_MAT = 20, SD_ARGS = 24, SD_SIZE = 32 };
+// SD_CLOSED: ED(reference window, this haplotype) when it is known without aligning, else -1; SD_MAT: bytes materialised;
+// SD_ARGS: (side, hap, result, type filter) the buffer was described from, for materialising it later
 
 static __device__ __forceinline__ bool type_supported(int t) {   // SUPPORTED_VARIANT_TYPES waffle_solver.rs:82-91
     return t == AVK_VT_SNV || t == AVK_VT_INSERTION || t == AVK_VT_DELETION || t == AVK_VT_INDEL ||
@@ -958,10 +960,21 @@ struct RegionSolver {
     // generate_allele_sequence(): waffle_solver.rs:726-778 as a virtual sequence in buffer `k` (0 T, 1 Q, 2 F).
     // side 0 truth / 1 query, hap 0/1, alleles from result r; type_filter < 0 keeps every variant.
     // Fills sdesc[k] = {mlen, cur, failed ED, #ALT spliced}; returns 0, -1 (capacity) or -2 (variant past the window).
-    __device__ __noinline__ int build_hap_seq(int k, int side, int hap, int r, int type_filter) {
+    // With copy == false only the description is computed; materialise(k) writes the bytes when an alignment needs them.
+    //
+    // ED(reference window, haplotype) is known without aligning in two cases (SD_CLOSED):
+    //  (1) every spliced ALT is a single-base substitution and at most two of them differ from the reference base:
+    //      the haplotype has the window's length and Hamming distance d <= 2 to it, and for equal lengths ED = 1 iff the
+    //      Hamming distance is 1, so ED = d;
+    //  (2) no substitution changes a base and every other spliced ALT is an anchored pure insertion (1 -> L, first base
+    //      == the reference base), or every one an anchored pure deletion (L -> 1): the window is obtained from the
+    //      haplotype (or the reverse) by deleting exactly D bases, D = the length difference, so D <= ED <= D.
+    __device__ __noinline__ int build_hap_seq(int k, int side, int hap, int r, int type_filter, bool copy) {
         const addr dst = dyn + (u32)(k * seq_cap);
         const addr ra = res_alle + (u32)(r * Npad);
-        int cur = start, mlen = 0, failed = 0, n_alt = 0, last = 0;
+        int cur = start, mlen = 0, failed = 0, n_alt = 0;
+        int subm = 0, ins = 0, del = 0;
+        bool open = false;
         const int n = N;
 #pragma unroll 1
         for (int oi = 0; oi < n; ++oi) {
@@ -975,21 +988,43 @@ struct RegionSolver {
             const int l0 = (int)LD32(rec + VI_L0), l1 = (int)LD32(rec + VI_L1);
             const int nref = vpos - cur;
             if (mlen + nref + l1 > seq_cap) return -1;
-            if (nref > 0) warp_copy<SMEM>(dst + mlen, ref_base + cur, nref);
-            warp_copy<SMEM>(dst + mlen + nref, alle_base + LD32(rec + VI_AOFF) + l0, l1);
+            const addr a1 = alle_base + LD32(rec + VI_AOFF) + l0;
+            if (copy) {
+                if (nref > 0) warp_copy<SMEM>(dst + mlen, ref_base + cur, nref);
+                warp_copy<SMEM>(dst + mlen + nref, a1, l1);
+            }
+            const bool anchored = LD8(a1) == LD8(ref_base + vpos);
+            if (l0 == 1 && l1 == 1) subm += anchored ? 0 : 1;
+            else if (l0 == 1 && anchored) ins += l1 - 1;
+            else if (l1 == 1 && anchored) del += l0 - 1;
+            else open = true;
             mlen += nref + l1;
             cur = vpos + l0;
             n_alt += 1;
-            last = oi;
         }
         if (cur > end) return -2;
+        int closed = -1;
+        if (!open) {
+            if (ins == 0 && del == 0) { if (subm <= 2) closed = subm; }
+            else if (subm == 0 && (ins == 0 || del == 0)) closed = ins + del;
+        }
         __syncwarp();
         if (lane_id() == 0) {
             const addr sd = sdesc + (u32)(k * SD_SIZE);
-            ST32(sd + SD_MLEN, mlen); ST32(sd + SD_CUR, cur); ST32(sd + SD_FAILED, failed); ST32(sd + SD_NALT, n_alt); ST32(sd + SD_LAST, last);
+            ST32(sd + SD_MLEN, mlen); ST32(sd + SD_CUR, cur); ST32(sd + SD_FAILED, failed); ST32(sd + SD_NALT, n_alt);
+            ST32(sd + SD_CLOSED, closed); ST32(sd + SD_MAT, copy ? 1 : 0);
+            ST32(sd + SD_ARGS, side | (hap << 1) | ((type_filter + 1) << 2) | (r << 8));
         }
         __syncwarp();
         return 0;
+    }
+    // make sure buffer k holds its bytes (no-op for the reference window, k < 0)
+    __device__ __forceinline__ void materialise(int k) {
+        if (k < 0) return;
+        const addr sd = sdesc + (u32)(k * SD_SIZE);
+        if (LDI(sd + SD_MAT)) return;
+        const int a = LDI(sd + SD_ARGS);
+        build_hap_seq(k, a & 1, (a >> 1) & 1, a >> 8, ((a >> 2) & 63) - 1, true);   // same walk as before: cannot fail
     }
     // virtual sequence of buffer k (k < 0: the reference window itself)
     __device__ __forceinline__ VS seq_vs(int k) const {
@@ -1000,31 +1035,29 @@ struct RegionSolver {
         v.data = dyn + (u32)(k * seq_cap); v.tail = ref_base + cur; v.mlen = mlen; v.len = mlen + (end - cur);
         return v;
     }
-    // ED(reference window, buffer k).  A haplotype whose only spliced ALT is a single-base substitution has the
-    // window's length and differs from it in at most that one position, so the distance is 0 or 1 without aligning.
+    // ED(reference window, buffer k): closed form when build_hap_seq found one, otherwise a global alignment
     __device__ __forceinline__ u64 ed_to_ref(int k) {
-        const addr sd = sdesc + (u32)(k * SD_SIZE);
-        if (LDI(sd + SD_NALT) == 1) {
-            const addr rec = vi(LDI(sd + SD_LAST));
-            if (LD32(rec + VI_L0) == 1 && LD32(rec + VI_L1) == 1) {
-                __syncwarp();
-                if (lane_id() == 0) {
-                    ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
-                    ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1);
-                }
-                return LD8(alle_base + LD32(rec + VI_AOFF) + 1) != LD8(ref_base + LD32(rec + VI_POS)) ? 1u : 0u;
+        const int closed = LDI(sdesc + (u32)(k * SD_SIZE) + SD_CLOSED);
+        if (closed >= 0) {
+            __syncwarp();
+            if (lane_id() == 0) {
+                ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
+                ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1);
             }
+            return (u64)closed;
         }
         return ed_between(-1, k);
     }
     // global edit distance between two sequence buffers, with overflow trap
     __device__ __noinline__ u64 ed_between(int ka, int kb) {
+        materialise(ka); materialise(kb);
         const int e = wfa_ed_warp<SMEM>(seq_vs(ka), seq_vs(kb), dyn + (u32)(3 * seq_cap), (wf_cap - 3) / 2, wk());
         if (e < 0) { ed_overflow = 1; return 0; }
         return (u64)e;
     }
     // copy a sequence buffer to the optional sequence-bundle output
     __device__ __noinline__ void emit_seq(const DevCompareOut &out, u64 r, int s, int k) {
+        materialise(k);
         const VS v = seq_vs(k);
         u8 *dst = out.seq_pool + out.seq_off[r * 5 + s];
 #pragma unroll 1
@@ -1242,7 +1275,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
         // truth / query haplotypes (buffers 0 / 1)
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {
-            const int brc = build_hap_seq(side, side, h, rsel, -1);
+            const int brc = build_hap_seq(side, side, h, rsel, -1, false);
             if (brc) return brc == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
             if (want_seq) emit_seq(out, r, 1 + 2 * side + h, side);
         }
@@ -1272,7 +1305,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
                 if (nf == nv[side]) {                 // filtered == full haplotype
                     f_tp = tp; f_bad = side ? (2 * Y - tp + 2 * failQ) : (2 * X - tp + 2 * failT);
                 } else {
-                    const int brc = build_hap_seq(2, side, h, best_r, ft);
+                    const int brc = build_hap_seq(2, side, h, best_r, ft, false);
                     if (brc) return brc == -1 ? SOLVE_WORKSPACE : AVK_ST_BAD_INPUT;
                     const bool altF = LDI(sdesc + 2 * SD_SIZE + SD_NALT) != 0;
                     const u64 failF = (u64)LDI(sdesc + 2 * SD_SIZE + SD_FAILED);
