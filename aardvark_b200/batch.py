@@ -106,6 +106,25 @@ class RegionBatch:
             [r.coordinates.start for r in regions], [r.coordinates.end for r in regions],
             [[list(zip(v, z)) for v, z in zip(r.variants, r.zygosity)] for r in regions])
 
+    @staticmethod
+    def concat(batches, contigs=None):
+        """Batches over different contigs -> one batch (region ids renumbered in order; batch k gets contig index
+        contigs[k], default k).  allele_off is u32: the joined allele pool must stay below 4 GiB."""
+        k = batches[0].n_inputs
+        assert all(b.n_inputs == k for b in batches)
+        contigs = list(range(len(batches))) if contigs is None else list(contigs)
+        v0 = np.cumsum([0] + [b.n_variants for b in batches])
+        p0 = np.cumsum([0] + [int(b.allele_pool.size) if b.n_variants else 0 for b in batches])
+        assert int(p0[-1]) < (1 << 32)
+        var_off = np.concatenate([b.var_off[:-1] + np.uint64(v0[i]) for i, b in enumerate(batches)] + [np.array([v0[-1]], dtype=np.uint64)])
+        cat = lambda name: np.concatenate([getattr(b, name) for b in batches])
+        n = sum(b.n_regions for b in batches)
+        return RegionBatch(
+            k, np.arange(n, dtype=np.uint64), np.concatenate([np.full(b.n_regions, contigs[i], dtype=np.uint32) for i, b in enumerate(batches)]),
+            cat("start"), cat("end"), var_off, cat("position"), cat("variant_type"), cat("zygosity"), cat("raw_allele_space"),
+            np.concatenate([b.allele_off + np.uint32(p0[i]) for i, b in enumerate(batches)]), cat("a0_len"), cat("a1_len"),
+            np.concatenate([b.allele_pool if b.n_variants else b.allele_pool[:0] for b in batches]))
+
     def slice_regions(self, lo, hi):
         """Contiguous region bin [lo, hi) as its own batch (multi-GPU sharding)."""
         k = self.n_inputs

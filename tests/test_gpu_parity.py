@@ -221,6 +221,24 @@ def test_compare_single_snv_pairs_closed_form_vs_oracle(solver):
     assert gpu.diff(cpu) == []
 
 
+def test_compare_multi_contig_vs_oracle(solver):
+    """BASELINE configs[2] shape: one batch over several contigs of different lengths (contig index -> reference)."""
+    parts = [synth.workload_chr20(scale=sc, seed=sd) for sc, sd in ((0.003, 101), (0.0012, 102), (0.002, 103))]
+    contigs = [p[0] for p in parts]
+    batch = RegionBatch.concat([p[1] for p in parts])
+    assert sorted(set(batch.contig.tolist())) == [0, 1, 2]
+    solver.set_reference(contigs)
+    gpu, cpu = _both_compare(solver, batch, contigs, CompareConfig(enable_sequences=False))
+    assert gpu.diff(cpu) == []
+    assert int(gpu.error_blocks[0]) == 0
+    # a contig bin solved on its own gives the same rows (sharding property, SURVEY 8e)
+    lo = parts[0][1].n_regions
+    hi = lo + parts[1][1].n_regions
+    part = solver.compare_batch(batch.slice_regions(lo, hi), CompareConfig(enable_sequences=False))
+    assert np.array_equal(part.region_metrics[:hi - lo], gpu.region_metrics[lo:hi])
+    assert np.array_equal(part.status[:hi - lo], gpu.status[lo:hi])
+
+
 def test_merge_synthetic_vs_oracle(solver):
     ref, batch = synth.workload_merge(150_000, 400, n_sets=5, seed=38)
     solver.set_reference([ref])
