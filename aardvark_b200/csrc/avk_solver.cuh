@@ -158,6 +158,18 @@ struct RegionSolver {
         return true;
     }
 
+    // wait for the window load issued by begin_region (every issued load must be waited for exactly once: the
+    // mbarrier's parity is tracked in tma_phase)
+    __device__ __forceinline__ void drain_window() {
+        if (SMEM && tma_pending) {
+            const u32 ph = tma_phase;
+            tma_window_wait((u32)arena, ph);
+            __syncwarp();
+            if (lane_id() == 0) { tma_phase = ph ^ 1u; tma_pending = 0; }
+            __syncwarp();
+        }
+    }
+
     // per-lane partial validation of one variant list (same rules as the oracle's list_valid)
     __device__ __noinline__ bool validate_list(u64 v0, int n, int *sums) const {
         const DevBatch &b = *bp;
@@ -292,13 +304,7 @@ struct RegionSolver {
         off = (off + 15u) & ~15u;
         dyn = arena + off;
         dyn_bytes = arena_bytes - off;
-        if (SMEM && tma_pending) {
-            const u32 ph = tma_phase;
-            tma_window_wait((u32)arena, ph);
-            __syncwarp();
-            if (lane == 0) { tma_phase = ph ^ 1u; tma_pending = 0; }
-            __syncwarp();
-        }
+        drain_window();
         __syncwarp();
         return SOLVE_OK;
     }
@@ -1085,6 +1091,40 @@ struct RegionSolver {
         ST64(g, LD64(g) + a); ST64(g + 8, LD64(g + 8) + b2); ST64(g + 16, LD64(g + 16) + c); ST64(g + 24, LD64(g + 24) + d);
     }
 
+    // Merge shortcut: inputs i and j of cluster r carry the same variants (position, both alleles) with the same number
+    // of ALT copies each, no two of them overlap, and the search tree (2 orientations per heterozygous variant, both
+    // lists) cannot reach the branch quota.  Then optimize_sequences explores every orientation pair, the pair that
+    // assigns each query variant to its truth twin's haplotype spells identical sequences without a skipped variant,
+    // and the minimum cost is 0: is_exact_match() (query_optimizer.rs:96-98) holds without running the search.
+    __device__ __noinline__ bool merge_pair_identical(u64 r, u32 i, u32 j) {
+        const DevBatch &b = *bp;
+        const u32 K = b.n_inputs;
+        const u64 vi0 = b.var_off[r * K + i], vj0 = b.var_off[r * K + j];
+        const int ni = (int)(b.var_off[r * K + i + 1] - vi0), nj = (int)(b.var_off[r * K + j + 1] - vj0);
+        if (ni != nj) return false;
+        bool ok = true;
+        int hets = 0;
+#pragma unroll 1
+        for (int k = lane_id(); k < ni; k += 32) {
+            const u64 gi = vi0 + k, gj = vj0 + k;
+            const u32 l0 = b.l0[gi], l1 = b.l1[gi];
+            const int zi = b.zyg[gi], zj = b.zyg[gj];
+            const int ci = zi == AVK_ZYG_HOM_ALT ? 2 : (zi >= AVK_ZYG_UNPHASED_HET ? 1 : 0);
+            const int cj = zj == AVK_ZYG_HOM_ALT ? 2 : (zj >= AVK_ZYG_UNPHASED_HET ? 1 : 0);
+            ok = ok && b.pos[gi] == b.pos[gj] && l0 == b.l0[gj] && l1 == b.l1[gj] && l0 + l1 <= 64 && ci == cj && ci > 0;
+            if (k > 0) ok = ok && b.pos[gi] >= b.pos[gi - 1] + b.l0[gi - 1];
+            if (ok) {
+                const u8 *pa = b.pool + b.aoff[gi], *pb = b.pool + b.aoff[gj];
+#pragma unroll 1
+                for (u32 t = 0; t < l0 + l1; ++t) ok = ok && pa[t] == pb[t];
+            }
+            hets += ci == 1 ? 1 : 0;
+        }
+        ok = __all_sync(AVK_FULL, ok);
+        hets = __reduce_add_sync(AVK_FULL, hets);
+        return ok && hets <= 12 && (1 << (2 * hets)) <= mbf;
+    }
+
     __device__ int solve_compare(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out);
     __device__ int compare_prepare(u64 r, const avk_compare_cfg &cfg, bool want_metrics);
     __device__ int compare_search_to_blob(u64 r, const avk_compare_cfg &cfg, u8 *blob);
@@ -1436,7 +1476,7 @@ __device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, 
             delta += ((long long)b.l1[gv] - (long long)b.l0[gv]) * cnt;
         }
     }
-    if (__any_sync(AVK_FULL, unknown)) return AVK_ST_BAD_ZYGOSITY;
+    if (__any_sync(AVK_FULL, unknown)) { drain_window(); return AVK_ST_BAD_ZYGOSITY; }
     u32 match_row = ((u32)lane < K) ? (1u << lane) : 0;   // lane i holds match_sets[i] as a bit mask
     bool all_identical = true, no_conflict = true;
 #pragma unroll 1
@@ -1447,9 +1487,10 @@ __device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, 
             bool exact = false;
             const bool empty_i = b.var_off[r * K + i + 1] == b.var_off[r * K + i];
             const bool empty_j = b.var_off[r * K + j + 1] == b.var_off[r * K + j];
-            if (di == dj) {                                              // :135-143
+            if (di == dj && merge_pair_identical(r, i, j)) exact = true;
+            else if (di == dj) {                                         // :135-143
                 int rc = setup_pair(r, i, j, false);
-                if (rc) return rc;
+                if (rc) { drain_window(); return rc; }
                 rc = optimize(true);
                 if (rc) return rc;
                 if (n_res > 0) {
@@ -1467,6 +1508,7 @@ __device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, 
             }
         }
     }
+    drain_window();   // every pair may have taken the identical-lists shortcut
     const u32 maj = K / 2 + 1;                                            // :167
     const unsigned has = __ballot_sync(AVK_FULL, (u32)lane < K && (u32)__popc(match_row) >= maj);
     u32 first_maj = 0;
