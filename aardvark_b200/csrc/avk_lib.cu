@@ -242,16 +242,19 @@ __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const Dev
 }
 
 // ---- closed form for the commonest cluster shape ------------------------------------------------------------
-// One truth SNV and one query SNV at the same position with the same ALT base (!= the reference base) and the same
-// number of ALT copies: ~60 % of a small-variant WGS comparison.  What solve_compare_region computes for it follows
-// from the search itself (query_optimizer.rs:203-328): the orientation(s) in which both haplotypes spell identical
-// sequences finalise with cost 0 after at most four pops at the last depth (hence max_branch_factor >= 4), every
-// other orientation spells ref-vs-alt on some haplotype and costs more, so each equal-best result has ED 0, no skipped
-// variant and expected == observed == ALT copies for both records.  Metrics: gt/hap/weighted_hap TP on both sides
-// (grouped_metrics.rs:183-227), basepair X = Y = ED(ref, alt hap) = 1 per ALT haplotype, Z = 0
-// (waffle_solver.rs:639-648), record basepair 2 * copies * raw_allele_space (:455-522; needs raw >= 1, else the
-// general path reports the underflow).  Everything else -- including these shapes with the hidden exact shortcut or
-// the sequence bundle requested -- goes to the search kernels through `work_list`.
+// One truth and one query record that are the same variant -- same position, reference span, ALT bytes, (supported) type
+// label and number of ALT copies -- where the variant is a substitution that changes the base, or an anchored pure
+// insertion / deletion (first ALT base == the reference base): ~70 % of a small-variant WGS comparison.  What
+// solve_compare_region computes for it follows from the search itself (query_optimizer.rs:203-328): the orientation(s)
+// in which both haplotypes spell identical sequences finalise with cost 0 after at most four pops at the last depth
+// (hence max_branch_factor >= 4); every other orientation pairs the reference window with the ALT haplotype -- a
+// different string -- on some haplotype and costs more.  So each equal-best result has ED 0, no skipped variant and
+// expected == observed == ALT copies for both records.  Metrics: gt/hap/weighted_hap TP on both sides
+// (grouped_metrics.rs:183-227); basepair X = Y = ED(reference window, ALT haplotype) = 1 resp. the length difference
+// (closed form, see RegionSolver::build_hap_seq) per ALT haplotype, Z = 0 (waffle_solver.rs:639-648); record basepair
+// 2 * copies * raw_allele_space (:455-522; needs raw >= X, else the general path reports the underflow).  Everything
+// else -- including these shapes with the hidden exact shortcut or the sequence bundle requested -- goes to the search
+// kernels through `work_list`.
 __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, u64 n, u32 *work_list,
                                                         u32 *work_ctr) {
     const int lane = lane_id();
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
     for (u64 base = warp * 32; base < n; base += n_warps * 32) {
         const u64 r = base + lane;
         bool simple = false;
-        u32 copies = 0, gvT = 0, gvQ = 0, wT = 0, wQ = 0, rawT = 0, rawQ = 0;
+        u32 copies = 0, gvT = 0, gvQ = 0, wT = 0, wQ = 0, rawT = 0, rawQ = 0, edX = 0, vtype = 0;
         if (r < n && enabled) {
             const u8 *dig = b.digest + b.digest_off[r];
             const int4 h = *(const int4 *)dig;                         // status, N, nT, nQ
@@ -276,12 +279,22 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
                 const u32 zT = (t1.w >> 8) & 0xff, zQ = (q1.w >> 8) & 0xff;
                 const u32 cT = zT == AVK_ZYG_HOM_ALT ? 2u : (zT >= AVK_ZYG_UNPHASED_HET ? 1u : 0u);
                 const u32 cQ = zQ == AVK_ZYG_HOM_ALT ? 2u : (zQ >= AVK_ZYG_UNPHASED_HET ? 1u : 0u);
-                if ((t1.w & 0x100ffu) == (0x10000u | AVK_VT_SNV) && (q1.w & 0x100ffu) == AVK_VT_SNV && t0.x == q0.x &&
-                    t0.y == 1 && t0.z == 1 && q0.y == 1 && q0.z == 1 && cT != 0 && cT == cQ && t1.y >= 1 && q1.y >= 1) {
+                const u32 ty = t1.w & 0xffu;
+                // same record on both sides: position, reference span, ALT bytes, type label (a supported one), ALT copies
+                if ((t1.w & 0x10000u) && !(q1.w & 0x10000u) && ty == (q1.w & 0xffu) && ((supported >> ty) & 1u) && t0.x == q0.x &&
+                    t0.y == q0.y && t0.z == q0.z && (t0.y == 1 || t0.z == 1) && t0.y + t0.z <= 64 && cT != 0 && cT == cQ) {
                     const u8 *alle = dig + PH_SIZE + 2 * VI_SIZE;
-                    const u8 altT = alle[t0.w + 1], altQ = alle[q0.w + 1];
-                    simple = altT == altQ && altT != b.contig_ptr[c][t0.x];
-                    copies = cT; gvT = t1.z; gvQ = q1.z; wT = t1.x; wQ = q1.x; rawT = t1.y; rawQ = q1.y;
+                    const u8 *aT = alle + t0.w + t0.y, *aQ = alle + q0.w + q0.y;   // ALT alleles
+                    bool same = true;
+                    for (u32 k = 0; k < t0.z; ++k) same = same && aT[k] == aQ[k];
+                    const bool anchored = aT[0] == b.contig_ptr[c][t0.x];
+                    // ED(reference window, ALT haplotype): substitution that changes the base: 1; anchored pure
+                    // insertion / deletion: the length difference (RegionSolver::build_hap_seq, SD_CLOSED)
+                    u32 X = 0;
+                    if (t0.y == 1 && t0.z == 1) X = anchored ? 0u : 1u;
+                    else if (anchored) X = (t0.y == 1 ? t0.z : t0.y) - 1u;
+                    simple = same && X != 0 && t1.y >= X && q1.y >= X;
+                    copies = cT; gvT = t1.z; gvQ = q1.z; wT = t1.x; wQ = q1.x; rawT = t1.y; rawQ = q1.y; edX = X; vtype = ty;
                 }
             }
         }
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
         pos0 = __shfl_sync(AVK_FULL, pos0, 0);
         if (r < n && !simple) work_list[pos0 + __popc(rest & ((1u << lane) - 1))] = (u32)r;
         if (simple) {
-            out.status[r] = AVK_ST_OK; out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = (uint16_t)supported;
+            out.status[r] = AVK_ST_OK; out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = (uint16_t)supported;   // vtype is one of them
             out.vexp[gvT] = (u8)copies; out.vobs[gvT] = (u8)copies; out.vcls[gvT] = AVK_CLASS_TP;
             out.vexp[gvQ] = (u8)copies; out.vobs[gvQ] = (u8)copies; out.vcls[gvQ] = AVK_CLASS_TP;
         }
@@ -304,17 +317,19 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
             const u64 cp = __shfl_sync(AVK_FULL, copies, src);
             const u64 vwT = __shfl_sync(AVK_FULL, wT, src), vwQ = __shfl_sync(AVK_FULL, wQ, src);
             const u64 vrT = __shfl_sync(AVK_FULL, rawT, src), vrQ = __shfl_sync(AVK_FULL, rawQ, src);
+            const u64 vX = __shfl_sync(AVK_FULL, edX, src);
+            const int grow = 1 + (int)__shfl_sync(AVK_FULL, vtype, src);
             u64 *dst = out.region_metrics + (base + src) * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
 #pragma unroll 1
             for (int i = lane; i < AVK_N_GROUPS * AVK_N_METRICS; i += 32) {
                 const int g = i / AVK_N_METRICS, m = i - g * AVK_N_METRICS;
                 u64 v = 0;
-                if (g == 0 || g == 1 + AVK_VT_SNV) {
+                if (g == 0 || g == grow) {
                     if (m == AVK_M_GT || m == AVK_M_GT + 2) v = 1;
                     else if (m == AVK_M_HAP || m == AVK_M_HAP + 2) v = cp;
                     else if (m == AVK_M_WEIGHTED_HAP) v = cp * vwT;
                     else if (m == AVK_M_WEIGHTED_HAP + 2) v = cp * vwQ;
-                    else if (m == AVK_M_BASEPAIR || m == AVK_M_BASEPAIR + 2) v = 2 * cp;
+                    else if (m == AVK_M_BASEPAIR || m == AVK_M_BASEPAIR + 2) v = 2 * cp * vX;
                     else if (m == AVK_M_RECORD_BP) v = 2 * cp * vrT;
                     else if (m == AVK_M_RECORD_BP + 2) v = 2 * cp * vrQ;
                 }

@@ -193,7 +193,7 @@ def test_compare_single_snv_pairs_closed_form_vs_oracle(solver):
     regions, zero_raw = [], []
     rid = 0
     for zt, zq in itertools.product(zygs, zygs):
-        for shape in range(7):
+        for shape in range(13):
             p = 60 + 7 * (rid % 500)
             r0 = ref[p:p + 1]
             alts = [b for b in (b"A", b"C", b"G", b"T") if b != r0]
@@ -205,6 +205,15 @@ def test_compare_single_snv_pairs_closed_form_vs_oracle(solver):
             if shape == 4: qp = p + 1; q0 = ref[qp:qp + 1]; qa = [b for b in (b"A", b"C", b"G", b"T") if b != q0][0]
             if shape == 5: qt = VariantType.Indel  # odd label on a 1 -> 1 substitution
             if shape == 6: zero_raw.append(rid)
+            if shape >= 7:                          # indel pairs around the closed form for anchored pure indels
+                ins = bytes(synth.ACGT[rng.integers(0, 4, size=int(rng.integers(1, 9)))])
+                dl = int(rng.integers(2, 10))
+                if shape == 7: tt = qt = VariantType.Insertion; t0 = q0 = r0; ta = qa = r0 + ins
+                if shape == 8: tt = qt = VariantType.Deletion; t0 = q0 = ref[p:p + dl]; ta = qa = r0
+                if shape == 9: tt = qt = VariantType.Insertion; t0 = q0 = r0; ta = qa = alts[0] + ins      # anchor != reference
+                if shape == 10: tt = qt = VariantType.Insertion; t0 = q0 = r0; ta = r0 + ins; qa = r0 + ins[::-1] + b"A"
+                if shape == 11: tt = qt = VariantType.Indel; t0 = q0 = r0; ta = qa = r0 + ins              # odd but supported label
+                if shape == 12: tt = VariantType.Deletion; qt = VariantType.Indel; t0 = q0 = ref[p:p + dl]; ta = qa = r0
             regions.append(CompareRegion(rid, Coordinates("c", p - 50, p + 52), [Variant(0, tt, tp, t0, ta)], [zt],
                                          [Variant(0, qt, qp, q0, qa)], [zq]))
             rid += 1
