@@ -587,7 +587,7 @@ struct avk_ctx {
     DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, strat_off, strat_idx, strat_totals,
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx;
     // workspace
-    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     // resident batch
     bool have_batch = false;
     u64 n_regions = 0, n_variants = 0;
@@ -655,7 +655,8 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        for (auto &st : ctx->side) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi);
+        // side streams carry the kernel that should only fill SMs the main stream's kernel has left: lowest priority
+        for (auto &st : ctx->side) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (auto &e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -672,7 +673,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
@@ -898,7 +899,10 @@ static void launch_compare(avk_ctx *ctx, const DevBatch &db, const DevCompareOut
     // function attributes are set once per instantiation (the call may synchronise the device)
     static size_t configured = 0;
     if (configured < smem + 1) {
-        if (SMEM) cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+        if (SMEM) {
+            cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+            cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        }
         configured = 228 * 1024;
     }
     k_compare<SMEM, MIN_CTAS, MODE><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
@@ -939,7 +943,7 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
     const int INF = 0x7fffffff;
-    ENSURE(ctx->fail_a, 4 * n); ENSURE(ctx->fail_b, 4 * n); ENSURE(ctx->fail_c, 4 * n); ENSURE(ctx->fail_d, 4 * n); ENSURE(ctx->fail_h, 4 * n);
+    ENSURE(ctx->fail_a, 4 * n); ENSURE(ctx->fail_b, 4 * n); ENSURE(ctx->fail_c, 4 * n); ENSURE(ctx->fail_d, 4 * n); ENSURE(ctx->fail_h, 4 * n); ENSURE(ctx->fail_w, 4 * n);
     ENSURE(ctx->counters, 256);
     ENSURE(ctx->blobs, (size_t)n * RB_SIZE);
     u32 *ctrs = (u32 *)ctx->counters.p;
@@ -960,19 +964,33 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     const Stage SEARCH = {MODE_SEARCH, true, 3, 8192, sm * 3, 8}, SCORE = {MODE_SCORE, true, 4, 5120, sm * 4, 8};
     const Stage S1 = {MODE_FUSED, true, 1, 27648, sm, 8}, G0 = {MODE_FUSED, false, 1, 2LL << 20, sm, 8};
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
-    u32 *LW = (u32 *)ctx->fail_h.p;
+    u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p;
     simple(LW, ctrs + 12);                                                                        // closed-form clusters; the rest -> W
     {
         TierArgs a = args(LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr);
         launch(SEARCH, a, (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8), ctx->stream);
     }
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
-    launch(SCORE, args(LW, 12, 2, LA, 1, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->stream);   // overflows join A
-    CK(cudaEventRecord(ctx->tev[2], ctx->stream));
+    // The fused stage for the search kernel's rejects (list A) ends with a few warps that each finish one dense cluster
+    // alone.  It is launched first (main stream, one 216 KB CTA per SM); the score kernel follows on a side stream behind
+    // an event, so it becomes runnable a moment later: as the fused CTAs run out of work and retire, the block scheduler
+    // fills their SMs with score CTAs, and score runs in the shadow of that tail.  (All k_compare kernels ask for the
+    // maximum shared-memory carveout; kernels of different streams do not take over an SM otherwise: tools/overlap_probe.cu.)
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
     {
         TierArgs a = args(LA, 1, 4, LB, 5, S1.arena_bytes, nullptr);
         a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;   // dense clusters keep running here: cold nodes spill to HBM
         launch(S1, a, S1.ctas, ctx->stream);                                                      // A -> B   (8 warps x 27 KB per SM)
+    }
+    CK(cudaEventRecord(ctx->tev[2], ctx->stream));
+    launch(SCORE, args(LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);   // rejects -> A2
+    CK(cudaEventRecord(ctx->ev_join[0], ctx->side[0]));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+    {
+        TierArgs a = args(LA2, 15, 16, LB, 5, S1.arena_bytes, nullptr);
+        a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;
+        launch(S1, a, S1.ctas, ctx->stream);                                                      // A2 -> B  (score kernel's rejects, rare)
     }
     {
         TierArgs a = args(LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p);
@@ -980,7 +998,7 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
         launch(G0, a, G0.ctas, ctx->stream);                                                      // B -> D   (2 MB global arenas)
     }
     CK(cudaEventRecord(ctx->tev[3], ctx->stream));
-    ctx->launches += 5;
+    ctx->launches += 6;
     CK(cudaGetLastError());
     u32 h[16];
     CK(cudaMemcpyAsync(h, ctrs, 64, cudaMemcpyDeviceToHost, ctx->stream));
