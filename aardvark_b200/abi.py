@@ -65,6 +65,14 @@ class RegionBatch(C.Structure):
     ]
 
 
+class CallSets(C.Structure):
+    _fields_ = [
+        ("n_inputs", C.c_uint32),
+        ("input_off", _u64p),
+        ("variants", VariantTable),
+    ]
+
+
 class CompareCfg(C.Structure):
     _fields_ = [
         ("max_branch_factor", C.c_uint32),

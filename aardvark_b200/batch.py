@@ -142,6 +142,44 @@ class RegionBatch:
             self.a0_len[v0:v1], self.a1_len[v0:v1], self.allele_pool[p0:p1])
 
 
+class CallSets:
+    """K call sets of one contig as one variant table (avk_callsets): input k = variants [input_off[k], input_off[k+1]),
+    each in VCF order.  Records are (position, allele0, allele1, zygosity code, type code, raw_allele_space)."""
+
+    def __init__(self, inputs):
+        pos, vt, zy, raw, aoff, l0, l1 = [], [], [], [], [], [], []
+        pool = bytearray()
+        off = [0]
+        for lst in inputs:
+            for (p_, a0, a1, z, t, rw) in lst:
+                pos.append(p_); vt.append(t); zy.append(z); raw.append(rw)
+                aoff.append(len(pool)); l0.append(len(a0)); l1.append(len(a1))
+                pool.extend(a0); pool.extend(a1)
+            off.append(len(pos))
+        self.n_inputs = len(inputs)
+        self.input_off = np.asarray(off, dtype=np.uint64)
+        self.position = np.asarray(pos, dtype=np.uint32)
+        self.variant_type = np.asarray(vt, dtype=np.uint8)
+        self.zygosity = np.asarray(zy, dtype=np.uint8)
+        self.raw_allele_space = np.asarray(raw, dtype=np.uint32)
+        self.allele_off = np.asarray(aoff, dtype=np.uint32)
+        self.a0_len = np.asarray(l0, dtype=np.uint32)
+        self.a1_len = np.asarray(l1, dtype=np.uint32)
+        self.allele_pool = np.frombuffer(bytes(pool) or b"\0", dtype=np.uint8).copy()
+        self.pool_len = len(pool)
+
+    @property
+    def n_variants(self):
+        return int(self.position.size)
+
+    def to_c(self) -> abi.CallSets:
+        vt = abi.VariantTable(
+            self.n_variants, abi.ptr(self.position), abi.ptr(self.variant_type), abi.ptr(self.zygosity),
+            abi.ptr(self.raw_allele_space), abi.ptr(self.allele_off), abi.ptr(self.a0_len), abi.ptr(self.a1_len),
+            abi.ptr(self.allele_pool), self.pool_len)
+        return abi.CallSets(self.n_inputs, abi.ptr(self.input_off), vt)
+
+
 class CompareOutputs:
     """Caller-allocated arrays of an avk_compare_out."""
 

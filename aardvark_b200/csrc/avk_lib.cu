@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "avk_solver.cuh"
@@ -588,6 +589,7 @@ struct avk_ctx {
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx;
     // workspace
     DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    DevBuf rb[20];   // region builder temporaries
     // resident batch
     bool have_batch = false;
     u64 n_regions = 0, n_variants = 0;
@@ -676,6 +678,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
     for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -1172,6 +1175,169 @@ extern "C" int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch, co
     rc = download_compare(ctx, out, want_seq, seq_pool_len);
     if (rc != AVK_OK) return rc;
     return fetch_timings(ctx);
+}
+
+// ------------------------------------------------------------------------------------ region builder
+// src/parsing/region_generation.rs:352-469 as sorts, scans and gathers; see include/aardvark_b200.h.
+// A variant closes the open cluster iff its position reaches the running maximum of (pos + ref_len + flank) -- and the
+// maximum over ALL earlier variants equals the maximum inside the open cluster whenever that comparison matters (every
+// earlier cluster ended at or before the position that opened this one), so one exclusive max-scan gives the breaks.
+struct MaxOp { __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a > b ? a : b; } };
+
+__global__ void __launch_bounds__(256) k_rb_keys(u64 nv, const u32 *pos, const u32 *l0, u64 contig_len, u32 *key, u32 *idx) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    idx[i] = (u32)i;
+    key[i] = ((u64)pos[i] + l0[i] > contig_len) ? 0xffffffffu : pos[i];       // not fully contained: dropped (:551), sorted to the end
+}
+__global__ void __launch_bounds__(256) k_rb_vend(u64 nv, const u32 *key, const u32 *idx, const u32 *l0, u64 contig_len, u32 flank,
+                                                 u32 *vend, unsigned long long *n_valid) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    const bool valid = key[i] != 0xffffffffu;
+    vend[i] = valid ? (u32)min((u64)key[i] + l0[idx[i]] + flank, contig_len) : 0u;                 // :411-429
+    if (valid && (i + 1 == nv || key[i + 1] == 0xffffffffu)) *n_valid = i + 1;
+    if (i == 0 && !valid) *n_valid = 0;
+}
+__global__ void __launch_bounds__(256) k_rb_flags(u64 nv, const u32 *key, const u32 *pmax, u32 *flag) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    flag[i] = (key[i] != 0xffffffffu && key[i] >= pmax[i]) ? 1u : 0u;         // pos >= window_end opens a new cluster (:396-409)
+}
+// per sorted variant: cluster id, grouping key (cluster, input); per cluster: window and ids
+__global__ void __launch_bounds__(256) k_rb_clusters(u64 nvalid, const u32 *key, const u32 *idx, const u32 *cid1, const u32 *flag,
+                                                     const u32 *pmax, const u32 *vend, const u64 *input_off, u32 K, u32 flank, u32 contig,
+                                                     u64 first_region_id, u64 *key2, u64 *region_id, u32 *rcontig, u32 *start, u32 *end) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvalid) return;
+    const u32 c = cid1[i] - 1;                                                // inclusive sum of the break flags
+    u32 k = 0;
+    while (k + 1 < K && input_off[k + 1] <= idx[i]) ++k;
+    key2[i] = (u64)c * K + k;
+    if (flag[i]) { start[c] = key[i] > flank ? key[i] - flank : 0u; region_id[c] = first_region_id + c; rcontig[c] = contig; }
+    if (i + 1 == nvalid || flag[i + 1]) end[c] = max(pmax[i], vend[i]);      // running maximum at the cluster's last variant
+}
+__global__ void __launch_bounds__(256) k_rb_varoff(u64 n_seg, u64 nvalid, const u64 *key2_sorted, u64 *var_off) {
+    const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_seg) return;
+    u64 lo = 0, hi = nvalid;                                                  // first sorted variant with key2 >= s
+    while (lo < hi) { const u64 m = (lo + hi) >> 1; if (key2_sorted[m] < s) lo = m + 1; else hi = m; }
+    var_off[s] = lo;
+}
+__global__ void __launch_bounds__(256) k_rb_gather(u64 nvalid, const u32 *perm, const u32 *pos, const u8 *vt, const u8 *zy, const u32 *raw,
+                                                   const u32 *l0, const u32 *l1, u32 *opos, u8 *ovt, u8 *ozy, u32 *oraw, u32 *ol0, u32 *ol1, u32 *alen) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvalid) return;
+    const u32 j = perm[i];
+    opos[i] = pos[j]; ovt[i] = vt[j]; ozy[i] = zy[j]; oraw[i] = raw[j]; ol0[i] = l0[j]; ol1[i] = l1[j];
+    alen[i] = l0[j] + l1[j];
+}
+__global__ void __launch_bounds__(256) k_rb_alleles(u64 nvalid, const u32 *perm, const u32 *aoff_in, const u32 *alen, const u32 *aoff_out,
+                                                    const u8 *pool_in, u8 *pool_out) {
+    const int lane = lane_id();
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 i = warp; i < nvalid; i += n_warps) {
+        const u8 *src = pool_in + aoff_in[perm[i]];
+        u8 *dst = pool_out + aoff_out[i];
+        for (u32 t = lane; t < alen[i]; t += 32) dst[t] = src[t];
+    }
+}
+
+extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t contig, uint32_t flank, uint64_t first_region_id,
+                                 uint64_t *n_regions_out, uint64_t *n_variants_out) {
+    if (!ctx || !in || !n_regions_out || !n_variants_out || in->n_inputs == 0 || !in->input_off) return AVK_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (contig >= ctx->contig_lens.size()) { ctx->err = "avk_build_regions: unknown contig (call avk_set_reference first)"; return AVK_ERR_INVALID; }
+    const avk_variant_table &t = in->variants;
+    const u64 nv = t.n_variants, K = in->n_inputs, contig_len = ctx->contig_lens[contig];
+    if (in->input_off[K] != nv || nv >= 0xffffffffull || t.allele_pool_len >= 0xffffffffull) { ctx->err = "avk_build_regions: bad call-set table"; return AVK_ERR_INVALID; }
+    enum { T_POS, T_VT, T_ZY, T_RAW, T_AOFF, T_L0, T_L1, T_POOL, T_KEY, T_IDX, T_KEY_S, T_IDX_S, T_VEND, T_PMAX, T_FLAG, T_CID, T_KEY2, T_KEY2_S, T_PERM, T_MISC };
+    DevBuf *rb = ctx->rb;
+    UPLOAD(rb[T_POS], t.position, 4 * nv); UPLOAD(rb[T_VT], t.variant_type, nv); UPLOAD(rb[T_ZY], t.zygosity, nv);
+    UPLOAD(rb[T_RAW], t.raw_allele_space, 4 * nv); UPLOAD(rb[T_AOFF], t.allele_off, 4 * nv); UPLOAD(rb[T_L0], t.a0_len, 4 * nv);
+    UPLOAD(rb[T_L1], t.a1_len, 4 * nv); UPLOAD(rb[T_POOL], t.allele_pool, t.allele_pool_len);
+    for (int b : {T_KEY, T_IDX, T_KEY_S, T_IDX_S, T_VEND, T_PMAX, T_FLAG, T_CID, T_PERM}) ENSURE(rb[b], 4 * nv);
+    ENSURE(rb[T_KEY2], 8 * nv); ENSURE(rb[T_KEY2_S], 8 * nv);
+    ENSURE(rb[T_MISC], 8 * (K + 1) + 64);
+    u64 *d_input_off = (u64 *)rb[T_MISC].p;
+    unsigned long long *d_nvalid = (unsigned long long *)((u8 *)rb[T_MISC].p + 8 * (K + 1));
+    CK(cudaMemcpyAsync(d_input_off, in->input_off, 8 * (K + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_nvalid, 0, 8, ctx->stream));
+    u32 mx = 1;
+    u64 sum_alle = 0;
+    for (u64 i = 0; i < nv; ++i) { mx = std::max(mx, std::max(t.a0_len[i], t.a1_len[i])); sum_alle += (u64)t.a0_len[i] + t.a1_len[i]; }
+    if (sum_alle >= 0xffffffffull) { ctx->err = "avk_build_regions: allele bytes exceed 4 GiB"; return AVK_ERR_INVALID; }
+    ctx->have_batch = false;
+    *n_regions_out = 0; *n_variants_out = 0;
+    if (nv == 0) { ctx->n_regions = 0; ctx->n_variants = 0; ctx->n_inputs = (u32)K; ctx->max_allele = 1; ctx->pool_len = 0; ctx->have_batch = true; ENSURE(ctx->var_off, 8); CK(cudaMemsetAsync(ctx->var_off.p, 0, 8, ctx->stream)); return AVK_OK; }
+    const unsigned g = (unsigned)((nv + 255) / 256);
+    u32 *key = (u32 *)rb[T_KEY].p, *idx = (u32 *)rb[T_IDX].p, *key_s = (u32 *)rb[T_KEY_S].p, *idx_s = (u32 *)rb[T_IDX_S].p;
+    u32 *vend = (u32 *)rb[T_VEND].p, *pmax = (u32 *)rb[T_PMAX].p, *flag = (u32 *)rb[T_FLAG].p, *cid = (u32 *)rb[T_CID].p, *perm = (u32 *)rb[T_PERM].p;
+    u64 *key2 = (u64 *)rb[T_KEY2].p, *key2_s = (u64 *)rb[T_KEY2_S].p;
+    const u32 *pos = (const u32 *)rb[T_POS].p, *l0 = (const u32 *)rb[T_L0].p;
+    size_t tmp = 0, need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, key, key_s, idx, idx_s, (int)nv, 0, 32, ctx->stream); tmp = std::max(tmp, need);
+    cub::DeviceRadixSort::SortPairs(nullptr, need, key2, key2_s, idx_s, perm, (int)nv, 0, 64, ctx->stream); tmp = std::max(tmp, need);
+    cub::DeviceScan::ExclusiveScan(nullptr, need, vend, pmax, MaxOp(), 0u, (int)nv, ctx->stream); tmp = std::max(tmp, need);
+    cub::DeviceScan::InclusiveSum(nullptr, need, flag, cid, (int)nv, ctx->stream); tmp = std::max(tmp, need);
+    ENSURE(ctx->scan_tmp, tmp);
+    k_rb_keys<<<g, 256, 0, ctx->stream>>>(nv, pos, l0, contig_len, key, idx);
+    need = tmp; cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, need, key, key_s, idx, idx_s, (int)nv, 0, 32, ctx->stream);   // stable: ties keep input then list order (:352-373)
+    k_rb_vend<<<g, 256, 0, ctx->stream>>>(nv, key_s, idx_s, l0, contig_len, flank, vend, d_nvalid);
+    need = tmp; cub::DeviceScan::ExclusiveScan(ctx->scan_tmp.p, need, vend, pmax, MaxOp(), 0u, (int)nv, ctx->stream);
+    k_rb_flags<<<g, 256, 0, ctx->stream>>>(nv, key_s, pmax, flag);
+    need = tmp; cub::DeviceScan::InclusiveSum(ctx->scan_tmp.p, need, flag, cid, (int)nv, ctx->stream);
+    unsigned long long nvalid = 0;
+    CK(cudaMemcpyAsync(&nvalid, d_nvalid, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u32 n_reg = 0;
+    if (nvalid) CK(cudaMemcpy(&n_reg, cid + (nvalid - 1), 4, cudaMemcpyDeviceToHost));
+    const u64 n = n_reg;
+    ENSURE(ctx->region_id, 8 * n); ENSURE(ctx->contig, 4 * n); ENSURE(ctx->start, 4 * n); ENSURE(ctx->end, 4 * n);
+    ENSURE(ctx->var_off, 8 * (n * K + 1));
+    ENSURE(ctx->pos, 4 * nvalid); ENSURE(ctx->vtype, nvalid); ENSURE(ctx->zyg, nvalid); ENSURE(ctx->raw, 4 * nvalid);
+    ENSURE(ctx->aoff, 4 * nvalid); ENSURE(ctx->l0, 4 * nvalid); ENSURE(ctx->l1, 4 * nvalid); ENSURE(ctx->pool, sum_alle + 16);
+    ENSURE(ctx->alt_ed, 4 * nvalid);
+    if (nvalid) {
+        const unsigned gv = (unsigned)((nvalid + 255) / 256);
+        k_rb_clusters<<<gv, 256, 0, ctx->stream>>>(nvalid, key_s, idx_s, cid, flag, pmax, vend, d_input_off, (u32)K, flank, contig, first_region_id,
+                                                   key2, (u64 *)ctx->region_id.p, (u32 *)ctx->contig.p, (u32 *)ctx->start.p, (u32 *)ctx->end.p);
+        need = tmp; cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, need, key2, key2_s, idx_s, perm, (int)nvalid, 0, 64, ctx->stream);   // stable regroup: (cluster, input)
+        k_rb_varoff<<<(unsigned)((n * K + 1 + 255) / 256), 256, 0, ctx->stream>>>(n * K, nvalid, key2_s, (u64 *)ctx->var_off.p);
+        u32 *alen = vend;   // reuse
+        k_rb_gather<<<gv, 256, 0, ctx->stream>>>(nvalid, perm, pos, (const u8 *)rb[T_VT].p, (const u8 *)rb[T_ZY].p, (const u32 *)rb[T_RAW].p, l0,
+                                                 (const u32 *)rb[T_L1].p, (u32 *)ctx->pos.p, (u8 *)ctx->vtype.p, (u8 *)ctx->zyg.p, (u32 *)ctx->raw.p,
+                                                 (u32 *)ctx->l0.p, (u32 *)ctx->l1.p, alen);
+        need = tmp; cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, need, alen, (u32 *)ctx->aoff.p, (int)nvalid, ctx->stream);
+        k_rb_alleles<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(nvalid, perm, (const u32 *)rb[T_AOFF].p, alen, (const u32 *)ctx->aoff.p,
+                                                                 (const u8 *)rb[T_POOL].p, (u8 *)ctx->pool.p);
+        ctx->launches += 12;
+    } else {
+        CK(cudaMemsetAsync(ctx->var_off.p, 0, 8, ctx->stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_regions = n; ctx->n_variants = nvalid; ctx->n_inputs = (u32)K; ctx->max_allele = mx; ctx->pool_len = sum_alle;
+    ctx->have_batch = true;
+    *n_regions_out = n; *n_variants_out = nvalid;
+    return AVK_OK;
+}
+
+extern "C" int avk_regions_download(avk_ctx *ctx, avk_region_batch *out) {
+    if (!ctx || !out) return AVK_ERR_INVALID;
+    if (!ctx->have_batch) { ctx->err = "avk_regions_download: no resident batch"; return AVK_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const u64 n = ctx->n_regions, nv = ctx->n_variants, K = ctx->n_inputs;
+    avk_variant_table &t = out->variants;
+#define RBDL(dst, buf, bytes) do { if ((bytes) && (dst)) CK(cudaMemcpyAsync((void *)(dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream)); } while (0)
+    RBDL(out->region_id, ctx->region_id, 8 * n); RBDL(out->contig, ctx->contig, 4 * n); RBDL(out->start, ctx->start, 4 * n); RBDL(out->end, ctx->end, 4 * n);
+    RBDL(out->var_off, ctx->var_off, 8 * (n * K + 1));
+    RBDL(t.position, ctx->pos, 4 * nv); RBDL(t.variant_type, ctx->vtype, nv); RBDL(t.zygosity, ctx->zyg, nv); RBDL(t.raw_allele_space, ctx->raw, 4 * nv);
+    RBDL(t.allele_off, ctx->aoff, 4 * nv); RBDL(t.a0_len, ctx->l0, 4 * nv); RBDL(t.a1_len, ctx->l1, 4 * nv); RBDL(t.allele_pool, ctx->pool, ctx->pool_len);
+#undef RBDL
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->n_regions = n; out->n_inputs = (uint32_t)K; t.n_variants = nv; t.allele_pool_len = ctx->pool_len;
+    return AVK_OK;
 }
 
 extern "C" int avk_compare_upload(avk_ctx *ctx, const avk_region_batch *batch) {

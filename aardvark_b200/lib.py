@@ -72,6 +72,8 @@ def load():
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint32)]
     lib.avk_compare_seq_offsets.argtypes = [C.POINTER(abi.RegionBatch), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.avk_build_regions.argtypes = [vp, C.POINTER(abi.CallSets), C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.avk_regions_download.argtypes = [vp, C.POINTER(abi.RegionBatch)]
     lib.avk_compare_upload.argtypes = [vp, C.POINTER(abi.RegionBatch)]
     lib.avk_compare_run_resident.argtypes = [vp, C.POINTER(abi.CompareCfg)]
     lib.avk_compare_download.argtypes = [vp, C.POINTER(abi.CompareOut)]
@@ -85,7 +87,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "avk_create", "avk_destroy", "avk_last_error", "avk_set_reference", "avk_compare_batch", "avk_merge_batch",
     "avk_wfa_ed_batch", "avk_compare_seq_offsets", "avk_compare_upload", "avk_compare_run_resident",
-    "avk_compare_download", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak", "avk_last_tier_overflow", "avk_last_tier_ms",
+    "avk_compare_download", "avk_build_regions", "avk_regions_download", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak", "avk_last_tier_overflow", "avk_last_tier_ms",
 ]
 
 
@@ -173,6 +175,29 @@ class Solver:
         self._check(self._lib.avk_wfa_ed_batch(self._ctx, len(a_off), abi.ptr(pool_a), len(pool), abi.ptr(ao), abi.ptr(al),
                                                 abi.ptr(bo), abi.ptr(bl), abi.ptr(ed)), "avk_wfa_ed_batch")
         return ed[:len(a_off)]
+
+    # -- region builder on the device ------------------------------------------
+    def build_regions(self, callsets, contig: int, flank: int, first_region_id: int = 0, download: bool = True):
+        """region_generation.rs:352-469 on the device for one contig: clusters K call sets (batch.CallSets) into a
+        batch that stays resident (run_resident() can follow).  Returns the RegionBatch (or (n_regions, n_variants)
+        when download is False)."""
+        import numpy as np
+        cs = callsets.to_c()
+        n, nv = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.avk_build_regions(self._ctx, C.byref(cs), contig, flank, first_region_id, C.byref(n), C.byref(nv)),
+                    "avk_build_regions")
+        n, nv = int(n.value), int(nv.value)
+        if not download:
+            return n, nv
+        k = callsets.n_inputs
+        b = RegionBatch(k, np.zeros(n, np.uint64), np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32),
+                        np.zeros(n * k + 1, np.uint64), np.zeros(nv, np.uint32), np.zeros(nv, np.uint8), np.zeros(nv, np.uint8),
+                        np.zeros(nv, np.uint32), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32),
+                        np.zeros(max(callsets.pool_len, 1), np.uint8))
+        cb = b.to_c()
+        self._check(self._lib.avk_regions_download(self._ctx, C.byref(cb)), "avk_regions_download")
+        b.allele_pool = b.allele_pool[:max(int(cb.variants.allele_pool_len), 1)]
+        return b
 
     # -- resident mode (bench: inputs already in HBM) --------------------------------------
     def upload(self, batch: RegionBatch):

@@ -352,13 +352,19 @@ def cluster_regions(inputs: Sequence[Sequence[Rec]], contig_len: int, flank: int
 CHR20_LEN = 64_444_167
 
 
-def workload_compare(contig_len: int, params: SynthParams, seed: int):
-    """(reference contig as uint8 array, compare RegionBatch with n_inputs == 2)."""
+def callsets_compare(contig_len: int, params: SynthParams, seed: int):
+    """(reference contig, [truth records, query records]): the call sets before clustering."""
     rng = np.random.default_rng(seed)
     ref = random_reference(contig_len, rng)
     truth = gen_truth(ref, params, rng)
     query = derive_query(ref, truth, params, rng)
-    return ref, cluster_regions([truth, query], contig_len, params.flank)
+    return ref, [truth, query]
+
+
+def workload_compare(contig_len: int, params: SynthParams, seed: int):
+    """(reference contig as uint8 array, compare RegionBatch with n_inputs == 2)."""
+    ref, inputs = callsets_compare(contig_len, params, seed)
+    return ref, cluster_regions(inputs, contig_len, params.flank)
 
 
 def workload_chr20(scale: float = 1.0, seed: int = 20):
@@ -379,10 +385,17 @@ def workload_sv(scale: float = 1.0, seed: int = 4):
 def workload_merge(contig_len: int, n_variants: int, n_sets: int = 5, seed: int = 38,
                    err_scales=(0.25, 0.5, 0.5, 1.0, 1.5), dropout: float = 0.05):
     """BASELINE.json configs[4]: K call sets derived independently from one truth."""
+    ref, sets, flank = callsets_merge(contig_len, n_variants, n_sets, seed, err_scales, dropout)
+    return ref, cluster_regions(sets, contig_len, flank)
+
+
+def callsets_merge(contig_len: int, n_variants: int, n_sets: int = 5, seed: int = 38,
+                   err_scales=(0.25, 0.5, 0.5, 1.0, 1.5), dropout: float = 0.05):
+    """(reference contig, K call sets, flank): the merge inputs before clustering."""
     rng = np.random.default_rng(seed)
     ref = random_reference(contig_len, rng)
     p = SynthParams(n_variants=n_variants)
     truth = gen_truth(ref, p, rng)
     sets = [derive_query(ref, truth, p, rng, err_scale=err_scales[k % len(err_scales)], dropout_blocks=dropout)
             for k in range(n_sets)]
-    return ref, cluster_regions(sets, contig_len, p.flank)
+    return ref, sets, p.flank

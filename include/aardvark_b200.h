@@ -264,6 +264,24 @@ int avk_compare_seq_offsets(const avk_region_batch *batch, uint64_t *seq_off, ui
 
 /* Device-resident variants used by bench.py (`value`, inputs already in HBM):
  * upload once, run many times, download once. */
+/* ---- region builder: src/parsing/region_generation.rs:352-469 for ONE contig and one BED interval
+ * spanning it.  K call sets in one variant table, input k = variants [input_off[k], input_off[k+1]), each range sorted
+ * by position (VCF order).  Variants not fully inside the contig are dropped (:551); all inputs are concatenated in
+ * input order and stable-sorted by position (:352-373); a variant with pos >= window_end closes the cluster, where
+ * window_start = first pos - flank (saturating) and window_end = max(pos + ref_len + flank) clipped to the contig
+ * (:396-433).  The batch is built ON THE DEVICE and stays resident exactly as after avk_compare_upload (region_id =
+ * first_region_id + running index, n_inputs = K), so avk_compare_run_resident can follow without a host round trip;
+ * avk_regions_download copies it out (caller-allocated arrays sized from *n_regions / *n_variants; allele pool
+ * capacity >= the input pool length). */
+typedef struct {
+    uint32_t n_inputs;
+    const uint64_t *input_off;   /* [n_inputs + 1] */
+    avk_variant_table variants;
+} avk_callsets;
+int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t contig, uint32_t flank, uint64_t first_region_id,
+                      uint64_t *n_regions, uint64_t *n_variants);
+int avk_regions_download(avk_ctx *ctx, avk_region_batch *out);
+
 int avk_compare_upload(avk_ctx *ctx, const avk_region_batch *batch);
 int avk_compare_run_resident(avk_ctx *ctx, const avk_compare_cfg *cfg);
 int avk_compare_download(avk_ctx *ctx, avk_compare_out *out);
@@ -288,6 +306,8 @@ int orc_compare_batch(const avk_region_batch *batch, const uint8_t *const *conti
                       const uint64_t *contig_lens, uint32_t n_contigs,
                       const avk_compare_cfg *cfg, avk_compare_out *out,
                       int n_threads, avk_work_counters *work);
+int orc_build_regions(const avk_callsets *in, uint64_t contig_len, uint32_t contig, uint32_t flank, uint64_t first_region_id,
+                      avk_region_batch *out);
 int orc_merge_batch(const avk_region_batch *batch, const uint8_t *const *contigs,
                     const uint64_t *contig_lens, uint32_t n_contigs,
                     const avk_merge_cfg *cfg, avk_merge_out *out,

@@ -1258,6 +1258,61 @@ int64_t orc_variant_delta_length(const avk_region_batch *b, uint32_t k) {
     return variant_delta_length(v, z, st);
 }
 
+// ---------------------------------------------------------------------------
+// Region builder -- src/parsing/region_generation.rs:352-469 for one contig and one BED interval spanning it
+// (SURVEY 8f N1).  The reference has no tests for this function (region_generation.rs:814-821): parity unpinned;
+// it is pinned here against the generator's host builder (aardvark_b200/synth.py::cluster_regions) instead.
+// `out` arrays are caller-allocated with room for every input variant; returns 0 and fills out->n_regions etc.
+// ---------------------------------------------------------------------------
+int orc_build_regions(const avk_callsets *in, uint64_t contig_len, uint32_t contig, uint32_t flank, uint64_t first_region_id,
+                      avk_region_batch *out) {
+    const avk_variant_table &t = in->variants;
+    const uint32_t K = in->n_inputs;
+    std::vector<uint32_t> order;                                  // all inputs concatenated in input order (:352-366)
+    order.reserve(t.n_variants);
+    for (uint64_t i = 0; i < t.n_variants; ++i)
+        if ((uint64_t)t.position[i] + t.a0_len[i] <= contig_len) order.push_back((uint32_t)i);   // fully contained (:551)
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return t.position[a] < t.position[b]; });   // :367-373
+    std::vector<uint32_t> input_of(t.n_variants);
+    for (uint32_t k = 0; k < K; ++k) for (uint64_t i = in->input_off[k]; i < in->input_off[k + 1]; ++i) input_of[i] = k;
+    avk_variant_table &o = const_cast<avk_variant_table &>(out->variants);
+    uint64_t n = 0, nv = 0, pool = 0;
+    uint64_t *region_id = const_cast<uint64_t *>(out->region_id), *var_off = const_cast<uint64_t *>(out->var_off);
+    uint32_t *rc = const_cast<uint32_t *>(out->contig), *rs = const_cast<uint32_t *>(out->start), *re = const_cast<uint32_t *>(out->end);
+    std::vector<std::vector<uint32_t>> cur(K);
+    bool open = false;
+    uint64_t w_start = 0, w_end = 0;
+    var_off[0] = 0;
+    auto flush = [&]() {                                          // :403-409, :459-466
+        region_id[n] = first_region_id + n; rc[n] = contig; rs[n] = (uint32_t)w_start; re[n] = (uint32_t)w_end;
+        for (uint32_t k = 0; k < K; ++k) {
+            for (uint32_t i : cur[k]) {
+                const_cast<uint32_t *>(o.position)[nv] = t.position[i]; const_cast<uint8_t *>(o.variant_type)[nv] = t.variant_type[i];
+                const_cast<uint8_t *>(o.zygosity)[nv] = t.zygosity[i]; const_cast<uint32_t *>(o.raw_allele_space)[nv] = t.raw_allele_space[i];
+                const_cast<uint32_t *>(o.allele_off)[nv] = (uint32_t)pool; const_cast<uint32_t *>(o.a0_len)[nv] = t.a0_len[i];
+                const_cast<uint32_t *>(o.a1_len)[nv] = t.a1_len[i];
+                std::memcpy(const_cast<uint8_t *>(o.allele_pool) + pool, t.allele_pool + t.allele_off[i], (size_t)t.a0_len[i] + t.a1_len[i]);
+                pool += (uint64_t)t.a0_len[i] + t.a1_len[i];
+                nv += 1;
+            }
+            var_off[n * K + k + 1] = nv;
+            cur[k].clear();
+        }
+        n += 1;
+    };
+    for (uint32_t i : order) {
+        const uint64_t p = t.position[i];
+        if (open && p >= w_end) { flush(); open = false; }        // :396-409
+        const uint64_t vend = std::min<uint64_t>(p + t.a0_len[i] + flank, contig_len);   // :411-429
+        if (!open) { w_start = p > flank ? p - flank : 0; w_end = vend; open = true; }
+        else w_end = std::max(w_end, vend);
+        cur[input_of[i]].push_back(i);
+    }
+    if (open) flush();                                            // :449-469
+    out->n_regions = n; out->n_inputs = K; o.n_variants = nv; o.allele_pool_len = pool;
+    return 0;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -247,3 +247,22 @@ def variant_delta_length(batch: RegionBatch, k=0):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def build_regions(callsets, contig_len: int, flank: int, contig: int = 0, first_region_id: int = 0) -> RegionBatch:
+    """Region builder restatement (region_generation.rs:352-469) -> RegionBatch."""
+    nv, k = callsets.n_variants, callsets.n_inputs
+    b = RegionBatch(k, np.zeros(nv, np.uint64), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32),
+                    np.zeros(nv * k + 1, np.uint64), np.zeros(nv, np.uint32), np.zeros(nv, np.uint8), np.zeros(nv, np.uint8),
+                    np.zeros(nv, np.uint32), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32),
+                    np.zeros(max(callsets.pool_len, 1), np.uint8))
+    cs, cb = callsets.to_c(), b.to_c()
+    fn = lib().orc_build_regions
+    fn.argtypes = [C.POINTER(abi.CallSets), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(abi.RegionBatch)]
+    rc = fn(C.byref(cs), contig_len, contig, flank, first_region_id, C.byref(cb))
+    if rc != 0:
+        raise RuntimeError(f"orc_build_regions failed: {rc}")
+    n, nvo = int(cb.n_regions), int(cb.variants.n_variants)
+    return RegionBatch(k, b.region_id[:n], b.contig[:n], b.start[:n], b.end[:n], b.var_off[:n * k + 1], b.position[:nvo],
+                       b.variant_type[:nvo], b.zygosity[:nvo], b.raw_allele_space[:nvo], b.allele_off[:nvo], b.a0_len[:nvo],
+                       b.a1_len[:nvo], b.allele_pool[:max(int(cb.variants.allele_pool_len), 1)])

@@ -248,6 +248,48 @@ def test_compare_multi_contig_vs_oracle(solver):
     assert np.array_equal(part.status[:hi - lo], gpu.status[lo:hi])
 
 
+def _same_batch(a: RegionBatch, b: RegionBatch):
+    for f in ("region_id", "contig", "start", "end", "var_off", "position", "variant_type", "zygosity", "raw_allele_space",
+              "allele_off", "a0_len", "a1_len"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    n = int(a.a0_len.sum() + a.a1_len.sum())
+    assert np.array_equal(a.allele_pool[:n], b.allele_pool[:n])
+    assert a.n_inputs == b.n_inputs
+
+
+def test_build_regions_vs_host_builder(solver):
+    """Device region builder (region_generation.rs:352-469) against the host builder the generator uses: compare and
+    merge call sets, flanks 0 / 50 / 1000, ties across inputs, an empty input, variants reaching past the contig end;
+    then the batch is solved where it was built (no upload) and must equal the uploaded host-built batch."""
+    from aardvark_b200.batch import CallSets
+    ref, inputs = synth.callsets_compare(400_000, synth.SynthParams(n_variants=900), seed=71)
+    solver.set_reference([ref])
+    for flank in (0, 50, 1000):
+        host = synth.cluster_regions(inputs, len(ref), flank)
+        dev = solver.build_regions(CallSets(inputs), 0, flank)
+        _same_batch(dev, host)
+    host = synth.cluster_regions(inputs, len(ref), 50)
+    solver.build_regions(CallSets(inputs), 0, 50, download=False)
+    solver.run_resident(CompareConfig(enable_sequences=False))
+    built = solver.download(CompareOutputs(host))
+    assert built.diff(solver.compare_batch(host, CompareConfig(enable_sequences=False))) == []
+    # K = 5 call sets with dropout (merge inputs), first_region_id offset
+    ref5, sets, flank5 = synth.callsets_merge(200_000, 500, n_sets=5, seed=72)
+    solver.set_reference([ref5])
+    host = synth.cluster_regions(sets, len(ref5), flank5, first_region_id=1000)
+    _same_batch(solver.build_regions(CallSets(sets), 0, flank5, first_region_id=1000), host)
+    # hand-made corner cases on a short contig
+    small = bytes(synth.ACGT[np.random.default_rng(5).integers(0, 4, size=600)])
+    solver.set_reference([small], ["s"])
+    rec = lambda p, a0, a1: synth.make_rec(p, a0, a1, abi.ZYG_HOM_ALT)
+    A = [rec(10, small[10:11], b"T" if small[10:11] != b"T" else b"G"), rec(10, small[10:11], b"AAAC"), rec(300, small[300:303], small[300:301]),
+         rec(598, small[598:600], b"A"), rec(599, small[599:600] + b"A", b"C")]          # the last one reaches past the end: dropped
+    B = [rec(10, small[10:11], b"C" if small[10:11] != b"C" else b"G"), rec(61, small[61:62], b"A" if small[61:62] != b"A" else b"C"),
+         rec(352, small[352:353], b"T" if small[352:353] != b"T" else b"C")]
+    for sets3, flank in (([A, B], 50), ([A, [], B], 50), ([[], []], 50), ([B, A], 0), ([A, B], 5000)):
+        _same_batch(solver.build_regions(CallSets(sets3), 0, flank), synth.cluster_regions(sets3, len(small), flank))
+
+
 def test_merge_synthetic_vs_oracle(solver):
     ref, batch = synth.workload_merge(150_000, 400, n_sets=5, seed=38)
     solver.set_reference([ref])

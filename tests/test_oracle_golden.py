@@ -377,3 +377,32 @@ def test_variant_length_delta():  # src/merge_solver.rs:350-370
     for i, d in enumerate((0, -7, 4)):
         assert orc.variant_delta_length(_hb(0, 40, vs[i:i + 1], zs[i:i + 1])) == d
     assert orc.variant_delta_length(_hb(0, 40, vs, zs)) == -3
+
+
+def test_region_builder_oracle_matches_host_builder():
+    """the reference has no tests for its region builder (parity unpinned); the C++ restatement is
+    pinned against the generator's host builder on compare and merge call sets and on hand-made corner cases."""
+    import numpy as np
+    from aardvark_b200 import abi, synth
+    from aardvark_b200.batch import CallSets
+
+    def same(a, b):
+        for f in ("region_id", "contig", "start", "end", "var_off", "position", "variant_type", "zygosity", "raw_allele_space",
+                  "allele_off", "a0_len", "a1_len"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+        n = int(a.a0_len.sum() + a.a1_len.sum())
+        assert np.array_equal(a.allele_pool[:n], b.allele_pool[:n])
+
+    ref, inputs = synth.callsets_compare(300_000, synth.SynthParams(n_variants=700), seed=81)
+    for flank in (0, 50, 1000):
+        same(orc.build_regions(CallSets(inputs), len(ref), flank), synth.cluster_regions(inputs, len(ref), flank))
+    ref5, sets, flank5 = synth.callsets_merge(150_000, 400, n_sets=5, seed=82)
+    same(orc.build_regions(CallSets(sets), len(ref5), flank5, first_region_id=7),
+         synth.cluster_regions(sets, len(ref5), flank5, first_region_id=7))
+    small = bytes(synth.ACGT[np.random.default_rng(5).integers(0, 4, size=600)])
+    rec = lambda p, a0, a1: synth.make_rec(p, a0, a1, abi.ZYG_HOM_ALT)
+    A = [rec(10, small[10:11], b"TT"), rec(10, small[10:11], b"AAAC"), rec(300, small[300:303], small[300:301]),
+         rec(598, small[598:600], b"A"), rec(599, small[599:600] + b"A", b"C")]
+    B = [rec(10, small[10:11], b"CC"), rec(61, small[61:62], b"AG"), rec(352, small[352:353], b"TG")]
+    for sets3, flank in (([A, B], 50), ([A, [], B], 50), ([[], []], 50), ([B, A], 0), ([A, B], 5000)):
+        same(orc.build_regions(CallSets(sets3), len(small), flank), synth.cluster_regions(sets3, len(small), flank))
