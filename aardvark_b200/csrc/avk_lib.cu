@@ -346,6 +346,11 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
 struct TierArgs {
     const u32 *work_list;
     const u32 *n_work_ptr;
+    const u32 *work_list2;   // optional second list, consumed after the first (length *n_work_ptr2)
+    const u32 *n_work_ptr2;
+    u32 *fail_list2;         // optional: rejected clusters with >= dense_n variants go here instead of fail_list
+    u32 *fail_ctr2;
+    int dense_n;
     u32 n_work;
     u32 *work_ctr;
     u32 *fail_ctr;
@@ -359,9 +364,6 @@ struct TierArgs {
     u8 *spill_base;        // shared-memory stages: per-warp node spill area in global memory (may be NULL)
     u32 spill_bytes;       // per warp
     int n_lo, n_hi;        // stages that scan all regions only take clusters with n_lo <= #variants <= n_hi
-    u32 *heavy_list;       // optional: clusters whose FIRST partition already needs more than heavy_bytes go here
-    u32 *heavy_ctr;
-    u32 heavy_bytes;
 };
 
 enum { MODE_FUSED = 0, MODE_SEARCH = 1, MODE_SCORE = 2, MODE_COOP = 3 };
@@ -407,17 +409,14 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompar
     __shared__ RegionSolver<SMEM> sol[8];
     const int lane = lane_id();
     RegionSolver<SMEM> &s = init_solver<SMEM>(b, t, sb, sol);
-    const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
+    const u32 n1 = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
+    const u32 n_work = n1 + (t.n_work_ptr2 ? *t.n_work_ptr2 : 0u);
     for (;;) {
         u32 idx = 0;
         if (lane == 0) idx = atomicAdd(t.work_ctr, 1u);
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
-        const u64 r = t.work_list ? t.work_list[idx] : idx;
-        if (!t.work_list) {   // self-selection by cluster size: the size classes run concurrently on separate streams
-            const int nvar = (int)(sb.var_off[r * 2 + 2] - sb.var_off[r * 2]);
-            if (nvar < t.n_lo || nvar > t.n_hi) continue;
-        }
+        const u64 r = t.work_list ? (idx < n1 ? t.work_list[idx] : t.work_list2[idx - n1]) : idx;
         u8 *blob = t.blobs + r * (u64)RB_SIZE;
         int rc;
         if (MODE == MODE_SEARCH) {
@@ -435,7 +434,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompar
         if (rc == SOLVE_WORKSPACE) {
             if (!t.last_tier) {
                 if (lane == 0) {
-                    if (t.heavy_list && s.last_need > t.heavy_bytes) t.heavy_list[atomicAdd(t.heavy_ctr, 1u)] = (u32)r;
+                    if (t.fail_list2 && s.N >= t.dense_n) t.fail_list2[atomicAdd(t.fail_ctr2, 1u)] = (u32)r;   // the long searches: started first
                     else t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
                 }
                 continue;
@@ -588,7 +587,7 @@ struct avk_ctx {
     DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, strat_off, strat_idx, strat_totals,
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx;
     // workspace
-    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, fail_x, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     DevBuf rb[20];   // region builder temporaries
     // resident batch
     bool have_batch = false;
@@ -675,7 +674,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
@@ -829,7 +828,7 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
             for (int k = 0; k < 2; ++k) { CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); }
             joined = true;
         }
-        TierArgs a;
+        TierArgs a = {};
         a.work_list = st.in_list < 0 ? nullptr : fail_lists[st.in_list];
         a.n_work_ptr = st.in_list < 0 ? nullptr : ctrs + st.in_ctr;
         a.n_work = (u32)n;
@@ -843,7 +842,6 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
         a.blobs = (u8 *)ctx->blobs.p;
         a.spill_base = nullptr; a.spill_bytes = 0;
         a.n_lo = st.n_lo; a.n_hi = st.n_hi;
-        a.heavy_list = nullptr; a.heavy_ctr = nullptr; a.heavy_bytes = 0;
         int ctas = st.ctas;
         if (st.in_list < 0) ctas = (int)std::min<u64>((u64)ctas, (n + st.warps - 1) / st.warps);
         launch(st, a, ctas, strm);
@@ -872,7 +870,7 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
     for (int t = 0; t < 2 && n_work > 0; ++t) {
         ENSURE(ctx->arena, (size_t)big[t].ctas * big[t].warps * (size_t)big[t].arena_bytes);
         CK(cudaMemsetAsync(ctrs + 32, 0, 8, ctx->stream));
-        TierArgs a;
+        TierArgs a = {};
         a.work_list = fail_lists[cur_list];
         a.n_work_ptr = nullptr;
         a.n_work = n_work;
@@ -946,7 +944,7 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
     const int INF = 0x7fffffff;
-    ENSURE(ctx->fail_a, 4 * n); ENSURE(ctx->fail_b, 4 * n); ENSURE(ctx->fail_c, 4 * n); ENSURE(ctx->fail_d, 4 * n); ENSURE(ctx->fail_h, 4 * n); ENSURE(ctx->fail_w, 4 * n);
+    ENSURE(ctx->fail_a, 4 * n); ENSURE(ctx->fail_b, 4 * n); ENSURE(ctx->fail_c, 4 * n); ENSURE(ctx->fail_d, 4 * n); ENSURE(ctx->fail_h, 4 * n); ENSURE(ctx->fail_w, 4 * n); ENSURE(ctx->fail_x, 4 * n);
     ENSURE(ctx->counters, 256);
     ENSURE(ctx->blobs, (size_t)n * RB_SIZE);
     u32 *ctrs = (u32 *)ctx->counters.p;
@@ -955,22 +953,22 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     ENSURE(ctx->arena, (size_t)sm * 8 * (size_t)(2LL << 20));
     ENSURE(ctx->arena2, (size_t)sm * 8 * (size_t)(1u << 20));
     auto args = [&](const u32 *list, int in_ctr, int work_ctr, u32 *fail_list, int fail_ctr, long long arena_bytes, u8 *garena) {
-        TierArgs a;
+        TierArgs a = {};
         a.work_list = list; a.n_work_ptr = list ? ctrs + in_ctr : nullptr; a.n_work = (u32)n;
         a.work_ctr = ctrs + work_ctr; a.fail_ctr = ctrs + fail_ctr; a.fail_list = fail_list;
         a.arena_base = garena; a.arena_bytes = arena_bytes; a.last_tier = 0;
         a.work_out = (unsigned long long *)ctx->work_ctr.p; a.blobs = (u8 *)ctx->blobs.p; a.n_lo = 0; a.n_hi = INF;
         a.spill_base = nullptr; a.spill_bytes = 0;
-        a.heavy_list = nullptr; a.heavy_ctr = nullptr; a.heavy_bytes = 0;
         return a;
     };
     const Stage SEARCH = {MODE_SEARCH, true, 3, 8192, sm * 3, 8}, SCORE = {MODE_SCORE, true, 4, 5120, sm * 4, 8};
     const Stage S1 = {MODE_FUSED, true, 1, 27648, sm, 8}, G0 = {MODE_FUSED, false, 1, 2LL << 20, sm, 8};
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
-    u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p;
+    u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p, *LX = (u32 *)ctx->fail_x.p;
     simple(LW, ctrs + 12);                                                                        // closed-form clusters; the rest -> W
     {
         TierArgs a = args(LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr);
+        a.fail_list2 = LX; a.fail_ctr2 = ctrs + 17; a.dense_n = 10;     // rejects with >= 10 variants: first in the fused stage
         launch(SEARCH, a, (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8), ctx->stream);
     }
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
@@ -982,9 +980,10 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
     {
-        TierArgs a = args(LA, 1, 4, LB, 5, S1.arena_bytes, nullptr);
+        TierArgs a = args(LX, 17, 4, LB, 5, S1.arena_bytes, nullptr);
+        a.work_list2 = LA; a.n_work_ptr2 = ctrs + 1;
         a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;   // dense clusters keep running here: cold nodes spill to HBM
-        launch(S1, a, S1.ctas, ctx->stream);                                                      // A -> B   (8 warps x 27 KB per SM)
+        launch(S1, a, S1.ctas, ctx->stream);                                                      // X, A -> B   (8 warps x 27 KB per SM)
     }
     CK(cudaEventRecord(ctx->tev[2], ctx->stream));
     launch(SCORE, args(LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);   // rejects -> A2
