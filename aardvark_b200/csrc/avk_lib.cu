@@ -256,8 +256,10 @@ __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const Dev
 // 2 * copies * raw_allele_space (:455-522; needs raw >= X, else the general path reports the underflow).  Everything
 // else -- including these shapes with the hidden exact shortcut or the sequence bundle requested -- goes to the search
 // kernels through `work_list`.
+// Clusters with at least `dense_n` variants skip the search / score pair: they go to list `dense`, which the fused
+// stage starts on first (the longest searches of a batch are among them).
 __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, u64 n, u32 *work_list,
-                                                        u32 *work_ctr) {
+                                                        u32 *work_ctr, u32 *dense, u32 *dense_ctr, int dense_n) {
     const int lane = lane_id();
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
@@ -267,11 +269,13 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
     for (u64 base = warp * 32; base < n; base += n_warps * 32) {
         const u64 r = base + lane;
         bool simple = false;
+        int nvar = 0;
         u32 copies = 0, gvT = 0, gvQ = 0, wT = 0, wQ = 0, rawT = 0, rawQ = 0, edX = 0, vtype = 0;
         if (r < n && enabled) {
             const u8 *dig = b.digest + b.digest_off[r];
             const int4 h = *(const int4 *)dig;                         // status, N, nT, nQ
             const u32 c = b.contig[r];
+            nvar = h.x == AVK_ST_OK ? h.y : 0;
             if (h.x == AVK_ST_OK && h.y == 2 && h.z == 1 && h.w == 1 && c < b.n_contigs && b.start[r] <= b.end[r] &&
                 (u64)b.end[r] <= b.contig_len[c] && b.end[r] <= 0x7fff0000u) {
                 const uint4 t0 = *(const uint4 *)(dig + PH_SIZE), t1 = *(const uint4 *)(dig + PH_SIZE + 16);
@@ -300,11 +304,16 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
             }
         }
         // everything else: compact list for the search / score kernels (cluster order kept inside a warp's chunk)
-        const u32 rest = __ballot_sync(AVK_FULL, r < n && !simple);
-        u32 pos0 = 0;
+        const bool is_dense = r < n && !simple && nvar >= dense_n;
+        const u32 rest = __ballot_sync(AVK_FULL, r < n && !simple && !is_dense);
+        const u32 dn = __ballot_sync(AVK_FULL, is_dense);
+        u32 pos0 = 0, pos1 = 0;
         if (lane == 0 && rest) pos0 = atomicAdd(work_ctr, (u32)__popc(rest));
+        if (lane == 0 && dn) pos1 = atomicAdd(dense_ctr, (u32)__popc(dn));
         pos0 = __shfl_sync(AVK_FULL, pos0, 0);
-        if (r < n && !simple) work_list[pos0 + __popc(rest & ((1u << lane) - 1))] = (u32)r;
+        pos1 = __shfl_sync(AVK_FULL, pos1, 0);
+        if (r < n && !simple && !is_dense) work_list[pos0 + __popc(rest & ((1u << lane) - 1))] = (u32)r;
+        if (is_dense) dense[pos1 + __popc(dn & ((1u << lane) - 1))] = (u32)r;
         if (simple) {
             out.status[r] = AVK_ST_OK; out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = (uint16_t)supported;   // vtype is one of them
             out.vexp[gvT] = (u8)copies; out.vobs[gvT] = (u8)copies; out.vcls[gvT] = AVK_CLASS_TP;
@@ -589,6 +598,7 @@ struct avk_ctx {
     // workspace
     DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, fail_x, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     DevBuf rb[20];   // region builder temporaries
+    int dense_n = 10;   // clusters with at least this many variants start in the fused dense-cluster stage (tuning: AVK_DENSE_N)
     // resident batch
     bool have_batch = false;
     u64 n_regions = 0, n_variants = 0;
@@ -652,6 +662,7 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    if (const char *dn = getenv("AVK_DENSE_N")) ctx->dense_n = std::max(3, atoi(dn));
     for (auto &e : ctx->tev) cudaEventCreate(&e);
     {
         int lo = 0, hi = 0;
@@ -951,7 +962,7 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     u32 *LA = (u32 *)ctx->fail_a.p, *LB = (u32 *)ctx->fail_b.p, *LC = (u32 *)ctx->fail_c.p, *LD = (u32 *)ctx->fail_d.p;
     CK(cudaMemsetAsync(ctrs, 0, 256, ctx->stream));
     ENSURE(ctx->arena, (size_t)sm * 8 * (size_t)(2LL << 20));
-    ENSURE(ctx->arena2, (size_t)sm * 8 * (size_t)(1u << 20));
+    ENSURE(ctx->arena2, 2 * (size_t)sm * 8 * (size_t)(1u << 20));   // two fused stages may run side by side
     auto args = [&](const u32 *list, int in_ctr, int work_ctr, u32 *fail_list, int fail_ctr, long long arena_bytes, u8 *garena) {
         TierArgs a = {};
         a.work_list = list; a.n_work_ptr = list ? ctrs + in_ctr : nullptr; a.n_work = (u32)n;
@@ -965,30 +976,28 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     const Stage S1 = {MODE_FUSED, true, 1, 27648, sm, 8}, G0 = {MODE_FUSED, false, 1, 2LL << 20, sm, 8};
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p, *LX = (u32 *)ctx->fail_x.p;
-    simple(LW, ctrs + 12);                                                                        // closed-form clusters; the rest -> W
-    {
-        TierArgs a = args(LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr);
-        a.fail_list2 = LX; a.fail_ctr2 = ctrs + 17; a.dense_n = 10;     // rejects with >= 10 variants: first in the fused stage
-        launch(SEARCH, a, (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8), ctx->stream);
-    }
-    CK(cudaEventRecord(ctx->tev[1], ctx->stream));
-    // The fused stage for the search kernel's rejects (list A) ends with a few warps that each finish one dense cluster
-    // alone.  It is launched first (main stream, one 216 KB CTA per SM); the score kernel follows on a side stream behind
-    // an event, so it becomes runnable a moment later: as the fused CTAs run out of work and retire, the block scheduler
-    // fills their SMs with score CTAs, and score runs in the shadow of that tail.  (All k_compare kernels ask for the
+    simple(LW, ctrs + 12, LX, ctrs + 17);        // closed-form clusters; >= 10 variants -> X (dense); the rest -> W
+    const size_t spill_warp = 1u << 20, spill_half = (size_t)sm * 8 * spill_warp;
+    auto fused27 = [&](const u32 *list, int in_ctr, int work_ctr, int half, cudaStream_t strm) {   // 8 warps x 27 KB per SM, rejects -> B
+        TierArgs a = args(list, in_ctr, work_ctr, LB, 5, S1.arena_bytes, nullptr);
+        a.spill_base = (u8 *)ctx->arena2.p + half * spill_half; a.spill_bytes = (u32)spill_warp;   // cold search nodes spill to HBM instead of restarting the cluster
+        launch(S1, a, S1.ctas, strm);
+    };
+    // A dense cluster is solved by one warp in up to ~2 ms, so the dense stage ends with a few busy warps.  It is launched
+    // first (main stream, one 216 KB CTA per SM); search, score and the fused stage for their rejects follow on a
+    // lowest-priority side stream behind an event: as the dense CTAs run out of work and retire, the block scheduler fills
+    // their SMs with the other kernels' CTAs, which then run in the shadow of that tail.  (All k_compare kernels ask for the
     // maximum shared-memory carveout; kernels of different streams do not take over an SM otherwise: tools/overlap_probe.cu.)
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
-    {
-        TierArgs a = args(LX, 17, 4, LB, 5, S1.arena_bytes, nullptr);
-        a.work_list2 = LA; a.n_work_ptr2 = ctrs + 1;
-        a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;   // dense clusters keep running here: cold nodes spill to HBM
-        launch(S1, a, S1.ctas, ctx->stream);                                                      // X, A -> B   (8 warps x 27 KB per SM)
-    }
-    CK(cudaEventRecord(ctx->tev[2], ctx->stream));
-    launch(SCORE, args(LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);   // rejects -> A2
+    fused27(LX, 17, 4, 0, ctx->stream);                                                           // X -> B
+    CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+    launch(SEARCH, args(LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr), (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8), ctx->side[0]);   // W -> blobs, rejects -> A
+    launch(SCORE, args(LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);    // rejects -> A2
+    fused27(LA, 1, 18, 1, ctx->side[0]);                                                          // A -> B  (did not fit the 8 KB search arena)
     CK(cudaEventRecord(ctx->ev_join[0], ctx->side[0]));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+    CK(cudaEventRecord(ctx->tev[2], ctx->stream));
     {
         TierArgs a = args(LA2, 15, 16, LB, 5, S1.arena_bytes, nullptr);
         a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;
@@ -1000,7 +1009,7 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
         launch(G0, a, G0.ctas, ctx->stream);                                                      // B -> D   (2 MB global arenas)
     }
     CK(cudaEventRecord(ctx->tev[3], ctx->stream));
-    ctx->launches += 6;
+    ctx->launches += 7;
     CK(cudaGetLastError());
     u32 h[16];
     CK(cudaMemcpyAsync(h, ctrs, 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1062,8 +1071,8 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     rc = run_prepare(ctx, db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = run_compare_pipeline(ctx, n, [&](u32 *list, u32 *ctr) {
-        k_compare_simple<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, out, c, n, list, ctr);
+    rc = run_compare_pipeline(ctx, n, [&](u32 *list, u32 *ctr, u32 *dense, u32 *dense_ctr) {
+        k_compare_simple<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, out, c, n, list, ctr, dense, dense_ctr, ctx->dense_n);
     }, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
         if (st.mode == MODE_COOP) {
             const int cap_ints = 26000;                                  // wavefronts up to ED 12998 stay in shared memory
