@@ -92,7 +92,7 @@ EXPORTED_SYMBOLS = [
 
 
 def compare_cfg(cfg: CompareConfig) -> abi.CompareCfg:
-    return abi.CompareCfg(cfg.max_branch_factor, int(cfg.enable_exact_shortcut), int(cfg.enable_sequences), int(os.environ.get('AVK_EXPERIMENT', '0')))
+    return abi.CompareCfg(cfg.max_branch_factor, int(cfg.enable_exact_shortcut), int(cfg.enable_sequences), 0)
 
 
 def merge_cfg(cfg: MergeConfig) -> abi.MergeCfg:
