@@ -824,6 +824,7 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
     size_t garena = 0;
     for (const Stage &st : stages) if (!st.smem) garena = std::max(garena, (size_t)st.ctas * st.warps * (size_t)st.arena_bytes);
     if (garena) ENSURE(ctx->arena, garena);
+    ENSURE(ctx->arena2, (size_t)sm * 8 * (size_t)(1u << 20));
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     int ev = 1;
     bool forked = false, joined = false;
@@ -852,6 +853,7 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
         a.work_out = (unsigned long long *)ctx->work_ctr.p;
         a.blobs = (u8 *)ctx->blobs.p;
         a.spill_base = nullptr; a.spill_bytes = 0;
+        if (st.smem && st.arena_bytes >= 16384) { a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20; }   // cold search nodes spill to HBM
         a.n_lo = st.n_lo; a.n_hi = st.n_hi;
         int ctas = st.ctas;
         if (st.in_list < 0) ctas = (int)std::min<u64>((u64)ctas, (n + st.warps - 1) / st.warps);

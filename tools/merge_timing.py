@@ -12,6 +12,7 @@ s = Solver(0); s.set_reference([ref])
 cfg = MergeConfig(majority_voting_enabled=True)
 for i in range(3):
     t0 = time.time(); gpu = s.merge_batch(b, cfg); dt = time.time() - t0
+print("tiers ms", [round(x, 2) for x in s.last_tier_ms()], "overflow", s.last_tier_overflow(), "work", s.last_work())
 print(f"merge x5: {b.n_regions} clusters, {b.n_variants} variants; GPU (host buffers through the C ABI) {dt * 1e3:.1f} ms -> {b.n_regions / dt / 1e6:.2f} M clusters/s; device", s.last_timings_ms())
 t0 = time.time(); cpu = orc.merge_batch(b, [ref], merge_cfg(cfg), n_threads=orc.num_threads()); dc = time.time() - t0
 print(f"oracle {dc:.2f} s on {orc.num_threads()} threads -> {b.n_regions / dc / 1e6:.2f} M clusters/s; diff {gpu.diff(cpu)}")

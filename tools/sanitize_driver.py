@@ -27,5 +27,16 @@ print("dense", batch.n_regions, int(out.solved_blocks[0]), s.last_tier_overflow(
 ref, mb = synth.workload_merge(30_000, 120, n_sets=3, seed=38)
 s.set_reference([ref])
 print("merge", s.merge_batch(mb, MergeConfig(majority_voting_enabled=True)).classification[:10])
+# SV-sized events: 2 MB global tier -> cooperative tier (named barriers, shared-memory wavefronts)
+ps = synth.SynthParams(n_variants=12, sv_events=3, sv_min=600, sv_max=1500, flank=1000)
+ref, sv = synth.workload_compare(60_000, ps, seed=44)
+s.set_reference([ref])
+out = s.compare_batch(sv, CompareConfig(enable_sequences=False))
+print("sv", sv.n_regions, int(out.solved_blocks[0]), s.last_tier_overflow())
+# device region builder
+from aardvark_b200.batch import CallSets
+ref, inputs = synth.callsets_compare(50_000, synth.SynthParams(n_variants=150), seed=7)
+s.set_reference([ref])
+print("builder", s.build_regions(CallSets(inputs), 0, 50).n_regions)
 print("wfa", s.wfa_ed_batch([(b"ACGTACGTACGT", b"ACTACGCACGGGT"), (b"A" * 300, b"A" * 150 + b"C" + b"A" * 149)]))
 s.close()
