@@ -498,8 +498,34 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_compare_coop(DevBatch b, De
     coop_release_helpers();
 }
 
+// merge, stage 1 of 3: per cluster validation, length prefilter, identical-lists shortcut; emits the pair tasks
+__global__ void __launch_bounds__(256) k_merge_front(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, MergeWork w, u64 n) {
+    __shared__ DevBatch sb;
+    __shared__ RegionSolver<false> sol[8];
+    const int lane = lane_id();
+    if (threadIdx.x == 0) sb = b;
+    __syncthreads();
+    RegionSolver<false> &s = sol[threadIdx.x >> 5];
+    if (lane == 0) s.bp = &sb;
+    __syncwarp();
+    const u32 K = b.n_inputs;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 r = warp; r < n; r += n_warps) {
+        const int rc = s.merge_front(r, cfg, w);
+        __syncwarp();
+        if (lane == 0) {
+            out.status[r] = rc;
+            if (rc != AVK_ST_OK) {
+                out.cls[r] = AVK_MERGE_DIFFERENT; out.n_idx[r] = 0;
+                for (u32 k = 0; k < K; ++k) out.idx[r * K + k] = 0xFF;
+            }
+        }
+    }
+}
+
+// merge, stage 2 of 3: one pair search per warp (persistent warps over the task list, workspace tiers as for compare)
 template <bool SMEM, int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS) k_merge(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, TierArgs t) {
+__global__ void __launch_bounds__(256, MIN_CTAS) k_merge_pairs(DevBatch b, avk_merge_cfg cfg, TierArgs t, MergeWork w) {
     __shared__ DevBatch sb;
     __shared__ RegionSolver<SMEM> sol[8];
     const int lane = lane_id();
@@ -511,29 +537,49 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_merge(DevBatch b, DevMergeOut
         if (lane == 0) idx = atomicAdd(t.work_ctr, 1u);
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
-        const u64 r = t.work_list ? t.work_list[idx] : idx;
-        if (!t.work_list) {
-            const int nvar = (int)(sb.var_off[r * K + K] - sb.var_off[r * K]);
-            if (nvar < t.n_lo || nvar > t.n_hi) continue;
-        }
-        int rc = s.solve_merge(r, cfg, out);
+        const u32 task = t.work_list ? t.work_list[idx] : idx;
+        const u64 tk = w.tasks[task];
+        const u64 r = tk >> 16;
+        const u32 i = (u32)(tk >> 8) & 0xffu, j = (u32)tk & 0xffu;
+        bool exact = false;
+        int rc = s.merge_pair(r, i, j, cfg, &exact);
         __syncwarp();
         if (rc == SOLVE_WORKSPACE) {
             if (!t.last_tier) {
-                if (lane == 0) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
+                if (lane == 0) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = task;
                 continue;
             }
             rc = AVK_ST_WORKSPACE;
         }
         if (lane == 0) {
-            out.status[r] = rc;
-            if (rc != AVK_ST_OK) {
-                out.cls[r] = AVK_MERGE_DIFFERENT; out.n_idx[r] = 0;
-                for (u32 k = 0; k < K; ++k) out.idx[r * K + k] = 0xFF;
-            }
+            if (rc != AVK_ST_OK) atomicMin(w.pair_err + r, ((i * K - i * (i + 1) / 2 + (j - i - 1)) << 8) | (u32)rc);   // first failing pair in loop order
+            else if (exact) { atomicOr(w.rows + r * K + i, 1u << j); atomicOr(w.rows + r * K + j, 1u << i); }
         }
     }
     flush_work<SMEM>(s.arena, t.work_out);
+}
+
+// merge, stage 3 of 3: match sets -> classification
+__global__ void __launch_bounds__(256) k_merge_classify(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, MergeWork w, u64 n) {
+    __shared__ DevBatch sb;
+    __shared__ RegionSolver<false> sol[8];
+    const int lane = lane_id();
+    if (threadIdx.x == 0) sb = b;
+    __syncthreads();
+    RegionSolver<false> &s = sol[threadIdx.x >> 5];
+    if (lane == 0) s.bp = &sb;
+    __syncwarp();
+    const u32 K = b.n_inputs;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 r = warp; r < n; r += n_warps) {
+        if (out.status[r] != AVK_ST_OK) continue;                      // rejected by the front stage
+        const int rc = s.merge_classify(r, cfg, out, w);
+        __syncwarp();
+        if (lane == 0 && rc != AVK_ST_OK) {
+            out.status[r] = rc; out.cls[r] = AVK_MERGE_DIFFERENT; out.n_idx[r] = 0;
+            for (u32 k = 0; k < K; ++k) out.idx[r * K + k] = 0xFF;
+        }
+    }
 }
 
 // SummaryWriter::add_comparison_benchmark (writers/summary.rs:146-158): thread j sums column j of the
@@ -594,7 +640,7 @@ struct avk_ctx {
     DevBuf region_id, contig, start, end, var_off, pos, vtype, zyg, raw, aoff, l0, l1, pool, alt_ed;
     // outputs
     DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, strat_off, strat_idx, strat_totals,
-        seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx;
+        seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx, m_rows, m_perr, m_tasks;
     // workspace
     DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, fail_x, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     DevBuf rb[20];   // region builder temporaries
@@ -685,7 +731,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
@@ -811,8 +857,10 @@ struct Stage {
     int n_lo, n_hi;        // cluster-size class (stages scanning all regions)
 };
 
-template <class F>
-static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F launch) {
+// `pre(ctrs)` runs after the counters are cleared and before the first stage; when `first_ctr` >= 0 the first stage takes
+// its work count from that counter (written by `pre`) instead of n, which is then only an upper bound.
+template <class P, class F>
+static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, P pre, int first_ctr, F launch) {
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
     ENSURE(ctx->fail_a, 4 * n);
@@ -826,6 +874,7 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
     if (garena) ENSURE(ctx->arena, garena);
     ENSURE(ctx->arena2, (size_t)sm * 8 * (size_t)(1u << 20));
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+    pre(ctrs);
     int ev = 1;
     bool forked = false, joined = false;
     for (size_t i = 0; i < stages.size(); ++i) {
@@ -842,7 +891,7 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, F l
         }
         TierArgs a = {};
         a.work_list = st.in_list < 0 ? nullptr : fail_lists[st.in_list];
-        a.n_work_ptr = st.in_list < 0 ? nullptr : ctrs + st.in_ctr;
+        a.n_work_ptr = st.in_list < 0 ? (first_ctr >= 0 ? ctrs + first_ctr : nullptr) : ctrs + st.in_ctr;
         a.n_work = (u32)n;
         a.work_ctr = ctrs + st.work_ctr;
         a.fail_ctr = ctrs + st.fail_ctr;
@@ -922,14 +971,14 @@ static void launch_compare(avk_ctx *ctx, const DevBatch &db, const DevCompareOut
     k_compare<SMEM, MIN_CTAS, MODE><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
 }
 template <bool SMEM, int MIN_CTAS>
-static void launch_merge(avk_ctx *ctx, const DevBatch &db, const DevMergeOut &out, const avk_merge_cfg &c, const TierArgs &a, int ctas, int warps, cudaStream_t strm) {
+static void launch_merge_pairs(avk_ctx *ctx, const DevBatch &db, const avk_merge_cfg &c, const TierArgs &a, const MergeWork &w, int ctas, int warps, cudaStream_t strm) {
     const size_t smem = SMEM ? (size_t)a.arena_bytes * warps : 0;
     static bool configured = false;
     if (!configured) {
-        if (SMEM) cudaFuncSetAttribute(k_merge<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+        if (SMEM) cudaFuncSetAttribute(k_merge_pairs<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
         configured = true;
     }
-    k_merge<SMEM, MIN_CTAS><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
+    k_merge_pairs<SMEM, MIN_CTAS><<<ctas, 32 * warps, smem, strm>>>(db, c, a, w);
 }
 
 static int run_prepare(avk_ctx *ctx, const DevBatch &db) {
@@ -1445,16 +1494,33 @@ extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, cons
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     const int sm = ctx->sm_count;
     const int INF = 0x7fffffff;
+    // front stage (per cluster) -> pair tasks (per pair, three workspace tiers) -> classification (per cluster)
+    const u64 pairs = (u64)K * (K - 1) / 2, max_tasks = n * pairs;
+    if (max_tasks >= 0xffffffffull || n >= (1ull << 47)) { ctx->err = "avk_merge_batch: too many pair tasks"; return AVK_ERR_INVALID; }
+    ENSURE(ctx->m_rows, 4 * n * K); ENSURE(ctx->m_perr, 4 * n); ENSURE(ctx->m_tasks, 8 * max_tasks);
+    MergeWork mw;
+    mw.rows = (u32 *)ctx->m_rows.p; mw.pair_err = (u32 *)ctx->m_perr.p; mw.tasks = (u64 *)ctx->m_tasks.p; mw.task_ctr = nullptr;
     const std::vector<Stage> stages = {
         {MODE_FUSED, true, 3, 8192, sm * 3, 8, -1, 0, 0, 0, 1, 0, 0, INF},
         {MODE_FUSED, true, 1, 27648, sm, 8, 0, 1, 3, 1, 4, 0, 0, INF},
         {MODE_FUSED, false, 1, 2LL << 20, sm, 8, 1, 4, 5, 0, 6, 0, 0, INF},
     };
-    rc = run_stages(ctx, n, stages, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
-        if (st.smem && st.min_ctas == 3) launch_merge<true, 3>(ctx, db, mo, c, a, ctas, st.warps, strm);
-        else if (st.smem) launch_merge<true, 1>(ctx, db, mo, c, a, ctas, st.warps, strm);
-        else launch_merge<false, 1>(ctx, db, mo, c, a, ctas, st.warps, strm);
+    const unsigned cgrid = (unsigned)std::min<u64>((u64)sm * 8, (n + 7) / 8);
+    rc = run_stages(ctx, std::max<u64>(max_tasks, 1), stages, [&](u32 *ctrs) {   // (an upper bound; the task count is produced on the device)
+        mw.task_ctr = ctrs + 20;
+        if (n) k_merge_front<<<cgrid, 256, 0, ctx->stream>>>(db, mo, c, mw, n);
+        ctx->launches += 1;
+    }, 20, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
+        if (st.smem && st.min_ctas == 3) launch_merge_pairs<true, 3>(ctx, db, c, a, mw, ctas, st.warps, strm);
+        else if (st.smem) launch_merge_pairs<true, 1>(ctx, db, c, a, mw, ctas, st.warps, strm);
+        else launch_merge_pairs<false, 1>(ctx, db, c, a, mw, ctas, st.warps, strm);
     });
+    if (rc != AVK_OK) return rc;
+    if (n) {
+        k_merge_classify<<<cgrid, 256, 0, ctx->stream>>>(db, mo, c, mw, n);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+    }
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));

@@ -1130,7 +1130,9 @@ struct RegionSolver {
     __device__ int compare_search_to_blob(u64 r, const avk_compare_cfg &cfg, u8 *blob);
     __device__ int compare_score_from_blob(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out, const u8 *blob);
     __device__ int compare_score(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out);
-    __device__ int solve_merge(u64 r, const avk_merge_cfg &cfg, const DevMergeOut &out);
+    __device__ int merge_front(u64 r, const avk_merge_cfg &cfg, const struct MergeWork &w);
+    __device__ int merge_pair(u64 r, u32 i, u32 j, const avk_merge_cfg &cfg, bool *exact);
+    __device__ int merge_classify(u64 r, const avk_merge_cfg &cfg, const DevMergeOut &out, const struct MergeWork &w);
 };
 
 // Hand-off record between the search kernel and the score kernel of the common tier (N <= 16, <= 8 results).
@@ -1441,9 +1443,23 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
     return AVK_ST_OK;
 }
 
-// solve_merge_region(): merge_solver.rs:110-200
+// solve_merge_region(): merge_solver.rs:110-200, split in three so that the K(K-1)/2 pair searches of a cluster -- which are
+// independent -- become separate work items (a dense 5-input cluster is ten searches of ~1 ms each):
+//   merge_front    per cluster: validation, variant_delta_length prefilter (:211-223), identical-lists shortcut; the pairs
+//                  that need a search are appended to a task list, the others are decided here;
+//   merge_pair     per task: optimize_sequences on (v_i as truth, v_j as query), is_exact_match() of the result (:135-143);
+//   merge_classify per cluster: match_sets -> classification (:152-197).
+// `rows[r*K + i]` is match_sets[i] as a bit mask; `pair_err[r]` keeps the error of the FIRST failing pair in the
+// reference's loop order, (pair index << 8) | status, like the `?` in the sequential loop.
+struct MergeWork {
+    u32 *rows;        // [n][K]
+    u32 *pair_err;    // [n], 0xffffffff = none
+    u64 *tasks;       // (r << 16) | (i << 8) | j
+    u32 *task_ctr;
+};
+
 template <bool SMEM>
-__device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, const DevMergeOut &out) {
+__device__ int RegionSolver<SMEM>::merge_front(u64 r, const avk_merge_cfg &cfg, const MergeWork &w) {
     const DevBatch &b = *bp;
     const int lane = lane_id();
     const u32 K = b.n_inputs;
@@ -1463,7 +1479,6 @@ __device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, 
         }
         if (__any_sync(AVK_FULL, invalid)) return AVK_ST_BAD_INPUT;
     }
-    if (!begin_region(b.contig_ptr[c])) return SOLVE_WORKSPACE;
     // variant_delta_length(): :211-223, lane k holds input k
     long long delta = 0;
     bool unknown = false;
@@ -1476,39 +1491,66 @@ __device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, 
             delta += ((long long)b.l1[gv] - (long long)b.l0[gv]) * cnt;
         }
     }
-    if (__any_sync(AVK_FULL, unknown)) { drain_window(); return AVK_ST_BAD_ZYGOSITY; }
+    if (__any_sync(AVK_FULL, unknown)) return AVK_ST_BAD_ZYGOSITY;
     u32 match_row = ((u32)lane < K) ? (1u << lane) : 0;   // lane i holds match_sets[i] as a bit mask
-    bool all_identical = true, no_conflict = true;
 #pragma unroll 1
     for (u32 i = 0; i < K; ++i) {
 #pragma unroll 1
         for (u32 j = i + 1; j < K; ++j) {
             const long long di = __shfl_sync(AVK_FULL, delta, i), dj = __shfl_sync(AVK_FULL, delta, j);
-            bool exact = false;
-            const bool empty_i = b.var_off[r * K + i + 1] == b.var_off[r * K + i];
-            const bool empty_j = b.var_off[r * K + j + 1] == b.var_off[r * K + j];
-            if (di == dj && merge_pair_identical(r, i, j)) exact = true;
-            else if (di == dj) {                                         // :135-143
-                int rc = setup_pair(r, i, j, false);
-                if (rc) { drain_window(); return rc; }
-                rc = optimize(true);
-                if (rc) return rc;
-                if (n_res > 0) {
-                    int s = 0;
-#pragma unroll 1
-                    for (int k = 0; k < 6; ++k) s += LDI(res_num + 4 * k);
-                    exact = s == 0;
-                }
-            }
-            all_identical = all_identical && exact;
-            no_conflict = no_conflict && (empty_i || empty_j || exact);   // :155-157
-            if (exact) {
+            if (di != dj) continue;                                      // :135: different total length change, no search
+            if (merge_pair_identical(r, i, j)) {
                 if ((u32)lane == i) match_row |= 1u << j;
                 if ((u32)lane == j) match_row |= 1u << i;
+            } else if (lane == 0) {
+                w.tasks[atomicAdd(w.task_ctr, 1u)] = (r << 16) | ((u64)i << 8) | j;
             }
         }
     }
-    drain_window();   // every pair may have taken the identical-lists shortcut
+    if ((u32)lane < K) w.rows[r * K + lane] = match_row;
+    if (lane == 0) w.pair_err[r] = 0xffffffffu;
+    return AVK_ST_OK;
+}
+
+// one pair search; *exact is meaningful when AVK_ST_OK is returned
+template <bool SMEM>
+__device__ int RegionSolver<SMEM>::merge_pair(u64 r, u32 i, u32 j, const avk_merge_cfg &cfg, bool *exact) {
+    const DevBatch &b = *bp;
+    const u32 c = b.contig[r];
+    start = (int)b.start[r];
+    end = (int)b.end[r];
+    mbf = (int)cfg.max_branch_factor;
+    *exact = false;
+    if (!begin_region(b.contig_ptr[c])) return SOLVE_WORKSPACE;
+    int rc = setup_pair(r, i, j, false);
+    if (rc) { drain_window(); return rc; }
+    rc = optimize(true);
+    if (rc) return rc;
+    if (n_res > 0) {
+        int s = 0;
+#pragma unroll 1
+        for (int k = 0; k < 6; ++k) s += LDI(res_num + 4 * k);
+        *exact = s == 0;
+    }
+    return AVK_ST_OK;
+}
+
+// classification from the match sets (lanes = inputs); status of the cluster is returned
+template <bool SMEM>
+__device__ int RegionSolver<SMEM>::merge_classify(u64 r, const avk_merge_cfg &cfg, const DevMergeOut &out, const MergeWork &w) {
+    const DevBatch &b = *bp;
+    const int lane = lane_id();
+    const u32 K = b.n_inputs;
+    const u32 perr = w.pair_err[r];
+    if (perr != 0xffffffffu) return (int)(perr & 0xffu);
+    const u32 match_row = ((u32)lane < K) ? w.rows[r * K + lane] : 0;
+    const u32 full = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+    const bool empty = (u32)lane < K && b.var_off[r * K + lane + 1] == b.var_off[r * K + lane];
+    const u32 empty_mask = __ballot_sync(AVK_FULL, empty);
+    const bool all_identical = __all_sync(AVK_FULL, (u32)lane >= K || match_row == full);
+    // no_conflict: every pair (i, j) has empty_i || empty_j || exact (:155-157)
+    const bool row_ok = (u32)lane >= K || empty || ((match_row | empty_mask) & full) == full;
+    const bool no_conflict = __all_sync(AVK_FULL, row_ok);
     const u32 maj = K / 2 + 1;                                            // :167
     const unsigned has = __ballot_sync(AVK_FULL, (u32)lane < K && (u32)__popc(match_row) >= maj);
     u32 first_maj = 0;
@@ -1517,11 +1559,8 @@ __device__ int RegionSolver<SMEM>::solve_merge(u64 r, const avk_merge_cfg &cfg, 
     u32 idx_mask = 0;
     int sel = -1;
     if (all_identical) cls = AVK_MERGE_BASEPAIR_IDENTICAL;               // :174-197
-    else if (cfg.no_conflict_enabled && no_conflict) {
-        cls = AVK_MERGE_NO_CONFLICT;
-        const bool nonempty = (u32)lane < K && b.var_off[r * K + lane + 1] != b.var_off[r * K + lane];
-        idx_mask = __ballot_sync(AVK_FULL, nonempty);
-    } else if (cfg.majority_voting_enabled && first_maj != 0) { cls = AVK_MERGE_MAJORITY_AGREE; idx_mask = first_maj; }
+    else if (cfg.no_conflict_enabled && no_conflict) { cls = AVK_MERGE_NO_CONFLICT; idx_mask = full & ~empty_mask; }
+    else if (cfg.majority_voting_enabled && first_maj != 0) { cls = AVK_MERGE_MAJORITY_AGREE; idx_mask = first_maj; }
     else if (cfg.conflict_selection >= 0) { cls = AVK_MERGE_CONFLICT_SELECTION; sel = cfg.conflict_selection; }
     else cls = AVK_MERGE_DIFFERENT;
     __syncwarp();
