@@ -245,17 +245,19 @@ __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const Dev
 // ---- closed form for the commonest cluster shape ------------------------------------------------------------
 // One truth and one query record that are the same variant -- same position, reference span, ALT bytes, (supported) type
 // label and number of ALT copies -- where the variant is a substitution that changes the base, or an anchored pure
-// insertion / deletion (first ALT base == the reference base): ~70 % of a small-variant WGS comparison.  What
-// solve_compare_region computes for it follows from the search itself (query_optimizer.rs:203-328): the orientation(s)
-// in which both haplotypes spell identical sequences finalise with cost 0 after at most four pops at the last depth
-// (hence max_branch_factor >= 4); every other orientation pairs the reference window with the ALT haplotype -- a
-// different string -- on some haplotype and costs more.  So each equal-best result has ED 0, no skipped variant and
-// expected == observed == ALT copies for both records.  Metrics: gt/hap/weighted_hap TP on both sides
-// (grouped_metrics.rs:183-227); basepair X = Y = ED(reference window, ALT haplotype) = 1 resp. the length difference
-// (closed form, see RegionSolver::build_hap_seq) per ALT haplotype, Z = 0 (waffle_solver.rs:639-648); record basepair
-// 2 * copies * raw_allele_space (:455-522; needs raw >= X, else the general path reports the underflow).  Everything
-// else -- including these shapes with the hidden exact shortcut or the sequence bundle requested -- goes to the search
-// kernels through `work_list`.
+// insertion / deletion (first ALT base == the reference base); or TWO such pairs of substitutions at increasing positions:
+// ~80 % of a small-variant WGS comparison.  What solve_compare_region computes for them follows from the search itself
+// (query_optimizer.rs:203-328): the orientation(s) in which both haplotypes spell identical sequences finalise with cost
+// 0 -- the search tree has at most 4 (one pair) or 16 (two pairs) nodes per depth, hence max_branch_factor >= 4 / 16 so
+// that the branch quota never drops one; every other orientation pairs two different strings on some haplotype and costs
+// more.  So each equal-best result has ED 0, no skipped variant and expected == observed == ALT copies for every record,
+// whichever of them comes first.  Metrics: gt/hap/weighted_hap TP on both sides (grouped_metrics.rs:183-227); basepair
+// X = Y = ED(reference window, haplotype), Z = 0 (waffle_solver.rs:639-648), where the sum of X over the two haplotypes
+// is the same for every equal-best result: 1 per copy of a substitution (a haplotype with two of them has Hamming
+// distance 2 = ED 2 to the window), the length difference per copy of an anchored indel (closed forms of
+// RegionSolver::build_hap_seq); record basepair 2 * copies * raw_allele_space (:455-522; needs raw >= X, else the
+// general path reports the underflow).  Everything else -- including these shapes with the hidden exact shortcut or the
+// sequence bundle requested -- goes to the search kernels through `work_list`.
 // Clusters with at least `dense_n` variants skip the search / score pair: they go to list `dense`, which the fused
 // stage starts on first (the longest searches of a batch are among them).
 __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, u64 n, u32 *work_list,
@@ -269,38 +271,49 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
     for (u64 base = warp * 32; base < n; base += n_warps * 32) {
         const u64 r = base + lane;
         bool simple = false;
-        int nvar = 0;
-        u32 copies = 0, gvT = 0, gvQ = 0, wT = 0, wQ = 0, rawT = 0, rawQ = 0, edX = 0, vtype = 0;
-        if (r < n && enabled) {
+        int nvar = 0, npairs = 0;
+        u32 gv[4] = {0, 0, 0, 0}, cp[2] = {0, 0}, vtype = 0;
+        u32 s_c = 0, s_wT = 0, s_wQ = 0, s_X = 0, s_rT = 0, s_rQ = 0;   // sums over the pairs, each weighted by its ALT copies
+        if (r < n) {
             const u8 *dig = b.digest + b.digest_off[r];
             const int4 h = *(const int4 *)dig;                         // status, N, nT, nQ
             const u32 c = b.contig[r];
             nvar = h.x == AVK_ST_OK ? h.y : 0;
-            if (h.x == AVK_ST_OK && h.y == 2 && h.z == 1 && h.w == 1 && c < b.n_contigs && b.start[r] <= b.end[r] &&
+            const int M = (h.y == 2 && h.z == 1 && h.w == 1) ? 1 : ((h.y == 4 && h.z == 2 && h.w == 2) ? 2 : 0);
+            if (enabled && h.x == AVK_ST_OK && M && (M == 1 || cfg.max_branch_factor >= 16) && c < b.n_contigs && b.start[r] <= b.end[r] &&
                 (u64)b.end[r] <= b.contig_len[c] && b.end[r] <= 0x7fff0000u) {
-                const uint4 t0 = *(const uint4 *)(dig + PH_SIZE), t1 = *(const uint4 *)(dig + PH_SIZE + 16);
-                const uint4 q0 = *(const uint4 *)(dig + PH_SIZE + VI_SIZE), q1 = *(const uint4 *)(dig + PH_SIZE + VI_SIZE + 16);
-                // t0 = {pos, l0, l1, aoff}, t1 = {alt_ed, raw, gv, flags}
-                const u32 zT = (t1.w >> 8) & 0xff, zQ = (q1.w >> 8) & 0xff;
-                const u32 cT = zT == AVK_ZYG_HOM_ALT ? 2u : (zT >= AVK_ZYG_UNPHASED_HET ? 1u : 0u);
-                const u32 cQ = zQ == AVK_ZYG_HOM_ALT ? 2u : (zQ >= AVK_ZYG_UNPHASED_HET ? 1u : 0u);
-                const u32 ty = t1.w & 0xffu;
-                // same record on both sides: position, reference span, ALT bytes, type label (a supported one), ALT copies
-                if ((t1.w & 0x10000u) && !(q1.w & 0x10000u) && ty == (q1.w & 0xffu) && ((supported >> ty) & 1u) && t0.x == q0.x &&
-                    t0.y == q0.y && t0.z == q0.z && (t0.y == 1 || t0.z == 1) && t0.y + t0.z <= 64 && cT != 0 && cT == cQ) {
-                    const u8 *alle = dig + PH_SIZE + 2 * VI_SIZE;
+                const u8 *alle = dig + PH_SIZE + 2 * M * VI_SIZE;
+                bool ok = true;
+                u32 prev_pos = 0;
+                for (int m = 0; m < M && ok; ++m) {
+                    const u8 *rt = dig + PH_SIZE + 2 * m * VI_SIZE, *rq = rt + VI_SIZE;      // merged order: truth before query on ties
+                    const uint4 t0 = *(const uint4 *)rt, t1 = *(const uint4 *)(rt + 16), q0 = *(const uint4 *)rq, q1 = *(const uint4 *)(rq + 16);
+                    // t0 = {pos, l0, l1, aoff}, t1 = {alt_ed, raw, gv, flags}
+                    const u32 zT = (t1.w >> 8) & 0xff, zQ = (q1.w >> 8) & 0xff;
+                    const u32 cT = zT == AVK_ZYG_HOM_ALT ? 2u : (zT >= AVK_ZYG_UNPHASED_HET ? 1u : 0u);
+                    const u32 cQ = zQ == AVK_ZYG_HOM_ALT ? 2u : (zQ >= AVK_ZYG_UNPHASED_HET ? 1u : 0u);
+                    const u32 ty = t1.w & 0xffu;
+                    // same record on both sides: position, reference span, ALT bytes, type label (a supported one), ALT copies
+                    ok = (t1.w & 0x10000u) && !(q1.w & 0x10000u) && ty == (q1.w & 0xffu) && ((supported >> ty) & 1u) && t0.x == q0.x &&
+                         t0.y == q0.y && t0.z == q0.z && (t0.y == 1 || t0.z == 1) && t0.y + t0.z <= 64 && cT != 0 && cT == cQ;
+                    // two pairs: substitutions only, at increasing positions (the Hamming argument below needs equal lengths)
+                    if (M == 2) ok = ok && t0.y == 1 && t0.z == 1 && ty == AVK_VT_SNV && (m == 0 || t0.x > prev_pos);
+                    if (!ok) break;
                     const u8 *aT = alle + t0.w + t0.y, *aQ = alle + q0.w + q0.y;   // ALT alleles
-                    bool same = true;
-                    for (u32 k = 0; k < t0.z; ++k) same = same && aT[k] == aQ[k];
+                    for (u32 k = 0; k < t0.z; ++k) ok = ok && aT[k] == aQ[k];
                     const bool anchored = aT[0] == b.contig_ptr[c][t0.x];
-                    // ED(reference window, ALT haplotype): substitution that changes the base: 1; anchored pure
-                    // insertion / deletion: the length difference (RegionSolver::build_hap_seq, SD_CLOSED)
+                    // ED(reference window, ALT haplotype): a substitution that changes the base: 1 (two of them on one
+                    // haplotype: Hamming 2 = ED 2); anchored pure insertion / deletion: the length difference
+                    // (RegionSolver::build_hap_seq, SD_CLOSED)
                     u32 X = 0;
                     if (t0.y == 1 && t0.z == 1) X = anchored ? 0u : 1u;
                     else if (anchored) X = (t0.y == 1 ? t0.z : t0.y) - 1u;
-                    simple = same && X != 0 && t1.y >= X && q1.y >= X;
-                    copies = cT; gvT = t1.z; gvQ = q1.z; wT = t1.x; wQ = q1.x; rawT = t1.y; rawQ = q1.y; edX = X; vtype = ty;
+                    ok = ok && X != 0 && t1.y >= X && q1.y >= X;
+                    gv[2 * m] = t1.z; gv[2 * m + 1] = q1.z; cp[m] = cT; vtype = ty; prev_pos = t0.x;
+                    s_c += cT; s_wT += cT * t1.x; s_wQ += cT * q1.x; s_X += cT * X; s_rT += cT * t1.y; s_rQ += cT * q1.y;
                 }
+                simple = ok;
+                npairs = M;
             }
         }
         // everything else: compact list for the search / score kernels (cluster order kept inside a warp's chunk)
@@ -316,18 +329,20 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
         if (is_dense) dense[pos1 + __popc(dn & ((1u << lane) - 1))] = (u32)r;
         if (simple) {
             out.status[r] = AVK_ST_OK; out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = (uint16_t)supported;   // vtype is one of them
-            out.vexp[gvT] = (u8)copies; out.vobs[gvT] = (u8)copies; out.vcls[gvT] = AVK_CLASS_TP;
-            out.vexp[gvQ] = (u8)copies; out.vobs[gvQ] = (u8)copies; out.vcls[gvQ] = AVK_CLASS_TP;
+            for (int m = 0; m < npairs; ++m) {
+                out.vexp[gv[2 * m]] = (u8)cp[m]; out.vobs[gv[2 * m]] = (u8)cp[m]; out.vcls[gv[2 * m]] = AVK_CLASS_TP;
+                out.vexp[gv[2 * m + 1]] = (u8)cp[m]; out.vobs[gv[2 * m + 1]] = (u8)cp[m]; out.vcls[gv[2 * m + 1]] = AVK_CLASS_TP;
+            }
         }
-        // metric rows [13][22], written by the whole warp per cluster: joint row == SNV row, the rest zero
+        // metric rows [13][22], written by the whole warp per cluster: joint row == the (single) type's row, the rest zero
         u32 todo = __ballot_sync(AVK_FULL, simple);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
-            const u64 cp = __shfl_sync(AVK_FULL, copies, src);
-            const u64 vwT = __shfl_sync(AVK_FULL, wT, src), vwQ = __shfl_sync(AVK_FULL, wQ, src);
-            const u64 vrT = __shfl_sync(AVK_FULL, rawT, src), vrQ = __shfl_sync(AVK_FULL, rawQ, src);
-            const u64 vX = __shfl_sync(AVK_FULL, edX, src);
+            const u64 vM = (u64)__shfl_sync(AVK_FULL, npairs, src), vc = __shfl_sync(AVK_FULL, s_c, src);
+            const u64 vwT = __shfl_sync(AVK_FULL, s_wT, src), vwQ = __shfl_sync(AVK_FULL, s_wQ, src);
+            const u64 vrT = __shfl_sync(AVK_FULL, s_rT, src), vrQ = __shfl_sync(AVK_FULL, s_rQ, src);
+            const u64 vX = __shfl_sync(AVK_FULL, s_X, src);
             const int grow = 1 + (int)__shfl_sync(AVK_FULL, vtype, src);
             u64 *dst = out.region_metrics + (base + src) * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
 #pragma unroll 1
@@ -335,13 +350,13 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
                 const int g = i / AVK_N_METRICS, m = i - g * AVK_N_METRICS;
                 u64 v = 0;
                 if (g == 0 || g == grow) {
-                    if (m == AVK_M_GT || m == AVK_M_GT + 2) v = 1;
-                    else if (m == AVK_M_HAP || m == AVK_M_HAP + 2) v = cp;
-                    else if (m == AVK_M_WEIGHTED_HAP) v = cp * vwT;
-                    else if (m == AVK_M_WEIGHTED_HAP + 2) v = cp * vwQ;
-                    else if (m == AVK_M_BASEPAIR || m == AVK_M_BASEPAIR + 2) v = 2 * cp * vX;
-                    else if (m == AVK_M_RECORD_BP) v = 2 * cp * vrT;
-                    else if (m == AVK_M_RECORD_BP + 2) v = 2 * cp * vrQ;
+                    if (m == AVK_M_GT || m == AVK_M_GT + 2) v = vM;
+                    else if (m == AVK_M_HAP || m == AVK_M_HAP + 2) v = vc;
+                    else if (m == AVK_M_WEIGHTED_HAP) v = vwT;
+                    else if (m == AVK_M_WEIGHTED_HAP + 2) v = vwQ;
+                    else if (m == AVK_M_BASEPAIR || m == AVK_M_BASEPAIR + 2) v = 2 * vX;
+                    else if (m == AVK_M_RECORD_BP) v = 2 * vrT;
+                    else if (m == AVK_M_RECORD_BP + 2) v = 2 * vrQ;
                 }
                 dst[i] = v;
             }

@@ -290,6 +290,46 @@ def test_build_regions_vs_host_builder(solver):
         _same_batch(solver.build_regions(CallSets(sets3), 0, flank), synth.cluster_regions(sets3, len(small), flank))
 
 
+def test_compare_two_snv_pairs_closed_form_vs_oracle(solver):
+    """Two truth + two query SNVs: every zygosity combination of the four records (allele-bearing codes), at distances
+    1 / 2 / 30, plus the neighbouring shapes that must take the general path (different ALT, ALT == reference base,
+    same position, an insertion instead of a substitution, a third query record) -- around k_compare_simple's
+    two-pair closed form -- under branch factors 4, 15, 16, 50."""
+    import itertools
+    from aardvark_b200.types import Coordinates, PhasedZygosity as Z, Variant, VariantType
+    rng = np.random.default_rng(12)
+    ref = bytes(synth.ACGT[rng.integers(0, 4, size=6000)])
+    solver.set_reference([ref], ["c"])
+    zygs = [Z.UnphasedHeterozygous, Z.PhasedHet01, Z.PhasedHet10, Z.HomozygousAlternate]
+    other = lambda b_, k=0: [x for x in (b"A", b"C", b"G", b"T") if x != b_][k]
+    snv = lambda p, alt: Variant(0, VariantType.Snv, p, ref[p:p + 1], alt)
+    regions = []
+    rid = 0
+    for z in itertools.product(zygs, repeat=4):
+        for shape in range(9):
+            p = 100 + 11 * (rid % 450)
+            d = (1, 2, 30)[rid % 3]
+            q = p + d
+            a, b2 = other(ref[p:p + 1]), other(ref[q:q + 1])
+            tv, qv = [snv(p, a), snv(q, b2)], [snv(p, a), snv(q, b2)]
+            tz, qz = [z[0], z[1]], [z[2], z[3]]
+            if shape == 1: qv[1] = snv(q, other(ref[q:q + 1], 1))                       # different ALT on the second pair
+            if shape == 2: tv[0] = qv[0] = snv(p, ref[p:p + 1])                         # ALT == reference base
+            if shape == 3: tv[1] = qv[1] = snv(p, other(ref[p:p + 1], 1))               # both at the same position
+            if shape == 4: tv[1] = qv[1] = Variant(0, VariantType.Insertion, q, ref[q:q + 1], ref[q:q + 1] + b"GT")
+            if shape == 5: qv.append(snv(q + 3, other(ref[q + 3:q + 4]))); qz.append(Z.HomozygousAlternate)
+            if shape == 6: qz = [z[2], Z.HomozygousAlternate if z[1] != Z.HomozygousAlternate else Z.PhasedHet01]   # copies differ
+            if shape == 7: tv[0] = Variant(0, VariantType.Snv, p, other(ref[p:p + 1], 2), a); qv[0] = tv[0]        # allele0 != reference
+            regions.append(CompareRegion(rid, Coordinates("c", p - 50, q + 55), tv, tz, qv, qz))
+            rid += 1
+    batch = RegionBatch.from_compare_regions(regions, {"c": 0})
+    for mbf in (4, 15, 16, 50):
+        gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False, max_branch_factor=mbf))
+        assert gpu.diff(cpu) == [], f"max_branch_factor={mbf}"
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False, enable_exact_shortcut=True))
+    assert gpu.diff(cpu) == []
+
+
 def test_merge_synthetic_vs_oracle(solver):
     ref, batch = synth.workload_merge(150_000, 400, n_sets=5, seed=38)
     solver.set_reference([ref])
