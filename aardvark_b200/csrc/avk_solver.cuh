@@ -1221,9 +1221,19 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
         // haplotype scores at least 1: its zero-flip path ends in unequal sequences or a skipped variant.  Only a
         // strictly smaller total replaces the current first minimum, so a solution whose lower bound already reaches
         // it is not searched at all, and a search stops once it has used up what is left of the budget.
+        // A solution with both haplotypes at 0 totals 0, which nothing later can beat and nothing earlier (>= 1) reaches:
+        // the first such solution is the answer and no search is needed at all.
         int best_total = 0x7fffffff;
+        int lo = 0, hi = n_res;
 #pragma unroll 1
         for (int ri = 0; ri < n_res; ++ri) {
+            int sum = 0;
+#pragma unroll 1
+            for (int k = 0; k < 6; ++k) sum += LDI(res_num + (u32)(ri * 24 + 4 * k));
+            if (sum == 0) { lo = ri; hi = ri + 1; break; }
+        }
+#pragma unroll 1
+        for (int ri = lo; ri < hi; ++ri) {
             const addr ra = res_alle + (u32)(ri * npad);
             const addr rnum = res_num + (u32)(ri * 24);
             const bool zero0 = LDI(rnum) + LDI(rnum + 8) + LDI(rnum + 16) == 0;
