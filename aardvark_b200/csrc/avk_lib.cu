@@ -1083,14 +1083,16 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
     ctx->tier_fail[0] = h[1]; ctx->tier_fail[1] = h[5]; ctx->tier_fail[2] = h[7];
     // rare: clusters that overflow 2 MB per warp (list D); host-synchronised escalation
-    // (SV-sized events).  64 MB: one cluster per CTA, wide wavefronts advanced by the whole CTA; 2 GB: last resort.
-    const Stage big[2] = {{MODE_COOP, false, 1, 64LL << 20, sm, 1}, {MODE_FUSED, false, 1, 2048LL << 20, 1, 8}};
+    // (SV-sized events): one cluster per CTA, wide wavefronts advanced by the whole CTA; 256 MB arenas, then 2 GB (last resort).
+    Stage big[2] = {{MODE_COOP, false, 1, 256LL << 20, sm, 1}, {MODE_COOP, false, 1, 2048LL << 20, 16, 1}};
     const u32 *cur = LD;
     u32 *other = LC;
     u32 n_work = h[7];
     for (int t = 0; t < 2 && n_work > 0; ++t) {
+        big[t].ctas = (int)std::min<u64>((u64)big[t].ctas, n_work);           // one cluster per CTA
         ENSURE(ctx->arena, (size_t)big[t].ctas * big[t].warps * (size_t)big[t].arena_bytes);
         CK(cudaMemsetAsync(ctrs + 32, 0, 8, ctx->stream));
+        if (getenv("AVK_DEBUG")) cudaEventRecord(ctx->dbg[0], ctx->stream);
         TierArgs a = args(cur, 0, 32, other, 33, big[t].arena_bytes, (u8 *)ctx->arena.p);
         a.n_work_ptr = nullptr; a.n_work = n_work; a.last_tier = t == 1;
         launch(big[t], a, big[t].ctas, ctx->stream);
@@ -1098,6 +1100,11 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h, ctrs + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (getenv("AVK_DEBUG")) {
+            float ms = 0;
+            cudaEventRecord(ctx->dbg[1], ctx->stream); cudaEventSynchronize(ctx->dbg[1]); cudaEventElapsedTime(&ms, ctx->dbg[0], ctx->dbg[1]);
+            fprintf(stderr, "[avk] big tier %d (%s): %u clusters in, %u rejected, %.1f ms\n", t, t == 0 ? "cooperative, 256 MB" : "cooperative, 2 GB", n_work, h[1], ms);
+        }
         n_work = h[1];
         const u32 *tmp = cur; cur = other; other = (u32 *)tmp;
     }

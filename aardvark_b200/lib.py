@@ -72,8 +72,9 @@ def load():
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint32)]
     lib.avk_compare_seq_offsets.argtypes = [C.POINTER(abi.RegionBatch), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-    lib.avk_build_regions.argtypes = [vp, C.POINTER(abi.CallSets), C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-    lib.avk_regions_download.argtypes = [vp, C.POINTER(abi.RegionBatch)]
+    if hasattr(lib, "avk_build_regions"):   # (older builds used for A/B timing do not have the region builder)
+        lib.avk_build_regions.argtypes = [vp, C.POINTER(abi.CallSets), C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.avk_regions_download.argtypes = [vp, C.POINTER(abi.RegionBatch)]
     lib.avk_compare_upload.argtypes = [vp, C.POINTER(abi.RegionBatch)]
     lib.avk_compare_run_resident.argtypes = [vp, C.POINTER(abi.CompareCfg)]
     lib.avk_compare_download.argtypes = [vp, C.POINTER(abi.CompareOut)]
