@@ -513,6 +513,37 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_compare_coop(DevBatch b, De
     coop_release_helpers();
 }
 
+// Biggest first for the cooperative tiers: a cluster there can occupy its SM for seconds, so the expensive ones (edit-distance
+// bound x variants, both from the digest header) must not start last.  One CTA, bitonic sort in shared memory, <= 4096 entries.
+__global__ void __launch_bounds__(1024) k_sort_biggest_first(DevBatch b, u32 *list, u32 n) {
+    __shared__ unsigned long long key[4096];
+    u32 m = 1;
+    while (m < n) m <<= 1;
+    for (u32 i = threadIdx.x; i < m; i += blockDim.x) {
+        unsigned long long k = 0;
+        if (i < n) {
+            const int *h = (const int *)(b.digest + b.digest_off[list[i]]);
+            const unsigned long long cost = h[PH_STATUS / 4] == AVK_ST_OK ? (unsigned long long)(u32)h[PH_B0 / 4] * (u32)(h[PH_N / 4] + 1) : 0ull;
+            k = (min(cost, 0xffffffffull) << 32) | (0xffffffffu - list[i]);     // ties: lower cluster id first
+        }
+        key[i] = k;
+    }
+    __syncthreads();
+    for (u32 k2 = 2; k2 <= m; k2 <<= 1)
+        for (u32 j = k2 >> 1; j > 0; j >>= 1) {
+            for (u32 i = threadIdx.x; i < m; i += blockDim.x) {
+                const u32 l = i ^ j;
+                if (l > i) {
+                    const bool desc = (i & k2) == 0;
+                    const unsigned long long a = key[i], c = key[l];
+                    if (desc ? a < c : a > c) { key[i] = c; key[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) list[i] = 0xffffffffu - (u32)(key[i] & 0xffffffffull);
+}
+
 // merge, stage 1 of 3: per cluster validation, length prefilter, identical-lists shortcut; emits the pair tasks
 __global__ void __launch_bounds__(256) k_merge_front(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, MergeWork w, u64 n) {
     __shared__ DevBatch sb;
@@ -1016,8 +1047,8 @@ static int run_prepare(avk_ctx *ctx, const DevBatch &db) {
 // host-synchronised bigger arenas (list D).  Every stage reads its work count from the previous stage's overflow
 // counter in device memory, so the common case needs no host round trip.
 // counters (u32): 12 |W| (clusters without a closed form), 0 search work, 1 |A|, 2 score work, 4 S1 work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
-template <class P, class F>
-static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
+template <class P, class Q, class F>
+static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, Q sort_list, F launch) {
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
     const int INF = 0x7fffffff;
@@ -1090,6 +1121,7 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, F launch) {
     u32 n_work = h[7];
     for (int t = 0; t < 2 && n_work > 0; ++t) {
         big[t].ctas = (int)std::min<u64>((u64)big[t].ctas, n_work);           // one cluster per CTA
+        if (n_work > 1 && n_work <= 4096) { sort_list((u32 *)cur, n_work); ctx->launches += 1; }
         ENSURE(ctx->arena, (size_t)big[t].ctas * big[t].warps * (size_t)big[t].arena_bytes);
         CK(cudaMemsetAsync(ctrs + 32, 0, 8, ctx->stream));
         if (getenv("AVK_DEBUG")) cudaEventRecord(ctx->dbg[0], ctx->stream);
@@ -1146,6 +1178,8 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     rc = run_compare_pipeline(ctx, n, [&](u32 *list, u32 *ctr, u32 *dense, u32 *dense_ctr) {
         k_compare_simple<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, out, c, n, list, ctr, dense, dense_ctr, ctx->dense_n);
+    }, [&](u32 *list, u32 cnt) {
+        k_sort_biggest_first<<<1, 1024, 0, ctx->stream>>>(db, list, cnt);
     }, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
         if (st.mode == MODE_COOP) {
             const int cap_ints = 26000;                                  // wavefronts up to ED 12998 stay in shared memory
