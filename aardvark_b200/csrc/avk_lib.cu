@@ -638,14 +638,29 @@ __global__ void __launch_bounds__(288) k_reduce(u64 n, const int *status, const 
     const int j = threadIdx.x;
     unsigned long long acc = 0, ok = 0, bad = 0;
     u32 mask = 0;
-    for (u64 r = blockIdx.x; r < n; r += gridDim.x) {
-        const bool good = status[r] == AVK_ST_OK;
-        if (j == 0) { if (good) { ok += 1; mask |= type_mask[r]; } else bad += 1; }
-        if (!good || j >= RED_COLS) continue;
-        const unsigned long long v = region_metrics[r * RED_COLS + j];
-        acc += v;
-        if (strat_off && v) {
-            for (u64 s = strat_off[r]; s < strat_off[r + 1]; ++s) atomicAdd(strat_totals + (u64)strat_idx[s] * RED_COLS + j, v);
+    // four regions per trip: the status loads, then the row loads, are issued together (the loop is latency-bound otherwise)
+    for (u64 r0 = blockIdx.x; r0 < n; r0 += 4ull * gridDim.x) {
+        bool good[4];
+        unsigned long long v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u64 r = r0 + (u64)k * gridDim.x;
+            good[k] = r < n && status[r] == AVK_ST_OK;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u64 r = r0 + (u64)k * gridDim.x;
+            v[k] = (good[k] && j < RED_COLS) ? region_metrics[r * RED_COLS + j] : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u64 r = r0 + (u64)k * gridDim.x;
+            if (r >= n) break;
+            if (j == 0) { if (good[k]) { ok += 1; mask |= type_mask[r]; } else bad += 1; }
+            acc += v[k];
+            if (strat_off && v[k]) {
+                for (u64 s = strat_off[r]; s < strat_off[r + 1]; ++s) atomicAdd(strat_totals + (u64)strat_idx[s] * RED_COLS + j, v[k]);
+            }
         }
     }
     if (j < RED_COLS && acc) atomicAdd(totals + j, acc);
