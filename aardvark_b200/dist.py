@@ -67,38 +67,61 @@ def _unpack(buf: np.ndarray):
     tb = 8 * abi.N_GROUPS * abi.N_METRICS
     res["totals"] = buf[o:o + tb].view(np.uint64).reshape(abi.N_GROUPS, abi.N_METRICS).copy(); o += tb
     res["totals_mask"] = int(buf[o:o + 2].view(np.uint16)[0]); o += 2
-    res["status"] = buf[o:o + 4 * n].view(np.int32).copy(); o += 4 * n
-    res["ed1"] = buf[o:o + 4 * n].view(np.uint32).copy(); o += 4 * n
-    res["ed2"] = buf[o:o + 4 * n].view(np.uint32).copy(); o += 4 * n
-    res["type_mask"] = buf[o:o + 2 * n].view(np.uint16).copy(); o += 2 * n
+    res["status"] = buf[o:o + 4 * n].view(np.int32); o += 4 * n
+    res["ed1"] = buf[o:o + 4 * n].view(np.uint32); o += 4 * n
+    res["ed2"] = buf[o:o + 4 * n].view(np.uint32); o += 4 * n
+    res["type_mask"] = buf[o:o + 2 * n].view(np.uint16); o += 2 * n
     for f in ("var_expected", "var_observed", "var_class"):
-        res[f] = buf[o:o + nv].copy(); o += nv
+        res[f] = buf[o:o + nv]; o += nv
     return res
+
+
+_STAGE = {}   # (device, nbytes) -> (pinned host staging tensor, device tensor): reused across calls
+
+
+def _staging(dev, nbytes, pinned):
+    import torch
+    key = (str(dev), int(nbytes))
+    if key not in _STAGE:
+        if len(_STAGE) > 16:
+            _STAGE.clear()
+        host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pinned)
+        _STAGE[key] = (host, torch.empty(nbytes, dtype=torch.uint8, device=dev) if dev.type == "cuda" else host)
+    return _STAGE[key]
 
 
 def gather_compare_outputs(out: CompareOutputs, n_regions: int, n_variants: int, dst: int = 0):
     """The single result gather of the multi-GPU path.  Every rank contributes its summary counters
     and per-region / per-variant arrays; rank `dst` returns the merged result (concatenated in rank ==
-    region_id order, totals summed with wrapping u64 like the reference's AddAssign), others None."""
+    region_id order, totals summed with wrapping u64 like the reference's AddAssign), others None.
+    Payloads travel through pinned staging buffers that are kept between calls."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size()
     rank = dist.get_rank()
-    backend = dist.get_backend()
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    cuda = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
     payload = _pack(out, n_regions, n_variants)
-    size = torch.tensor([payload.size], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, size)
-    max_size = int(max(int(s.item()) for s in sizes))
-    send = torch.zeros(max_size, dtype=torch.uint8, device=dev)
-    send[:payload.size] = torch.from_numpy(payload).to(dev)
-    recv = [torch.zeros(max_size, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == dst else None
-    dist.gather(send, recv, dst=dst)
-    if rank != dst:
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, torch.tensor([payload.size], dtype=torch.int64, device=dev))
+    sizes = sizes.tolist()
+    max_size = (max(sizes) + 15) & ~15
+    host, send = _staging(dev, max_size, cuda)
+    host.numpy()[:payload.size] = payload
+    if cuda:
+        send.copy_(host, non_blocking=True)
+    if rank == dst:
+        rhost, recv = _staging(dev, max_size * world, cuda)
+        dist.gather(send, list(recv.view(world, max_size).unbind(0)), dst=dst)
+        if cuda:
+            rhost.copy_(recv, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        rbuf = rhost.numpy().reshape(world, max_size)
+    else:
+        dist.gather(send, None, dst=dst)
         return None
-    parts = [_unpack(recv[r].cpu().numpy()[:int(sizes[r].item())]) for r in range(world)]
+    parts = [_unpack(rbuf[r, :sizes[r]]) for r in range(world)]
     merged = {
         "n_regions": sum(p["n_regions"] for p in parts), "n_variants": sum(p["n_variants"] for p in parts),
         "solved": sum(p["solved"] for p in parts), "errors": sum(p["errors"] for p in parts),

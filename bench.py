@@ -168,6 +168,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: aardvark_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would land there too
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ref, batch = workload(rank, args.scale)
