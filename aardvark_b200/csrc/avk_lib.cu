@@ -408,7 +408,7 @@ __device__ __forceinline__ RegionSolver<SMEM> &init_solver(const DevBatch &b, co
         s.tma_pending = 0;
         s.arena_bytes = (u32)t.arena_bytes;
         s.arena = arena;
-        s.spill_base = nullptr; s.spill_bytes = 0;
+        s.spill_base = nullptr; s.spill_bytes = 0; s.team = nullptr;
         s.wide_b0 = t.wide_b0;
         if (SMEM && t.spill_base) {
             s.spill_base = t.spill_base + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (u64)t.spill_bytes;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_compare_coop(DevBatch b, De
     if (lane == 0) {
         s.bp = &sb; s.tma_phase = 0; s.tma_pending = 0;
         s.arena_bytes = (u32)(t.arena_bytes > 0xfffffff0LL ? 0xfffffff0LL : t.arena_bytes); s.arena = arena;
-        s.spill_base = nullptr; s.spill_bytes = 0; s.wide_b0 = 0;
+        s.spill_base = nullptr; s.spill_bytes = 0; s.wide_b0 = 0; s.team = nullptr;
     }
     clear_work<false>(arena);
     if (lane == 0) *(u32 *)(uintptr_t)(arena + WK_COOP) = 1u;
@@ -542,6 +542,63 @@ __global__ void __launch_bounds__(1024) k_sort_biggest_first(DevBatch b, u32 *li
             __syncthreads();
         }
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) list[i] = 0xffffffffu - (u32)(key[i] & 0xffffffffull);
+}
+
+// ---- warp team per dense cluster ----------------------------------------------------------------------------------------
+// The clusters with many variants (list X) bound a pass: one of them is hundreds of queue pops, each of which extends up to
+// four (child, haplotype) pairs -- independent of each other -- and a lone warp issues one dependent instruction every ~9
+// cycles.  Here a team of four warps takes one cluster (two teams per CTA, 108 KB of shared memory each, cold nodes spill
+// to HBM): warp 0 of the team runs the solver and every pop's extensions are spread over the four warps (TeamBoard,
+// avk_solver.cuh).
+enum { TEAMS_PER_CTA = 2 };
+__global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, TierArgs t) {
+    __shared__ DevBatch sb;
+    __shared__ RegionSolver<true> sol2[TEAMS_PER_CTA];
+    __shared__ TeamBoard board[TEAMS_PER_CTA];
+    const int lane = lane_id(), warp = (threadIdx.x >> 5) & 3, tm = threadIdx.x >> 7;   // TEAMS_PER_CTA teams of four warps per CTA
+    if (threadIdx.x == 0) sb = b;
+    if ((threadIdx.x & 127) == 0) { board[tm].exit_ = 0; board[tm].count = 0; board[tm].bar = 1 + tm; }
+    __syncthreads();
+    RegionSolver<true> &s = sol2[tm];
+    TeamBoard &B = board[tm];
+    if (warp != 0) {                                   // helpers: one round per barrier pair until the master says stop
+        for (;;) {
+            asm volatile("bar.sync %0, 128;" ::"r"(B.bar) : "memory");
+            if (B.exit_) return;
+            s.team_exec(warp);
+            asm volatile("bar.sync %0, 128;" ::"r"(B.bar) : "memory");
+        }
+    }
+    const u32 arena = (u32)tm * (u32)t.arena_bytes;
+    if (lane == 0) {
+        s.bp = &sb; s.tma_phase = 0; s.tma_pending = 0; s.arena_bytes = (u32)t.arena_bytes; s.arena = arena;
+        s.spill_base = nullptr; s.spill_bytes = 0; s.wide_b0 = 0; s.team = &B;
+        if (t.spill_base) { s.spill_base = t.spill_base + ((u64)blockIdx.x * TEAMS_PER_CTA + tm) * (u64)t.spill_bytes; s.spill_bytes = t.spill_bytes; }
+        mbar_init(arena);
+    }
+    clear_work<true>(arena);
+    __syncwarp();
+    const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
+    for (;;) {
+        u32 idx = 0;
+        if (lane == 0) idx = atomicAdd(t.work_ctr, 1u);
+        idx = __shfl_sync(AVK_FULL, idx, 0);
+        if (idx >= n_work) break;
+        const u64 r = t.work_list[idx];
+        int rc = s.solve_compare(r, cfg, out);
+        __syncwarp();
+        if (rc == SOLVE_WORKSPACE) {
+            if (lane == 0) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
+            continue;
+        }
+        if (rc != AVK_ST_OK) zero_region_outputs(sb, out, r, false);
+        if (lane == 0) out.status[r] = rc;
+    }
+    flush_work<true>(s.arena, t.work_out);
+    __syncwarp();
+    if (lane == 0) B.exit_ = 1;
+    __syncwarp();
+    asm volatile("bar.sync %0, 128;" ::"r"(B.bar) : "memory");   // releases the helpers
 }
 
 // merge, stage 1 of 3: per cluster validation, length prefilter, identical-lists shortcut; emits the pair tasks
@@ -1062,8 +1119,8 @@ static int run_prepare(avk_ctx *ctx, const DevBatch &db) {
 // host-synchronised bigger arenas (list D).  Every stage reads its work count from the previous stage's overflow
 // counter in device memory, so the common case needs no host round trip.
 // counters (u32): 12 |W| (clusters without a closed form), 0 search work, 1 |A|, 2 score work, 4 S1 work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
-template <class P, class Q, class F>
-static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, Q sort_list, F launch) {
+template <class P, class T, class Q, class F>
+static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, T team, Q sort_list, F launch) {
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
     const int INF = 0x7fffffff;
@@ -1102,7 +1159,11 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, Q sort_list, F la
     // maximum shared-memory carveout; kernels of different streams do not take over an SM otherwise: tools/overlap_probe.cu.)
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
-    fused27(LX, 17, 4, 0, ctx->stream);                                                           // X -> B
+    {
+        TierArgs a = args(LX, 17, 4, LB, 5, 108 * 1024, nullptr);
+        a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = (u32)spill_warp;
+        team(a, sm);                                                                              // X -> B  (one warp team per cluster)
+    }
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
     launch(SEARCH, args(LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr), (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8), ctx->side[0]);   // W -> blobs, rejects -> A
     launch(SCORE, args(LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);    // rejects -> A2
@@ -1193,6 +1254,14 @@ static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool wan
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     rc = run_compare_pipeline(ctx, n, [&](u32 *list, u32 *ctr, u32 *dense, u32 *dense_ctr) {
         k_compare_simple<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, out, c, n, list, ctr, dense, dense_ctr, ctx->dense_n);
+    }, [&](const TierArgs &a, int ctas) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_compare_team, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+            cudaFuncSetAttribute(k_compare_team, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            configured = true;
+        }
+        k_compare_team<<<ctas, 128 * TEAMS_PER_CTA, TEAMS_PER_CTA * (size_t)a.arena_bytes, ctx->stream>>>(db, out, c, a);
     }, [&](u32 *list, u32 cnt) {
         k_sort_biggest_first<<<1, 1024, 0, ctx->stream>>>(db, list, cnt);
     }, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {

@@ -88,6 +88,18 @@ static __device__ __forceinline__ bool type_supported(int t) {   // SUPPORTED_VA
            t == AVK_VT_TR_CONTRACTION || t == AVK_VT_TR_EXPANSION || t == AVK_VT_SV_DELETION || t == AVK_VT_SV_INSERTION;
 }
 
+// Job board of a warp team (k_compare_team): the master warp runs the solver; the independent pieces of one queue pop --
+// the two haplotypes of each child node (optimize_sequences), the two children (optimize_gt_alleles) -- are executed by
+// up to four warps at once, a named barrier on either side of a round.
+struct TeamBoard {
+    int kind;        // 0: opt_extend_hap(nb, h, rec, alt, sync, finalize); 1: ex_extend(nb, oi, alt, err, finalize)
+    int count, exit_, finalize, sync, oi;
+    int bar;         // named barrier of this team (128 threads)
+    unsigned rec;
+    unsigned nb[4];
+    int h[4], alt[4], err[4], rc[4];
+};
+
 template <bool SMEM>
 struct RegionSolver {
     typedef Mem<SMEM> M;
@@ -98,6 +110,7 @@ struct RegionSolver {
     const DevBatch *bp;
     addr arena;           // this warp's workspace (shared-memory offset or global address)
     u32 arena_bytes;
+    TeamBoard *team;      // set: this warp is the master of a warp team (shared-memory tiers only)
     int wide_b0;          // global tiers: clusters whose edit-distance bound reaches this go on to the cooperative tier (0 = keep)
     addr ref_base;        // byte of absolute contig position p is at ref_base + p (staged window or global contig)
     addr alle_base;       // allele bytes (staged copy or the global pool)
@@ -670,6 +683,31 @@ struct RegionSolver {
         __syncwarp();
         return SOLVE_OK;
     }
+    // ---- warp team ------------------------------------------------------------------------------------------------
+    // executed by every warp of the team between the two barriers of a round; warp w takes job w
+    __device__ __forceinline__ void team_exec(int w) {
+        TeamBoard &B = *team;
+        if (w < B.count) {
+            const int rc = B.kind == 0 ? opt_extend_hap((addr)B.nb[w], B.h[w], (addr)B.rec, B.alt[w] != 0, B.sync, B.finalize != 0)
+                                       : ex_extend((addr)B.nb[w], B.oi, B.alt[w] != 0, B.err[w] != 0, B.finalize != 0);
+            if (lane_id() == 0) B.rc[w] = rc;
+        }
+    }
+    // master warp: the board is filled (by lane 0, before); run one round
+    __device__ __forceinline__ void team_sync() const { asm volatile("bar.sync %0, 128;" ::"r"(team->bar) : "memory"); }
+    __device__ __noinline__ void team_round() {
+        __syncwarp();
+        team_sync();
+        team_exec(0);
+        team_sync();
+    }
+    // second half of opt_extend: record the alleles, return the node's new cost
+    __device__ __forceinline__ u32 opt_commit(addr nb, int oi, bool a1_alt, bool a2_alt) {
+        __syncwarp();
+        if (lane_id() == 0) { ST8(nb + ON_HDR + oi, (a1_alt ? 1 : 0) | (a2_alt ? 2 : 0)); ST32(nb + ON_DEPTH, oi + 1); }
+        __syncwarp();
+        return opt_cost(nb);
+    }
     // ComparisonNode::extend_variant :443-451 followed by the push; returns the node's new cost via *cost
     __device__ __noinline__ int opt_extend(addr nb, int oi, bool a1_alt, bool a2_alt, u32 *cost) {
         const addr rec = vi(oi);
@@ -734,10 +772,21 @@ struct RegionSolver {
             if (lane == 0) ST32(bucket + 4 * oi, bc + 1);
             __syncwarp();
             if (oi == n) {                                                     // :227-247
+                if (SMEM && team) {                                            // both haplotypes at once
+                    if (lane == 0) {
+                        TeamBoard &B = *team;
+                        B.kind = 0; B.count = 2; B.finalize = 1; B.rec = 0; B.sync = 0;
+                        B.nb[0] = B.nb[1] = (unsigned)nb; B.h[0] = 0; B.h[1] = 1; B.alt[0] = B.alt[1] = 0;
+                    }
+                    team_round();
+                    if (team->rc[0]) return team->rc[0];
+                    if (team->rc[1]) return team->rc[1];
+                } else {
                 int rc = opt_extend_hap(nb, 0, 0, false, 0, true);
                 if (rc) return rc;
                 rc = opt_extend_hap(nb, 1, 0, false, 0, true);
                 if (rc) return rc;
+                }
                 const u32 c = opt_cost(nb);
                 if (c < best) { best = c; nres = 0; }
                 if (c == best) {
@@ -773,6 +822,31 @@ struct RegionSolver {
             }
             // child order: (REF, ALT) then (ALT, REF) for a split; the single fixed orientation otherwise
             // (phased truth het :294-312, hom-alt :313-327) keeps the node id.
+            if (SMEM && team) {                                                // all haplotype extensions of this pop at once
+                const int nk = two ? 2 : 1;
+                if (lane == 0) {
+                    TeamBoard &B = *team;
+                    B.kind = 0; B.count = 2 * nk; B.finalize = 0; B.rec = (unsigned)vi(oi); B.sync = sync_pos(oi);
+                    for (int k = two ? 0 : 1, q = 0; k < 2; ++k, ++q) {
+                        const int sl = (two && k == 0) ? s2 : s;
+                        bool a1, a2;
+                        if (two) { a1 = k == 1; a2 = k == 0; }
+                        else if (het) { a1 = (z == AVK_ZYG_PHASED_HET10); a2 = !a1; }
+                        else { a1 = true; a2 = true; }
+                        B.nb[2 * q] = B.nb[2 * q + 1] = (unsigned)node(sl);
+                        B.h[2 * q] = 0; B.h[2 * q + 1] = 1; B.alt[2 * q] = a1; B.alt[2 * q + 1] = a2;
+                    }
+                }
+                team_round();
+#pragma unroll 1
+                for (int q = 0; q < 2 * nk; ++q) if (team->rc[q]) return team->rc[q];
+#pragma unroll 1
+                for (int k = two ? 0 : 1, q = 0; k < 2; ++k, ++q) {
+                    const int sl = (two && k == 0) ? s2 : s;
+                    const u32 c = opt_commit(node(sl), oi, team->alt[2 * q] != 0, team->alt[2 * q + 1] != 0);
+                    if (!push(((u64)c << 32) | LD32(node(sl) + ON_ID), sl)) return SOLVE_WORKSPACE;
+                }
+            } else {
 #pragma unroll 1
             for (int k = two ? 0 : 1; k < 2; ++k) {
                 const int sl = (two && k == 0) ? s2 : s;
@@ -784,6 +858,7 @@ struct RegionSolver {
                 const int rc = opt_extend(node(sl), oi, a1, a2, &c);
                 if (rc) return rc;
                 if (!push(((u64)c << 32) | LD32(node(sl) + ON_ID), sl)) return SOLVE_WORKSPACE;
+            }
             }
         }
         n_res = nres;
@@ -926,10 +1001,19 @@ struct RegionSolver {
                 __syncwarp();
                 next_id += do_alt ? 2 : 1;
             }
+            if (SMEM && team && do_alt) {                                      // both children at once
+                if (lane == 0) {
+                    TeamBoard &B = *team;
+                    B.kind = 1; B.count = 2; B.finalize = 0; B.oi = oi;
+                    B.nb[0] = (unsigned)node(s); B.alt[0] = 0; B.err[0] = is_alt;
+                    B.nb[1] = (unsigned)node(s_alt); B.alt[1] = 1; B.err[1] = 0;
+                }
+                team_round();
+            }
 #pragma unroll 1
             for (int k = 0; k < (do_alt ? 2 : 1); ++k) {
                 const int sl = k ? s_alt : s;
-                const int keep = ex_extend(node(sl), oi, k == 1, is_alt && k == 0, false);
+                const int keep = (SMEM && team && do_alt) ? team->rc[k] : ex_extend(node(sl), oi, k == 1, is_alt && k == 0, false);
                 if (keep < 0) return keep;
                 if (keep) { if (!push(ex_key(node(sl)), sl)) return SOLVE_WORKSPACE; } else free_slot(sl);
             }

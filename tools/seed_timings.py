@@ -6,7 +6,7 @@ from aardvark_b200.lib import Solver
 from aardvark_b200.types import CompareConfig
 s = Solver(0)
 cfg = CompareConfig(enable_sequences=False)
-for seed in range(20, 28):
+for seed in ([int(x) for x in sys.argv[1:]] or range(20, 28)):
     ref, b = synth.workload_chr20(1.0, seed)
     s.set_reference([ref]); s.upload(b)
     for _ in range(4): s.run_resident(cfg)
