@@ -61,6 +61,12 @@ template <> struct Mem<false> {
 enum { WK_COOP = 8, WK_CELLS = 16, WK_MATCHED = 24, WK_ALIGN = 32, WK_SPOPS = 36, WK_XPOPS = 40, ARENA_HDR = 48 };
 // WK_COOP != 0: the warp is the master warp of a k_compare_coop CTA and may hand wide wavefronts to the whole CTA
 
+// counters that several warps of a team may bump at the same time (k_compare_team): atomic adds
+template <bool SMEM>
+__device__ __forceinline__ void wk_add64(typename Mem<SMEM>::addr a, u64 v) { atomicAdd((unsigned long long *)Mem<SMEM>::p(a), (unsigned long long)v); }
+template <bool SMEM>
+__device__ __forceinline__ void wk_add32(typename Mem<SMEM>::addr a, u32 v) { atomicAdd((u32 *)Mem<SMEM>::p(a), v); }
+
 // ---- unaligned 32-bit load: two aligned loads + funnel shift ------------------------------------
 template <bool SMEM>
 __device__ __forceinline__ u32 ld4u(typename Mem<SMEM>::addr a) {
@@ -221,7 +227,7 @@ __device__ __noinline__ Reach dwfa_extend(typename Mem<SMEM>::addr wf, int ed, c
         matched = __reduce_add_sync(AVK_FULL, matched);
     }
     __syncwarp();
-    if (lane == 0) { ST64(wk + WK_CELLS, LD64(wk + WK_CELLS) + (u64)n); ST64(wk + WK_MATCHED, LD64(wk + WK_MATCHED) + (u64)matched); }
+    if (lane == 0) { wk_add64<SMEM>(wk + WK_CELLS, (u64)n); wk_add64<SMEM>(wk + WK_MATCHED, (u64)matched); }
     Reach r;
     r.max_base = mb; r.max_other = mo; r.full = full;
     return r;

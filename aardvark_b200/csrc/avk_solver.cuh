@@ -662,11 +662,11 @@ struct RegionSolver {
                 __syncwarp();
                 if (lane_id() == 0) {
                     ST32(n_wf(nb, h), nd);
-                    ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1); ST64(wk() + WK_MATCHED, LD64(wk() + WK_MATCHED) + (u64)(nd - d));
+                    wk_add64<SMEM>(wk() + WK_CELLS, 1); wk_add64<SMEM>(wk() + WK_MATCHED, (u64)(nd - d));
                 }
                 __syncwarp();
                 done = !finalize || T.len == Q.len;     // finalize: the diagonal is at the end of both <=> equal lengths
-                if (done && finalize && lane_id() == 0) ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1);
+                if (done && finalize && lane_id() == 0) wk_add64<SMEM>(wk() + WK_CELLS, 1);
             }
         }
         if (!done) {
@@ -678,7 +678,7 @@ struct RegionSolver {
         if (lane_id() == 0) {
             ST32(hb + H_TRP, t_rp); ST32(hb + H_QRP, q_rp); ST32(hb + H_TML, t_ml); ST32(hb + H_QML, q_ml);
             ST32(hb + H_TMR, t_mr); ST32(hb + H_QMR, q_mr); ST32(hb + H_TSK, t_sk); ST32(hb + H_QSK, q_sk); ST32(hb + H_ED, ed);
-            if (finalize) ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
+            if (finalize) wk_add32<SMEM>(wk() + WK_ALIGN, 1);
         }
         __syncwarp();
         return SOLVE_OK;
@@ -914,8 +914,8 @@ struct RegionSolver {
                                     : ((d >= T.len) || (d >= Q.len));
         __syncwarp();
         if (lane_id() == 0) {
-            ST64(wk() + WK_CELLS, LD64(wk() + WK_CELLS) + 1); ST64(wk() + WK_MATCHED, LD64(wk() + WK_MATCHED) + (u64)ext);
-            if (finalize) ST32(wk() + WK_ALIGN, LD32(wk() + WK_ALIGN) + 1);
+            wk_add64<SMEM>(wk() + WK_CELLS, 1); wk_add64<SMEM>(wk() + WK_MATCHED, (u64)ext);
+            if (finalize) wk_add32<SMEM>(wk() + WK_ALIGN, 1);
             else {
                 if (is_error) ST32(nb + XN_ERR, LD32(nb + XN_ERR) + 1);
                 ST32(nb + XN_DEPTH, oi + 1);
