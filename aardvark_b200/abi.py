@@ -26,7 +26,8 @@ M_GT, M_GT_TRUTH_FN_GT, M_GT_QUERY_FP_GT, M_HAP, M_WEIGHTED_HAP, M_BASEPAIR, M_R
 N_METRICS = 22
 N_GROUPS = 1 + N_VARIANT_TYPES
 
-ST_OK, ST_BAD_ZYGOSITY, ST_NO_RESULT, ST_TRUTH_FP, ST_TP_UNDERFLOW, ST_BAD_INPUT, ST_WORKSPACE = range(7)
+ST_OK, ST_BAD_ZYGOSITY, ST_NO_RESULT, ST_TRUTH_FP, ST_TP_UNDERFLOW, ST_BAD_INPUT, ST_WORKSPACE, ST_TIMEOUT = range(8)
+CMP_KEEP_REGION_ROWS = 1
 
 AVK_OK, AVK_ERR_INVALID, AVK_ERR_CUDA, AVK_ERR_NO_REFERENCE, AVK_ERR_OOM = 0, -1, -2, -3, -4
 
@@ -78,7 +79,7 @@ class CompareCfg(C.Structure):
         ("max_branch_factor", C.c_uint32),
         ("enable_exact_shortcut", C.c_uint32),
         ("enable_sequences", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -113,6 +114,14 @@ class CompareOut(C.Structure):
         ("seq_off", _u64p),
         ("seq_len", _u32p),
         ("seq_pool", _u8p),
+    ]
+
+
+class CompareDevView(C.Structure):
+    _fields_ = [
+        ("lo", C.c_uint64), ("n_regions", C.c_uint64), ("v_base", C.c_uint64), ("n_variants", C.c_uint64),
+        ("status", C.c_void_p), ("ed1", C.c_void_p), ("ed2", C.c_void_p), ("type_mask", C.c_void_p),
+        ("var_expected", C.c_void_p), ("var_observed", C.c_void_p), ("var_class", C.c_void_p), ("totals", C.c_void_p),
     ]
 
 

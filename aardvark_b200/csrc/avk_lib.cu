@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -67,17 +68,19 @@ __device__ __forceinline__ VSeq<false> plain_seq(const u8 *p, int n) {
 
 // alt_ed: 32 variants per warp pass; SNVs are answered by their lane, everything else is aligned
 // warp-cooperatively (prefix shortcut for pure insertions/deletions, WFA otherwise).
-__global__ void __launch_bounds__(256) k_alt_ed(DevBatch b, u64 n_variants, u32 *alt_ed, u8 *scratch, int scratch_ints,
+// Variants [v_base, v_base + n_variants) of the caller's table are resident (a contiguous bin of regions); every per-variant
+// device pointer is biased so that it is indexed with the caller's (global) variant index.
+__global__ void __launch_bounds__(256) k_alt_ed(DevBatch b, u64 v_base, u64 n_variants, u32 *alt_ed, u8 *scratch, int scratch_ints,
                                                 unsigned long long *work_out) {
     const int lane = lane_id();
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
     const u64 hdr = (u64)(uintptr_t)(scratch + warp * ((u64)scratch_ints * 4 + ARENA_HDR));
     clear_work<false>(hdr);
-    for (u64 base = warp * 32; base < n_variants; base += n_warps * 32) {
+    for (u64 base = v_base + warp * 32; base < v_base + n_variants; base += n_warps * 32) {
         const u64 v = base + lane;
         bool coop = false;
-        if (v < n_variants) {
+        if (v < v_base + n_variants) {
             const u32 l0 = b.l0[v], l1 = b.l1[v];
             if (l0 == 1 && l1 == 1) alt_ed[v] = (b.pool[b.aoff[v]] != b.pool[b.aoff[v] + 1]) ? 1u : 0u;
             else coop = true;
@@ -231,8 +234,10 @@ __global__ void __launch_bounds__(256) k_prep_fill(DevBatch b, u64 n, const u64 
 
 __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const DevCompareOut &out, u64 r, bool metrics_only) {
     const int lane = lane_id();
-    u64 *gm = out.region_metrics + r * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
-    for (int i = lane; i < AVK_N_GROUPS * AVK_N_METRICS; i += 32) gm[i] = 0;
+    if (out.region_metrics) {
+        u64 *gm = out.region_metrics + r * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
+        for (int i = lane; i < AVK_N_GROUPS * AVK_N_METRICS; i += 32) gm[i] = 0;
+    }
     if (!metrics_only) {
         const u64 v0 = b.var_off[r * 2], v1 = b.var_off[r * 2 + 2];
         for (u64 v = v0 + lane; v < v1; v += 32) { out.vexp[v] = 0; out.vobs[v] = 0; out.vcls[v] = AVK_CLASS_UNKNOWN; }
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
         bool simple = false;
         int nvar = 0, npairs = 0;
         u32 gv[4] = {0, 0, 0, 0}, cp[2] = {0, 0}, vtype = 0;
-        u32 s_c = 0, s_wT = 0, s_wQ = 0, s_X = 0, s_rT = 0, s_rQ = 0;   // sums over the pairs, each weighted by its ALT copies
+        u64 s_c = 0, s_wT = 0, s_wQ = 0, s_X = 0, s_rT = 0, s_rQ = 0;   // sums over the pairs, each weighted by its ALT copies
         if (r < n) {
             const u8 *dig = b.digest + b.digest_off[r];
             const int4 h = *(const int4 *)dig;                         // status, N, nT, nQ
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
                     else if (anchored) X = (t0.y == 1 ? t0.z : t0.y) - 1u;
                     ok = ok && X != 0 && t1.y >= X && q1.y >= X;
                     gv[2 * m] = t1.z; gv[2 * m + 1] = q1.z; cp[m] = cT; vtype = ty; prev_pos = t0.x;
-                    s_c += cT; s_wT += cT * t1.x; s_wQ += cT * q1.x; s_X += cT * X; s_rT += cT * t1.y; s_rQ += cT * q1.y;
+                    s_c += cT; s_wT += (u64)cT * t1.x; s_wQ += (u64)cT * q1.x; s_X += (u64)cT * X; s_rT += (u64)cT * t1.y; s_rQ += (u64)cT * q1.y;
                 }
                 simple = ok;
                 npairs = M;
@@ -334,15 +339,45 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
                 out.vexp[gv[2 * m + 1]] = (u8)cp[m]; out.vobs[gv[2 * m + 1]] = (u8)cp[m]; out.vcls[gv[2 * m + 1]] = AVK_CLASS_TP;
             }
         }
-        // metric rows [13][22], written by the whole warp per cluster: joint row == the (single) type's row, the rest zero
-        u32 todo = __ballot_sync(AVK_FULL, simple);
+        // summary counters (in-kernel totals): one warp reduction per variant type present among this warp's closed-form
+        // clusters; the joint row of such a cluster equals its (single) type's row
+        if (out.tot_slots) {
+            unsigned long long *slot = out.tot_slots + (size_t)(blockIdx.x & (TOT_SLOTS - 1)) * TOT_STRIDE;
+            u32 left = __ballot_sync(AVK_FULL, simple);
+            while (left) {
+                const u32 ty = __shfl_sync(AVK_FULL, vtype, __ffs(left) - 1);
+                const bool in = simple && vtype == ty;
+                const u32 same = __ballot_sync(AVK_FULL, in);
+                left &= ~same;
+                unsigned long long v[7] = {(unsigned long long)npairs, (unsigned long long)s_c, (unsigned long long)s_wT, (unsigned long long)s_wQ,
+                                           2ull * s_X, 2ull * s_rT, 2ull * s_rQ};
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    if (!in) v[k] = 0;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(AVK_FULL, v[k], o);
+                }
+                if (lane < 2) {                                          // lane 0: joint row, lane 1: the type's row
+                    unsigned long long *g = slot + (lane == 0 ? 0 : (1 + ty) * AVK_N_METRICS);
+                    atomicAdd(g + AVK_M_GT, v[0]); atomicAdd(g + AVK_M_GT + 2, v[0]);
+                    atomicAdd(g + AVK_M_HAP, v[1]); atomicAdd(g + AVK_M_HAP + 2, v[1]);
+                    atomicAdd(g + AVK_M_WEIGHTED_HAP, v[2]); atomicAdd(g + AVK_M_WEIGHTED_HAP + 2, v[3]);
+                    atomicAdd(g + AVK_M_BASEPAIR, v[4]); atomicAdd(g + AVK_M_BASEPAIR + 2, v[4]);
+                    atomicAdd(g + AVK_M_RECORD_BP, v[5]); atomicAdd(g + AVK_M_RECORD_BP + 2, v[6]);
+                    if (lane == 0) { atomicAdd(slot + TOT_SOLVED, (unsigned long long)__popc(same)); atomicOr(slot + TOT_MASK, (unsigned long long)supported); }
+                }
+            }
+        }
+        // metric rows [13][22] (only when the caller wants per-region rows or strata), written by the whole warp per
+        // cluster: joint row == the (single) type's row, the rest zero
+        u32 todo = out.region_metrics ? __ballot_sync(AVK_FULL, simple) : 0u;
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
-            const u64 vM = (u64)__shfl_sync(AVK_FULL, npairs, src), vc = __shfl_sync(AVK_FULL, s_c, src);
-            const u64 vwT = __shfl_sync(AVK_FULL, s_wT, src), vwQ = __shfl_sync(AVK_FULL, s_wQ, src);
-            const u64 vrT = __shfl_sync(AVK_FULL, s_rT, src), vrQ = __shfl_sync(AVK_FULL, s_rQ, src);
-            const u64 vX = __shfl_sync(AVK_FULL, s_X, src);
+            const u64 vM = (u64)__shfl_sync(AVK_FULL, npairs, src), vc = __shfl_sync(AVK_FULL, (unsigned long long)s_c, src);
+            const u64 vwT = __shfl_sync(AVK_FULL, (unsigned long long)s_wT, src), vwQ = __shfl_sync(AVK_FULL, (unsigned long long)s_wQ, src);
+            const u64 vrT = __shfl_sync(AVK_FULL, (unsigned long long)s_rT, src), vrQ = __shfl_sync(AVK_FULL, (unsigned long long)s_rQ, src);
+            const u64 vX = __shfl_sync(AVK_FULL, (unsigned long long)s_X, src);
             const int grow = 1 + (int)__shfl_sync(AVK_FULL, vtype, src);
             u64 *dst = out.region_metrics + (base + src) * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
 #pragma unroll 1
@@ -362,6 +397,23 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
             }
         }
     }
+}
+
+// final status of a region that ends in an error: counted as an error block (main.rs:259-262, summary.rs:161-163)
+__device__ __forceinline__ void count_error_block(const DevCompareOut &out) {
+    if (out.tot_slots) atomicAdd(out.tot_slots + (size_t)(blockIdx.x & (TOT_SLOTS - 1)) * TOT_STRIDE + TOT_ERRORS, 1ull);
+}
+
+// totals[j] = sum (type mask: OR) over the partial tables; layout [13][22] sums, type mask, solved blocks, error blocks
+__global__ void __launch_bounds__(320) k_fold_slots(const unsigned long long *slots, unsigned long long *totals) {
+    const int j = threadIdx.x;
+    if (j >= TOT_COLS + 3) return;
+    unsigned long long acc = 0;
+    for (int s = 0; s < TOT_SLOTS; ++s) {
+        const unsigned long long v = slots[(size_t)s * TOT_STRIDE + j];
+        acc = (j == TOT_MASK) ? (acc | v) : (acc + v);
+    }
+    totals[j] = acc;
 }
 
 // Work distribution of one stage.  work_ctr = work counter of this launch, fail_ctr = number of clusters
@@ -466,7 +518,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_compare(DevBatch b, DevCompar
             rc = AVK_ST_WORKSPACE;
         }
         if (rc != AVK_ST_OK) zero_region_outputs(sb, out, r, false);
-        if (lane == 0) out.status[r] = rc;
+        if (lane == 0) { out.status[r] = rc; if (rc != AVK_ST_OK) count_error_block(out); }
     }
     flush_work<SMEM>(s.arena, t.work_out);
 }
@@ -507,7 +559,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_compare_coop(DevBatch b, De
             rc = AVK_ST_WORKSPACE;
         }
         if (rc != AVK_ST_OK) zero_region_outputs(sb, out, r, false);
-        if (lane == 0) out.status[r] = rc;
+        if (lane == 0) { out.status[r] = rc; if (rc != AVK_ST_OK) count_error_block(out); }
     }
     flush_work<false>(arena, t.work_out);
     coop_release_helpers();
@@ -592,7 +644,7 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
             continue;
         }
         if (rc != AVK_ST_OK) zero_region_outputs(sb, out, r, false);
-        if (lane == 0) out.status[r] = rc;
+        if (lane == 0) { out.status[r] = rc; if (rc != AVK_ST_OK) count_error_block(out); }
     }
     flush_work<true>(s.arena, t.work_out);
     __syncwarp();
@@ -757,19 +809,23 @@ struct avk_ctx {
     // batch buffers
     DevBuf region_id, contig, start, end, var_off, pos, vtype, zyg, raw, aoff, l0, l1, pool, alt_ed;
     // outputs
-    DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, strat_off, strat_idx, strat_totals,
+    DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, tot_slots, strat_off, strat_idx, strat_totals,
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx, m_rows, m_perr, m_tasks;
     // workspace
     DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, fail_x, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
-    DevBuf rb[20];   // region builder temporaries
+    DevBuf rb[24];   // region builder temporaries
     int dense_n = 10;   // clusters with at least this many variants start in the fused dense-cluster stage (tuning: AVK_DENSE_N)
-    // resident batch
+    // Resident batch: regions [lo, lo + n_regions) of the caller's batch, i.e. variants [v_base, v_base + n_variants) of its
+    // variant table and bytes [p_base, ..) of its allele pool.  Per-variant device pointers are biased by these bases so
+    // that kernels index them with the caller's own (global) indices: a contiguous bin needs no re-basing on the host.
     bool have_batch = false;
-    u64 n_regions = 0, n_variants = 0;
+    bool have_result = false, result_has_rows = false;
+    u64 lo = 0, n_regions = 0, v_base = 0, n_variants = 0, p_base = 0, pool_bytes = 0;
+    u64 seq_base = 0, strat_base = 0;
     u32 n_inputs = 0;
     u32 max_allele = 1;
-    u64 pool_len = 0;
-    bool resident_has_seq = false;
+    u64 pool_len = 0;    // allele bytes the cluster digests need
+    u32 *h_pin = nullptr;   // pinned host scratch: pipeline counters read back without a blocking copy
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
     avk_work_counters last_work = {0, 0, 0, 0, 0};
@@ -778,6 +834,10 @@ struct avk_ctx {
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, dbg[3] = {nullptr, nullptr, nullptr};
     float tier_ms[3] = {0, 0, 0};
+    // test knobs (environment): shrink the workspace tiers so that small inputs exercise the last-resort paths
+    long long coop_arena0 = 256LL << 20, coop_arena1 = 2048LL << 20;
+    int coop_cap_ints = 26000;
+    int wide_b0 = 256;
 };
 
 static int ensure(avk_ctx *ctx, DevBuf &b, size_t bytes) {
@@ -812,6 +872,29 @@ static int upload(avk_ctx *ctx, DevBuf &b, const void *src, size_t bytes) {
         if (rc_ != AVK_OK) return rc_;                   \
     } while (0)
 
+enum { COOP_CAP_INTS_MAX = 26000 };   // wavefronts up to ED 12998 stay in shared memory (k_compare_coop)
+
+// Function attributes are per DEVICE: every context sets them for its own device right after cudaSetDevice (a second
+// context on another GPU of the same process needs them too).
+static int configure_kernels(avk_ctx *ctx) {
+    const int big = 222 * 1024;
+#define SMEM_OPT_IN(k)                                                                            \
+    do {                                                                                          \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, big));            \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+    } while (0)
+    SMEM_OPT_IN((k_compare<true, 3, MODE_SEARCH>));
+    SMEM_OPT_IN((k_compare<true, 4, MODE_SCORE>));
+    SMEM_OPT_IN((k_compare<true, 1, MODE_FUSED>));
+    SMEM_OPT_IN(k_compare_team);
+    SMEM_OPT_IN((k_merge_pairs<true, 3>));
+    SMEM_OPT_IN((k_merge_pairs<true, 1>));
+#undef SMEM_OPT_IN
+    CK(cudaFuncSetAttribute(k_compare_coop, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(COOP_JOB_BYTES + 2 * sizeof(int) * (size_t)COOP_CAP_INTS_MAX)));
+    return AVK_OK;
+}
+
 extern "C" int avk_create(int device, avk_ctx **out) {
     if (!out) return AVK_ERR_INVALID;
     *out = nullptr;
@@ -825,8 +908,18 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (configure_kernels(ctx) != AVK_OK) {
+        fprintf(stderr, "[avk] avk_create: %s\n", ctx->err.c_str());
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return AVK_ERR_CUDA;
+    }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     if (const char *dn = getenv("AVK_DENSE_N")) ctx->dense_n = std::max(3, atoi(dn));
+    // test knobs: tiny workspace tiers so that small inputs reach the last-resort code paths (tests/test_gpu_parity.py)
+    if (const char *s = getenv("AVK_TEST_COOP_ARENA_MB")) { ctx->coop_arena0 = std::max(1LL, atoll(s)) << 20; }
+    if (const char *s = getenv("AVK_TEST_COOP_CAP_INTS")) ctx->coop_cap_ints = std::min<int>(COOP_CAP_INTS_MAX, std::max(64, atoi(s)));
+    if (const char *s = getenv("AVK_TEST_WIDE_B0")) ctx->wide_b0 = std::max(1, atoi(s));
     for (auto &e : ctx->tev) cudaEventCreate(&e);
     {
         int lo = 0, hi = 0;
@@ -837,6 +930,9 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (auto &e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : ctx->dbg) cudaEventCreate(&e);
+    if (cudaMallocHost((void **)&ctx->h_pin, 4096) != cudaSuccess) { ctx->h_pin = nullptr; cudaGetLastError(); }
+    if (!ctx->h_pin) { avk_destroy(ctx); return AVK_ERR_OOM; }
+    memset(ctx->h_pin, 0, 4096);
     *out = ctx;
     return AVK_OK;
 }
@@ -845,16 +941,23 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto &st : ctx->side) if (st) cudaStreamSynchronize(st);
     DevBuf *bufs[] = {&ctx->d_contig_ptr, &ctx->d_contig_len, &ctx->region_id, &ctx->contig, &ctx->start, &ctx->end, &ctx->var_off,
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
-                      &ctx->totals, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
+                      &ctx->totals, &ctx->tot_slots, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
                       &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
     for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->tev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_join) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->dbg) if (e) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (auto &st : ctx->side) if (st) cudaStreamDestroy(st);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -878,6 +981,67 @@ extern "C" int avk_set_reference(avk_ctx *ctx, uint32_t n_contigs, const uint8_t
     UPLOAD(ctx->d_contig_ptr, ptrs.data(), sizeof(u8 *) * n_contigs);
     UPLOAD(ctx->d_contig_len, lens, sizeof(u64) * n_contigs);
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_result = false;
+    return AVK_OK;
+}
+
+// ---- host-side batch validation ---------------------------------------------------------------------------------------
+// Everything the kernels use as a memory offset is checked here, before anything is uploaded: var_off monotone and inside
+// the variant table, allele ranges inside the pool, allele lengths <= 16 MiB (the digest and workspace sizes are 32-bit),
+// stratum indices < n_strata, seq_off monotone.  A violation is a whole-batch AVK_ERR_INVALID; what the reference would
+// report per region (window outside the contig, unsorted list, empty allele, bad enum code) stays a per-region
+// AVK_ST_BAD_INPUT decided on the device.  The scan also yields what sizes the device workspaces (longest allele, allele
+// bytes, the pool range the bin touches); it runs on a few host threads for WGS-sized tables.
+struct BinScan {
+    u64 lo = 0, hi = 0, v0 = 0, v1 = 0, p0 = 0, p1 = 0, sum_alle = 0;
+    u32 max_allele = 1;
+};
+
+static int scan_bin(avk_ctx *ctx, const avk_region_batch *b, u64 lo, u64 hi, BinScan &sc) {
+    const u64 K = b->n_inputs;
+    const avk_variant_table &t = b->variants;
+    sc.lo = lo; sc.hi = hi;
+    if (hi == lo) return AVK_OK;
+    const u64 *vo = b->var_off;
+    sc.v0 = vo[lo * K]; sc.v1 = vo[hi * K];
+    if (sc.v0 > sc.v1 || sc.v1 > t.n_variants) { ctx->err = "var_off outside the variant table"; return AVK_ERR_INVALID; }
+    const u64 nv = sc.v1 - sc.v0, nr = (hi - lo) * K;
+    if (nv && (!t.position || !t.variant_type || !t.zygosity || !t.raw_allele_space || !t.allele_off || !t.a0_len || !t.a1_len || !t.allele_pool)) {
+        ctx->err = "null variant arrays";
+        return AVK_ERR_INVALID;
+    }
+    const int nt = (int)std::min<u64>(8, std::max<u64>(1, (nv + nr) / 500000));
+    struct Part { u64 p0 = ~0ull, p1 = 0, sum = 0; u32 mx = 1; int bad = 0; };
+    std::vector<Part> parts(nt);
+    auto work = [&](int ti) {
+        Part &P = parts[ti];
+        for (u64 i = lo * K + nr * ti / nt, e = lo * K + nr * (ti + 1) / nt; i < e; ++i) if (vo[i] > vo[i + 1]) P.bad = 1;
+        const u64 pool_len = t.allele_pool_len;
+        for (u64 v = sc.v0 + nv * ti / nt, e = sc.v0 + nv * (ti + 1) / nt; v < e; ++v) {
+            const u64 a = t.allele_off[v], l0 = t.a0_len[v], l1 = t.a1_len[v];
+            if (l0 > (1u << 24) || l1 > (1u << 24)) { P.bad = 2; continue; }
+            if (a + l0 + l1 > pool_len) { P.bad = 3; continue; }
+            P.p0 = std::min(P.p0, a); P.p1 = std::max(P.p1, a + l0 + l1);
+            P.sum += l0 + l1;
+            P.mx = std::max(P.mx, (u32)std::max(l0, l1));
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int ti = 0; ti < nt; ++ti) th.emplace_back(work, ti);
+        for (auto &x : th) x.join();
+    }
+    u64 p0 = ~0ull, p1 = 0;
+    for (const Part &P : parts) {
+        if (P.bad) {
+            ctx->err = P.bad == 1 ? "var_off is not monotone" : (P.bad == 2 ? "allele longer than 16 MiB" : "allele range outside the allele pool");
+            return AVK_ERR_INVALID;
+        }
+        p0 = std::min(p0, P.p0); p1 = std::max(p1, P.p1);
+        sc.sum_alle += P.sum; sc.max_allele = std::max(sc.max_allele, P.mx);
+    }
+    if (p1 > p0) { sc.p0 = p0; sc.p1 = p1; }
     return AVK_OK;
 }
 
@@ -893,62 +1057,64 @@ static int validate_batch(avk_ctx *ctx, const avk_region_batch *b, bool compare)
     return AVK_OK;
 }
 
-static int upload_batch(avk_ctx *ctx, const avk_region_batch *b) {
+// Upload regions [sc.lo, sc.hi) of the batch: a contiguous bin (the whole batch for one GPU).
+static int upload_batch(avk_ctx *ctx, const avk_region_batch *b, const BinScan &sc) {
     if (ctx->contig_bufs.empty()) { ctx->err = "avk_set_reference has not been called"; return AVK_ERR_NO_REFERENCE; }
-    const u64 n = b->n_regions, nv = b->variants.n_variants;
+    const u64 lo = sc.lo, n = sc.hi - sc.lo, K = b->n_inputs, v0 = sc.v0, nv = sc.v1 - sc.v0;
     const avk_variant_table &t = b->variants;
-    UPLOAD(ctx->region_id, b->region_id, 8 * n);
-    UPLOAD(ctx->contig, b->contig, 4 * n);
-    UPLOAD(ctx->start, b->start, 4 * n);
-    UPLOAD(ctx->end, b->end, 4 * n);
-    UPLOAD(ctx->var_off, b->var_off, 8 * (n * b->n_inputs + 1));
-    UPLOAD(ctx->pos, t.position, 4 * nv);
-    UPLOAD(ctx->vtype, t.variant_type, nv);
-    UPLOAD(ctx->zyg, t.zygosity, nv);
-    UPLOAD(ctx->raw, t.raw_allele_space, 4 * nv);
-    UPLOAD(ctx->aoff, t.allele_off, 4 * nv);
-    UPLOAD(ctx->l0, t.a0_len, 4 * nv);
-    UPLOAD(ctx->l1, t.a1_len, 4 * nv);
-    UPLOAD(ctx->pool, t.allele_pool, t.allele_pool_len);
+    ctx->have_batch = false; ctx->have_result = false;
+    UPLOAD(ctx->contig, b->contig + lo, 4 * n);
+    UPLOAD(ctx->start, b->start + lo, 4 * n);
+    UPLOAD(ctx->end, b->end + lo, 4 * n);
+    if (n) UPLOAD(ctx->var_off, b->var_off + lo * K, 8 * (n * K + 1));
+    else { ENSURE(ctx->var_off, 8); CK(cudaMemsetAsync(ctx->var_off.p, 0, 8, ctx->stream)); }
+    UPLOAD(ctx->pos, t.position + v0, 4 * nv);
+    UPLOAD(ctx->vtype, t.variant_type + v0, nv);
+    UPLOAD(ctx->zyg, t.zygosity + v0, nv);
+    UPLOAD(ctx->raw, t.raw_allele_space + v0, 4 * nv);
+    UPLOAD(ctx->aoff, t.allele_off + v0, 4 * nv);
+    UPLOAD(ctx->l0, t.a0_len + v0, 4 * nv);
+    UPLOAD(ctx->l1, t.a1_len + v0, 4 * nv);
+    UPLOAD(ctx->pool, t.allele_pool + sc.p0, sc.p1 - sc.p0);
     ENSURE(ctx->alt_ed, 4 * nv);
-    u32 mx = 1;
-    u64 sum_alle = 0;
-    for (u64 i = 0; i < nv; ++i) {
-        mx = std::max(mx, std::max(t.a0_len[i], t.a1_len[i]));
-        sum_alle += (u64)std::min(t.a0_len[i], 1u << 24) + (u64)std::min(t.a1_len[i], 1u << 24);
-    }
-    ctx->max_allele = mx;
-    ctx->pool_len = sum_alle;   // bytes the cluster digests need for alleles
-    ctx->n_regions = n; ctx->n_variants = nv; ctx->n_inputs = b->n_inputs;
+    ctx->max_allele = sc.max_allele;
+    ctx->pool_len = sc.sum_alle;
+    ctx->lo = lo; ctx->n_regions = n; ctx->v_base = v0; ctx->n_variants = nv; ctx->p_base = sc.p0; ctx->pool_bytes = sc.p1 - sc.p0;
+    ctx->n_inputs = b->n_inputs;
     ctx->have_batch = true;
     return AVK_OK;
 }
 
+// device pointer biased so that element `base` of the caller's array is the first resident element
+template <class T>
+static inline T *biased(const DevBuf &b, u64 base) { return (T *)((uintptr_t)b.p - (uintptr_t)(base * sizeof(T))); }
+
 static DevBatch dev_batch(avk_ctx *ctx) {
     DevBatch d;
+    const u64 vb = ctx->v_base;
     d.n_regions = ctx->n_regions; d.n_inputs = ctx->n_inputs;
-    d.region_id = (const u64 *)ctx->region_id.p; d.contig = (const u32 *)ctx->contig.p;
+    d.region_id = nullptr; d.contig = (const u32 *)ctx->contig.p;
     d.start = (const u32 *)ctx->start.p; d.end = (const u32 *)ctx->end.p; d.var_off = (const u64 *)ctx->var_off.p;
-    d.pos = (const u32 *)ctx->pos.p; d.vtype = (const u8 *)ctx->vtype.p; d.zyg = (const u8 *)ctx->zyg.p;
-    d.raw = (const u32 *)ctx->raw.p; d.aoff = (const u32 *)ctx->aoff.p; d.l0 = (const u32 *)ctx->l0.p; d.l1 = (const u32 *)ctx->l1.p;
-    d.pool = (const u8 *)ctx->pool.p;
+    d.pos = biased<const u32>(ctx->pos, vb); d.vtype = biased<const u8>(ctx->vtype, vb); d.zyg = biased<const u8>(ctx->zyg, vb);
+    d.raw = biased<const u32>(ctx->raw, vb); d.aoff = biased<const u32>(ctx->aoff, vb); d.l0 = biased<const u32>(ctx->l0, vb);
+    d.l1 = biased<const u32>(ctx->l1, vb);
+    d.pool = biased<const u8>(ctx->pool, ctx->p_base);
     d.contig_ptr = (const u8 *const *)ctx->d_contig_ptr.p; d.contig_len = (const u64 *)ctx->d_contig_len.p;
     d.n_contigs = (u32)ctx->contig_lens.size();
-    d.alt_ed = (const u32 *)ctx->alt_ed.p;
+    d.alt_ed = biased<const u32>(ctx->alt_ed, vb);
     d.digest = (const u8 *)ctx->digest.p;
     d.digest_off = (const u64 *)ctx->digest_offs.p;
     return d;
 }
 
-// counters layout (u32): [0] work counter, [1] fail count A, [2] fail count B
 static int run_alt_ed(avk_ctx *ctx, const DevBatch &db) {
     if (ctx->n_variants == 0) return AVK_OK;
     const int blocks = ctx->sm_count * 4, threads = 256;
     const int warps = blocks * threads / 32;
     const int scratch_ints = (2 * (int)ctx->max_allele + 8 + 3) / 4 * 4;
     ENSURE(ctx->scratch, (size_t)warps * ((size_t)scratch_ints * 4 + ARENA_HDR));
-    k_alt_ed<<<blocks, threads, 0, ctx->stream>>>(db, ctx->n_variants, (u32 *)ctx->alt_ed.p, (u8 *)ctx->scratch.p, scratch_ints,
-                                                   (unsigned long long *)ctx->work_ctr.p);
+    k_alt_ed<<<blocks, threads, 0, ctx->stream>>>(db, ctx->v_base, ctx->n_variants, biased<u32>(ctx->alt_ed, ctx->v_base), (u8 *)ctx->scratch.p,
+                                                   scratch_ints, (unsigned long long *)ctx->work_ctr.p);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return AVK_OK;
@@ -975,8 +1141,8 @@ struct Stage {
     int n_lo, n_hi;        // cluster-size class (stages scanning all regions)
 };
 
-// `pre(ctrs)` runs after the counters are cleared and before the first stage; when `first_ctr` >= 0 the first stage takes
-// its work count from that counter (written by `pre`) instead of n, which is then only an upper bound.
+// Merge pipeline driver.  `pre(ctrs)` runs after the counters are cleared and before the first stage; when `first_ctr` >= 0
+// the first stage takes its work count from that counter (written by `pre`) instead of n, which is then only an upper bound.
 template <class P, class F>
 static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, P pre, int first_ctr, F launch) {
     if (n == 0) return AVK_OK;
@@ -994,19 +1160,8 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, P p
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     pre(ctrs);
     int ev = 1;
-    bool forked = false, joined = false;
     for (size_t i = 0; i < stages.size(); ++i) {
         const Stage &st = stages[i];
-        cudaStream_t strm = st.stream == 0 ? ctx->stream : ctx->side[st.stream - 1];
-        if (st.stream != 0 && !forked) {   // side streams start after everything queued so far on the main stream
-            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-            for (int k = 0; k < 2; ++k) CK(cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0));
-            forked = true;
-        }
-        if (forked && !joined && st.in_list >= 0) {   // first chained stage: wait for the concurrent group
-            for (int k = 0; k < 2; ++k) { CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); }
-            joined = true;
-        }
         TierArgs a = {};
         a.work_list = st.in_list < 0 ? nullptr : fail_lists[st.in_list];
         a.n_work_ptr = st.in_list < 0 ? (first_ctr >= 0 ? ctrs + first_ctr : nullptr) : ctrs + st.in_ctr;
@@ -1024,28 +1179,25 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, P p
         a.n_lo = st.n_lo; a.n_hi = st.n_hi;
         int ctas = st.ctas;
         if (st.in_list < 0) ctas = (int)std::min<u64>((u64)ctas, (n + st.warps - 1) / st.warps);
-        launch(st, a, ctas, strm);
+        launch(st, a, ctas, ctx->stream);
         ctx->launches += 1;
         CK(cudaGetLastError());
-        if (ev < 3 && st.stream == 0 && stages[i].mode != MODE_SEARCH && (i + 1 < stages.size())) CK(cudaEventRecord(ctx->tev[ev++], ctx->stream));
-    }
-    if (forked && !joined) {
-        for (int k = 0; k < 2; ++k) { CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); }
+        if (ev < 3 && (i + 1 < stages.size())) CK(cudaEventRecord(ctx->tev[ev++], ctx->stream));
     }
     while (ev < 4) CK(cudaEventRecord(ctx->tev[ev++], ctx->stream));
     const Stage &lastst = stages.back();
-    u32 host_ctrs[16];
-    CK(cudaMemcpyAsync(host_ctrs, ctrs, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin, ctrs, 64, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    const u32 *host_ctrs = ctx->h_pin;
     for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
     {   // diagnostics: overflow counts of the (up to) three chained tiers
         int k = 0;
-        for (const Stage &st : stages) if (st.mode != MODE_SEARCH && k < 3) ctx->tier_fail[k++] = host_ctrs[st.fail_ctr];
+        for (const Stage &st : stages) if (k < 3) ctx->tier_fail[k++] = host_ctrs[st.fail_ctr];
         while (k < 3) ctx->tier_fail[k++] = 0;
     }
     u32 n_work = host_ctrs[lastst.fail_ctr];
     int cur_list = lastst.fail_list;
-    // rare: clusters that overflow 2 MB per warp; host-synchronised escalation
+    // rare: pair searches that overflow 2 MB per warp; host-synchronised escalation
     const Stage big[2] = {{MODE_FUSED, false, 1, 64LL << 20, (sm + 7) / 8, 8, 0, 0, 0, 0, 0, 0, 0, 0x7fffffff}, {MODE_FUSED, false, 1, 2048LL << 20, 1, 8, 0, 0, 0, 0, 0, 0, 0, 0x7fffffff}};
     for (int t = 0; t < 2 && n_work > 0; ++t) {
         ENSURE(ctx->arena, (size_t)big[t].ctas * big[t].warps * (size_t)big[t].arena_bytes);
@@ -1066,36 +1218,22 @@ static int run_stages(avk_ctx *ctx, u64 n, const std::vector<Stage> &stages, P p
         launch(big[t], a, big[t].ctas, ctx->stream);
         ctx->launches += 1;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(host_ctrs, ctrs + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pin, ctrs + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        n_work = host_ctrs[1];
+        n_work = ctx->h_pin[1];
         cur_list ^= 1;
     }
     return AVK_OK;
 }
 
 template <bool SMEM, int MIN_CTAS, int MODE>
-static void launch_compare(avk_ctx *ctx, const DevBatch &db, const DevCompareOut &out, const avk_compare_cfg &c, const TierArgs &a, int ctas, int warps, cudaStream_t strm) {
+static void launch_compare(const DevBatch &db, const DevCompareOut &out, const avk_compare_cfg &c, const TierArgs &a, int ctas, int warps, cudaStream_t strm) {
     const size_t smem = SMEM ? (size_t)a.arena_bytes * warps : 0;
-    // function attributes are set once per instantiation (the call may synchronise the device)
-    static size_t configured = 0;
-    if (configured < smem + 1) {
-        if (SMEM) {
-            cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-            cudaFuncSetAttribute(k_compare<SMEM, MIN_CTAS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        }
-        configured = 228 * 1024;
-    }
     k_compare<SMEM, MIN_CTAS, MODE><<<ctas, 32 * warps, smem, strm>>>(db, out, c, a);
 }
 template <bool SMEM, int MIN_CTAS>
-static void launch_merge_pairs(avk_ctx *ctx, const DevBatch &db, const avk_merge_cfg &c, const TierArgs &a, const MergeWork &w, int ctas, int warps, cudaStream_t strm) {
+static void launch_merge_pairs(const DevBatch &db, const avk_merge_cfg &c, const TierArgs &a, const MergeWork &w, int ctas, int warps, cudaStream_t strm) {
     const size_t smem = SMEM ? (size_t)a.arena_bytes * warps : 0;
-    static bool configured = false;
-    if (!configured) {
-        if (SMEM) cudaFuncSetAttribute(k_merge_pairs<SMEM, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-        configured = true;
-    }
     k_merge_pairs<SMEM, MIN_CTAS><<<ctas, 32 * warps, smem, strm>>>(db, c, a, w);
 }
 
@@ -1114,45 +1252,66 @@ static int run_prepare(avk_ctx *ctx, const DevBatch &db) {
     return AVK_OK;
 }
 
-// The compare pipeline (one stream): search kernel (all clusters) -> score kernel -> fused 27 KB shared-memory stage
-// for the clusters that did not fit the common tier (list A) -> fused 2 MB global-arena stage (list B) -> rare
-// host-synchronised bigger arenas (list D).  Every stage reads its work count from the previous stage's overflow
-// counter in device memory, so the common case needs no host round trip.
-// counters (u32): 12 |W| (clusters without a closed form), 0 search work, 1 |A|, 2 score work, 4 S1 work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
-template <class P, class T, class Q, class F>
-static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, T team, Q sort_list, F launch) {
+struct CompareRun {           // what one compare pass needs to know to launch, finish and (rarely) re-finish
+    DevBatch db;
+    DevCompareOut out;
+    avk_compare_cfg cfg;
+    bool strata = false;
+    const u64 *strat_off = nullptr;
+    const u32 *strat_idx = nullptr;
+    u32 n_strata = 0;
+};
+
+static void launch_stage(avk_ctx *ctx, const CompareRun &R, const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
+    if (st.mode == MODE_COOP) {
+        const size_t smem = COOP_JOB_BYTES + 2 * sizeof(int) * (size_t)ctx->coop_cap_ints;
+        k_compare_coop<<<ctas, COOP_THREADS, smem, strm>>>(R.db, R.out, R.cfg, a, ctx->coop_cap_ints);
+    }
+    else if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(R.db, R.out, R.cfg, a, ctas, st.warps, strm);
+    else if (st.mode == MODE_SCORE) launch_compare<true, 4, MODE_SCORE>(R.db, R.out, R.cfg, a, ctas, st.warps, strm);
+    else if (st.smem) launch_compare<true, 1, MODE_FUSED>(R.db, R.out, R.cfg, a, ctas, st.warps, strm);
+    else launch_compare<false, 1, MODE_FUSED>(R.db, R.out, R.cfg, a, ctas, st.warps, strm);
+}
+
+static TierArgs tier_args(avk_ctx *ctx, const u32 *list, int in_ctr, int work_ctr, u32 *fail_list, int fail_ctr, long long arena_bytes, u8 *garena) {
+    u32 *ctrs = (u32 *)ctx->counters.p;
+    TierArgs a = {};
+    a.work_list = list; a.n_work_ptr = list ? ctrs + in_ctr : nullptr; a.n_work = (u32)ctx->n_regions;
+    a.work_ctr = ctrs + work_ctr; a.fail_ctr = ctrs + fail_ctr; a.fail_list = fail_list;
+    a.arena_base = garena; a.arena_bytes = arena_bytes; a.last_tier = 0;
+    a.work_out = (unsigned long long *)ctx->work_ctr.p; a.blobs = (u8 *)ctx->blobs.p; a.n_lo = 0; a.n_hi = 0x7fffffff;
+    a.spill_base = nullptr; a.spill_bytes = 0;
+    return a;
+}
+
+// The compare pipeline: closed-form kernel (all clusters) -> warp-team stage for the dense list X on the main stream,
+// and beside it on a low-priority side stream: search kernel -> score kernel -> fused 27 KB shared-memory stage for the
+// clusters that did not fit the common tier (list A); then the fused 2 MB global-arena stage (list B).  Every stage reads
+// its work count from an earlier stage's counter in device memory and NOTHING here waits for the device: the counters
+// travel back with the results (compare_finish), and only if list D (SV-sized clusters) turns out non-empty does the host
+// launch the cooperative tiers afterwards.
+// counters (u32): 12 |W| (clusters without a closed form), 17 |X| dense, 0 search work, 1 |A|, 2 score work, 15 |A2|, 4 team work,
+// 18 S1 work, 16 S1' work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
+static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
+    const u64 n = ctx->n_regions;
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
-    const int INF = 0x7fffffff;
     ENSURE(ctx->fail_a, 4 * n); ENSURE(ctx->fail_b, 4 * n); ENSURE(ctx->fail_c, 4 * n); ENSURE(ctx->fail_d, 4 * n); ENSURE(ctx->fail_h, 4 * n); ENSURE(ctx->fail_w, 4 * n); ENSURE(ctx->fail_x, 4 * n);
     ENSURE(ctx->counters, 256);
     ENSURE(ctx->blobs, (size_t)n * RB_SIZE);
     u32 *ctrs = (u32 *)ctx->counters.p;
-    u32 *LA = (u32 *)ctx->fail_a.p, *LB = (u32 *)ctx->fail_b.p, *LC = (u32 *)ctx->fail_c.p, *LD = (u32 *)ctx->fail_d.p;
+    u32 *LA = (u32 *)ctx->fail_a.p, *LB = (u32 *)ctx->fail_b.p, *LD = (u32 *)ctx->fail_d.p;
     CK(cudaMemsetAsync(ctrs, 0, 256, ctx->stream));
     ENSURE(ctx->arena, (size_t)sm * 8 * (size_t)(2LL << 20));
     ENSURE(ctx->arena2, 2 * (size_t)sm * 8 * (size_t)(1u << 20));   // two fused stages may run side by side
-    auto args = [&](const u32 *list, int in_ctr, int work_ctr, u32 *fail_list, int fail_ctr, long long arena_bytes, u8 *garena) {
-        TierArgs a = {};
-        a.work_list = list; a.n_work_ptr = list ? ctrs + in_ctr : nullptr; a.n_work = (u32)n;
-        a.work_ctr = ctrs + work_ctr; a.fail_ctr = ctrs + fail_ctr; a.fail_list = fail_list;
-        a.arena_base = garena; a.arena_bytes = arena_bytes; a.last_tier = 0;
-        a.work_out = (unsigned long long *)ctx->work_ctr.p; a.blobs = (u8 *)ctx->blobs.p; a.n_lo = 0; a.n_hi = INF;
-        a.spill_base = nullptr; a.spill_bytes = 0;
-        return a;
-    };
     const Stage SEARCH = {MODE_SEARCH, true, 3, 8192, sm * 3, 8}, SCORE = {MODE_SCORE, true, 4, 5120, sm * 4, 8};
     const Stage S1 = {MODE_FUSED, true, 1, 27648, sm, 8}, G0 = {MODE_FUSED, false, 1, 2LL << 20, sm, 8};
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p, *LX = (u32 *)ctx->fail_x.p;
-    simple(LW, ctrs + 12, LX, ctrs + 17);        // closed-form clusters; >= 10 variants -> X (dense); the rest -> W
+    // closed-form clusters; >= dense_n variants -> X (dense); the rest -> W
+    k_compare_simple<<<sm * 8, 256, 0, ctx->stream>>>(R.db, R.out, R.cfg, n, LW, ctrs + 12, LX, ctrs + 17, ctx->dense_n);
     const size_t spill_warp = 1u << 20, spill_half = (size_t)sm * 8 * spill_warp;
-    auto fused27 = [&](const u32 *list, int in_ctr, int work_ctr, int half, cudaStream_t strm) {   // 8 warps x 27 KB per SM, rejects -> B
-        TierArgs a = args(list, in_ctr, work_ctr, LB, 5, S1.arena_bytes, nullptr);
-        a.spill_base = (u8 *)ctx->arena2.p + half * spill_half; a.spill_bytes = (u32)spill_warp;   // cold search nodes spill to HBM instead of restarting the cluster
-        launch(S1, a, S1.ctas, strm);
-    };
-    // A dense cluster is solved by one warp in up to ~2 ms, so the dense stage ends with a few busy warps.  It is launched
+    // A dense cluster is solved by one warp team in up to ~1 ms, so the dense stage ends with a few busy teams.  It is launched
     // first (main stream, one 216 KB CTA per SM); search, score and the fused stage for their rejects follow on a
     // lowest-priority side stream behind an event: as the dense CTAs run out of work and retire, the block scheduler fills
     // their SMs with the other kernels' CTAs, which then run in the shadow of that tail.  (All k_compare kernels ask for the
@@ -1160,136 +1319,169 @@ static int run_compare_pipeline(avk_ctx *ctx, u64 n, P simple, T team, Q sort_li
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
     {
-        TierArgs a = args(LX, 17, 4, LB, 5, 108 * 1024, nullptr);
+        TierArgs a = tier_args(ctx, LX, 17, 4, LB, 5, 108 * 1024, nullptr);
         a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = (u32)spill_warp;
-        team(a, sm);                                                                              // X -> B  (one warp team per cluster)
+        k_compare_team<<<sm, 128 * TEAMS_PER_CTA, TEAMS_PER_CTA * (size_t)a.arena_bytes, ctx->stream>>>(R.db, R.out, R.cfg, a);   // X -> B
     }
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
-    launch(SEARCH, args(LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr), (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8), ctx->side[0]);   // W -> blobs, rejects -> A
-    launch(SCORE, args(LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);    // rejects -> A2
-    fused27(LA, 1, 18, 1, ctx->side[0]);                                                          // A -> B  (did not fit the 8 KB search arena)
+    const int small_ctas = (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8);
+    launch_stage(ctx, R, SEARCH, tier_args(ctx, LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr), small_ctas, ctx->side[0]);                                         // W -> blobs, rejects -> A
+    launch_stage(ctx, R, SCORE, tier_args(ctx, LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);    // rejects -> A2
+    {
+        TierArgs a = tier_args(ctx, LA, 1, 18, LB, 5, S1.arena_bytes, nullptr);
+        a.spill_base = (u8 *)ctx->arena2.p + spill_half; a.spill_bytes = (u32)spill_warp;   // cold search nodes spill to HBM instead of restarting the cluster
+        launch_stage(ctx, R, S1, a, S1.ctas, ctx->side[0]);                                  // A -> B  (did not fit the 8 KB search arena)
+    }
     CK(cudaEventRecord(ctx->ev_join[0], ctx->side[0]));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
     CK(cudaEventRecord(ctx->tev[2], ctx->stream));
     {
-        TierArgs a = args(LA2, 15, 16, LB, 5, S1.arena_bytes, nullptr);
+        TierArgs a = tier_args(ctx, LA2, 15, 16, LB, 5, S1.arena_bytes, nullptr);
         a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;
-        launch(S1, a, S1.ctas, ctx->stream);                                                      // A2 -> B  (score kernel's rejects, rare)
+        launch_stage(ctx, R, S1, a, S1.ctas, ctx->stream);                                   // A2 -> B  (score kernel's rejects, rare)
     }
     {
-        TierArgs a = args(LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p);
-        a.wide_b0 = 256;                                                                          // SV-sized events: cooperative tier
-        launch(G0, a, G0.ctas, ctx->stream);                                                      // B -> D   (2 MB global arenas)
+        TierArgs a = tier_args(ctx, LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p);
+        a.wide_b0 = ctx->wide_b0;                                                            // SV-sized events: cooperative tier
+        launch_stage(ctx, R, G0, a, G0.ctas, ctx->stream);                                   // B -> D   (2 MB global arenas)
     }
     CK(cudaEventRecord(ctx->tev[3], ctx->stream));
     ctx->launches += 7;
     CK(cudaGetLastError());
-    u32 h[16];
-    CK(cudaMemcpyAsync(h, ctrs, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
-    ctx->tier_fail[0] = h[1]; ctx->tier_fail[1] = h[5]; ctx->tier_fail[2] = h[7];
-    // rare: clusters that overflow 2 MB per warp (list D); host-synchronised escalation
-    // (SV-sized events): one cluster per CTA, wide wavefronts advanced by the whole CTA; 256 MB arenas, then 2 GB (last resort).
-    Stage big[2] = {{MODE_COOP, false, 1, 256LL << 20, sm, 1}, {MODE_COOP, false, 1, 2048LL << 20, 16, 1}};
-    const u32 *cur = LD;
-    u32 *other = LC;
-    u32 n_work = h[7];
+    return AVK_OK;
+}
+
+// Rare: clusters that overflow 2 MB per warp or carry SV-sized events (list D): one cluster per CTA, wide wavefronts
+// advanced by the whole CTA; 256 MB arenas, then 2 GB (last resort).  Host-synchronised.
+static int run_big_tiers(avk_ctx *ctx, const CompareRun &R, u32 n_work) {
+    const int sm = ctx->sm_count;
+    u32 *ctrs = (u32 *)ctx->counters.p;
+    Stage big[2] = {{MODE_COOP, false, 1, ctx->coop_arena0, sm, 1}, {MODE_COOP, false, 1, ctx->coop_arena1, 16, 1}};
+    const u32 *cur = (u32 *)ctx->fail_d.p;
+    u32 *other = (u32 *)ctx->fail_c.p;
     for (int t = 0; t < 2 && n_work > 0; ++t) {
         big[t].ctas = (int)std::min<u64>((u64)big[t].ctas, n_work);           // one cluster per CTA
-        if (n_work > 1 && n_work <= 4096) { sort_list((u32 *)cur, n_work); ctx->launches += 1; }
+        if (n_work > 1 && n_work <= 4096) { k_sort_biggest_first<<<1, 1024, 0, ctx->stream>>>(R.db, (u32 *)cur, n_work); ctx->launches += 1; }
         ENSURE(ctx->arena, (size_t)big[t].ctas * big[t].warps * (size_t)big[t].arena_bytes);
         CK(cudaMemsetAsync(ctrs + 32, 0, 8, ctx->stream));
         if (getenv("AVK_DEBUG")) cudaEventRecord(ctx->dbg[0], ctx->stream);
-        TierArgs a = args(cur, 0, 32, other, 33, big[t].arena_bytes, (u8 *)ctx->arena.p);
+        TierArgs a = tier_args(ctx, cur, 0, 32, other, 33, big[t].arena_bytes, (u8 *)ctx->arena.p);
         a.n_work_ptr = nullptr; a.n_work = n_work; a.last_tier = t == 1;
-        launch(big[t], a, big[t].ctas, ctx->stream);
+        launch_stage(ctx, R, big[t], a, big[t].ctas, ctx->stream);
         ctx->launches += 1;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h, ctrs + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pin + 64, ctrs + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (getenv("AVK_DEBUG")) {
             float ms = 0;
             cudaEventRecord(ctx->dbg[1], ctx->stream); cudaEventSynchronize(ctx->dbg[1]); cudaEventElapsedTime(&ms, ctx->dbg[0], ctx->dbg[1]);
-            fprintf(stderr, "[avk] big tier %d (%s): %u clusters in, %u rejected, %.1f ms\n", t, t == 0 ? "cooperative, 256 MB" : "cooperative, 2 GB", n_work, h[1], ms);
+            fprintf(stderr, "[avk] big tier %d (cooperative, %lld MB): %u clusters in, %u rejected, %.1f ms\n", t, big[t].arena_bytes >> 20, n_work, ctx->h_pin[65], ms);
         }
-        n_work = h[1];
+        n_work = ctx->h_pin[65];
         const u32 *tmp = cur; cur = other; other = (u32 *)tmp;
     }
     return AVK_OK;
 }
 
-static int run_compare_device(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, const u64 *strat_off_dev,
-                              const u32 *strat_idx_dev, u32 n_strata) {
+// Summary counters: fold the partial tables (in-kernel totals), or -- when strata are requested -- reduce the per-region
+// rows (k_reduce also sums the strata).  Idempotent: may be run again after the cooperative tiers added their clusters.
+static int run_finalize(avk_ctx *ctx, const CompareRun &R) {
+    const u64 n = ctx->n_regions;
+    unsigned long long *tot = (unsigned long long *)ctx->totals.p;
+    if (!R.strata) {
+        k_fold_slots<<<1, 320, 0, ctx->stream>>>((const unsigned long long *)ctx->tot_slots.p, tot);
+        ctx->launches += 1;
+    } else {
+        CK(cudaMemsetAsync(tot, 0, 8 * RED_COLS + 64, ctx->stream));
+        CK(cudaMemsetAsync(ctx->strat_totals.p, 0, 8ull * RED_COLS * R.n_strata, ctx->stream));
+        if (n) {
+            k_reduce<<<(unsigned)std::min<u64>(n, (u64)ctx->sm_count * 8), 288, 0, ctx->stream>>>(
+                n, R.out.status, R.out.region_metrics, R.out.type_mask, tot, (u32 *)(tot + RED_COLS), tot + RED_COLS + 1, tot + RED_COLS + 2,
+                R.strat_off, R.strat_idx, (unsigned long long *)ctx->strat_totals.p);
+            ctx->launches += 1;
+        }
+    }
+    CK(cudaGetLastError());
+    return AVK_OK;
+}
+
+// Launches one compare pass over the resident batch; nothing waits for the device.
+static int compare_launch(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, bool want_rows, bool strata, u32 n_strata, CompareRun &R) {
     const u64 n = ctx->n_regions, nv = ctx->n_variants;
+    const bool rows = want_rows || strata;
     ENSURE(ctx->status, 4 * n); ENSURE(ctx->ed1, 4 * n); ENSURE(ctx->ed2, 4 * n);
-    ENSURE(ctx->region_metrics, 8ull * RED_COLS * n);
+    if (rows) ENSURE(ctx->region_metrics, 8ull * RED_COLS * n);
     ENSURE(ctx->type_mask, 2 * n);
     ENSURE(ctx->vexp, nv); ENSURE(ctx->vobs, nv); ENSURE(ctx->vcls, nv);
     ENSURE(ctx->totals, 8 * RED_COLS + 64);
-    ENSURE(ctx->counters, 64);
+    ENSURE(ctx->tot_slots, 8ull * TOT_SLOTS * TOT_STRIDE);
+    ENSURE(ctx->counters, 256);
     ENSURE(ctx->work_ctr, 64);
-    if (n_strata) ENSURE(ctx->strat_totals, 8ull * RED_COLS * n_strata);
+    if (strata) ENSURE(ctx->strat_totals, 8ull * RED_COLS * n_strata);
     CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
-    CK(cudaMemsetAsync(ctx->totals.p, 0, 8 * RED_COLS + 64, ctx->stream));
-    if (n_strata) CK(cudaMemsetAsync(ctx->strat_totals.p, 0, 8ull * RED_COLS * n_strata, ctx->stream));
+    CK(cudaMemsetAsync(ctx->tot_slots.p, 0, 8ull * TOT_SLOTS * TOT_STRIDE, ctx->stream));
     // digest buffers are sized from a host-side upper bound, so no device round trip is needed
     ENSURE(ctx->digest, (size_t)n * (PH_SIZE + 32) + (size_t)VI_SIZE * nv + (size_t)ctx->pool_len + 256);
     ENSURE(ctx->digest_sizes, 8 * (n + 1));
     ENSURE(ctx->digest_offs, 8 * (n + 1));
-    DevBatch db = dev_batch(ctx);
-    DevCompareOut out;
+    R.db = dev_batch(ctx);
+    DevCompareOut &out = R.out;
     out.status = (int *)ctx->status.p; out.ed1 = (u32 *)ctx->ed1.p; out.ed2 = (u32 *)ctx->ed2.p;
-    out.region_metrics = (u64 *)ctx->region_metrics.p; out.type_mask = (uint16_t *)ctx->type_mask.p;
-    out.vexp = (u8 *)ctx->vexp.p; out.vobs = (u8 *)ctx->vobs.p; out.vcls = (u8 *)ctx->vcls.p;
+    out.region_metrics = rows ? (u64 *)ctx->region_metrics.p : nullptr;
+    out.tot_slots = strata ? nullptr : (unsigned long long *)ctx->tot_slots.p;
+    out.type_mask = (uint16_t *)ctx->type_mask.p;
+    out.vexp = biased<u8>(ctx->vexp, ctx->v_base); out.vobs = biased<u8>(ctx->vobs, ctx->v_base); out.vcls = biased<u8>(ctx->vcls, ctx->v_base);
     out.seq_off = want_seq ? (const u64 *)ctx->seq_off.p : nullptr;
-    out.seq_len = (u32 *)ctx->seq_len.p; out.seq_pool = (u8 *)ctx->seq_pool.p;
-    avk_compare_cfg c = *cfg;
+    out.seq_len = (u32 *)ctx->seq_len.p; out.seq_pool = biased<u8>(ctx->seq_pool, ctx->seq_base);
+    R.cfg = *cfg;
+    R.strata = strata; R.n_strata = n_strata;
+    R.strat_off = strata ? (const u64 *)ctx->strat_off.p : nullptr;
+    R.strat_idx = strata ? biased<const u32>(ctx->strat_idx, ctx->strat_base) : nullptr;
+    ctx->have_result = false;
 
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    int rc = run_alt_ed(ctx, db);
+    int rc = run_alt_ed(ctx, R.db);
     if (rc != AVK_OK) return rc;
-    rc = run_prepare(ctx, db);
+    rc = run_prepare(ctx, R.db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = run_compare_pipeline(ctx, n, [&](u32 *list, u32 *ctr, u32 *dense, u32 *dense_ctr) {
-        k_compare_simple<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, out, c, n, list, ctr, dense, dense_ctr, ctx->dense_n);
-    }, [&](const TierArgs &a, int ctas) {
-        static bool configured = false;
-        if (!configured) {
-            cudaFuncSetAttribute(k_compare_team, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
-            cudaFuncSetAttribute(k_compare_team, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            configured = true;
-        }
-        k_compare_team<<<ctas, 128 * TEAMS_PER_CTA, TEAMS_PER_CTA * (size_t)a.arena_bytes, ctx->stream>>>(db, out, c, a);
-    }, [&](u32 *list, u32 cnt) {
-        k_sort_biggest_first<<<1, 1024, 0, ctx->stream>>>(db, list, cnt);
-    }, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
-        if (st.mode == MODE_COOP) {
-            const int cap_ints = 26000;                                  // wavefronts up to ED 12998 stay in shared memory
-            const size_t smem = COOP_JOB_BYTES + 2 * sizeof(int) * (size_t)cap_ints;
-            static bool configured = false;
-            if (!configured) { cudaFuncSetAttribute(k_compare_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
-            k_compare_coop<<<ctas, COOP_THREADS, smem, strm>>>(db, out, c, a, cap_ints);
-        }
-        else if (st.mode == MODE_SEARCH) launch_compare<true, 3, MODE_SEARCH>(ctx, db, out, c, a, ctas, st.warps, strm);
-        else if (st.mode == MODE_SCORE) launch_compare<true, 4, MODE_SCORE>(ctx, db, out, c, a, ctas, st.warps, strm);
-        else if (st.smem && st.min_ctas == 2) launch_compare<true, 2, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);
-        else if (st.smem) launch_compare<true, 1, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);
-        else launch_compare<false, 1, MODE_FUSED>(ctx, db, out, c, a, ctas, st.warps, strm);
-    });
+    rc = run_compare_pipeline(ctx, R);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (n) {
-        unsigned long long *tot = (unsigned long long *)ctx->totals.p;
-        k_reduce<<<std::min<u64>(n, (u64)ctx->sm_count * 8), 288, 0, ctx->stream>>>(
-            n, out.status, out.region_metrics, out.type_mask, tot, (u32 *)(tot + RED_COLS), tot + RED_COLS + 1, tot + RED_COLS + 2,
-            strat_off_dev, strat_idx_dev, (unsigned long long *)ctx->strat_totals.p);
-        ctx->launches += 1;
-        CK(cudaGetLastError());
-    }
+    rc = run_finalize(ctx, R);
+    if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    // pipeline counters + work counters travel back behind the kernels (pinned scratch: the copies do not block)
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->counters.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->result_has_rows = rows;
+    return AVK_OK;
+}
+
+// Waits for the pass; if SV-sized clusters were left for the cooperative tiers, runs them and the summary again.
+// *redo is set when outputs copied to the host before this call are stale.
+static int compare_finish(avk_ctx *ctx, const CompareRun &R, bool *redo) {
+    if (redo) *redo = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const u32 *h = ctx->h_pin;
+    if (ctx->n_regions) {
+        for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
+        ctx->tier_fail[0] = h[1]; ctx->tier_fail[1] = h[5]; ctx->tier_fail[2] = h[7];
+        if (h[7] > 0) {
+            int rc = run_big_tiers(ctx, R, h[7]);
+            if (rc != AVK_OK) return rc;
+            CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+            CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+            rc = run_finalize(ctx, R);
+            if (rc != AVK_OK) return rc;
+            CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (redo) *redo = true;
+        }
+    } else {
+        for (int t = 0; t < 3; ++t) { ctx->tier_ms[t] = 0; ctx->tier_fail[t] = 0; }
+    }
+    ctx->have_result = true;
     return AVK_OK;
 }
 
@@ -1300,7 +1492,7 @@ static int fetch_timings(avk_ctx *ctx) {
     cudaEventElapsedTime(&ctx->last_ms[2], ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->last_ms[3], ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&ctx->last_ms[4], ctx->ev[0], ctx->ev[4]);
-    unsigned long long w[8];
+    unsigned long long *w = (unsigned long long *)(ctx->h_pin + 128);
     CK(cudaMemcpyAsync(w, ctx->work_ctr.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->last_work.alignments = w[0]; ctx->last_work.cells = w[1]; ctx->last_work.matched_bases = w[2];
@@ -1313,67 +1505,193 @@ static int fetch_timings(avk_ctx *ctx) {
         if ((dst) && (bytes)) CK(cudaMemcpyAsync((dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream)); \
     } while (0)
 
-static int download_compare(avk_ctx *ctx, avk_compare_out *out, bool want_seq, u64 seq_pool_len) {
-    const u64 n = ctx->n_regions, nv = ctx->n_variants;
-    DL(out->status, ctx->status, 4 * n);
-    DL(out->ed1, ctx->ed1, 4 * n);
-    DL(out->ed2, ctx->ed2, 4 * n);
-    DL(out->region_metrics, ctx->region_metrics, 8ull * RED_COLS * n);
-    DL(out->type_mask, ctx->type_mask, 2 * n);
-    DL(out->var_expected, ctx->vexp, nv);
-    DL(out->var_observed, ctx->vobs, nv);
-    DL(out->var_class, ctx->vcls, nv);
+// Partial results of one bin: what the host adds up over bins (wrapping u64, like the reference's AddAssign).
+struct BinTotals {
     unsigned long long tot[RED_COLS + 8];
-    CK(cudaMemcpyAsync(tot, ctx->totals.p, 8 * RED_COLS + 64, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out->strat_totals && out->n_strata) DL(out->strat_totals, ctx->strat_totals, 8ull * RED_COLS * out->n_strata);
-    if (want_seq) {
-        DL(out->seq_len, ctx->seq_len, 4 * 5 * n);
-        DL(out->seq_pool, ctx->seq_pool, seq_pool_len);
+    std::vector<u64> strat;
+};
+
+// Queues the device->host copies of the resident bin's results INTO THE CALLER'S ARRAYS AT THE BIN'S OFFSETS (regions from
+// ctx->lo, variants from ctx->v_base); totals go to `bt` (pinned scratch first).  No synchronisation here.
+static int download_compare_async(avk_ctx *ctx, avk_compare_out *out, bool want_seq, u64 seq_bytes) {
+    const u64 n = ctx->n_regions, nv = ctx->n_variants, lo = ctx->lo, vb = ctx->v_base;
+    DL(out->status ? out->status + lo : nullptr, ctx->status, 4 * n);
+    DL(out->ed1 ? out->ed1 + lo : nullptr, ctx->ed1, 4 * n);
+    DL(out->ed2 ? out->ed2 + lo : nullptr, ctx->ed2, 4 * n);
+    if (out->region_metrics && n) {
+        if (!ctx->result_has_rows) { ctx->err = "per-region metric rows were not kept by this run (AVK_CMP_KEEP_REGION_ROWS)"; return AVK_ERR_INVALID; }
+        DL(out->region_metrics + lo * RED_COLS, ctx->region_metrics, 8ull * RED_COLS * n);
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (out->totals) memcpy(out->totals, tot, 8 * RED_COLS);
-    if (out->totals_mask) *out->totals_mask = (uint16_t)(tot[RED_COLS] & 0xffff);
-    if (out->solved_blocks) *out->solved_blocks = tot[RED_COLS + 1];
-    if (out->error_blocks) *out->error_blocks = tot[RED_COLS + 2];
+    DL(out->type_mask ? out->type_mask + lo : nullptr, ctx->type_mask, 2 * n);
+    DL(out->var_expected ? out->var_expected + vb : nullptr, ctx->vexp, nv);
+    DL(out->var_observed ? out->var_observed + vb : nullptr, ctx->vobs, nv);
+    DL(out->var_class ? out->var_class + vb : nullptr, ctx->vcls, nv);
+    CK(cudaMemcpyAsync(ctx->h_pin + 256, ctx->totals.p, 8 * RED_COLS + 64, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_seq) {
+        DL(out->seq_len + lo * 5, ctx->seq_len, 4 * 5 * n);
+        DL(out->seq_pool + ctx->seq_base, ctx->seq_pool, seq_bytes);
+    }
     return AVK_OK;
 }
 
-static int prepare_outputs_on_device(avk_ctx *ctx, const avk_compare_out *out, bool &want_seq, u64 &seq_pool_len) {
-    const u64 n = ctx->n_regions;
+// after the stream has been synchronised: collect totals (+ strata) of this bin
+static int collect_totals(avk_ctx *ctx, const avk_compare_out *out, bool strata, BinTotals &bt) {
+    memcpy(bt.tot, ctx->h_pin + 256, 8 * RED_COLS + 64);
+    bt.strat.clear();
+    if (strata) {
+        bt.strat.resize((size_t)RED_COLS * out->n_strata);
+        CK(cudaMemcpyAsync(bt.strat.data(), ctx->strat_totals.p, 8ull * RED_COLS * out->n_strata, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return AVK_OK;
+}
+
+static void store_totals(avk_compare_out *out, const BinTotals &bt, bool strata, bool accumulate) {
+    if (out->totals) for (int j = 0; j < RED_COLS; ++j) out->totals[j] = (accumulate ? out->totals[j] : 0) + bt.tot[j];
+    if (out->totals_mask) *out->totals_mask = (uint16_t)((accumulate ? *out->totals_mask : 0) | (bt.tot[RED_COLS] & 0xffff));
+    if (out->solved_blocks) *out->solved_blocks = (accumulate ? *out->solved_blocks : 0) + bt.tot[RED_COLS + 1];
+    if (out->error_blocks) *out->error_blocks = (accumulate ? *out->error_blocks : 0) + bt.tot[RED_COLS + 2];
+    if (strata && out->strat_totals)
+        for (size_t j = 0; j < bt.strat.size(); ++j) out->strat_totals[j] = (accumulate ? out->strat_totals[j] : 0) + bt.strat[j];
+}
+
+// optional inputs that travel with the outputs struct: sequence-bundle layout and stratum membership of the bin
+static int prepare_outputs_on_device(avk_ctx *ctx, const avk_compare_out *out, u64 n_total, bool &want_seq, u64 &seq_bytes, bool &strata) {
+    const u64 n = ctx->n_regions, lo = ctx->lo;
     want_seq = out->seq_off && out->seq_len && out->seq_pool;
-    seq_pool_len = 0;
+    seq_bytes = 0;
+    ctx->seq_base = 0; ctx->strat_base = 0;
     if (want_seq) {
-        seq_pool_len = out->seq_off[n * 5];
-        UPLOAD(ctx->seq_off, out->seq_off, 8 * (n * 5 + 1));
-        ENSURE(ctx->seq_len, 4 * 5 * n);
-        ENSURE(ctx->seq_pool, seq_pool_len);
+        for (u64 i = lo * 5; i < (lo + n) * 5; ++i) if (out->seq_off[i] > out->seq_off[i + 1]) { ctx->err = "seq_off is not monotone"; return AVK_ERR_INVALID; }
+        ctx->seq_base = out->seq_off[lo * 5];
+        seq_bytes = out->seq_off[(lo + n) * 5] - ctx->seq_base;
+        UPLOAD(ctx->seq_off, out->seq_off + lo * 5, 8 * (n * 5 + 1));
+        ENSURE(ctx->seq_len, 4 * 5 * n + 4);
+        ENSURE(ctx->seq_pool, seq_bytes);
         CK(cudaMemsetAsync(ctx->seq_len.p, 0, 4 * 5 * n + 4, ctx->stream));
     }
-    if (out->strat_off && out->strat_totals && out->n_strata) {
-        UPLOAD(ctx->strat_off, out->strat_off, 8 * (n + 1));
-        UPLOAD(ctx->strat_idx, out->strat_idx, 4 * out->strat_off[n]);
+    strata = out->strat_off && out->strat_totals && out->n_strata;
+    if (strata) {
+        const u64 s0 = out->strat_off[lo], s1 = out->strat_off[lo + n];
+        bool bad = s0 > s1 || (s1 > s0 && !out->strat_idx);
+        for (u64 r = lo; r < lo + n && !bad; ++r) bad = out->strat_off[r] > out->strat_off[r + 1];
+        for (u64 s = s0; s < s1 && !bad; ++s) bad = out->strat_idx[s] >= out->n_strata;
+        if (bad) { ctx->err = "strat_off / strat_idx are inconsistent (not monotone, or a stratum index >= n_strata)"; return AVK_ERR_INVALID; }
+        ctx->strat_base = s0;
+        UPLOAD(ctx->strat_off, out->strat_off + lo, 8 * (n + 1));
+        UPLOAD(ctx->strat_idx, out->strat_idx + s0, 4 * (s1 - s0));
     }
+    (void)n_total;
+    return AVK_OK;
+}
+
+// One contiguous bin [lo, hi) of the batch on this context's GPU; results land in the caller's arrays at the bin's
+// offsets, the bin's summary counters in `bt`.
+static int compare_bin(avk_ctx *ctx, const avk_region_batch *batch, u64 lo, u64 hi, const avk_compare_cfg *cfg, avk_compare_out *out, BinTotals &bt) {
+    CK(cudaSetDevice(ctx->device));
+    BinScan sc;
+    int rc = scan_bin(ctx, batch, lo, hi, sc);
+    if (rc != AVK_OK) return rc;
+    rc = upload_batch(ctx, batch, sc);
+    if (rc != AVK_OK) return rc;
+    bool want_seq, strata; u64 seq_bytes;
+    rc = prepare_outputs_on_device(ctx, out, batch->n_regions, want_seq, seq_bytes, strata);
+    if (rc != AVK_OK) return rc;
+    CompareRun R;
+    const bool want_rows = out->region_metrics != nullptr || (cfg->flags & AVK_CMP_KEEP_REGION_ROWS);
+    rc = compare_launch(ctx, cfg, want_seq, want_rows, strata, strata ? out->n_strata : 0, R);
+    if (rc != AVK_OK) return rc;
+    rc = download_compare_async(ctx, out, want_seq, seq_bytes);
+    if (rc != AVK_OK) return rc;
+    bool redo = false;
+    rc = compare_finish(ctx, R, &redo);
+    if (rc != AVK_OK) return rc;
+    if (redo) {
+        rc = download_compare_async(ctx, out, want_seq, seq_bytes);
+        if (rc != AVK_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    rc = collect_totals(ctx, out, strata, bt);
+    if (rc != AVK_OK) return rc;
+    return fetch_timings(ctx);
+}
+
+extern "C" int avk_compare_batch_range(avk_ctx *ctx, const avk_region_batch *batch, uint64_t lo, uint64_t hi,
+                                       const avk_compare_cfg *cfg, avk_compare_out *out) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+    int rc = validate_batch(ctx, batch, true);
+    if (rc != AVK_OK) return rc;
+    if (lo > hi || hi > batch->n_regions) { ctx->err = "region range outside the batch"; return AVK_ERR_INVALID; }
+    BinTotals bt;
+    rc = compare_bin(ctx, batch, lo, hi, cfg, out, bt);
+    if (rc != AVK_OK) return rc;
+    store_totals(out, bt, out->strat_off && out->strat_totals && out->n_strata, false);
     return AVK_OK;
 }
 
 extern "C" int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out) {
     if (!ctx) return AVK_ERR_INVALID;
+    if (!batch) { ctx->err = "null batch"; return AVK_ERR_INVALID; }
+    return avk_compare_batch_range(ctx, batch, 0, batch->n_regions, cfg, out);
+}
+
+// ---- multi-GPU behind the C ABI ---------------------------------------------------------------------------
+// Cost proxy per region: (variants + 1) * window + sum over variants of max(|allele0|, |allele1|)^2 (the SV tail is quadratic).
+// cuts[k] = first region of bin k: the first index whose cumulative cost reaches k/n of the total (bins are contiguous in
+// region_id order, so concatenating the bins' results restores the reference's output order, src/main.rs:271).
+extern "C" int avk_partition_regions(const avk_region_batch *b, uint32_t n_bins, uint64_t *cuts) {
+    if (!b || !cuts || n_bins == 0) return AVK_ERR_INVALID;
+    const u64 n = b->n_regions, K = b->n_inputs;
+    std::vector<u64> cum(n + 1, 0);
+    for (u64 r = 0; r < n; ++r) {
+        const u64 v0 = b->var_off[r * K], v1 = b->var_off[(r + 1) * K];
+        u64 c = (v1 - v0 + 1) * (u64)(b->end[r] > b->start[r] ? b->end[r] - b->start[r] : 0);
+        for (u64 v = v0; v < v1; ++v) { const u64 m = std::max(b->variants.a0_len[v], b->variants.a1_len[v]); c += m * m; }
+        cum[r + 1] = cum[r] + c;
+    }
+    const unsigned __int128 total = cum[n];
+    cuts[0] = 0;
+    for (uint32_t k = 1; k < n_bins; ++k) {
+        // first r with cum[r + 1] * n_bins >= total * k
+        u64 lo = 0, hi = n;
+        while (lo < hi) {
+            const u64 m = (lo + hi) >> 1;
+            if ((unsigned __int128)cum[m + 1] * n_bins < total * k) lo = m + 1; else hi = m;
+        }
+        cuts[k] = std::max(lo, cuts[k - 1]);
+    }
+    cuts[n_bins] = n;
+    return AVK_OK;
+}
+
+// One host thread per context (= per GPU); bin k goes to ctxs[k].  Every device copies its slice of the results straight into
+// the caller's arrays at its bin offset -- the bins are contiguous, so on one node the "gather" is those copies -- and the
+// summary counters of the bins are added on the host.  Every context must hold the reference (avk_set_reference).
+extern "C" int avk_compare_batch_multi(avk_ctx *const *ctxs, uint32_t n_ctx, const avk_region_batch *batch,
+                                       const avk_compare_cfg *cfg, avk_compare_out *out) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return AVK_ERR_INVALID;
+    avk_ctx *ctx = ctxs[0];
     if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
-    CK(cudaSetDevice(ctx->device));
     int rc = validate_batch(ctx, batch, true);
     if (rc != AVK_OK) return rc;
-    rc = upload_batch(ctx, batch);
-    if (rc != AVK_OK) return rc;
-    bool want_seq; u64 seq_pool_len;
-    rc = prepare_outputs_on_device(ctx, out, want_seq, seq_pool_len);
-    if (rc != AVK_OK) return rc;
-    const bool strat = out->strat_off && out->strat_totals && out->n_strata;
-    rc = run_compare_device(ctx, cfg, want_seq, strat ? (const u64 *)ctx->strat_off.p : nullptr,
-                            strat ? (const u32 *)ctx->strat_idx.p : nullptr, strat ? out->n_strata : 0);
-    if (rc != AVK_OK) return rc;
-    rc = download_compare(ctx, out, want_seq, seq_pool_len);
-    if (rc != AVK_OK) return rc;
-    return fetch_timings(ctx);
+    std::vector<u64> cuts(n_ctx + 1);
+    if (batch->n_regions && (!batch->variants.a0_len || !batch->variants.a1_len) && batch->variants.n_variants) { ctx->err = "null variant arrays"; return AVK_ERR_INVALID; }
+    avk_partition_regions(batch, n_ctx, cuts.data());
+    std::vector<BinTotals> bts(n_ctx);
+    std::vector<int> rcs(n_ctx, AVK_OK);
+    std::vector<std::thread> th;
+    for (uint32_t k = 0; k < n_ctx; ++k)
+        th.emplace_back([&, k]() {
+            if (!ctxs[k]) { rcs[k] = AVK_ERR_INVALID; return; }
+            rcs[k] = compare_bin(ctxs[k], batch, cuts[k], cuts[k + 1], cfg, out, bts[k]);
+        });
+    for (auto &t : th) t.join();
+    for (uint32_t k = 0; k < n_ctx; ++k)
+        if (rcs[k] != AVK_OK) { if (k && ctxs[k]) ctx->err = "device " + std::to_string(k) + ": " + ctxs[k]->err; return rcs[k]; }
+    const bool strata = out->strat_off && out->strat_totals && out->n_strata;
+    for (uint32_t k = 0; k < n_ctx; ++k) store_totals(out, bts[k], strata, k > 0);
+    return AVK_OK;
 }
 
 // ------------------------------------------------------------------------------------ region builder
@@ -1450,6 +1768,7 @@ extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t 
     const avk_variant_table &t = in->variants;
     const u64 nv = t.n_variants, K = in->n_inputs, contig_len = ctx->contig_lens[contig];
     if (in->input_off[K] != nv || nv >= 0xffffffffull || t.allele_pool_len >= 0xffffffffull) { ctx->err = "avk_build_regions: bad call-set table"; return AVK_ERR_INVALID; }
+    if (contig_len > 0xffffffffull) { ctx->err = "avk_build_regions: contig longer than 2^32 - 1 bases"; return AVK_ERR_INVALID; }
     enum { T_POS, T_VT, T_ZY, T_RAW, T_AOFF, T_L0, T_L1, T_POOL, T_KEY, T_IDX, T_KEY_S, T_IDX_S, T_VEND, T_PMAX, T_FLAG, T_CID, T_KEY2, T_KEY2_S, T_PERM, T_MISC };
     DevBuf *rb = ctx->rb;
     UPLOAD(rb[T_POS], t.position, 4 * nv); UPLOAD(rb[T_VT], t.variant_type, nv); UPLOAD(rb[T_ZY], t.zygosity, nv);
@@ -1464,9 +1783,16 @@ extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t 
     CK(cudaMemsetAsync(d_nvalid, 0, 8, ctx->stream));
     u32 mx = 1;
     u64 sum_alle = 0;
-    for (u64 i = 0; i < nv; ++i) { mx = std::max(mx, std::max(t.a0_len[i], t.a1_len[i])); sum_alle += (u64)t.a0_len[i] + t.a1_len[i]; }
+    for (u64 i = 0; i < nv; ++i) {
+        mx = std::max(mx, std::max(t.a0_len[i], t.a1_len[i])); sum_alle += (u64)t.a0_len[i] + t.a1_len[i];
+        if ((u64)t.allele_off[i] + t.a0_len[i] + t.a1_len[i] > t.allele_pool_len || t.a0_len[i] > (1u << 24) || t.a1_len[i] > (1u << 24)) {
+            ctx->err = "avk_build_regions: allele range outside the pool (or longer than 16 MiB)";
+            return AVK_ERR_INVALID;
+        }
+    }
     if (sum_alle >= 0xffffffffull) { ctx->err = "avk_build_regions: allele bytes exceed 4 GiB"; return AVK_ERR_INVALID; }
-    ctx->have_batch = false;
+    ctx->have_batch = false; ctx->have_result = false;
+    ctx->lo = 0; ctx->v_base = 0; ctx->p_base = 0; ctx->pool_bytes = 0;
     *n_regions_out = 0; *n_variants_out = 0;
     if (nv == 0) { ctx->n_regions = 0; ctx->n_variants = 0; ctx->n_inputs = (u32)K; ctx->max_allele = 1; ctx->pool_len = 0; ctx->have_batch = true; ENSURE(ctx->var_off, 8); CK(cudaMemsetAsync(ctx->var_off.p, 0, 8, ctx->stream)); return AVK_OK; }
     const unsigned g = (unsigned)((nv + 255) / 256);
@@ -1515,8 +1841,16 @@ extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t 
         CK(cudaMemsetAsync(ctx->var_off.p, 0, 8, ctx->stream));
     }
     CK(cudaGetLastError());
+    u64 kept_bytes = 0;                                           // allele bytes of the variants that were kept
+    if (nvalid) {
+        u32 last[2] = {0, 0};
+        CK(cudaMemcpyAsync(&last[0], (u32 *)ctx->aoff.p + (nvalid - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&last[1], vend + (nvalid - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));   // alen (vend reused)
+        CK(cudaStreamSynchronize(ctx->stream));
+        kept_bytes = (u64)last[0] + last[1];
+    }
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->n_regions = n; ctx->n_variants = nvalid; ctx->n_inputs = (u32)K; ctx->max_allele = mx; ctx->pool_len = sum_alle;
+    ctx->n_regions = n; ctx->n_variants = nvalid; ctx->n_inputs = (u32)K; ctx->max_allele = mx; ctx->pool_len = kept_bytes; ctx->pool_bytes = kept_bytes;
     ctx->have_batch = true;
     *n_regions_out = n; *n_variants_out = nvalid;
     return AVK_OK;
@@ -1524,7 +1858,7 @@ extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t 
 
 extern "C" int avk_regions_download(avk_ctx *ctx, avk_region_batch *out) {
     if (!ctx || !out) return AVK_ERR_INVALID;
-    if (!ctx->have_batch) { ctx->err = "avk_regions_download: no resident batch"; return AVK_ERR_INVALID; }
+    if (!ctx->have_batch || ctx->lo != 0 || ctx->v_base != 0) { ctx->err = "avk_regions_download: no device-built batch is resident"; return AVK_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     const u64 n = ctx->n_regions, nv = ctx->n_variants, K = ctx->n_inputs;
     avk_variant_table &t = out->variants;
@@ -1532,38 +1866,71 @@ extern "C" int avk_regions_download(avk_ctx *ctx, avk_region_batch *out) {
     RBDL(out->region_id, ctx->region_id, 8 * n); RBDL(out->contig, ctx->contig, 4 * n); RBDL(out->start, ctx->start, 4 * n); RBDL(out->end, ctx->end, 4 * n);
     RBDL(out->var_off, ctx->var_off, 8 * (n * K + 1));
     RBDL(t.position, ctx->pos, 4 * nv); RBDL(t.variant_type, ctx->vtype, nv); RBDL(t.zygosity, ctx->zyg, nv); RBDL(t.raw_allele_space, ctx->raw, 4 * nv);
-    RBDL(t.allele_off, ctx->aoff, 4 * nv); RBDL(t.a0_len, ctx->l0, 4 * nv); RBDL(t.a1_len, ctx->l1, 4 * nv); RBDL(t.allele_pool, ctx->pool, ctx->pool_len);
+    RBDL(t.allele_off, ctx->aoff, 4 * nv); RBDL(t.a0_len, ctx->l0, 4 * nv); RBDL(t.a1_len, ctx->l1, 4 * nv); RBDL(t.allele_pool, ctx->pool, ctx->pool_bytes);
 #undef RBDL
     CK(cudaStreamSynchronize(ctx->stream));
-    out->n_regions = n; out->n_inputs = (uint32_t)K; t.n_variants = nv; t.allele_pool_len = ctx->pool_len;
+    out->n_regions = n; out->n_inputs = (uint32_t)K; t.n_variants = nv; t.allele_pool_len = ctx->pool_bytes;
+    return AVK_OK;
+}
+
+extern "C" int avk_compare_upload_range(avk_ctx *ctx, const avk_region_batch *batch, uint64_t lo, uint64_t hi) {
+    if (!ctx) return AVK_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = validate_batch(ctx, batch, true);
+    if (rc != AVK_OK) return rc;
+    if (lo > hi || hi > batch->n_regions) { ctx->err = "region range outside the batch"; return AVK_ERR_INVALID; }
+    BinScan sc;
+    rc = scan_bin(ctx, batch, lo, hi, sc);
+    if (rc != AVK_OK) return rc;
+    rc = upload_batch(ctx, batch, sc);
+    if (rc != AVK_OK) return rc;
+    ctx->seq_base = 0; ctx->strat_base = 0;
+    CK(cudaStreamSynchronize(ctx->stream));
     return AVK_OK;
 }
 
 extern "C" int avk_compare_upload(avk_ctx *ctx, const avk_region_batch *batch) {
     if (!ctx) return AVK_ERR_INVALID;
-    CK(cudaSetDevice(ctx->device));
-    int rc = validate_batch(ctx, batch, true);
-    if (rc != AVK_OK) return rc;
-    rc = upload_batch(ctx, batch);
-    if (rc != AVK_OK) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
-    return AVK_OK;
+    if (!batch) { ctx->err = "null batch"; return AVK_ERR_INVALID; }
+    return avk_compare_upload_range(ctx, batch, 0, batch->n_regions);
 }
 
 extern "C" int avk_compare_run_resident(avk_ctx *ctx, const avk_compare_cfg *cfg) {
     if (!ctx) return AVK_ERR_INVALID;
     if (!cfg || !ctx->have_batch || ctx->n_inputs != 2) { ctx->err = "no resident compare batch"; return AVK_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
-    int rc = run_compare_device(ctx, cfg, false, nullptr, nullptr, 0);
+    CompareRun R;
+    int rc = compare_launch(ctx, cfg, false, (cfg->flags & AVK_CMP_KEEP_REGION_ROWS) != 0, false, 0, R);
+    if (rc != AVK_OK) return rc;
+    rc = compare_finish(ctx, R, nullptr);
     if (rc != AVK_OK) return rc;
     return fetch_timings(ctx);
 }
 
+// Results of the last run, copied into the caller's arrays at the resident bin's offsets.
 extern "C" int avk_compare_download(avk_ctx *ctx, avk_compare_out *out) {
     if (!ctx) return AVK_ERR_INVALID;
-    if (!out || !ctx->have_batch) { ctx->err = "no resident batch"; return AVK_ERR_INVALID; }
+    if (!out || !ctx->have_batch || !ctx->have_result) { ctx->err = "no compare result is resident (run avk_compare_run_resident first)"; return AVK_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
-    return download_compare(ctx, out, false, 0);
+    int rc = download_compare_async(ctx, out, false, 0);
+    if (rc != AVK_OK) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    BinTotals bt;
+    rc = collect_totals(ctx, out, false, bt);
+    if (rc != AVK_OK) return rc;
+    store_totals(out, bt, false, false);
+    return AVK_OK;
+}
+
+// Device addresses of the last run's results (the single gather of a one-process-per-GPU run sends them to the root
+// GPU over NVLink without a host round trip).  The arrays stay valid until the next call on this context.
+extern "C" int avk_compare_result_device(avk_ctx *ctx, avk_compare_dev_view *v) {
+    if (!ctx || !v) return AVK_ERR_INVALID;
+    if (!ctx->have_batch || !ctx->have_result) { ctx->err = "no compare result is resident"; return AVK_ERR_INVALID; }
+    v->lo = ctx->lo; v->n_regions = ctx->n_regions; v->v_base = ctx->v_base; v->n_variants = ctx->n_variants;
+    v->status = ctx->status.p; v->ed1 = ctx->ed1.p; v->ed2 = ctx->ed2.p; v->type_mask = ctx->type_mask.p;
+    v->var_expected = ctx->vexp.p; v->var_observed = ctx->vobs.p; v->var_class = ctx->vcls.p; v->totals = ctx->totals.p;
+    return AVK_OK;
 }
 
 // Measured INT32 throughput in integer ops per second (3 ops per chain step: add, max, xor).
@@ -1611,13 +1978,13 @@ extern "C" int avk_last_work(avk_ctx *ctx, avk_work_counters *out) {
     return AVK_OK;
 }
 
-extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, const avk_merge_cfg *cfg, avk_merge_out *out) {
-    if (!ctx) return AVK_ERR_INVALID;
-    if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+// solve_merge_region over one contiguous bin [lo, hi) of the batch; results land in the caller's arrays at the bin's offsets
+static int merge_bin(avk_ctx *ctx, const avk_region_batch *batch, u64 lo, u64 hi, const avk_merge_cfg *cfg, avk_merge_out *out) {
     CK(cudaSetDevice(ctx->device));
-    int rc = validate_batch(ctx, batch, false);
+    BinScan sc;
+    int rc = scan_bin(ctx, batch, lo, hi, sc);
     if (rc != AVK_OK) return rc;
-    rc = upload_batch(ctx, batch);
+    rc = upload_batch(ctx, batch, sc);
     if (rc != AVK_OK) return rc;
     const u64 n = ctx->n_regions;
     const u32 K = ctx->n_inputs;
@@ -1651,9 +2018,9 @@ extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, cons
         if (n) k_merge_front<<<cgrid, 256, 0, ctx->stream>>>(db, mo, c, mw, n);
         ctx->launches += 1;
     }, 20, [&](const Stage &st, const TierArgs &a, int ctas, cudaStream_t strm) {
-        if (st.smem && st.min_ctas == 3) launch_merge_pairs<true, 3>(ctx, db, c, a, mw, ctas, st.warps, strm);
-        else if (st.smem) launch_merge_pairs<true, 1>(ctx, db, c, a, mw, ctas, st.warps, strm);
-        else launch_merge_pairs<false, 1>(ctx, db, c, a, mw, ctas, st.warps, strm);
+        if (st.smem && st.min_ctas == 3) launch_merge_pairs<true, 3>(db, c, a, mw, ctas, st.warps, strm);
+        else if (st.smem) launch_merge_pairs<true, 1>(db, c, a, mw, ctas, st.warps, strm);
+        else launch_merge_pairs<false, 1>(db, c, a, mw, ctas, st.warps, strm);
     });
     if (rc != AVK_OK) return rc;
     if (n) {
@@ -1665,13 +2032,43 @@ extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, cons
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    DL(out->status, ctx->status, 4 * n);
-    DL(out->classification, ctx->m_cls, n);
-    DL(out->n_indices, ctx->m_nidx, n);
-    DL(out->indices, ctx->m_idx, n * K);
+    DL(out->status + lo, ctx->status, 4 * n);
+    DL(out->classification ? out->classification + lo : nullptr, ctx->m_cls, n);
+    DL(out->n_indices ? out->n_indices + lo : nullptr, ctx->m_nidx, n);
+    DL(out->indices ? out->indices + lo * K : nullptr, ctx->m_idx, n * K);
     CK(cudaStreamSynchronize(ctx->stream));
     return fetch_timings(ctx);
 }
+
+extern "C" int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch, const avk_merge_cfg *cfg, avk_merge_out *out) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+    int rc = validate_batch(ctx, batch, false);
+    if (rc != AVK_OK) return rc;
+    return merge_bin(ctx, batch, 0, batch->n_regions, cfg, out);
+}
+
+// Multi-GPU merge: contiguous bins, one host thread per context, results written at the bins' offsets (see
+// avk_compare_batch_multi).
+extern "C" int avk_merge_batch_multi(avk_ctx *const *ctxs, uint32_t n_ctx, const avk_region_batch *batch,
+                                     const avk_merge_cfg *cfg, avk_merge_out *out) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return AVK_ERR_INVALID;
+    avk_ctx *ctx = ctxs[0];
+    if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+    int rc = validate_batch(ctx, batch, false);
+    if (rc != AVK_OK) return rc;
+    std::vector<u64> cuts(n_ctx + 1);
+    avk_partition_regions(batch, n_ctx, cuts.data());
+    std::vector<int> rcs(n_ctx, AVK_OK);
+    std::vector<std::thread> th;
+    for (uint32_t k = 0; k < n_ctx; ++k)
+        th.emplace_back([&, k]() { rcs[k] = ctxs[k] ? merge_bin(ctxs[k], batch, cuts[k], cuts[k + 1], cfg, out) : AVK_ERR_INVALID; });
+    for (auto &t : th) t.join();
+    for (uint32_t k = 0; k < n_ctx; ++k)
+        if (rcs[k] != AVK_OK) { if (k && ctxs[k]) ctx->err = "device " + std::to_string(k) + ": " + ctxs[k]->err; return rcs[k]; }
+    return AVK_OK;
+}
+
 
 extern "C" int avk_wfa_ed_batch(avk_ctx *ctx, uint64_t n_pairs, const uint8_t *pool, uint64_t pool_len, const uint64_t *a_off,
                                 const uint32_t *a_len, const uint64_t *b_off, const uint32_t *b_len, uint32_t *ed_out) {

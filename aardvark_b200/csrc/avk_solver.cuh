@@ -48,10 +48,17 @@ struct DevBatch {
 enum { PH_STATUS = 0, PH_N = 4, PH_N0 = 8, PH_N1 = 12, PH_SUM_L1 = 16, PH_B0 = 20, PH_SUM_ALLE = 24, PH_MAX_END = 28,
        PH_NSLOTS = 32, PH_SLOT_TYPE = 36, PH_SIZE = 64 };
 
+// Summary counters accumulated inside the solver kernels (SummaryWriter::add_comparison_benchmark,
+// writers/summary.rs:146-158): TOT_SLOTS partial tables of [13][22] metric sums + {type mask, solved, errors};
+// a CTA adds to slot blockIdx.x % TOT_SLOTS (u64 atomics in L2, little contention), k_fold_slots sums the slots.
+enum { TOT_SLOTS = 128, TOT_COLS = AVK_N_GROUPS * AVK_N_METRICS, TOT_MASK = TOT_COLS, TOT_SOLVED = TOT_COLS + 1,
+       TOT_ERRORS = TOT_COLS + 2, TOT_STRIDE = TOT_COLS + 6 };
+
 struct DevCompareOut {
     int *status;
     u32 *ed1, *ed2;
-    u64 *region_metrics;   // [n][13][22]
+    u64 *region_metrics;   // [n][13][22], or NULL when the caller wants neither per-region rows nor strata
+    unsigned long long *tot_slots;   // [TOT_SLOTS][TOT_STRIDE], or NULL (rows mode: k_reduce sums the rows instead)
     uint16_t *type_mask;
     u8 *vexp, *vobs, *vcls;
     const u64 *seq_off;    // may be NULL
@@ -1508,8 +1515,21 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
     if (ed_overflow) return SOLVE_WORKSPACE;
     if (status != AVK_ST_OK) return status;
     __syncwarp();
+    // ---- summary counters of this region straight into this CTA's partial table (only the non-zero entries)
+    if (out.tot_slots) {
+        unsigned long long *slot = out.tot_slots + (size_t)(blockIdx.x & (TOT_SLOTS - 1)) * TOT_STRIDE;
+#pragma unroll 1
+        for (int i = lane; i < AVK_N_METRICS * (1 + n_slots); i += 32) {
+            const u64 v = LD64(gm + 8 * i);
+            if (v) {
+                const int k = i / AVK_N_METRICS, m = i - k * AVK_N_METRICS;
+                atomicAdd(slot + (k == 0 ? 0 : (1 + slot_type[k - 1]) * AVK_N_METRICS) + m, (unsigned long long)v);
+            }
+        }
+        if (lane == 0) { atomicOr(slot + TOT_MASK, (unsigned long long)mask); atomicAdd(slot + TOT_SOLVED, 1ull); }
+    }
     // ---- write the full GroupTypeMetrics row [13][22] (coalesced), zeros for absent types
-    {
+    if (out.region_metrics) {
         u64 *dst = out.region_metrics + r * (u64)(AVK_N_GROUPS * AVK_N_METRICS);
         // type -> slot lookup in a register: 4 bits per type, 15 = absent
         u64 lut = ~0ull;

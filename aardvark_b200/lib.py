@@ -75,6 +75,17 @@ def load():
     if hasattr(lib, "avk_build_regions"):   # (older builds used for A/B timing do not have the region builder)
         lib.avk_build_regions.argtypes = [vp, C.POINTER(abi.CallSets), C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.avk_regions_download.argtypes = [vp, C.POINTER(abi.RegionBatch)]
+    lib.avk_compare_batch_range.argtypes = [vp, C.POINTER(abi.RegionBatch), C.c_uint64, C.c_uint64, C.POINTER(abi.CompareCfg),
+                                            C.POINTER(abi.CompareOut)]
+    lib.avk_compare_batch_multi.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(abi.RegionBatch), C.POINTER(abi.CompareCfg),
+                                            C.POINTER(abi.CompareOut)]
+    lib.avk_merge_batch_multi.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(abi.RegionBatch), C.POINTER(abi.MergeCfg),
+                                          C.POINTER(abi.MergeOut)]
+    lib.avk_partition_regions.argtypes = [C.POINTER(abi.RegionBatch), C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.avk_compare_upload_range.argtypes = [vp, C.POINTER(abi.RegionBatch), C.c_uint64, C.c_uint64]
+    lib.avk_compare_result_device.argtypes = [vp, C.POINTER(abi.CompareDevView)]
+    lib.avk_last_tier_overflow.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.avk_last_tier_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.avk_compare_upload.argtypes = [vp, C.POINTER(abi.RegionBatch)]
     lib.avk_compare_run_resident.argtypes = [vp, C.POINTER(abi.CompareCfg)]
     lib.avk_compare_download.argtypes = [vp, C.POINTER(abi.CompareOut)]
@@ -89,11 +100,23 @@ EXPORTED_SYMBOLS = [
     "avk_create", "avk_destroy", "avk_last_error", "avk_set_reference", "avk_compare_batch", "avk_merge_batch",
     "avk_wfa_ed_batch", "avk_compare_seq_offsets", "avk_compare_upload", "avk_compare_run_resident",
     "avk_compare_download", "avk_build_regions", "avk_regions_download", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak", "avk_last_tier_overflow", "avk_last_tier_ms",
+    "avk_compare_batch_range", "avk_compare_batch_multi", "avk_merge_batch_multi", "avk_partition_regions", "avk_compare_upload_range",
+    "avk_compare_result_device",
 ]
 
 
-def compare_cfg(cfg: CompareConfig) -> abi.CompareCfg:
-    return abi.CompareCfg(cfg.max_branch_factor, int(cfg.enable_exact_shortcut), int(cfg.enable_sequences), 0)
+def compare_cfg(cfg: CompareConfig, flags: int = 0) -> abi.CompareCfg:
+    return abi.CompareCfg(cfg.max_branch_factor, int(cfg.enable_exact_shortcut), int(cfg.enable_sequences), flags)
+
+
+def partition_regions(batch: RegionBatch, n_bins: int):
+    """Contiguous bins [lo, hi) balanced by the library's cost proxy (avk_partition_regions; host only, no GPU needed)."""
+    cuts = (C.c_uint64 * (n_bins + 1))()
+    cb = batch.to_c()
+    rc = load().avk_partition_regions(C.byref(cb), n_bins, cuts)
+    if rc != 0:
+        raise AvkError(f"avk_partition_regions failed ({rc})")
+    return [(int(cuts[k]), int(cuts[k + 1])) for k in range(n_bins)]
 
 
 def merge_cfg(cfg: MergeConfig) -> abi.MergeCfg:
@@ -155,6 +178,15 @@ class Solver:
         self._check(self._lib.avk_compare_batch(self._ctx, C.byref(cb), C.byref(cc), C.byref(co)), "avk_compare_batch")
         return out
 
+    def compare_batch_range(self, batch: RegionBatch, lo: int, hi: int, cfg: CompareConfig = None, out: CompareOutputs = None, **out_kwargs):
+        """One contiguous bin [lo, hi) of `batch`; results land in out[lo:hi] (totals = this bin's sums)."""
+        cfg = cfg or CompareConfig(enable_sequences=False)
+        if out is None:
+            out = CompareOutputs(batch, **out_kwargs)
+        cb, cc, co = batch.to_c(), compare_cfg(cfg), out.to_c()
+        self._check(self._lib.avk_compare_batch_range(self._ctx, C.byref(cb), lo, hi, C.byref(cc), C.byref(co)), "avk_compare_batch_range")
+        return out
+
     def merge_batch(self, batch: RegionBatch, cfg: MergeConfig = None) -> MergeOutputs:
         cfg = cfg or MergeConfig()
         out = MergeOutputs(batch)
@@ -201,13 +233,23 @@ class Solver:
         return b
 
     # -- resident mode (bench: inputs already in HBM) --------------------------------------
-    def upload(self, batch: RegionBatch):
+    def upload(self, batch: RegionBatch, lo: int = None, hi: int = None):
         cb = batch.to_c()
-        self._check(self._lib.avk_compare_upload(self._ctx, C.byref(cb)), "avk_compare_upload")
+        if lo is None:
+            self._check(self._lib.avk_compare_upload(self._ctx, C.byref(cb)), "avk_compare_upload")
+        else:
+            self._check(self._lib.avk_compare_upload_range(self._ctx, C.byref(cb), lo, hi), "avk_compare_upload_range")
 
-    def run_resident(self, cfg: CompareConfig = None):
-        cc = compare_cfg(cfg or CompareConfig(enable_sequences=False))
+    def run_resident(self, cfg: CompareConfig = None, region_metrics: bool = False):
+        """One pass over the resident batch.  region_metrics=True keeps the per-region metric rows on the device so
+        that download() can return them."""
+        cc = compare_cfg(cfg or CompareConfig(enable_sequences=False), abi.CMP_KEEP_REGION_ROWS if region_metrics else 0)
         self._check(self._lib.avk_compare_run_resident(self._ctx, C.byref(cc)), "avk_compare_run_resident")
+
+    def result_device_view(self) -> abi.CompareDevView:
+        v = abi.CompareDevView()
+        self._check(self._lib.avk_compare_result_device(self._ctx, C.byref(v)), "avk_compare_result_device")
+        return v
 
     def download(self, out: CompareOutputs):
         co = out.to_c()
@@ -265,3 +307,41 @@ class Solver:
         if isinstance(res, RegionError):
             raise res
         return res
+
+
+class MultiSolver:
+    """Several GPUs of one node behind one call (avk_compare_batch_multi / avk_merge_batch_multi): one context per
+    device, contiguous region bins, one host thread per device inside the library."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.solvers = [Solver(d) for d in devices]
+        self._lib = self.solvers[0]._lib
+        self._ctxs = (C.c_void_p * len(self.solvers))(*[s._ctx for s in self.solvers])
+
+    def close(self):
+        for s in self.solvers:
+            s.close()
+
+    def set_reference(self, contigs, names: Sequence[str] = None):
+        for s in self.solvers:
+            s.set_reference(contigs, names)
+
+    def compare_batch(self, batch: RegionBatch, cfg: CompareConfig = None, out: CompareOutputs = None, **out_kwargs):
+        cfg = cfg or CompareConfig(enable_sequences=False)
+        if out is None:
+            if cfg.enable_sequences and "seq_off" not in out_kwargs:
+                off, plen = seq_offsets(batch)
+                out_kwargs.update(seq_off=off, seq_pool_len=plen)
+            out = CompareOutputs(batch, **out_kwargs)
+        cb, cc, co = batch.to_c(), compare_cfg(cfg), out.to_c()
+        self.solvers[0]._check(self._lib.avk_compare_batch_multi(self._ctxs, len(self.solvers), C.byref(cb), C.byref(cc), C.byref(co)),
+                               "avk_compare_batch_multi")
+        return out
+
+    def merge_batch(self, batch: RegionBatch, cfg: MergeConfig = None) -> MergeOutputs:
+        cfg = cfg or MergeConfig()
+        out = MergeOutputs(batch)
+        cb, cc, co = batch.to_c(), merge_cfg(cfg), out.to_c()
+        self.solvers[0]._check(self._lib.avk_merge_batch_multi(self._ctxs, len(self.solvers), C.byref(cb), C.byref(cc), C.byref(co)),
+                               "avk_merge_batch_multi")
+        return out

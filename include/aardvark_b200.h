@@ -23,10 +23,9 @@
  * pointers unless a function says otherwise; the library owns all device
  * memory.  Nothing allocated by the library is freed by the caller.
  *
- * Two libraries implement (subsets of) this header with identical struct
- * layouts so that outputs can be compared bit for bit:
- *   aardvark_b200/csrc  -> libaardvark_b200.so   (CUDA sm_100a; the product)
- *   oracle/             -> liboracle.so          (CPU restatement; TEST ONLY)
+ * Implemented by aardvark_b200/csrc -> libaardvark_b200.so (CUDA sm_100a).  The CPU
+ * oracle used by the tests takes the same structs (oracle/oracle.h) so that outputs
+ * can be compared bit for bit; it is not part of the product.
  */
 #ifndef AARDVARK_B200_H
 #define AARDVARK_B200_H
@@ -109,7 +108,9 @@ enum {
     AVK_ST_TRUTH_FP = 3,          /* expected < observed (waffle_solver.rs:322, grouped_metrics.rs:197) */
     AVK_ST_TP_UNDERFLOW = 4,      /* ensure!(truth_tp >= basepair tp) waffle_solver.rs:492-493 */
     AVK_ST_BAD_INPUT = 5,         /* malformed batch entry (window outside contig, empty allele, ...) */
-    AVK_ST_WORKSPACE = 6          /* GPU only: search exceeded the largest workspace tier */
+    AVK_ST_WORKSPACE = 6,         /* GPU only: search exceeded the largest workspace tier */
+    AVK_ST_TIMEOUT = 7            /* optimize_gt_alleles gave up: deterministic stand-in (node-expansion cap) for the
+                                   * reference's 300 s wall-clock bail-out, exact_gt_optimizer.rs:165,174-176 */
 };
 
 /* Library-level return codes */
@@ -162,8 +163,11 @@ typedef struct avk_compare_cfg {
     uint32_t max_branch_factor;      /* default 50 */
     uint32_t enable_exact_shortcut;  /* default 0 */
     uint32_t enable_sequences;       /* fill the sequence bundle outputs */
-    uint32_t reserved;
+    uint32_t flags;                  /* AVK_CMP_* (GPU library only; 0 = defaults) */
 } avk_compare_cfg;
+/* avk_compare_run_resident: keep the per-region GroupTypeMetrics rows (2288 B per region) on the device so that
+ * avk_compare_download can return out->region_metrics.  avk_compare_batch* decide from out->region_metrics != NULL. */
+#define AVK_CMP_KEEP_REGION_ROWS 1u
 
 /* MergeConfig, src/merge_solver.rs:62-84 */
 typedef struct avk_merge_cfg {
@@ -233,7 +237,8 @@ typedef struct avk_work_counters {
 
 typedef struct avk_ctx avk_ctx;
 
-/* Create a context bound to one CUDA device (one process per GPU). */
+/* Create a context bound to one CUDA device.  One process may hold one context per
+ * GPU (avk_compare_batch_multi); a context is used by one host thread at a time. */
 int avk_create(int device, avk_ctx **out);
 void avk_destroy(avk_ctx *ctx);
 const char *avk_last_error(const avk_ctx *ctx);
@@ -251,6 +256,26 @@ int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch,
 /* Replaces the par_iter over solve_merge_region (src/main.rs:463-478). */
 int avk_merge_batch(avk_ctx *ctx, const avk_region_batch *batch,
                     const avk_merge_cfg *cfg, avk_merge_out *out);
+
+/* ---- several GPUs of one node behind the same call.  The reference host is ONE process
+ * (src/main.rs:251-271): the region_id-ordered list is cut into contiguous bins balanced by a cost proxy
+ * (avk_partition_regions), bin k is solved on ctxs[k] by its own host thread, every device copies its
+ * slice of the results straight into the caller's arrays at its bin offset, and the bins' summary
+ * counters are added on the host (wrapping u64, like SummaryWriter's AddAssign).  No collective is
+ * needed on the data path; result order == region order (src/main.rs:271).  Every context must hold
+ * the reference (avk_set_reference). */
+int avk_compare_batch_multi(avk_ctx *const *ctxs, uint32_t n_ctx, const avk_region_batch *batch,
+                            const avk_compare_cfg *cfg, avk_compare_out *out);
+int avk_merge_batch_multi(avk_ctx *const *ctxs, uint32_t n_ctx, const avk_region_batch *batch,
+                          const avk_merge_cfg *cfg, avk_merge_out *out);
+/* cuts[0..n_bins]: bin k = regions [cuts[k], cuts[k+1]).  Cost per region: (variants + 1) * window +
+ * sum of max(|allele0|, |allele1|)^2.  Host only. */
+int avk_partition_regions(const avk_region_batch *batch, uint32_t n_bins, uint64_t *cuts);
+/* One bin on one context (the building block of the calls above; also what a one-process-per-GPU
+ * launcher calls with its own bin): regions [lo, hi) are solved and written to out->status[lo..hi) etc.;
+ * totals / strat_totals receive this bin's sums only. */
+int avk_compare_batch_range(avk_ctx *ctx, const avk_region_batch *batch, uint64_t lo, uint64_t hi,
+                            const avk_compare_cfg *cfg, avk_compare_out *out);
 
 /* Batched global edit distance == wfa_ed (src/util/sequence_alignment.rs:9-13).
  * Pair p aligns pool[a_off[p]..+a_len[p]] against pool[b_off[p]..+b_len[p]]. */
@@ -283,8 +308,24 @@ int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t contig, uin
 int avk_regions_download(avk_ctx *ctx, avk_region_batch *out);
 
 int avk_compare_upload(avk_ctx *ctx, const avk_region_batch *batch);
+int avk_compare_upload_range(avk_ctx *ctx, const avk_region_batch *batch, uint64_t lo, uint64_t hi);
 int avk_compare_run_resident(avk_ctx *ctx, const avk_compare_cfg *cfg);
+/* copies the resident bin's results into out->...[lo..hi) / [v_base..) of the caller's arrays */
 int avk_compare_download(avk_ctx *ctx, avk_compare_out *out);
+/* DEVICE addresses of the resident bin's results (valid until the next call on the context): what a
+ * one-process-per-GPU run hands to its single NCCL gather, so that results travel GPU -> root GPU over
+ * NVLink and reach the host in one copy.  totals = [AVK_N_GROUPS*AVK_N_METRICS] sums, type mask, solved
+ * blocks, error blocks (u64 each). */
+typedef struct avk_compare_dev_view {
+    uint64_t lo, n_regions;      /* resident bin = regions [lo, lo + n_regions) of the uploaded batch */
+    uint64_t v_base, n_variants; /* = variants [v_base, v_base + n_variants) of its variant table */
+    void *status;                /* int32  [n_regions] */
+    void *ed1, *ed2;             /* uint32 [n_regions] */
+    void *type_mask;             /* uint16 [n_regions] */
+    void *var_expected, *var_observed, *var_class; /* uint8 [n_variants] */
+    void *totals;                /* uint64 [AVK_N_GROUPS*AVK_N_METRICS + 3] */
+} avk_compare_dev_view;
+int avk_compare_result_device(avk_ctx *ctx, avk_compare_dev_view *view);
 /* Milliseconds spent in the phases of the last resident run (CUDA events on the
  * library's stream): [0] alt_ed kernel, [1] search kernel(s), [2] heavy ED kernel,
  * [3] finalize/reduce, [4] total. */
@@ -299,19 +340,6 @@ int avk_last_tier_ms(avk_ctx *ctx, float *out3);
 int avk_int_peak(avk_ctx *ctx, double *ops_per_s);
 /* Number of kernel launches issued by the library since avk_create. */
 uint64_t avk_launch_count(const avk_ctx *ctx);
-
-/* ------------------------------------------------------ CPU oracle (tests only) */
-
-int orc_compare_batch(const avk_region_batch *batch, const uint8_t *const *contigs,
-                      const uint64_t *contig_lens, uint32_t n_contigs,
-                      const avk_compare_cfg *cfg, avk_compare_out *out,
-                      int n_threads, avk_work_counters *work);
-int orc_build_regions(const avk_callsets *in, uint64_t contig_len, uint32_t contig, uint32_t flank, uint64_t first_region_id,
-                      avk_region_batch *out);
-int orc_merge_batch(const avk_region_batch *batch, const uint8_t *const *contigs,
-                    const uint64_t *contig_lens, uint32_t n_contigs,
-                    const avk_merge_cfg *cfg, avk_merge_out *out,
-                    int n_threads, avk_work_counters *work);
 
 #ifdef __cplusplus
 }

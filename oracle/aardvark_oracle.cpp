@@ -19,7 +19,7 @@
 // line by line: sequences are std::vector<uint8_t>, the priority queue is a
 // binary heap keyed by the reference's (unique) priority tuples.
 
-#include "../include/aardvark_b200.h"
+#include "oracle.h"
 
 #include <algorithm>
 #include <cstdint>

@@ -1,0 +1,34 @@
+/*
+ * oracle.h -- entry points of the CPU ORACLE (oracle/aardvark_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+ *
+ * The oracle takes the product's batch / output structs (include/aardvark_b200.h) so that a batch can be
+ * handed to either side and the outputs compared bit for bit.  Nothing under aardvark_b200/ includes
+ * this header or links liboracle.so; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs do (through oracle/oracle_py.py).
+ */
+#ifndef AARDVARK_ORACLE_H
+#define AARDVARK_ORACLE_H
+
+#include "../include/aardvark_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+
+int orc_compare_batch(const avk_region_batch *batch, const uint8_t *const *contigs,
+                      const uint64_t *contig_lens, uint32_t n_contigs,
+                      const avk_compare_cfg *cfg, avk_compare_out *out,
+                      int n_threads, avk_work_counters *work);
+int orc_build_regions(const avk_callsets *in, uint64_t contig_len, uint32_t contig, uint32_t flank, uint64_t first_region_id,
+                      avk_region_batch *out);
+int orc_merge_batch(const avk_region_batch *batch, const uint8_t *const *contigs,
+                    const uint64_t *contig_lens, uint32_t n_contigs,
+                    const avk_merge_cfg *cfg, avk_merge_out *out,
+                    int n_threads, avk_work_counters *work);
+
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AARDVARK_ORACLE_H */

@@ -20,12 +20,34 @@ _LIB = None
 U64MAX = (1 << 64) - 1
 
 
+def _cpu_tag():
+    """Identifies the host CPU: the oracle is built with -march=native, so a library built on another
+    machine (it travels with the repo snapshot) is rebuilt before it is loaded."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "aardvark_oracle.cpp")
-    hdr = os.path.join(_HERE, "..", "include", "aardvark_b200.h")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    tag_file = so + ".cpu"
+    srcs = [os.path.join(_HERE, "aardvark_oracle.cpp"), os.path.join(_HERE, "oracle.h"), os.path.join(_HERE, "Makefile"),
+            os.path.join(_HERE, "..", "include", "aardvark_b200.h")]
+    tag = _cpu_tag()
+    try:
+        built_for = open(tag_file).read().strip()
+    except OSError:
+        built_for = ""
+    if force or not os.path.exists(so) or built_for != tag or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["make", "-B", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+        with open(tag_file, "w") as f:
+            f.write(tag)
     return so
 
 
