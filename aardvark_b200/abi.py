@@ -141,6 +141,7 @@ class WorkCounters(C.Structure):
         ("matched_bases", C.c_uint64),
         ("search_pops", C.c_uint64),
         ("exact_pops", C.c_uint64),
+        ("alg_bytes", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -828,7 +828,7 @@ struct avk_ctx {
     u32 *h_pin = nullptr;   // pinned host scratch: pipeline counters read back without a blocking copy
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
-    avk_work_counters last_work = {0, 0, 0, 0, 0};
+    avk_work_counters last_work = {0, 0, 0, 0, 0, 0};
     u32 tier_fail[3] = {0, 0, 0};
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side[2] = {nullptr, nullptr};
@@ -917,7 +917,8 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     if (const char *dn = getenv("AVK_DENSE_N")) ctx->dense_n = std::max(3, atoi(dn));
     // test knobs: tiny workspace tiers so that small inputs reach the last-resort code paths (tests/test_gpu_parity.py)
-    if (const char *s = getenv("AVK_TEST_COOP_ARENA_MB")) { ctx->coop_arena0 = std::max(1LL, atoll(s)) << 20; }
+    if (const char *s = getenv("AVK_TEST_COOP_ARENA_MB")) ctx->coop_arena0 = std::max(1LL, atoll(s)) << 20;
+    if (const char *s = getenv("AVK_TEST_COOP_ARENA1_MB")) ctx->coop_arena1 = std::max(1LL, atoll(s)) << 20;
     if (const char *s = getenv("AVK_TEST_COOP_CAP_INTS")) ctx->coop_cap_ints = std::min<int>(COOP_CAP_INTS_MAX, std::max(64, atoi(s)));
     if (const char *s = getenv("AVK_TEST_WIDE_B0")) ctx->wide_b0 = std::max(1, atoi(s));
     for (auto &e : ctx->tev) cudaEventCreate(&e);

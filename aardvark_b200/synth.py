@@ -374,6 +374,36 @@ def workload_chr20(scale: float = 1.0, seed: int = 20):
     return workload_compare(L, SynthParams(n_variants=max(1, int(150_000 * scale))), seed)
 
 
+GRCH38_LENS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422,
+               135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167,
+               46709983, 50818468, 156040895, 57227415]
+
+
+def _wgs_contig(args):
+    i, length, n_variants, seed = args
+    ref, batch = workload_compare(length, SynthParams(n_variants=n_variants), seed)
+    return i, ref, batch
+
+
+def workload_wgs(scale: float = 1.0, seed: int = 38, workers: int = 1):
+    """BASELINE.json configs[2]: whole-genome HG002-like compare -- 24 contigs with GRCh38 lengths (3.09 Gbp at scale 1),
+    ~5 M variants per side, ~3.95 M clusters; contig i uses seed + i.  `scale` shrinks contig lengths and variant counts
+    together.  Returns ([contig arrays], one multi-contig RegionBatch in region_id order).  `workers` > 1 generates the
+    contigs in forked worker processes -- call it BEFORE the process initialises CUDA."""
+    jobs = []
+    for i, L in enumerate(GRCH38_LENS):
+        Ls = max(20000, int(L * scale))
+        jobs.append((i, Ls, max(1, int(5_000_000 * Ls / 3.1e9)), seed + i))
+    if workers > 1:
+        import multiprocessing as mp
+        order = sorted(jobs, key=lambda j: -j[1])          # longest contigs first
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            parts = sorted(pool.imap_unordered(_wgs_contig, order), key=lambda t: t[0])
+    else:
+        parts = [_wgs_contig(j) for j in jobs]
+    return [p[1] for p in parts], RegionBatch.concat([p[2] for p in parts])
+
+
 def workload_sv(scale: float = 1.0, seed: int = 4):
     """BASELINE.json configs[3]: SV / long-indel heavy compare (50 bp - 10 kbp events, min gap 1000),
     with background small variants."""

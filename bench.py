@@ -1,21 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- variant clusters/sec through the compare solve phase (BASELINE.json metric).
+"""bench.py -- variant clusters/sec and whole-genome compare time through the solve phase (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --config chr20|sv|wgs [--scale F]        (default: wgs, scale 1.0)
 
-A "step" is one pass of the hot path (alt_ed + per-cluster solve + summary reduction) over one
-batch: the synthetic chr20-scale compare of BASELINE.json configs[1] (~150k variants per side,
-~118k clusters).  Weak scaling: every rank solves its own chr20-sized contig (seed 20 + rank),
-regions binned by contig across GPUs with no data-path collective; only the per-GPU counters and
-per-variant annotation arrays are gathered (one NCCL gather) in the e2e leg.
+A "step" is one pass of the hot path (alt_ed + cluster digests + per-cluster solve + summary counters) over ONE batch:
+the synthetic whole-genome HG002-like compare of BASELINE.json configs[2] -- 24 contigs with GRCh38 lengths (3.09 Gbp),
+~4.95 M variants per side, ~3.95 M clusters (the phase the reference times as "Comparing regions", src/main.rs:250-272).
+STRONG scaling: the same genome at every N; the region_id-ordered cluster list is cut into N contiguous bins
+(avk_partition_regions) and rank r solves bin r with no data-path collective; one NCCL gather (grouped send/recv over
+NVLink) brings the per-region / per-variant result arrays and the summary counters to rank 0.
 
-  value  clusters/s with the batch already resident in HBM (device time, CUDA events on the
+  value  clusters/s with the batch already resident in HBM (device time of the slowest rank, CUDA events on the
          library's stream, L2 flushed between steps)
-  e2e    clusters/s through the C ABI call with HOST (pinned) buffers: H2D of the batch, kernels,
-         D2H of status/ed/per-variant labels/summary counters inside the timed region
-  --impl reference: the CPU restatement of the reference path (oracle "port", OpenMP over clusters,
-         all host threads) on the same batch -- the reference is Rust and cannot be built here.
+  e2e    clusters/s through the C ABI with HOST (pinned) buffers, wall clock: H2D of the bin, kernels, the gather
+         (N > 1) and the D2H of status / ed / per-variant labels / summary counters inside the timed region
+         => e2e.seconds_per_genome is the "WGS compare wall-time" half of the metric
+  --impl reference: the CPU restatement of the reference path (oracle "port"; the reference is Rust and cannot be
+         built here) on the SAME whole batch, OpenMP over clusters on ALL host cores, whatever N is.
 """
 import argparse
 import json
@@ -23,7 +26,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -35,18 +37,27 @@ METRIC = "variant_clusters_per_sec"
 UNIT = "clusters/s"
 
 
-def workload(rank, scale):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload(config, scale, workers):
+    """([contig arrays], RegionBatch, description).  Called before CUDA is initialised (forks workers)."""
     from aardvark_b200 import synth
-    return synth.workload_chr20(scale=scale, seed=20 + rank)
-
-
-def algorithmic_bytes(batch):
-    """Compulsory HBM bytes of one solve pass as laid out (DESIGN.md 'algorithmic bytes'): every input
-    array read once, the reference window of every cluster read once, every output written once."""
-    from aardvark_b200 import abi
-    win = int((batch.end.astype(np.int64) - batch.start.astype(np.int64)).sum())
-    out_bytes = batch.n_regions * (4 + 4 + 4 + 2 + 8 * abi.N_GROUPS * abi.N_METRICS) + 3 * batch.n_variants
-    return batch.nbytes() + 4 * batch.n_variants + win + out_bytes
+    if config == "wgs":
+        refs, batch = synth.workload_wgs(scale=scale, seed=38, workers=workers)
+        return refs, batch, (f"WGS HG002-like synthetic compare (BASELINE configs[2]): 24 contigs with GRCh38 lengths, "
+                             f"{sum(r.size for r in refs) / 1e9:.2f} Gbp, scale={scale}, seed=38+contig")
+    if config == "chr20":
+        ref, batch = synth.workload_chr20(scale=scale, seed=20)
+        return [ref], batch, f"chr20-scale synthetic compare (BASELINE configs[1]), scale={scale}, seed=20"
+    if config == "sv":
+        ref, batch = synth.workload_sv(scale=scale, seed=4)
+        return [ref], batch, f"SV / long-indel heavy synthetic compare (BASELINE configs[3]), scale={scale}, seed=4"
+    raise SystemExit(f"unknown --config {config}")
 
 
 class ClockSampler:
@@ -106,32 +117,44 @@ def pin_batch(batch):
                        f(batch.allele_off), f(batch.a0_len), f(batch.a1_len), f(batch.allele_pool))
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; the Rust crate cannot be built here)."""
+def bin_h2d_bytes(batch, lo, hi):
+    """Bytes the library uploads for bin [lo, hi) (region_id stays on the host)."""
+    k = batch.n_inputs
+    v0, v1 = int(batch.var_off[lo * k]), int(batch.var_off[hi * k])
+    pool = 0
+    if v1 > v0:
+        pool = int(batch.allele_off[v1 - 1]) + int(batch.a0_len[v1 - 1]) + int(batch.a1_len[v1 - 1]) - int(batch.allele_off[v0])
+    return (hi - lo) * 12 + ((hi - lo) * k + 1) * 8 + (v1 - v0) * 22 + pool
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port; the Rust crate cannot be built here) on the SAME whole
+    batch the GPU arm solves, on all host cores (torchrun's OMP_NUM_THREADS=1 is overridden explicitly)."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as orc
     from aardvark_b200 import abi
-    ref, batch = workload(0, args.scale)
+    cores = host_cores()
+    refs, batch, desc = workload(args.config, args.scale, cores)
     cfg = abi.CompareCfg(50, 0, 0, 0)
-    threads = orc.num_threads()
-    for _ in range(args.warmup):
-        orc.compare_batch(batch, [ref], cfg, n_threads=threads)
+    for _ in range(min(args.warmup, 1)):
+        orc.compare_batch(batch, refs, cfg, n_threads=cores, region_metrics=False)
+    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.compare_batch(batch, [ref], cfg, n_threads=threads)
+    for _ in range(steps):
+        orc.compare_batch(batch, refs, cfg, n_threads=cores, region_metrics=False)
     dt = time.perf_counter() - t0
-    v = batch.n_regions * args.steps / dt
+    v = batch.n_regions * steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"chr20-scale synthetic compare (BASELINE configs[1]), scale={args.scale}, seed=20",
-                   "regions_per_step": batch.n_regions, "variants_per_step": batch.n_variants, "max_branch_factor": 50},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"whole batch ({batch.n_regions} clusters) x {args.steps} steps, OpenMP dynamic over clusters"},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": desc, "regions_per_step": batch.n_regions, "variants_per_step": batch.n_variants, "max_branch_factor": 50},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"the whole batch ({batch.n_regions} clusters) x {steps} steps (capped at 5), OpenMP dynamic over clusters, "
+                                   "solve phase only; oracle built -O3 -march=native -flto on this host"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "seconds_per_genome": dt / steps},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -143,7 +166,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the chr20-scale workload (tests only; default = full)")
+    ap.add_argument("--config", default="wgs", choices=["wgs", "chr20", "sv"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named workload (tests only; default = full)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -153,14 +177,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
+
+    # ---------------- workload: generated before CUDA is touched (forked workers), identical on every rank --------------
+    t_gen = time.perf_counter()
+    refs, batch, desc = workload(args.config, args.scale, max(1, host_cores() // world))
+    t_gen = time.perf_counter() - t_gen
 
     import torch
     import torch.distributed as dist
-    from aardvark_b200 import abi
     from aardvark_b200.batch import CompareOutputs
-    from aardvark_b200.dist import gather_compare_outputs
+    from aardvark_b200.dist import DeviceGather, partition_regions
     from aardvark_b200.lib import Solver
     from aardvark_b200.types import CompareConfig
 
@@ -173,9 +201,15 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    ref, batch = workload(rank, args.scale)
+    k = batch.n_inputs
+    bins = partition_regions(batch, world)
+    var_bins = [(int(batch.var_off[lo * k]), int(batch.var_off[hi * k])) for lo, hi in bins]
+    lo, hi = bins[rank]
+    n_bin = hi - lo
     solver = Solver(local_rank)
-    solver.set_reference([ref])
+    # this rank's GPU holds the contigs its bin touches (all of them at N = 1)
+    used = set(np.unique(batch.contig[lo:hi]).tolist())
+    solver.set_reference([r if i in used else r[:0] for i, r in enumerate(refs)])
     cfg = CompareConfig(enable_sequences=False)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -185,58 +219,79 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- resident leg: `value` -------------------------------------------------------
-    solver.upload(batch)
+    solver.upload(batch, lo, hi)
     for _ in range(args.warmup):
         solver.run_resident(cfg)
     launches0 = solver.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
-    dev_ms, search_ms = 0.0, 0.0
+    dev_ms, pipe_ms = 0.0, 0.0
+    tier_ms = np.zeros(3)
     for _ in range(args.steps):
         l2_flush.zero_()
         torch.cuda.synchronize()
         solver.run_resident(cfg)           # returns after its CUDA events (own stream) have completed
         tm = solver.last_timings_ms()
         dev_ms += tm["total"]
-        search_ms += tm["search"]
+        pipe_ms += tm["search"]
+        tier_ms += np.array(solver.last_tier_ms())
     barrier()
     launches = solver.launch_count() - launches0
     work = solver.last_work()
-    resident_out = solver.download(CompareOutputs(batch, region_metrics=False))
+    resident_out = CompareOutputs(batch, region_metrics=False)
+    solver.download(resident_out)
 
     # ---------------- e2e leg: host buffers through the C ABI ----------------------------------------
     pbatch = pin_batch(batch)
     out = CompareOutputs(pbatch, region_metrics=False)
-    for f in ("status", "ed1", "ed2", "type_mask", "var_expected", "var_observed", "var_class"):
+    OUT_FIELDS = ("status", "ed1", "ed2", "type_mask", "var_expected", "var_observed", "var_class")
+    for f in OUT_FIELDS:
         setattr(out, f, pinned_copy(getattr(out, f)))
+    gather = DeviceGather(bins, var_bins, rank) if world > 1 else None
+    merged = None
+
+    def e2e_step():
+        nonlocal merged
+        if world == 1:
+            solver.compare_batch(pbatch, cfg, out=out)                 # H2D + kernels + D2H in one C-ABI call
+        else:
+            solver.upload(pbatch, lo, hi)                              # H2D of this rank's bin
+            solver.run_resident(cfg)
+            merged = gather.gather(solver.result_device_view())        # ONE NCCL gather to rank 0 + its D2H
+
     for _ in range(3):
-        solver.compare_batch(pbatch, cfg, out=out)
-        if world > 1:
-            gather_compare_outputs(out, pbatch.n_regions, pbatch.n_variants)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        solver.compare_batch(pbatch, cfg, out=out)
-        if world > 1:
-            gather_compare_outputs(out, pbatch.n_regions, pbatch.n_variants)
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
-    assert out.diff(resident_out) == [], "e2e and resident outputs differ"
-    h2d = pbatch.nbytes()
-    d2h = sum(getattr(out, f).nbytes for f in ("status", "ed1", "ed2", "type_mask", "var_expected", "var_observed", "var_class")) \
-        + out.totals.nbytes + 24
+    h2d = bin_h2d_bytes(batch, lo, hi)
+    if world == 1:
+        assert out.diff(resident_out) == [], "e2e and resident outputs differ"
+        d2h = sum(getattr(out, f).nbytes for f in OUT_FIELDS) + out.totals.nbytes + 24
+        solved, errors = int(out.solved_blocks[0]), int(out.error_blocks[0])
+    else:
+        d2h = gather.d2h_bytes() if rank == 0 else 0
+        solved = errors = 0
+        if rank == 0:
+            solved, errors = merged["solved"], merged["errors"]
+            for f in OUT_FIELDS:       # this rank's bin of the gathered arrays == its own resident result
+                a, b = ((var_bins[0][0], var_bins[0][1]) if f.startswith("var_") else (lo, hi))
+                assert np.array_equal(merged[f][a:b], getattr(resident_out, f)[a:b]), f"gathered {f} differs from the resident result"
 
-    # ---------------- aggregate over ranks: max time, summed clusters --------------------------------
-    stats = torch.tensor([dev_ms, e2e_s * 1e3, search_ms], dtype=torch.float64, device="cuda")
-    counts = torch.tensor([batch.n_regions, batch.n_variants, int(out.solved_blocks[0]), int(out.error_blocks[0]), h2d, d2h],
-                          dtype=torch.int64, device="cuda")
+    # ---------------- aggregate over ranks: max time, summed bytes --------------------------------
+    stats = torch.tensor([dev_ms, e2e_s * 1e3, pipe_ms], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([n_bin, h2d, d2h, launches], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max, search_ms_max = (float(x) for x in stats.tolist())
-    n_regions, n_variants, solved, errors, h2d_all, d2h_all = (int(x) for x in counts.tolist())
+    dev_ms_max, e2e_ms_max, pipe_ms_max = (float(x) for x in stats.tolist())
+    n_solved_regions, h2d_all, d2h_all, launches_all = (int(x) for x in counts.tolist())
+    assert n_solved_regions == batch.n_regions
 
     if rank == 0:
         peaks = {}
@@ -246,69 +301,85 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        alg_bytes = algorithmic_bytes(batch)
-        k_ms = search_ms / args.steps                       # rank 0's dominant kernel (k_compare, all tiers)
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        k_ms = pipe_ms / args.steps                        # rank 0's compare pipeline (all solver kernels between prepare and fold)
         int_peak = solver.int_peak_ops_per_s()
         int_ops = 6 * work["cells"] + 4 * ((work["matched_bases"] + 15) // 16)
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "k_compare_traffic.json")))
-            if abs(prof.get("scale", -1) - args.scale) < 1e-9:
-                traffic = prof.get("dram_bytes_per_launch")
-        except (OSError, ValueError):
-            pass
         line = {
-            "metric": METRIC, "value": n_regions * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": batch.n_regions * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"chr20-scale synthetic compare (BASELINE configs[1]) per GPU, scale={args.scale}, seed=20+rank",
-                       "regions_per_step": n_regions, "variants_per_step": n_variants, "max_branch_factor": 50,
-                       "l2": "flushed between timed steps (256 MiB write)", "solved_blocks": solved, "error_blocks": errors,
-                       "partition": "one contig bin per GPU, no data-path collective; single gather of results in e2e"},
-            "e2e": {"value": n_regions * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "ms_per_step": e2e_ms_max / args.steps},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "kernel": "k_compare", "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
-                         "peak_source": peak_src,
-                         "note": "integer DP: the binding roof is the INT32 ALU pipe / latency, see int_roofline"},
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": desc, "regions_per_step": batch.n_regions, "variants_per_step": batch.n_variants,
+                       "max_branch_factor": 50, "l2": "flushed between timed steps (256 MiB write)",
+                       "solved_blocks": solved, "error_blocks": errors,
+                       "partition": f"{world} contiguous region bin(s) balanced by the cost proxy, no data-path collective; "
+                                    "single NCCL gather of results to rank 0 in e2e",
+                       "regions_per_rank": [b - a for a, b in bins], "generation_s": round(t_gen, 1)},
+            "e2e": {"value": batch.n_regions * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "ms_per_step": e2e_ms_max / args.steps,
+                    "seconds_per_genome": e2e_ms_max / args.steps / 1e3},
+            "gpu_launches": launches_all,
             # executed on the device (closed forms and pruned searches do less than the reference algorithm);
             # replaced below by the reference algorithm's own counts when the CPU leg runs
             "int_roofline": {"achieved_gops": int_ops / (k_ms * 1e-3) / 1e9, "peak_gops": int_peak / 1e9,
                              "frac": int_ops / (k_ms * 1e-3) / int_peak, "algorithmic_int_ops": int_ops,
-                             "ops_counted_by": "device counters (work actually executed)",
+                             "ops_counted_by": "device counters (work actually executed by rank 0's bin)",
                              "cells": work["cells"], "matched_bases": work["matched_bases"],
                              "search_pops": work["search_pops"], "exact_pops": work["exact_pops"],
                              "peak_source": "measured live (avk_int_peak: add/max/xor chains)"},
+            "phases_ms": {"alt_ed+digests": (dev_ms - pipe_ms) / args.steps, "solver_pipeline": k_ms,
+                          "closed_form+dense_stage": float(tier_ms[0]) / args.steps,
+                          "search+score+27KB_stage": float(tier_ms[1]) / args.steps, "2MB_stage": float(tier_ms[2]) / args.steps},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        alg_bytes = None
+        if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle_py as orc
             from aardvark_b200.lib import compare_cfg
-            threads = orc.num_threads()
+            threads = host_cores()
             best = None
             cpu_out = None
             reps = 3
             for _ in range(reps):
                 t0 = time.perf_counter()
-                cpu_out = orc.compare_batch(batch, [ref], compare_cfg(cfg), n_threads=threads, region_metrics=False)
+                cpu_out = orc.compare_batch(batch, refs, compare_cfg(cfg), n_threads=threads, region_metrics=False)
                 dt = time.perf_counter() - t0
                 best = dt if best is None else min(best, dt)
             # algorithmic work = what the reference algorithm computes, counted by the CPU restatement
-            _, cw = orc.compare_batch(batch, [ref], compare_cfg(cfg), n_threads=threads, region_metrics=False, work=True)
+            _, cw = orc.compare_batch(batch, refs, compare_cfg(cfg), n_threads=threads, region_metrics=False, work=True)
             ref_ops = 6 * cw["cells"] + 4 * ((cw["matched_bases"] + 15) // 16)
+            alg_bytes = cw["alg_bytes"]
             ir = line["int_roofline"]
-            ir.update({"device_executed": {k: ir[k] for k in ("algorithmic_int_ops", "cells", "matched_bases", "search_pops", "exact_pops")},
+            ir.update({"device_executed": {kk: ir[kk] for kk in ("algorithmic_int_ops", "cells", "matched_bases", "search_pops", "exact_pops")},
                        "achieved_gops": ref_ops / (k_ms * 1e-3) / 1e9, "frac": ref_ops / (k_ms * 1e-3) / int_peak,
                        "algorithmic_int_ops": ref_ops, "cells": cw["cells"], "matched_bases": cw["matched_bases"],
-                       "search_pops": cw["search_pops"], "exact_pops": cw["exact_pops"],
+                       "search_pops": cw["search_pops"], "exact_pops": cw["exact_pops"], "alignments": cw["alignments"],
                        "ops_counted_by": "CPU restatement of the reference algorithm (6*cells + 4*ceil(matched/16))"})
             line["cpu_baseline"] = {"value": batch.n_regions / best, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"rank 0's whole batch ({batch.n_regions} clusters), best of {reps}, "
+                                    "sample": f"the whole batch ({batch.n_regions} clusters), best of {reps}, "
                                               "OpenMP dynamic over clusters, solve phase only",
+                                    "seconds_per_genome": best,
                                     "matches_gpu_bit_exact": out.diff(cpu_out) == []}
+        traffic, traffic_src = None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r2_pipeline_traffic.json")))
+            if prof.get("config") == args.config and abs(prof.get("scale", -1) - args.scale) < 1e-9:
+                traffic, traffic_src = prof.get("dram_bytes_per_step"), prof.get("source")
+        except (OSError, ValueError):
+            pass
+        if alg_bytes is not None:
+            achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                                "traffic": traffic, "traffic_source": traffic_src, "kernel": "compare pipeline (solver kernels of one pass)",
+                                "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
+                                "algorithmic_bytes_definition": "SURVEY 8(d): sum over the reference algorithm's global alignments of "
+                                                                "ceil(|a|/4) + ceil(|b|/4) + 8, counted by the CPU restatement",
+                                "peak_source": peak_src,
+                                "note": "integer DP: the binding roof is the INT32 ALU pipe / latency, see int_roofline"}
+        else:
+            line["roofline"] = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": traffic,
+                                "kernel": "compare pipeline", "kernel_ms": k_ms, "peak_source": peak_src,
+                                "note": "algorithmic bytes are counted by the CPU leg, which runs at N = 1 only"}
         print(json.dumps(line))
     solver.close()
     if world > 1:

@@ -231,6 +231,7 @@ typedef struct avk_work_counters {
     uint64_t matched_bases;  /* bases walked by extend() */
     uint64_t search_pops;    /* optimize_sequences pops */
     uint64_t exact_pops;     /* optimize_gt_alleles pops */
+    uint64_t alg_bytes;      /* sum over alignments of ceil(|a|/4) + ceil(|b|/4) + 8 (CPU oracle only; GPU leaves 0) */
 } avk_work_counters;
 
 /* ------------------------------------------------------ GPU library (product) */

@@ -38,10 +38,10 @@ namespace orc {
 using Seq = std::vector<uint8_t>;
 
 struct Work {
-    uint64_t alignments = 0, cells = 0, matched = 0, search_pops = 0, exact_pops = 0;
+    uint64_t alignments = 0, cells = 0, matched = 0, search_pops = 0, exact_pops = 0, alg_bytes = 0;
     void add(const Work &o) {
         alignments += o.alignments; cells += o.cells; matched += o.matched;
-        search_pops += o.search_pops; exact_pops += o.exact_pops;
+        search_pops += o.search_pops; exact_pops += o.exact_pops; alg_bytes += o.alg_bytes;
     }
 };
 static thread_local Work *tl_work = nullptr;
@@ -118,7 +118,7 @@ struct DWFALite {
     // finalize(): :183-198 -- stop when one diagonal is at the end of BOTH sequences (:192)
     DErr finalize(const uint8_t *b, size_t lb, const uint8_t *o, size_t lo) {
         if (finalized) return DErr::AlreadyFinalized;
-        if (tl_work) tl_work->alignments += 1;
+        if (tl_work) { tl_work->alignments += 1; tl_work->alg_bytes += (lb + 3) / 4 + (lo + 3) / 4 + 8; }   // 2-bit bases + 8
         extend(b, lb, o, lo);
         while (!reached_full(lb, lo)) {
             DErr e = increase(b, lb, o, lo);
@@ -1092,6 +1092,7 @@ int orc_compare_batch(const avk_region_batch *b, const uint8_t *const *contigs, 
     if (work) {
         work->alignments = total_work.alignments; work->cells = total_work.cells; work->matched_bases = total_work.matched;
         work->search_pops = total_work.search_pops; work->exact_pops = total_work.exact_pops;
+        work->alg_bytes = total_work.alg_bytes;
     }
     return AVK_OK;
 }
@@ -1136,6 +1137,7 @@ int orc_merge_batch(const avk_region_batch *b, const uint8_t *const *contigs, co
     if (work) {
         work->alignments = total_work.alignments; work->cells = total_work.cells; work->matched_bases = total_work.matched;
         work->search_pops = total_work.search_pops; work->exact_pops = total_work.exact_pops;
+        work->alg_bytes = total_work.alg_bytes;
     }
     return AVK_OK;
 }

@@ -270,7 +270,7 @@ def test_build_regions_vs_host_builder(solver):
         _same_batch(dev, host)
     host = synth.cluster_regions(inputs, len(ref), 50)
     solver.build_regions(CallSets(inputs), 0, 50, download=False)
-    solver.run_resident(CompareConfig(enable_sequences=False))
+    solver.run_resident(CompareConfig(enable_sequences=False), region_metrics=True)
     built = solver.download(CompareOutputs(host))
     assert built.diff(solver.compare_batch(host, CompareConfig(enable_sequences=False))) == []
     # K = 5 call sets with dropout (merge inputs), first_region_id offset
@@ -345,10 +345,204 @@ def test_resident_mode_matches_batch_mode(solver):
     solver.set_reference([ref])
     a = solver.compare_batch(batch, CompareConfig(enable_sequences=False))
     solver.upload(batch)
-    solver.run_resident(CompareConfig(enable_sequences=False))
-    solver.run_resident(CompareConfig(enable_sequences=False))   # idempotent
+    solver.run_resident(CompareConfig(enable_sequences=False), region_metrics=True)
+    solver.run_resident(CompareConfig(enable_sequences=False), region_metrics=True)   # idempotent
     b = solver.download(CompareOutputs(batch))
     assert a.diff(b) == []
+    # without per-region rows: the summary counters come from the in-kernel totals alone and must be the same
+    solver.run_resident(CompareConfig(enable_sequences=False))
+    c = solver.download(CompareOutputs(batch, region_metrics=False))
+    assert a.diff(c) == []
+    with pytest.raises(Exception):
+        solver.download(CompareOutputs(batch))               # rows were not kept by that run
     assert solver.launch_count() > 0
     w = solver.last_work()
     assert w["search_pops"] > 0 and w["alignments"] > 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Round-2 parity tests: the regimes the first round's driver-run suite did not reach
+
+def _sv_corner_batch(seed=91):
+    """Hand-made SV clusters (min gap 1000, region_generation.rs:621-626 admits alleles up to 10 kbp): single events of
+    6 / 8 / 10 kbp as INS and DEL (identical on both sides, hom and het), a sequence-divergent 6 kbp INS, a right-shifted
+    representation of a tandem INS, a 3 kbp DEL against a 2 kbp INS at the same place (last row),
+    an FN and an FP event."""
+    rng = np.random.default_rng(seed)
+    ref = synth.random_reference(260_000, rng)
+    T, Q = [], []
+    rs = lambda n: synth._rand_seq(rng, n)
+    pos = 3000
+
+    def ins(p, n, tandem=False):
+        anchor = bytes([int(ref[p])])
+        body = ref[p + 1:p + 1 + n].tobytes() if tandem else rs(n)
+        return p, anchor, anchor + body
+
+    def dele(p, n):
+        return p, ref[p:p + 1 + n].tobytes(), bytes([int(ref[p])])
+
+    HOM, HET, H01 = abi.ZYG_HOM_ALT, abi.ZYG_UNPHASED_HET, abi.ZYG_PHASED_HET01
+    for n, zt, zq in ((6000, HOM, HOM), (8000, HET, H01), (10000, H01, HET)):
+        p, a0, a1 = ins(pos, n); T.append(synth.make_rec(p, a0, a1, zt, sv=True)); Q.append(synth.make_rec(p, a0, a1, zq, sv=True)); pos += 14000
+        p, a0, a1 = dele(pos, n); T.append(synth.make_rec(p, a0, a1, zt, sv=True)); Q.append(synth.make_rec(p, a0, a1, zq, sv=True)); pos += 14000 + n
+    # divergent insertion: ~2 % substitutions inside the inserted sequence
+    p, a0, a1 = ins(pos, 6000)
+    arr = np.frombuffer(a1, dtype=np.uint8).copy()
+    idx = rng.integers(1, arr.size, size=120)
+    arr[idx] = synth.ACGT[rng.integers(0, 4, size=120)]
+    T.append(synth.make_rec(p, a0, a1, HOM, sv=True)); Q.append(synth.make_rec(p, a0, arr.tobytes(), HOM, sv=True)); pos += 14000
+    # tandem duplication, query right-shifted inside the repeat (same haplotype, other record)
+    p, a0, a1 = ins(pos, 7000, tandem=True)
+    sh = synth._shift_insertion(ref, p, a0, a1, rng)
+    T.append(synth.make_rec(p, a0, a1, HET, sv=True)); Q.append(synth.make_rec(sh[0], sh[1], sh[2], HET, sv=True)); pos += 16000
+    # 3 kbp deletion vs 2 kbp insertion at the same position
+    p, a0, a1 = dele(pos, 3000); T.append(synth.make_rec(p, a0, a1, HOM, sv=True))
+    p, a0, a1 = ins(pos, 2000); Q.append(synth.make_rec(p, a0, a1, HOM, sv=True)); pos += 12000
+    # false negative (9 kbp DEL missing from the query) and false positive (6.5 kbp INS only in the query)
+    p, a0, a1 = dele(pos, 9000); T.append(synth.make_rec(p, a0, a1, HET, sv=True)); pos += 20000
+    p, a0, a1 = ins(pos, 6500); Q.append(synth.make_rec(p, a0, a1, HOM, sv=True)); pos += 12000
+    assert pos < ref.size - 12000
+    return ref, synth.cluster_regions([T, Q], ref.size, 1000)
+
+
+def test_compare_sv_6_to_10kbp_vs_oracle(solver):
+    """configs[3] goes to 10 kbp events: edit distances up to ~10^4, wavefronts 2 * 10^4 wide (dynamic_wfa.rs:452-468 is
+    the reference's own wide vector, ED 5278)."""
+    ref, batch = _sv_corner_batch()
+    assert int(np.maximum(batch.a0_len, batch.a1_len).max()) == 10001
+    solver.set_reference([ref])
+    gpu, cpu = _both_compare(solver, batch, [ref], CompareConfig(enable_sequences=False))
+    assert gpu.diff(cpu) == []
+    assert int(gpu.error_blocks[0]) == 0 and int(gpu.solved_blocks[0]) == batch.n_regions
+    assert int(max(gpu.ed1.max(), gpu.ed2.max())) >= 9000          # the FN deletion: ED(truth hap, query hap) ~ its length
+
+
+def _solver_with_env(**env):
+    """A context of its own created under test knobs (read once in avk_create)."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return Solver(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_compare_forced_last_resort_tiers_vs_oracle():
+    """The 2 GB cooperative tier and the DWFA_COOP_SPILL fallback (a wavefront that outgrows shared memory is finished on
+    the warp path) are reached by a fraction of a per cent of configs[3]; test knobs shrink the tiers so that a small SV
+    batch drives every cluster with an edit-distance bound >= 32 through them."""
+    p = synth.SynthParams(n_variants=120, sv_events=30, sv_min=60, sv_max=900, flank=1000)
+    ref, batch = synth.workload_compare(250_000, p, seed=45)
+    cfg = CompareConfig(enable_sequences=False)
+    cpu = orc.compare_batch(batch, [ref], compare_cfg(cfg))
+    # (1) tiny first cooperative tier: clusters overflow it and finish in the last-resort tier
+    # (2) tiny shared-memory wavefront: the CTA-wide DWFA spills back to the warp path mid-alignment
+    for env in (dict(AVK_TEST_WIDE_B0=32, AVK_TEST_COOP_ARENA_MB=1, AVK_TEST_COOP_ARENA1_MB=256),
+                dict(AVK_TEST_WIDE_B0=32, AVK_TEST_COOP_CAP_INTS=200)):
+        s = _solver_with_env(**env)
+        try:
+            s.set_reference([ref])
+            gpu = s.compare_batch(batch, cfg)
+            assert gpu.diff(cpu) == [], env
+            assert s.last_tier_overflow()[2] > 0, "no cluster reached the cooperative tiers"
+        finally:
+            s.close()
+
+
+def test_merge_k5_tenth_chr20_vs_oracle(solver):
+    """configs[4] shape: 5 call sets with per-set error rates and 5 % dropout, majority voting, 0.1 x chr20."""
+    ref, batch = synth.workload_merge(int(synth.CHR20_LEN * 0.1), 15_000, n_sets=5, seed=38)
+    solver.set_reference([ref])
+    cfg = MergeConfig(majority_voting_enabled=True)
+    gpu = solver.merge_batch(batch, cfg)
+    cpu = orc.merge_batch(batch, [ref], merge_cfg(cfg), n_threads=orc.num_threads())
+    assert gpu.diff(cpu) == []
+    assert batch.n_regions > 10_000 and len(set(gpu.classification.tolist())) >= 3
+
+
+def test_wgs_24_contigs_and_8_bin_sharding_vs_oracle(solver):
+    """configs[2] at 1/20 scale: 24 contigs in one batch, bit-exact against the oracle; then the multi-GPU property --
+    8 contiguous bins solved separately (avk_compare_batch_range writes each bin at its offset of ONE output set)
+    reproduce the whole batch, and the bins' counters add up to its totals."""
+    from aardvark_b200.dist import partition_regions
+    refs, batch = synth.workload_wgs(scale=0.05, seed=38, workers=1)
+    assert len(refs) == 24 and batch.n_regions > 150_000
+    solver.set_reference(refs)
+    cfg = CompareConfig(enable_sequences=False)
+    gpu, cpu = _both_compare(solver, batch, refs, cfg)
+    assert gpu.diff(cpu) == []
+    bins = partition_regions(batch, 8)
+    assert bins[0][0] == 0 and bins[-1][1] == batch.n_regions and all(a[1] == b[0] for a, b in zip(bins, bins[1:]))
+    sharded = CompareOutputs(batch)
+    tot = np.zeros_like(gpu.totals)
+    solved = 0
+    for lo, hi in bins:
+        solver.compare_batch_range(batch, lo, hi, cfg, out=sharded)
+        tot += sharded.totals
+        solved += int(sharded.solved_blocks[0])
+    sharded.totals[...] = tot
+    sharded.solved_blocks[0] = solved
+    sharded.totals_mask[0] = gpu.totals_mask[0]
+    assert sharded.diff(gpu) == []
+
+
+def test_multi_context_entry_point_vs_single(solver):
+    """avk_compare_batch_multi / avk_merge_batch_multi: one host thread per context inside the library, contiguous bins,
+    results written at the bins' offsets, counters added on the host.  Uses two GPUs when the box has them, else two
+    contexts on GPU 0 (the same code path: a context per bin)."""
+    import torch
+    from aardvark_b200.lib import MultiSolver
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    ref, batch = synth.workload_chr20(scale=0.02, seed=23)
+    solver.set_reference([ref])
+    cfg = CompareConfig(enable_sequences=False)
+    strat_off = np.arange(batch.n_regions + 1, dtype=np.uint64)
+    strat_idx = (np.arange(batch.n_regions) % 3).astype(np.uint32)
+    one = solver.compare_batch(batch, cfg, strat_off=strat_off, strat_idx=strat_idx, n_strata=3)
+    one_tot = solver.compare_batch(batch, cfg, region_metrics=False)
+    m = MultiSolver(devs + devs[:1])          # three bins
+    try:
+        m.set_reference([ref])
+        multi = m.compare_batch(batch, cfg, strat_off=strat_off, strat_idx=strat_idx, n_strata=3)
+        assert multi.diff(one) == []
+        assert m.compare_batch(batch, cfg, region_metrics=False).diff(one_tot) == []
+        refm, mb = synth.workload_merge(200_000, 600, n_sets=5, seed=9)
+        solver.set_reference([refm])
+        m.set_reference([refm])
+        mc = MergeConfig(majority_voting_enabled=True)
+        assert m.merge_batch(mb, mc).diff(solver.merge_batch(mb, mc)) == []
+    finally:
+        m.close()
+
+
+def test_wfa_ed_100k_random_pairs_vs_oracle(solver):
+    """10^5 random pairs, lengths up to 2 kbp (SURVEY section 7's minimum slice): substitutions, insertions, deletions and
+    block moves; GPU batched wfa_ed against the oracle's (sequence_alignment.rs:9-13)."""
+    rng = np.random.default_rng(2024)
+    n_pairs = 100_000
+    lens = np.minimum(2000, (rng.exponential(220.0, n_pairs)).astype(np.int64))
+    lens[::97] = 2000
+    lens[::101] = 0
+    pairs = []
+    for i in range(n_pairs):
+        n = int(lens[i])
+        a = synth.ACGT[rng.integers(0, 4, size=n)]
+        b = a
+        k = int(rng.integers(0, 9))
+        if k and n:
+            b = a.copy()
+            where = rng.integers(0, n, size=k)
+            b[where] = synth.ACGT[rng.integers(0, 4, size=k)]
+            if i % 3 == 0:                                    # an indel block
+                c = int(rng.integers(0, n)); ln = int(rng.integers(1, 40))
+                b = np.concatenate([b[:c], b[c + ln:]]) if i % 2 else np.concatenate([b[:c], synth.ACGT[rng.integers(0, 4, size=ln)], b[c:]])
+        pairs.append((a.tobytes(), b.tobytes()))
+    gpu = solver.wfa_ed_batch(pairs)
+    cpu = np.array([orc.wfa_ed(a, b) for a, b in pairs], dtype=np.uint32)
+    assert np.array_equal(gpu, cpu)
+    assert int(cpu.max()) > 30 and int((cpu == 0).sum()) > 1000

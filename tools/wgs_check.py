@@ -28,7 +28,7 @@ s = Solver(0); s.set_reference(contigs)
 cfg = CompareConfig(enable_sequences=False)
 s.upload(batch)
 for _ in range(3):
-    s.run_resident(cfg)
+    s.run_resident(cfg, region_metrics=True)
 t = s.last_timings_ms()
 print(f"device: total {t['total']:.2f} ms, search {t['search']:.2f} ms -> {batch.n_regions / t['total'] / 1e3:.2f} M clusters/s; tiers",
       [round(x, 2) for x in s.last_tier_ms()], "overflow", s.last_tier_overflow())
