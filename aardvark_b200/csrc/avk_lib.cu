@@ -23,6 +23,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "avk_solver.cuh"
+#include "avk_thread_solver.cuh"
 
 using namespace avk;
 
@@ -653,6 +654,77 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
     asm volatile("bar.sync %0, 128;" ::"r"(B.bar) : "memory");   // releases the helpers
 }
 
+// ---- thread per cluster -------------------------------------------------------------------------------------------------
+// The common non-closed-form cluster (a few variants, a window of a few hundred bases, edit distances of a few units) is
+// solved by ONE thread (avk_thread_solver.cuh): 32 clusters per warp instead of one, a 1.1 KB workspace per thread in shared
+// memory (search nodes are 12-byte queue entries, sequences are never materialised).  Threads pull clusters from the list W
+// one at a time; a cluster that does not fit the fixed workspace is appended to the reject list -- nothing has been written
+// for it -- and goes through the warp kernels (search / score / fused stages) as before.
+enum { THREAD_TPB = 192 };
+__global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, TierArgs t) {
+    avk_ts::Work &w = ((avk_ts::Work *)avk_dyn_smem)[threadIdx.x];
+    avk_ts::Counters ctr = {0, 0, 0, 0, 0};
+    const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
+    const bool enabled = !cfg.enable_exact_shortcut && !(out.seq_off && cfg.enable_sequences);
+    unsigned long long *slot = out.tot_slots ? out.tot_slots + (size_t)(blockIdx.x & (TOT_SLOTS - 1)) * TOT_STRIDE : nullptr;
+    for (;;) {
+        const u32 idx = atomicAdd(t.work_ctr, 1u);
+        if (idx >= n_work) break;
+        const u32 r = t.work_list[idx];
+        int rc = avk_ts::TS_REJECT;
+        avk_ts::Cluster cl;
+        avk_ts::Solution sol;
+        if (enabled) {
+            const u32 c = b.contig[r];
+            if (c >= b.n_contigs || b.start[r] > b.end[r] || (u64)b.end[r] > b.contig_len[c] || b.end[r] > 0x7fff0000u || (int)cfg.max_branch_factor <= 0)
+                rc = AVK_ST_BAD_INPUT;
+            else {
+                rc = avk_ts::load_cluster(b.digest + b.digest_off[r], b.contig_ptr[c], (int)b.start[r], (int)b.end[r], (int)cfg.max_branch_factor, cl, w);
+                if (rc == AVK_ST_OK) rc = avk_ts::solve_compare(cl, w, ctr, sol);
+            }
+        }
+        if (rc == avk_ts::TS_REJECT) { t.fail_list[atomicAdd(t.fail_ctr, 1u)] = r; continue; }
+        // ---- commit
+        u64 *row = out.region_metrics ? out.region_metrics + (u64)r * (AVK_N_GROUPS * AVK_N_METRICS) : nullptr;
+        if (row) for (int i = 0; i < AVK_N_GROUPS * AVK_N_METRICS; ++i) row[i] = 0;
+        out.status[r] = rc;
+        if (rc != AVK_ST_OK) {
+            const u64 v0 = b.var_off[(u64)r * 2], v1 = b.var_off[(u64)r * 2 + 2];
+            for (u64 v = v0; v < v1; ++v) { out.vexp[v] = 0; out.vobs[v] = 0; out.vcls[v] = AVK_CLASS_UNKNOWN; }
+            out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = 0;
+            if (out.seq_off) for (int k = 0; k < 5; ++k) out.seq_len[(u64)r * 5 + k] = 0;
+            if (slot) atomicAdd(slot + TOT_ERRORS, 1ull);
+            continue;
+        }
+        out.ed1[r] = sol.ed1; out.ed2[r] = sol.ed2; out.type_mask[r] = sol.type_mask;
+        for (int oi = 0; oi < sol.n; ++oi) {
+            const u32 gv = avk_ts::rec32(cl, oi, VI_GV);
+            const bool tr = (avk_ts::rec32(cl, oi, VI_FLAGS) & 0x10000u) != 0;
+            out.vexp[gv] = sol.exp[oi]; out.vobs[gv] = sol.obs[oi];
+            out.vcls[gv] = sol.exp[oi] == sol.obs[oi] ? AVK_CLASS_TP : (tr ? AVK_CLASS_FN : AVK_CLASS_FP);
+        }
+        for (int k = 0; k < sol.n_rows; ++k) {
+            const int g = sol.row_group[k];
+            for (int m = 0; m < AVK_N_METRICS; ++m) {
+                const u64 v = sol.rows[k][m];
+                if (!v) continue;
+                if (row) row[g * AVK_N_METRICS + m] = v;
+                if (slot) atomicAdd(slot + g * AVK_N_METRICS + m, (unsigned long long)v);
+            }
+        }
+        if (slot) { atomicOr(slot + TOT_MASK, (unsigned long long)sol.type_mask); atomicAdd(slot + TOT_SOLVED, 1ull); }
+    }
+    if (t.work_out) {   // work actually executed: one set of atomics per warp
+        unsigned long long v[5] = {ctr.alignments, ctr.cells, ctr.matched, ctr.spops, ctr.xpops};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(AVK_FULL, v[k], o);
+            if (lane_id() == 0 && v[k]) atomicAdd(t.work_out + k, v[k]);
+        }
+    }
+}
+
 // merge, stage 1 of 3: per cluster validation, length prefilter, identical-lists shortcut; emits the pair tasks
 __global__ void __launch_bounds__(256) k_merge_front(DevBatch b, DevMergeOut out, avk_merge_cfg cfg, MergeWork w, u64 n) {
     __shared__ DevBatch sb;
@@ -812,7 +884,7 @@ struct avk_ctx {
     DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, tot_slots, strat_off, strat_idx, strat_totals,
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx, m_rows, m_perr, m_tasks;
     // workspace
-    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, fail_x, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, fail_x, fail_t, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     DevBuf rb[24];   // region builder temporaries
     int dense_n = 10;   // clusters with at least this many variants start in the fused dense-cluster stage (tuning: AVK_DENSE_N)
     // Resident batch: regions [lo, lo + n_regions) of the caller's batch, i.e. variants [v_base, v_base + n_variants) of its
@@ -838,6 +910,7 @@ struct avk_ctx {
     long long coop_arena0 = 256LL << 20, coop_arena1 = 2048LL << 20;
     int coop_cap_ints = 26000;
     int wide_b0 = 256;
+    bool use_thread_stage = true;   // AVK_NO_THREAD_STAGE=1: warp kernels only (A/B timing, tests of the warp path)
 };
 
 static int ensure(avk_ctx *ctx, DevBuf &b, size_t bytes) {
@@ -887,6 +960,7 @@ static int configure_kernels(avk_ctx *ctx) {
     SMEM_OPT_IN((k_compare<true, 4, MODE_SCORE>));
     SMEM_OPT_IN((k_compare<true, 1, MODE_FUSED>));
     SMEM_OPT_IN(k_compare_team);
+    SMEM_OPT_IN(k_compare_thread);
     SMEM_OPT_IN((k_merge_pairs<true, 3>));
     SMEM_OPT_IN((k_merge_pairs<true, 1>));
 #undef SMEM_OPT_IN
@@ -921,6 +995,7 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (const char *s = getenv("AVK_TEST_COOP_ARENA1_MB")) ctx->coop_arena1 = std::max(1LL, atoll(s)) << 20;
     if (const char *s = getenv("AVK_TEST_COOP_CAP_INTS")) ctx->coop_cap_ints = std::min<int>(COOP_CAP_INTS_MAX, std::max(64, atoi(s)));
     if (const char *s = getenv("AVK_TEST_WIDE_B0")) ctx->wide_b0 = std::max(1, atoi(s));
+    if (const char *s = getenv("AVK_NO_THREAD_STAGE")) ctx->use_thread_stage = atoi(s) == 0;
     for (auto &e : ctx->tev) cudaEventCreate(&e);
     {
         int lo = 0, hi = 0;
@@ -947,7 +1022,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->tot_slots, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x, &ctx->fail_t,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
@@ -1291,13 +1366,13 @@ static TierArgs tier_args(avk_ctx *ctx, const u32 *list, int in_ctr, int work_ct
 // its work count from an earlier stage's counter in device memory and NOTHING here waits for the device: the counters
 // travel back with the results (compare_finish), and only if list D (SV-sized clusters) turns out non-empty does the host
 // launch the cooperative tiers afterwards.
-// counters (u32): 12 |W| (clusters without a closed form), 17 |X| dense, 0 search work, 1 |A|, 2 score work, 15 |A2|, 4 team work,
+// counters (u32): 12 |W| (clusters without a closed form), 17 |X| dense, 19 thread-stage work, 13 |W2| (its rejects), 0 search work, 1 |A|, 2 score work, 15 |A2|, 4 team work,
 // 18 S1 work, 16 S1' work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
 static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     const u64 n = ctx->n_regions;
     if (n == 0) return AVK_OK;
     const int sm = ctx->sm_count;
-    ENSURE(ctx->fail_a, 4 * n); ENSURE(ctx->fail_b, 4 * n); ENSURE(ctx->fail_c, 4 * n); ENSURE(ctx->fail_d, 4 * n); ENSURE(ctx->fail_h, 4 * n); ENSURE(ctx->fail_w, 4 * n); ENSURE(ctx->fail_x, 4 * n);
+    ENSURE(ctx->fail_a, 4 * n); ENSURE(ctx->fail_b, 4 * n); ENSURE(ctx->fail_c, 4 * n); ENSURE(ctx->fail_d, 4 * n); ENSURE(ctx->fail_h, 4 * n); ENSURE(ctx->fail_w, 4 * n); ENSURE(ctx->fail_x, 4 * n); ENSURE(ctx->fail_t, 4 * n);
     ENSURE(ctx->counters, 256);
     ENSURE(ctx->blobs, (size_t)n * RB_SIZE);
     u32 *ctrs = (u32 *)ctx->counters.p;
@@ -1326,8 +1401,17 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     }
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
     const int small_ctas = (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8);
-    launch_stage(ctx, R, SEARCH, tier_args(ctx, LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr), small_ctas, ctx->side[0]);                                         // W -> blobs, rejects -> A
-    launch_stage(ctx, R, SCORE, tier_args(ctx, LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);    // rejects -> A2
+    const u32 *LS = LW;          // what the warp search / score kernels consume
+    int ls_ctr = 12;
+    if (ctx->use_thread_stage) {                                                             // W -> solved by one thread each; rejects -> W2
+        u32 *LW2 = (u32 *)ctx->fail_t.p;
+        TierArgs a = tier_args(ctx, LW, 12, 19, LW2, 13, sizeof(avk_ts::Work), nullptr);
+        k_compare_thread<<<(unsigned)std::min<u64>((u64)sm, (n + THREAD_TPB - 1) / THREAD_TPB), THREAD_TPB, THREAD_TPB * sizeof(avk_ts::Work), ctx->side[0]>>>(R.db, R.out, R.cfg, a);
+        ctx->launches += 1;
+        LS = LW2; ls_ctr = 13;
+    }
+    launch_stage(ctx, R, SEARCH, tier_args(ctx, LS, ls_ctr, 0, LA, 1, SEARCH.arena_bytes, nullptr), small_ctas, ctx->side[0]);                                         // -> blobs, rejects -> A
+    launch_stage(ctx, R, SCORE, tier_args(ctx, LS, ls_ctr, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);    // rejects -> A2
     {
         TierArgs a = tier_args(ctx, LA, 1, 18, LB, 5, S1.arena_bytes, nullptr);
         a.spill_base = (u8 *)ctx->arena2.p + spill_half; a.spill_bytes = (u32)spill_warp;   // cold search nodes spill to HBM instead of restarting the cluster

@@ -21,7 +21,7 @@
 // lives in shared memory (one per warp); all arena accesses use Mem<SMEM> addresses.
 #pragma once
 #include "avk_device.cuh"
-#include "../../include/aardvark_b200.h"
+#include "avk_layout.h"
 
 namespace avk {
 
@@ -44,16 +44,6 @@ struct DevBatch {
     const u64 *digest_off;   // [n_regions + 1]
 };
 
-// digest header (64 bytes), then N VI_* records, then the allele bytes (VI_AOFF is relative to their start)
-enum { PH_STATUS = 0, PH_N = 4, PH_N0 = 8, PH_N1 = 12, PH_SUM_L1 = 16, PH_B0 = 20, PH_SUM_ALLE = 24, PH_MAX_END = 28,
-       PH_NSLOTS = 32, PH_SLOT_TYPE = 36, PH_SIZE = 64 };
-
-// Summary counters accumulated inside the solver kernels (SummaryWriter::add_comparison_benchmark,
-// writers/summary.rs:146-158): TOT_SLOTS partial tables of [13][22] metric sums + {type mask, solved, errors};
-// a CTA adds to slot blockIdx.x % TOT_SLOTS (u64 atomics in L2, little contention), k_fold_slots sums the slots.
-enum { TOT_SLOTS = 128, TOT_COLS = AVK_N_GROUPS * AVK_N_METRICS, TOT_MASK = TOT_COLS, TOT_SOLVED = TOT_COLS + 1,
-       TOT_ERRORS = TOT_COLS + 2, TOT_STRIDE = TOT_COLS + 6 };
-
 struct DevCompareOut {
     int *status;
     u32 *ed1, *ed2;
@@ -71,15 +61,10 @@ struct DevMergeOut {
     u8 *cls, *n_idx, *idx;
 };
 
-enum { AL_UNSET = 0, AL_REF = 1, AL_ALT = 2 };
 enum { SOLVE_OK = 0, SOLVE_WORKSPACE = -1 };   // internal; positive values are AVK_ST_*
 
 __device__ __forceinline__ int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-// One variant of the cluster in merged processing order (order_variants, query_optimizer.rs:372-381):
-// 32-byte record in the arena.
-enum { VI_POS = 0, VI_L0 = 4, VI_L1 = 8, VI_AOFF = 12, VI_ALTED = 16, VI_RAW = 20, VI_GV = 24, VI_FLAGS = 28, VI_SIZE = 32 };
-// flags: type | zyg << 8 | is_truth << 16 | slot << 24
 // optimize node: ints {id, depth, hap0[9], hap1[9]}; hap = {t_ref_pos, q_ref_pos, t_mlen, q_mlen, t_mref, q_mref, t_skip, q_skip, ed}
 enum { ON_ID = 0, ON_DEPTH = 4, ON_HAP = 8, ON_HAPSZ = 36, ON_HDR = 80 };
 enum { H_TRP = 0, H_QRP = 4, H_TML = 8, H_QML = 12, H_TMR = 16, H_QMR = 20, H_TSK = 24, H_QSK = 28, H_ED = 32 };
@@ -90,10 +75,6 @@ enum { SD_MLEN = 0, SD_CUR = 4, SD_FAILED = 8, SD_NALT = 12, SD_CLOSED = 16, SD_
 // SD_CLOSED: ED(reference window, this haplotype) when it is known without aligning, else -1; SD_MAT: bytes materialised;
 // SD_ARGS: (side, hap, result, type filter) the buffer was described from, for materialising it later
 
-static __device__ __forceinline__ bool type_supported(int t) {   // SUPPORTED_VARIANT_TYPES waffle_solver.rs:82-91
-    return t == AVK_VT_SNV || t == AVK_VT_INSERTION || t == AVK_VT_DELETION || t == AVK_VT_INDEL ||
-           t == AVK_VT_TR_CONTRACTION || t == AVK_VT_TR_EXPANSION || t == AVK_VT_SV_DELETION || t == AVK_VT_SV_INSERTION;
-}
 
 // Job board of a warp team (k_compare_team): the master warp runs the solver; the independent pieces of one queue pop --
 // the two haplotypes of each child node (optimize_sequences), the two children (optimize_gt_alleles) -- are executed by
