@@ -65,6 +65,10 @@ enum { SOLVE_OK = 0, SOLVE_WORKSPACE = -1 };   // internal; positive values are 
 
 __device__ __forceinline__ int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
+// The solver object is shared by the 32 lanes of its warp.  Convention (checked with compute-sanitizer racecheck): every
+// lane may read a field, lane 0 alone writes it, with a __syncwarp() on either side of the write.
+#define SOLVER_WRITE(...) do { __syncwarp(); if (lane_id() == 0) { __VA_ARGS__; } __syncwarp(); } while (0)
+
 // optimize node: ints {id, depth, hap0[9], hap1[9]}; hap = {t_ref_pos, q_ref_pos, t_mlen, q_mlen, t_mref, q_mref, t_skip, q_skip, ed}
 enum { ON_ID = 0, ON_DEPTH = 4, ON_HAP = 8, ON_HAPSZ = 36, ON_HDR = 80 };
 enum { H_TRP = 0, H_QRP = 4, H_TML = 8, H_QML = 12, H_TMR = 16, H_QMR = 20, H_TSK = 24, H_QSK = 28, H_ED = 32 };
@@ -126,7 +130,6 @@ struct RegionSolver {
     int n_res, res_cap, n_slots;
     int region_off;       // first arena byte after the header (+ staged window)
     int ed_overflow;
-    u32 last_need;        // arena bytes the failed partition() would have needed (0: overflow happened later)
     u8 slot_type[AVK_N_VARIANT_TYPES];
     // queue + node slots (partitioned per phase)
     addr qkeys, qslot, freel, nodes;
@@ -147,15 +150,12 @@ struct RegionSolver {
     // bulk copy (cp.async.bulk, 16-byte aligned superset of [start, end)), and ref_base is set so that
     // ref_base + pos still addresses absolute contig positions.
     __device__ __noinline__ bool begin_region(const u8 *contig) {
-        region_off = ARENA_HDR;
-        if (!SMEM) { ref_base = (addr)(uintptr_t)contig; return true; }
+        if (!SMEM) { SOLVER_WRITE(region_off = ARENA_HDR; ref_base = (addr)(uintptr_t)contig); return true; }
         const int a0 = start & ~15;
         const int bytes = align_up(end - a0 + 16, 16);        // >= 16 bytes of slack for ld4u
-        if ((u32)(ARENA_HDR + bytes + 2048) > arena_bytes) return false;
+        if ((u32)(ARENA_HDR + bytes + 2048) > arena_bytes) { SOLVER_WRITE(region_off = ARENA_HDR); return false; }
         tma_window_issue((u32)arena + ARENA_HDR, contig + a0, (u32)bytes, (u32)arena);   // waited for at the end of setup_pair
-        tma_pending = 1;
-        ref_base = arena + ARENA_HDR - (u32)a0;
-        region_off = ARENA_HDR + bytes;
+        SOLVER_WRITE(tma_pending = 1; ref_base = arena + ARENA_HDR - (u32)a0; region_off = ARENA_HDR + bytes);
         return true;
     }
 
@@ -200,9 +200,8 @@ struct RegionSolver {
         const u32 K = b.n_inputs;
         const u64 v0[2] = {b.var_off[r * K + ki], b.var_off[r * K + kj]};
         const int n0 = (int)(b.var_off[r * K + ki + 1] - v0[0]), n1 = (int)(b.var_off[r * K + kj + 1] - v0[1]);
-        nv[0] = n0; nv[1] = n1;
         const int n = n0 + n1;
-        N = n;
+        SOLVER_WRITE(nv[0] = n0; nv[1] = n1; N = n);
         int sums[4] = {0, 0, 0, start};
         bool invalid = validate_list(v0[0], n0, sums);
         invalid = validate_list(v0[1], n1, sums) || invalid;
@@ -214,24 +213,26 @@ struct RegionSolver {
 
         // ---- layout of the fixed part
         const int npad = align_up(max(n, 1), 16);
-        Npad = npad;
-        seq_cap = align_up((max_end - start) + sum_l1 + 16, 16);   // materialised prefix: up to the last variant end + all ALTs
-        wf_cap = align_up(2 * b0 + 3, 4);
         // room for equal-best results: all of them (<= max_branch_factor) when the arena is large,
         // a handful in the small shared-memory tiers (more than that escalates to the next tier)
         const int rcap = (arena_bytes >= (16u << 10)) ? mbf : min(mbf, 8);
-        res_cap = rcap;
         u32 off = (u32)region_off;
-        vinfo = arena + off; off += (u32)(VI_SIZE * max(n, 1));
+        const addr L_vinfo = arena + off; off += (u32)(VI_SIZE * max(n, 1));
         const addr alle_buf = arena + off;
         if (SMEM) off += (u32)align_up(sum_alle + 16, 16);
-        bucket = arena + off; off += (u32)align_up(4 * (n + 1), 16);
-        res_alle = arena + off; off += (u32)(rcap * npad);
-        res_num = arena + off; off += (u32)align_up(rcap * 24, 16);
-        hap_alle = arena + off; off += (u32)npad;
-        cur_obs = arena + off; off += (u32)(2 * npad);
-        best_obs = arena + off; off += (u32)(2 * npad);
-        sdesc = arena + off; off += 3 * SD_SIZE;
+        const addr L_bucket = arena + off; off += (u32)align_up(4 * (n + 1), 16);
+        const addr L_res_alle = arena + off; off += (u32)(rcap * npad);
+        const addr L_res_num = arena + off; off += (u32)align_up(rcap * 24, 16);
+        const addr L_hap_alle = arena + off; off += (u32)npad;
+        const addr L_cur_obs = arena + off; off += (u32)(2 * npad);
+        const addr L_best_obs = arena + off; off += (u32)(2 * npad);
+        const addr L_sdesc = arena + off; off += 3 * SD_SIZE;
+        SOLVER_WRITE(Npad = npad;
+                     seq_cap = align_up((max_end - start) + sum_l1 + 16, 16);   // materialised prefix: up to the last variant end + all ALTs
+                     wf_cap = align_up(2 * b0 + 3, 4); res_cap = rcap;
+                     vinfo = L_vinfo; bucket = L_bucket; res_alle = L_res_alle; res_num = L_res_num; hap_alle = L_hap_alle;
+                     cur_obs = L_cur_obs; best_obs = L_best_obs; sdesc = L_sdesc;
+                     alle_base = SMEM ? alle_buf : (addr)(uintptr_t)b.pool);
         if (off + 1024 > arena_bytes) return SOLVE_WORKSPACE;
 
         // ---- merged order: stable, truth before query on equal positions
@@ -259,7 +260,6 @@ struct RegionSolver {
         }
         __syncwarp();
         // ---- stage allele bytes (shared-memory tiers)
-        alle_base = (addr)(uintptr_t)b.pool;
         if (SMEM) {
             int acc = 0;
 #pragma unroll 1
@@ -272,7 +272,6 @@ struct RegionSolver {
                 if (lane == 0) ST32(vi(oi) + VI_AOFF, acc);
                 acc += na;
             }
-            alle_base = alle_buf;
         }
         int ns = 0;
         if (want_metrics) {
@@ -292,19 +291,18 @@ struct RegionSolver {
                 ST32(vi(oi) + VI_FLAGS, f | ((u32)__popc(seen & ((1u << (f & 0xff)) - 1)) << 24));
             }
             off = (off + 7u) & ~7u;
-            mrows = arena + off; off += (u32)(8 * AVK_N_METRICS * (1 + ns));
-            slot_tot = arena + off; off += (u32)(16 * max(ns, 1));
-            slot_cnt = arena + off; off += (u32)(16 * max(ns, 1));
+            const addr L_mrows = arena + off; off += (u32)(8 * AVK_N_METRICS * (1 + ns));
+            const addr L_slot_tot = arena + off; off += (u32)(16 * max(ns, 1));
+            const addr L_slot_cnt = arena + off; off += (u32)(16 * max(ns, 1));
+            SOLVER_WRITE(mrows = L_mrows; slot_tot = L_slot_tot; slot_cnt = L_slot_cnt);
             if (off + 512 > arena_bytes) return SOLVE_WORKSPACE;
 #pragma unroll 1
-            for (int i = lane; i < AVK_N_METRICS * (1 + ns); i += 32) ST64(mrows + 8 * i, 0);
+            for (int i = lane; i < AVK_N_METRICS * (1 + ns); i += 32) ST64(L_mrows + 8 * i, 0);
 #pragma unroll 1
-            for (int i = lane; i < 2 * ns; i += 32) { ST32(slot_cnt + 4 * i, 0); ST64(slot_tot + 8 * i, 0); }
+            for (int i = lane; i < 2 * ns; i += 32) { ST32(L_slot_cnt + 4 * i, 0); ST64(L_slot_tot + 8 * i, 0); }
         }
-        n_slots = ns;
         off = (off + 15u) & ~15u;
-        dyn = arena + off;
-        dyn_bytes = arena_bytes - off;
+        SOLVER_WRITE(n_slots = ns; dyn = arena + off; dyn_bytes = arena_bytes - off);
         drain_window();
         __syncwarp();
         return SOLVE_OK;
@@ -320,65 +318,63 @@ struct RegionSolver {
         const u32 dbytes = (u32)(b.digest_off[r + 1] - d0);
         const u8 *dig = b.digest + d0;
         u32 off = ARENA_HDR;
-        addr hdr;
+        addr hdr, L_ref_base;
         if (SMEM) {
             const int a0 = start & ~15;
             const u32 wbytes = (u32)align_up(end - a0 + 16, 16);        // >= 16 bytes of slack for ld4u
-            if (ARENA_HDR + wbytes + dbytes + 1024 > arena_bytes) { last_need = ARENA_HDR + wbytes + dbytes + 4096; return SOLVE_WORKSPACE; }
+            if (ARENA_HDR + wbytes + dbytes + 1024 > arena_bytes) return SOLVE_WORKSPACE;
             const u32 ph = tma_phase;
             tma_issue2((u32)arena + ARENA_HDR, contig + a0, wbytes, (u32)arena + ARENA_HDR + wbytes, dig, dbytes, (u32)arena);
             tma_window_wait((u32)arena, ph);
-            __syncwarp();
-            if (lane == 0) tma_phase = ph ^ 1u;
-            __syncwarp();
-            ref_base = arena + ARENA_HDR - (u32)a0;
+            SOLVER_WRITE(tma_phase = ph ^ 1u);
+            L_ref_base = arena + ARENA_HDR - (u32)a0;
             hdr = arena + ARENA_HDR + wbytes;
             off = ARENA_HDR + wbytes + dbytes;
         } else {
-            ref_base = (addr)(uintptr_t)contig;
+            L_ref_base = (addr)(uintptr_t)contig;
             hdr = (addr)(uintptr_t)dig;
         }
         const int st = LDI(hdr + PH_STATUS);
         if (st) return st;
         if (!SMEM && wide_b0 && LDI(hdr + PH_B0) >= wide_b0) return SOLVE_WORKSPACE;   // wide wavefronts: cooperative tier
         const int n = LDI(hdr + PH_N);
-        N = n; nv[0] = LDI(hdr + PH_N0); nv[1] = LDI(hdr + PH_N1);
         const int npad = align_up(max(n, 1), 16);
-        Npad = npad;
-        seq_cap = align_up((LDI(hdr + PH_MAX_END) - start) + LDI(hdr + PH_SUM_L1) + 16, 16);
-        wf_cap = align_up(2 * LDI(hdr + PH_B0) + 3, 4);
         const int rcap = (arena_bytes >= (16u << 10)) ? mbf : min(mbf, 8);
-        res_cap = rcap;
-        vinfo = hdr + PH_SIZE;
-        alle_base = vinfo + (u32)(VI_SIZE * n);
-        bucket = arena + off; off += (u32)align_up(4 * (n + 1), 16);
-        res_alle = arena + off; off += (u32)(rcap * npad);
-        res_num = arena + off; off += (u32)align_up(rcap * 24, 16);
-        hap_alle = arena + off; off += (u32)npad;
-        cur_obs = arena + off; off += (u32)(2 * npad);
-        best_obs = arena + off; off += (u32)(2 * npad);
-        sdesc = arena + off; off += 3 * SD_SIZE;
+        const addr L_vinfo = hdr + PH_SIZE;
+        const addr L_bucket = arena + off; off += (u32)align_up(4 * (n + 1), 16);
+        const addr L_res_alle = arena + off; off += (u32)(rcap * npad);
+        const addr L_res_num = arena + off; off += (u32)align_up(rcap * 24, 16);
+        const addr L_hap_alle = arena + off; off += (u32)npad;
+        const addr L_cur_obs = arena + off; off += (u32)(2 * npad);
+        const addr L_best_obs = arena + off; off += (u32)(2 * npad);
+        const addr L_sdesc = arena + off; off += 3 * SD_SIZE;
         int ns = 0;
+        addr L_mrows = 0, L_slot_tot = 0, L_slot_cnt = 0;
         if (want_metrics) {
             ns = LDI(hdr + PH_NSLOTS);
-            __syncwarp();
-            if (lane < ns) slot_type[lane] = LD8(hdr + PH_SLOT_TYPE + lane);
             off = (off + 7u) & ~7u;
-            mrows = arena + off; off += (u32)(8 * AVK_N_METRICS * (1 + ns));
-            slot_tot = arena + off; off += (u32)(16 * max(ns, 1));
-            slot_cnt = arena + off; off += (u32)(16 * max(ns, 1));
+            L_mrows = arena + off; off += (u32)(8 * AVK_N_METRICS * (1 + ns));
+            L_slot_tot = arena + off; off += (u32)(16 * max(ns, 1));
+            L_slot_cnt = arena + off; off += (u32)(16 * max(ns, 1));
         }
-        if (off + 512 > arena_bytes) { last_need = off + 4096; return SOLVE_WORKSPACE; }
+        const u32 fixed_end = off;
+        off = (off + 15u) & ~15u;
+        SOLVER_WRITE(ref_base = L_ref_base; N = n; nv[0] = LDI(hdr + PH_N0); nv[1] = LDI(hdr + PH_N1); Npad = npad;
+                     seq_cap = align_up((LDI(hdr + PH_MAX_END) - start) + LDI(hdr + PH_SUM_L1) + 16, 16);
+                     wf_cap = align_up(2 * LDI(hdr + PH_B0) + 3, 4); res_cap = rcap;
+                     vinfo = L_vinfo; alle_base = L_vinfo + (u32)(VI_SIZE * n);
+                     bucket = L_bucket; res_alle = L_res_alle; res_num = L_res_num; hap_alle = L_hap_alle;
+                     cur_obs = L_cur_obs; best_obs = L_best_obs; sdesc = L_sdesc;
+                     mrows = L_mrows; slot_tot = L_slot_tot; slot_cnt = L_slot_cnt; n_slots = ns;
+                     dyn = arena + off; dyn_bytes = arena_bytes > off ? arena_bytes - off : 0;
+                     for (int k = 0; k < ns && k < AVK_N_VARIANT_TYPES; ++k) slot_type[k] = LD8(hdr + PH_SLOT_TYPE + k));
+        if (fixed_end + 512 > arena_bytes) return SOLVE_WORKSPACE;
         if (want_metrics) {
 #pragma unroll 1
-            for (int i = lane; i < AVK_N_METRICS * (1 + ns); i += 32) ST64(mrows + 8 * i, 0);
+            for (int i = lane; i < AVK_N_METRICS * (1 + ns); i += 32) ST64(L_mrows + 8 * i, 0);
 #pragma unroll 1
-            for (int i = lane; i < 2 * ns; i += 32) { ST32(slot_cnt + 4 * i, 0); ST64(slot_tot + 8 * i, 0); }
+            for (int i = lane; i < 2 * ns; i += 32) { ST32(L_slot_cnt + 4 * i, 0); ST64(L_slot_tot + 8 * i, 0); }
         }
-        n_slots = ns;
-        off = (off + 15u) & ~15u;
-        dyn = arena + off;
-        dyn_bytes = arena_bytes - off;
         __syncwarp();
         return SOLVE_OK;
     }
@@ -392,7 +388,7 @@ struct RegionSolver {
         const u32 per = (u32)stride_ + 16u;
         if (dyn_bytes < 12u * (u32)extra + 64u) return false;
         int ms = (int)min((dyn_bytes - 12u * (u32)extra - 16u) / per, 60000u);
-        if (ms < min_slots) { last_need = (arena_bytes - dyn_bytes) + (u32)min_slots * per + 12u * (u32)extra + 64; return false; }
+        if (ms < min_slots) return false;
         const int qc = ms + extra;
         u32 off = 0;
         const addr qk = dyn + off; off += (u32)qc * 8;
@@ -725,7 +721,7 @@ struct RegionSolver {
         if (!partition(opt_stride(), spill_bytes ? 6 : min(n + 3, 48))) return SOLVE_WORKSPACE;
 #pragma unroll 1
         for (int i = lane; i <= n; i += 32) ST32(bucket + 4 * i, 0);
-        n_res = 0;
+        SOLVER_WRITE(n_res = 0);
         int nres = 0;
         u32 best = 0xffffffffu;
         u32 next_id = 1;
@@ -849,7 +845,7 @@ struct RegionSolver {
             }
             }
         }
-        n_res = nres;
+        SOLVER_WRITE(n_res = nres);
         if (nres == 0 && !stop_at_nonzero) return AVK_ST_NO_RESULT;            // :331
         return SOLVE_OK;
     }
@@ -1130,7 +1126,7 @@ struct RegionSolver {
     __device__ __noinline__ u64 ed_between(int ka, int kb) {
         materialise(ka); materialise(kb);
         const int e = wfa_ed_warp<SMEM>(seq_vs(ka), seq_vs(kb), dyn + (u32)(3 * seq_cap), (wf_cap - 3) / 2, wk());
-        if (e < 0) { ed_overflow = 1; return 0; }
+        if (e < 0) { SOLVER_WRITE(ed_overflow = 1); return 0; }
         return (u64)e;
     }
     // copy a sequence buffer to the optional sequence-bundle output
@@ -1216,12 +1212,9 @@ template <bool SMEM>
 __device__ int RegionSolver<SMEM>::compare_prepare(u64 r, const avk_compare_cfg &cfg, bool want_metrics) {
     const DevBatch &b = *bp;
     const u32 c = b.contig[r];
-    start = (int)b.start[r];
-    end = (int)b.end[r];
+    SOLVER_WRITE(start = (int)b.start[r]; end = (int)b.end[r]; mbf = (int)cfg.max_branch_factor);
     if (c >= b.n_contigs || b.start[r] > b.end[r] || (u64)b.end[r] > b.contig_len[c] || b.end[r] > 0x7fff0000u) return AVK_ST_BAD_INPUT;
-    mbf = (int)cfg.max_branch_factor;
     if (mbf <= 0) return AVK_ST_BAD_INPUT;
-    last_need = 0;
     return load_cluster(r, b.contig_ptr[c], want_metrics);
 }
 
@@ -1255,8 +1248,7 @@ __device__ int RegionSolver<SMEM>::compare_score_from_blob(u64 r, const avk_comp
     for (int i = lane; i < nres * 16; i += 32) ST8(res_alle + (u32)((i >> 4) * Npad + (i & 15)), blob[RB_ALLE + i]);
 #pragma unroll 1
     for (int i = lane; i < nres * 6; i += 32) ST32(res_num + 4 * i, ((const int *)(blob + RB_NUM))[i]);
-    n_res = nres;
-    __syncwarp();
+    SOLVER_WRITE(n_res = nres);
     return compare_score(r, cfg, out);
 }
 
@@ -1387,7 +1379,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
     // ---- basepair metrics: three sequence buffers + one wavefront in the dynamic part
     if ((u32)(3 * seq_cap + 4 * wf_cap + 16) > dyn_bytes) return SOLVE_WORKSPACE;
     const bool want_seq = out.seq_off && cfg.enable_sequences;
-    ed_overflow = 0;
+    SOLVER_WRITE(ed_overflow = 0);
     u32 mask = 0;
 #pragma unroll 1
     for (int k = 0; k < n_slots; ++k) mask |= 1u << slot_type[k];
@@ -1559,10 +1551,8 @@ __device__ int RegionSolver<SMEM>::merge_front(u64 r, const avk_merge_cfg &cfg, 
     const int lane = lane_id();
     const u32 K = b.n_inputs;
     const u32 c = b.contig[r];
-    start = (int)b.start[r];
-    end = (int)b.end[r];
+    SOLVER_WRITE(start = (int)b.start[r]; end = (int)b.end[r]; mbf = (int)cfg.max_branch_factor);
     if (c >= b.n_contigs || b.start[r] > b.end[r] || (u64)b.end[r] > b.contig_len[c] || b.end[r] > 0x7fff0000u) return AVK_ST_BAD_INPUT;
-    mbf = (int)cfg.max_branch_factor;
     if (mbf <= 0 || K > 32) return AVK_ST_BAD_INPUT;
     {
         bool invalid = false;
@@ -1612,9 +1602,7 @@ template <bool SMEM>
 __device__ int RegionSolver<SMEM>::merge_pair(u64 r, u32 i, u32 j, const avk_merge_cfg &cfg, bool *exact) {
     const DevBatch &b = *bp;
     const u32 c = b.contig[r];
-    start = (int)b.start[r];
-    end = (int)b.end[r];
-    mbf = (int)cfg.max_branch_factor;
+    SOLVER_WRITE(start = (int)b.start[r]; end = (int)b.end[r]; mbf = (int)cfg.max_branch_factor);
     *exact = false;
     if (!begin_region(b.contig_ptr[c])) return SOLVE_WORKSPACE;
     int rc = setup_pair(r, i, j, false);

@@ -78,6 +78,7 @@ extern "C" int ts_compare_batch(const avk_region_batch *b, const uint8_t *const 
     if (!b || b->n_inputs != 2 || !out || !rejected) return -1;
     std::vector<uint8_t> dig;
     Counters ctr = {0, 0, 0, 0, 0};
+    uint64_t steps = 0;
     uint64_t acc = 0, rej = 0;
     Work *w = new Work();
     for (uint64_t r = 0; r < b->n_regions; ++r) {
@@ -86,10 +87,17 @@ extern "C" int ts_compare_batch(const avk_region_batch *b, const uint8_t *const 
         if (c >= n_contigs || b->start[r] > b->end[r] || (uint64_t)b->end[r] > contig_lens[c] || b->end[r] > 0x7fff0000u) { rej += 1; continue; }
         if (cfg->enable_exact_shortcut || cfg->enable_sequences) { rej += 1; continue; }
         build_digest(b, r, dig);
-        Cluster cl;
         Solution sol;
-        int rc = load_cluster(dig.data(), contigs[c], (int)b->start[r], (int)b->end[r], (int)cfg->max_branch_factor, cl, *w);
-        if (rc == AVK_ST_OK) rc = solve_compare(cl, *w, ctr, sol);
+        Solver S;
+        S.wp = w; S.ctr = &ctr;
+        S.begin(dig.data(), contigs[c], (int)b->start[r], (int)b->end[r], (int)cfg->max_branch_factor);
+        while (S.phase == PH_SEARCH || S.phase == PH_EXACT) {            // the kernel runs these steps in warp-wide rounds
+            if (S.phase == PH_SEARCH) S.search_step(); else S.exact_step();
+            steps += 1;
+        }
+        int rc = S.rc;
+        if (rc == AVK_ST_OK) rc = S.finish(sol);
+        const Cluster &cl = S.c;
         if (rc == TS_REJECT) { rej += 1; continue; }
         rejected[r] = 0;
         acc += 1;
@@ -112,6 +120,6 @@ extern "C" int ts_compare_batch(const avk_region_batch *b, const uint8_t *const 
         if (row) for (int k = 0; k < sol.n_rows; ++k) memcpy(row + (size_t)sol.row_group[k] * AVK_N_METRICS, sol.rows[k], sizeof(uint64_t) * AVK_N_METRICS);
     }
     delete w;
-    if (stats) { stats[0] = acc; stats[1] = rej; stats[2] = ctr.spops; stats[3] = ctr.xpops; stats[4] = ctr.cells; stats[5] = sizeof(Work); }
+    if (stats) { stats[0] = acc; stats[1] = rej; stats[2] = ctr.spops; stats[3] = ctr.xpops; stats[4] = ctr.cells; stats[5] = sizeof(Work); stats[6] = steps; }
     return 0;
 }
