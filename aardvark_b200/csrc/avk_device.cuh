@@ -300,9 +300,111 @@ __device__ __forceinline__ int lcp_thread(const VSeq<false> &A, int ia, const VS
     return total;
 }
 
+// ---- fast path of the CTA-wide DWFA: both sequences staged in shared memory, 16-bit wavefront --------------------------------
+// Shared-memory layout behind the job slot (area = 8 * cap_ints bytes, the same allocation the 32-bit path ping-pongs in):
+//   [cur: cap_ints u16][nxt: cap_ints u16][sequence A bytes, 8 bytes slack][sequence B bytes, 8 bytes slack]
+// so the wavefront takes half of the area and the two sequences share the other half (4 * cap_ints bytes: 104 KB at the
+// default capacity, i.e. a 10 kbp event inside a 22 kbp window fits with room to spare).  Per wavefront entry a thread then
+// executes: three 16-bit shared loads for the recurrence (dynamic_wfa.rs:152-168), one byte compare that ends the extension
+// of 3 diagonals in 4 on unrelated sequence, and only for the others an aligned-word XOR + ffs loop (4 bases per step) --
+// ~20 instructions instead of ~57 with virtual sequences read through 64-bit global addresses.
+__device__ __forceinline__ u32 lds4u(const u8 *p) {          // unaligned 32-bit read from shared memory: two aligned words + funnel shift
+    const u32 *w = (const u32 *)((uintptr_t)p & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], ((u32)(uintptr_t)p & 3u) * 8u);
+}
+__device__ __forceinline__ int lcp_staged(const u8 *sa, int ia, int la, const u8 *sb, int ib, int lb) {   // ia < la && ib < lb
+    if (sa[ia] != sb[ib]) return 0;
+    const int maxn = min(la - ia, lb - ib);
+    int k = 1;
+#pragma unroll 1
+    while (k < maxn) {
+        const u32 x = lds4u(sa + ia + k) ^ lds4u(sb + ib + k);
+        if (x) { k += (__ffs(x) - 1) >> 3; break; }
+        k += 4;
+    }
+    return min(k, maxn);
+}
+// stage the logical bytes [0, len) of a virtual sequence into shared memory (4 bytes per thread and trip)
+__device__ __forceinline__ void coop_stage(u8 *dst, const VSeq<false> &S) {
+    typedef Mem<false> M;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int words = (S.len + 3) >> 2;
+#pragma unroll 1
+    for (int wi = tid; wi < words; wi += T) {
+        const int x = 4 * wi;
+        u32 v;
+        if (x + 4 <= S.mlen) v = ld4u<false>(S.data + x);
+        else if (x >= S.mlen) v = ld4u<false>(S.tail + (x - S.mlen));
+        else { v = 0; for (int k = 0; k < 4; ++k) v |= (u32)LD8(S.at(min(x + k, S.len - 1))) << (8 * k); }   // the word that straddles the two pieces
+        *(u32 *)(dst + x) = v;
+    }
+}
+__device__ __noinline__ void coop_dwfa_body_staged() {
+    CoopJob &J = *(CoopJob *)avk_dyn_smem;
+    const int cap = J.cap_ints;
+    unsigned short *cur = (unsigned short *)(avk_dyn_smem + COOP_JOB_BYTES), *nxt = cur + cap;
+    u8 *sa = avk_dyn_smem + COOP_JOB_BYTES + 4 * (size_t)cap;
+    const int tid = threadIdx.x, T = blockDim.x;
+    VSeq<false> A, B;
+    A.data = J.a_data; A.tail = J.a_tail; A.mlen = J.a_mlen; A.len = J.a_len;
+    B.data = J.b_data; B.tail = J.b_tail; B.mlen = J.b_mlen; B.len = J.b_len;
+    const int la = A.len, lb = B.len, max_ed = J.max_ed, e_cap = (cap - 3) / 2;
+    u8 *sb = sa + ((la + 8 + 3) & ~3);
+    const bool to_full = J.to_full != 0;
+    int *gw = (int *)(uintptr_t)J.wf;
+    int e = J.ed, status = DWFA_OK;
+    coop_stage(sa, A);
+    coop_stage(sb, B);
+#pragma unroll 1
+    for (int i = tid; i < 2 * e + 1; i += T) cur[i] = (unsigned short)gw[i];
+    __syncthreads();
+    unsigned long long matched = 0, cells = 0;
+    bool flag = false;
+#pragma unroll 1
+    for (int i = tid; i < 2 * e + 1; i += T) {           // extend() of the wavefront as it stands
+        int d = cur[i];
+        int boff = d + e - i;
+        if (boff < la && d < lb) { const int ext = lcp_staged(sa, boff, la, sb, d, lb); d += ext; boff += ext; matched += ext; cur[i] = (unsigned short)d; }
+        flag = flag || (to_full ? (boff >= la && d >= lb) : (boff >= la || d >= lb));
+    }
+    cells += 2 * e + 1;
+    int stop = __syncthreads_or(flag);
+#pragma unroll 1
+    while (!stop) {
+        e += 1;
+        if (e > max_ed) { status = DWFA_MAX_ED; break; }                 // *ed stays incremented, wavefront not grown
+        if (e > e_cap) { status = DWFA_COOP_SPILL; e -= 1; break; }      // does not fit shared memory: back to the warp path
+        const int n = 2 * e + 1, n_old = n - 2;
+        flag = false;
+#pragma unroll 1
+        for (int i = tid; i < n; i += T) {
+            int d = 0;                                                   // increase_edit_distance(): dynamic_wfa.rs:152-168
+            if (i < n_old) d = cur[i];
+            if (i >= 1 && i - 1 < n_old) d = max(d, (int)cur[i - 1] + 1);
+            if (i >= 2 && i - 2 < n_old) d = max(d, (int)cur[i - 2] + 1);
+            int boff = d + e - i;
+            if (boff < la && d < lb) { const int ext = lcp_staged(sa, boff, la, sb, d, lb); d += ext; boff += ext; matched += ext; }
+            nxt[i] = (unsigned short)d;
+            flag = flag || (to_full ? (boff >= la && d >= lb) : (boff >= la || d >= lb));
+        }
+        cells += n;
+        stop = __syncthreads_or(flag);
+        unsigned short *t = cur; cur = nxt; nxt = t;
+    }
+    const int n_out = 2 * (status == DWFA_MAX_ED ? e - 1 : e) + 1;
+#pragma unroll 1
+    for (int i = tid; i < n_out; i += T) gw[i] = (int)cur[i];
+    if (matched) atomicAdd(&J.matched, matched);
+    if (tid == 0) { J.ed = e; J.status = status; J.cells = cells; }
+    __threadfence_block();
+    __syncthreads();
+}
+
 // executed by every thread of the CTA; the job is in CoopJob at the start of dynamic shared memory
 __device__ __noinline__ void coop_dwfa_body() {
     CoopJob &J = *(CoopJob *)avk_dyn_smem;
+    // both sequences fit beside a 16-bit wavefront (offsets stay below 65535 even with the +1 per step): fast path
+    if ((long long)J.a_len + J.b_len + 32 <= 4LL * J.cap_ints && J.a_len + J.cap_ints < 65000 && J.b_len + J.cap_ints < 65000) { coop_dwfa_body_staged(); return; }
     int *cur = (int *)(avk_dyn_smem + COOP_JOB_BYTES), *nxt = cur + J.cap_ints;
     const int tid = threadIdx.x, T = blockDim.x;
     VSeq<false> A, B;

@@ -656,15 +656,31 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
 
 // ---- thread per cluster -------------------------------------------------------------------------------------------------
 // The common non-closed-form cluster (a few variants, a window of a few hundred bases, edit distances of a few units) is
-// solved by ONE thread (avk_thread_solver.cuh): 32 clusters per warp instead of one, an 804-byte workspace per thread in
+// solved by ONE thread (avk_thread_solver.cuh): 32 clusters per warp instead of one, an 836-byte workspace per thread in
 // shared memory (search nodes are 12-byte queue entries, sequences are never materialised).
-// A thread's solve is a state machine of STEPS (one queue pop of optimize_sequences, one pop of optimize_gt_alleles, the
-// final scoring); the warp runs the step kinds in ROUNDS so that its 32 threads, each on its own cluster, execute the same
-// code: fetch round (threads without a cluster take the next ones from the list W with one atomic per warp), search rounds
-// (repeated while at least TS_SEARCH_MIN lanes are still searching), exact-GT rounds, finish round (scoring + commit).
-// A cluster that does not fit the fixed workspace is appended to the reject list -- nothing has been written for it -- and
-// goes through the warp kernels (search / score / fused stages) as before.
-enum { THREAD_TPB = 256, TS_SEARCH_MIN = 20, TS_EXACT_MIN = 8 };
+// 32 threads on 32 different clusters only run together where they execute the same instructions, so the solver is a
+// coroutine: advance() runs a cluster's control flow up to the next alignment it needs, exec_task() -- the one place where
+// sequences are built and wavefronts advanced -- executes it.  The warp alternates the two: all lanes advance, all lanes
+// execute their task side by side; lanes whose cluster is finished commit it and take the next one from the list W (one
+// atomic per warp and round).  A cluster that does not fit the fixed workspace is appended to the reject list -- nothing
+// has been written for it -- and goes through the warp kernels (search / score / fused stages) as before.
+enum { THREAD_TPB = 256 };
+struct ThreadSink {
+    const avk_ts::Cluster &cl;
+    const DevCompareOut &out;
+    u64 *row;
+    unsigned long long *slot;
+    __device__ __forceinline__ void variant(int oi, int e, int o) {
+        const u32 gv = avk_ts::rec32(cl, oi, VI_GV);
+        const bool tr = (avk_ts::rec32(cl, oi, VI_FLAGS) & 0x10000u) != 0;
+        out.vexp[gv] = (u8)e; out.vobs[gv] = (u8)o;
+        out.vcls[gv] = (u8)(e == o ? AVK_CLASS_TP : (tr ? AVK_CLASS_FN : AVK_CLASS_FP));
+    }
+    __device__ __forceinline__ void metric(int g, int m, u64 v) {
+        if (row) row[g * AVK_N_METRICS + m] = v;
+        if (slot) atomicAdd(slot + g * AVK_N_METRICS + m, (unsigned long long)v);
+    }
+};
 __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, TierArgs t) {
     using namespace avk_ts;
     const int lane = lane_id();
@@ -673,13 +689,14 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
     S.wp = &((Work *)avk_dyn_smem)[threadIdx.x];
     S.ctr = &ctr;
     S.phase = PH_FETCH;
+    S.task.kind = TK_NONE;
     const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
     const bool enabled = !cfg.enable_exact_shortcut && !(out.seq_off && cfg.enable_sequences);
     unsigned long long *slot = out.tot_slots ? out.tot_slots + (size_t)(blockIdx.x & (TOT_SLOTS - 1)) * TOT_STRIDE : nullptr;
     u32 r = 0;
     bool more = true;                                            // warp-uniform: the list is not exhausted yet
     for (;;) {
-        // ---- fetch round
+        // ---- fetch round: lanes without a cluster take the next ones
         {
             const bool want = S.phase == PH_FETCH;
             const u32 m = __ballot_sync(AVK_FULL, want);
@@ -695,34 +712,40 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
                     else {
                         r = t.work_list[idx];
                         const u32 c = b.contig[r];
-                        if (!enabled) S.fail(TS_REJECT);
+                        if (!enabled) S.stop(TS_REJECT);
                         else if (c >= b.n_contigs || b.start[r] > b.end[r] || (u64)b.end[r] > b.contig_len[c] || b.end[r] > 0x7fff0000u ||
                                  (int)cfg.max_branch_factor <= 0)
-                            S.fail(AVK_ST_BAD_INPUT);
+                            S.stop(AVK_ST_BAD_INPUT);
                         else S.begin(b.digest + b.digest_off[r], b.contig_ptr[c], (int)b.start[r], (int)b.end[r], (int)cfg.max_branch_factor);
                     }
                 }
             } else if (want) S.phase = PH_DONE;
         }
         if (__all_sync(AVK_FULL, S.phase == PH_DONE)) break;
-        // ---- search rounds: one queue pop of optimize_sequences per lane and round
-        do {
-            if (S.phase == PH_SEARCH) S.search_step();
-        } while (__popc(__ballot_sync(AVK_FULL, S.phase == PH_SEARCH)) >= TS_SEARCH_MIN);
-        // ---- exact-GT rounds: one queue pop of optimize_gt_alleles per lane and round
-        do {
-            if (S.phase == PH_EXACT) S.exact_step();
-        } while (__popc(__ballot_sync(AVK_FULL, S.phase == PH_EXACT)) >= TS_EXACT_MIN);
-        // ---- finish round: final scoring, then commit (or reject)
-        if (S.phase == PH_FINISH) {
-            Solution sol;
+        // ---- every lane runs its cluster's control flow up to the next alignment ...
+        if (S.phase == PH_RUN) S.advance();
+        __syncwarp();
+        // ---- ... and all lanes execute their alignments side by side
+        if (S.task.kind != TK_NONE) S.exec_task();
+        __syncwarp();
+        // ---- commit round
+        if (S.phase == PH_COMMIT) {
             int rc = S.rc;
-            if (rc == AVK_ST_OK) rc = S.finish(sol);
             S.phase = PH_FETCH;
             if (rc == TS_REJECT) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = r;
             else {
                 u64 *row = out.region_metrics ? out.region_metrics + (u64)r * (AVK_N_GROUPS * AVK_N_METRICS) : nullptr;
                 if (row) for (int i = 0; i < AVK_N_GROUPS * AVK_N_METRICS; ++i) row[i] = 0;
+                if (rc == AVK_ST_OK) {
+                    ThreadSink sink{S.c, out, row, slot};
+                    u32 e1 = 0, e2 = 0;
+                    uint16_t tm = 0;
+                    rc = commit_solution(S, sink, &e1, &e2, &tm);
+                    if (rc == AVK_ST_OK) {
+                        out.ed1[r] = e1; out.ed2[r] = e2; out.type_mask[r] = tm;
+                        if (slot) { atomicOr(slot + TOT_MASK, (unsigned long long)tm); atomicAdd(slot + TOT_SOLVED, 1ull); }
+                    }
+                }
                 out.status[r] = rc;
                 if (rc != AVK_ST_OK) {
                     const u64 v0 = b.var_off[(u64)r * 2], v1 = b.var_off[(u64)r * 2 + 2];
@@ -730,24 +753,6 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
                     out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = 0;
                     if (out.seq_off) for (int k = 0; k < 5; ++k) out.seq_len[(u64)r * 5 + k] = 0;
                     if (slot) atomicAdd(slot + TOT_ERRORS, 1ull);
-                } else {
-                    out.ed1[r] = sol.ed1; out.ed2[r] = sol.ed2; out.type_mask[r] = sol.type_mask;
-                    for (int oi = 0; oi < sol.n; ++oi) {
-                        const u32 gv = rec32(S.c, oi, VI_GV);
-                        const bool tr = (rec32(S.c, oi, VI_FLAGS) & 0x10000u) != 0;
-                        out.vexp[gv] = sol.exp[oi]; out.vobs[gv] = sol.obs[oi];
-                        out.vcls[gv] = sol.exp[oi] == sol.obs[oi] ? AVK_CLASS_TP : (tr ? AVK_CLASS_FN : AVK_CLASS_FP);
-                    }
-                    for (int k = 0; k < sol.n_rows; ++k) {
-                        const int g = sol.row_group[k];
-                        for (int m = 0; m < AVK_N_METRICS; ++m) {
-                            const u64 v = sol.rows[k][m];
-                            if (!v) continue;
-                            if (row) row[g * AVK_N_METRICS + m] = v;
-                            if (slot) atomicAdd(slot + g * AVK_N_METRICS + m, (unsigned long long)v);
-                        }
-                    }
-                    if (slot) { atomicOr(slot + TOT_MASK, (unsigned long long)sol.type_mask); atomicAdd(slot + TOT_SOLVED, 1ull); }
                 }
             }
         }

@@ -87,37 +87,42 @@ extern "C" int ts_compare_batch(const avk_region_batch *b, const uint8_t *const 
         if (c >= n_contigs || b->start[r] > b->end[r] || (uint64_t)b->end[r] > contig_lens[c] || b->end[r] > 0x7fff0000u) { rej += 1; continue; }
         if (cfg->enable_exact_shortcut || cfg->enable_sequences) { rej += 1; continue; }
         build_digest(b, r, dig);
-        Solution sol;
         Solver S;
         S.wp = w; S.ctr = &ctr;
         S.begin(dig.data(), contigs[c], (int)b->start[r], (int)b->end[r], (int)cfg->max_branch_factor);
-        while (S.phase == PH_SEARCH || S.phase == PH_EXACT) {            // the kernel runs these steps in warp-wide rounds
-            if (S.phase == PH_SEARCH) S.search_step(); else S.exact_step();
-            steps += 1;
+        while (S.phase == PH_RUN) {                                      // the kernel alternates these two for a whole warp
+            S.advance();
+            if (S.task.kind != TK_NONE) { S.exec_task(); steps += 1; }
         }
         int rc = S.rc;
-        if (rc == AVK_ST_OK) rc = S.finish(sol);
         const Cluster &cl = S.c;
         if (rc == TS_REJECT) { rej += 1; continue; }
-        rejected[r] = 0;
-        acc += 1;
-        out->status[r] = rc;
         const uint64_t v0 = b->var_off[r * 2], v1 = b->var_off[r * 2 + 2];
         uint64_t *row = out->region_metrics ? out->region_metrics + r * (uint64_t)(AVK_N_GROUPS * AVK_N_METRICS) : nullptr;
         if (row) memset(row, 0, sizeof(uint64_t) * AVK_N_GROUPS * AVK_N_METRICS);
+        if (rc == AVK_ST_OK) {
+            struct Sink {
+                const Cluster &cl; avk_compare_out *out; uint64_t *row;
+                void variant(int oi, int e, int o) {
+                    const uint32_t gv = rec32(cl, oi, VI_GV);
+                    const bool tr = (rec32(cl, oi, VI_FLAGS) & 0x10000u) != 0;
+                    out->var_expected[gv] = (uint8_t)e; out->var_observed[gv] = (uint8_t)o;
+                    out->var_class[gv] = e == o ? AVK_CLASS_TP : (tr ? AVK_CLASS_FN : AVK_CLASS_FP);
+                }
+                void metric(int g, int m, uint64_t v) { if (row) row[g * AVK_N_METRICS + m] = v; }
+            } sink{cl, out, row};
+            uint32_t e1 = 0, e2 = 0; uint16_t tm = 0;
+            rc = commit_solution(S, sink, &e1, &e2, &tm);
+            if (rc == AVK_ST_OK) { out->ed1[r] = e1; out->ed2[r] = e2; out->type_mask[r] = tm; }
+        }
+        rejected[r] = 0;
+        acc += 1;
+        out->status[r] = rc;
         if (rc != AVK_ST_OK) {
+            if (row) memset(row, 0, sizeof(uint64_t) * AVK_N_GROUPS * AVK_N_METRICS);
             out->ed1[r] = 0; out->ed2[r] = 0; out->type_mask[r] = 0;
             for (uint64_t v = v0; v < v1; ++v) { out->var_expected[v] = 0; out->var_observed[v] = 0; out->var_class[v] = AVK_CLASS_UNKNOWN; }
-            continue;
         }
-        out->ed1[r] = sol.ed1; out->ed2[r] = sol.ed2; out->type_mask[r] = sol.type_mask;
-        for (int oi = 0; oi < sol.n; ++oi) {
-            const uint32_t gv = rec32(cl, oi, VI_GV);
-            const bool tr = (rec32(cl, oi, VI_FLAGS) & 0x10000u) != 0;
-            out->var_expected[gv] = sol.exp[oi]; out->var_observed[gv] = sol.obs[oi];
-            out->var_class[gv] = sol.exp[oi] == sol.obs[oi] ? AVK_CLASS_TP : (tr ? AVK_CLASS_FN : AVK_CLASS_FP);
-        }
-        if (row) for (int k = 0; k < sol.n_rows; ++k) memcpy(row + (size_t)sol.row_group[k] * AVK_N_METRICS, sol.rows[k], sizeof(uint64_t) * AVK_N_METRICS);
     }
     delete w;
     if (stats) { stats[0] = acc; stats[1] = rej; stats[2] = ctr.spops; stats[3] = ctr.xpops; stats[4] = ctr.cells; stats[5] = sizeof(Work); stats[6] = steps; }

@@ -5,7 +5,6 @@ timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider 
 echo "pytest rc=$?" >> gpurun_out/c3_pytest.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/c3_bench_wgs.json 2> gpurun_out/c3_bench_wgs.err
 echo "bench rc=$?" >> gpurun_out/c3_bench_wgs.err
-AVK_NO_THREAD_STAGE=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/c3_bench_wgs_nothread.json 2> gpurun_out/c3_bench_wgs_nothread.err
 timeout 300 python bench.py --config chr20 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/c3_bench_chr20.json 2> gpurun_out/c3_bench_chr20.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/c3_launches_wgs.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/c3_bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_compare_thread -c 1 -s 3 -o gpurun_out/c3_thread_full python bench.py --config wgs --scale 0.25 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/c3_ncu_full.log 2>&1
