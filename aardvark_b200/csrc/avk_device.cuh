@@ -302,9 +302,9 @@ __device__ __forceinline__ int lcp_thread(const VSeq<false> &A, int ia, const VS
 
 // ---- fast path of the CTA-wide DWFA: both sequences staged in shared memory, 16-bit wavefront --------------------------------
 // Shared-memory layout behind the job slot (area = 8 * cap_ints bytes, the same allocation the 32-bit path ping-pongs in):
-//   [cur: cap_ints u16][nxt: cap_ints u16][sequence A bytes, 8 bytes slack][sequence B bytes, 8 bytes slack]
-// so the wavefront takes half of the area and the two sequences share the other half (4 * cap_ints bytes: 104 KB at the
-// default capacity, i.e. a 10 kbp event inside a 22 kbp window fits with room to spare).  Per wavefront entry a thread then
+//   [sequence A bytes, 8 bytes slack][sequence B bytes, 8 bytes slack][cur: cap16 u16][nxt: cap16 u16]
+// The sequences take what they need and the two wavefront buffers share the rest (208 KB in all at the default capacity:
+// two 45 kbp haplotypes still leave room for edit distances up to ~14,000).  Per wavefront entry a thread then
 // executes: three 16-bit shared loads for the recurrence (dynamic_wfa.rs:152-168), one byte compare that ends the extension
 // of 3 diagonals in 4 on unrelated sequence, and only for the others an aligned-word XOR + ffs loop (4 bases per step) --
 // ~20 instructions instead of ~57 with virtual sequences read through 64-bit global addresses.
@@ -339,17 +339,26 @@ __device__ __forceinline__ void coop_stage(u8 *dst, const VSeq<false> &S) {
         *(u32 *)(dst + x) = v;
     }
 }
+// entries of each of the two 16-bit wavefront buffers once both sequences are staged (<= 0: they do not fit); offsets must
+// stay below 65535 even with the +1 per step of an untrimmed wavefront
+__device__ __forceinline__ int coop_staged_cap16(int la, int lb, int cap_ints) {
+    const long long seq = (long long)((la + 8 + 3) & ~3) + ((lb + 8 + 3) & ~3);
+    long long cap = (8LL * cap_ints - seq) / 4;
+    cap = min(cap, 2LL * (64000 - lb));
+    return (int)max(cap, 0LL);
+}
 __device__ __noinline__ void coop_dwfa_body_staged() {
     CoopJob &J = *(CoopJob *)avk_dyn_smem;
-    const int cap = J.cap_ints;
-    unsigned short *cur = (unsigned short *)(avk_dyn_smem + COOP_JOB_BYTES), *nxt = cur + cap;
-    u8 *sa = avk_dyn_smem + COOP_JOB_BYTES + 4 * (size_t)cap;
     const int tid = threadIdx.x, T = blockDim.x;
     VSeq<false> A, B;
     A.data = J.a_data; A.tail = J.a_tail; A.mlen = J.a_mlen; A.len = J.a_len;
     B.data = J.b_data; B.tail = J.b_tail; B.mlen = J.b_mlen; B.len = J.b_len;
-    const int la = A.len, lb = B.len, max_ed = J.max_ed, e_cap = (cap - 3) / 2;
+    const int la = A.len, lb = B.len, max_ed = J.max_ed;
+    u8 *sa = avk_dyn_smem + COOP_JOB_BYTES;
     u8 *sb = sa + ((la + 8 + 3) & ~3);
+    const int cap = coop_staged_cap16(la, lb, J.cap_ints);
+    unsigned short *cur = (unsigned short *)(sb + ((lb + 8 + 3) & ~3)), *nxt = cur + cap;
+    const int e_cap = (cap - 3) / 2;
     const bool to_full = J.to_full != 0;
     int *gw = (int *)(uintptr_t)J.wf;
     int e = J.ed, status = DWFA_OK;
@@ -403,8 +412,8 @@ __device__ __noinline__ void coop_dwfa_body_staged() {
 // executed by every thread of the CTA; the job is in CoopJob at the start of dynamic shared memory
 __device__ __noinline__ void coop_dwfa_body() {
     CoopJob &J = *(CoopJob *)avk_dyn_smem;
-    // both sequences fit beside a 16-bit wavefront (offsets stay below 65535 even with the +1 per step): fast path
-    if ((long long)J.a_len + J.b_len + 32 <= 4LL * J.cap_ints && J.a_len + J.cap_ints < 65000 && J.b_len + J.cap_ints < 65000) { coop_dwfa_body_staged(); return; }
+    // both sequences fit beside a 16-bit wavefront with room to grow: fast path
+    if (J.a_len < 64000 && J.b_len < 64000 && coop_staged_cap16(J.a_len, J.b_len, J.cap_ints) >= 2 * J.ed + 256) { coop_dwfa_body_staged(); return; }
     int *cur = (int *)(avk_dyn_smem + COOP_JOB_BYTES), *nxt = cur + J.cap_ints;
     const int tid = threadIdx.x, T = blockDim.x;
     VSeq<false> A, B;

@@ -112,23 +112,80 @@ __global__ void __launch_bounds__(256) k_alt_ed(DevBatch b, u64 v_base, u64 n_va
     flush_work<false>(hdr, work_out);
 }
 
-__global__ void __launch_bounds__(256) k_wfa_ed(u64 n_pairs, const u8 *pool, const u64 *a_off, const u32 *a_len,
+__global__ void __launch_bounds__(256) k_wfa_ed(const u32 *list, const u32 *n_list, const u8 *pool, const u64 *a_off, const u32 *a_len,
                                                 const u64 *b_off, const u32 *b_len, u32 *ed_out, u8 *scratch,
                                                 int scratch_ints, u32 *counter, unsigned long long *work_out) {
     const int lane = lane_id();
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 hdr = (u64)(uintptr_t)(scratch + warp * ((u64)scratch_ints * 4 + ARENA_HDR));
     clear_work<false>(hdr);
+    const u32 n_pairs = *n_list;
     for (;;) {
         u32 p = 0;
         if (lane == 0) p = atomicAdd(counter, 1u);
         p = __shfl_sync(AVK_FULL, p, 0);
         if (p >= n_pairs) break;
+        p = list[p];
         const int ed = wfa_ed_warp<false>(plain_seq(pool + a_off[p], (int)a_len[p]), plain_seq(pool + b_off[p], (int)b_len[p]),
                                           hdr + ARENA_HDR, (scratch_ints - 3) / 2, hdr);
         if (lane == 0) ed_out[p] = (u32)ed;
     }
     flush_work<false>(hdr, work_out);
+}
+
+// Long pairs: one alignment per CTA, advanced by all COOP_THREADS threads (coop_dwfa_body: sequences staged in shared memory,
+// 16-bit wavefront).  Thread 0 posts the job; if the wavefront outgrows shared memory warp 0 finishes it on the warp path.
+__global__ void __launch_bounds__(COOP_THREADS, 1) k_wfa_ed_cta(const u32 *list, const u32 *n_list, const u8 *pool, const u64 *a_off, const u32 *a_len,
+                                                                const u64 *b_off, const u32 *b_len, u32 *ed_out, u8 *scratch, int scratch_ints,
+                                                                int cap_ints, u32 *counter, unsigned long long *work_out) {
+    __shared__ u32 s_idx;
+    CoopJob &J = *(CoopJob *)avk_dyn_smem;
+    const u64 hdr = (u64)(uintptr_t)(scratch + (u64)blockIdx.x * ((u64)scratch_ints * 4 + ARENA_HDR));
+    if (threadIdx.x < 32) clear_work<false>(hdr);
+    const u32 n = *n_list;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_idx = atomicAdd(counter, 1u);
+        __syncthreads();
+        const u32 idx = s_idx;
+        if (idx >= n) break;
+        const u32 p = list[idx];
+        if (threadIdx.x == 0) {
+            int *gw = (int *)(uintptr_t)(hdr + ARENA_HDR);
+            gw[0] = 0;
+            J.wf = hdr + ARENA_HDR;
+            J.a_data = (u64)(uintptr_t)(pool + a_off[p]); J.a_mlen = J.a_len = (int)a_len[p]; J.a_tail = J.a_data + a_len[p];
+            J.b_data = (u64)(uintptr_t)(pool + b_off[p]); J.b_mlen = J.b_len = (int)b_len[p]; J.b_tail = J.b_data + b_len[p];
+            J.ed = 0; J.max_ed = 0x7ffffff0; J.to_full = 1; J.status = 0; J.exit_ = 0; J.matched = 0; J.cells = 0; J.cap_ints = cap_ints;
+        }
+        __threadfence();
+        __syncthreads();
+        coop_dwfa_body();
+        int ed = J.ed;
+        const int st = J.status;
+        if (threadIdx.x < 32) {
+            if (st == DWFA_COOP_SPILL) {                                   // wavefront outgrew shared memory: finish on the warp path
+                const int rc = dwfa_run<false>(hdr + ARENA_HDR, &ed, (scratch_ints - 3) / 2, plain_seq(pool + a_off[p], (int)a_len[p]),
+                                               plain_seq(pool + b_off[p], (int)b_len[p]), true, hdr);
+                if (rc != DWFA_OK) ed = -1;
+            }
+            if (threadIdx.x == 0) {
+                ed_out[p] = (u32)ed;
+                *(u64 *)(uintptr_t)(hdr + WK_CELLS) += J.cells; *(u64 *)(uintptr_t)(hdr + WK_MATCHED) += J.matched; *(u32 *)(uintptr_t)(hdr + WK_ALIGN) += 1;
+            }
+        }
+    }
+    if (threadIdx.x < 32) flush_work<false>(hdr, work_out);
+}
+
+// splits the pairs of a wfa_ed batch: long pairs go to the CTA-wide kernel, the rest to one warp each
+__global__ void __launch_bounds__(256) k_wfa_split(u64 n_pairs, const u32 *a_len, const u32 *b_len, u32 long_min, u32 max_sum, u32 *list_warp, u32 *n_warp,
+                                                   u32 *list_cta, u32 *n_cta) {
+    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const u32 la = a_len[p], lb = b_len[p];
+    const bool cta = min(la, lb) >= long_min && (u64)la + lb + 4096 <= max_sum && max(la, lb) < 60000u;
+    if (cta) list_cta[atomicAdd(n_cta, 1u)] = (u32)p; else list_warp[atomicAdd(n_warp, 1u)] = (u32)p;
 }
 
 // ---- cluster digests (compare path) -------------------------------------------------------------------------
@@ -664,7 +721,7 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
 // execute their task side by side; lanes whose cluster is finished commit it and take the next one from the list W (one
 // atomic per warp and round).  A cluster that does not fit the fixed workspace is appended to the reject list -- nothing
 // has been written for it -- and goes through the warp kernels (search / score / fused stages) as before.
-enum { THREAD_TPB = 256 };
+enum { THREAD_TPB = 256, TS_BATCH_MIN = 8 };
 struct ThreadSink {
     const avk_ts::Cluster &cl;
     const DevCompareOut &out;
@@ -696,66 +753,83 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
     u32 r = 0;
     bool more = true;                                            // warp-uniform: the list is not exhausted yet
     for (;;) {
-        // ---- fetch round: lanes without a cluster take the next ones
+        // Every trip: one diagonal for every lane that has a task (below).  The other kinds of work are done in batches --
+        // when at least TS_BATCH_MIN lanes wait for them, or when no lane can step -- so that the code they execute runs with
+        // several lanes at a time.
+        const bool idle = __ballot_sync(AVK_FULL, S.task.kind != TK_NONE) == 0u;
+        // ---- commit: lanes whose cluster is finished write its outputs (or hand it to the reject list)
         {
-            const bool want = S.phase == PH_FETCH;
-            const u32 m = __ballot_sync(AVK_FULL, want);
-            if (m && more) {
-                const int leader = __ffs(m) - 1;
-                u32 base = 0;
-                if (lane == leader) base = atomicAdd(t.work_ctr, (u32)__popc(m));
-                base = __shfl_sync(AVK_FULL, base, leader);
-                if (base + (u32)__popc(m) >= n_work) more = false;
-                if (want) {
-                    const u32 idx = base + (u32)__popc(m & ((1u << lane) - 1u));
-                    if (idx >= n_work) S.phase = PH_DONE;
-                    else {
-                        r = t.work_list[idx];
-                        const u32 c = b.contig[r];
-                        if (!enabled) S.stop(TS_REJECT);
-                        else if (c >= b.n_contigs || b.start[r] > b.end[r] || (u64)b.end[r] > b.contig_len[c] || b.end[r] > 0x7fff0000u ||
-                                 (int)cfg.max_branch_factor <= 0)
-                            S.stop(AVK_ST_BAD_INPUT);
-                        else S.begin(b.digest + b.digest_off[r], b.contig_ptr[c], (int)b.start[r], (int)b.end[r], (int)cfg.max_branch_factor);
-                    }
-                }
-            } else if (want) S.phase = PH_DONE;
-        }
-        if (__all_sync(AVK_FULL, S.phase == PH_DONE)) break;
-        // ---- every lane runs its cluster's control flow up to the next alignment ...
-        if (S.phase == PH_RUN) S.advance();
-        __syncwarp();
-        // ---- ... and all lanes execute their alignments side by side
-        if (S.task.kind != TK_NONE) S.exec_task();
-        __syncwarp();
-        // ---- commit round
-        if (S.phase == PH_COMMIT) {
-            int rc = S.rc;
-            S.phase = PH_FETCH;
-            if (rc == TS_REJECT) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = r;
-            else {
-                u64 *row = out.region_metrics ? out.region_metrics + (u64)r * (AVK_N_GROUPS * AVK_N_METRICS) : nullptr;
-                if (row) for (int i = 0; i < AVK_N_GROUPS * AVK_N_METRICS; ++i) row[i] = 0;
-                if (rc == AVK_ST_OK) {
-                    ThreadSink sink{S.c, out, row, slot};
-                    u32 e1 = 0, e2 = 0;
-                    uint16_t tm = 0;
-                    rc = commit_solution(S, sink, &e1, &e2, &tm);
+            const bool want = S.phase == PH_COMMIT;
+            const int cnt = __popc(__ballot_sync(AVK_FULL, want));
+            if (want && (cnt >= TS_BATCH_MIN || idle)) {
+                int rc = S.rc;
+                S.phase = PH_FETCH;
+                if (rc == TS_REJECT) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = r;
+                else {
+                    u64 *row = out.region_metrics ? out.region_metrics + (u64)r * (AVK_N_GROUPS * AVK_N_METRICS) : nullptr;
+                    if (row) for (int i = 0; i < AVK_N_GROUPS * AVK_N_METRICS; ++i) row[i] = 0;
                     if (rc == AVK_ST_OK) {
-                        out.ed1[r] = e1; out.ed2[r] = e2; out.type_mask[r] = tm;
-                        if (slot) { atomicOr(slot + TOT_MASK, (unsigned long long)tm); atomicAdd(slot + TOT_SOLVED, 1ull); }
+                        ThreadSink sink{S.c, out, row, slot};
+                        u32 e1 = 0, e2 = 0;
+                        uint16_t tm = 0;
+                        rc = commit_solution(S, sink, &e1, &e2, &tm);
+                        if (rc == AVK_ST_OK) {
+                            out.ed1[r] = e1; out.ed2[r] = e2; out.type_mask[r] = tm;
+                            if (slot) { atomicOr(slot + TOT_MASK, (unsigned long long)tm); atomicAdd(slot + TOT_SOLVED, 1ull); }
+                        }
                     }
-                }
-                out.status[r] = rc;
-                if (rc != AVK_ST_OK) {
-                    const u64 v0 = b.var_off[(u64)r * 2], v1 = b.var_off[(u64)r * 2 + 2];
-                    for (u64 v = v0; v < v1; ++v) { out.vexp[v] = 0; out.vobs[v] = 0; out.vcls[v] = AVK_CLASS_UNKNOWN; }
-                    out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = 0;
-                    if (out.seq_off) for (int k = 0; k < 5; ++k) out.seq_len[(u64)r * 5 + k] = 0;
-                    if (slot) atomicAdd(slot + TOT_ERRORS, 1ull);
+                    out.status[r] = rc;
+                    if (rc != AVK_ST_OK) {
+                        const u64 v0 = b.var_off[(u64)r * 2], v1 = b.var_off[(u64)r * 2 + 2];
+                        for (u64 v = v0; v < v1; ++v) { out.vexp[v] = 0; out.vobs[v] = 0; out.vcls[v] = AVK_CLASS_UNKNOWN; }
+                        out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = 0;
+                        if (out.seq_off) for (int k = 0; k < 5; ++k) out.seq_len[(u64)r * 5 + k] = 0;
+                        if (slot) atomicAdd(slot + TOT_ERRORS, 1ull);
+                    }
                 }
             }
         }
+        // ---- fetch: lanes without a cluster take the next ones from the list (one atomic per warp)
+        {
+            const bool want = S.phase == PH_FETCH;
+            const u32 m = __ballot_sync(AVK_FULL, want);
+            if (m && (__popc(m) >= TS_BATCH_MIN || idle)) {
+                if (more) {
+                    const int leader = __ffs(m) - 1;
+                    u32 base = 0;
+                    if (lane == leader) base = atomicAdd(t.work_ctr, (u32)__popc(m));
+                    base = __shfl_sync(AVK_FULL, base, leader);
+                    if (base + (u32)__popc(m) >= n_work) more = false;
+                    if (want) {
+                        const u32 idx = base + (u32)__popc(m & ((1u << lane) - 1u));
+                        if (idx >= n_work) S.phase = PH_DONE;
+                        else {
+                            r = t.work_list[idx];
+                            const u32 c = b.contig[r];
+                            if (!enabled) S.stop(TS_REJECT);
+                            else if (c >= b.n_contigs || b.start[r] > b.end[r] || (u64)b.end[r] > b.contig_len[c] || b.end[r] > 0x7fff0000u ||
+                                     (int)cfg.max_branch_factor <= 0)
+                                S.stop(AVK_ST_BAD_INPUT);
+                            else S.begin(b.digest + b.digest_off[r], b.contig_ptr[c], (int)b.start[r], (int)b.end[r], (int)cfg.max_branch_factor);
+                        }
+                    }
+                } else if (want) S.phase = PH_DONE;
+            }
+        }
+        if (__all_sync(AVK_FULL, S.phase == PH_DONE)) break;
+        // ---- advance: lanes between two tasks run their cluster's control flow up to the next alignment and set it up
+        {
+            const bool want = S.phase == PH_RUN && S.task.kind == TK_NONE;
+            const int cnt = __popc(__ballot_sync(AVK_FULL, want));
+            if (want && (cnt >= TS_BATCH_MIN || idle)) {
+                S.advance();
+                if (S.task.kind != TK_NONE) S.task_setup();
+            }
+        }
+        __syncwarp();
+        // ---- step: one wavefront diagonal per lane
+        if (S.task.kind != TK_NONE) S.task_step();
+        __syncwarp();
     }
     if (t.work_out) {   // work actually executed: one set of atomics per warp
         unsigned long long v[5] = {ctr.alignments, ctr.cells, ctr.matched, ctr.spops, ctr.xpops};
@@ -954,7 +1028,14 @@ struct avk_ctx {
     int coop_cap_ints = 26000;
     int wide_b0 = 256;
     bool use_thread_stage = true;   // AVK_NO_THREAD_STAGE=1: warp kernels only (A/B timing, tests of the warp path)
+    // Pipelined single-GPU call: sibling contexts on the same device (own stream and buffers, the owner's reference) solve
+    // alternating bins so that one bin's upload, another's kernels and a third's download overlap.
+    avk_ctx *ref_owner = nullptr;   // set in a sibling: whose reference it reads
+    avk_ctx *sib[2] = {nullptr, nullptr};
+    int pipe_bins = 8;              // AVK_PIPELINE_BINS (0 or 1: off)
+    u64 pipe_min_regions = 200000;  // batches below this are solved in one piece
 };
+static inline const avk_ctx *ref_of(const avk_ctx *ctx) { return ctx->ref_owner ? ctx->ref_owner : ctx; }
 
 static int ensure(avk_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -1004,6 +1085,7 @@ static int configure_kernels(avk_ctx *ctx) {
     SMEM_OPT_IN((k_compare<true, 1, MODE_FUSED>));
     SMEM_OPT_IN(k_compare_team);
     SMEM_OPT_IN(k_compare_thread);
+    SMEM_OPT_IN(k_wfa_ed_cta);
     SMEM_OPT_IN((k_merge_pairs<true, 3>));
     SMEM_OPT_IN((k_merge_pairs<true, 1>));
 #undef SMEM_OPT_IN
@@ -1039,6 +1121,8 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (const char *s = getenv("AVK_TEST_COOP_CAP_INTS")) ctx->coop_cap_ints = std::min<int>(COOP_CAP_INTS_MAX, std::max(64, atoi(s)));
     if (const char *s = getenv("AVK_TEST_WIDE_B0")) ctx->wide_b0 = std::max(1, atoi(s));
     if (const char *s = getenv("AVK_NO_THREAD_STAGE")) ctx->use_thread_stage = atoi(s) == 0;
+    if (const char *s = getenv("AVK_PIPELINE_BINS")) ctx->pipe_bins = std::max(0, atoi(s));
+    if (const char *s = getenv("AVK_PIPELINE_MIN_REGIONS")) ctx->pipe_min_regions = (u64)std::max(1LL, atoll(s));
     for (auto &e : ctx->tev) cudaEventCreate(&e);
     {
         int lo = 0, hi = 0;
@@ -1058,6 +1142,7 @@ extern "C" int avk_create(int device, avk_ctx **out) {
 
 extern "C" void avk_destroy(avk_ctx *ctx) {
     if (!ctx) return;
+    for (auto &sb : ctx->sib) if (sb) { avk_destroy(sb); sb = nullptr; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &st : ctx->side) if (st) cudaStreamSynchronize(st);
@@ -1178,7 +1263,7 @@ static int validate_batch(avk_ctx *ctx, const avk_region_batch *b, bool compare)
 
 // Upload regions [sc.lo, sc.hi) of the batch: a contiguous bin (the whole batch for one GPU).
 static int upload_batch(avk_ctx *ctx, const avk_region_batch *b, const BinScan &sc) {
-    if (ctx->contig_bufs.empty()) { ctx->err = "avk_set_reference has not been called"; return AVK_ERR_NO_REFERENCE; }
+    if (ref_of(ctx)->contig_bufs.empty()) { ctx->err = "avk_set_reference has not been called"; return AVK_ERR_NO_REFERENCE; }
     const u64 lo = sc.lo, n = sc.hi - sc.lo, K = b->n_inputs, v0 = sc.v0, nv = sc.v1 - sc.v0;
     const avk_variant_table &t = b->variants;
     ctx->have_batch = false; ctx->have_result = false;
@@ -1218,8 +1303,8 @@ static DevBatch dev_batch(avk_ctx *ctx) {
     d.raw = biased<const u32>(ctx->raw, vb); d.aoff = biased<const u32>(ctx->aoff, vb); d.l0 = biased<const u32>(ctx->l0, vb);
     d.l1 = biased<const u32>(ctx->l1, vb);
     d.pool = biased<const u8>(ctx->pool, ctx->p_base);
-    d.contig_ptr = (const u8 *const *)ctx->d_contig_ptr.p; d.contig_len = (const u64 *)ctx->d_contig_len.p;
-    d.n_contigs = (u32)ctx->contig_lens.size();
+    d.contig_ptr = (const u8 *const *)ref_of(ctx)->d_contig_ptr.p; d.contig_len = (const u64 *)ref_of(ctx)->d_contig_len.p;
+    d.n_contigs = (u32)ref_of(ctx)->contig_lens.size();
     d.alt_ed = biased<const u32>(ctx->alt_ed, vb);
     d.digest = (const u8 *)ctx->digest.p;
     d.digest_off = (const u64 *)ctx->digest_offs.p;
@@ -1758,9 +1843,56 @@ extern "C" int avk_compare_batch_range(avk_ctx *ctx, const avk_region_batch *bat
     return AVK_OK;
 }
 
+// Large batches on one GPU are solved as a pipeline: the batch is cut into contiguous bins (avk_partition_regions) and up to
+// three contexts on the same device -- this one and two siblings with their own stream and buffers, reading this context's
+// reference -- take the bins in turn, each from its own host thread.  A bin is upload -> kernels -> download on its
+// context's stream, so one bin's H2D copy, another's kernels and a third's D2H copy run at the same time; results land in
+// the caller's arrays at the bins' offsets and the bins' counters are added up, exactly as avk_compare_batch_multi does
+// across GPUs.
+static int compare_pipelined(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out) {
+    const int n_lanes = 3;
+    avk_ctx *lanes[3] = {ctx, nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) {
+        if (!ctx->sib[k]) {
+            avk_ctx *sb = nullptr;
+            const int rc = avk_create(ctx->device, &sb);
+            if (rc != AVK_OK) { ctx->err = "pipelined compare: could not create a sibling context"; return rc; }
+            sb->ref_owner = ctx;
+            sb->pipe_bins = 0;
+            ctx->sib[k] = sb;
+        }
+        lanes[1 + k] = ctx->sib[k];
+    }
+    const u32 n_bins = (u32)ctx->pipe_bins;
+    std::vector<u64> cuts(n_bins + 1);
+    avk_partition_regions(batch, n_bins, cuts.data());
+    std::vector<BinTotals> bts(n_bins);
+    std::vector<int> rcs(n_bins, AVK_OK);
+    std::vector<std::thread> th;
+    for (int l = 0; l < n_lanes; ++l)
+        th.emplace_back([&, l]() {
+            for (u32 k = (u32)l; k < n_bins; k += n_lanes) {
+                rcs[k] = compare_bin(lanes[l], batch, cuts[k], cuts[k + 1], cfg, out, bts[k]);
+                if (rcs[k] != AVK_OK) break;
+            }
+        });
+    for (auto &t : th) t.join();
+    for (u32 k = 0; k < n_bins; ++k)
+        if (rcs[k] != AVK_OK) { avk_ctx *l = lanes[k % n_lanes]; if (l != ctx) ctx->err = l->err; return rcs[k]; }
+    const bool strata = out->strat_off && out->strat_totals && out->n_strata;
+    for (u32 k = 0; k < n_bins; ++k) store_totals(out, bts[k], strata, k > 0);
+    return AVK_OK;
+}
+
 extern "C" int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out) {
     if (!ctx) return AVK_ERR_INVALID;
     if (!batch) { ctx->err = "null batch"; return AVK_ERR_INVALID; }
+    if (ctx->pipe_bins >= 2 && batch->n_regions >= ctx->pipe_min_regions && !ctx->ref_owner) {
+        if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+        const int rc = validate_batch(ctx, batch, true);
+        if (rc != AVK_OK) return rc;
+        return compare_pipelined(ctx, batch, cfg, out);
+    }
     return avk_compare_batch_range(ctx, batch, 0, batch->n_regions, cfg, out);
 }
 
@@ -2222,18 +2354,31 @@ extern "C" int avk_wfa_ed_batch(avk_ctx *ctx, uint64_t n_pairs, const uint8_t *p
     const int scratch_ints = (2 * (int)mx + 8 + 3) / 4 * 4;
     int warps = (int)std::min<u64>((u64)ctx->sm_count * 32, (n_pairs + 7) / 8 * 8);
     warps = (warps + 7) / 8 * 8;
-    ENSURE(ctx->scratch, (size_t)warps * ((size_t)scratch_ints * 4 + ARENA_HDR));
+    const int ctas = (int)std::min<u64>((u64)ctx->sm_count, n_pairs);
+    ENSURE(ctx->scratch, (size_t)(warps + ctas) * ((size_t)scratch_ints * 4 + ARENA_HDR));
+    ENSURE(ctx->fail_a, 4 * n_pairs); ENSURE(ctx->fail_b, 4 * n_pairs);
+    u32 *ctrs = (u32 *)ctx->counters.p;          // [0] warp work, [1] cta work, [2] |warp list|, [3] |cta list|
+    const int cap_ints = ctx->coop_cap_ints;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    k_wfa_split<<<(unsigned)((n_pairs + 255) / 256), 256, 0, ctx->stream>>>(n_pairs, (const u32 *)ctx->pair_a_len.p, (const u32 *)ctx->pair_b_len.p, 512u,
+                                                                          (u32)(8 * cap_ints), (u32 *)ctx->fail_a.p, ctrs + 2, (u32 *)ctx->fail_b.p, ctrs + 3);
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    k_wfa_ed<<<warps / 8, 256, 0, ctx->stream>>>(n_pairs, (const u8 *)ctx->pair_pool.p, (const u64 *)ctx->pair_a_off.p,
+    // long pairs first: one CTA each, the whole CTA on one wavefront
+    k_wfa_ed_cta<<<ctas, COOP_THREADS, COOP_JOB_BYTES + 2 * sizeof(int) * (size_t)cap_ints, ctx->stream>>>(
+        (const u32 *)ctx->fail_b.p, ctrs + 3, (const u8 *)ctx->pair_pool.p, (const u64 *)ctx->pair_a_off.p, (const u32 *)ctx->pair_a_len.p,
+        (const u64 *)ctx->pair_b_off.p, (const u32 *)ctx->pair_b_len.p, (u32 *)ctx->pair_ed.p,
+        (u8 *)ctx->scratch.p + (size_t)warps * ((size_t)scratch_ints * 4 + ARENA_HDR), scratch_ints, cap_ints, ctrs + 1, (unsigned long long *)ctx->work_ctr.p);
+    k_wfa_ed<<<warps / 8, 256, 0, ctx->stream>>>((const u32 *)ctx->fail_a.p, ctrs + 2, (const u8 *)ctx->pair_pool.p, (const u64 *)ctx->pair_a_off.p,
                                                   (const u32 *)ctx->pair_a_len.p, (const u64 *)ctx->pair_b_off.p,
                                                   (const u32 *)ctx->pair_b_len.p, (u32 *)ctx->pair_ed.p, (u8 *)ctx->scratch.p,
-                                                  scratch_ints, (u32 *)ctx->counters.p, (unsigned long long *)ctx->work_ctr.p);
+                                                  scratch_ints, ctrs, (unsigned long long *)ctx->work_ctr.p);
+    ctx->launches += 2;
     ctx->launches += 1;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    ctx->have_result = false;
     CK(cudaMemcpyAsync(ed_out, ctx->pair_ed.p, 4 * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return fetch_timings(ctx);

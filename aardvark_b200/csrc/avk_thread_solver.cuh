@@ -15,11 +15,13 @@
 //   * A haplotype sequence is never materialised: it is a list of pieces (reference runs and ALT alleles) and the
 //     longest-common-prefix walk reads the bytes in place; two reference runs at the same coordinate match without
 //     being read.
-//   * SIMT: 32 threads on 32 different clusters only run together where they execute the SAME instructions.  All the
-//     heavy work of the solve -- building two sequences and advancing a wavefront over them -- is therefore ONE function,
-//     exec_task(), and everything else is a coroutine, advance(), that runs a cluster's control flow (queue pops, quotas,
-//     prunes, scoring) up to the next alignment it needs and returns with a Task.  The kernel alternates the two for the
-//     whole warp: every lane advances to its next task, then all lanes execute their tasks side by side.
+//   * SIMT: 32 threads on 32 different clusters only run together where they execute the SAME instructions, and only stay
+//     together if what they execute there takes about the same time.  The unit of work every alignment decomposes into is the
+//     extension of ONE wavefront diagonal (a longest-common-prefix walk): task_step() does exactly one, and it is the only
+//     place in the kernel where sequences are compared.  Everything else is a coroutine: advance() runs a cluster's control
+//     flow (queue pops, quotas, prunes, scoring) up to the next alignment it needs and returns with a Task; task_setup()
+//     builds the task's two sequences.  The kernel's main loop gives every lane one task_step() per trip and lets the lanes
+//     that have finished a task advance to their next one in batches.
 //
 // Exactly the reference's searches are replayed -- same priority keys, node ids, quotas, prunes and tie-breaks
 // (query_optimizer.rs:166-365, exact_gt_optimizer.rs:108-357, waffle_solver.rs:122-522) -- with the exactness-preserving
@@ -110,6 +112,9 @@ struct Task {
     Spec a, b;
     int buf, init, src, ed_in, d0;
     bool update, finalize;
+    // micro-state of the wavefront pass in flight (task_step): next diagonal, maxima of the pass, finalize pass?
+    int i, mb, mo, matched;
+    bool full, fin_pass;
     // results
     bool ok;            // false: capacity exceeded, reject the cluster
     int ed, m;
@@ -232,65 +237,80 @@ struct Solver {
         }
     }
 
-    // DWFALite::update (to_full == false, dynamic_wfa.rs:68-84) / finalize (:183-198) on wavefront wf with distance *ed.
-    // returns false when the distance would exceed TS_EDCAP (the cluster is rejected)
-    AVK_HD bool dwfa_run(u16 *wf, int *ed_io, const PSeq &A, int la, const PSeq &B, int lb, bool to_full) {
-        int ed = *ed_io;
-        for (;;) {
-            int mb = -1, mo = -1, matched = 0;
-            bool full = false;
-            const int n = 2 * ed + 1;
-            for (int i = 0; i < n; ++i) {                     // extend(): :94-130
-                int d = wf[i];
-                int boff = d + ed - i;
-                if (boff < la && d < lb) {
-                    const int ext = lcp(A, la, boff, B, lb, d);
-                    d += ext; boff += ext; matched += ext;
-                    wf[i] = (u16)d;
-                }
-                mb = max_i(mb, boff); mo = max_i(mo, d);
-                full = full || (boff >= la && d >= lb);
-            }
-            ctr->cells += (u64)n; ctr->matched += (u64)matched;
-            if (to_full ? full : (mb >= la || mo >= lb)) break;
-            if (ed + 1 > TS_EDCAP) return false;
-            // increase_edit_distance(): :152-168, in place from the top
-            for (int i = n + 1; i >= 0; --i) {
-                int v = 0;
-                if (i < n) v = wf[i];
-                if (i >= 1 && i - 1 < n) v = max_i(v, wf[i - 1] + 1);
-                if (i >= 2 && i - 2 < n) v = max_i(v, wf[i - 2] + 1);
-                wf[i] = (u16)v;
-            }
-            ed += 1;
-        }
-        *ed_io = ed;
-        return true;
-    }
-
-    // ================================================================== the ONE place where sequences are built and aligned
-    AVK_HD void exec_task() {
+    // ================================================================== the ONE place where sequences are built ...
+    // task_setup(): builds the two sequences of the task and initialises its wavefront.  A task that cannot be set up (piece
+    // capacity) ends here with ok == false.
+    AVK_HD void task_setup() {
         Work &W = w();
         Task &t = task;
-        PSeq &A = W.seq[0], &B = W.seq[1];
-        t.ok = replay<true>(&A, t.ia, t.a) && replay<true>(&B, t.ib, t.b);
+        t.ok = replay<true>(&W.seq[0], t.ia, t.a) && replay<true>(&W.seq[1], t.ib, t.b);
         if (!t.ok) { t.kind = TK_NONE; return; }
+        if (t.kind == TK_PREFIX) return;
+        u16 *wf = W.wf[t.buf];
+        int ed = t.ed_in;
+        if (t.init == INIT_ZERO) { wf[0] = 0; ed = 0; }
+        else if (t.init == INIT_CLOSED0) { wf[0] = (u16)min_i(t.ia.plen, t.ib.plen); ed = 0; }   // parent had ED 0: its one diagonal stood at the end of its shorter sequence
+        else if (t.init == INIT_COPY) { const u16 *sw = W.wf[t.src]; for (int i = 0; i < 2 * ed + 1; ++i) wf[i] = sw[i]; }
+        t.ed = ed; t.i = 0; t.mb = -1; t.mo = -1; t.matched = 0; t.full = false;
+        t.fin_pass = !t.update;                                // wfa_ed: finalize() only
+    }
+    // ================================================================== ... and where wavefronts advance: ONE diagonal per call
+    // DWFALite::update (dynamic_wfa.rs:68-84) then finalize (:183-198), cut at the diagonal: extend() of diagonal t.i (:94-130);
+    // at the end of a pass over the wavefront the stop rule of the current pass is tested and, if it does not hold,
+    // increase_edit_distance() (:152-168) grows the wavefront in place.  finalize() starts with an extend() of its own: a pass
+    // over the already extended diagonals that only evaluates reached_full_diagonal.  The task ends with kind == TK_NONE.
+    AVK_HD void task_step() {
+        Work &W = w();
+        Task &t = task;
+        const PSeq &A = W.seq[0], &B = W.seq[1];
         const int la = t.ia.len, lb = t.ib.len;
         if (t.kind == TK_PREFIX) {
             t.m = lcp(A, la, t.d0, B, lb, t.d0);
             ctr->cells += 1; ctr->matched += (u64)t.m;
-        } else {
-            u16 *wf = W.wf[t.buf];
-            int ed = t.ed_in;
-            if (t.init == INIT_ZERO) { wf[0] = 0; ed = 0; }
-            else if (t.init == INIT_CLOSED0) { wf[0] = (u16)min_i(t.ia.plen, t.ib.plen); ed = 0; }   // parent had ED 0: its one diagonal stood at the end of its shorter sequence
-            else if (t.init == INIT_COPY) { const u16 *s = W.wf[t.src]; for (int i = 0; i < 2 * ed + 1; ++i) wf[i] = s[i]; }
-            bool ok = true;
-            if (t.update) ok = dwfa_run(wf, &ed, A, la, B, lb, false);
-            if (ok && t.finalize) { ok = dwfa_run(wf, &ed, A, la, B, lb, true); ctr->alignments += 1; }
-            t.ok = ok; t.ed = ed;
+            t.kind = TK_NONE;
+            return;
         }
-        t.kind = TK_NONE;
+        u16 *wf = W.wf[t.buf];
+        const int ed = t.ed, n = 2 * ed + 1;
+        {
+            const int i = t.i;
+            int d = wf[i];
+            int boff = d + ed - i;
+            if (boff < la && d < lb) {
+                const int ext = lcp(A, la, boff, B, lb, d);
+                d += ext; boff += ext; t.matched += ext;
+                wf[i] = (u16)d;
+            }
+            t.mb = max_i(t.mb, boff); t.mo = max_i(t.mo, d);
+            t.full = t.full || (boff >= la && d >= lb);
+            t.i = i + 1;
+        }
+        if (t.i < n) return;
+        // ---- end of a pass over the wavefront
+        ctr->cells += (u64)n; ctr->matched += (u64)t.matched;
+        const bool done = t.fin_pass ? t.full : (t.mb >= la || t.mo >= lb);
+        t.i = 0; t.mb = -1; t.mo = -1; t.matched = 0; t.full = false;
+        if (done) {
+            if (!t.fin_pass && t.finalize) { t.fin_pass = true; return; }
+            if (t.fin_pass) ctr->alignments += 1;
+            t.ok = true;
+            t.kind = TK_NONE;
+            return;
+        }
+        if (ed + 1 > TS_EDCAP) { t.ok = false; t.kind = TK_NONE; return; }
+        for (int i = n + 1; i >= 0; --i) {                    // increase_edit_distance(): in place from the top
+            int v = 0;
+            if (i < n) v = wf[i];
+            if (i >= 1 && i - 1 < n) v = max_i(v, wf[i - 1] + 1);
+            if (i >= 2 && i - 2 < n) v = max_i(v, wf[i - 2] + 1);
+            wf[i] = (u16)v;
+        }
+        t.ed = ed + 1;
+    }
+    // whole task at once (host harness)
+    AVK_HD void exec_task() {
+        task_setup();
+        while (task.kind != TK_NONE) task_step();
     }
 
     // ================================================================== begin: load the cluster

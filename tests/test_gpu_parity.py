@@ -546,3 +546,26 @@ def test_wfa_ed_100k_random_pairs_vs_oracle(solver):
     cpu = np.array([orc.wfa_ed(a, b) for a, b in pairs], dtype=np.uint32)
     assert np.array_equal(gpu, cpu)
     assert int(cpu.max()) > 30 and int((cpu == 0).sum()) > 1000
+
+
+def test_pipelined_single_gpu_call_vs_unpipelined(solver):
+    """avk_compare_batch on a large batch runs as a pipeline over sibling contexts of the same GPU (bins' uploads, kernels and
+    downloads overlap); the result must not depend on it.  The knob lowers the size threshold so that a small batch takes the
+    pipelined path."""
+    ref, batch = synth.workload_chr20(scale=0.03, seed=29)
+    cfg = CompareConfig(enable_sequences=False)
+    solver.set_reference([ref])
+    strat_off = np.arange(batch.n_regions + 1, dtype=np.uint64)
+    strat_idx = (np.arange(batch.n_regions) % 2).astype(np.uint32)
+    plain = solver.compare_batch(batch, cfg, strat_off=strat_off, strat_idx=strat_idx, n_strata=2)
+    plain_tot = solver.compare_batch(batch, cfg, region_metrics=False)
+    s = _solver_with_env(AVK_PIPELINE_MIN_REGIONS=100, AVK_PIPELINE_BINS=7)
+    try:
+        s.set_reference([ref])
+        assert s.compare_batch(batch, cfg, strat_off=strat_off, strat_idx=strat_idx, n_strata=2).diff(plain) == []
+        assert s.compare_batch(batch, cfg, region_metrics=False).diff(plain_tot) == []
+        off, plen = seq_offsets(batch)
+        cs = CompareConfig(enable_sequences=True)
+        assert s.compare_batch(batch, cs, seq_off=off, seq_pool_len=plen).diff(solver.compare_batch(batch, cs, seq_off=off, seq_pool_len=plen)) == []
+    finally:
+        s.close()
