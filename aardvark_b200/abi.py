@@ -114,6 +114,7 @@ class CompareOut(C.Structure):
         ("seq_off", _u64p),
         ("seq_len", _u32p),
         ("seq_pool", _u8p),
+        ("containment", _u64p),
     ]
 
 
@@ -122,6 +123,13 @@ class CompareDevView(C.Structure):
         ("lo", C.c_uint64), ("n_regions", C.c_uint64), ("v_base", C.c_uint64), ("n_variants", C.c_uint64),
         ("status", C.c_void_p), ("ed1", C.c_void_p), ("ed2", C.c_void_p), ("type_mask", C.c_void_p),
         ("var_expected", C.c_void_p), ("var_observed", C.c_void_p), ("var_class", C.c_void_p), ("totals", C.c_void_p),
+    ]
+
+
+class StratIntervals(C.Structure):
+    _fields_ = [
+        ("n_strata", C.c_uint32), ("n_contigs", C.c_uint32),
+        ("off", _u64p), ("first", _u32p), ("last", _u32p),
     ]
 
 

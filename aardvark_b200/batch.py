@@ -184,7 +184,9 @@ class CompareOutputs:
     """Caller-allocated arrays of an avk_compare_out."""
 
     def __init__(self, batch: RegionBatch, region_metrics=True, strat_off=None, strat_idx=None, n_strata=0,
-                 seq_off=None, seq_pool_len=0):
+                 seq_off=None, seq_pool_len=0, containment=False, device_strata=False):
+        """containment: ask for the per-region containment masks of the device lookup (Solver.set_stratifications);
+        device_strata: stratified sums over that lookup instead of a strat_off / strat_idx membership list."""
         n, nv = batch.n_regions, batch.n_variants
         self.status = np.full(max(n, 1), -1, dtype=np.int32)
         self.ed1 = np.zeros(max(n, 1), dtype=np.uint32)
@@ -205,7 +207,8 @@ class CompareOutputs:
             self.strat_idx = np.zeros(1, dtype=np.uint32)
         self.n_strata = int(n_strata)
         self.strat_totals = (np.zeros((max(n_strata, 1), abi.N_GROUPS, abi.N_METRICS), dtype=np.uint64)
-                             if strat_off is not None else None)
+                             if (strat_off is not None or device_strata) else None)
+        self.containment = np.zeros(max(n, 1), dtype=np.uint64) if containment else None
         self.seq_off = None if seq_off is None else np.ascontiguousarray(seq_off, dtype=np.uint64)
         self.seq_len = np.zeros(max(n, 1) * 5, dtype=np.uint32) if seq_off is not None else None
         self.seq_pool = np.zeros(max(int(seq_pool_len), 1), dtype=np.uint8) if seq_off is not None else None
@@ -218,10 +221,10 @@ class CompareOutputs:
             abi.ptr(self.type_mask), abi.ptr(self.var_expected), abi.ptr(self.var_observed), abi.ptr(self.var_class),
             abi.ptr(self.totals), abi.ptr(self.totals_mask), abi.ptr(self.solved_blocks), abi.ptr(self.error_blocks),
             abi.ptr(self.strat_off), abi.ptr(self.strat_idx), self.n_strata, 0, abi.ptr(self.strat_totals),
-            abi.ptr(self.seq_off), abi.ptr(self.seq_len), abi.ptr(self.seq_pool))
+            abi.ptr(self.seq_off), abi.ptr(self.seq_len), abi.ptr(self.seq_pool), abi.ptr(self.containment))
 
     FIELDS = ("status", "ed1", "ed2", "region_metrics", "type_mask", "var_expected", "var_observed", "var_class",
-              "totals", "totals_mask", "solved_blocks", "error_blocks", "strat_totals", "seq_len")
+              "totals", "totals_mask", "solved_blocks", "error_blocks", "strat_totals", "seq_len", "containment")
 
     def diff(self, other) -> List[str]:
         """Names of output arrays that differ from `other` (bit-exact comparison)."""
@@ -275,3 +278,40 @@ def seq_offsets(batch: RegionBatch):
     sizes = np.stack([win, win + t_alt, win + t_alt, win + q_alt, win + q_alt], axis=1).reshape(-1)
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
     return off, int(off[-1])
+
+
+class StratIntervals:
+    """Stratification interval sets for the device containment lookup (avk_strat_intervals): `strata` is a list (one entry
+    per stratum, in label order) of lists of (contig index, BED start, BED end) -- half-open BED coordinates, stored 0-based
+    inclusive as the reference does (stratifications.rs:158-163)."""
+
+    def __init__(self, strata, n_contigs):
+        self.n_strata, self.n_contigs = len(strata), int(n_contigs)
+        off, first, last = [0], [], []
+        for ivs in strata:
+            for c in range(self.n_contigs):
+                for (cc, s, e) in ivs:
+                    if cc == c:
+                        first.append(s)
+                        last.append(e - 1)
+                off.append(len(first))
+        self.off = np.asarray(off, dtype=np.uint64)
+        self.first = np.asarray(first if first else [0], dtype=np.uint32)
+        self.last = np.asarray(last if last else [0], dtype=np.uint32)
+
+    def to_c(self) -> abi.StratIntervals:
+        return abi.StratIntervals(self.n_strata, self.n_contigs, abi.ptr(self.off), abi.ptr(self.first), abi.ptr(self.last))
+
+
+def masks_to_membership(masks: np.ndarray):
+    """containment bit masks -> (strat_off, strat_idx) membership lists"""
+    off, idx = [0], []
+    for m in masks.tolist():
+        s = 0
+        while m:
+            if m & 1:
+                idx.append(s)
+            m >>= 1
+            s += 1
+        off.append(len(idx))
+    return np.asarray(off, dtype=np.uint64), np.asarray(idx if idx else [0], dtype=np.uint32)

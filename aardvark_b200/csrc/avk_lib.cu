@@ -324,7 +324,7 @@ __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const Dev
 // Clusters with at least `dense_n` variants skip the search / score pair: they go to list `dense`, which the fused
 // stage starts on first (the longest searches of a batch are among them).
 __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, u64 n, u32 *work_list,
-                                                        u32 *work_ctr, u32 *dense, u32 *dense_ctr, int dense_n) {
+                                                        u32 *work_ctr, u32 *dense, u32 *dense_ctr, int dense_n, u64 *work_key) {
     const int lane = lane_id();
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
@@ -388,7 +388,30 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
         if (lane == 0 && dn) pos1 = atomicAdd(dense_ctr, (u32)__popc(dn));
         pos0 = __shfl_sync(AVK_FULL, pos0, 0);
         pos1 = __shfl_sync(AVK_FULL, pos1, 0);
-        if (r < n && !simple && !is_dense) work_list[pos0 + __popc(rest & ((1u << lane) - 1))] = (u32)r;
+        if (r < n && !simple && !is_dense) {
+            const u32 slot_ = pos0 + __popc(rest & ((1u << lane) - 1));
+            work_list[slot_] = (u32)r;
+            if (work_key) {
+                // SHAPE of the cluster: per order entry {side, zygosity, same position as the previous entry, allele-length class}.
+                // Clusters of the same shape run (nearly) the same control flow in the thread-per-cluster stage; the list is
+                // sorted by this key so that the 32 lanes of a warp get clusters of one shape.
+                u64 key = 0;
+                if (nvar > 0 && nvar <= 10) {
+                    const u8 *recs = b.digest + b.digest_off[r] + PH_SIZE;
+                    u32 prev = 0xffffffffu;
+                    for (int oi = 0; oi < nvar; ++oi) {
+                        const uint4 a = *(const uint4 *)(recs + (size_t)VI_SIZE * oi);          // pos, l0, l1, aoff
+                        const u32 f = *(const u32 *)(recs + (size_t)VI_SIZE * oi + VI_FLAGS);
+                        const u32 lc = (a.y == 1 && a.z == 1) ? 0u : (a.y == 1 ? 1u : (a.z == 1 ? 2u : 3u));
+                        const u32 code = ((f >> 16) & 1u) | ((((f >> 8) & 0xffu) & 3u) << 1) | ((a.x == prev ? 1u : 0u) << 3) | (lc << 4);
+                        key = (key << 6) | code;
+                        prev = a.x;
+                    }
+                    key |= (u64)nvar << 60;
+                } else key = (u64)min(nvar, 15) << 60;
+                work_key[slot_] = key;
+            }
+        }
         if (is_dense) dense[pos1 + __popc(dn & ((1u << lane) - 1))] = (u32)r;
         if (simple) {
             out.status[r] = AVK_ST_OK; out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = (uint16_t)supported;   // vtype is one of them
@@ -932,7 +955,7 @@ __global__ void __launch_bounds__(256) k_merge_classify(DevBatch b, DevMergeOut 
 __global__ void __launch_bounds__(288) k_reduce(u64 n, const int *status, const u64 *region_metrics, const uint16_t *type_mask,
                                                 unsigned long long *totals, u32 *totals_mask, unsigned long long *solved,
                                                 unsigned long long *errors, const u64 *strat_off, const u32 *strat_idx,
-                                                unsigned long long *strat_totals) {
+                                                const u64 *strat_mask, unsigned long long *strat_totals) {
     const int j = threadIdx.x;
     unsigned long long acc = 0, ok = 0, bad = 0;
     u32 mask = 0;
@@ -958,11 +981,40 @@ __global__ void __launch_bounds__(288) k_reduce(u64 n, const int *status, const 
             acc += v[k];
             if (strat_off && v[k]) {
                 for (u64 s = strat_off[r]; s < strat_off[r + 1]; ++s) atomicAdd(strat_totals + (u64)strat_idx[s] * RED_COLS + j, v[k]);
+            } else if (strat_mask && v[k]) {
+                for (u64 m = strat_mask[r]; m; m &= m - 1) atomicAdd(strat_totals + (u64)(__ffsll((long long)m) - 1) * RED_COLS + j, v[k]);
             }
         }
     }
     if (j < RED_COLS && acc) atomicAdd(totals + j, acc);
     if (j == 0) { atomicAdd(solved, ok); atomicAdd(errors, bad); atomicOr(totals_mask, mask); }
+}
+
+// Stratifications::containments (stratifications.rs:108-118, 197-210) for every region: one thread per region.
+// var_coordinates() (compare_region.rs:63-74): start = min(first truth pos, first query pos), end = max(end of the LAST truth
+// variant, end of the LAST query variant) -- last(), not the furthest-reaching variant -- queried 0-based inclusive as
+// (start, end - 1) (waffle_solver.rs:151-166).  The intervals of a (stratum, contig) are sorted by `first` with a running
+// maximum of `last`: some interval contains [a, b] iff the running maximum at the rightmost interval with first <= a is >= b.
+__global__ void __launch_bounds__(256) k_strat_contain(DevBatch b, u64 n, u32 n_strata, u32 n_contigs, const u64 *off, const u32 *first,
+                                                       const u32 *pmax_last, u64 *mask_out) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const u64 t0 = b.var_off[r * 2], q0 = b.var_off[r * 2 + 1], q1 = b.var_off[r * 2 + 2];
+    u64 start = ~0ull, end = 0;
+    if (q0 > t0) { start = min(start, (u64)b.pos[t0]); end = max(end, (u64)b.pos[q0 - 1] + b.l0[q0 - 1]); }
+    if (q1 > q0) { start = min(start, (u64)b.pos[q0]); end = max(end, (u64)b.pos[q1 - 1] + b.l0[q1 - 1]); }
+    u64 mask = 0;
+    const u32 c = b.contig[r];
+    if (start < end && c < n_contigs) {
+        const u64 a = start, z = end - 1;
+        for (u32 s = 0; s < n_strata; ++s) {
+            const u64 i0 = off[(u64)s * n_contigs + c], i1 = off[(u64)s * n_contigs + c + 1];
+            u64 lo = i0, hi = i1;                                   // first interval with first > a
+            while (lo < hi) { const u64 m = (lo + hi) >> 1; if ((u64)first[m] <= a) lo = m + 1; else hi = m; }
+            if (lo > i0 && (u64)pmax_last[lo - 1] >= z) mask |= 1ull << s;
+        }
+    }
+    mask_out[r] = mask;
 }
 
 // INT32 ALU peak probe for the integer roofline: 8 independent chains of
@@ -1001,8 +1053,10 @@ struct avk_ctx {
     DevBuf status, ed1, ed2, region_metrics, type_mask, vexp, vobs, vcls, totals, tot_slots, strat_off, strat_idx, strat_totals,
         seq_off, seq_len, seq_pool, m_cls, m_nidx, m_idx, m_rows, m_perr, m_tasks;
     // workspace
-    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, fail_x, fail_t, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
+    DevBuf digest, digest_sizes, digest_offs, scan_tmp, blobs, scratch, arena, arena2, counters, fail_a, fail_b, fail_c, fail_d, fail_h, fail_w, fail_x, fail_t, fail_s, shape_key, work_ctr, pair_a_off, pair_b_off, pair_a_len, pair_b_len, pair_ed, pair_pool;
     DevBuf rb[24];   // region builder temporaries
+    DevBuf st_off, st_first, st_pmax, st_mask;   // stratification intervals (avk_set_stratifications) and per-region containment masks
+    u32 st_n = 0, st_contigs = 0;
     int dense_n = 10;   // clusters with at least this many variants start in the fused dense-cluster stage (tuning: AVK_DENSE_N)
     // Resident batch: regions [lo, lo + n_regions) of the caller's batch, i.e. variants [v_base, v_base + n_variants) of its
     // variant table and bytes [p_base, ..) of its allele pool.  Per-variant device pointers are biased by these bases so
@@ -1028,11 +1082,12 @@ struct avk_ctx {
     int coop_cap_ints = 26000;
     int wide_b0 = 256;
     bool use_thread_stage = true;   // AVK_NO_THREAD_STAGE=1: warp kernels only (A/B timing, tests of the warp path)
+    bool sort_shapes = true;        // AVK_NO_SHAPE_SORT=1: the thread stage takes its clusters in list order
     // Pipelined single-GPU call: sibling contexts on the same device (own stream and buffers, the owner's reference) solve
     // alternating bins so that one bin's upload, another's kernels and a third's download overlap.
     avk_ctx *ref_owner = nullptr;   // set in a sibling: whose reference it reads
     avk_ctx *sib[2] = {nullptr, nullptr};
-    int pipe_bins = 8;              // AVK_PIPELINE_BINS (0 or 1: off)
+    int pipe_bins = 0;              // AVK_PIPELINE_BINS (0 or 1: off, the default: measured slower than one piece)
     u64 pipe_min_regions = 200000;  // batches below this are solved in one piece
 };
 static inline const avk_ctx *ref_of(const avk_ctx *ctx) { return ctx->ref_owner ? ctx->ref_owner : ctx; }
@@ -1121,6 +1176,7 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (const char *s = getenv("AVK_TEST_COOP_CAP_INTS")) ctx->coop_cap_ints = std::min<int>(COOP_CAP_INTS_MAX, std::max(64, atoi(s)));
     if (const char *s = getenv("AVK_TEST_WIDE_B0")) ctx->wide_b0 = std::max(1, atoi(s));
     if (const char *s = getenv("AVK_NO_THREAD_STAGE")) ctx->use_thread_stage = atoi(s) == 0;
+    if (const char *s = getenv("AVK_NO_SHAPE_SORT")) ctx->sort_shapes = atoi(s) == 0;
     if (const char *s = getenv("AVK_PIPELINE_BINS")) ctx->pipe_bins = std::max(0, atoi(s));
     if (const char *s = getenv("AVK_PIPELINE_MIN_REGIONS")) ctx->pipe_min_regions = (u64)std::max(1LL, atoll(s));
     for (auto &e : ctx->tev) cudaEventCreate(&e);
@@ -1150,10 +1206,11 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->tot_slots, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x, &ctx->fail_t,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x, &ctx->fail_t, &ctx->fail_s, &ctx->shape_key,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
+    for (DevBuf *b : {&ctx->st_off, &ctx->st_first, &ctx->st_pmax, &ctx->st_mask}) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->tev) if (e) cudaEventDestroy(e);
@@ -1186,6 +1243,35 @@ extern "C" int avk_set_reference(avk_ctx *ctx, uint32_t n_contigs, const uint8_t
     UPLOAD(ctx->d_contig_len, lens, sizeof(u64) * n_contigs);
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_result = false;
+    return AVK_OK;
+}
+
+extern "C" int avk_set_stratifications(avk_ctx *ctx, const avk_strat_intervals *in) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!in || in->n_strata > 64 || (in->n_strata && in->n_contigs && !in->off)) { ctx->err = "avk_set_stratifications: at most 64 strata, non-null offsets"; return AVK_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const u64 cells = (u64)in->n_strata * in->n_contigs;
+    const u64 n_iv = cells ? in->off[cells] : 0;
+    if (n_iv && (!in->first || !in->last)) { ctx->err = "avk_set_stratifications: null interval arrays"; return AVK_ERR_INVALID; }
+    std::vector<u32> first(n_iv), pmax(n_iv);
+    std::vector<std::pair<u32, u32>> iv;
+    for (u64 k = 0; k < cells; ++k) {
+        const u64 i0 = in->off[k], i1 = in->off[k + 1];
+        if (i0 > i1 || i1 > n_iv) { ctx->err = "avk_set_stratifications: offsets are not monotone"; return AVK_ERR_INVALID; }
+        iv.clear();
+        for (u64 i = i0; i < i1; ++i) iv.emplace_back(in->first[i], in->last[i]);
+        std::sort(iv.begin(), iv.end());
+        u32 run = 0;
+        for (u64 i = i0; i < i1; ++i) { run = std::max(run, iv[i - i0].second); first[i] = iv[i - i0].first; pmax[i] = run; }
+    }
+    std::vector<u64> off(cells + 1, 0);
+    for (u64 k = 0; k <= cells && cells; ++k) off[k] = in->off[k];
+    UPLOAD(ctx->st_off, off.data(), 8 * (cells + 1));
+    UPLOAD(ctx->st_first, first.data(), 4 * n_iv);
+    UPLOAD(ctx->st_pmax, pmax.data(), 4 * n_iv);
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->st_n = in->n_strata; ctx->st_contigs = in->n_contigs;
+    for (auto &sb : ctx->sib) if (sb) { const int rc = avk_set_stratifications(sb, in); if (rc != AVK_OK) return rc; }
     return AVK_OK;
 }
 
@@ -1456,6 +1542,10 @@ static int run_prepare(avk_ctx *ctx, const DevBatch &db) {
     return AVK_OK;
 }
 
+// strata sums are requested with a caller-provided membership list (strat_off / strat_idx) or, when strat_off is NULL, through
+// the device containment lookup (avk_set_stratifications)
+static inline bool strata_wanted(const avk_compare_out *out) { return out->strat_totals && out->n_strata; }
+
 struct CompareRun {           // what one compare pass needs to know to launch, finish and (rarely) re-finish
     DevBatch db;
     DevCompareOut out;
@@ -1463,6 +1553,8 @@ struct CompareRun {           // what one compare pass needs to know to launch, 
     bool strata = false;
     const u64 *strat_off = nullptr;
     const u32 *strat_idx = nullptr;
+    const u64 *strat_mask = nullptr;   // device containment lookup instead of a caller-provided membership list
+    bool want_contain = false;         // compute the containment masks (for the strata sums and / or out->containment)
     u32 n_strata = 0;
 };
 
@@ -1513,7 +1605,21 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p, *LX = (u32 *)ctx->fail_x.p;
     // closed-form clusters; >= dense_n variants -> X (dense); the rest -> W
-    k_compare_simple<<<sm * 8, 256, 0, ctx->stream>>>(R.db, R.out, R.cfg, n, LW, ctrs + 12, LX, ctrs + 17, ctx->dense_n);
+    u64 *keys = nullptr;
+    if (ctx->use_thread_stage && ctx->sort_shapes) {
+        ENSURE(ctx->shape_key, 16 * n);                               // keys in / out
+        ENSURE(ctx->fail_s, 4 * n);
+        keys = (u64 *)ctx->shape_key.p;
+        CK(cudaMemsetAsync(keys, 0xff, 8 * n, ctx->stream));          // unused tail sorts behind every real key
+    }
+    k_compare_simple<<<sm * 8, 256, 0, ctx->stream>>>(R.db, R.out, R.cfg, n, LW, ctrs + 12, LX, ctrs + 17, ctx->dense_n, keys);
+    if (keys) {                                                       // W sorted by shape -> fail_s (the first |W| entries are the real ones)
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys + n, LW, (u32 *)ctx->fail_s.p, (int)n, 0, 64, ctx->stream);
+        ENSURE(ctx->scan_tmp, need);
+        cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, need, keys, keys + n, LW, (u32 *)ctx->fail_s.p, (int)n, 0, 64, ctx->stream);
+        ctx->launches += 1;
+    }
     const size_t spill_warp = 1u << 20, spill_half = (size_t)sm * 8 * spill_warp;
     // A dense cluster is solved by one warp team in up to ~1 ms, so the dense stage ends with a few busy teams.  It is launched
     // first (main stream, one 216 KB CTA per SM); search, score and the fused stage for their rejects follow on a
@@ -1533,7 +1639,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     int ls_ctr = 12;
     if (ctx->use_thread_stage) {                                                             // W -> solved by one thread each; rejects -> W2
         u32 *LW2 = (u32 *)ctx->fail_t.p;
-        TierArgs a = tier_args(ctx, LW, 12, 19, LW2, 13, sizeof(avk_ts::Work), nullptr);
+        TierArgs a = tier_args(ctx, keys ? (const u32 *)ctx->fail_s.p : LW, 12, 19, LW2, 13, sizeof(avk_ts::Work), nullptr);
         k_compare_thread<<<(unsigned)std::min<u64>((u64)sm, (n + THREAD_TPB - 1) / THREAD_TPB), THREAD_TPB, THREAD_TPB * sizeof(avk_ts::Work), ctx->side[0]>>>(R.db, R.out, R.cfg, a);
         ctx->launches += 1;
         LS = LW2; ls_ctr = 13;
@@ -1610,7 +1716,7 @@ static int run_finalize(avk_ctx *ctx, const CompareRun &R) {
         if (n) {
             k_reduce<<<(unsigned)std::min<u64>(n, (u64)ctx->sm_count * 8), 288, 0, ctx->stream>>>(
                 n, R.out.status, R.out.region_metrics, R.out.type_mask, tot, (u32 *)(tot + RED_COLS), tot + RED_COLS + 1, tot + RED_COLS + 2,
-                R.strat_off, R.strat_idx, (unsigned long long *)ctx->strat_totals.p);
+                R.strat_off, R.strat_idx, R.strat_mask, (unsigned long long *)ctx->strat_totals.p);
             ctx->launches += 1;
         }
     }
@@ -1619,9 +1725,10 @@ static int run_finalize(avk_ctx *ctx, const CompareRun &R) {
 }
 
 // Launches one compare pass over the resident batch; nothing waits for the device.
-static int compare_launch(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, bool want_rows, bool strata, u32 n_strata, CompareRun &R) {
+static int compare_launch(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, bool want_rows, bool strata, u32 n_strata, bool strat_dev, bool want_contain, CompareRun &R) {
     const u64 n = ctx->n_regions, nv = ctx->n_variants;
     const bool rows = want_rows || strata;
+    if (strat_dev || want_contain) ENSURE(ctx->st_mask, 8 * n);
     ENSURE(ctx->status, 4 * n); ENSURE(ctx->ed1, 4 * n); ENSURE(ctx->ed2, 4 * n);
     if (rows) ENSURE(ctx->region_metrics, 8ull * RED_COLS * n);
     ENSURE(ctx->type_mask, 2 * n);
@@ -1648,8 +1755,10 @@ static int compare_launch(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_se
     out.seq_len = (u32 *)ctx->seq_len.p; out.seq_pool = biased<u8>(ctx->seq_pool, ctx->seq_base);
     R.cfg = *cfg;
     R.strata = strata; R.n_strata = n_strata;
-    R.strat_off = strata ? (const u64 *)ctx->strat_off.p : nullptr;
-    R.strat_idx = strata ? biased<const u32>(ctx->strat_idx, ctx->strat_base) : nullptr;
+    R.strat_off = (strata && !strat_dev) ? (const u64 *)ctx->strat_off.p : nullptr;
+    R.strat_idx = (strata && !strat_dev) ? biased<const u32>(ctx->strat_idx, ctx->strat_base) : nullptr;
+    R.strat_mask = (strata && strat_dev) ? (const u64 *)ctx->st_mask.p : nullptr;
+    R.want_contain = strat_dev || want_contain;
     ctx->have_result = false;
 
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1658,6 +1767,11 @@ static int compare_launch(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_se
     rc = run_prepare(ctx, R.db);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (R.want_contain && n) {
+        k_strat_contain<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(R.db, n, ctx->st_n, ctx->st_contigs, (const u64 *)ctx->st_off.p,
+                                                                              (const u32 *)ctx->st_first.p, (const u32 *)ctx->st_pmax.p, (u64 *)ctx->st_mask.p);
+        ctx->launches += 1;
+    }
     rc = run_compare_pipeline(ctx, R);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1740,6 +1854,7 @@ static int download_compare_async(avk_ctx *ctx, avk_compare_out *out, bool want_
     DL(out->var_observed ? out->var_observed + vb : nullptr, ctx->vobs, nv);
     DL(out->var_class ? out->var_class + vb : nullptr, ctx->vcls, nv);
     CK(cudaMemcpyAsync(ctx->h_pin + 256, ctx->totals.p, 8 * RED_COLS + 64, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->containment && ctx->st_mask.p) DL(out->containment + lo, ctx->st_mask, 8 * n);
     if (want_seq) {
         DL(out->seq_len + lo * 5, ctx->seq_len, 4 * 5 * n);
         DL(out->seq_pool + ctx->seq_base, ctx->seq_pool, seq_bytes);
@@ -1769,7 +1884,7 @@ static void store_totals(avk_compare_out *out, const BinTotals &bt, bool strata,
 }
 
 // optional inputs that travel with the outputs struct: sequence-bundle layout and stratum membership of the bin
-static int prepare_outputs_on_device(avk_ctx *ctx, const avk_compare_out *out, u64 n_total, bool &want_seq, u64 &seq_bytes, bool &strata) {
+static int prepare_outputs_on_device(avk_ctx *ctx, const avk_compare_out *out, u64 n_total, bool &want_seq, u64 &seq_bytes, bool &strata, bool &strat_dev) {
     const u64 n = ctx->n_regions, lo = ctx->lo;
     want_seq = out->seq_off && out->seq_len && out->seq_pool;
     seq_bytes = 0;
@@ -1783,8 +1898,13 @@ static int prepare_outputs_on_device(avk_ctx *ctx, const avk_compare_out *out, u
         ENSURE(ctx->seq_pool, seq_bytes);
         CK(cudaMemsetAsync(ctx->seq_len.p, 0, 4 * 5 * n + 4, ctx->stream));
     }
-    strata = out->strat_off && out->strat_totals && out->n_strata;
-    if (strata) {
+    strata = strata_wanted(out);
+    strat_dev = strata && !out->strat_off;
+    if ((strat_dev || out->containment) && (ctx->st_n == 0 || (strat_dev && ctx->st_n != out->n_strata) || ctx->st_contigs != (u32)ref_of(ctx)->contig_lens.size())) {
+        ctx->err = "the device containment lookup needs avk_set_stratifications (same number of strata as n_strata, contigs as the reference)";
+        return AVK_ERR_INVALID;
+    }
+    if (strata && !strat_dev) {
         const u64 s0 = out->strat_off[lo], s1 = out->strat_off[lo + n];
         bool bad = s0 > s1 || (s1 > s0 && !out->strat_idx);
         for (u64 r = lo; r < lo + n && !bad; ++r) bad = out->strat_off[r] > out->strat_off[r + 1];
@@ -1807,12 +1927,12 @@ static int compare_bin(avk_ctx *ctx, const avk_region_batch *batch, u64 lo, u64 
     if (rc != AVK_OK) return rc;
     rc = upload_batch(ctx, batch, sc);
     if (rc != AVK_OK) return rc;
-    bool want_seq, strata; u64 seq_bytes;
-    rc = prepare_outputs_on_device(ctx, out, batch->n_regions, want_seq, seq_bytes, strata);
+    bool want_seq, strata, strat_dev; u64 seq_bytes;
+    rc = prepare_outputs_on_device(ctx, out, batch->n_regions, want_seq, seq_bytes, strata, strat_dev);
     if (rc != AVK_OK) return rc;
     CompareRun R;
     const bool want_rows = out->region_metrics != nullptr || (cfg->flags & AVK_CMP_KEEP_REGION_ROWS);
-    rc = compare_launch(ctx, cfg, want_seq, want_rows, strata, strata ? out->n_strata : 0, R);
+    rc = compare_launch(ctx, cfg, want_seq, want_rows, strata, strata ? out->n_strata : 0, strat_dev, out->containment != nullptr, R);
     if (rc != AVK_OK) return rc;
     rc = download_compare_async(ctx, out, want_seq, seq_bytes);
     if (rc != AVK_OK) return rc;
@@ -1839,7 +1959,7 @@ extern "C" int avk_compare_batch_range(avk_ctx *ctx, const avk_region_batch *bat
     BinTotals bt;
     rc = compare_bin(ctx, batch, lo, hi, cfg, out, bt);
     if (rc != AVK_OK) return rc;
-    store_totals(out, bt, out->strat_off && out->strat_totals && out->n_strata, false);
+    store_totals(out, bt, strata_wanted(out), false);
     return AVK_OK;
 }
 
@@ -1879,7 +1999,7 @@ static int compare_pipelined(avk_ctx *ctx, const avk_region_batch *batch, const 
     for (auto &t : th) t.join();
     for (u32 k = 0; k < n_bins; ++k)
         if (rcs[k] != AVK_OK) { avk_ctx *l = lanes[k % n_lanes]; if (l != ctx) ctx->err = l->err; return rcs[k]; }
-    const bool strata = out->strat_off && out->strat_totals && out->n_strata;
+    const bool strata = strata_wanted(out);
     for (u32 k = 0; k < n_bins; ++k) store_totals(out, bts[k], strata, k > 0);
     return AVK_OK;
 }
@@ -1949,7 +2069,7 @@ extern "C" int avk_compare_batch_multi(avk_ctx *const *ctxs, uint32_t n_ctx, con
     for (auto &t : th) t.join();
     for (uint32_t k = 0; k < n_ctx; ++k)
         if (rcs[k] != AVK_OK) { if (k && ctxs[k]) ctx->err = "device " + std::to_string(k) + ": " + ctxs[k]->err; return rcs[k]; }
-    const bool strata = out->strat_off && out->strat_totals && out->n_strata;
+    const bool strata = strata_wanted(out);
     for (uint32_t k = 0; k < n_ctx; ++k) store_totals(out, bts[k], strata, k > 0);
     return AVK_OK;
 }
@@ -2160,7 +2280,7 @@ extern "C" int avk_compare_run_resident(avk_ctx *ctx, const avk_compare_cfg *cfg
     if (!cfg || !ctx->have_batch || ctx->n_inputs != 2) { ctx->err = "no resident compare batch"; return AVK_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     CompareRun R;
-    int rc = compare_launch(ctx, cfg, false, (cfg->flags & AVK_CMP_KEEP_REGION_ROWS) != 0, false, 0, R);
+    int rc = compare_launch(ctx, cfg, false, (cfg->flags & AVK_CMP_KEEP_REGION_ROWS) != 0, false, 0, false, false, R);
     if (rc != AVK_OK) return rc;
     rc = compare_finish(ctx, R, nullptr);
     if (rc != AVK_OK) return rc;

@@ -223,9 +223,10 @@ struct RegionSolver {
         const addr L_bucket = arena + off; off += (u32)align_up(4 * (n + 1), 16);
         const addr L_res_alle = arena + off; off += (u32)(rcap * npad);
         const addr L_res_num = arena + off; off += (u32)align_up(rcap * 24, 16);
-        const addr L_hap_alle = arena + off; off += (u32)npad;
-        const addr L_cur_obs = arena + off; off += (u32)(2 * npad);
-        const addr L_best_obs = arena + off; off += (u32)(2 * npad);
+        // (16 bytes between the arrays: the word-wise copies between them read up to 7 bytes past their source)
+        const addr L_hap_alle = arena + off; off += (u32)npad + 16;
+        const addr L_cur_obs = arena + off; off += (u32)(2 * npad) + 16;
+        const addr L_best_obs = arena + off; off += (u32)(2 * npad) + 16;
         const addr L_sdesc = arena + off; off += 3 * SD_SIZE;
         SOLVER_WRITE(Npad = npad;
                      seq_cap = align_up((max_end - start) + sum_l1 + 16, 16);   // materialised prefix: up to the last variant end + all ALTs
@@ -344,9 +345,10 @@ struct RegionSolver {
         const addr L_bucket = arena + off; off += (u32)align_up(4 * (n + 1), 16);
         const addr L_res_alle = arena + off; off += (u32)(rcap * npad);
         const addr L_res_num = arena + off; off += (u32)align_up(rcap * 24, 16);
-        const addr L_hap_alle = arena + off; off += (u32)npad;
-        const addr L_cur_obs = arena + off; off += (u32)(2 * npad);
-        const addr L_best_obs = arena + off; off += (u32)(2 * npad);
+        // (16 bytes between the arrays: the word-wise copies between them read up to 7 bytes past their source)
+        const addr L_hap_alle = arena + off; off += (u32)npad + 16;
+        const addr L_cur_obs = arena + off; off += (u32)(2 * npad) + 16;
+        const addr L_best_obs = arena + off; off += (u32)(2 * npad) + 16;
         const addr L_sdesc = arena + off; off += 3 * SD_SIZE;
         int ns = 0;
         addr L_mrows = 0, L_slot_tot = 0, L_slot_cnt = 0;

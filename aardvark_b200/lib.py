@@ -86,6 +86,7 @@ def load():
     lib.avk_compare_result_device.argtypes = [vp, C.POINTER(abi.CompareDevView)]
     lib.avk_last_tier_overflow.argtypes = [vp, C.POINTER(C.c_uint32)]
     lib.avk_last_tier_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.avk_set_stratifications.argtypes = [vp, C.POINTER(abi.StratIntervals)]
     lib.avk_compare_upload.argtypes = [vp, C.POINTER(abi.RegionBatch)]
     lib.avk_compare_run_resident.argtypes = [vp, C.POINTER(abi.CompareCfg)]
     lib.avk_compare_download.argtypes = [vp, C.POINTER(abi.CompareOut)]
@@ -101,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "avk_wfa_ed_batch", "avk_compare_seq_offsets", "avk_compare_upload", "avk_compare_run_resident",
     "avk_compare_download", "avk_build_regions", "avk_regions_download", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak", "avk_last_tier_overflow", "avk_last_tier_ms",
     "avk_compare_batch_range", "avk_compare_batch_multi", "avk_merge_batch_multi", "avk_partition_regions", "avk_compare_upload_range",
-    "avk_compare_result_device",
+    "avk_compare_result_device", "avk_set_stratifications",
 ]
 
 
@@ -165,6 +166,12 @@ class Solver:
         self._check(self._lib.avk_set_reference(self._ctx, len(arrs), ptrs, lens), "avk_set_reference")
         names = list(names) if names is not None else [str(i) for i in range(len(arrs))]
         self.contig_index = {n: i for i, n in enumerate(names)}
+
+    def set_stratifications(self, strat):
+        """strat: batch.StratIntervals.  Replaces Stratifications::from_tsv_batch (stratifications.rs:23-80): the interval
+        sets stay resident; CompareOutputs(containment=True / device_strata=True) use the device lookup."""
+        cs = strat.to_c()
+        self._check(self._lib.avk_set_stratifications(self._ctx, C.byref(cs)), "avk_set_stratifications")
 
     # -- batched operators --------------------------------------------------------------
     def compare_batch(self, batch: RegionBatch, cfg: CompareConfig = None, out: CompareOutputs = None, **out_kwargs):
@@ -325,6 +332,10 @@ class MultiSolver:
     def set_reference(self, contigs, names: Sequence[str] = None):
         for s in self.solvers:
             s.set_reference(contigs, names)
+
+    def set_stratifications(self, strat):
+        for s in self.solvers:
+            s.set_stratifications(strat)
 
     def compare_batch(self, batch: RegionBatch, cfg: CompareConfig = None, out: CompareOutputs = None, **out_kwargs):
         cfg = cfg or CompareConfig(enable_sequences=False)

@@ -213,6 +213,11 @@ typedef struct avk_compare_out {
     const uint64_t *seq_off;  /* [n_regions*5 + 1] */
     uint32_t *seq_len;        /* [n_regions*5] */
     uint8_t *seq_pool;
+    /* containment_regions (compare_benchmark.rs:28-30) by device lookup: bit s set <=> the region's var_coordinates()
+     * (compare_region.rs:63-74) lie inside one interval of stratum s (waffle_solver.rs:151-166).  Needs
+     * avk_set_stratifications.  May be NULL.  When strat_totals is set and strat_off is NULL, the stratified sums
+     * use this lookup instead of a caller-provided membership list. */
+    uint64_t *containment;    /* [n_regions] */
 } avk_compare_out;
 
 /* MergeBenchmark (src/data_types/merge_benchmark.rs:57-62) */
@@ -249,6 +254,20 @@ const char *avk_last_error(const avk_ctx *ctx);
  * stay resident in HBM for every later batch. */
 int avk_set_reference(avk_ctx *ctx, uint32_t n_contigs,
                       const uint8_t *const *seqs, const uint64_t *lens);
+
+/* Stratification BED sets.  Replaces Stratifications::from_tsv_batch + containments
+ * (src/parsing/stratifications.rs:23-80, 108-118, 197-210): the intervals of every (stratum, contig) -- 0-based
+ * INCLUSIVE [first, last], i.e. BED start and BED end - 1 (:158-163) -- stay resident on the device, sorted by first
+ * with a running maximum of last, so that "is [a, b] inside one interval" is one binary search per (region, stratum).
+ * Strata are numbered in the order given (the reference orders its labels alphabetically, :37,63). */
+typedef struct avk_strat_intervals {
+    uint32_t n_strata;      /* <= 64 */
+    uint32_t n_contigs;     /* contig numbering of avk_set_reference */
+    const uint64_t *off;    /* [n_strata * n_contigs + 1]: (stratum s, contig c) owns intervals [off[s*n_contigs+c], off[s*n_contigs+c+1]) */
+    const uint32_t *first;
+    const uint32_t *last;
+} avk_strat_intervals;
+int avk_set_stratifications(avk_ctx *ctx, const avk_strat_intervals *in);
 
 /* Replaces the par_iter over solve_compare_region (src/main.rs:251-268). */
 int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch,

@@ -1097,6 +1097,34 @@ int orc_compare_batch(const avk_region_batch *b, const uint8_t *const *contigs, 
     return AVK_OK;
 }
 
+// containment_regions of solve_compare_region (waffle_solver.rs:151-166): var_coordinates() (compare_region.rs:63-74) is
+// [min(first truth pos, first query pos), max(LAST truth variant's end, LAST query variant's end)) -- the end comes from
+// the last variant of each list, not from the furthest-reaching one -- queried 0-based inclusive as (start, end - 1);
+// a stratum contains it when one of its intervals on that contig has first <= start && last >= end - 1
+// (stratifications.rs:197-210; every interval is tested, like the COITree query callback).
+int orc_containments(const avk_region_batch *b, const avk_strat_intervals *st, uint64_t *mask) {
+    if (!b || !st || !mask || b->n_inputs != 2 || st->n_strata > 64) return AVK_ERR_INVALID;
+    const avk_variant_table &t = b->variants;
+    for (uint64_t r = 0; r < b->n_regions; ++r) {
+        mask[r] = 0;
+        const uint64_t t0 = b->var_off[r * 2], q0 = b->var_off[r * 2 + 1], q1 = b->var_off[r * 2 + 2];
+        uint64_t start = UINT64_MAX, end = 0;
+        if (q0 > t0) { start = std::min<uint64_t>(start, t.position[t0]); end = std::max<uint64_t>(end, (uint64_t)t.position[q0 - 1] + t.a0_len[q0 - 1]); }
+        if (q1 > q0) { start = std::min<uint64_t>(start, t.position[q0]); end = std::max<uint64_t>(end, (uint64_t)t.position[q1 - 1] + t.a0_len[q1 - 1]); }
+        if (!(start < end)) continue;                      // assert!(first < last) :158 would panic; no variants never occurs
+        const uint32_t c = b->contig[r];
+        if (c >= st->n_contigs) continue;
+        const int64_t first = (int64_t)start, last = (int64_t)end - 1;
+        for (uint32_t s = 0; s < st->n_strata; ++s) {
+            bool included = false;
+            for (uint64_t i = st->off[(uint64_t)s * st->n_contigs + c]; i < st->off[(uint64_t)s * st->n_contigs + c + 1]; ++i)
+                if ((int64_t)st->first[i] <= first && (int64_t)st->last[i] >= last) included = true;
+            if (included) mask[r] |= 1ull << s;
+        }
+    }
+    return AVK_OK;
+}
+
 int orc_merge_batch(const avk_region_batch *b, const uint8_t *const *contigs, const uint64_t *contig_lens,
                     uint32_t n_contigs, const avk_merge_cfg *cfg, avk_merge_out *out, int n_threads,
                     avk_work_counters *work) {

@@ -267,6 +267,18 @@ def variant_delta_length(batch: RegionBatch, k=0):
     return int(lib().orc_variant_delta_length(C.byref(cb), k))
 
 
+def containments(batch: RegionBatch, strat) -> np.ndarray:
+    """Stratifications::containments of every region's var_coordinates() (orc_containments); strat: batch.StratIntervals."""
+    mask = np.zeros(max(batch.n_regions, 1), dtype=np.uint64)
+    cb, cs = batch.to_c(), strat.to_c()
+    f = lib().orc_containments
+    f.argtypes = [C.POINTER(abi.RegionBatch), C.POINTER(abi.StratIntervals), C.POINTER(C.c_uint64)]
+    rc = f(C.byref(cb), C.byref(cs), abi.ptr(mask))
+    if rc != 0:
+        raise RuntimeError(f"orc_containments failed: {rc}")
+    return mask[:batch.n_regions]
+
+
 def num_threads():
     return int(lib().orc_num_threads())
 

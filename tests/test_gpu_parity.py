@@ -569,3 +569,36 @@ def test_pipelined_single_gpu_call_vs_unpipelined(solver):
         assert s.compare_batch(batch, cs, seq_off=off, seq_pool_len=plen).diff(solver.compare_batch(batch, cs, seq_off=off, seq_pool_len=plen)) == []
     finally:
         s.close()
+
+
+def test_config0_golden_clusters_with_stratification(solver):
+    """BASELINE configs[0] (the bundle does not exist: SURVEY 8d substitutes the unit-test clusters on contigs `mock` /
+    `mock2` with test_data/example_stratification): the golden clusters, shifted onto both contigs, are solved with the
+    DEVICE containment lookup (avk_set_stratifications); containment masks and stratified sums against the oracle's
+    restatement of Stratifications::containments + var_coordinates()."""
+    from aardvark_b200.batch import StratIntervals, masks_to_membership
+    from aardvark_b200.types import Coordinates
+    from test_strat import EXAMPLE1, EXAMPLE2
+    mock = MOCK_CHR1 * 2                      # 50 bp: the golden clusters live in [0, 25), a second copy in [25, 50)
+    regions = []
+    for ci, chrom in enumerate(("mock", "mock2")):
+        for shift in (0, 25):
+            for (_, r, _) in COMPARE_CASES:
+                sh = lambda vs: [type(v)(v.vcf_index, v.variant_type, v.position + shift, v.allele0, v.allele1) for v in vs]
+                regions.append(CompareRegion(len(regions), Coordinates(chrom, r.coordinates.start + shift, r.coordinates.end + shift),
+                                             sh(r.truth_variants), r.truth_zygosity, sh(r.query_variants), r.query_zygosity))
+    batch = RegionBatch.from_compare_regions(regions, {"mock": 0, "mock2": 1})
+    strat = StratIntervals([EXAMPLE1, EXAMPLE2], n_contigs=2)
+    solver.set_reference([mock, mock], ["mock", "mock2"])
+    solver.set_stratifications(strat)
+    cfg = CompareConfig(enable_sequences=False)
+    gpu = solver.compare_batch(batch, cfg, n_strata=2, device_strata=True, containment=True)
+    masks = orc.containments(batch, strat)
+    assert np.array_equal(gpu.containment[:batch.n_regions], masks)
+    assert len(set(masks.tolist())) >= 3                      # regions inside neither, one and both strata
+    so, si = masks_to_membership(masks)
+    cpu = orc.compare_batch(batch, [mock, mock], compare_cfg(cfg), strat_off=so, strat_idx=si, n_strata=2)
+    assert gpu.diff(cpu) == []
+    assert int(gpu.solved_blocks[0]) == batch.n_regions
+    # the caller-provided membership list gives the same stratified sums
+    assert solver.compare_batch(batch, cfg, strat_off=so, strat_idx=si, n_strata=2).diff(cpu) == []

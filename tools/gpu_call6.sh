@@ -1,0 +1,13 @@
+#!/bin/bash
+# GPU call 6: shape-sorted work list for the thread stage, device strata lookup, racecheck after padding
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > gpurun_out/c6_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/c6_pytest.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/c6_bench_wgs.json 2> gpurun_out/c6_bench_wgs.err
+echo "bench rc=$?" >> gpurun_out/c6_bench_wgs.err
+AVK_NO_SHAPE_SORT=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/c6_bench_wgs_nosort.json 2> gpurun_out/c6_bench_wgs_nosort.err
+timeout 300 python bench.py --config chr20 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/c6_bench_chr20.json 2> gpurun_out/c6_bench_chr20.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/c6_launches_wgs.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/c6_bench_under_ncu.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_compare_thread -c 1 -s 3 -o gpurun_out/c6_thread_full python bench.py --config wgs --scale 0.25 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/c6_ncu_full.log 2>&1
+timeout 900 compute-sanitizer --tool racecheck --kernel-name kns=k_compare_team python tools/sanitize_driver.py > gpurun_out/c6_racecheck_team.log 2>&1
+tail -5 gpurun_out/c6_pytest.log; cut -c1-300 gpurun_out/c6_bench_wgs.json; tail -3 gpurun_out/c6_bench_wgs.err; tail -3 gpurun_out/c6_racecheck_team.log
