@@ -203,11 +203,13 @@ __global__ void __launch_bounds__(256) k_prep_size(DevBatch b, u64 n, u64 *sizes
     sizes[r] = (PH_SIZE + VI_SIZE * (v1 - v0) + alle + 16 + 15) & ~15ull;
 }
 
-__global__ void __launch_bounds__(256) k_prep_fill(DevBatch b, u64 n, const u64 *offs, u8 *digest) {
+__global__ void __launch_bounds__(256) k_prep_fill(DevBatch b, u64 n_all, const u64 *offs, u8 *digest, const u32 *list, const u32 *n_list) {
     const int lane = lane_id();
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
-    for (u64 r = warp; r < n; r += n_warps) {
+    const u64 n = list ? (u64)*n_list : n_all;
+    for (u64 ri = warp; ri < n; ri += n_warps) {
+        const u64 r = list ? (u64)list[ri] : ri;
         u8 *dig = digest + offs[r];
         int *hdr = (int *)dig;
         const long long start = b.start[r], end = b.end[r];
@@ -288,6 +290,62 @@ __global__ void __launch_bounds__(256) k_prep_fill(DevBatch b, u64 n, const u64 
             for (int t = 0; t < AVK_N_VARIANT_TYPES; ++t) if (seen & (1u << t)) dig[PH_SLOT_TYPE + (k++)] = (u8)t;
         }
     }
+}
+
+// k_prep_fill for the common small cluster, one THREAD per cluster (a warp per two-variant cluster leaves 30 lanes idle and
+// serialises on its shuffles): same digest, byte for byte.  Clusters with more than PREP_SMALL_N variants are appended to
+// `big` and take the warp kernel.
+enum { PREP_SMALL_N = 12 };
+__global__ void __launch_bounds__(256) k_prep_fill_small(DevBatch b, u64 n, const u64 *offs, u8 *digest, u32 *big, u32 *big_ctr) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const u64 v0 = b.var_off[r * 2], vq = b.var_off[r * 2 + 1], v1 = b.var_off[r * 2 + 2];
+    const int nT = (int)(vq - v0), nQ = (int)(v1 - vq), N = nT + nQ;
+    if (N > PREP_SMALL_N) { big[atomicAdd(big_ctr, 1u)] = (u32)r; return; }
+    u8 *dig = digest + offs[r];
+    int *hdr = (int *)dig;
+    const long long start = b.start[r], end = b.end[r];
+    bool invalid = false;
+    int s_l1 = 0, s_b0 = 0, s_al = 0, mx = (int)min(start, 0x7fffffffLL);
+    u32 seen = 0;
+    for (u64 gv = v0; gv < v1; ++gv) {
+        const u32 l0 = b.l0[gv], l1 = b.l1[gv], p = b.pos[gv], ty = b.vtype[gv];
+        invalid = invalid || l0 == 0 || l1 == 0 || ty >= AVK_N_VARIANT_TYPES || b.zyg[gv] > AVK_ZYG_HOM_ALT;
+        invalid = invalid || (long long)p < start || (long long)p + l0 > end;
+        if (gv != v0 && gv != vq) invalid = invalid || b.pos[gv - 1] > p;
+        s_l1 += (int)min(l1, 1u << 24); s_b0 += (int)min(max(l0, l1), 1u << 24); s_al += (int)min(l0, 1u << 24) + (int)min(l1, 1u << 24);
+        mx = max(mx, (int)min(p + l0, 0x7fffffffu));
+        seen |= 1u << (ty & 31u);
+    }
+    uint4 *h4 = (uint4 *)dig;
+    if (invalid) {
+        h4[0] = make_uint4((u32)AVK_ST_BAD_INPUT, 0, 0, 0); h4[1] = make_uint4(0, 0, 0, 0); h4[2] = make_uint4(0, 0, 0, 0); h4[3] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    // merged order: stable, truth before query on equal positions (order_variants, query_optimizer.rs:372-381)
+    u8 *recs = dig + PH_SIZE, *alle = recs + (size_t)VI_SIZE * N;
+    u64 it = v0, iq = vq;
+    u32 acc = 0;
+    for (int oi = 0; oi < N; ++oi) {
+        const bool take_t = it < vq && (iq >= v1 || b.pos[it] <= b.pos[iq]);
+        const u64 gv = take_t ? it : iq;
+        if (take_t) ++it; else ++iq;
+        const u32 l0 = b.l0[gv], l1 = b.l1[gv], ty = b.vtype[gv];
+        uint4 *rec = (uint4 *)(recs + (size_t)VI_SIZE * oi);
+        rec[0] = make_uint4(b.pos[gv], l0, l1, acc);
+        rec[1] = make_uint4(b.alt_ed[gv], b.raw[gv], (u32)gv,
+                            ty | ((u32)b.zyg[gv] << 8) | ((take_t ? 1u : 0u) << 16) | ((u32)__popc(seen & ((1u << ty) - 1)) << 24));
+        const u8 *src = b.pool + b.aoff[gv];
+        for (u32 k = 0; k < l0 + l1; ++k) alle[acc + k] = src[k];
+        acc += l0 + l1;
+    }
+    h4[0] = make_uint4((u32)AVK_ST_OK, (u32)N, (u32)nT, (u32)nQ);
+    h4[1] = make_uint4((u32)s_l1, (u32)s_b0, (u32)s_al, (u32)mx);
+    u32 st[4] = {0, 0, 0, 0};
+    int k = 0;
+    for (int ty = 0; ty < AVK_N_VARIANT_TYPES; ++ty) if (seen & (1u << ty)) { st[k >> 2] |= (u32)ty << (8 * (k & 3)); ++k; }
+    h4[2] = make_uint4((u32)__popc(seen), st[0], st[1], st[2]);
+    h4[3] = make_uint4(0, 0, 0, 0);
 }
 
 __device__ __forceinline__ void zero_region_outputs(const DevBatch &b, const DevCompareOut &out, u64 r, bool metrics_only) {
@@ -396,7 +454,13 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
                 // Clusters of the same shape run (nearly) the same control flow in the thread-per-cluster stage; the list is
                 // sorted by this key so that the 32 lanes of a warp get clusters of one shape.
                 u64 key = 0;
-                if (nvar > 0 && nvar <= 10) {
+                const int *dh = (const int *)(b.digest + b.digest_off[r]);
+                // heaviest first (a thread is a slow serial machine: what takes thousands of wavefront steps must not start
+                // last): weight ~ variants x (edit-distance bound + 1)^2, in powers of two
+                const u32 edb = (u32)min(max(dh[PH_B0 / 4], 0), 16);
+                const u32 wgt = (u32)max(nvar, 1) * (edb + 1u) * (edb + 1u);
+                const u32 heavy = min(15u, (u32)(31 - __clz((int)max(wgt, 1u))));
+                if (nvar > 0 && nvar <= 9) {
                     const u8 *recs = b.digest + b.digest_off[r] + PH_SIZE;
                     u32 prev = 0xffffffffu;
                     for (int oi = 0; oi < nvar; ++oi) {
@@ -407,8 +471,9 @@ __global__ void __launch_bounds__(256) k_compare_simple(DevBatch b, DevCompareOu
                         key = (key << 6) | code;
                         prev = a.x;
                     }
-                    key |= (u64)nvar << 60;
-                } else key = (u64)min(nvar, 15) << 60;
+                    key |= (u64)nvar << 54;
+                } else key = (u64)min(nvar, 15) << 54;
+                key |= (u64)(15u - heavy) << 58;
                 work_key[slot_] = key;
             }
         }
@@ -1083,6 +1148,8 @@ struct avk_ctx {
     int wide_b0 = 256;
     bool use_thread_stage = true;   // AVK_NO_THREAD_STAGE=1: warp kernels only (A/B timing, tests of the warp path)
     bool sort_shapes = true;        // AVK_NO_SHAPE_SORT=1: the thread stage takes its clusters in list order
+    u64 thread_min_regions = 400000; // smaller batches go to the warp kernels directly: with at most a cluster or two per thread the
+                                     // thread stage is bound by its slowest cluster, not by throughput (AVK_THREAD_MIN_REGIONS)
     // Pipelined single-GPU call: sibling contexts on the same device (own stream and buffers, the owner's reference) solve
     // alternating bins so that one bin's upload, another's kernels and a third's download overlap.
     avk_ctx *ref_owner = nullptr;   // set in a sibling: whose reference it reads
@@ -1177,6 +1244,7 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (const char *s = getenv("AVK_TEST_WIDE_B0")) ctx->wide_b0 = std::max(1, atoi(s));
     if (const char *s = getenv("AVK_NO_THREAD_STAGE")) ctx->use_thread_stage = atoi(s) == 0;
     if (const char *s = getenv("AVK_NO_SHAPE_SORT")) ctx->sort_shapes = atoi(s) == 0;
+    if (const char *s = getenv("AVK_THREAD_MIN_REGIONS")) ctx->thread_min_regions = (u64)std::max(0LL, atoll(s));
     if (const char *s = getenv("AVK_PIPELINE_BINS")) ctx->pipe_bins = std::max(0, atoi(s));
     if (const char *s = getenv("AVK_PIPELINE_MIN_REGIONS")) ctx->pipe_min_regions = (u64)std::max(1LL, atoll(s));
     for (auto &e : ctx->tev) cudaEventCreate(&e);
@@ -1536,8 +1604,14 @@ static int run_prepare(avk_ctx *ctx, const DevBatch &db) {
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sizes, offs, (int)(n + 1), ctx->stream);
     ENSURE(ctx->scan_tmp, tmp_bytes);
     cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, sizes, offs, (int)(n + 1), ctx->stream);
-    k_prep_fill<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db, n, offs, (u8 *)ctx->digest.p);
-    ctx->launches += 3;
+    // small clusters: one thread each; the few large ones (list in fail_a, count in counters[40]) one warp each
+    ENSURE(ctx->fail_a, 4 * n);
+    ENSURE(ctx->counters, 256);
+    u32 *big_ctr = (u32 *)ctx->counters.p + 40;
+    CK(cudaMemsetAsync(big_ctr, 0, 4, ctx->stream));
+    k_prep_fill_small<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(db, n, offs, (u8 *)ctx->digest.p, (u32 *)ctx->fail_a.p, big_ctr);
+    k_prep_fill<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(db, n, offs, (u8 *)ctx->digest.p, (const u32 *)ctx->fail_a.p, big_ctr);
+    ctx->launches += 4;
     CK(cudaGetLastError());
     return AVK_OK;
 }
@@ -1606,7 +1680,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p, *LX = (u32 *)ctx->fail_x.p;
     // closed-form clusters; >= dense_n variants -> X (dense); the rest -> W
     u64 *keys = nullptr;
-    if (ctx->use_thread_stage && ctx->sort_shapes) {
+    if (ctx->use_thread_stage && n >= ctx->thread_min_regions && ctx->sort_shapes) {
         ENSURE(ctx->shape_key, 16 * n);                               // keys in / out
         ENSURE(ctx->fail_s, 4 * n);
         keys = (u64 *)ctx->shape_key.p;
@@ -1637,7 +1711,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     const int small_ctas = (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8);
     const u32 *LS = LW;          // what the warp search / score kernels consume
     int ls_ctr = 12;
-    if (ctx->use_thread_stage) {                                                             // W -> solved by one thread each; rejects -> W2
+    if (ctx->use_thread_stage && n >= ctx->thread_min_regions) {                             // W -> solved by one thread each; rejects -> W2
         u32 *LW2 = (u32 *)ctx->fail_t.p;
         TierArgs a = tier_args(ctx, keys ? (const u32 *)ctx->fail_s.p : LW, 12, 19, LW2, 13, sizeof(avk_ts::Work), nullptr);
         k_compare_thread<<<(unsigned)std::min<u64>((u64)sm, (n + THREAD_TPB - 1) / THREAD_TPB), THREAD_TPB, THREAD_TPB * sizeof(avk_ts::Work), ctx->side[0]>>>(R.db, R.out, R.cfg, a);

@@ -602,3 +602,40 @@ def test_config0_golden_clusters_with_stratification(solver):
     assert int(gpu.solved_blocks[0]) == batch.n_regions
     # the caller-provided membership list gives the same stratified sums
     assert solver.compare_batch(batch, cfg, strat_off=so, strat_idx=si, n_strata=2).diff(cpu) == []
+
+
+def test_cpp_abi_harness():
+    """A C++ program (tests/abi_harness.cpp) calls the C ABI directly -- the reference's run_compare around one batched call
+    (src/main.rs:217-279) -- and prints what the reference's first solve_compare_region test asserts (waffle_solver.rs:897-930)
+    plus a false negative."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = os.path.join(HERE, "_build", "abi_harness")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    libdir = os.path.join(root, "aardvark_b200", "csrc")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-o", exe, os.path.join(HERE, "abi_harness.cpp"),
+                           "-L" + libdir, "-laardvark_b200", "-Wl,-rpath," + libdir])
+    txt = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert txt[0] == "status 0 0 ed 0 0 1 1 solved 2 errors 0"
+    assert txt[1] == "variants 1/1/1 1/1/1 2/0/2"                    # TP, TP, FN (expected 2, observed 0)
+    assert txt[2] == "joint GT tp 1 fn 1 qtp 1 qfp 0 BASEPAIR tp 2 fn 4 qtp 2 qfp 0"
+
+
+def test_warp_only_pipeline_vs_oracle():
+    """The pipeline without the thread-per-cluster stage (what small batches get by default): warp search / score / fused /
+    team kernels only."""
+    s = _solver_with_env(AVK_NO_THREAD_STAGE=1)
+    try:
+        for seed in (24, 25):
+            ref, batch = synth.workload_chr20(scale=0.02, seed=seed)
+            s.set_reference([ref])
+            cfg = CompareConfig(enable_sequences=False)
+            gpu = s.compare_batch(batch, cfg)
+            cpu = orc.compare_batch(batch, [ref], compare_cfg(cfg))
+            assert gpu.diff(cpu) == []
+        p = synth.SynthParams(n_variants=2000, dense_frac=0.9, dense_mean=6.0, het_frac=0.95, phased_frac=0.2, p_repr=0.05, p_gt_err=0.05, p_fn=0.05, p_fp=0.05)
+        ref, batch = synth.workload_compare(40_000, p, seed=12)
+        s.set_reference([ref])
+        assert s.compare_batch(batch, CompareConfig(enable_sequences=False)).diff(orc.compare_batch(batch, [ref], compare_cfg(CompareConfig(enable_sequences=False)))) == []
+    finally:
+        s.close()
