@@ -80,6 +80,7 @@ class CompareCfg(C.Structure):
         ("enable_exact_shortcut", C.c_uint32),
         ("enable_sequences", C.c_uint32),
         ("flags", C.c_uint32),
+        ("exact_gt_max_expansions", C.c_uint32),
     ]
 
 

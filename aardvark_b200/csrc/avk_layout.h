@@ -6,8 +6,10 @@
 
 #if defined(__CUDACC__)
 #define AVK_HD __host__ __device__
+#define AVK_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define AVK_HD
+#define AVK_HD_NOINLINE
 #endif
 
 namespace avk {

@@ -303,7 +303,6 @@ __global__ void __launch_bounds__(256) k_prep_fill_small(DevBatch b, u64 n, cons
     const int nT = (int)(vq - v0), nQ = (int)(v1 - vq), N = nT + nQ;
     if (N > PREP_SMALL_N) { big[atomicAdd(big_ctr, 1u)] = (u32)r; return; }
     u8 *dig = digest + offs[r];
-    int *hdr = (int *)dig;
     const long long start = b.start[r], end = b.end[r];
     bool invalid = false;
     int s_l1 = 0, s_b0 = 0, s_al = 0, mx = (int)min(start, 0x7fffffffLL);
@@ -809,7 +808,7 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
 // execute their task side by side; lanes whose cluster is finished commit it and take the next one from the list W (one
 // atomic per warp and round).  A cluster that does not fit the fixed workspace is appended to the reject list -- nothing
 // has been written for it -- and goes through the warp kernels (search / score / fused stages) as before.
-enum { THREAD_TPB = 256, TS_BATCH_MIN = 8 };
+enum { THREAD_TPB = 256, TS_BATCH_MIN = 24 };
 struct ThreadSink {
     const avk_ts::Cluster &cl;
     const DevCompareOut &out;
@@ -898,7 +897,7 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
                             else if (c >= b.n_contigs || b.start[r] > b.end[r] || (u64)b.end[r] > b.contig_len[c] || b.end[r] > 0x7fff0000u ||
                                      (int)cfg.max_branch_factor <= 0)
                                 S.stop(AVK_ST_BAD_INPUT);
-                            else S.begin(b.digest + b.digest_off[r], b.contig_ptr[c], (int)b.start[r], (int)b.end[r], (int)cfg.max_branch_factor);
+                            else S.begin(b.digest + b.digest_off[r], b.contig_ptr[c], (int)b.start[r], (int)b.end[r], (int)cfg.max_branch_factor, cfg.exact_gt_max_expansions);
                         }
                     }
                 } else if (want) S.phase = PH_DONE;

@@ -923,7 +923,8 @@ struct RegionSolver {
     // `budget`: the caller only cares about results with fewer than `budget` errors.  Nodes are popped in
     // non-decreasing error order, so the search stops at the first popped node that reaches the budget and reports
     // *errors_out = budget ("at least").
-    __device__ __noinline__ int exact_gt(addr obs, int *errors_out, int budget) {
+    __device__ __noinline__ int exact_gt(addr obs, int *errors_out, int budget, u32 max_expansions) {
+        u32 expansions = 0;
         const int lane = lane_id();
         const int n = N;
         if (n >= 0xffff) return SOLVE_WORKSPACE;
@@ -951,6 +952,7 @@ struct RegionSolver {
             const int errors = LDI(nb + XN_ERR);
             if (errors >= budget && !have_best) { *errors_out = budget; return SOLVE_OK; }
             if (errors >= best_err) { free_slot(s); continue; }                // :169 non-strict
+            if (++expansions > max_expansions) return AVK_ST_TIMEOUT;          // stand-in for the 300 s bail (:174-176)
             const int oi = LDI(nb + XN_DEPTH);
             if (oi == n) {                                                     // :180-192
                 const int exact = ex_extend(nb, oi, false, false, true);
@@ -1318,7 +1320,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
                     __syncwarp();
                 } else {
                     const int budget = best_total - total - ((h == 0 && !zero1) ? 1 : 0);
-                    rc = exact_gt(cur_obs + (u32)(h * npad), &errs, budget);
+                    rc = exact_gt(cur_obs + (u32)(h * npad), &errs, budget, cfg.exact_gt_max_expansions ? cfg.exact_gt_max_expansions : AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS);
                     if (rc) return rc;
                     lost = errs >= budget;
                 }

@@ -92,6 +92,7 @@ struct Cluster {
     const u8 *recs;    // N VI_* records in merged order (digest)
     const u8 *alle;    // allele bytes of the digest
     int wlen, N, nT, nQ, mbf, n_slots;   // wlen = window length (end - start)
+    u32 xcap;          // optimize_gt_alleles: node expansions allowed per call (AVK_ST_TIMEOUT beyond)
     u32 slot_types;    // 4 bits per slot: variant type of metric-row slot k
 };
 
@@ -154,7 +155,7 @@ struct Solver {
     // optimize_gt_alleles
     int xn, best_err, min_sync, af_index, af_counts, x_errors, x_d0;
     bool have_best, x_is_alt, x_do_alt;
-    u32 x_next_id, hap_alt, x_keep, x_ekeep, x_id0, x_id1;
+    u32 x_next_id, hap_alt, x_keep, x_ekeep, x_id0, x_id1, x_expansions;
     // final scoring
     u32 f_X, f_Y, f_tp, f_Ef, f_failT, f_failQ, f_failF, f_other;
     int f_altT, f_altQ, f_side, f_alt_other;
@@ -173,27 +174,34 @@ struct Solver {
     AVK_HD static Spec spec(int side, u32 mask, int depth, bool to_end) { Spec s; s.side = (u8)side; s.depth = (u8)depth; s.to_end = to_end ? 1 : 0; s.pad = 0; s.mask = (u16)mask; return s; }
 
     // HaplotypeTracker replay (haplotype_dwfa.rs:175-227); positions relative to the region start.
-    // returns false when the sequence has more than TS_MAXALT spliced ALTs.
-    template <bool PIECES>
-    AVK_HD bool replay(PSeq *ps, SeqInfo &s, const Spec sp) const {
+    // returns false when the sequence has more than TS_MAXALT spliced ALTs.  (One out-of-line copy: it is called from a dozen
+    // places of the coroutine and must not drag the solver's registers into local memory, hence static with explicit arguments.)
+    static AVK_HD_NOINLINE bool replay_impl(const Work *wp_, int wlen, int N, PSeq *ps, SeqInfo *out, const Spec sp) {
+#if defined(__CUDA_ARCH__)
+        const Work &W = ((const Work *)avk_dyn_smem)[threadIdx.x];
+        (void)wp_;
+#else
+        const Work &W = *wp_;
+#endif
         int cur = 0, ref_pos = 0, len = 0, m = 0, skip = 0, last_ok = 1, plen = 0, prp = 0;
-        const Work &W = w();
-        if (PIECES) { ps->ls[0] = 0; ps->src[0] = 0; }
+        const bool pieces = ps != nullptr;
+        if (pieces) { ps->ls[0] = 0; ps->src[0] = 0; }
         if (sp.side < 2) {
             const bool want_truth = sp.side == 0;
             const int depth = sp.depth;
+            const u32 tmask = W.truth_mask;
             for (int i = 0; i < depth; ++i) {
                 if (i == depth - 1) { plen = len + (ref_pos - cur); prp = ref_pos; }
-                if (is_truth(i) == want_truth && ((sp.mask >> i) & 1)) {
+                if ((((tmask >> i) & 1u) != 0) == want_truth && ((sp.mask >> i) & 1)) {
                     const VarInfo v = W.var[i];
                     const int vpos = v.pos;
                     if (ref_pos <= vpos) {                        // compatible (:189)
                         if (m >= TS_MAXALT) return false;
                         len += vpos - cur;
-                        if (PIECES) { ps->ls[2 * m + 1] = (u16)len; ps->src[2 * m + 1] = (u16)(v.aoff + v.l0); }
+                        if (pieces) { ps->ls[2 * m + 1] = (u16)len; ps->src[2 * m + 1] = (u16)(v.aoff + v.l0); }
                         len += v.l1;
                         cur = vpos + v.l0;
-                        if (PIECES) { ps->ls[2 * m + 2] = (u16)len; ps->src[2 * m + 2] = (u16)cur; }
+                        if (pieces) { ps->ls[2 * m + 2] = (u16)len; ps->src[2 * m + 2] = (u16)cur; }
                         m += 1;
                         ref_pos = cur;
                     } else {
@@ -201,16 +209,18 @@ struct Solver {
                         if (i == depth - 1) last_ok = 0;
                     }
                 }
-                const int sy = sync_pos(i);
+                const int sy = (i == N - 1) ? wlen : (int)W.var[i + 1].pos;   // query_optimizer.rs:258-265
                 if (ref_pos < sy) ref_pos = sy;
             }
         }
-        if ((sp.to_end || sp.side >= 2) && ref_pos < c.wlen) ref_pos = c.wlen;
+        if ((sp.to_end || sp.side >= 2) && ref_pos < wlen) ref_pos = wlen;
         len += ref_pos - cur;
-        if (PIECES) ps->ls[2 * m + 1] = (u16)len;
-        s.len = len; s.ref_pos = ref_pos; s.skip = skip; s.n_alt = m; s.last_ok = last_ok; s.plen = plen; s.prp = prp;
+        if (pieces) ps->ls[2 * m + 1] = (u16)len;
+        out->len = len; out->ref_pos = ref_pos; out->skip = skip; out->n_alt = m; out->last_ok = last_ok; out->plen = plen; out->prp = prp;
         return true;
     }
+    template <bool PIECES>
+    AVK_HD bool replay(PSeq *ps, SeqInfo &s, const Spec sp) const { return replay_impl(wp, c.wlen, c.N, PIECES ? ps : nullptr, &s, sp); }
 
     AVK_HD const u8 *piece_ptr(const PSeq &s, int pk, int x) const { return ((pk & 1) ? c.alle : c.ref) + s.src[pk] + (x - s.ls[pk]); }
 
@@ -243,7 +253,12 @@ struct Solver {
     AVK_HD void task_setup() {
         Work &W = w();
         Task &t = task;
-        t.ok = replay<true>(&W.seq[0], t.ia, t.a) && replay<true>(&W.seq[1], t.ib, t.b);
+        {   // (out-of-line call: its outputs go through locals so that the solver itself can stay in registers)
+            SeqInfo ia, ib;
+            const Spec sa = t.a, sb = t.b;
+            t.ok = replay<true>(&W.seq[0], ia, sa) && replay<true>(&W.seq[1], ib, sb);
+            t.ia = ia; t.ib = ib;
+        }
         if (!t.ok) { t.kind = TK_NONE; return; }
         if (t.kind == TK_PREFIX) return;
         u16 *wf = W.wf[t.buf];
@@ -315,7 +330,7 @@ struct Solver {
 
     // ================================================================== begin: load the cluster
     // leaves phase = PH_RUN with the workspace loaded, or PH_COMMIT with rc = an error status / TS_REJECT
-    AVK_HD void begin(const u8 *digest, const u8 *contig, int start, int end, int mbf) {
+    AVK_HD void begin(const u8 *digest, const u8 *contig, int start, int end, int mbf, u32 xcap) {
         const int *hdr = (const int *)digest;
         task.kind = TK_NONE;
         phase = PH_COMMIT;
@@ -329,6 +344,7 @@ struct Solver {
         const int ns = hdr[PH_NSLOTS / 4];
         if (ns > TS_MAXSLOT) return;
         c.ref = contig + start; c.recs = digest + PH_SIZE; c.alle = c.recs + (size_t)VI_SIZE * n;
+        c.xcap = xcap ? xcap : AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS;
         c.wlen = end - start; c.N = n; c.nT = hdr[PH_N0 / 4]; c.nQ = hdr[PH_N1 / 4]; c.mbf = mbf; c.n_slots = ns;
         c.slot_types = 0;
         for (int s = 0; s < ns; ++s) c.slot_types |= (u32)digest[PH_SLOT_TYPE + s] << (4 * s);
@@ -516,7 +532,7 @@ struct Solver {
                     // optimize_gt_alleles (exact_gt_optimizer.rs:108-357) on this haplotype
                     hap_alt = ha; x_keep = 0;
                     x_next_id = 1; best_err = 0x7fffffff; have_best = false;
-                    min_sync = 0; af_index = 0; af_counts = 0;
+                    min_sync = 0; af_index = 0; af_counts = 0; x_expansions = 0;
                     xn = 0;
                     { XEnt e; e.key = (31u << 22); e.keep = 0; e.depth = 0; e.pad = 0; W.x[xn++] = e; }
                     pc = PC_X_POP;
@@ -542,6 +558,7 @@ struct Solver {
                     x_errors = (int)(e.key >> 27);
                     if (x_errors >= budget && !have_best) errs = budget;         // nodes pop in non-decreasing error order
                     else if (x_errors >= best_err) break;                        // :169 non-strict
+                    else if (++x_expansions > c.xcap) { stop(AVK_ST_TIMEOUT); return; }   // stand-in for the 300 s bail (:174-176)
                     else {
                         oi = e.depth; x_ekeep = e.keep; x_id0 = e.key & 0x3fffffu;
                         if (oi == n) {                                           // :180-192: finalize; exact <=> sequences equal

@@ -107,7 +107,8 @@ EXPORTED_SYMBOLS = [
 
 
 def compare_cfg(cfg: CompareConfig, flags: int = 0) -> abi.CompareCfg:
-    return abi.CompareCfg(cfg.max_branch_factor, int(cfg.enable_exact_shortcut), int(cfg.enable_sequences), flags)
+    return abi.CompareCfg(cfg.max_branch_factor, int(cfg.enable_exact_shortcut), int(cfg.enable_sequences), flags,
+                          int(getattr(cfg, "exact_gt_max_expansions", 0)))
 
 
 def partition_regions(batch: RegionBatch, n_bins: int):

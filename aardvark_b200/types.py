@@ -197,6 +197,9 @@ class CompareConfig:
     enable_sequences: bool = True
     enable_exact_shortcut: bool = False
     max_branch_factor: int = 50
+    # not in the reference: node expansions one optimize_gt_alleles call may use before the region ends with the stand-in for
+    # the reference's 300 s bail-out (0 = the library default, 2^24)
+    exact_gt_max_expansions: int = 0
 
 
 @dataclass
@@ -381,7 +384,8 @@ class RegionError(RuntimeError):
 
     def __init__(self, region_id, status):
         names = ["ok", "unsupported zygosity", "no result found", "truth false positive",
-                 "TP is less than basepair TP", "malformed region", "workspace exhausted"]
+                 "TP is less than basepair TP", "malformed region", "workspace exhausted",
+                 "exact-GT expansion limit reached (stands for the reference's 300 second time limit)"]
         super().__init__(f"region {region_id}: {names[status] if status < len(names) else status}")
         self.region_id = region_id
         self.status = status

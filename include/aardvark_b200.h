@@ -164,7 +164,14 @@ typedef struct avk_compare_cfg {
     uint32_t enable_exact_shortcut;  /* default 0 */
     uint32_t enable_sequences;       /* fill the sequence bundle outputs */
     uint32_t flags;                  /* AVK_CMP_* (GPU library only; 0 = defaults) */
+    /* Deterministic stand-in for the reference's 300 s wall-clock bail-out of optimize_gt_alleles
+     * (exact_gt_optimizer.rs:165,174-176): one call may expand at most this many queue nodes (nodes that pass the
+     * `errors >= best` skip, where the reference looks at its clock), else the region ends with AVK_ST_TIMEOUT.
+     * 0 = AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS.  The auto-fail heuristic (:160,309-339) bounds sane inputs far below it:
+     * it never fires on the five BASELINE configs. */
+    uint32_t exact_gt_max_expansions;
 } avk_compare_cfg;
+#define AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS (1u << 24)
 /* avk_compare_run_resident: keep the per-region GroupTypeMetrics rows (2288 B per region) on the device so that
  * avk_compare_download can return out->region_metrics.  avk_compare_batch* decide from out->region_metrics != NULL. */
 #define AVK_CMP_KEEP_REGION_ROWS 1u

@@ -435,7 +435,8 @@ struct ExactNode {                    // ExactMatchNode :361-368, DWFA max ED 0 
 static int optimize_gt_alleles(const uint8_t *ref, size_t start, size_t end,
                                const std::vector<Var> &tv, const std::vector<uint8_t> &ta,
                                const std::vector<Var> &qv, const std::vector<uint8_t> &qa,
-                               OptAlleles &out) {
+                               OptAlleles &out, uint64_t max_expansions = AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS) {
+    uint64_t expansions = 0;
     std::vector<OrderEnt> order = order_variants(tv, qv);
     const size_t N = order.size();
 
@@ -471,7 +472,9 @@ static int optimize_gt_alleles(const uint8_t *ref, size_t start, size_t end,
         std::unique_ptr<ExactNode> cur = std::move(pool[top.slot]);
         if (tl_work) tl_work->exact_pops += 1;
         if (cur->errors >= best_err) continue;                    // :169 (non-strict)
-        // (300 s wall-clock bail :174-176 is not reproduced: it is non-deterministic)
+        // the 300 s wall-clock bail (:174-176) is non-deterministic; its stand-in is a cap on the nodes expanded by one call,
+        // tested where the reference reads its clock
+        if (++expansions > max_expansions) return AVK_ST_TIMEOUT;
         size_t oi = cur->h.set_alleles();
         if (oi == N) {                                            // :180-192
             DErr e = cur->h.finalize_dwfa(ref, end);
@@ -864,9 +867,10 @@ static int solve_compare_region(const uint8_t *ref, size_t ref_len, size_t start
         for (uint8_t z : oh.query_zyg) { uint8_t a, b2; zyg_decompose(z, a, b2); qh1.push_back(a); qh2.push_back(b2); }
         Cand c;
         c.idx = si;
-        st = optimize_gt_alleles(ref, start, end, tv, th1, qv, qh1, c.h1);   // :214-218
+        const uint64_t xcap = cfg.exact_gt_max_expansions ? cfg.exact_gt_max_expansions : AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS;
+        st = optimize_gt_alleles(ref, start, end, tv, th1, qv, qh1, c.h1, xcap);   // :214-218
         if (st) return st;
-        st = optimize_gt_alleles(ref, start, end, tv, th2, qv, qh2, c.h2);   // :219-223
+        st = optimize_gt_alleles(ref, start, end, tv, th2, qv, qh2, c.h2, xcap);   // :219-223
         if (st) return st;
         st = compare_expected_observed(oh.ed1, oh.ed2, tv, th1, c.h1.truth_alleles, th2, c.h2.truth_alleles, c.ts);  // :226-235
         if (st) return st;

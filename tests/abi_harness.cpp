@@ -45,7 +45,7 @@ int main() {
     out.status = status; out.ed1 = ed1; out.ed2 = ed2; out.type_mask = type_mask;
     out.var_expected = vexp; out.var_observed = vobs; out.var_class = vcls;
     out.totals = totals.data(); out.totals_mask = &totals_mask; out.solved_blocks = &solved; out.error_blocks = &errors;
-    const avk_compare_cfg cfg = {50, 0, 0, 0};
+    const avk_compare_cfg cfg = {50, 0, 0, 0, 0};
     if (avk_compare_batch(ctx, &b, &cfg, &out) != AVK_OK) { fprintf(stderr, "%s\n", avk_last_error(ctx)); return 2; }
     printf("status %d %d ed %u %u %u %u solved %llu errors %llu\n", status[0], status[1], ed1[0], ed2[0], ed1[1], ed2[1],
            (unsigned long long)solved, (unsigned long long)errors);

@@ -639,3 +639,27 @@ def test_warp_only_pipeline_vs_oracle():
         assert s.compare_batch(batch, CompareConfig(enable_sequences=False)).diff(orc.compare_batch(batch, [ref], compare_cfg(CompareConfig(enable_sequences=False)))) == []
     finally:
         s.close()
+
+
+def test_exact_gt_expansion_cap_timeout(solver):
+    """AVK_ST_TIMEOUT, the deterministic stand-in for the reference's 300 s bail-out (exact_gt_optimizer.rs:165,174-176): a cap
+    of 3 expansions per optimize_gt_alleles call trips on dense het clusters.  The device prunes exact-GT searches the oracle
+    runs in full, so it can only time out where the oracle does; wherever both agree on the status every output
+    is identical, and with the default cap nothing times out."""
+    p = synth.SynthParams(n_variants=1500, dense_frac=0.9, dense_mean=6.0, het_frac=0.95, phased_frac=0.2,
+                          p_repr=0.05, p_gt_err=0.08, p_fn=0.08, p_fp=0.08)
+    ref, batch = synth.workload_compare(30_000, p, seed=17)
+    solver.set_reference([ref])
+    cfg = CompareConfig(enable_sequences=False, exact_gt_max_expansions=3)
+    gpu = solver.compare_batch(batch, cfg)
+    cpu = orc.compare_batch(batch, [ref], compare_cfg(cfg))
+    n = batch.n_regions
+    g_to, c_to = gpu.status[:n] == abi.ST_TIMEOUT, cpu.status[:n] == abi.ST_TIMEOUT
+    assert g_to.sum() > 0 and c_to[g_to].all()
+    same = gpu.status[:n] == cpu.status[:n]
+    assert same.mean() > 0.9
+    assert (gpu.region_metrics[:n][same] == cpu.region_metrics[:n][same]).all()
+    assert (gpu.ed1[:n][same] == cpu.ed1[:n][same]).all()
+    dflt = solver.compare_batch(batch, CompareConfig(enable_sequences=False))
+    assert (dflt.status[:n] != abi.ST_TIMEOUT).all()
+    assert dflt.diff(orc.compare_batch(batch, [ref], compare_cfg(CompareConfig(enable_sequences=False)))) == []

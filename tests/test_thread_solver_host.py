@@ -92,3 +92,23 @@ def test_thread_solver_sv_shape_mostly_rejected_but_exact():
     p = synth.SynthParams(n_variants=300, sv_events=40, sv_max=800, flank=1000)
     ref, batch = synth.workload_compare(400_000, p, seed=4)
     check(batch, [ref])
+
+
+def test_thread_solver_exact_gt_expansion_cap():
+    """AVK_ST_TIMEOUT: with a tiny cap the searches that the (pruned) fast path runs and the oracle's agree on which regions
+    time out whenever the first search of a region trips it; here every region's status must match."""
+    p = synth.SynthParams(n_variants=1500, dense_frac=0.9, dense_mean=6.0, het_frac=0.95, phased_frac=0.2,
+                          p_repr=0.05, p_gt_err=0.08, p_fn=0.08, p_fp=0.08)
+    ref, batch = synth.workload_compare(30_000, p, seed=17)
+    cfg = abi.CompareCfg(50, 0, 0, 0, 3)
+    ts, rej, stats = run_ts(batch, [ref], cfg)
+    cpu = orc.compare_batch(batch, [ref], cfg, n_threads=orc.num_threads())
+    n = batch.n_regions
+    ok = ~rej
+    timed_out = cpu.status[:n] == abi.ST_TIMEOUT
+    assert timed_out.sum() > 0
+    # the fast path may prune a search the oracle runs to the cap (documented); where it also times out, outputs agree
+    both = ok & (ts.status[:n] == abi.ST_TIMEOUT)
+    assert both.sum() > 0 and (timed_out[both]).all()
+    same = ok & (ts.status[:n] == cpu.status[:n])
+    assert (ts.region_metrics[:n][same] == cpu.region_metrics[:n][same]).all()

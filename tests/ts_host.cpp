@@ -89,7 +89,7 @@ extern "C" int ts_compare_batch(const avk_region_batch *b, const uint8_t *const 
         build_digest(b, r, dig);
         Solver S;
         S.wp = w; S.ctr = &ctr;
-        S.begin(dig.data(), contigs[c], (int)b->start[r], (int)b->end[r], (int)cfg->max_branch_factor);
+        S.begin(dig.data(), contigs[c], (int)b->start[r], (int)b->end[r], (int)cfg->max_branch_factor, cfg->exact_gt_max_expansions);
         while (S.phase == PH_RUN) {                                      // the kernel alternates these two for a whole warp
             S.advance();
             if (S.task.kind != TK_NONE) { S.exec_task(); steps += 1; }
