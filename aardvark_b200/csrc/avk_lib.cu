@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -585,6 +586,8 @@ struct TierArgs {
     u8 *spill_base;        // shared-memory stages: per-warp node spill area in global memory (may be NULL)
     u32 spill_bytes;       // per warp
     int n_lo, n_hi;        // stages that scan all regions only take clusters with n_lo <= #variants <= n_hi
+    u8 *dense_blobs;       // speculative dense search -> team stage: [dense_cap][SPB_SIZE], slot = index in the dense list
+    u32 dense_cap;
 };
 
 enum { MODE_FUSED = 0, MODE_SEARCH = 1, MODE_SCORE = 2, MODE_COOP = 3 };
@@ -605,7 +608,7 @@ __device__ __forceinline__ RegionSolver<SMEM> &init_solver(const DevBatch &b, co
         s.tma_pending = 0;
         s.arena_bytes = (u32)t.arena_bytes;
         s.arena = arena;
-        s.spill_base = nullptr; s.spill_bytes = 0; s.team = nullptr;
+        s.spill_base = nullptr; s.spill_bytes = 0; s.team = nullptr; s.pre_scored = 0;
         s.wide_b0 = t.wide_b0;
         if (SMEM && t.spill_base) {
             s.spill_base = t.spill_base + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (u64)t.spill_bytes;
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) k_compare_coop(DevBatch b, De
     if (lane == 0) {
         s.bp = &sb; s.tma_phase = 0; s.tma_pending = 0;
         s.arena_bytes = (u32)(t.arena_bytes > 0xfffffff0LL ? 0xfffffff0LL : t.arena_bytes); s.arena = arena;
-        s.spill_base = nullptr; s.spill_bytes = 0; s.wide_b0 = 0; s.team = nullptr;
+        s.spill_base = nullptr; s.spill_bytes = 0; s.wide_b0 = 0; s.team = nullptr; s.pre_scored = 0;
     }
     clear_work<false>(arena);
     if (lane == 0) *(u32 *)(uintptr_t)(arena + WK_COOP) = 1u;
@@ -769,7 +772,7 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
     const u32 arena = (u32)tm * (u32)t.arena_bytes;
     if (lane == 0) {
         s.bp = &sb; s.tma_phase = 0; s.tma_pending = 0; s.arena_bytes = (u32)t.arena_bytes; s.arena = arena;
-        s.spill_base = nullptr; s.spill_bytes = 0; s.wide_b0 = 0; s.team = &B;
+        s.spill_base = nullptr; s.spill_bytes = 0; s.wide_b0 = 0; s.team = &B; s.pre_scored = 0;
         if (t.spill_base) { s.spill_base = t.spill_base + ((u64)blockIdx.x * TEAMS_PER_CTA + tm) * (u64)t.spill_bytes; s.spill_bytes = t.spill_bytes; }
         mbar_init(arena);
     }
@@ -782,7 +785,12 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
         idx = __shfl_sync(AVK_FULL, idx, 0);
         if (idx >= n_work) break;
         const u64 r = t.work_list[idx];
-        int rc = s.solve_compare(r, cfg, out);
+        // searched (and usually scored) already by k_search_spec?  then only the metrics are left
+        const u8 *blob = (t.dense_blobs && idx < t.dense_cap) ? t.dense_blobs + (size_t)idx * avk_sp::SPB_SIZE : nullptr;
+        if (blob && *(const int *)(blob + avk_sp::SPB_NRES) == avk_sp::SPB_DONE) continue;   // finished by k_search_spec
+        int rc;
+        if (blob && *(const int *)(blob + avk_sp::SPB_NRES) > 0) rc = s.compare_score_from_dense(r, cfg, out, blob);
+        else rc = s.solve_compare(r, cfg, out);
         __syncwarp();
         if (rc == SOLVE_WORKSPACE) {
             if (lane == 0) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = (u32)r;
@@ -796,6 +804,118 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
     if (lane == 0) B.exit_ = 1;
     __syncwarp();
     asm volatile("bar.sync %0, 128;" ::"r"(B.bar) : "memory");   // releases the helpers
+}
+
+// ---- speculative search of the dense clusters ---------------------------------------------------------------------------
+// One warp per cluster of the dense list X (avk_spec_search.cuh): optimize_sequences with up to 32 queue pops in flight -- one
+// chain per lane, committed in the reference's order -- then optimize_gt_alleles of every equal-best result's haplotypes,
+// one search per lane.  What leaves is the chosen solution and its exact-GT alleles in the cluster's slot of `dense_blobs`
+// (slot = index in X); the team stage that follows computes the metrics from it.  A cluster outside the fast path's limits
+// gets SPB_NONE in its slot and is solved from scratch by the team stage.
+enum { SPEC_WARPS = 8 };
+struct SpecSink {
+    const avk_sp::View &V;
+    const DevCompareOut &out;
+    u64 *row;
+    unsigned long long *slot;
+    __device__ __forceinline__ void variant(int oi, int e, int o) {
+        const u32 *rec = (const u32 *)(V.recs + (size_t)VI_SIZE * oi);
+        const u32 gv = rec[VI_GV / 4];
+        const bool tr = (rec[VI_FLAGS / 4] & 0x10000u) != 0;
+        out.vexp[gv] = (u8)e; out.vobs[gv] = (u8)o;
+        out.vcls[gv] = (u8)(e == o ? AVK_CLASS_TP : (tr ? AVK_CLASS_FN : AVK_CLASS_FP));
+    }
+    __device__ __forceinline__ void metric(int g, int m, u64 v) {
+        if (row) row[g * AVK_N_METRICS + m] = v;
+        if (slot) atomicAdd(slot + g * AVK_N_METRICS + m, (unsigned long long)v);
+    }
+};
+// lane 0: outputs of a cluster the speculative path has solved completely (as the commit block of k_compare_thread)
+__device__ __noinline__ void spec_commit(const avk_sp::View &V, const avk_sp::Shared &S, const DevBatch &b, const DevCompareOut &out, u32 r, unsigned long long *slot) {
+    u64 *row = out.region_metrics ? out.region_metrics + (u64)r * (AVK_N_GROUPS * AVK_N_METRICS) : nullptr;
+    if (row) for (int i = 0; i < AVK_N_GROUPS * AVK_N_METRICS; ++i) row[i] = 0;
+    SpecSink sink{V, out, row, slot};
+    u32 e1 = 0, e2 = 0;
+    uint16_t tm = 0;
+    const int rc = avk_sp::commit_metrics(V, S, sink, &e1, &e2, &tm);
+    if (rc == AVK_ST_OK) {
+        out.ed1[r] = e1; out.ed2[r] = e2; out.type_mask[r] = tm;
+        if (slot) { atomicOr(slot + TOT_MASK, (unsigned long long)tm); atomicAdd(slot + TOT_SOLVED, 1ull); }
+    } else {
+        const u64 v0 = b.var_off[(u64)r * 2], v1 = b.var_off[(u64)r * 2 + 2];
+        for (u64 v = v0; v < v1; ++v) { out.vexp[v] = 0; out.vobs[v] = 0; out.vcls[v] = AVK_CLASS_UNKNOWN; }
+        out.ed1[r] = 0; out.ed2[r] = 0; out.type_mask[r] = 0;
+        if (out.seq_off) for (int k = 0; k < 5; ++k) out.seq_len[(u64)r * 5 + k] = 0;
+        if (slot) atomicAdd(slot + TOT_ERRORS, 1ull);
+    }
+    out.status[r] = rc;
+}
+__global__ void __launch_bounds__(32 * SPEC_WARPS, 1) k_search_spec(DevBatch b, DevCompareOut out, avk_compare_cfg cfg, TierArgs t) {
+    using namespace avk_sp;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    u8 *base = avk_dyn_smem + (size_t)warp * (sizeof(Shared) + 32 * sizeof(Scratch));
+    Shared &S = *(Shared *)base;
+    Scratch &X = ((Scratch *)(base + sizeof(Shared)))[lane];
+    Counters ctr = {0, 0, 0};
+    u32 spops = 0, xpops = 0;
+    const u32 n_work = min(t.n_work_ptr ? *t.n_work_ptr : t.n_work, t.dense_cap);
+    const u32 xcap = cfg.exact_gt_max_expansions ? cfg.exact_gt_max_expansions : AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS;
+    const bool finish_here = !(out.seq_off && cfg.enable_sequences);   // the sequence bundle is emitted by the team stage
+    unsigned long long *slot = out.tot_slots ? out.tot_slots + (size_t)(blockIdx.x & (TOT_SLOTS - 1)) * TOT_STRIDE : nullptr;
+    for (;;) {
+        u32 idx = 0;
+        if (lane == 0) idx = atomicAdd(t.work_ctr, 1u);
+        idx = __shfl_sync(AVK_FULL, idx, 0);
+        if (idx >= n_work) break;
+        const u32 r = t.work_list[idx];
+        u8 *blob = t.dense_blobs + (size_t)idx * SPB_SIZE;
+        const u32 c = b.contig[r];
+        bool ok = !cfg.enable_exact_shortcut && c < b.n_contigs && b.start[r] <= b.end[r] && (u64)b.end[r] <= b.contig_len[c] && b.end[r] <= 0x7fff0000u &&
+                  (int)cfg.max_branch_factor > 0;
+        const u8 *digest = b.digest + b.digest_off[r];
+        __syncwarp();
+        if (ok) {
+            if (lane == 0) ok = load_cluster(S, digest, (int)b.start[r], (int)b.end[r], (int)cfg.max_branch_factor);
+            ok = __shfl_sync(AVK_FULL, ok, 0);
+        }
+        __syncwarp();
+        int nres = SPB_NONE;
+        if (ok) {
+            View V;
+            V.S = &S; V.ref = b.contig_ptr[c] + b.start[r]; V.recs = digest + PH_SIZE; V.alle = V.recs + (size_t)VI_SIZE * S.N;
+            if (search_warp(S, X, V, ctr)) {
+                spops += S.spops;                                   // (warp-uniform reads of the shared state)
+                const int n = S.N, found = S.nres;
+                if (score_warp(S, X, V, ctr, xcap)) {
+                    xpops += S.xpops;
+                    if (finish_here && metrics_warp(S, X, V, ctr)) {    // metrics + every output right here: nothing is left for the team stage
+                        if (lane == 0) spec_commit(V, S, b, out, r, slot);
+                        nres = SPB_DONE;
+                    } else if (lane == 0) {
+                        store_result(blob, 0, S.res[S.best_r], n);
+                        *(int *)(blob + SPB_SCORED) = 1; *(u32 *)(blob + SPB_KEEP0) = S.keep0; *(u32 *)(blob + SPB_KEEP1) = S.keep1;
+                    }
+                    if (nres != SPB_DONE) nres = 1;
+                } else {                                            // scoring outside its limits: hand over the search results only
+                    for (int i = lane; i < found; i += 32) store_result(blob, i, S.res[i], n);
+                    if (lane == 0) *(int *)(blob + SPB_SCORED) = 0;
+                    nres = found;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) *(int *)(blob + SPB_NRES) = nres;
+        __syncwarp();
+    }
+    if (t.work_out) {
+        unsigned long long v[5] = {ctr.alignments, ctr.cells, ctr.matched, lane == 0 ? spops : 0u, lane == 0 ? xpops : 0u};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(AVK_FULL, v[k], o);
+            if (lane == 0 && v[k]) atomicAdd(t.work_out + k, v[k]);
+        }
+    }
 }
 
 // ---- thread per cluster -------------------------------------------------------------------------------------------------
@@ -1121,7 +1241,8 @@ struct avk_ctx {
     DevBuf rb[24];   // region builder temporaries
     DevBuf st_off, st_first, st_pmax, st_mask;   // stratification intervals (avk_set_stratifications) and per-region containment masks
     u32 st_n = 0, st_contigs = 0;
-    int dense_n = 10;   // clusters with at least this many variants start in the fused dense-cluster stage (tuning: AVK_DENSE_N)
+    int dense_n = 0;    // clusters with at least this many variants go to the dense list X: speculative search + team stage
+                        // (AVK_DENSE_N; 0 = 10 when the thread-per-cluster stage runs, 6 for the small batches that go without it)
     // Resident batch: regions [lo, lo + n_regions) of the caller's batch, i.e. variants [v_base, v_base + n_variants) of its
     // variant table and bytes [p_base, ..) of its allele pool.  Per-variant device pointers are biased by these bases so
     // that kernels index them with the caller's own (global) indices: a contiguous bin needs no re-basing on the host.
@@ -1145,6 +1266,8 @@ struct avk_ctx {
     long long coop_arena0 = 256LL << 20, coop_arena1 = 2048LL << 20;
     int coop_cap_ints = 26000;
     int wide_b0 = 256;
+    DevBuf dense_blobs, dense_blobs2;
+    bool use_spec_search = true;    // AVK_NO_SPEC_SEARCH=1: the team stage searches the dense clusters itself (A/B timing)
     bool use_thread_stage = true;   // AVK_NO_THREAD_STAGE=1: warp kernels only (A/B timing, tests of the warp path)
     bool sort_shapes = true;        // AVK_NO_SHAPE_SORT=1: the thread stage takes its clusters in list order
     u64 thread_min_regions = 400000; // smaller batches go to the warp kernels directly: with at most a cluster or two per thread the
@@ -1153,8 +1276,16 @@ struct avk_ctx {
     // alternating bins so that one bin's upload, another's kernels and a third's download overlap.
     avk_ctx *ref_owner = nullptr;   // set in a sibling: whose reference it reads
     avk_ctx *sib[2] = {nullptr, nullptr};
-    int pipe_bins = 0;              // AVK_PIPELINE_BINS (0 or 1: off, the default: measured slower than one piece)
-    u64 pipe_min_regions = 200000;  // batches below this are solved in one piece
+    int pipe_bins = 0;              // AVK_PIPELINE_BINS: bins of a streamed call (-1: one bin per pipe_bin_regions clusters; 0 or 1: off, the default:
+                                    // a pass has ~10 ms of fixed cost (its longest clusters), so bins only pay for batches of many millions of clusters)
+    u64 pipe_min_regions = 1500000; // batches below this are solved in one piece
+    u64 pipe_bin_regions = 1000000;
+    // Streamed call (compare_streamed): host->device copies go on `up`, device->host copies on `dn`; both NULL outside it
+    // (copies then go on `stream`).  A sibling lane shares the owner's compute streams (own_streams == false).
+    cudaStream_t up = nullptr, dn = nullptr;
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};   // created on first use, kept
+    cudaEvent_t ev_up = nullptr, ev_done = nullptr;
+    bool own_streams = true;
 };
 static inline const avk_ctx *ref_of(const avk_ctx *ctx) { return ctx->ref_owner ? ctx->ref_owner : ctx; }
 
@@ -1181,7 +1312,15 @@ static int ensure(avk_ctx *ctx, DevBuf &b, size_t bytes) {
 static int upload(avk_ctx *ctx, DevBuf &b, const void *src, size_t bytes) {
     int rc = ensure(ctx, b, bytes);
     if (rc != AVK_OK) return rc;
-    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->up ? ctx->up : ctx->stream));
+    return AVK_OK;
+}
+// kernels launched on ctx->stream after this call see everything upload() has queued so far
+static int uploads_done(avk_ctx *ctx) {
+    if (ctx->up) {
+        CK(cudaEventRecord(ctx->ev_up, ctx->up));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0));
+    }
     return AVK_OK;
 }
 #define UPLOAD(buf, src, bytes)                          \
@@ -1206,6 +1345,7 @@ static int configure_kernels(avk_ctx *ctx) {
     SMEM_OPT_IN((k_compare<true, 1, MODE_FUSED>));
     SMEM_OPT_IN(k_compare_team);
     SMEM_OPT_IN(k_compare_thread);
+    SMEM_OPT_IN(k_search_spec);
     SMEM_OPT_IN(k_wfa_ed_cta);
     SMEM_OPT_IN((k_merge_pairs<true, 3>));
     SMEM_OPT_IN((k_merge_pairs<true, 1>));
@@ -1242,9 +1382,11 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (const char *s = getenv("AVK_TEST_COOP_CAP_INTS")) ctx->coop_cap_ints = std::min<int>(COOP_CAP_INTS_MAX, std::max(64, atoi(s)));
     if (const char *s = getenv("AVK_TEST_WIDE_B0")) ctx->wide_b0 = std::max(1, atoi(s));
     if (const char *s = getenv("AVK_NO_THREAD_STAGE")) ctx->use_thread_stage = atoi(s) == 0;
+    if (const char *s = getenv("AVK_NO_SPEC_SEARCH")) ctx->use_spec_search = atoi(s) == 0;
     if (const char *s = getenv("AVK_NO_SHAPE_SORT")) ctx->sort_shapes = atoi(s) == 0;
     if (const char *s = getenv("AVK_THREAD_MIN_REGIONS")) ctx->thread_min_regions = (u64)std::max(0LL, atoll(s));
-    if (const char *s = getenv("AVK_PIPELINE_BINS")) ctx->pipe_bins = std::max(0, atoi(s));
+    if (const char *s = getenv("AVK_PIPELINE_BINS")) ctx->pipe_bins = std::max(-1, atoi(s));
+    if (const char *s = getenv("AVK_PIPELINE_BIN_REGIONS")) ctx->pipe_bin_regions = (u64)std::max(1LL, atoll(s));
     if (const char *s = getenv("AVK_PIPELINE_MIN_REGIONS")) ctx->pipe_min_regions = (u64)std::max(1LL, atoll(s));
     for (auto &e : ctx->tev) cudaEventCreate(&e);
     {
@@ -1256,6 +1398,8 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (auto &e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : ctx->dbg) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
     if (cudaMallocHost((void **)&ctx->h_pin, 4096) != cudaSuccess) { ctx->h_pin = nullptr; cudaGetLastError(); }
     if (!ctx->h_pin) { avk_destroy(ctx); return AVK_ERR_OOM; }
     memset(ctx->h_pin, 0, 4096);
@@ -1269,11 +1413,12 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &st : ctx->side) if (st) cudaStreamSynchronize(st);
+    for (cudaStream_t st : ctx->copy_streams) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     DevBuf *bufs[] = {&ctx->d_contig_ptr, &ctx->d_contig_len, &ctx->region_id, &ctx->contig, &ctx->start, &ctx->end, &ctx->var_off,
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->tot_slots, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x, &ctx->fail_t, &ctx->fail_s, &ctx->shape_key,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x, &ctx->fail_t, &ctx->fail_s, &ctx->shape_key, &ctx->dense_blobs, &ctx->dense_blobs2,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
@@ -1284,14 +1429,23 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
     for (auto &e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->dbg) if (e) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    for (auto &st : ctx->side) if (st) cudaStreamDestroy(st);
+    if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (ctx->own_streams) {
+        for (auto &st : ctx->side) if (st) cudaStreamDestroy(st);
+        cudaStreamDestroy(ctx->stream);
+    }
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 extern "C" const char *avk_last_error(const avk_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-extern "C" uint64_t avk_launch_count(const avk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t avk_launch_count(const avk_ctx *ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (const avk_ctx *sb : ctx->sib) if (sb) n += sb->launches;
+    return n;
+}
 
 extern "C" int avk_set_reference(avk_ctx *ctx, uint32_t n_contigs, const uint8_t *const *seqs, const uint64_t *lens) {
     if (!ctx || (n_contigs && (!seqs || !lens))) return AVK_ERR_INVALID;
@@ -1354,7 +1508,8 @@ struct BinScan {
     u32 max_allele = 1;
 };
 
-static int scan_bin(avk_ctx *ctx, const avk_region_batch *b, u64 lo, u64 hi, BinScan &sc) {
+// the bin's variant range (cheap; the uploads of the region and variant arrays can start from this alone)
+static int bin_range(avk_ctx *ctx, const avk_region_batch *b, u64 lo, u64 hi, BinScan &sc) {
     const u64 K = b->n_inputs;
     const avk_variant_table &t = b->variants;
     sc.lo = lo; sc.hi = hi;
@@ -1362,12 +1517,20 @@ static int scan_bin(avk_ctx *ctx, const avk_region_batch *b, u64 lo, u64 hi, Bin
     const u64 *vo = b->var_off;
     sc.v0 = vo[lo * K]; sc.v1 = vo[hi * K];
     if (sc.v0 > sc.v1 || sc.v1 > t.n_variants) { ctx->err = "var_off outside the variant table"; return AVK_ERR_INVALID; }
-    const u64 nv = sc.v1 - sc.v0, nr = (hi - lo) * K;
-    if (nv && (!t.position || !t.variant_type || !t.zygosity || !t.raw_allele_space || !t.allele_off || !t.a0_len || !t.a1_len || !t.allele_pool)) {
+    if (sc.v1 > sc.v0 && (!t.position || !t.variant_type || !t.zygosity || !t.raw_allele_space || !t.allele_off || !t.a0_len || !t.a1_len || !t.allele_pool)) {
         ctx->err = "null variant arrays";
         return AVK_ERR_INVALID;
     }
-    const int nt = (int)std::min<u64>(8, std::max<u64>(1, (nv + nr) / 500000));
+    return AVK_OK;
+}
+// host-side validation of the offsets the kernels index with, and the bin's allele-pool range (after bin_range)
+static int scan_bin(avk_ctx *ctx, const avk_region_batch *b, BinScan &sc) {
+    const u64 K = b->n_inputs, lo = sc.lo, hi = sc.hi;
+    const avk_variant_table &t = b->variants;
+    if (hi == lo) return AVK_OK;
+    const u64 *vo = b->var_off;
+    const u64 nv = sc.v1 - sc.v0, nr = (hi - lo) * K;
+    const int nt = (int)std::min<u64>(12, std::max<u64>(1, (nv + nr) / 400000));
     struct Part { u64 p0 = ~0ull, p1 = 0, sum = 0; u32 mx = 1; int bad = 0; };
     std::vector<Part> parts(nt);
     auto work = [&](int ti) {
@@ -1414,8 +1577,8 @@ static int validate_batch(avk_ctx *ctx, const avk_region_batch *b, bool compare)
     return AVK_OK;
 }
 
-// Upload regions [sc.lo, sc.hi) of the batch: a contiguous bin (the whole batch for one GPU).
-static int upload_batch(avk_ctx *ctx, const avk_region_batch *b, const BinScan &sc) {
+// Upload regions [sc.lo, sc.hi) of the batch (after bin_range): a contiguous bin (the whole batch for one GPU).
+static int upload_batch(avk_ctx *ctx, const avk_region_batch *b, BinScan &sc) {
     if (ref_of(ctx)->contig_bufs.empty()) { ctx->err = "avk_set_reference has not been called"; return AVK_ERR_NO_REFERENCE; }
     const u64 lo = sc.lo, n = sc.hi - sc.lo, K = b->n_inputs, v0 = sc.v0, nv = sc.v1 - sc.v0;
     const avk_variant_table &t = b->variants;
@@ -1432,8 +1595,11 @@ static int upload_batch(avk_ctx *ctx, const avk_region_batch *b, const BinScan &
     UPLOAD(ctx->aoff, t.allele_off + v0, 4 * nv);
     UPLOAD(ctx->l0, t.a0_len + v0, 4 * nv);
     UPLOAD(ctx->l1, t.a1_len + v0, 4 * nv);
-    UPLOAD(ctx->pool, t.allele_pool + sc.p0, sc.p1 - sc.p0);
     ENSURE(ctx->alt_ed, 4 * nv);
+    // while those copies are under way the host validates the offsets and finds the bin's allele-pool range
+    int rc = scan_bin(ctx, b, sc);
+    if (rc != AVK_OK) { cudaStreamSynchronize(ctx->up ? ctx->up : ctx->stream); return rc; }
+    UPLOAD(ctx->pool, t.allele_pool + sc.p0, sc.p1 - sc.p0);
     ctx->max_allele = sc.max_allele;
     ctx->pool_len = sc.sum_alle;
     ctx->lo = lo; ctx->n_regions = n; ctx->v_base = v0; ctx->n_variants = nv; ctx->p_base = sc.p0; ctx->pool_bytes = sc.p1 - sc.p0;
@@ -1653,14 +1819,17 @@ static TierArgs tier_args(avk_ctx *ctx, const u32 *list, int in_ctr, int work_ct
     return a;
 }
 
-// The compare pipeline: closed-form kernel (all clusters) -> warp-team stage for the dense list X on the main stream,
-// and beside it on a low-priority side stream: search kernel -> score kernel -> fused 27 KB shared-memory stage for the
-// clusters that did not fit the common tier (list A); then the fused 2 MB global-arena stage (list B).  Every stage reads
-// its work count from an earlier stage's counter in device memory and NOTHING here waits for the device: the counters
-// travel back with the results (compare_finish), and only if list D (SV-sized clusters) turns out non-empty does the host
-// launch the cooperative tiers afterwards.
-// counters (u32): 12 |W| (clusters without a closed form), 17 |X| dense, 19 thread-stage work, 13 |W2| (its rejects), 0 search work, 1 |A|, 2 score work, 15 |A2|, 4 team work,
-// 18 S1 work, 16 S1' work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers
+// The compare pipeline.  k_compare_simple takes every cluster: closed forms are final, clusters with >= dense_n variants go
+// to the dense list X, the rest to W.  Main stream: X -> speculative search + team stage.  Beside it on a lowest-priority
+// side stream: W -> one thread per cluster (large batches; its rejects W2 -> speculative search + team stage), or for small
+// batches W -> warp search / score kernels (the search kernel's rejects A -> speculative search + team stage).  Then on the
+// main stream the fused 27 KB stage for the score kernel's rejects (A2) and the fused 2 MB global-arena stage for whatever did
+// not fit a team's shared memory (B).  Every stage reads its work count from an earlier stage's counter in device memory and
+// NOTHING here waits for the device: the counters travel back with the results (compare_finish), and only if list D
+// (SV-sized clusters) turns out non-empty does the host launch the cooperative tiers afterwards.
+// counters (u32): 12 |W| (clusters without a closed form), 17 |X| dense, 20 / 4 speculative search / team work on X, 19 thread-stage
+// work, 13 |W2| (its rejects), 0 search work, 1 |A|, 2 score work, 15 |A2|, 22 / 23 speculative search / team work on W2 or A,
+// 16 S1 work, 5 |B|, 9 G0 work, 7 |D|; 32.. big tiers; 40 digest builder
 static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     const u64 n = ctx->n_regions;
     if (n == 0) return AVK_OK;
@@ -1677,15 +1846,17 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     const Stage S1 = {MODE_FUSED, true, 1, 27648, sm, 8}, G0 = {MODE_FUSED, false, 1, 2LL << 20, sm, 8};
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p, *LX = (u32 *)ctx->fail_x.p;
+    const bool thread_stage = ctx->use_thread_stage && n >= ctx->thread_min_regions;
+    const int dense_n = ctx->dense_n ? ctx->dense_n : (thread_stage ? 10 : 6);
     // closed-form clusters; >= dense_n variants -> X (dense); the rest -> W
     u64 *keys = nullptr;
-    if (ctx->use_thread_stage && n >= ctx->thread_min_regions && ctx->sort_shapes) {
+    if (thread_stage && ctx->sort_shapes) {
         ENSURE(ctx->shape_key, 16 * n);                               // keys in / out
         ENSURE(ctx->fail_s, 4 * n);
         keys = (u64 *)ctx->shape_key.p;
         CK(cudaMemsetAsync(keys, 0xff, 8 * n, ctx->stream));          // unused tail sorts behind every real key
     }
-    k_compare_simple<<<sm * 8, 256, 0, ctx->stream>>>(R.db, R.out, R.cfg, n, LW, ctrs + 12, LX, ctrs + 17, ctx->dense_n, keys);
+    k_compare_simple<<<sm * 8, 256, 0, ctx->stream>>>(R.db, R.out, R.cfg, n, LW, ctrs + 12, LX, ctrs + 17, dense_n, keys);
     if (keys) {                                                       // W sorted by shape -> fail_s (the first |W| entries are the real ones)
         size_t need = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys + n, LW, (u32 *)ctx->fail_s.p, (int)n, 0, 64, ctx->stream);
@@ -1694,35 +1865,52 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
         ctx->launches += 1;
     }
     const size_t spill_warp = 1u << 20, spill_half = (size_t)sm * 8 * spill_warp;
-    // A dense cluster is solved by one warp team in up to ~1 ms, so the dense stage ends with a few busy teams.  It is launched
-    // first (main stream, one 216 KB CTA per SM); search, score and the fused stage for their rejects follow on a
-    // lowest-priority side stream behind an event: as the dense CTAs run out of work and retire, the block scheduler fills
-    // their SMs with the other kernels' CTAs, which then run in the shadow of that tail.  (All k_compare kernels ask for the
-    // maximum shared-memory carveout; kernels of different streams do not take over an SM otherwise: tools/overlap_probe.cu.)
+    const u32 dense_cap = (u32)std::min<u64>(n, std::max<u64>(8192, n / 32));
+    // A list of hard clusters is solved in two launches: k_search_spec -- optimize_sequences with up to 32 queue pops in flight
+    // and the exact-GT scoring of the equal-best results, one search per lane -- leaves the chosen solution in the cluster's
+    // blob, and the team stage computes the metrics from it (or solves the cluster from scratch when the speculative search
+    // declined it); what does not fit the team stage's 108 KB goes on to list B.
+    auto spec_then_team = [&](const u32 *list, int in_ctr, int spec_ctr, int team_ctr, DevBuf &blobs, u8 *spill, cudaStream_t strm) -> int {
+        TierArgs a = tier_args(ctx, list, in_ctr, team_ctr, LB, 5, 108 * 1024, nullptr);
+        a.spill_base = spill; a.spill_bytes = (u32)spill_warp;
+        if (ctx->use_spec_search) {
+            ENSURE(blobs, (size_t)dense_cap * avk_sp::SPB_SIZE);
+            TierArgs sa = tier_args(ctx, list, in_ctr, spec_ctr, nullptr, 21, 0, nullptr);
+            sa.dense_blobs = (u8 *)blobs.p; sa.dense_cap = dense_cap;
+            k_search_spec<<<sm, 32 * SPEC_WARPS, SPEC_WARPS * (sizeof(avk_sp::Shared) + 32 * sizeof(avk_sp::Scratch)), strm>>>(R.db, R.out, R.cfg, sa);
+            ctx->launches += 1;
+            a.dense_blobs = sa.dense_blobs; a.dense_cap = dense_cap;
+        }
+        k_compare_team<<<sm, 128 * TEAMS_PER_CTA, TEAMS_PER_CTA * (size_t)a.arena_bytes, strm>>>(R.db, R.out, R.cfg, a);
+        ctx->launches += 1;
+        return AVK_OK;
+    };
+    // The dense list X starts first on the main stream; everything else follows on a lowest-priority side stream behind an
+    // event and fills the SMs the dense stage leaves free (all these kernels ask for the maximum shared-memory carveout;
+    // kernels of different streams do not take over an SM otherwise: tools/overlap_probe.cu).
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
     {
-        TierArgs a = tier_args(ctx, LX, 17, 4, LB, 5, 108 * 1024, nullptr);
-        a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = (u32)spill_warp;
-        k_compare_team<<<sm, 128 * TEAMS_PER_CTA, TEAMS_PER_CTA * (size_t)a.arena_bytes, ctx->stream>>>(R.db, R.out, R.cfg, a);   // X -> B
+        const int rc = spec_then_team(LX, 17, 20, 4, ctx->dense_blobs, (u8 *)ctx->arena2.p, ctx->stream);            // X -> B
+        if (rc != AVK_OK) return rc;
     }
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
-    const int small_ctas = (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8);
-    const u32 *LS = LW;          // what the warp search / score kernels consume
-    int ls_ctr = 12;
-    if (ctx->use_thread_stage && n >= ctx->thread_min_regions) {                             // W -> solved by one thread each; rejects -> W2
+    if (thread_stage) {
+        // W -> one thread per cluster; what exceeds a thread's fixed workspace (W2) is a hard cluster
         u32 *LW2 = (u32 *)ctx->fail_t.p;
         TierArgs a = tier_args(ctx, keys ? (const u32 *)ctx->fail_s.p : LW, 12, 19, LW2, 13, sizeof(avk_ts::Work), nullptr);
         k_compare_thread<<<(unsigned)std::min<u64>((u64)sm, (n + THREAD_TPB - 1) / THREAD_TPB), THREAD_TPB, THREAD_TPB * sizeof(avk_ts::Work), ctx->side[0]>>>(R.db, R.out, R.cfg, a);
         ctx->launches += 1;
-        LS = LW2; ls_ctr = 13;
-    }
-    launch_stage(ctx, R, SEARCH, tier_args(ctx, LS, ls_ctr, 0, LA, 1, SEARCH.arena_bytes, nullptr), small_ctas, ctx->side[0]);                                         // -> blobs, rejects -> A
-    launch_stage(ctx, R, SCORE, tier_args(ctx, LS, ls_ctr, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);    // rejects -> A2
-    {
-        TierArgs a = tier_args(ctx, LA, 1, 18, LB, 5, S1.arena_bytes, nullptr);
-        a.spill_base = (u8 *)ctx->arena2.p + spill_half; a.spill_bytes = (u32)spill_warp;   // cold search nodes spill to HBM instead of restarting the cluster
-        launch_stage(ctx, R, S1, a, S1.ctas, ctx->side[0]);                                  // A -> B  (did not fit the 8 KB search arena)
+        const int rc = spec_then_team(LW2, 13, 22, 23, ctx->dense_blobs2, (u8 *)ctx->arena2.p + spill_half, ctx->side[0]);   // W2 -> B
+        if (rc != AVK_OK) return rc;
+    } else {
+        // small batches: W -> warp search / score kernels (8 KB / 5 KB per warp); the search kernel's rejects (A) are hard clusters
+        const int small_ctas = (int)std::min<u64>((u64)SEARCH.ctas, (n + 7) / 8);
+        launch_stage(ctx, R, SEARCH, tier_args(ctx, LW, 12, 0, LA, 1, SEARCH.arena_bytes, nullptr), small_ctas, ctx->side[0]);                                         // -> blobs, rejects -> A
+        launch_stage(ctx, R, SCORE, tier_args(ctx, LW, 12, 2, LA2, 15, SCORE.arena_bytes, nullptr), (int)std::min<u64>((u64)SCORE.ctas, (n + 7) / 8), ctx->side[0]);    // rejects -> A2
+        ctx->launches += 2;
+        const int rc = spec_then_team(LA, 1, 22, 23, ctx->dense_blobs2, (u8 *)ctx->arena2.p + spill_half, ctx->side[0]);     // A -> B
+        if (rc != AVK_OK) return rc;
     }
     CK(cudaEventRecord(ctx->ev_join[0], ctx->side[0]));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
@@ -1730,7 +1918,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     {
         TierArgs a = tier_args(ctx, LA2, 15, 16, LB, 5, S1.arena_bytes, nullptr);
         a.spill_base = (u8 *)ctx->arena2.p; a.spill_bytes = 1u << 20;
-        launch_stage(ctx, R, S1, a, S1.ctas, ctx->stream);                                   // A2 -> B  (score kernel's rejects, rare)
+        launch_stage(ctx, R, S1, a, S1.ctas, ctx->stream);                                   // A2 -> B  (score kernel's rejects, rare; empty with the thread stage)
     }
     {
         TierArgs a = tier_args(ctx, LB, 5, 9, LD, 7, G0.arena_bytes, (u8 *)ctx->arena.p);
@@ -1738,7 +1926,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
         launch_stage(ctx, R, G0, a, G0.ctas, ctx->stream);                                   // B -> D   (2 MB global arenas)
     }
     CK(cudaEventRecord(ctx->tev[3], ctx->stream));
-    ctx->launches += 7;
+    ctx->launches += 3;
     CK(cudaGetLastError());
     return AVK_OK;
 }
@@ -1797,6 +1985,15 @@ static int run_finalize(avk_ctx *ctx, const CompareRun &R) {
     return AVK_OK;
 }
 
+// pipeline counters + work counters travel back behind the kernels (pinned scratch: the copies do not block); ev_done marks
+// the point where the pass and these copies are complete
+static int queue_counter_copies(avk_ctx *ctx) {
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->counters.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin + 128, ctx->work_ctr.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_done, ctx->stream));
+    return AVK_OK;
+}
+
 // Launches one compare pass over the resident batch; nothing waits for the device.
 static int compare_launch(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_seq, bool want_rows, bool strata, u32 n_strata, bool strat_dev, bool want_contain, CompareRun &R) {
     const u64 n = ctx->n_regions, nv = ctx->n_variants;
@@ -1852,17 +2049,15 @@ static int compare_launch(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_se
     rc = run_finalize(ctx, R);
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    // pipeline counters + work counters travel back behind the kernels (pinned scratch: the copies do not block)
-    CK(cudaMemcpyAsync(ctx->h_pin, ctx->counters.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->result_has_rows = rows;
-    return AVK_OK;
+    return queue_counter_copies(ctx);
 }
 
 // Waits for the pass; if SV-sized clusters were left for the cooperative tiers, runs them and the summary again.
 // *redo is set when outputs copied to the host before this call are stale.
 static int compare_finish(avk_ctx *ctx, const CompareRun &R, bool *redo) {
     if (redo) *redo = false;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev_done));          // (not the stream: in a streamed call the next bin's kernels are queued behind)
     const u32 *h = ctx->h_pin;
     if (ctx->n_regions) {
         for (int t = 0; t < 3; ++t) cudaEventElapsedTime(&ctx->tier_ms[t], ctx->tev[t], ctx->tev[t + 1]);
@@ -1875,7 +2070,9 @@ static int compare_finish(avk_ctx *ctx, const CompareRun &R, bool *redo) {
             rc = run_finalize(ctx, R);
             if (rc != AVK_OK) return rc;
             CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            rc = queue_counter_copies(ctx);
+            if (rc != AVK_OK) return rc;
+            CK(cudaEventSynchronize(ctx->ev_done));
             if (redo) *redo = true;
         }
     } else {
@@ -1892,9 +2089,8 @@ static int fetch_timings(avk_ctx *ctx) {
     cudaEventElapsedTime(&ctx->last_ms[2], ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->last_ms[3], ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&ctx->last_ms[4], ctx->ev[0], ctx->ev[4]);
-    unsigned long long *w = (unsigned long long *)(ctx->h_pin + 128);
-    CK(cudaMemcpyAsync(w, ctx->work_ctr.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev_done));
+    const unsigned long long *w = (const unsigned long long *)(ctx->h_pin + 128);
     ctx->last_work.alignments = w[0]; ctx->last_work.cells = w[1]; ctx->last_work.matched_bases = w[2];
     ctx->last_work.search_pops = w[3]; ctx->last_work.exact_pops = w[4];
     return AVK_OK;
@@ -1902,7 +2098,7 @@ static int fetch_timings(avk_ctx *ctx) {
 
 #define DL(dst, buf, bytes)                                                                                     \
     do {                                                                                                        \
-        if ((dst) && (bytes)) CK(cudaMemcpyAsync((dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream)); \
+        if ((dst) && (bytes)) CK(cudaMemcpyAsync((dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, ds)); \
     } while (0)
 
 // Partial results of one bin: what the host adds up over bins (wrapping u64, like the reference's AddAssign).
@@ -1915,6 +2111,8 @@ struct BinTotals {
 // ctx->lo, variants from ctx->v_base); totals go to `bt` (pinned scratch first).  No synchronisation here.
 static int download_compare_async(avk_ctx *ctx, avk_compare_out *out, bool want_seq, u64 seq_bytes) {
     const u64 n = ctx->n_regions, nv = ctx->n_variants, lo = ctx->lo, vb = ctx->v_base;
+    const cudaStream_t ds = ctx->dn ? ctx->dn : ctx->stream;
+    if (ctx->dn) CK(cudaStreamWaitEvent(ctx->dn, ctx->ev_done, 0));
     DL(out->status ? out->status + lo : nullptr, ctx->status, 4 * n);
     DL(out->ed1 ? out->ed1 + lo : nullptr, ctx->ed1, 4 * n);
     DL(out->ed2 ? out->ed2 + lo : nullptr, ctx->ed2, 4 * n);
@@ -1926,7 +2124,7 @@ static int download_compare_async(avk_ctx *ctx, avk_compare_out *out, bool want_
     DL(out->var_expected ? out->var_expected + vb : nullptr, ctx->vexp, nv);
     DL(out->var_observed ? out->var_observed + vb : nullptr, ctx->vobs, nv);
     DL(out->var_class ? out->var_class + vb : nullptr, ctx->vcls, nv);
-    CK(cudaMemcpyAsync(ctx->h_pin + 256, ctx->totals.p, 8 * RED_COLS + 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin + 256, ctx->totals.p, 8 * RED_COLS + 64, cudaMemcpyDeviceToHost, ds));
     if (out->containment && ctx->st_mask.p) DL(out->containment + lo, ctx->st_mask, 8 * n);
     if (want_seq) {
         DL(out->seq_len + lo * 5, ctx->seq_len, 4 * 5 * n);
@@ -1935,14 +2133,15 @@ static int download_compare_async(avk_ctx *ctx, avk_compare_out *out, bool want_
     return AVK_OK;
 }
 
-// after the stream has been synchronised: collect totals (+ strata) of this bin
+// after the download stream has been synchronised: collect totals (+ strata) of this bin
 static int collect_totals(avk_ctx *ctx, const avk_compare_out *out, bool strata, BinTotals &bt) {
     memcpy(bt.tot, ctx->h_pin + 256, 8 * RED_COLS + 64);
     bt.strat.clear();
     if (strata) {
         bt.strat.resize((size_t)RED_COLS * out->n_strata);
-        CK(cudaMemcpyAsync(bt.strat.data(), ctx->strat_totals.p, 8ull * RED_COLS * out->n_strata, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        const cudaStream_t ds = ctx->dn ? ctx->dn : ctx->stream;
+        CK(cudaMemcpyAsync(bt.strat.data(), ctx->strat_totals.p, 8ull * RED_COLS * out->n_strata, cudaMemcpyDeviceToHost, ds));
+        CK(cudaStreamSynchronize(ds));
     }
     return AVK_OK;
 }
@@ -1992,34 +2191,61 @@ static int prepare_outputs_on_device(avk_ctx *ctx, const avk_compare_out *out, u
 }
 
 // One contiguous bin [lo, hi) of the batch on this context's GPU; results land in the caller's arrays at the bin's
-// offsets, the bin's summary counters in `bt`.
-static int compare_bin(avk_ctx *ctx, const avk_region_batch *batch, u64 lo, u64 hi, const avk_compare_cfg *cfg, avk_compare_out *out, BinTotals &bt) {
+// offsets, the bin's summary counters in `bt`.  bin_enqueue queues upload, kernels and download without waiting for the
+// device; bin_finish waits for them (and runs the cooperative tiers if SV-sized clusters were left over).
+static inline double host_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct BinPending {
+    CompareRun R;
+    bool want_seq = false, strata = false;
+    u64 seq_bytes = 0;
+};
+static int bin_enqueue(avk_ctx *ctx, const avk_region_batch *batch, u64 lo, u64 hi, const avk_compare_cfg *cfg, avk_compare_out *out, BinPending &P) {
     CK(cudaSetDevice(ctx->device));
+    const bool timing = getenv("AVK_TIMING") != nullptr;
+    const double t0 = timing ? host_ms() : 0;
     BinScan sc;
-    int rc = scan_bin(ctx, batch, lo, hi, sc);
+    int rc = bin_range(ctx, batch, lo, hi, sc);
     if (rc != AVK_OK) return rc;
+    const double t1 = timing ? host_ms() : 0;
     rc = upload_batch(ctx, batch, sc);
     if (rc != AVK_OK) return rc;
-    bool want_seq, strata, strat_dev; u64 seq_bytes;
-    rc = prepare_outputs_on_device(ctx, out, batch->n_regions, want_seq, seq_bytes, strata, strat_dev);
+    if (timing) fprintf(stderr, "[avk]   enqueue: queueing the uploads + host scan beside them %.2f ms\n", host_ms() - t1);
+    (void)t0;
+    bool strat_dev;
+    rc = prepare_outputs_on_device(ctx, out, batch->n_regions, P.want_seq, P.seq_bytes, P.strata, strat_dev);
     if (rc != AVK_OK) return rc;
-    CompareRun R;
+    rc = uploads_done(ctx);
+    if (rc != AVK_OK) return rc;
     const bool want_rows = out->region_metrics != nullptr || (cfg->flags & AVK_CMP_KEEP_REGION_ROWS);
-    rc = compare_launch(ctx, cfg, want_seq, want_rows, strata, strata ? out->n_strata : 0, strat_dev, out->containment != nullptr, R);
+    rc = compare_launch(ctx, cfg, P.want_seq, want_rows, P.strata, P.strata ? out->n_strata : 0, strat_dev, out->containment != nullptr, P.R);
     if (rc != AVK_OK) return rc;
-    rc = download_compare_async(ctx, out, want_seq, seq_bytes);
-    if (rc != AVK_OK) return rc;
+    return download_compare_async(ctx, out, P.want_seq, P.seq_bytes);
+}
+static int bin_finish(avk_ctx *ctx, avk_compare_out *out, const BinPending &P, BinTotals &bt) {
+    CK(cudaSetDevice(ctx->device));
     bool redo = false;
-    rc = compare_finish(ctx, R, &redo);
+    int rc = compare_finish(ctx, P.R, &redo);
     if (rc != AVK_OK) return rc;
     if (redo) {
-        rc = download_compare_async(ctx, out, want_seq, seq_bytes);
+        rc = download_compare_async(ctx, out, P.want_seq, P.seq_bytes);
         if (rc != AVK_OK) return rc;
-        CK(cudaStreamSynchronize(ctx->stream));
     }
-    rc = collect_totals(ctx, out, strata, bt);
+    CK(cudaStreamSynchronize(ctx->dn ? ctx->dn : ctx->stream));
+    rc = collect_totals(ctx, out, P.strata, bt);
     if (rc != AVK_OK) return rc;
     return fetch_timings(ctx);
+}
+static int compare_bin(avk_ctx *ctx, const avk_region_batch *batch, u64 lo, u64 hi, const avk_compare_cfg *cfg, avk_compare_out *out, BinTotals &bt) {
+    BinPending P;
+    const bool timing = getenv("AVK_TIMING") != nullptr;
+    const double t0 = timing ? host_ms() : 0;
+    int rc = bin_enqueue(ctx, batch, lo, hi, cfg, out, P);
+    if (rc != AVK_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+    const double t1 = timing ? host_ms() : 0;
+    rc = bin_finish(ctx, out, P, bt);
+    if (timing) fprintf(stderr, "[avk] one bin: %llu regions, host enqueue %.2f ms (scan + async copies + launches), wait %.2f ms, device pass %.2f ms\n",
+                        (unsigned long long)(hi - lo), t1 - t0, host_ms() - t1, ctx->last_ms[4]);
+    return rc;
 }
 
 extern "C" int avk_compare_batch_range(avk_ctx *ctx, const avk_region_batch *batch, uint64_t lo, uint64_t hi,
@@ -2036,42 +2262,63 @@ extern "C" int avk_compare_batch_range(avk_ctx *ctx, const avk_region_batch *bat
     return AVK_OK;
 }
 
-// Large batches on one GPU are solved as a pipeline: the batch is cut into contiguous bins (avk_partition_regions) and up to
-// three contexts on the same device -- this one and two siblings with their own stream and buffers, reading this context's
-// reference -- take the bins in turn, each from its own host thread.  A bin is upload -> kernels -> download on its
-// context's stream, so one bin's H2D copy, another's kernels and a third's D2H copy run at the same time; results land in
-// the caller's arrays at the bins' offsets and the bins' counters are added up, exactly as avk_compare_batch_multi does
-// across GPUs.
-static int compare_pipelined(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out) {
-    const int n_lanes = 3;
-    avk_ctx *lanes[3] = {ctx, nullptr, nullptr};
-    for (int k = 0; k < 2; ++k) {
-        if (!ctx->sib[k]) {
-            avk_ctx *sb = nullptr;
-            const int rc = avk_create(ctx->device, &sb);
-            if (rc != AVK_OK) { ctx->err = "pipelined compare: could not create a sibling context"; return rc; }
-            sb->ref_owner = ctx;
-            sb->pipe_bins = 0;
-            ctx->sib[k] = sb;
-        }
-        lanes[1 + k] = ctx->sib[k];
+// Large batches on one GPU are STREAMED: the batch is cut into contiguous bins (avk_partition_regions) that go through
+// the device one after the other on this context's compute streams, alternating between two sets of buffers (this context
+// and a sibling lane that shares its streams and reads its reference).  A bin's host->device copies run on its lane's
+// `up` stream, its device->host copies on the lane's `dn` stream, so bin k+1 is uploaded (and scanned on the host) while
+// bin k is being solved and bin k-1 is travelling back; results land in the caller's arrays at the bins' offsets and the
+// bins' counters are added up, exactly as avk_compare_batch_multi does across GPUs.  One host thread; the host waits for
+// bin k-2 before it re-uses that lane for bin k, so at most two bins are in flight.
+static int streamed_lane(avk_ctx *ctx, avk_ctx **lane) {
+    if (!ctx->sib[0]) {
+        avk_ctx *sb = nullptr;
+        const int rc = avk_create(ctx->device, &sb);
+        if (rc != AVK_OK) { ctx->err = "streamed compare: could not create the second lane"; return rc; }
+        // the lane launches on the owner's compute streams: bins stay in order and never compete for the SMs
+        for (auto &st : sb->side) if (st) cudaStreamDestroy(st);
+        cudaStreamDestroy(sb->stream);
+        sb->stream = ctx->stream; sb->side[0] = ctx->side[0]; sb->side[1] = ctx->side[1];
+        sb->own_streams = false;
+        sb->ref_owner = ctx;
+        sb->pipe_bins = 0;
+        ctx->sib[0] = sb;
     }
-    const u32 n_bins = (u32)ctx->pipe_bins;
+    *lane = ctx->sib[0];
+    return AVK_OK;
+}
+static int compare_streamed(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out, u32 n_bins) {
+    avk_ctx *lanes[2] = {ctx, nullptr};
+    int rc = streamed_lane(ctx, &lanes[1]);
+    if (rc != AVK_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    for (avk_ctx *l : lanes) {
+        l->dense_n = ctx->dense_n; l->use_thread_stage = ctx->use_thread_stage; l->sort_shapes = ctx->sort_shapes; l->thread_min_regions = ctx->thread_min_regions;
+        for (auto &st : l->copy_streams) if (!st) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        l->up = l->copy_streams[0]; l->dn = l->copy_streams[1];
+    }
     std::vector<u64> cuts(n_bins + 1);
     avk_partition_regions(batch, n_bins, cuts.data());
     std::vector<BinTotals> bts(n_bins);
-    std::vector<int> rcs(n_bins, AVK_OK);
-    std::vector<std::thread> th;
-    for (int l = 0; l < n_lanes; ++l)
-        th.emplace_back([&, l]() {
-            for (u32 k = (u32)l; k < n_bins; k += n_lanes) {
-                rcs[k] = compare_bin(lanes[l], batch, cuts[k], cuts[k + 1], cfg, out, bts[k]);
-                if (rcs[k] != AVK_OK) break;
-            }
-        });
-    for (auto &t : th) t.join();
-    for (u32 k = 0; k < n_bins; ++k)
-        if (rcs[k] != AVK_OK) { avk_ctx *l = lanes[k % n_lanes]; if (l != ctx) ctx->err = l->err; return rcs[k]; }
+    BinPending pend[2];
+    rc = AVK_OK;
+    avk_ctx *failed = nullptr;
+    const bool timing = getenv("AVK_TIMING") != nullptr;
+    const double t0 = timing ? host_ms() : 0;
+    for (u32 k = 0; k < n_bins + 2 && rc == AVK_OK; ++k) {
+        const double ta = timing ? host_ms() : 0;
+        if (k >= 2) { rc = bin_finish(lanes[k & 1], out, pend[k & 1], bts[k - 2]); if (rc != AVK_OK) failed = lanes[k & 1]; }
+        const double tb = timing ? host_ms() : 0;
+        if (rc == AVK_OK && k < n_bins) { rc = bin_enqueue(lanes[k & 1], batch, cuts[k], cuts[k + 1], cfg, out, pend[k & 1]); if (rc != AVK_OK) failed = lanes[k & 1]; }
+        if (timing) fprintf(stderr, "[avk] streamed step %u at %.2f ms: wait for bin k-2 %.2f ms (its device pass %.2f ms), enqueue bin k %.2f ms\n", k, ta - t0, tb - ta,
+                            k >= 2 ? lanes[k & 1]->last_ms[4] : 0.f, host_ms() - tb);
+    }
+    // leave the streamed mode (the resident entry points copy on the compute stream); on an error nothing may stay in flight
+    cudaStreamSynchronize(ctx->stream);
+    for (avk_ctx *l : lanes) {
+        cudaStreamSynchronize(l->up); cudaStreamSynchronize(l->dn);
+        l->up = l->dn = nullptr;
+    }
+    if (rc != AVK_OK) { if (failed && failed != ctx) ctx->err = failed->err; return rc; }
     const bool strata = strata_wanted(out);
     for (u32 k = 0; k < n_bins; ++k) store_totals(out, bts[k], strata, k > 0);
     return AVK_OK;
@@ -2080,11 +2327,14 @@ static int compare_pipelined(avk_ctx *ctx, const avk_region_batch *batch, const 
 extern "C" int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out) {
     if (!ctx) return AVK_ERR_INVALID;
     if (!batch) { ctx->err = "null batch"; return AVK_ERR_INVALID; }
-    if (ctx->pipe_bins >= 2 && batch->n_regions >= ctx->pipe_min_regions && !ctx->ref_owner) {
-        if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
-        const int rc = validate_batch(ctx, batch, true);
-        if (rc != AVK_OK) return rc;
-        return compare_pipelined(ctx, batch, cfg, out);
+    if (ctx->pipe_bins != 0 && ctx->pipe_bins != 1 && batch->n_regions >= ctx->pipe_min_regions && !ctx->ref_owner) {
+        const u64 n_bins = ctx->pipe_bins > 1 ? (u64)ctx->pipe_bins : std::min<u64>(16, (batch->n_regions + ctx->pipe_bin_regions / 2) / ctx->pipe_bin_regions);
+        if (n_bins >= 2) {
+            if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+            const int rc = validate_batch(ctx, batch, true);
+            if (rc != AVK_OK) return rc;
+            return compare_streamed(ctx, batch, cfg, out, (u32)n_bins);
+        }
     }
     return avk_compare_batch_range(ctx, batch, 0, batch->n_regions, cfg, out);
 }
@@ -2333,7 +2583,7 @@ extern "C" int avk_compare_upload_range(avk_ctx *ctx, const avk_region_batch *ba
     if (rc != AVK_OK) return rc;
     if (lo > hi || hi > batch->n_regions) { ctx->err = "region range outside the batch"; return AVK_ERR_INVALID; }
     BinScan sc;
-    rc = scan_bin(ctx, batch, lo, hi, sc);
+    rc = bin_range(ctx, batch, lo, hi, sc);
     if (rc != AVK_OK) return rc;
     rc = upload_batch(ctx, batch, sc);
     if (rc != AVK_OK) return rc;
@@ -2435,7 +2685,7 @@ extern "C" int avk_last_work(avk_ctx *ctx, avk_work_counters *out) {
 static int merge_bin(avk_ctx *ctx, const avk_region_batch *batch, u64 lo, u64 hi, const avk_merge_cfg *cfg, avk_merge_out *out) {
     CK(cudaSetDevice(ctx->device));
     BinScan sc;
-    int rc = scan_bin(ctx, batch, lo, hi, sc);
+    int rc = bin_range(ctx, batch, lo, hi, sc);
     if (rc != AVK_OK) return rc;
     rc = upload_batch(ctx, batch, sc);
     if (rc != AVK_OK) return rc;
@@ -2485,10 +2735,13 @@ static int merge_bin(avk_ctx *ctx, const avk_region_batch *batch, u64 lo, u64 hi
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    const cudaStream_t ds = ctx->stream;
     DL(out->status + lo, ctx->status, 4 * n);
     DL(out->classification ? out->classification + lo : nullptr, ctx->m_cls, n);
     DL(out->n_indices ? out->n_indices + lo : nullptr, ctx->m_nidx, n);
     DL(out->indices ? out->indices + lo * K : nullptr, ctx->m_idx, n * K);
+    CK(cudaMemcpyAsync(ctx->h_pin + 128, ctx->work_ctr.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_done, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return fetch_timings(ctx);
 }
@@ -2573,6 +2826,8 @@ extern "C" int avk_wfa_ed_batch(avk_ctx *ctx, uint64_t n_pairs, const uint8_t *p
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     ctx->have_result = false;
     CK(cudaMemcpyAsync(ed_out, ctx->pair_ed.p, 4 * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin + 128, ctx->work_ctr.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_done, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return fetch_timings(ctx);
 }

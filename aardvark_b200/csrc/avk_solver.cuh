@@ -21,6 +21,7 @@
 // lives in shared memory (one per warp); all arena accesses use Mem<SMEM> addresses.
 #pragma once
 #include "avk_device.cuh"
+#include "avk_spec_search.cuh"
 #include "avk_layout.h"
 
 namespace avk {
@@ -128,6 +129,8 @@ struct RegionSolver {
     u32 dyn_bytes;
     int Npad, seq_cap, wf_cap;
     int n_res, res_cap, n_slots;
+    int pre_scored;       // the results come from the speculative dense search WITH their exact-GT scoring: result 0 is the solution
+    u32 pre_keep[2];      //   and these are its exact-GT alleles per haplotype (bit = order entry keeps its ALT)
     int region_off;       // first arena byte after the header (+ staged window)
     int ed_overflow;
     u8 slot_type[AVK_N_VARIANT_TYPES];
@@ -1201,6 +1204,7 @@ struct RegionSolver {
     __device__ int compare_prepare(u64 r, const avk_compare_cfg &cfg, bool want_metrics);
     __device__ int compare_search_to_blob(u64 r, const avk_compare_cfg &cfg, u8 *blob);
     __device__ int compare_score_from_blob(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out, const u8 *blob);
+    __device__ int compare_score_from_dense(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out, const u8 *blob);
     __device__ int compare_score(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out);
     __device__ int merge_front(u64 r, const avk_merge_cfg &cfg, const struct MergeWork &w);
     __device__ int merge_pair(u64 r, u32 i, u32 j, const avk_merge_cfg &cfg, bool *exact);
@@ -1256,6 +1260,27 @@ __device__ int RegionSolver<SMEM>::compare_score_from_blob(u64 r, const avk_comp
     return compare_score(r, cfg, out);
 }
 
+// Score phase from the speculative dense search's blob (avk_spec_search.cuh: SPB_* layout): the equal-best results, or -- when
+// the blob says `scored` -- the one chosen solution with its exact-GT alleles, in which case compare_score goes straight to
+// the metrics.
+template <bool SMEM>
+__device__ int RegionSolver<SMEM>::compare_score_from_dense(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out, const u8 *blob) {
+    int rc = compare_prepare(r, cfg, true);
+    if (rc) return rc;
+    const int lane = lane_id();
+    const int nres = *(const int *)(blob + avk_sp::SPB_NRES);
+    if (nres > res_cap || N > avk_sp::SP_MAXN) return SOLVE_WORKSPACE;
+    const int n = N, npad = Npad;
+#pragma unroll 1
+    for (int i = lane; i < nres * n; i += 32) { const int ri = i / n, oi = i - ri * n; ST8(res_alle + (u32)(ri * npad + oi), blob[avk_sp::SPB_RES + ri * avk_sp::SPB_RES_STRIDE + oi]); }
+#pragma unroll 1
+    for (int i = lane; i < nres * 6; i += 32) { const int ri = i / 6, k = i - ri * 6; ST32(res_num + (u32)(ri * 24 + 4 * k), ((const int *)(blob + avk_sp::SPB_RES + ri * avk_sp::SPB_RES_STRIDE + avk_sp::SPB_ALLE))[k]); }
+    SOLVER_WRITE(n_res = nres; pre_scored = *(const int *)(blob + avk_sp::SPB_SCORED); pre_keep[0] = *(const u32 *)(blob + avk_sp::SPB_KEEP0); pre_keep[1] = *(const u32 *)(blob + avk_sp::SPB_KEEP1));
+    rc = compare_score(r, cfg, out);
+    SOLVER_WRITE(pre_scored = 0);
+    return rc;
+}
+
 // solve_compare_region(): returns AVK_ST_* (>= 0) or SOLVE_WORKSPACE
 template <bool SMEM>
 __device__ int RegionSolver<SMEM>::solve_compare(u64 r, const avk_compare_cfg &cfg, const DevCompareOut &out) {
@@ -1281,7 +1306,11 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
         for (int k = 0; k < 6; ++k) s += LDI(res_num + 4 * k);
         shortcut = s == 0;
     }
-    if (!shortcut) {
+    if (!shortcut && pre_scored) {                                          // scored by the speculative dense search: result 0 with these alleles
+#pragma unroll 1
+        for (int i = lane; i < 2 * n; i += 32) { const int h = i >= n ? 1 : 0, oi = i - h * n; ST8(best_obs + (u32)(h * npad + oi), ((pre_keep[h] >> oi) & 1u) ? AL_ALT : AL_REF); }
+        __syncwarp();
+    } else if (!shortcut) {
         // ---- exact-GT scoring of every equal-best solution; first minimum wins (:169-265).
         // A haplotype with ED 0 and nothing skipped scores 0 errors: the zero-flip path of optimize_gt_alleles replays
         // exactly the optimizer's tracker steps, stays alive, is popped first (fewest errors, most set alleles) and

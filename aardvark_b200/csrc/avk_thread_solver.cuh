@@ -40,6 +40,14 @@ extern __shared__ __align__(128) unsigned char avk_dyn_smem[];
 
 namespace avk_ts {
 
+#if defined(__CUDA_ARCH__)
+// unaligned 32-bit little-endian read through a generic pointer
+static __device__ __forceinline__ uint32_t ld4u_any(const uint8_t *p) {
+    const uint32_t *w = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], ((uint32_t)(uintptr_t)p & 3u) * 8u);
+}
+#endif
+
 typedef uint8_t u8;
 typedef uint16_t u16;
 typedef uint32_t u32;
@@ -183,35 +191,55 @@ struct Solver {
 #else
         const Work &W = *wp_;
 #endif
-        int cur = 0, ref_pos = 0, len = 0, m = 0, skip = 0, last_ok = 1, plen = 0, prp = 0;
+        // The tracker's ref_pos before entry i is max(end of the last spliced ALT, position of entry i): the entries are in
+        // position order and every entry's sync point is the next entry's position (query_optimizer.rs:258-265).  So an ALT
+        // of this side is compatible iff the last spliced ALT ends at or before it, entries that are not ALTs of this side
+        // change nothing, and the walk only visits the set bits of (mask & side).
+        int cur = 0, len = 0, m = 0, skip = 0, last_ok = 1, plen = 0, prp = 0, ref_pos = 0;
         const bool pieces = ps != nullptr;
         if (pieces) { ps->ls[0] = 0; ps->src[0] = 0; }
-        if (sp.side < 2) {
-            const bool want_truth = sp.side == 0;
-            const int depth = sp.depth;
+        const int depth = sp.side < 2 ? (int)sp.depth : 0;
+        if (depth > 0) {
             const u32 tmask = W.truth_mask;
-            for (int i = 0; i < depth; ++i) {
-                if (i == depth - 1) { plen = len + (ref_pos - cur); prp = ref_pos; }
-                if ((((tmask >> i) & 1u) != 0) == want_truth && ((sp.mask >> i) & 1)) {
-                    const VarInfo v = W.var[i];
-                    const int vpos = v.pos;
-                    if (ref_pos <= vpos) {                        // compatible (:189)
-                        if (m >= TS_MAXALT) return false;
-                        len += vpos - cur;
-                        if (pieces) { ps->ls[2 * m + 1] = (u16)len; ps->src[2 * m + 1] = (u16)(v.aoff + v.l0); }
-                        len += v.l1;
-                        cur = vpos + v.l0;
-                        if (pieces) { ps->ls[2 * m + 2] = (u16)len; ps->src[2 * m + 2] = (u16)cur; }
-                        m += 1;
-                        ref_pos = cur;
-                    } else {
-                        skip += v.alted;                          // edit_distance(allele0, allele1) (:199)
-                        if (i == depth - 1) last_ok = 0;
-                    }
+            const u32 side_bits = sp.side == 0 ? tmask : ~tmask;
+            const u32 last_bit = 1u << (depth - 1);
+            u32 bits = (u32)sp.mask & side_bits & (last_bit | (last_bit - 1u));
+            bool snap = false;
+            while (bits) {
+                const u32 low = bits & (0u - bits);
+                bits ^= low;
+#if defined(__CUDA_ARCH__)
+                const int i = __ffs((int)low) - 1;
+#else
+                const int i = __builtin_ctz(low);
+#endif
+                const VarInfo v = W.var[i];
+                const int vpos = v.pos;
+                if (low == last_bit) {                            // state before the last replayed entry (the parent's)
+                    prp = depth == 1 ? 0 : (cur > vpos ? cur : vpos);
+                    plen = len + (prp - cur);
+                    snap = true;
                 }
-                const int sy = (i == N - 1) ? wlen : (int)W.var[i + 1].pos;   // query_optimizer.rs:258-265
-                if (ref_pos < sy) ref_pos = sy;
+                if (cur <= vpos) {                                // compatible (haplotype_dwfa.rs:189)
+                    if (m >= TS_MAXALT) return false;
+                    len += vpos - cur;
+                    if (pieces) { ps->ls[2 * m + 1] = (u16)len; ps->src[2 * m + 1] = (u16)(v.aoff + v.l0); }
+                    len += v.l1;
+                    cur = vpos + v.l0;
+                    if (pieces) { ps->ls[2 * m + 2] = (u16)len; ps->src[2 * m + 2] = (u16)cur; }
+                    m += 1;
+                } else {
+                    skip += v.alted;                              // edit_distance(allele0, allele1) (:199)
+                    if (low == last_bit) last_ok = 0;
+                }
             }
+            if (!snap) {
+                const int lp = W.var[depth - 1].pos;
+                prp = depth == 1 ? 0 : (cur > lp ? cur : lp);
+                plen = len + (prp - cur);
+            }
+            const int sy = (depth == N) ? wlen : (int)W.var[depth].pos;   // sync point of the last entry
+            ref_pos = cur > sy ? cur : sy;
         }
         if ((sp.to_end || sp.side >= 2) && ref_pos < wlen) ref_pos = wlen;
         len += ref_pos - cur;
@@ -237,7 +265,16 @@ struct Solver {
             const u8 *pa = piece_ptr(A, ka, x), *pb = piece_ptr(B, kb, y);
             if (pa != pb) {                                   // same reference bytes otherwise: equal by construction
                 int j = 0;
+#if defined(__CUDA_ARCH__)
+                while (j < n) {                                   // four bases per step (unaligned words: two aligned loads + funnel shift;
+                    const u32 x = ld4u_any(pa + j) ^ ld4u_any(pb + j);   //  every buffer read here has >= 8 bytes of slack behind it)
+                    if (x) { j += (__ffs((int)x) - 1) >> 3; break; }
+                    j += 4;
+                }
+                if (j > n) j = n;
+#else
                 while (j < n && pa[j] == pb[j]) ++j;
+#endif
                 if (j < n) return total + j;
             }
             total += n; x += n; y += n;
@@ -766,11 +803,17 @@ struct Solver {
     // (ED == the length difference).  -1 otherwise.
     AVK_HD int closed_form(int side, u32 mask, u32 bits) const {
         const Work &W = w();
-        const bool want_truth = side == 0;
         int cur = 0, subm = 0, ins = 0, del = 0;
         bool open = false;
-        for (int i = 0; i < c.N; ++i) {
-            if (is_truth(i) != want_truth || !((mask >> i) & 1) || !((bits >> i) & 1)) continue;
+        u32 todo = mask & bits & (side == 0 ? (u32)W.truth_mask : ~(u32)W.truth_mask) & ((1u << c.N) - 1u);
+        while (todo) {
+            const u32 low = todo & (0u - todo);
+            todo ^= low;
+#if defined(__CUDA_ARCH__)
+            const int i = __ffs((int)low) - 1;
+#else
+            const int i = __builtin_ctz(low);
+#endif
             const VarInfo v = W.var[i];
             if ((int)v.pos < cur) continue;                                      // overlapping: skipped (:745-753)
             cur = v.pos + v.l0;

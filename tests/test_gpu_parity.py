@@ -663,3 +663,30 @@ def test_exact_gt_expansion_cap_timeout(solver):
     dflt = solver.compare_batch(batch, CompareConfig(enable_sequences=False))
     assert (dflt.status[:n] != abi.ST_TIMEOUT).all()
     assert dflt.diff(orc.compare_batch(batch, [ref], compare_cfg(CompareConfig(enable_sequences=False)))) == []
+
+
+def test_speculative_dense_search_vs_oracle():
+    """k_search_spec (32 queue pops in flight per dense cluster, lane-parallel exact-GT scoring) feeding the team stage: with
+    AVK_DENSE_N=3 every cluster of three or more variants takes that path; AVK_NO_SPEC_SEARCH=1 keeps the team stage's own
+    search covered.  Small max_branch_factor values exercise the quota-safe batch prefix."""
+    p = synth.SynthParams(n_variants=2500, dense_frac=0.9, dense_mean=6.0, het_frac=0.95, phased_frac=0.2, p_repr=0.05, p_gt_err=0.05, p_fn=0.05, p_fp=0.05)
+    dense_ref, dense = synth.workload_compare(50_000, p, seed=19)
+    chr_ref, chr_b = synth.workload_chr20(scale=0.02, seed=31)
+    for env in (dict(AVK_DENSE_N=3), dict(AVK_NO_SPEC_SEARCH=1)):
+        s = _solver_with_env(**env)
+        try:
+            for ref, batch in ((dense_ref, dense), (chr_ref, chr_b)):
+                s.set_reference([ref])
+                for mbf in (50, 3, 1):
+                    cfg = CompareConfig(enable_sequences=False, max_branch_factor=mbf)
+                    gpu = s.compare_batch(batch, cfg)
+                    cpu = orc.compare_batch(batch, [ref], compare_cfg(cfg))
+                    assert gpu.diff(cpu) == [], (env, mbf)
+            # sequence bundle requested: the search still runs speculatively, the team stage emits the sequences
+            s.set_reference([dense_ref])
+            cfg = CompareConfig(enable_sequences=True)
+            off, plen = seq_offsets(dense)
+            gpu, cpu = _both_compare(s, dense, [dense_ref], cfg, seq_off=off, seq_pool_len=plen)
+            assert gpu.diff(cpu) == [], env
+        finally:
+            s.close()
