@@ -394,7 +394,7 @@ __device__ __noinline__ void coop_dwfa_body_staged() {
             int boff = d + e - i;
             if (boff < la && d < lb) { const int ext = lcp_staged(sa, boff, la, sb, d, lb); d += ext; boff += ext; matched += ext; }
             nxt[i] = (unsigned short)d;
-            flag = flag || (to_full ? (boff >= la && d >= lb) : (boff >= la || d >= lb));
+            { const bool ra = boff >= la, rb = d >= lb; flag = flag | (to_full ? (ra & rb) : (ra | rb)); }
         }
         cells += n;
         stop = __syncthreads_or(flag);
@@ -409,10 +409,177 @@ __device__ __noinline__ void coop_dwfa_body_staged() {
     __syncthreads();
 }
 
+// ---- fastest path of the CTA-wide DWFA: 2-bit packed sequences, four diagonals per thread and trip ---------------------------------
+// When both sequences are plain upper-case ACGT (the reference compares raw bytes, dynamic_wfa.rs:118, so anything else --
+// N, IUPAC, soft-masked bases -- takes the byte path above) they are staged as 2 bits per base, 16 bases per word.  Layout
+// behind the job slot:  [A words + 2][B words + 2][2 pad][cur: cap16 u16][2 pad][nxt: cap16 u16]
+// A wavefront entry is stored as offset + 1 with 0 meaning "no diagonal", which turns the recurrence (dynamic_wfa.rs:152-168)
+// into three unconditional max operations: the two pad entries before and the zeroed entries behind a wavefront stand for
+// its missing neighbours.  A thread takes one contiguous run of diagonals, FOUR per trip: one 64-bit and one 32-bit shared load
+// bring the six old entries they depend on, one 64-bit store writes the four new ones; the extension of a diagonal compares 16
+// bases per step (two words per sequence, funnel shift to the base offset, XOR, find-first-set), and the four extensions are
+// independent, so their shared-memory latencies overlap.
+enum { PK_DIAGS = 4 };
+__device__ int g_avk_packed_dwfa = 0;   // AVK_PACKED_DWFA=1: take this path when the sequences allow it (off by default: measured slower
+                                        // than the byte-staged path on the wide-wavefront microbenchmark)
+__device__ __forceinline__ u32 pk_code4(u32 v, bool &bad) {      // four ASCII bases -> 8 bits; anything but ACGT sets bad
+    u32 out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const u32 c = (v >> (8 * k)) & 0xffu;
+        bad = bad || (c & 0xe0u) != 0x40u || !((0x0010008au >> (c & 31u)) & 1u);   // 'A' 0x41, 'C' 0x43, 'G' 0x47, 'T' 0x54
+        out |= ((c >> 1) & 3u) << (2 * k);
+    }
+    return out;
+}
+// stage the logical bases [0, len) of a virtual sequence, 16 per word (the tail of the last word and two slack words are zero)
+__device__ __forceinline__ bool coop_stage_packed(u32 *dst, const VSeq<false> &S) {
+    typedef Mem<false> M;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int words = (S.len + 15) >> 4;
+    bool bad = false;
+#pragma unroll 1
+    for (int wi = tid; wi < words + 2; wi += T) {
+        u32 w = 0;
+        if (wi < words) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int x = 16 * wi + 4 * q;
+                if (x >= S.len) break;
+                u32 v;
+                if (x + 4 <= S.mlen) v = ld4u<false>(S.data + x);
+                else if (x >= S.mlen && x + 4 <= S.len) v = ld4u<false>(S.tail + (x - S.mlen));
+                else { v = 0; for (int k = 0; k < 4; ++k) v |= (u32)(x + k < S.len ? LD8(S.at(x + k)) : (u8)'A') << (8 * k); }   // straddles the two pieces or the end
+                w |= pk_code4(v, bad) << (8 * q);
+            }
+        }
+        dst[wi] = w;
+    }
+    return bad;
+}
+// equal leading bases of A[ia..la) and B[ib..lb), ia < la && ib < lb
+__device__ __forceinline__ int lcp_packed(const u32 *pa, int ia, int la, const u32 *pb, int ib, int lb) {
+    const int maxn = min(la - ia, lb - ib);
+    int k = 0;
+#pragma unroll 1
+    for (;;) {
+        const int xa = ia + k, xb = ib + k;
+        const u32 a = __funnelshift_r(pa[xa >> 4], pa[(xa >> 4) + 1], 2 * (xa & 15));
+        const u32 b = __funnelshift_r(pb[xb >> 4], pb[(xb >> 4) + 1], 2 * (xb & 15));
+        const u32 x = a ^ b;
+        if (x) { k += (__ffs((int)x) - 1) >> 1; break; }
+        k += 16;
+        if (k >= maxn) break;
+    }
+    return min(k, maxn);
+}
+// shared-memory words the packed layout needs for wavefronts of `cap` entries each
+__device__ __forceinline__ long long coop_packed_bytes(int la, int lb, long long cap) {
+    return 4LL * (((la + 15) >> 4) + 2 + ((lb + 15) >> 4) + 2) + 2LL * (2 * (cap + 16) + 8);
+}
+__device__ __forceinline__ int coop_packed_cap16(int la, int lb, int cap_ints) {
+    long long cap = (8LL * cap_ints - 4LL * (((la + 15) >> 4) + ((lb + 15) >> 4) + 4) - 64) / 4 - 16;
+    cap = min(cap, 2LL * (64000 - lb));
+    cap &= ~7LL;
+    return (int)max(cap, 0LL);
+}
+// returns false (nothing done, every thread agrees) when a sequence holds anything but ACGT
+template <bool TO_FULL>
+__device__ __noinline__ bool coop_dwfa_body_packed() {
+    CoopJob &J = *(CoopJob *)avk_dyn_smem;
+    const int tid = threadIdx.x, T = blockDim.x;
+    VSeq<false> A, B;
+    A.data = J.a_data; A.tail = J.a_tail; A.mlen = J.a_mlen; A.len = J.a_len;
+    B.data = J.b_data; B.tail = J.b_tail; B.mlen = J.b_mlen; B.len = J.b_len;
+    const int la = A.len, lb = B.len, max_ed = J.max_ed;
+    u32 *pa = (u32 *)(avk_dyn_smem + COOP_JOB_BYTES);
+    u32 *pb = pa + ((la + 15) >> 4) + 2;
+    const int cap = coop_packed_cap16(la, lb, J.cap_ints);
+    // wavefront buffers: 16-byte aligned at entry 0, with 8 entries (only 2 are read) of zero padding in front
+    unsigned short *w0 = (unsigned short *)((((uintptr_t)(pb + ((lb + 15) >> 4) + 2)) + 15) & ~(uintptr_t)15) + 8;
+    unsigned short *w1 = w0 + cap + 16;
+    const int e_cap = (cap - 3) / 2;
+    int *gw = (int *)(uintptr_t)J.wf;
+    int e = J.ed, status = DWFA_OK;
+    bool bad = coop_stage_packed(pa, A);
+    bad = coop_stage_packed(pb, B) || bad;
+    if (__syncthreads_or(bad)) return false;
+    unsigned short *cur = w0, *nxt = w1;
+#pragma unroll 1
+    for (int i = tid; i < cap + 16; i += T) { w0[i - 8] = 0; w1[i - 8] = 0; }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = tid; i < 2 * e + 1; i += T) cur[i] = (unsigned short)(gw[i] + 1);
+    __syncthreads();
+    unsigned long long matched = 0, cells = 0;
+    bool flag = false;
+#pragma unroll 1
+    for (int i = tid; i < 2 * e + 1; i += T) {           // extend() of the wavefront as it stands
+        int d = (int)cur[i] - 1;
+        int boff = d + e - i;
+        if (boff < la && d < lb) { const int ext = lcp_packed(pa, boff, la, pb, d, lb); d += ext; boff += ext; matched += ext; cur[i] = (unsigned short)(d + 1); }
+        flag = flag || (TO_FULL ? (boff >= la && d >= lb) : (boff >= la || d >= lb));
+    }
+    cells += 2 * e + 1;
+    int stop = __syncthreads_or(flag);
+#pragma unroll 1
+    while (!stop) {
+        e += 1;
+        if (e > max_ed) { status = DWFA_MAX_ED; break; }                 // *ed stays incremented, wavefront not grown
+        if (e > e_cap) { status = DWFA_COOP_SPILL; e -= 1; break; }      // does not fit shared memory: back to the warp path
+        const int n = 2 * e + 1;
+        // every thread takes one contiguous run of diagonals, a multiple of PK_DIAGS long: the step ends with a barrier, so the
+        // runs must be as equal as they can be
+        const int per = (((n + T - 1) / T) + PK_DIAGS - 1) & ~(PK_DIAGS - 1);
+        const int i_end = min(n, (tid + 1) * per);
+        u32 reached = 0;
+#pragma unroll 1
+        for (int i0 = tid * per; i0 < i_end; i0 += PK_DIAGS) {
+            // old entries i0 - 2 .. i0 + 3 (stored + 1; 0 = absent: the pads in front, the zeroes behind the old wavefront)
+            const uint2 v = *(const uint2 *)(cur + i0);
+            const u32 p = *(const u32 *)(cur + i0 - 2);
+            u32 o[PK_DIAGS + 2];
+            o[0] = p & 0xffffu; o[1] = p >> 16;
+            o[2] = v.x & 0xffffu; o[3] = v.x >> 16; o[4] = v.y & 0xffffu; o[5] = v.y >> 16;
+            u32 r[PK_DIAGS];
+#pragma unroll
+            for (int j = 0; j < PK_DIAGS; ++j) {
+                // increase_edit_distance(): max(old[i], old[i - 1] + 1, old[i - 2] + 1) on the + 1 representation; an absent
+                // neighbour contributes 0 or 1, below every real entry
+                int d = (int)max(o[j + 2], max(o[j + 1], o[j]) + 1u) - 1;
+                int boff = d + e - (i0 + j);
+                const bool live = i0 + j < n;
+                if (live && boff < la && d < lb) { const int ext = lcp_packed(pa, boff, la, pb, d, lb); d += ext; boff += ext; matched += ext; }
+                const u32 ra = boff >= la, rb = d >= lb;
+                reached |= live ? (TO_FULL ? (ra & rb) : (ra | rb)) : 0u;
+                r[j] = live ? (u32)(d + 1) : 0u;
+            }
+            uint2 w;
+            w.x = r[0] | (r[1] << 16); w.y = r[2] | (r[3] << 16);
+            *(uint2 *)(nxt + i0) = w;
+        }
+        cells += n;
+        stop = __syncthreads_or(reached != 0u);
+        unsigned short *t = cur; cur = nxt; nxt = t;
+    }
+    const int n_out = 2 * (status == DWFA_MAX_ED ? e - 1 : e) + 1;
+#pragma unroll 1
+    for (int i = tid; i < n_out; i += T) gw[i] = (int)cur[i] - 1;
+    if (matched) atomicAdd(&J.matched, matched);
+    if (tid == 0) { J.ed = e; J.status = status; J.cells = cells; }
+    __threadfence_block();
+    __syncthreads();
+    return true;
+}
+
 // executed by every thread of the CTA; the job is in CoopJob at the start of dynamic shared memory
 __device__ __noinline__ void coop_dwfa_body() {
     CoopJob &J = *(CoopJob *)avk_dyn_smem;
-    // both sequences fit beside a 16-bit wavefront with room to grow: fast path
+    // plain ACGT on both sides and room for the wavefront to grow: 2-bit packed path (declines when it meets another byte)
+    if (g_avk_packed_dwfa && J.a_len < 64000 && J.b_len < 64000 && J.a_len > 0 && J.b_len > 0 && coop_packed_cap16(J.a_len, J.b_len, J.cap_ints) >= 2 * J.ed + 256) {
+        if (J.to_full ? coop_dwfa_body_packed<true>() : coop_dwfa_body_packed<false>()) return;
+    }
+    // both sequences fit beside a 16-bit wavefront with room to grow: byte-staged path
     if (J.a_len < 64000 && J.b_len < 64000 && coop_staged_cap16(J.a_len, J.b_len, J.cap_ints) >= 2 * J.ed + 256) { coop_dwfa_body_staged(); return; }
     int *cur = (int *)(avk_dyn_smem + COOP_JOB_BYTES), *nxt = cur + J.cap_ints;
     const int tid = threadIdx.x, T = blockDim.x;

@@ -68,7 +68,7 @@ struct PSeq {
 };
 struct Spec { u8 side, depth, to_end, pad; u32 mask; };
 struct SeqInfo { int len, ref_pos, skip, n_alt, last_ok, plen, prp; };
-enum { INIT_KEEP = 0, INIT_ZERO = 1, INIT_COPY = 2, INIT_CLOSED0 = 3 };
+enum { INIT_KEEP = 0, INIT_ZERO = 1, INIT_COPY = 2, INIT_CLOSED0 = 3, INIT_VALUE = 4 };
 enum { CH_NONE = 0, CH_RESULT = 1, CH_PUSH1 = 2, CH_FORK = 3, CH_REJECT = 4 };
 
 // what one chain hands to the commit
@@ -238,8 +238,9 @@ static AVK_HD_NOINLINE int lcp(const View &V, const PSeq &A, int la, int x, cons
 }
 
 // One alignment: build sequences a (baseline) and b (other), then DWFALite::update (dynamic_wfa.rs:68-84) if `update` and
-// finalize (:183-198) if `finalize` on wavefront buffer `buf`, initialised per `init`.  false: capacity exceeded.
-static AVK_HD_NOINLINE bool align(const View &V, Scratch &X, Counters &ctr, const Spec a, const Spec b, int buf, int init, int src, int ed_in,
+// finalize (:183-198) if `finalize` on the wavefront `wf`, initialised per `init` (INIT_COPY: from `swf`; INIT_VALUE: one
+// diagonal at v0).  Sequences are built in this lane's scratch; the wavefronts may live in another lane's.  false: capacity exceeded.
+static AVK_HD_NOINLINE bool align(const View &V, Scratch &X, Counters &ctr, const Spec a, const Spec b, u16 *wf, int init, const u16 *swf, int ed_in, int v0,
                                   bool update, bool finalize, int *ed_out, SeqInfo *ia_out, SeqInfo *ib_out) {
     const Shared &S = *V.S;
     SeqInfo ia, ib;
@@ -247,11 +248,11 @@ static AVK_HD_NOINLINE bool align(const View &V, Scratch &X, Counters &ctr, cons
     *ia_out = ia; *ib_out = ib;
     const PSeq &A = X.seq[0], &B = X.seq[1];
     const int la = ia.len, lb = ib.len;
-    u16 *wf = X.wf[buf];
     int ed = ed_in;
     if (init == INIT_ZERO) { wf[0] = 0; ed = 0; }
     else if (init == INIT_CLOSED0) { wf[0] = (u16)min_i(ia.plen, ib.plen); ed = 0; }   // parent had ED 0: its one diagonal stood at the end of its shorter sequence
-    else if (init == INIT_COPY) { const u16 *sw = X.wf[src]; for (int i = 0; i < 2 * ed + 1; ++i) wf[i] = sw[i]; }
+    else if (init == INIT_VALUE) { wf[0] = (u16)v0; ed = 0; }
+    else if (init == INIT_COPY) { for (int i = 0; i < 2 * ed + 1; ++i) wf[i] = swf[i]; }
     bool fin_pass = !update;
     for (;;) {
         const int n = 2 * ed + 1;
@@ -289,15 +290,59 @@ static AVK_HD_NOINLINE bool align(const View &V, Scratch &X, Counters &ctr, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// A chain is run by a GROUP of G = 1, 2 or 4 adjacent lanes (G = 32 / batch size, rounded down): every lane of the group
+// executes the chain's control flow on the same values, and where a pop needs several alignments that are independent of
+// each other -- the two parent wavefronts, then the two haplotypes of each child -- they are dealt out over the group's
+// lanes (job j to lane j mod G), each lane building its job's sequences in its own scratch, and the results are exchanged
+// with shuffles.  The group's wavefront buffers are the 3 G buffers of its lanes' scratch areas.
+struct Group {
+    int G, sub;            // lanes in the group, this lane's index in it
+    u32 mask;              // the group's lanes
+    int base;              // first lane of the group
+    Scratch *gs;           // scratch of the group's first lane (the others follow)
+};
+struct Job { Spec a, b; u16 *wf; const u16 *swf; int init, ed_in, v0; bool update, finalize; };
+struct JobRes { int ed, askip, bskip; bool ok; };
+static AVK_HD inline u16 *group_wf(const Group &g, int b) { return g.gs[b / 3].wf[b % 3]; }
+
+static AVK_HD inline void run_jobs(const View &V, const Group &g, Scratch &X, Counters &ctr, const Job *jobs, int nj, JobRes *res) {
+    for (int j = 0; j < nj; ++j) { res[j].ok = true; res[j].ed = 0; res[j].askip = 0; res[j].bskip = 0; }
+    for (int j = g.sub; j < nj; j += g.G) {                                     // (one trip for every lane of the group: they stay converged)
+        int ed = 0; SeqInfo ia, ib;
+        ia.skip = ib.skip = 0;
+        const Job &J = jobs[j];
+        res[j].ok = align(V, X, ctr, J.a, J.b, J.wf, J.init, J.swf, J.ed_in, J.v0, J.update, J.finalize, &ed, &ia, &ib);
+        res[j].ed = ed; res[j].askip = ia.skip; res[j].bskip = ib.skip;
+    }
+#if defined(__CUDA_ARCH__)
+    if (g.G > 1) {
+        __syncwarp(g.mask);                                                     // the wavefronts written above are read by other lanes' next jobs
+        for (int j = 0; j < nj; ++j) {
+            const int owner = g.base + j % g.G;
+            res[j].ed = __shfl_sync(g.mask, res[j].ed, owner);
+            res[j].askip = __shfl_sync(g.mask, res[j].askip, owner);
+            res[j].bskip = __shfl_sync(g.mask, res[j].bskip, owner);
+            res[j].ok = __shfl_sync(g.mask, (int)res[j].ok, owner) != 0;
+        }
+    }
+#endif
+}
+
 // One chain: the popped entry `e` (cost c = the minimum in the queue) and, for as long as it has a single child of the same
-// cost, that child.  Quota counters are read as they stood before the batch (see the file header).
-static AVK_HD_NOINLINE void run_chain(const View &V, Scratch &X, Counters &ctr, QEnt e, ChainOut &o) {
+// cost, that child.  Quota counters are read as they stood before the batch (see the file header).  Every lane of the group
+// returns the same ChainOut.
+static AVK_HD_NOINLINE void run_chain(const View &V, const Group &g, Scratch &X, Counters &ctr, QEnt e, ChainOut &o) {
     const Shared &S = *V.S;
     const int n = S.N;
     const u32 c = e.key >> 16;
     o.kind = CH_NONE; o.d_first = e.depth; o.n_counted = 0; o.pops = 0; o.rcost = 0;
-    int pb0 = 0, pb1 = 1, fb = 2;                                               // wavefront buffers: parent hap 0 / hap 1, free
+    // wavefront buffers (indices into the group's pool): parent hap 0 / hap 1, children [k][h].  A lone lane has three
+    // buffers: the children take the free one, and a single child's hap 1 the buffer hap 0's parent has just left.
+    int pb0 = 0, pb1 = 1, cb[2][2] = {{2, 2}, {2, 2}};
+    if (g.G > 1) { cb[0][0] = 2; cb[0][1] = 3; cb[1][0] = 4; cb[1][1] = 5; }
     bool have_wf = false;                                                       // the parent's wavefronts are in place (chain continuation)
+    Job jobs[4];
+    JobRes res[4];
     for (;;) {
         o.pops += 1;
         const int oi = e.depth;
@@ -307,31 +352,40 @@ static AVK_HD_NOINLINE void run_chain(const View &V, Scratch &X, Counters &ctr, 
         const int ped0 = e.ed1, ped1 = e.ed2;
         // wavefront of a parent haplotype with ED > 0: recomputed from scratch (path independence) unless this chain has just
         // computed it as its previous node's child
-        for (int h = 0; h < 2 && !have_wf; ++h) {
-            const int pe = h ? ped1 : ped0;
-            if (pe == 0) continue;
-            const u32 pm = h ? pm1 : pm0;
-            int ed; SeqInfo ia, ib;
-            if (!align(V, X, ctr, spec(0, pm, oi, false), spec(1, pm, oi, false), h ? pb1 : pb0, INIT_ZERO, 0, 0, true, false, &ed, &ia, &ib) || ed != pe) { o.kind = CH_REJECT; return; }
+        if (!have_wf) {
+            int nj = 0, exp_ed[2];
+            for (int h = 0; h < 2; ++h) {
+                const int pe = h ? ped1 : ped0;
+                if (pe == 0) continue;
+                const u32 pm = h ? pm1 : pm0;
+                Job &J = jobs[nj];
+                J.a = spec(0, pm, oi, false); J.b = spec(1, pm, oi, false); J.wf = group_wf(g, h ? pb1 : pb0); J.swf = nullptr;
+                J.init = INIT_ZERO; J.ed_in = 0; J.v0 = 0; J.update = true; J.finalize = false;
+                exp_ed[nj++] = pe;
+            }
+            if (nj) {
+                run_jobs(V, g, X, ctr, jobs, nj, res);
+                for (int j = 0; j < nj; ++j) if (!res[j].ok || res[j].ed != exp_ed[j]) { o.kind = CH_REJECT; return; }
+            }
         }
         if (oi == n) {                                                          // :227-247 finalize_dwfa (haplotype_dwfa.rs:84-95)
-            int fed[2], tsk[2], qsk[2];
             for (int h = 0; h < 2; ++h) {
                 const u32 pm = h ? pm1 : pm0;
                 const int pe = h ? ped1 : ped0;
+                Job &J = jobs[h];
+                J.a = spec(0, pm, n, true); J.b = spec(1, pm, n, true); J.wf = group_wf(g, h ? pb1 : pb0); J.swf = nullptr;
+                J.init = INIT_KEEP; J.ed_in = pe; J.v0 = 0; J.update = true; J.finalize = true;
                 if (pe == 0) {                                                  // closed-form parent diagonal: see PC_S_FINAL in avk_thread_solver.cuh
                     SeqInfo ti, qi;
                     if (!replay(S, nullptr, &ti, spec(0, pm, n, false)) || !replay(S, nullptr, &qi, spec(1, pm, n, false))) { o.kind = CH_REJECT; return; }
-                    X.wf[h ? pb1 : pb0][0] = (u16)min_i(ti.len, qi.len);
+                    J.init = INIT_VALUE; J.v0 = min_i(ti.len, qi.len);
                 }
-                int ed; SeqInfo ia, ib;
-                if (!align(V, X, ctr, spec(0, pm, n, true), spec(1, pm, n, true), h ? pb1 : pb0, INIT_KEEP, 0, pe, true, true, &ed, &ia, &ib)) { o.kind = CH_REJECT; return; }
-                if (ia.skip > 255 || ib.skip > 255 || ed > 255) { o.kind = CH_REJECT; return; }
-                fed[h] = ed; tsk[h] = ia.skip; qsk[h] = ib.skip;
             }
-            o.rcost = (u32)(fed[0] + fed[1] + tsk[0] + tsk[1] + qsk[0] + qsk[1]);
-            o.r.a1 = pm0; o.r.a2 = pm1; o.r.ed1 = (u8)fed[0]; o.r.ed2 = (u8)fed[1];
-            o.r.tvs1 = (u8)tsk[0]; o.r.tvs2 = (u8)tsk[1]; o.r.qvs1 = (u8)qsk[0]; o.r.qvs2 = (u8)qsk[1]; o.r.p0 = o.r.p1 = 0;
+            run_jobs(V, g, X, ctr, jobs, 2, res);
+            for (int h = 0; h < 2; ++h) if (!res[h].ok || res[h].askip > 255 || res[h].bskip > 255 || res[h].ed > 255) { o.kind = CH_REJECT; return; }
+            o.rcost = (u32)(res[0].ed + res[1].ed + res[0].askip + res[1].askip + res[0].bskip + res[1].bskip);
+            o.r.a1 = pm0; o.r.a2 = pm1; o.r.ed1 = (u8)res[0].ed; o.r.ed2 = (u8)res[1].ed;
+            o.r.tvs1 = (u8)res[0].askip; o.r.tvs2 = (u8)res[1].askip; o.r.qvs1 = (u8)res[0].bskip; o.r.qvs2 = (u8)res[1].bskip; o.r.p0 = o.r.p1 = 0;
             o.kind = CH_RESULT;
             return;
         }
@@ -340,35 +394,47 @@ static AVK_HD_NOINLINE void run_chain(const View &V, Scratch &X, Counters &ctr, 
         const bool het = (z == AVK_ZYG_UNPHASED_HET || z == AVK_ZYG_PHASED_HET01 || z == AVK_ZYG_PHASED_HET10);
         if (!het && z != AVK_ZYG_HOM_ALT) { o.kind = CH_REJECT; return; }       // assert_eq! :315 -> the team stage reports it
         const bool two = het && (!tr || z == AVK_ZYG_UNPHASED_HET);             // :269 both orientations, new ids
-        QEnt child[2];
-        for (int k = two ? 0 : 1; k < 2; ++k) {                                 // HaplotypeDWFA::extend_variant (haplotype_dwfa.rs:46-67)
+        // children: HaplotypeDWFA::extend_variant (haplotype_dwfa.rs:46-67) on both haplotypes of each
+        u32 cmask[2][2];
+        int nj = 0;
+        if (g.G == 1 && !two) { cb[1][0] = 3 - pb0 - pb1; cb[1][1] = pb0; }     // (three buffers: 0 + 1 + 2 == 3)
+        if (g.G == 1 && two) { cb[0][0] = cb[0][1] = cb[1][0] = cb[1][1] = 3 - pb0 - pb1; }
+        for (int k = two ? 0 : 1; k < 2; ++k) {
             bool a1, a2;
             if (two) { a1 = k == 1; a2 = k == 0; }                              // (REF, ALT) first, then (ALT, REF)
             else if (z != AVK_ZYG_HOM_ALT) { a1 = (z == AVK_ZYG_PHASED_HET10); a2 = !a1; }   // phased truth het :294-312
             else { a1 = true; a2 = true; }                                      // hom-alt :313-327
-            const u32 cm0 = pm0 | ((a1 ? 1u : 0u) << oi), cm1 = pm1 | ((a2 ? 1u : 0u) << oi);
-            int ccost = 0, ced[2];
-            // a single child's wavefronts are kept for the chain: hap 0 goes to the free buffer, hap 1 to the buffer hap 0's
-            // parent wavefront has just left; fork children (the chain ends with them) both use the free buffer
-            const int cb0 = fb, cb1 = two ? fb : pb0;
+            cmask[k][0] = pm0 | ((a1 ? 1u : 0u) << oi); cmask[k][1] = pm1 | ((a2 ? 1u : 0u) << oi);
             for (int h = 0; h < 2; ++h) {
-                const u32 cm = h ? cm1 : cm0;
                 const int pe = h ? ped1 : ped0;
-                int ed; SeqInfo ia, ib;
-                if (!align(V, X, ctr, spec(0, cm, oi + 1, false), spec(1, cm, oi + 1, false), h ? cb1 : cb0, pe == 0 ? INIT_CLOSED0 : INIT_COPY, h ? pb1 : pb0, pe, true, false, &ed, &ia, &ib)) { o.kind = CH_REJECT; return; }
-                ccost += ed + ia.skip + ib.skip;
-                ced[h] = ed;
+                Job &J = jobs[nj++];
+                J.a = spec(0, cmask[k][h], oi + 1, false); J.b = spec(1, cmask[k][h], oi + 1, false);
+                J.wf = group_wf(g, cb[k][h]); J.swf = group_wf(g, h ? pb1 : pb0);
+                J.init = pe == 0 ? INIT_CLOSED0 : INIT_COPY; J.ed_in = pe; J.v0 = 0; J.update = true; J.finalize = false;
             }
-            if (!two) { const int old1 = pb1; pb1 = cb1; pb0 = cb0; fb = old1; have_wf = true; }
-            if (ccost > 0xfffe || ced[0] > 255 || ced[1] > 255) { o.kind = CH_REJECT; return; }
+        }
+        if (g.G == 1) {
+            // a lone lane's jobs share buffers (hap 1 of a single child overwrites hap 0's parent wavefront, fork children reuse
+            // the free buffer): they run one after the other in this order, which is what makes that safe
+        }
+        run_jobs(V, g, X, ctr, jobs, nj, res);
+        QEnt child[2];
+        for (int k = two ? 0 : 1, q = 0; k < 2; ++k, ++q) {
+            const JobRes &r0 = res[2 * q], &r1 = res[2 * q + 1];
+            if (!r0.ok || !r1.ok) { o.kind = CH_REJECT; return; }
+            const int ccost = r0.ed + r0.askip + r0.bskip + r1.ed + r1.askip + r1.bskip;
+            if (ccost > 0xfffe || r0.ed > 255 || r1.ed > 255) { o.kind = CH_REJECT; return; }
             QEnt ne;
             ne.key = ((u32)ccost << 16) | (two ? 0u : (e.key & 0xffffu));       // fork children: id assigned by the commit
-            ne.a1 = cm0; ne.a2 = cm1; ne.depth = (u8)(oi + 1); ne.ed1 = (u8)ced[0]; ne.ed2 = (u8)ced[1]; ne.pad = 0;
+            ne.a1 = cmask[k][0]; ne.a2 = cmask[k][1]; ne.depth = (u8)(oi + 1); ne.ed1 = (u8)r0.ed; ne.ed2 = (u8)r1.ed; ne.pad = 0;
             child[k] = ne;
         }
         if (two) { o.c0 = child[0]; o.c1 = child[1]; o.kind = CH_FORK; return; }
         if ((child[1].key >> 16) != c) { o.c0 = child[1]; o.kind = CH_PUSH1; return; }
-        e = child[1];                                                           // same cost, same id: the reference pops it next
+        // same cost, same id: the reference pops it next; its wavefronts become the parent's
+        { const int t0 = pb0, t1 = pb1; pb0 = cb[1][0]; pb1 = cb[1][1]; if (g.G > 1) { cb[1][0] = t0; cb[1][1] = t1; } }
+        have_wf = true;
+        e = child[1];
     }
 }
 
@@ -699,7 +765,7 @@ static AVK_HD_NOINLINE bool metrics_walk(const View &V, Shared &S, bool collect)
 static AVK_HD_NOINLINE void metrics_align(const View &V, Scratch &X, Counters &ctr, MTask &m) {
     int ed = 0; SeqInfo ia, ib;
     const int n = V.S->N;
-    m.ok = align(V, X, ctr, spec(m.a_side, m.a_mask, n, true), spec(m.b_side, m.b_mask, n, true), 0, INIT_ZERO, 0, 0, false, true, &ed, &ia, &ib) ? 1 : 0;
+    m.ok = align(V, X, ctr, spec(m.a_side, m.a_mask, n, true), spec(m.b_side, m.b_mask, n, true), X.wf[0], INIT_ZERO, nullptr, 0, 0, false, true, &ed, &ia, &ib) ? 1 : 0;
     m.ed = (u32)ed;
 }
 
@@ -890,7 +956,16 @@ __device__ __noinline__ bool search_warp(Shared &S, Scratch &X, const View &V, C
     for (;;) {
         const int nb = select_batch_warp(S);
         if (nb == 0) break;
-        if (lane < nb) run_chain(V, X, ctr, S.batch[lane], S.out[lane]);
+        // a small batch leaves lanes free: groups of 2 or 4 lanes per chain share the alignments of each pop
+        Group g;
+        g.G = nb <= 8 ? 4 : (nb <= 16 ? 2 : 1);
+        g.sub = lane % g.G; g.base = lane - g.sub; g.mask = (g.G == 32 ? 0xffffffffu : ((1u << g.G) - 1u)) << g.base; g.gs = &X - g.sub;
+        const int chain = lane / g.G;
+        if (chain < nb) {
+            ChainOut o;
+            run_chain(V, g, X, ctr, S.batch[chain], o);
+            if (g.sub == 0) S.out[chain] = o;
+        }
         __syncwarp();
         bool ok = true;
         if (lane == 0) ok = commit_batch(S, nb);

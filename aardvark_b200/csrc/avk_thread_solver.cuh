@@ -56,6 +56,9 @@ using namespace avk;
 
 enum { TS_MAXN = 12, TS_EDCAP = 16, TS_QCAP = 16, TS_RESCAP = 8, TS_MAXALT = 6, TS_MAXP = 2 * TS_MAXALT + 1, TS_MAXSLOT = 4 };
 enum { TS_REJECT = -1 };   // >= 0: AVK_ST_*
+// A thread gives up on a cluster after this many queue pops (search + exact-GT): 32 clusters share a warp and a launch ends with
+// its slowest thread, so the rare long search is handed to the speculative solver (avk_spec_search.cuh), which pops 32 at a time.
+enum { TS_POP_BUDGET = 64 };
 enum { TS_WF = 2 * TS_EDCAP + 2 };
 // what the thread has to do next (outside advance / exec_task)
 enum { PH_FETCH = 0, PH_RUN = 1, PH_COMMIT = 2, PH_DONE = 3 };
@@ -150,6 +153,7 @@ struct Solver {
     Task task;
     int phase, pc;
     int rc;                        // status of the cluster when phase == PH_COMMIT (AVK_ST_* or TS_REJECT)
+    int pops_left;                 // TS_POP_BUDGET minus the queue pops of this cluster so far
     // optimize_sequences
     int qn, nres;
     u32 best, next_id;
@@ -367,10 +371,11 @@ struct Solver {
 
     // ================================================================== begin: load the cluster
     // leaves phase = PH_RUN with the workspace loaded, or PH_COMMIT with rc = an error status / TS_REJECT
-    AVK_HD void begin(const u8 *digest, const u8 *contig, int start, int end, int mbf, u32 xcap) {
+    AVK_HD void begin(const u8 *digest, const u8 *contig, int start, int end, int mbf, u32 xcap, int pop_budget = TS_POP_BUDGET) {
         const int *hdr = (const int *)digest;
         task.kind = TK_NONE;
         phase = PH_COMMIT;
+        pops_left = pop_budget;
         rc = hdr[PH_STATUS / 4];
         if (rc) return;
         rc = TS_REJECT;
@@ -446,6 +451,7 @@ struct Solver {
                 const QEnt e = W.q[bi];
                 W.q[bi] = W.q[--qn];
                 ctr->spops += 1;
+                if (--pops_left < 0) { stop(TS_REJECT); return; }               // a long search: not on a single thread
                 if ((e.key >> 16) > best) break;                                // :204 strict
                 if (W.bucket[e.depth] >= c.mbf) break;                          // :222
                 W.bucket[e.depth] += 1;
@@ -592,6 +598,7 @@ struct Solver {
                     const XEnt e = W.x[bi];
                     W.x[bi] = W.x[--xn];
                     ctr->xpops += 1;
+                    if (--pops_left < 0) { stop(TS_REJECT); return; }
                     x_errors = (int)(e.key >> 27);
                     if (x_errors >= budget && !have_best) errs = budget;         // nodes pop in non-decreasing error order
                     else if (x_errors >= best_err) break;                        // :169 non-strict

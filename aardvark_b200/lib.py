@@ -37,7 +37,7 @@ class AvkError(RuntimeError):
 
 def build(force=False, verbose=False):
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("avk_lib.cu", "avk_solver.cuh", "avk_device.cuh", "avk_layout.h", "avk_thread_solver.cuh")]
+    srcs = [os.path.join(CSRC, "avk_lib.cu")] + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     srcs.append(os.path.join(_HERE, "..", "include", "aardvark_b200.h"))
     if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= max(os.path.getmtime(s) for s in srcs):
         return SO_PATH

@@ -40,7 +40,7 @@ extern "C" int sp_search_batch(const avk_region_batch *b, const uint8_t *const *
             const int nb = select_batch_host(*S);
             if (nb == 0) break;
             stats[2] += 1; stats[3] += (uint64_t)nb; stats[5] = std::max<uint64_t>(stats[5], (uint64_t)nb);
-            for (int l = 0; l < nb; ++l) run_chain(V, X[l], ctr, S->batch[l], S->out[l]);
+            for (int l = 0; l < nb; ++l) { Group g; g.G = 1; g.sub = 0; g.mask = 1u << l; g.base = l; g.gs = &X[l]; run_chain(V, g, X[l], ctr, S->batch[l], S->out[l]); }
             if (!commit_batch(*S, nb)) { ok = false; break; }
         }
         if (!ok || S->nres == 0) { stats[1] += 1; continue; }
@@ -100,7 +100,7 @@ extern "C" int sp_solve_batch(const avk_region_batch *b, const uint8_t *const *c
         for (;;) {
             const int nb = select_batch_host(*S);
             if (nb == 0) break;
-            for (int l = 0; l < nb; ++l) run_chain(V, X[l], ctr, S->batch[l], S->out[l]);
+            for (int l = 0; l < nb; ++l) { Group g; g.G = 1; g.sub = 0; g.mask = 1u << l; g.base = l; g.gs = &X[l]; run_chain(V, g, X[l], ctr, S->batch[l], S->out[l]); }
             if (!commit_batch(*S, nb)) { ok = false; break; }
         }
         if (!ok || S->nres == 0) continue;

@@ -690,3 +690,45 @@ def test_speculative_dense_search_vs_oracle():
             assert gpu.diff(cpu) == [], env
         finally:
             s.close()
+
+
+def test_wfa_ed_cta_wide_paths_vs_oracle(solver):
+    """Long pairs through the CTA-wide DWFA (k_wfa_ed_cta), byte-staged (the default) and with the opt-in 2-bit packed path:
+    there plain ACGT pairs are packed 16 bases per word, while a single N, IUPAC code or soft-masked base anywhere in a pair
+    sends it down the byte-staged path -- the reference compares raw bytes (dynamic_wfa.rs:118).  Lengths around the 16-base word and 8-diagonal group boundaries,
+    one-sided empty tails, identical pairs, edit distances from 0 to a few thousand."""
+    rng = np.random.default_rng(77)
+    pairs = []
+    for i in range(60):
+        n = int(rng.integers(2500, 9000)) + (i % 17)
+        a = synth.ACGT[rng.integers(0, 4, size=n)]
+        kind = i % 6
+        if kind == 0:
+            b = a.copy()                                                       # identical
+        elif kind == 1:
+            b = a.copy(); idx = rng.integers(0, n, size=int(rng.integers(1, 60))); b[idx] = synth.ACGT[rng.integers(0, 4, size=idx.size)]
+        elif kind == 2:
+            c = int(rng.integers(0, n - 1500)); b = np.concatenate([a[:c], a[c + int(rng.integers(50, 1500)):]])          # deletion
+        elif kind == 3:
+            c = int(rng.integers(0, n)); b = np.concatenate([a[:c], synth.ACGT[rng.integers(0, 4, size=int(rng.integers(50, 1200)))], a[c:]])
+        elif kind == 4:
+            b = synth.ACGT[rng.integers(0, 4, size=int(rng.integers(2500, 4000)))]                                         # unrelated
+        else:
+            b = np.concatenate([a[int(rng.integers(1, 40)):], synth.ACGT[rng.integers(0, 4, size=int(rng.integers(0, 33)))]])   # shifted
+        a, b = a.copy(), b.copy()
+        if i % 4 == 1:
+            a[int(rng.integers(0, a.size))] = ord("N")
+        if i % 4 == 2:
+            k = int(rng.integers(0, b.size - 20)); b[k:k + 20] = np.frombuffer(bytes(b[k:k + 20]).lower(), dtype=np.uint8)
+        if i % 4 == 3 and i % 8 == 3:
+            b[-1] = ord("R")
+        pairs.append((a.tobytes(), b.tobytes()))
+    cpu = np.array([orc.wfa_ed(a, b) for a, b in pairs], dtype=np.uint32)
+    assert np.array_equal(solver.wfa_ed_batch(pairs), cpu)                    # default: byte-staged path for every pair
+    assert int(cpu.max()) > 1500 and int((cpu == 0).sum()) >= 2
+    s = _solver_with_env(AVK_PACKED_DWFA=1)                                   # opt-in 2-bit packed path (a device-wide switch set by avk_create)
+    try:
+        assert np.array_equal(s.wfa_ed_batch(pairs), cpu)
+    finally:
+        s.close()
+        Solver(0).close()                                                     # back to the default
