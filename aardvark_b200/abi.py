@@ -74,6 +74,15 @@ class CallSets(C.Structure):
     ]
 
 
+class BedIntervals(C.Structure):
+    _fields_ = [
+        ("n_contigs", C.c_uint32),
+        ("first", _u64p),
+        ("start", _u32p),
+        ("end", _u32p),
+    ]
+
+
 class CompareCfg(C.Structure):
     _fields_ = [
         ("max_branch_factor", C.c_uint32),

@@ -146,10 +146,12 @@ class CallSets:
     """K call sets of one contig as one variant table (avk_callsets): input k = variants [input_off[k], input_off[k+1]),
     each in VCF order.  Records are (position, allele0, allele1, zygosity code, type code, raw_allele_space)."""
 
-    def __init__(self, inputs):
+    def __init__(self, inputs, contigs=None):
+        """contigs: per input, the contig index of every record (several contigs in one table, avk_build_regions_bed)."""
         pos, vt, zy, raw, aoff, l0, l1 = [], [], [], [], [], [], []
         pool = bytearray()
         off = [0]
+        self.variant_contig = None if contigs is None else np.asarray([c for lst in contigs for c in lst], dtype=np.uint32)
         for lst in inputs:
             for (p_, a0, a1, z, t, rw) in lst:
                 pos.append(p_); vt.append(t); zy.append(z); raw.append(rw)
@@ -178,6 +180,21 @@ class CallSets:
             abi.ptr(self.raw_allele_space), abi.ptr(self.allele_off), abi.ptr(self.a0_len), abi.ptr(self.a1_len),
             abi.ptr(self.allele_pool), self.pool_len)
         return abi.CallSets(self.n_inputs, abi.ptr(self.input_off), vt)
+
+
+class BedIntervals:
+    """High-confidence intervals per contig (avk_bed_intervals): per_contig[c] = [(start, end), ...], 0-based half-open, sorted,
+    non-overlapping; one list per contig of the reference, in reference order."""
+
+    def __init__(self, per_contig):
+        self.n_contigs = len(per_contig)
+        self.first = np.asarray(np.cumsum([0] + [len(x) for x in per_contig]), dtype=np.uint64)
+        flat = [iv for lst in per_contig for iv in lst]
+        self.start = np.asarray([a for a, _ in flat] or [0], dtype=np.uint32)
+        self.end = np.asarray([b for _, b in flat] or [0], dtype=np.uint32)
+
+    def to_c(self) -> abi.BedIntervals:
+        return abi.BedIntervals(self.n_contigs, abi.ptr(self.first), abi.ptr(self.start), abi.ptr(self.end))
 
 
 class CompareOutputs:

@@ -25,6 +25,7 @@
 
 #include "avk_solver.cuh"
 #include "avk_thread_solver.cuh"
+#include "avk_writers.h"
 
 using namespace avk;
 
@@ -2408,31 +2409,52 @@ extern "C" int avk_compare_batch_multi(avk_ctx *const *ctxs, uint32_t n_ctx, con
 // A variant closes the open cluster iff its position reaches the running maximum of (pos + ref_len + flank) -- and the
 // maximum over ALL earlier variants equals the maximum inside the open cluster whenever that comparison matters (every
 // earlier cluster ended at or before the position that opened this one), so one exclusive max-scan gives the breaks.
-struct MaxOp { __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a > b ? a : b; } };
+struct MaxOp64 { __device__ __forceinline__ u64 operator()(u64 a, u64 b) const { return a > b ? a : b; } };
 
-__global__ void __launch_bounds__(256) k_rb_keys(u64 nv, const u32 *pos, const u32 *l0, u64 contig_len, u32 *key, u32 *idx) {
+// Sort key (contig << 32 | position) of every variant that lies fully inside one BED interval of its contig (0-based half-open,
+// sorted, non-overlapping): get_variant_containment (:796-812) against the first interval that ends behind the variant's
+// start -- for every earlier interval the variant is After, and Before / Overlapping variants are consumed without being used
+// (:388-391, :438-442).  Everything else gets the key ~0 and sorts to the end.  ivl[i] = 1 + global index of the interval.
+__global__ void __launch_bounds__(256) k_rb_keys(u64 nv, const u32 *pos, const u32 *l0, const u32 *vcontig, u32 contig0, const u64 *contig_len, u32 n_contigs,
+                                                 const u64 *ifirst, const u32 *istart, const u32 *iend, u64 *key, u32 *idx, u32 *ivl) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nv) return;
     idx[i] = (u32)i;
-    key[i] = ((u64)pos[i] + l0[i] > contig_len) ? 0xffffffffu : pos[i];       // not fully contained: dropped (:551), sorted to the end
+    const u32 c = vcontig ? vcontig[i] : contig0;
+    u64 k = ~0ull;
+    u32 tag = 0;
+    if (c < n_contigs && (u64)pos[i] + l0[i] <= contig_len[c]) {              // fully inside the contig (:551 against the full region)
+        if (!ifirst) { k = ((u64)c << 32) | pos[i]; tag = 1 + c; }            // no BED: one interval spanning each contig
+        else {
+            u64 lo = ifirst[c], hi = ifirst[c + 1];
+            const u64 end_c = hi;
+            while (lo < hi) { const u64 m = (lo + hi) >> 1; if (iend[m] <= pos[i]) lo = m + 1; else hi = m; }   // first interval with end > pos
+            if (lo < end_c && pos[i] >= istart[lo] && (u64)pos[i] + l0[i] <= iend[lo]) { k = ((u64)c << 32) | pos[i]; tag = 1 + (u32)lo; }
+        }
+    }
+    key[i] = k; ivl[i] = tag;
 }
-__global__ void __launch_bounds__(256) k_rb_vend(u64 nv, const u32 *key, const u32 *idx, const u32 *l0, u64 contig_len, u32 flank,
-                                                 u32 *vend, unsigned long long *n_valid) {
+// per sorted variant: (interval tag << 32 | window end it asks for); the exclusive running maximum of these is, inside one
+// interval, the open cluster's window end (intervals come in increasing tag order, so a later interval's entries always win)
+__global__ void __launch_bounds__(256) k_rb_vend(u64 nv, const u64 *key, const u32 *idx, const u32 *l0, const u32 *ivl, const u64 *contig_len, u32 flank,
+                                                 u64 *vend, unsigned long long *n_valid) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nv) return;
-    const bool valid = key[i] != 0xffffffffu;
-    vend[i] = valid ? (u32)min((u64)key[i] + l0[idx[i]] + flank, contig_len) : 0u;                 // :411-429
-    if (valid && (i + 1 == nv || key[i + 1] == 0xffffffffu)) *n_valid = i + 1;
+    const bool valid = key[i] != ~0ull;
+    const u32 p = (u32)key[i], c = (u32)(key[i] >> 32);
+    vend[i] = valid ? (((u64)ivl[idx[i]] << 32) | (u32)min((u64)p + l0[idx[i]] + flank, contig_len[c])) : 0ull;   // :411-429
+    if (valid && (i + 1 == nv || key[i + 1] == ~0ull)) *n_valid = i + 1;
     if (i == 0 && !valid) *n_valid = 0;
 }
-__global__ void __launch_bounds__(256) k_rb_flags(u64 nv, const u32 *key, const u32 *pmax, u32 *flag) {
+__global__ void __launch_bounds__(256) k_rb_flags(u64 nv, const u64 *key, const u64 *vend, const u64 *pmax, u32 *flag) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nv) return;
-    flag[i] = (key[i] != 0xffffffffu && key[i] >= pmax[i]) ? 1u : 0u;         // pos >= window_end opens a new cluster (:396-409)
+    // a new cluster: first variant of its interval (:379-383 fresh window per interval), or pos >= window_end (:396-409)
+    flag[i] = (key[i] != ~0ull && ((pmax[i] >> 32) != (vend[i] >> 32) || (u32)key[i] >= (u32)pmax[i])) ? 1u : 0u;
 }
 // per sorted variant: cluster id, grouping key (cluster, input); per cluster: window and ids
-__global__ void __launch_bounds__(256) k_rb_clusters(u64 nvalid, const u32 *key, const u32 *idx, const u32 *cid1, const u32 *flag,
-                                                     const u32 *pmax, const u32 *vend, const u64 *input_off, u32 K, u32 flank, u32 contig,
+__global__ void __launch_bounds__(256) k_rb_clusters(u64 nvalid, const u64 *key, const u32 *idx, const u32 *cid1, const u32 *flag,
+                                                     const u64 *pmax, const u64 *vend, const u64 *input_off, u32 K, u32 flank,
                                                      u64 first_region_id, u64 *key2, u64 *region_id, u32 *rcontig, u32 *start, u32 *end) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nvalid) return;
@@ -2440,8 +2462,12 @@ __global__ void __launch_bounds__(256) k_rb_clusters(u64 nvalid, const u32 *key,
     u32 k = 0;
     while (k + 1 < K && input_off[k + 1] <= idx[i]) ++k;
     key2[i] = (u64)c * K + k;
-    if (flag[i]) { start[c] = key[i] > flank ? key[i] - flank : 0u; region_id[c] = first_region_id + c; rcontig[c] = contig; }
-    if (i + 1 == nvalid || flag[i + 1]) end[c] = max(pmax[i], vend[i]);      // running maximum at the cluster's last variant
+    const u32 p = (u32)key[i];
+    if (flag[i]) { start[c] = p > flank ? p - flank : 0u; region_id[c] = first_region_id + c; rcontig[c] = (u32)(key[i] >> 32); }
+    if (i + 1 == nvalid || flag[i + 1]) {                                     // running maximum at the cluster's last variant (same interval only)
+        const u32 own = (u32)vend[i], before = (pmax[i] >> 32) == (vend[i] >> 32) ? (u32)pmax[i] : 0u;
+        end[c] = max(own, before);
+    }
 }
 __global__ void __launch_bounds__(256) k_rb_varoff(u64 n_seg, u64 nvalid, const u64 *key2_sorted, u64 *var_off) {
     const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2469,22 +2495,62 @@ __global__ void __launch_bounds__(256) k_rb_alleles(u64 nvalid, const u32 *perm,
     }
 }
 
+static int build_regions_impl(avk_ctx *ctx, const avk_callsets *in, const uint32_t *variant_contig, uint32_t contig, const avk_bed_intervals *bed,
+                              uint32_t flank, uint64_t first_region_id, uint64_t *n_regions_out, uint64_t *n_variants_out);
 extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t contig, uint32_t flank, uint64_t first_region_id,
                                  uint64_t *n_regions_out, uint64_t *n_variants_out) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (contig >= ctx->contig_lens.size()) { ctx->err = "avk_build_regions: unknown contig (call avk_set_reference first)"; return AVK_ERR_INVALID; }
+    return build_regions_impl(ctx, in, nullptr, contig, nullptr, flank, first_region_id, n_regions_out, n_variants_out);
+}
+extern "C" int avk_build_regions_bed(avk_ctx *ctx, const avk_callsets *in, const uint32_t *variant_contig, const avk_bed_intervals *bed,
+                                     uint32_t flank, uint64_t first_region_id, uint64_t *n_regions_out, uint64_t *n_variants_out) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!variant_contig) { ctx->err = "avk_build_regions_bed: null variant_contig"; return AVK_ERR_INVALID; }
+    if (bed) {
+        if (bed->n_contigs != ctx->contig_lens.size() || !bed->first || (bed->first[bed->n_contigs] && (!bed->start || !bed->end))) {
+            ctx->err = "avk_build_regions_bed: the interval table must cover the reference's contigs";
+            return AVK_ERR_INVALID;
+        }
+        for (uint32_t c = 0; c < bed->n_contigs; ++c) {
+            if (bed->first[c] > bed->first[c + 1]) { ctx->err = "avk_build_regions_bed: interval offsets are not monotone"; return AVK_ERR_INVALID; }
+            for (uint64_t j = bed->first[c]; j < bed->first[c + 1]; ++j)
+                if (bed->start[j] > bed->end[j] || (j > bed->first[c] && bed->start[j] < bed->end[j - 1])) {
+                    ctx->err = "avk_build_regions_bed: intervals must be sorted and non-overlapping within a contig";
+                    return AVK_ERR_INVALID;
+                }
+        }
+        if (bed->first[bed->n_contigs] >= 0xfffffffeull) { ctx->err = "avk_build_regions_bed: too many intervals"; return AVK_ERR_INVALID; }
+    }
+    return build_regions_impl(ctx, in, variant_contig, 0, bed, flank, first_region_id, n_regions_out, n_variants_out);
+}
+static int build_regions_impl(avk_ctx *ctx, const avk_callsets *in, const uint32_t *variant_contig, uint32_t contig, const avk_bed_intervals *bed,
+                              uint32_t flank, uint64_t first_region_id, uint64_t *n_regions_out, uint64_t *n_variants_out) {
     if (!ctx || !in || !n_regions_out || !n_variants_out || in->n_inputs == 0 || !in->input_off) return AVK_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    if (contig >= ctx->contig_lens.size()) { ctx->err = "avk_build_regions: unknown contig (call avk_set_reference first)"; return AVK_ERR_INVALID; }
+    if (ctx->contig_lens.empty()) { ctx->err = "avk_build_regions: avk_set_reference has not been called"; return AVK_ERR_NO_REFERENCE; }
     const avk_variant_table &t = in->variants;
-    const u64 nv = t.n_variants, K = in->n_inputs, contig_len = ctx->contig_lens[contig];
+    const u64 nv = t.n_variants, K = in->n_inputs;
+    const u32 n_contigs = (u32)ctx->contig_lens.size();
     if (in->input_off[K] != nv || nv >= 0xffffffffull || t.allele_pool_len >= 0xffffffffull) { ctx->err = "avk_build_regions: bad call-set table"; return AVK_ERR_INVALID; }
-    if (contig_len > 0xffffffffull) { ctx->err = "avk_build_regions: contig longer than 2^32 - 1 bases"; return AVK_ERR_INVALID; }
-    enum { T_POS, T_VT, T_ZY, T_RAW, T_AOFF, T_L0, T_L1, T_POOL, T_KEY, T_IDX, T_KEY_S, T_IDX_S, T_VEND, T_PMAX, T_FLAG, T_CID, T_KEY2, T_KEY2_S, T_PERM, T_MISC };
+    for (u64 len : ctx->contig_lens) if (len > 0xffffffffull) { ctx->err = "avk_build_regions: contig longer than 2^32 - 1 bases"; return AVK_ERR_INVALID; }
+    enum { T_POS, T_VT, T_ZY, T_RAW, T_AOFF, T_L0, T_L1, T_POOL, T_KEY, T_IDX, T_KEY_S, T_IDX_S, T_VEND, T_PMAX, T_FLAG, T_CID, T_KEY2, T_KEY2_S, T_PERM, T_MISC, T_VCONTIG, T_IVL, T_IFIRST, T_ISTART };
     DevBuf *rb = ctx->rb;
     UPLOAD(rb[T_POS], t.position, 4 * nv); UPLOAD(rb[T_VT], t.variant_type, nv); UPLOAD(rb[T_ZY], t.zygosity, nv);
     UPLOAD(rb[T_RAW], t.raw_allele_space, 4 * nv); UPLOAD(rb[T_AOFF], t.allele_off, 4 * nv); UPLOAD(rb[T_L0], t.a0_len, 4 * nv);
     UPLOAD(rb[T_L1], t.a1_len, 4 * nv); UPLOAD(rb[T_POOL], t.allele_pool, t.allele_pool_len);
-    for (int b : {T_KEY, T_IDX, T_KEY_S, T_IDX_S, T_VEND, T_PMAX, T_FLAG, T_CID, T_PERM}) ENSURE(rb[b], 4 * nv);
-    ENSURE(rb[T_KEY2], 8 * nv); ENSURE(rb[T_KEY2_S], 8 * nv);
+    for (int b : {T_IDX, T_IDX_S, T_FLAG, T_CID, T_PERM, T_IVL}) ENSURE(rb[b], 4 * nv);
+    for (int b : {T_KEY, T_KEY_S, T_VEND, T_PMAX, T_KEY2, T_KEY2_S}) ENSURE(rb[b], 8 * nv);
+    if (variant_contig) UPLOAD(rb[T_VCONTIG], variant_contig, 4 * nv);
+    const u64 n_ivl = bed ? bed->first[bed->n_contigs] : 0;
+    if (bed) {
+        UPLOAD(rb[T_IFIRST], bed->first, 8 * ((u64)n_contigs + 1));
+        ENSURE(rb[T_ISTART], 8 * n_ivl + 16);
+        if (n_ivl) {
+            CK(cudaMemcpyAsync(rb[T_ISTART].p, bed->start, 4 * n_ivl, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync((u32 *)rb[T_ISTART].p + n_ivl, bed->end, 4 * n_ivl, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
     ENSURE(rb[T_MISC], 8 * (K + 1) + 64);
     u64 *d_input_off = (u64 *)rb[T_MISC].p;
     unsigned long long *d_nvalid = (unsigned long long *)((u8 *)rb[T_MISC].p + 8 * (K + 1));
@@ -2505,21 +2571,26 @@ extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t 
     *n_regions_out = 0; *n_variants_out = 0;
     if (nv == 0) { ctx->n_regions = 0; ctx->n_variants = 0; ctx->n_inputs = (u32)K; ctx->max_allele = 1; ctx->pool_len = 0; ctx->have_batch = true; ENSURE(ctx->var_off, 8); CK(cudaMemsetAsync(ctx->var_off.p, 0, 8, ctx->stream)); return AVK_OK; }
     const unsigned g = (unsigned)((nv + 255) / 256);
-    u32 *key = (u32 *)rb[T_KEY].p, *idx = (u32 *)rb[T_IDX].p, *key_s = (u32 *)rb[T_KEY_S].p, *idx_s = (u32 *)rb[T_IDX_S].p;
-    u32 *vend = (u32 *)rb[T_VEND].p, *pmax = (u32 *)rb[T_PMAX].p, *flag = (u32 *)rb[T_FLAG].p, *cid = (u32 *)rb[T_CID].p, *perm = (u32 *)rb[T_PERM].p;
+    u64 *key = (u64 *)rb[T_KEY].p, *key_s = (u64 *)rb[T_KEY_S].p, *vend = (u64 *)rb[T_VEND].p, *pmax = (u64 *)rb[T_PMAX].p;
+    u32 *idx = (u32 *)rb[T_IDX].p, *idx_s = (u32 *)rb[T_IDX_S].p, *flag = (u32 *)rb[T_FLAG].p, *cid = (u32 *)rb[T_CID].p, *perm = (u32 *)rb[T_PERM].p, *ivl = (u32 *)rb[T_IVL].p;
+    const u64 *d_clen = (const u64 *)ctx->d_contig_len.p;
+    int key_bits = 33;
+    while (key_bits < 64 && (1ull << (key_bits - 32)) < (u64)n_contigs + 1) ++key_bits;     // (contig << 32 | pos); ~0 keys sort last within these bits
     u64 *key2 = (u64 *)rb[T_KEY2].p, *key2_s = (u64 *)rb[T_KEY2_S].p;
     const u32 *pos = (const u32 *)rb[T_POS].p, *l0 = (const u32 *)rb[T_L0].p;
     size_t tmp = 0, need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, key, key_s, idx, idx_s, (int)nv, 0, 32, ctx->stream); tmp = std::max(tmp, need);
+    cub::DeviceRadixSort::SortPairs(nullptr, need, key, key_s, idx, idx_s, (int)nv, 0, 64, ctx->stream); tmp = std::max(tmp, need);
     cub::DeviceRadixSort::SortPairs(nullptr, need, key2, key2_s, idx_s, perm, (int)nv, 0, 64, ctx->stream); tmp = std::max(tmp, need);
-    cub::DeviceScan::ExclusiveScan(nullptr, need, vend, pmax, MaxOp(), 0u, (int)nv, ctx->stream); tmp = std::max(tmp, need);
+    cub::DeviceScan::ExclusiveScan(nullptr, need, vend, pmax, MaxOp64(), 0ull, (int)nv, ctx->stream); tmp = std::max(tmp, need);
     cub::DeviceScan::InclusiveSum(nullptr, need, flag, cid, (int)nv, ctx->stream); tmp = std::max(tmp, need);
     ENSURE(ctx->scan_tmp, tmp);
-    k_rb_keys<<<g, 256, 0, ctx->stream>>>(nv, pos, l0, contig_len, key, idx);
-    need = tmp; cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, need, key, key_s, idx, idx_s, (int)nv, 0, 32, ctx->stream);   // stable: ties keep input then list order (:352-373)
-    k_rb_vend<<<g, 256, 0, ctx->stream>>>(nv, key_s, idx_s, l0, contig_len, flank, vend, d_nvalid);
-    need = tmp; cub::DeviceScan::ExclusiveScan(ctx->scan_tmp.p, need, vend, pmax, MaxOp(), 0u, (int)nv, ctx->stream);
-    k_rb_flags<<<g, 256, 0, ctx->stream>>>(nv, key_s, pmax, flag);
+    k_rb_keys<<<g, 256, 0, ctx->stream>>>(nv, pos, l0, variant_contig ? (const u32 *)rb[T_VCONTIG].p : nullptr, contig, d_clen, n_contigs,
+                                          bed ? (const u64 *)rb[T_IFIRST].p : nullptr, (const u32 *)rb[T_ISTART].p, (const u32 *)rb[T_ISTART].p + n_ivl, key, idx, ivl);
+    (void)key_bits;
+    need = tmp; cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, need, key, key_s, idx, idx_s, (int)nv, 0, 64, ctx->stream);   // stable: ties keep input then list order (:352-373)
+    k_rb_vend<<<g, 256, 0, ctx->stream>>>(nv, key_s, idx_s, l0, ivl, d_clen, flank, vend, d_nvalid);
+    need = tmp; cub::DeviceScan::ExclusiveScan(ctx->scan_tmp.p, need, vend, pmax, MaxOp64(), 0ull, (int)nv, ctx->stream);
+    k_rb_flags<<<g, 256, 0, ctx->stream>>>(nv, key_s, vend, pmax, flag);
     need = tmp; cub::DeviceScan::InclusiveSum(ctx->scan_tmp.p, need, flag, cid, (int)nv, ctx->stream);
     unsigned long long nvalid = 0;
     CK(cudaMemcpyAsync(&nvalid, d_nvalid, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2534,11 +2605,11 @@ extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t 
     ENSURE(ctx->alt_ed, 4 * nvalid);
     if (nvalid) {
         const unsigned gv = (unsigned)((nvalid + 255) / 256);
-        k_rb_clusters<<<gv, 256, 0, ctx->stream>>>(nvalid, key_s, idx_s, cid, flag, pmax, vend, d_input_off, (u32)K, flank, contig, first_region_id,
+        k_rb_clusters<<<gv, 256, 0, ctx->stream>>>(nvalid, key_s, idx_s, cid, flag, pmax, vend, d_input_off, (u32)K, flank, first_region_id,
                                                    key2, (u64 *)ctx->region_id.p, (u32 *)ctx->contig.p, (u32 *)ctx->start.p, (u32 *)ctx->end.p);
         need = tmp; cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, need, key2, key2_s, idx_s, perm, (int)nvalid, 0, 64, ctx->stream);   // stable regroup: (cluster, input)
         k_rb_varoff<<<(unsigned)((n * K + 1 + 255) / 256), 256, 0, ctx->stream>>>(n * K, nvalid, key2_s, (u64 *)ctx->var_off.p);
-        u32 *alen = vend;   // reuse
+        u32 *alen = (u32 *)vend;   // reuse
         k_rb_gather<<<gv, 256, 0, ctx->stream>>>(nvalid, perm, pos, (const u8 *)rb[T_VT].p, (const u8 *)rb[T_ZY].p, (const u32 *)rb[T_RAW].p, l0,
                                                  (const u32 *)rb[T_L1].p, (u32 *)ctx->pos.p, (u8 *)ctx->vtype.p, (u8 *)ctx->zyg.p, (u32 *)ctx->raw.p,
                                                  (u32 *)ctx->l0.p, (u32 *)ctx->l1.p, alen);
@@ -2554,7 +2625,7 @@ extern "C" int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t 
     if (nvalid) {
         u32 last[2] = {0, 0};
         CK(cudaMemcpyAsync(&last[0], (u32 *)ctx->aoff.p + (nvalid - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(&last[1], vend + (nvalid - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));   // alen (vend reused)
+        CK(cudaMemcpyAsync(&last[1], (u32 *)vend + (nvalid - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));   // alen (vend reused)
         CK(cudaStreamSynchronize(ctx->stream));
         kept_bytes = (u64)last[0] + last[1];
     }
@@ -2853,4 +2924,25 @@ extern "C" int avk_compare_seq_offsets(const avk_region_batch *b, uint64_t *seq_
     seq_off[b->n_regions * 5] = off;
     if (pool_len) *pool_len = off;
     return AVK_OK;
+}
+
+// ---- writers: host-side formatting of what the kernels counted -----------------------------------------
+static int copy_text(const std::string &txt, char *buf, uint64_t cap, uint64_t *len) {
+    if (len) *len = txt.size();
+    if (!buf) return AVK_OK;                                        // size query
+    if (cap < txt.size()) return AVK_ERR_INVALID;
+    memcpy(buf, txt.data(), txt.size());
+    return AVK_OK;
+}
+extern "C" int avk_summary_write(const uint64_t *totals, const uint8_t *metrics, uint32_t n_metrics, const char *compare_label, const char *region_label,
+                                 int csv, int header, char *buf, uint64_t cap, uint64_t *len) {
+    if (!totals || (!metrics && n_metrics) || !compare_label || !region_label) return AVK_ERR_INVALID;
+    return copy_text(avk_writers::summary_text(totals, metrics, n_metrics, compare_label, region_label, csv ? ',' : '\t', header != 0), buf, cap, len);
+}
+extern "C" int avk_vcf_records_write(const avk_region_batch *batch, uint32_t side, const char *const *contig_names, uint32_t n_contigs,
+                                     const uint8_t *var_class, const uint8_t *var_expected, const uint8_t *var_observed, uint64_t lo, uint64_t hi,
+                                     char *buf, uint64_t cap, uint64_t *len) {
+    if (!batch || !contig_names || !var_class || !var_expected || !var_observed || side >= batch->n_inputs || lo > hi || hi > batch->n_regions) return AVK_ERR_INVALID;
+    for (uint64_t r = lo; r < hi; ++r) if (batch->contig[r] >= n_contigs) return AVK_ERR_INVALID;
+    return copy_text(avk_writers::vcf_records_text(batch, side, contig_names, var_class, var_expected, var_observed, lo, hi), buf, cap, len);
 }

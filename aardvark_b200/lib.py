@@ -75,6 +75,8 @@ def load():
     if hasattr(lib, "avk_build_regions"):   # (older builds used for A/B timing do not have the region builder)
         lib.avk_build_regions.argtypes = [vp, C.POINTER(abi.CallSets), C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.avk_regions_download.argtypes = [vp, C.POINTER(abi.RegionBatch)]
+        lib.avk_build_regions_bed.argtypes = [vp, C.POINTER(abi.CallSets), C.POINTER(C.c_uint32), C.POINTER(abi.BedIntervals), C.c_uint32, C.c_uint64,
+                                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.avk_compare_batch_range.argtypes = [vp, C.POINTER(abi.RegionBatch), C.c_uint64, C.c_uint64, C.POINTER(abi.CompareCfg),
                                             C.POINTER(abi.CompareOut)]
     lib.avk_compare_batch_multi.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(abi.RegionBatch), C.POINTER(abi.CompareCfg),
@@ -100,7 +102,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "avk_create", "avk_destroy", "avk_last_error", "avk_set_reference", "avk_compare_batch", "avk_merge_batch",
     "avk_wfa_ed_batch", "avk_compare_seq_offsets", "avk_compare_upload", "avk_compare_run_resident",
-    "avk_compare_download", "avk_build_regions", "avk_regions_download", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak", "avk_last_tier_overflow", "avk_last_tier_ms",
+    "avk_compare_download", "avk_build_regions", "avk_build_regions_bed", "avk_regions_download", "avk_summary_write", "avk_vcf_records_write", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak", "avk_last_tier_overflow", "avk_last_tier_ms",
     "avk_compare_batch_range", "avk_compare_batch_multi", "avk_merge_batch_multi", "avk_partition_regions", "avk_compare_upload_range",
     "avk_compare_result_device", "avk_set_stratifications",
 ]
@@ -218,15 +220,24 @@ class Solver:
         return ed[:len(a_off)]
 
     # -- region builder on the device ------------------------------------------
-    def build_regions(self, callsets, contig: int, flank: int, first_region_id: int = 0, download: bool = True):
-        """region_generation.rs:352-469 on the device for one contig: clusters K call sets (batch.CallSets) into a
-        batch that stays resident (run_resident() can follow).  Returns the RegionBatch (or (n_regions, n_variants)
-        when download is False)."""
+    def build_regions(self, callsets, contig: int, flank: int, first_region_id: int = 0, download: bool = True, bed=None):
+        """region_generation.rs:276-479 on the device: clusters K call sets (batch.CallSets) into a batch that stays
+        resident (run_resident() can follow).  One contig spanned by one interval by default; with call sets that carry
+        variant_contig (several contigs in one table) and / or bed (batch.BedIntervals) the whole per-contig, per-interval
+        iteration runs in one call (avk_build_regions_bed).  Returns the RegionBatch (or (n_regions, n_variants) when
+        download is False)."""
         import numpy as np
         cs = callsets.to_c()
         n, nv = C.c_uint64(0), C.c_uint64(0)
-        self._check(self._lib.avk_build_regions(self._ctx, C.byref(cs), contig, flank, first_region_id, C.byref(n), C.byref(nv)),
-                    "avk_build_regions")
+        if bed is not None or getattr(callsets, "variant_contig", None) is not None:
+            vc = callsets.variant_contig if getattr(callsets, "variant_contig", None) is not None else np.full(callsets.n_variants, contig, dtype=np.uint32)
+            vc = np.ascontiguousarray(vc if vc.size else np.zeros(1, np.uint32), dtype=np.uint32)
+            cbed = bed.to_c() if bed is not None else None
+            self._check(self._lib.avk_build_regions_bed(self._ctx, C.byref(cs), abi.ptr(vc), C.byref(cbed) if cbed is not None else None, flank,
+                                                        first_region_id, C.byref(n), C.byref(nv)), "avk_build_regions_bed")
+        else:
+            self._check(self._lib.avk_build_regions(self._ctx, C.byref(cs), contig, flank, first_region_id, C.byref(n), C.byref(nv)),
+                        "avk_build_regions")
         n, nv = int(n.value), int(nv.value)
         if not download:
             return n, nv

@@ -332,7 +332,41 @@ typedef struct {
 } avk_callsets;
 int avk_build_regions(avk_ctx *ctx, const avk_callsets *in, uint32_t contig, uint32_t flank, uint64_t first_region_id,
                       uint64_t *n_regions, uint64_t *n_variants);
+/* The whole iterator of src/parsing/region_generation.rs:276-479 in one call: call sets that span several contigs and a
+ * BED of high-confidence intervals.  variant_contig[v] = contig of variant v (reference order; every input's list sorted
+ * by (contig, position), i.e. VCF order).  Intervals are 0-based half-open, sorted and non-overlapping within a contig
+ * (the reference assumes the latter, :438-441), contigs in reference order; bed == NULL means one interval spanning each
+ * contig.  Per contig (:283-292) and per interval (:374-470) in order: a variant starting before the interval is dropped
+ * (Containment::Before), one starting behind it is left for the next interval (After), one that starts inside but ends
+ * outside is dropped (Overlapping), a contained one joins the open cluster or -- pos >= window_end -- closes it
+ * (get_variant_containment :796-812).  Every interval starts with a fresh window, so clusters never span two intervals;
+ * window_start = first pos - flank (saturating, NOT clipped to the interval), window_end clipped to the contig length only
+ * (:411-429); region_id runs on across intervals and contigs from first_region_id (:403-409, :459-466). */
+typedef struct {
+    uint32_t n_contigs;          /* == contigs of avk_set_reference */
+    const uint64_t *first;       /* [n_contigs + 1]: intervals of contig c are first[c] .. first[c + 1] */
+    const uint32_t *start;       /* 0-based, inclusive */
+    const uint32_t *end;         /* 0-based, exclusive */
+} avk_bed_intervals;
+int avk_build_regions_bed(avk_ctx *ctx, const avk_callsets *in, const uint32_t *variant_contig, const avk_bed_intervals *bed,
+                          uint32_t flank, uint64_t first_region_id, uint64_t *n_regions, uint64_t *n_variants);
 int avk_regions_download(avk_ctx *ctx, avk_region_batch *out);
+
+/* ---- writers: host-side text of what the kernels counted.  buf == NULL: *len receives the size needed.
+ * avk_summary_write: the rows SummaryWriter::write_summary (src/writers/summary.rs:166-221, :243-420) emits for ONE
+ * GroupTypeMetrics table -- `totals` = avk_compare_out::totals for region_label "ALL", or row s of strat_totals for the
+ * label of stratum s -- for the metrics listed (0 GT, 1 HAP, 2 WEIGHTED_HAP, 3 BASEPAIR, 4 RECORD_BP, in this order):
+ * per metric the ALL row, the non-empty variant types, the non-empty JointIndel / JointStructuralVariant /
+ * JointTandemRepeat rows; recall / precision / F1 as f64 in the csv crate's formatting (shortest round trip), empty when
+ * undefined (src/data_types/summary_metrics.rs:48-74); filter column "ALL"; csv != 0 -> ',' instead of tab (:169-170). */
+int avk_summary_write(const uint64_t *totals, const uint8_t *metrics, uint32_t n_metrics, const char *compare_label, const char *region_label,
+                      int csv, int header, char *buf, uint64_t cap, uint64_t *len);
+/* avk_vcf_records_write: the body lines VariantCategorizer::write_variants (src/writers/variant_categorizer.rs:178-237)
+ * writes for input `side` (0 truth, 1 query) of regions [lo, hi): CHROM POS . REF ALT . . . GT:BD:EA:OA:RI and the
+ * sample column built from the variant's zygosity, var_class / var_expected / var_observed and the region id. */
+int avk_vcf_records_write(const avk_region_batch *batch, uint32_t side, const char *const *contig_names, uint32_t n_contigs,
+                          const uint8_t *var_class, const uint8_t *var_expected, const uint8_t *var_observed, uint64_t lo, uint64_t hi,
+                          char *buf, uint64_t cap, uint64_t *len);
 
 int avk_compare_upload(avk_ctx *ctx, const avk_region_batch *batch);
 int avk_compare_upload_range(avk_ctx *ctx, const avk_region_batch *batch, uint64_t lo, uint64_t hi);

@@ -1347,6 +1347,79 @@ int orc_build_regions(const avk_callsets *in, uint64_t contig_len, uint32_t cont
     return 0;
 }
 
+// RegionIterator::next over every contig and BED interval (region_generation.rs:276-479), literally: per contig the variants
+// fully inside the contig's full region [first interval start, last interval end) (:551, is_variant_contained :764-777) are
+// concatenated in input order, stable-sorted by position and consumed from a deque interval by interval.
+int orc_build_regions_bed(const avk_callsets *in, const uint32_t *variant_contig, const avk_bed_intervals *bed, const uint64_t *contig_lens,
+                          uint32_t n_contigs, uint32_t flank, uint64_t first_region_id, avk_region_batch *out) {
+    const avk_variant_table &t = in->variants;
+    const uint32_t K = in->n_inputs;
+    std::vector<uint32_t> input_of(t.n_variants);
+    for (uint32_t k = 0; k < K; ++k) for (uint64_t i = in->input_off[k]; i < in->input_off[k + 1]; ++i) input_of[i] = k;
+    avk_variant_table &o = const_cast<avk_variant_table &>(out->variants);
+    uint64_t n = 0, nv = 0, pool = 0;
+    uint64_t *region_id = const_cast<uint64_t *>(out->region_id), *var_off = const_cast<uint64_t *>(out->var_off);
+    uint32_t *rc = const_cast<uint32_t *>(out->contig), *rs = const_cast<uint32_t *>(out->start), *re = const_cast<uint32_t *>(out->end);
+    var_off[0] = 0;
+    for (uint32_t c = 0; c < n_contigs; ++c) {
+        std::vector<std::pair<uint64_t, uint64_t>> ivs;                       // 0-based half-open
+        if (bed) for (uint64_t j = bed->first[c]; j < bed->first[c + 1]; ++j) ivs.push_back({bed->start[j], bed->end[j]});
+        else ivs.push_back({0, contig_lens[c]});
+        if (ivs.empty()) continue;                                            // contigs without intervals are never visited (:283-284)
+        const uint64_t full_start = ivs.front().first, full_end = ivs.back().second, chrom_length = contig_lens[c];
+        std::vector<uint32_t> order;
+        for (uint64_t i = 0; i < t.n_variants; ++i) {
+            if (variant_contig[i] != c) continue;
+            const uint64_t vs = t.position[i], last = vs + t.a0_len[i] - 1;  // is_variant_contained :764-777
+            if (vs >= full_start && vs < full_end && last >= full_start && last < full_end && vs + t.a0_len[i] <= chrom_length) order.push_back((uint32_t)i);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return t.position[a] < t.position[b]; });   // :367-373
+        size_t front = 0;                                                     // the deque's front
+        for (const auto &iv : ivs) {
+            std::vector<std::vector<uint32_t>> cur(K);
+            bool have_start = false, have_end = false;
+            uint64_t w_start = 0, w_end = 0;
+            auto flush = [&]() {
+                region_id[n] = first_region_id + n; rc[n] = c; rs[n] = (uint32_t)w_start; re[n] = (uint32_t)w_end;
+                for (uint32_t k = 0; k < K; ++k) {
+                    for (uint32_t i : cur[k]) {
+                        const_cast<uint32_t *>(o.position)[nv] = t.position[i]; const_cast<uint8_t *>(o.variant_type)[nv] = t.variant_type[i];
+                        const_cast<uint8_t *>(o.zygosity)[nv] = t.zygosity[i]; const_cast<uint32_t *>(o.raw_allele_space)[nv] = t.raw_allele_space[i];
+                        const_cast<uint32_t *>(o.allele_off)[nv] = (uint32_t)pool; const_cast<uint32_t *>(o.a0_len)[nv] = t.a0_len[i];
+                        const_cast<uint32_t *>(o.a1_len)[nv] = t.a1_len[i];
+                        std::memcpy(const_cast<uint8_t *>(o.allele_pool) + pool, t.allele_pool + t.allele_off[i], (size_t)t.a0_len[i] + t.a1_len[i]);
+                        pool += (uint64_t)t.a0_len[i] + t.a1_len[i];
+                        nv += 1;
+                    }
+                    var_off[n * K + k + 1] = nv;
+                    cur[k].clear();
+                }
+                n += 1;
+            };
+            while (front < order.size()) {
+                const uint32_t i = order[front];
+                const uint64_t vs = t.position[i], ve = vs + t.a0_len[i];
+                if (vs < iv.first) { front += 1; continue; }                  // Before: skipped (:388-391)
+                if (vs >= iv.second) break;                                   // After: left for the next interval (:432-437)
+                front += 1;
+                if (ve > iv.second) continue;                                 // Overlapping: consumed, unused (:438-442)
+                if (have_end && vs >= w_end) {                                // :396-418 (window_end is deliberately not reset)
+                    flush();
+                    have_start = false;
+                }
+                if (!have_start) { w_start = vs > flank ? vs - flank : 0; have_start = true; }
+                const uint64_t vfe = std::min<uint64_t>(vs + t.a0_len[i] + flank, chrom_length);
+                w_end = have_end ? std::max(w_end, vfe) : vfe;
+                have_end = true;
+                cur[input_of[i]].push_back(i);
+            }
+            if (have_start && have_end) flush();                              // :447-466
+        }
+    }
+    out->n_regions = n; out->n_inputs = K; o.n_variants = nv; o.allele_pool_len = pool;
+    return 0;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

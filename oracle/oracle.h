@@ -22,6 +22,8 @@ int orc_compare_batch(const avk_region_batch *batch, const uint8_t *const *conti
                       int n_threads, avk_work_counters *work);
 int orc_build_regions(const avk_callsets *in, uint64_t contig_len, uint32_t contig, uint32_t flank, uint64_t first_region_id,
                       avk_region_batch *out);
+int orc_build_regions_bed(const avk_callsets *in, const uint32_t *variant_contig, const avk_bed_intervals *bed, const uint64_t *contig_lens,
+                          uint32_t n_contigs, uint32_t flank, uint64_t first_region_id, avk_region_batch *out);
 /* Stratifications::containments (stratifications.rs:108-118, 197-210) of every region's var_coordinates()
  * (compare_region.rs:63-74, incl. its last()-not-max end) as waffle_solver.rs:151-166 queries them: mask[r] bit s. */
 int orc_containments(const avk_region_batch *batch, const avk_strat_intervals *strata, uint64_t *mask);

@@ -300,3 +300,27 @@ def build_regions(callsets, contig_len: int, flank: int, contig: int = 0, first_
     return RegionBatch(k, b.region_id[:n], b.contig[:n], b.start[:n], b.end[:n], b.var_off[:n * k + 1], b.position[:nvo],
                        b.variant_type[:nvo], b.zygosity[:nvo], b.raw_allele_space[:nvo], b.allele_off[:nvo], b.a0_len[:nvo],
                        b.a1_len[:nvo], b.allele_pool[:max(int(cb.variants.allele_pool_len), 1)])
+
+
+def build_regions_bed(callsets, contig_lens, flank: int, bed=None, first_region_id: int = 0) -> RegionBatch:
+    """RegionIterator restatement over several contigs and BED intervals (region_generation.rs:276-479) -> RegionBatch."""
+    nv, k = callsets.n_variants, callsets.n_inputs
+    b = RegionBatch(k, np.zeros(nv, np.uint64), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32),
+                    np.zeros(nv * k + 1, np.uint64), np.zeros(nv, np.uint32), np.zeros(nv, np.uint8), np.zeros(nv, np.uint8),
+                    np.zeros(nv, np.uint32), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32), np.zeros(nv, np.uint32),
+                    np.zeros(max(callsets.pool_len, 1), np.uint8))
+    cs, cb = callsets.to_c(), b.to_c()
+    vc = np.ascontiguousarray(callsets.variant_contig if callsets.variant_contig is not None and callsets.variant_contig.size else np.zeros(max(nv, 1), np.uint32),
+                              dtype=np.uint32)
+    lens = np.asarray(contig_lens, dtype=np.uint64)
+    cbed = bed.to_c() if bed is not None else None
+    fn = lib().orc_build_regions_bed
+    fn.argtypes = [C.POINTER(abi.CallSets), C.POINTER(C.c_uint32), C.POINTER(abi.BedIntervals), C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32,
+                   C.c_uint64, C.POINTER(abi.RegionBatch)]
+    rc = fn(C.byref(cs), abi.ptr(vc), C.byref(cbed) if cbed is not None else None, abi.ptr(lens), len(lens), flank, first_region_id, C.byref(cb))
+    if rc != 0:
+        raise RuntimeError(f"orc_build_regions_bed failed: {rc}")
+    n, nvo = int(cb.n_regions), int(cb.variants.n_variants)
+    return RegionBatch(k, b.region_id[:n], b.contig[:n], b.start[:n], b.end[:n], b.var_off[:n * k + 1], b.position[:nvo],
+                       b.variant_type[:nvo], b.zygosity[:nvo], b.raw_allele_space[:nvo], b.allele_off[:nvo], b.a0_len[:nvo],
+                       b.a1_len[:nvo], b.allele_pool[:max(int(cb.variants.allele_pool_len), 1)])

@@ -732,3 +732,51 @@ def test_wfa_ed_cta_wide_paths_vs_oracle(solver):
     finally:
         s.close()
         Solver(0).close()                                                     # back to the default
+
+
+def _same_batch(a, b):
+    for f in ("region_id", "contig", "start", "end", "var_off", "position", "variant_type", "zygosity", "raw_allele_space", "allele_off", "a0_len", "a1_len"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    n = int(a.allele_off[-1] + a.a0_len[-1] + a.a1_len[-1]) if a.n_variants else 0
+    assert np.array_equal(a.allele_pool[:n], b.allele_pool[:n])
+
+
+def test_build_regions_bed_multi_contig_vs_oracle(solver):
+    """avk_build_regions_bed (several contigs, BED intervals, one call) against the oracle's literal restatement of the
+    reference iterator: hand-made corner cases (Before / After / Overlapping variants, adjacent intervals, contig-end
+    clipping), then random call sets over three contigs with random interval sets, and the built batch solved where it lies."""
+    from aardvark_b200.batch import BedIntervals, CallSets
+    from test_region_builder_bed import corner_case_callsets
+    cs, bed, lens = corner_case_callsets()
+    solver.set_reference([np.full(n, ord("A"), dtype=np.uint8) for n in lens])
+    _same_batch(solver.build_regions(cs, 0, 10, first_region_id=7, bed=bed), orc.build_regions_bed(cs, lens, 10, bed, first_region_id=7))
+    _same_batch(solver.build_regions(cs, 0, 10, bed=None), orc.build_regions_bed(cs, lens, 10, None))
+    rng = np.random.default_rng(99)
+    refs, inputs, contigs, per_contig = [], [[], []], [[], []], []
+    for c, L in enumerate((60_000, 25_000, 40_000)):
+        ref, (truth, query) = synth.callsets_compare(L, synth.SynthParams(n_variants=L // 150), seed=300 + c)
+        refs.append(ref)
+        for k, lst in enumerate((truth, query)):
+            inputs[k] += lst; contigs[k] += [c] * len(lst)
+        cuts = np.sort(rng.choice(np.arange(1, L), size=24, replace=False))
+        ivs = [(int(cuts[2 * j]), int(cuts[2 * j + 1])) for j in range(12)]
+        if c == 1:
+            ivs = []                                                       # a contig without intervals is never visited
+        if c == 2:
+            ivs[3] = (ivs[3][0], ivs[4][0]); ivs[7] = (ivs[7][0], ivs[7][0])   # two adjacent intervals, one empty interval
+        per_contig.append(ivs)
+    cs, bed = CallSets(inputs, contigs=contigs), BedIntervals(per_contig)
+    solver.set_reference(refs)
+    for flank in (50, 0, 1000):
+        gpu = solver.build_regions(cs, 0, flank, first_region_id=3, bed=bed)
+        cpu = orc.build_regions_bed(cs, [r.size for r in refs], flank, bed, first_region_id=3)
+        assert cpu.n_regions > 20
+        _same_batch(gpu, cpu)
+    # the device-built batch is resident: solve it in place and compare with the oracle on the oracle-built batch
+    solver.build_regions(cs, 0, 50, bed=bed, download=False)
+    cfg = CompareConfig(enable_sequences=False)
+    solver.run_resident(cfg)
+    cpu_b = orc.build_regions_bed(cs, [r.size for r in refs], 50, bed)
+    out = CompareOutputs(cpu_b)
+    solver.download(out)
+    assert out.diff(orc.compare_batch(cpu_b, refs, compare_cfg(cfg))) == []
