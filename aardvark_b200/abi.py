@@ -83,6 +83,14 @@ class BedIntervals(C.Structure):
     ]
 
 
+class VcfOut(C.Structure):
+    _fields_ = [
+        ("n_variants", C.c_uint64), ("allele_pool_len", C.c_uint64), ("cap_variants", C.c_uint64), ("cap_pool", C.c_uint64),
+        ("contig", _u32p), ("position", _u32p), ("variant_type", _u8p), ("zygosity", _u8p),
+        ("raw_allele_space", _u32p), ("allele_off", _u32p), ("a0_len", _u32p), ("a1_len", _u32p), ("allele_pool", _u8p),
+    ]
+
+
 class CompareCfg(C.Structure):
     _fields_ = [
         ("max_branch_factor", C.c_uint32),

@@ -22,10 +22,13 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "avk_solver.cuh"
 #include "avk_thread_solver.cuh"
 #include "avk_writers.h"
+#include "avk_vcf.cuh"
 
 using namespace avk;
 
@@ -1244,7 +1247,7 @@ struct avk_ctx {
     DevBuf st_off, st_first, st_pmax, st_mask;   // stratification intervals (avk_set_stratifications) and per-region containment masks
     u32 st_n = 0, st_contigs = 0;
     int dense_n = 0;    // clusters with at least this many variants go to the dense list X: speculative search + team stage
-                        // (AVK_DENSE_N; 0 = 10 when the thread-per-cluster stage runs, 6 for the small batches that go without it)
+                        // (AVK_DENSE_N; 0 = 10 when the thread-per-cluster stage runs, 8 or 6 (below 250 k clusters) for the batches that go without it)
     // Resident batch: regions [lo, lo + n_regions) of the caller's batch, i.e. variants [v_base, v_base + n_variants) of its
     // variant table and bytes [p_base, ..) of its allele pool.  Per-variant device pointers are biased by these bases so
     // that kernels index them with the caller's own (global) indices: a contiguous bin needs no re-basing on the host.
@@ -1274,8 +1277,9 @@ struct avk_ctx {
                                     // thread has the more that one cluster weighs: 64 pops for >= 2.5 M clusters, 48 for >= 1.2 M, else 32)
     bool use_thread_stage = true;   // AVK_NO_THREAD_STAGE=1: warp kernels only (A/B timing, tests of the warp path)
     bool sort_shapes = true;        // AVK_NO_SHAPE_SORT=1: the thread stage takes its clusters in list order
-    u64 thread_min_regions = 400000; // smaller batches go to the warp kernels directly: with at most a cluster or two per thread the
-                                     // thread stage is bound by its slowest cluster, not by throughput (AVK_THREAD_MIN_REGIONS)
+    u64 thread_min_regions = 700000; // smaller batches go to the warp kernels directly: with at most a cluster or two per thread the
+                                     // thread stage is bound by its slowest cluster, not by throughput (measured at 494 k clusters: 10.1 ms
+                                     // with the thread stage, 8.6 ms without; at 988 k: 11.2 vs 15.5 ms) (AVK_THREAD_MIN_REGIONS)
     // Pipelined single-GPU call: sibling contexts on the same device (own stream and buffers, the owner's reference) solve
     // alternating bins so that one bin's upload, another's kernels and a third's download overlap.
     avk_ctx *ref_owner = nullptr;   // set in a sibling: whose reference it reads
@@ -1853,7 +1857,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p, *LX = (u32 *)ctx->fail_x.p;
     const bool thread_stage = ctx->use_thread_stage && n >= ctx->thread_min_regions;
-    const int dense_n = ctx->dense_n ? ctx->dense_n : (thread_stage ? 10 : 6);
+    const int dense_n = ctx->dense_n ? ctx->dense_n : (thread_stage ? 10 : (n >= 250000 ? 8 : 6));
     // closed-form clusters; >= dense_n variants -> X (dense); the rest -> W
     u64 *keys = nullptr;
     if (thread_stage && ctx->sort_shapes) {
@@ -2945,4 +2949,123 @@ extern "C" int avk_vcf_records_write(const avk_region_batch *batch, uint32_t sid
     if (!batch || !contig_names || !var_class || !var_expected || !var_observed || side >= batch->n_inputs || lo > hi || hi > batch->n_regions) return AVK_ERR_INVALID;
     for (uint64_t r = lo; r < hi; ++r) if (batch->contig[r] >= n_contigs) return AVK_ERR_INVALID;
     return copy_text(avk_writers::vcf_records_text(batch, side, contig_names, var_class, var_expected, var_observed, lo, hi), buf, cap, len);
+}
+
+// ---- VCF body text -> call-set table (avk_vcf.cuh) -----------------------------------------------------------
+struct LineStart {
+    const u8 *t;
+    u64 len;
+    __device__ __forceinline__ bool operator()(const u64 &i) const { return i < len && (i == 0 || t[i - 1] == '\n'); }
+};
+// per line: number of variants it yields, their allele bytes, or an error (the first failing line wins, like the `?` of the loop)
+__global__ void __launch_bounds__(256) k_vcf_scan(const u8 *t, u64 len, const u64 *starts, u64 n_lines, const char *names, u32 n_contigs, u32 name_stride,
+                                                  u32 sample_index, int trim, u32 *n_out, u32 *n_bytes, unsigned long long *first_err) {
+    const u64 li = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_lines) return;
+    u64 b = starts[li], e = li + 1 < n_lines ? starts[li + 1] : len;
+    while (e > b && (t[e - 1] == '\n' || t[e - 1] == '\r')) --e;
+    avk_vcf::LineInfo L;
+    avk_vcf::parse_line(t, b, e, names, n_contigs, name_stride, sample_index, trim != 0, L);
+    u32 bytes = 0;
+    for (int q = 0; q < L.n; ++q) bytes += L.v[q].l0 + L.v[q].l1;
+    n_out[li] = L.err ? 0u : (u32)L.n; n_bytes[li] = L.err ? 0u : bytes;
+    if (L.err) atomicMin(first_err, (unsigned long long)((li << 8) | (u64)L.err));
+}
+__global__ void __launch_bounds__(256) k_vcf_emit(const u8 *t, u64 len, const u64 *starts, u64 n_lines, const char *names, u32 n_contigs, u32 name_stride,
+                                                  u32 sample_index, int trim, const u32 *v_off, const u32 *b_off, u32 *contig, u32 *pos, u8 *vt, u8 *zy,
+                                                  u32 *raw, u32 *aoff, u32 *l0, u32 *l1, u8 *pool) {
+    const u64 li = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_lines) return;
+    u64 b = starts[li], e = li + 1 < n_lines ? starts[li + 1] : len;
+    while (e > b && (t[e - 1] == '\n' || t[e - 1] == '\r')) --e;
+    avk_vcf::LineInfo L;
+    avk_vcf::parse_line(t, b, e, names, n_contigs, name_stride, sample_index, trim != 0, L);
+    if (L.err) return;
+    u32 v = v_off[li], o = b_off[li];
+    for (int q = 0; q < L.n; ++q, ++v) {
+        const avk_vcf::Var &V = L.v[q];
+        contig[v] = L.contig; pos[v] = L.pos; vt[v] = V.type; zy[v] = V.zyg; raw[v] = V.raw; aoff[v] = o; l0[v] = V.l0; l1[v] = V.l1;
+        for (u32 k = 0; k < V.l0; ++k) pool[o + k] = t[L.ref.b + k];
+        for (u32 k = 0; k < V.l1; ++k) pool[o + V.l0 + k] = t[b + V.alt_b + k];
+        o += V.l0 + V.l1;
+    }
+}
+extern "C" int avk_vcf_parse(avk_ctx *ctx, const uint8_t *text, uint64_t len, const char *const *contig_names, uint32_t n_contigs, uint32_t sample_index,
+                             int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if ((!text && len) || !out || !contig_names || n_contigs == 0 || len >= 0xfffffff0ull) { ctx->err = "avk_vcf_parse: bad arguments (text up to 4 GiB per call)"; return AVK_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    if (error_line) *error_line = 0;
+    if (error_code) *error_code = 0;
+    out->n_variants = 0; out->allele_pool_len = 0;
+    if (len == 0) return AVK_OK;
+    DevBuf *rb = ctx->rb;   // the region builder's temporaries are free between its calls
+    enum { V_TEXT, V_STARTS, V_NOUT, V_NBYTES, V_VOFF, V_BOFF, V_NAMES, V_MISC, V_C, V_POS, V_VT, V_ZY, V_RAW, V_AOFF, V_L0, V_L1, V_POOL };
+    u32 stride = 1;
+    for (u32 c = 0; c < n_contigs; ++c) { if (!contig_names[c]) { ctx->err = "avk_vcf_parse: null contig name"; return AVK_ERR_INVALID; } stride = std::max<u32>(stride, (u32)strlen(contig_names[c]) + 1); }
+    std::vector<char> names((size_t)stride * n_contigs, 0);
+    for (u32 c = 0; c < n_contigs; ++c) strcpy(names.data() + (size_t)c * stride, contig_names[c]);
+    UPLOAD(rb[V_TEXT], text, len);
+    UPLOAD(rb[V_NAMES], names.data(), names.size());
+    ENSURE(rb[V_STARTS], 8 * (len / 2 + 2));                      // a line is at least one byte and its newline
+    ENSURE(rb[V_MISC], 64);
+    const u8 *d_text = (const u8 *)rb[V_TEXT].p;
+    u64 *d_starts = (u64 *)rb[V_STARTS].p;
+    unsigned long long *d_misc = (unsigned long long *)rb[V_MISC].p;   // [0] number of lines, [1] first error
+    size_t need = 0, tmp = 0;
+    thrust::counting_iterator<u64> it(0);
+    LineStart pred{d_text, len};
+    cub::DeviceSelect::If(nullptr, need, it, d_starts, d_misc, (int)len, pred, ctx->stream); tmp = std::max(tmp, need);
+    ENSURE(ctx->scan_tmp, tmp);
+    need = tmp; cub::DeviceSelect::If(ctx->scan_tmp.p, need, it, d_starts, d_misc, (int)len, pred, ctx->stream);
+    const unsigned long long no_err = ~0ull;
+    CK(cudaMemcpyAsync(d_misc + 1, &no_err, 8, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long n_lines = 0;
+    CK(cudaMemcpyAsync(&n_lines, d_misc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 1;
+    if (n_lines == 0) return AVK_OK;
+    for (int b : {V_NOUT, V_NBYTES, V_VOFF, V_BOFF}) ENSURE(rb[b], 4 * (n_lines + 1));
+    u32 *n_out = (u32 *)rb[V_NOUT].p, *n_bytes = (u32 *)rb[V_NBYTES].p, *v_off = (u32 *)rb[V_VOFF].p, *b_off = (u32 *)rb[V_BOFF].p;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, n_out, v_off, (int)n_lines + 1, ctx->stream); tmp = std::max(tmp, need);
+    ENSURE(ctx->scan_tmp, tmp);
+    CK(cudaMemsetAsync(n_out + n_lines, 0, 4, ctx->stream)); CK(cudaMemsetAsync(n_bytes + n_lines, 0, 4, ctx->stream));
+    const unsigned g = (unsigned)((n_lines + 255) / 256);
+    k_vcf_scan<<<g, 256, 0, ctx->stream>>>(d_text, len, d_starts, n_lines, (const char *)rb[V_NAMES].p, n_contigs, stride, sample_index, enable_trimming, n_out, n_bytes, d_misc + 1);
+    need = tmp; cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, need, n_out, v_off, (int)n_lines + 1, ctx->stream);
+    need = tmp; cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, need, n_bytes, b_off, (int)n_lines + 1, ctx->stream);
+    unsigned long long first_err = 0;
+    u32 totals[2] = {0, 0};
+    CK(cudaMemcpyAsync(&first_err, d_misc + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&totals[0], v_off + n_lines, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&totals[1], b_off + n_lines, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 3;
+    if (first_err != no_err) {                                    // Err(..) of the first failing record (region_generation.rs:533-541)
+        if (error_line) *error_line = first_err >> 8;
+        if (error_code) *error_code = (int32_t)(first_err & 0xff);
+        ctx->err = "avk_vcf_parse: record " + std::to_string(first_err >> 8) + " cannot be parsed (code " + std::to_string(first_err & 0xff) + ")";
+        return AVK_ERR_INVALID;
+    }
+    const u64 nv = totals[0], nb = totals[1];
+    if (nv > out->cap_variants || nb > out->cap_pool) {
+        out->n_variants = nv; out->allele_pool_len = nb;          // what the caller must provide
+        ctx->err = "avk_vcf_parse: output capacity too small";
+        return AVK_ERR_OOM;
+    }
+    for (int b : {V_C, V_POS, V_RAW, V_AOFF, V_L0, V_L1}) ENSURE(rb[b], 4 * nv);
+    ENSURE(rb[V_VT], nv); ENSURE(rb[V_ZY], nv); ENSURE(rb[V_POOL], nb);
+    k_vcf_emit<<<g, 256, 0, ctx->stream>>>(d_text, len, d_starts, n_lines, (const char *)rb[V_NAMES].p, n_contigs, stride, sample_index, enable_trimming, v_off, b_off,
+                                           (u32 *)rb[V_C].p, (u32 *)rb[V_POS].p, (u8 *)rb[V_VT].p, (u8 *)rb[V_ZY].p, (u32 *)rb[V_RAW].p, (u32 *)rb[V_AOFF].p,
+                                           (u32 *)rb[V_L0].p, (u32 *)rb[V_L1].p, (u8 *)rb[V_POOL].p);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+#define VDL(dst, buf, bytes) do { if ((bytes) && (dst)) CK(cudaMemcpyAsync((void *)(dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream)); } while (0)
+    VDL(out->contig, rb[V_C], 4 * nv); VDL(out->position, rb[V_POS], 4 * nv); VDL(out->variant_type, rb[V_VT], nv); VDL(out->zygosity, rb[V_ZY], nv);
+    VDL(out->raw_allele_space, rb[V_RAW], 4 * nv); VDL(out->allele_off, rb[V_AOFF], 4 * nv); VDL(out->a0_len, rb[V_L0], 4 * nv); VDL(out->a1_len, rb[V_L1], 4 * nv);
+    VDL(out->allele_pool, rb[V_POOL], nb);
+#undef VDL
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->n_variants = nv; out->allele_pool_len = nb;
+    return AVK_OK;
 }

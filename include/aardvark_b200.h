@@ -352,6 +352,26 @@ int avk_build_regions_bed(avk_ctx *ctx, const avk_callsets *in, const uint32_t *
                           uint32_t flank, uint64_t first_region_id, uint64_t *n_regions, uint64_t *n_variants);
 int avk_regions_download(avk_ctx *ctx, avk_region_batch *out);
 
+/* ---- VCF ingest: parse_variant / parse_genotype / get_variant_type (src/parsing/region_generation.rs:565-758) on
+ * the device, one record line per thread.  `text` = inflated VCF record lines (header lines starting with '#' are skipped;
+ * BGZF inflate and the tabix query stay on the host), sample_index = column of the sample, contig_names = the reference's
+ * contigs.  Output: the variants in record order with multi-ALT genotypes split into one variant per ALT allele, '*' and
+ * symbolic ALTs, alleles over 10 kbp and BND / DUP records dropped, trailing bases trimmed (enable_trimming), types
+ * inferred from INFO SVTYPE / TRID / allele lengths, raw_allele_space taken before trimming -- i.e. one input of an
+ * avk_callsets table plus its variant_contig array.  A record the reference would fail on (missing GT key, ploidy > 2,
+ * unsupported SVTYPE, ALT index out of range, ...) fails the call: AVK_ERR_INVALID with its line number and a code.
+ * AVK_ERR_OOM with n_variants / allele_pool_len set: the caller's arrays are too small (2 * lines and len always suffice). */
+typedef struct {
+    uint64_t n_variants, allele_pool_len;        /* out */
+    uint64_t cap_variants, cap_pool;             /* in: capacity of the arrays below */
+    uint32_t *contig, *position;
+    uint8_t *variant_type, *zygosity;
+    uint32_t *raw_allele_space, *allele_off, *a0_len, *a1_len;
+    uint8_t *allele_pool;
+} avk_vcf_out;
+int avk_vcf_parse(avk_ctx *ctx, const uint8_t *text, uint64_t len, const char *const *contig_names, uint32_t n_contigs, uint32_t sample_index,
+                  int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code);
+
 /* ---- writers: host-side text of what the kernels counted.  buf == NULL: *len receives the size needed.
  * avk_summary_write: the rows SummaryWriter::write_summary (src/writers/summary.rs:166-221, :243-420) emits for ONE
  * GroupTypeMetrics table -- `totals` = avk_compare_out::totals for region_label "ALL", or row s of strat_totals for the

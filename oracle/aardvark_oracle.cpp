@@ -1420,6 +1420,111 @@ int orc_build_regions_bed(const avk_callsets *in, const uint32_t *variant_contig
     return 0;
 }
 
+// parse_variant / parse_genotype / get_variant_type (region_generation.rs:565-758) over inflated VCF record lines, written with
+// std::string splitting (independent of the device parser in aardvark_b200/csrc/avk_vcf.cuh).  Returns 0, or 1 + the index of
+// the first line the reference would fail on (*err_code: 1 columns, 2 POS, 3 no GT key, 4 GT, 5 ALT index, 6 SVTYPE, 7 contig,
+// 8 empty allele, 9 Variant constructor).
+static std::vector<std::string> split_str(const std::string &s, char d) {
+    std::vector<std::string> out;
+    size_t b = 0;
+    for (;;) { const size_t e = s.find(d, b); if (e == std::string::npos) { out.push_back(s.substr(b)); break; } out.push_back(s.substr(b, e - b)); b = e + 1; }
+    return out;
+}
+int orc_vcf_parse(const uint8_t *text, uint64_t len, const char *const *contig_names, uint32_t n_contigs, uint32_t sample_index, int enable_trimming,
+                  avk_vcf_out *out, int32_t *err_code) {
+    uint64_t nv = 0, pool = 0, line_no = 0;
+    size_t b = 0;
+    const std::string all((const char *)text, (size_t)len);
+    auto fail = [&](int code) { if (err_code) *err_code = code; return (int)(1 + line_no); };
+    while (b < all.size()) {
+        size_t e = all.find('\n', b);
+        if (e == std::string::npos) e = all.size();
+        std::string line = all.substr(b, e - b);
+        b = e + 1;
+        while (!line.empty() && line.back() == '\r') line.pop_back();
+        const uint64_t this_line = line_no;
+        (void)this_line;
+        if (line.empty() || line[0] == '#') { line_no += 1; continue; }
+        const std::vector<std::string> col = split_str(line, '\t');
+        if (col.size() < 10 || col.size() - 9 <= sample_index) return fail(1);
+        uint32_t contig = n_contigs;
+        for (uint32_t c = 0; c < n_contigs; ++c) if (col[0] == contig_names[c]) { contig = c; break; }
+        if (contig == n_contigs) return fail(7);
+        if (col[1].empty() || col[1].find_first_not_of("0123456789") != std::string::npos || col[1].size() > 10) return fail(2);
+        const uint64_t pos1 = std::stoull(col[1]);
+        if (pos1 == 0 || pos1 > 0xffffffffull) return fail(2);
+        const std::vector<std::string> fmt = split_str(col[8], ':'), smp = split_str(col[9 + sample_index], ':');
+        int gi = -1;
+        for (size_t k = 0; k < fmt.size(); ++k) if (fmt[k] == "GT") { gi = (int)k; break; }
+        if (gi < 0) return fail(3);                                             // "Missing GT" (:579-580)
+        if ((size_t)gi >= smp.size() || smp[gi].empty() || smp[gi] == ".") { line_no += 1; continue; }   // GT = '.': no-op (:581-587)
+        // parse_genotype (:660-712)
+        std::string g = smp[gi];
+        if (g[0] == '/' || g[0] == '|') g = g.substr(1);
+        std::vector<int> al;
+        bool phased = false;
+        size_t i = 0;
+        for (;;) {
+            if (al.size() == 2 || i >= g.size()) return fail(4);
+            if (g[i] == '.') { al.push_back(0); i += 1; }
+            else {
+                if (!isdigit((unsigned char)g[i])) return fail(4);
+                int v = 0;
+                while (i < g.size() && isdigit((unsigned char)g[i])) { v = v * 10 + (g[i] - '0'); if (v > 60000) return fail(4); i += 1; }
+                al.push_back(v);
+            }
+            if (i == g.size()) break;
+            if (g[i] == '|') phased = true; else if (g[i] != '/') return fail(4);
+            i += 1;
+        }
+        if (al.size() == 1) al.push_back(al[0]);                                 // hemizygous treated as homozygous (:671-673)
+        std::vector<std::pair<int, int>> picks;                                  // (alt index, zygosity)
+        if (al[0] == al[1]) { if (al[0] != 0) picks.push_back({al[0], AVK_ZYG_HOM_ALT}); }
+        else {
+            if (al[0] != 0) picks.push_back({al[0], phased ? AVK_ZYG_PHASED_HET10 : AVK_ZYG_UNPHASED_HET});
+            if (al[1] != 0) picks.push_back({al[1], phased ? AVK_ZYG_PHASED_HET01 : AVK_ZYG_UNPHASED_HET});
+        }
+        if (picks.empty()) { line_no += 1; continue; }
+        // INFO tags (get_variant_type :723-746)
+        int sv = -1; bool trid = false, bad_sv = false;
+        for (const std::string &f : split_str(col[7], ';')) {
+            if (f.rfind("SVTYPE=", 0) == 0 && f.size() > 7) {
+                const std::string v = f.substr(7);
+                if (v == "BND") sv = AVK_VT_SV_BREAKEND; else if (v == "DEL") sv = AVK_VT_SV_DELETION; else if (v == "DUP") sv = AVK_VT_SV_DUPLICATION;
+                else if (v == "INS") sv = AVK_VT_SV_INSERTION; else bad_sv = true;
+            }
+            if (f.rfind("TRID=", 0) == 0 && f.size() > 5) trid = true;
+        }
+        const std::vector<std::string> alts = split_str(col[4], ',');
+        for (const auto &pk : picks) {
+            if ((size_t)pk.first > alts.size()) return fail(5);
+            std::string r = col[3], a = alts[pk.first - 1];
+            if (r.empty() || a.empty()) return fail(8);
+            if (a == "*") continue;                                             // :596-599
+            if (a[0] == '<') continue;                                          // :603-606
+            const size_t raw = std::max(r.size(), a.size());                    // :610-612
+            while (enable_trimming && r.size() > 1 && a.size() > 1 && r.back() == a.back()) { r.pop_back(); a.pop_back(); }   // :615-618
+            if (r.size() > 10000 || a.size() > 10000) continue;                 // :621-626
+            if (bad_sv) return fail(6);
+            int vt;
+            if (sv >= 0) vt = sv;
+            else if (trid) vt = a.size() < r.size() ? AVK_VT_TR_CONTRACTION : AVK_VT_TR_EXPANSION;
+            else vt = (r.size() == 1 && a.size() == 1) ? AVK_VT_SNV : (r.size() == 1 ? AVK_VT_INSERTION : (a.size() == 1 ? AVK_VT_DELETION : AVK_VT_INDEL));
+            if (vt == AVK_VT_SV_BREAKEND || vt == AVK_VT_SV_DUPLICATION) continue;   // :641-644
+            if ((vt == AVK_VT_SV_DELETION && (r.size() <= 1 || a.size() > r.size())) || (vt == AVK_VT_SV_INSERTION && a.size() < r.size())) return fail(9);   // variants.rs:232-290
+            if (nv >= out->cap_variants || pool + r.size() + a.size() > out->cap_pool) return -1;
+            out->contig[nv] = contig; out->position[nv] = (uint32_t)(pos1 - 1); out->variant_type[nv] = (uint8_t)vt; out->zygosity[nv] = (uint8_t)pk.second;
+            out->raw_allele_space[nv] = (uint32_t)raw; out->allele_off[nv] = (uint32_t)pool; out->a0_len[nv] = (uint32_t)r.size(); out->a1_len[nv] = (uint32_t)a.size();
+            std::memcpy(out->allele_pool + pool, r.data(), r.size()); std::memcpy(out->allele_pool + pool + r.size(), a.data(), a.size());
+            pool += r.size() + a.size();
+            nv += 1;
+        }
+        line_no += 1;
+    }
+    out->n_variants = nv; out->allele_pool_len = pool;
+    return 0;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -24,6 +24,8 @@ int orc_build_regions(const avk_callsets *in, uint64_t contig_len, uint32_t cont
                       avk_region_batch *out);
 int orc_build_regions_bed(const avk_callsets *in, const uint32_t *variant_contig, const avk_bed_intervals *bed, const uint64_t *contig_lens,
                           uint32_t n_contigs, uint32_t flank, uint64_t first_region_id, avk_region_batch *out);
+int orc_vcf_parse(const uint8_t *text, uint64_t len, const char *const *contig_names, uint32_t n_contigs, uint32_t sample_index, int enable_trimming,
+                  avk_vcf_out *out, int32_t *err_code);
 /* Stratifications::containments (stratifications.rs:108-118, 197-210) of every region's var_coordinates()
  * (compare_region.rs:63-74, incl. its last()-not-max end) as waffle_solver.rs:151-166 queries them: mask[r] bit s. */
 int orc_containments(const avk_region_batch *batch, const avk_strat_intervals *strata, uint64_t *mask);

@@ -324,3 +324,18 @@ def build_regions_bed(callsets, contig_lens, flank: int, bed=None, first_region_
     return RegionBatch(k, b.region_id[:n], b.contig[:n], b.start[:n], b.end[:n], b.var_off[:n * k + 1], b.position[:nvo],
                        b.variant_type[:nvo], b.zygosity[:nvo], b.raw_allele_space[:nvo], b.allele_off[:nvo], b.a0_len[:nvo],
                        b.a1_len[:nvo], b.allele_pool[:max(int(cb.variants.allele_pool_len), 1)])
+
+
+def vcf_parse(text: bytes, contig_names, sample_index=0, enable_trimming=True):
+    """parse_variant / parse_genotype / get_variant_type restatement over VCF record lines -> (VcfTable, 0) or (None, (line, code))."""
+    from aardvark_b200.ingest import VcfTable
+    tab = VcfTable(2 * (text.count(b"\n") + 1), len(text))
+    c = tab.to_c()
+    names = (C.c_char_p * len(contig_names))(*[n.encode() for n in contig_names])
+    code = C.c_int32(0)
+    fn = lib().orc_vcf_parse
+    fn.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_int, C.POINTER(abi.VcfOut), C.POINTER(C.c_int32)]
+    rc = fn(text, len(text), names, len(contig_names), sample_index, 1 if enable_trimming else 0, C.byref(c), C.byref(code))
+    if rc != 0:
+        return None, (rc - 1, int(code.value))
+    return tab.finish(c), 0

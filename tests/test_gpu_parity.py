@@ -775,8 +775,59 @@ def test_build_regions_bed_multi_contig_vs_oracle(solver):
     # the device-built batch is resident: solve it in place and compare with the oracle on the oracle-built batch
     solver.build_regions(cs, 0, 50, bed=bed, download=False)
     cfg = CompareConfig(enable_sequences=False)
-    solver.run_resident(cfg)
+    solver.run_resident(cfg, region_metrics=True)
     cpu_b = orc.build_regions_bed(cs, [r.size for r in refs], 50, bed)
     out = CompareOutputs(cpu_b)
     solver.download(out)
     assert out.diff(orc.compare_batch(cpu_b, refs, compare_cfg(cfg))) == []
+
+
+def _vcf_text(records, contig_names, sample_gt=None):
+    """Call-set records [(contig, pos, a0, a1, zyg, type, raw)] -> VCF body text (one ALT per record)."""
+    gt = {abi.ZYG_UNPHASED_HET: b"0/1", abi.ZYG_PHASED_HET01: b"0|1", abi.ZYG_PHASED_HET10: b"1|0", abi.ZYG_HOM_ALT: b"1/1"}
+    lines = [b"##fileformat=VCFv4.2", b"#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSAMPLE"]
+    for (c, pos, a0, a1, z, t, raw) in records:
+        info = b"SVTYPE=INS" if t == abi.VT_SV_INSERTION else (b"SVTYPE=DEL" if t == abi.VT_SV_DELETION else b".")
+        lines.append(b"\t".join([contig_names[c].encode(), str(pos + 1).encode(), b".", a0, a1, b".", b"PASS", info, b"GT:GQ", gt[z] + b":40"]))
+    return b"\n".join(lines) + b"\n"
+
+
+def test_vcf_ingest_vs_oracle(solver):
+    """avk_vcf_parse (one VCF record per thread: GT parsing, multi-ALT split, trimming, type inference) against the oracle's
+    independent restatement: the hand-made records of tests/test_vcf_ingest.py, the error cases (same line and code), and a
+    synthetic call set written out as VCF, parsed on the device, clustered by the device region builder and solved -- equal to
+    the oracle on the host-built batch of the original records."""
+    from aardvark_b200.batch import CallSets
+    from aardvark_b200.ingest import parse_vcf_text
+    from aardvark_b200.lib import AvkError
+    import test_vcf_ingest as T
+    names = ["chr1", "chr2"]
+    for sample in (0, 1):
+        for trim in (True, False):
+            gpu = parse_vcf_text(solver, T.TEXT, names, sample, trim)
+            cpu, err = orc.vcf_parse(T.TEXT, names, sample, trim)
+            assert err == 0 and gpu.records() == cpu.records(), (sample, trim)
+    for line, code in ((b"chr1\t5\t.\tA\tG\t.\t.\t.\tDP\t3\t4", 3), (b"chr1\t5\t.\tA\tG\t.\t.\t.\tGT\t0/1/1\t0/1", 4), (b"chr1\t5\t.\tA\tG\t.\t.\tSVTYPE=INV\tGT\t0/1\t0/1", 6)):
+        with pytest.raises(AvkError, match=f"record 3 cannot be parsed \\(code {code}\\)"):
+            parse_vcf_text(solver, T.HEADER + T.LINES[0] + b"\n" + line + b"\n", names)
+    assert parse_vcf_text(solver, b"", names).n_variants == 0 and parse_vcf_text(solver, T.HEADER, names).n_variants == 0
+    # synthetic call sets -> VCF text -> device parse -> device region builder -> solve
+    refs, sides = [], [[], []]
+    for c, L in enumerate((50_000, 30_000)):
+        p = synth.SynthParams(n_variants=L // 200, sv_events=3 if c == 0 else 0, sv_min=60, sv_max=400)
+        ref, (truth, query) = synth.callsets_compare(L, p, seed=500 + c)
+        refs.append(ref)
+        for k, lst in enumerate((truth, query)):
+            sides[k] += [(c, pos, a0, a1, z, t, raw) for (pos, a0, a1, z, t, raw) in lst]
+    parsed = [parse_vcf_text(solver, _vcf_text(recs, names), names, 0, True) for recs in sides]
+    for recs, tab in zip(sides, parsed):
+        assert tab.records() == recs                      # (the generator's records are already trimmed: raw_allele_space is kept)
+    inputs = [[r[1:] for r in tab.records()] for tab in parsed]
+    contigs = [[r[0] for r in tab.records()] for tab in parsed]
+    solver.set_reference(refs)
+    cs = CallSets(inputs, contigs=contigs)
+    built = solver.build_regions(cs, 0, 50)
+    host = orc.build_regions_bed(CallSets([[r[1:] for r in s] for s in sides], contigs=[[r[0] for r in s] for s in sides]), [r.size for r in refs], 50, None)
+    _same_batch(built, host)
+    cfg = CompareConfig(enable_sequences=False)
+    assert solver.compare_batch(built, cfg).diff(orc.compare_batch(host, refs, compare_cfg(cfg))) == []
