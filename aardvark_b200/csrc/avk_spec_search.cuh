@@ -51,12 +51,28 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 using namespace avk;
 
-enum { SP_MAXN = 31, SP_QCAP = 384, SP_RESCAP = 64, SP_EDCAP = 24, SP_MAXALT = 12, SP_MAXP = 2 * SP_MAXALT + 1, SP_WF = 2 * SP_EDCAP + 2, SP_LANES = 32 };
+// capacities (overridable for the host harness' what-if runs)
+#ifndef AVK_SP_QCAP
+#define AVK_SP_QCAP 384
+#endif
+#ifndef AVK_SP_RESCAP
+#define AVK_SP_RESCAP 64
+#endif
+#ifndef AVK_SP_EDCAP
+#define AVK_SP_EDCAP 24
+#endif
+#ifndef AVK_SP_MAXALT
+#define AVK_SP_MAXALT 12
+#endif
+#ifndef AVK_SP_XCAP
+#define AVK_SP_XCAP 25
+#endif
+enum { SP_MAXN = 31, SP_QCAP = AVK_SP_QCAP, SP_RESCAP = AVK_SP_RESCAP, SP_EDCAP = AVK_SP_EDCAP, SP_MAXALT = AVK_SP_MAXALT, SP_MAXP = 2 * SP_MAXALT + 1, SP_WF = 2 * SP_EDCAP + 2, SP_LANES = 32 };
 // dense blob: what the team stage reads back (slot = index in the dense list)
 enum { SPB_NRES = 0, SPB_RES = 16, SPB_ALLE = 32, SPB_RES_STRIDE = SPB_ALLE + 24, SPB_SIZE = SPB_RES + SP_RESCAP * SPB_RES_STRIDE };
 enum { SPB_NONE = -1 };   // n_res value: no search result here, solve from scratch
 enum { SPB_SCORED = 4, SPB_KEEP0 = 8, SPB_KEEP1 = 12 };   // header: scored != 0 -> result 0 is THE solution and keep0 / keep1 its exact-GT alleles
-enum { SP_XCAP = 25, SP_MAXTASK = 2 * SP_RESCAP, SP_MAXSLOT = 4, SP_MAXMT = 40 };
+enum { SP_XCAP = AVK_SP_XCAP, SP_MAXTASK = 2 * SP_RESCAP, SP_MAXSLOT = 4, SP_MAXMT = 40 };
 enum { SPB_DONE = -2 };   // n_res value: the cluster is finished, every output has been written
 
 struct VarInfo { u16 pos, aoff; u8 l0, l1, alted, zyg; };                      // pos relative to the region start
