@@ -591,6 +591,7 @@ struct TierArgs {
     u32 spill_bytes;       // per warp
     int n_lo, n_hi;        // stages that scan all regions only take clusters with n_lo <= #variants <= n_hi
     int pop_budget;        // thread stage: queue pops a thread spends on one cluster before it hands it on
+    int batch_min;         // thread stage: lanes that must be waiting for a kind of bookkeeping before the warp does it (0 = TS_BATCH_MIN)
     u8 *dense_blobs;       // speculative dense search -> team stage: [dense_cap][SPB_SIZE], slot = index in the dense list
     u32 dense_cap;
 };
@@ -933,7 +934,7 @@ __global__ void __launch_bounds__(32 * SPEC_WARPS, 1) k_search_spec(DevBatch b, 
 // execute their task side by side; lanes whose cluster is finished commit it and take the next one from the list W (one
 // atomic per warp and round).  A cluster that does not fit the fixed workspace is appended to the reject list -- nothing
 // has been written for it -- and goes through the warp kernels (search / score / fused stages) as before.
-enum { THREAD_TPB = 256, TS_BATCH_MIN = 24 };
+enum { THREAD_TPB = 256, TS_BATCH_MIN = 16 };   // (default of TierArgs::batch_min; swept 1..24 on B200: 14-16 is the flat optimum at every batch size)
 struct ThreadSink {
     const avk_ts::Cluster &cl;
     const DevCompareOut &out;
@@ -962,6 +963,7 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
     const u32 n_work = t.n_work_ptr ? *t.n_work_ptr : t.n_work;
     const bool enabled = !cfg.enable_exact_shortcut && !(out.seq_off && cfg.enable_sequences);
     unsigned long long *slot = out.tot_slots ? out.tot_slots + (size_t)(blockIdx.x & (TOT_SLOTS - 1)) * TOT_STRIDE : nullptr;
+    const int batch_min = t.batch_min > 0 ? t.batch_min : TS_BATCH_MIN;
     u32 r = 0;
     bool more = true;                                            // warp-uniform: the list is not exhausted yet
     for (;;) {
@@ -973,7 +975,7 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
         {
             const bool want = S.phase == PH_COMMIT;
             const int cnt = __popc(__ballot_sync(AVK_FULL, want));
-            if (want && (cnt >= TS_BATCH_MIN || idle)) {
+            if (want && (cnt >= batch_min || idle)) {
                 int rc = S.rc;
                 S.phase = PH_FETCH;
                 if (rc == TS_REJECT) t.fail_list[atomicAdd(t.fail_ctr, 1u)] = r;
@@ -1005,7 +1007,7 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
         {
             const bool want = S.phase == PH_FETCH;
             const u32 m = __ballot_sync(AVK_FULL, want);
-            if (m && (__popc(m) >= TS_BATCH_MIN || idle)) {
+            if (m && (__popc(m) >= batch_min || idle)) {
                 if (more) {
                     const int leader = __ffs(m) - 1;
                     u32 base = 0;
@@ -1033,7 +1035,7 @@ __global__ void __launch_bounds__(THREAD_TPB, 1) k_compare_thread(DevBatch b, De
         {
             const bool want = S.phase == PH_RUN && S.task.kind == TK_NONE;
             const int cnt = __popc(__ballot_sync(AVK_FULL, want));
-            if (want && (cnt >= TS_BATCH_MIN || idle)) {
+            if (want && (cnt >= batch_min || idle)) {
                 S.advance();
                 if (S.task.kind != TK_NONE) S.task_setup();
             }
@@ -1273,6 +1275,7 @@ struct avk_ctx {
     int wide_b0 = 256;
     DevBuf dense_blobs, dense_blobs2;
     bool use_spec_search = true;    // AVK_NO_SPEC_SEARCH=1: the team stage searches the dense clusters itself (A/B timing)
+    int thread_batch_min = 0;       // AVK_THREAD_BATCH_MIN (0 = default)
     int thread_pop_budget = 0;      // AVK_THREAD_POP_BUDGET (0: by batch size -- a launch ends with its slowest thread, and the fewer clusters a
                                     // thread has the more that one cluster weighs: 64 pops for >= 2.5 M clusters, 48 for >= 1.2 M, else 32)
     bool use_thread_stage = true;   // AVK_NO_THREAD_STAGE=1: warp kernels only (A/B timing, tests of the warp path)
@@ -1392,6 +1395,7 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (const char *s = getenv("AVK_NO_THREAD_STAGE")) ctx->use_thread_stage = atoi(s) == 0;
     if (const char *s = getenv("AVK_NO_SPEC_SEARCH")) ctx->use_spec_search = atoi(s) == 0;
     if (const char *s = getenv("AVK_THREAD_POP_BUDGET")) ctx->thread_pop_budget = std::max(1, atoi(s));
+    if (const char *s = getenv("AVK_THREAD_BATCH_MIN")) ctx->thread_batch_min = std::min(32, std::max(1, atoi(s)));
     { const int v = getenv("AVK_PACKED_DWFA") ? atoi(getenv("AVK_PACKED_DWFA")) : 0; cudaMemcpyToSymbol(g_avk_packed_dwfa, &v, sizeof(int)); }
     if (const char *s = getenv("AVK_NO_SHAPE_SORT")) ctx->sort_shapes = atoi(s) == 0;
     if (const char *s = getenv("AVK_THREAD_MIN_REGIONS")) ctx->thread_min_regions = (u64)std::max(0LL, atoll(s));
@@ -1909,6 +1913,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
         // W -> one thread per cluster; what exceeds a thread's fixed workspace (W2) is a hard cluster
         u32 *LW2 = (u32 *)ctx->fail_t.p;
         TierArgs a = tier_args(ctx, keys ? (const u32 *)ctx->fail_s.p : LW, 12, 19, LW2, 13, sizeof(avk_ts::Work), nullptr);
+        a.batch_min = ctx->thread_batch_min;
         a.pop_budget = ctx->thread_pop_budget ? ctx->thread_pop_budget : (n >= 2500000 ? 64 : (n >= 1200000 ? 48 : 32));
         k_compare_thread<<<(unsigned)std::min<u64>((u64)sm, (n + THREAD_TPB - 1) / THREAD_TPB), THREAD_TPB, THREAD_TPB * sizeof(avk_ts::Work), ctx->side[0]>>>(R.db, R.out, R.cfg, a);
         ctx->launches += 1;
@@ -2303,7 +2308,7 @@ static int compare_streamed(avk_ctx *ctx, const avk_region_batch *batch, const a
     if (rc != AVK_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     for (avk_ctx *l : lanes) {
-        l->dense_n = ctx->dense_n; l->thread_pop_budget = ctx->thread_pop_budget; l->use_spec_search = ctx->use_spec_search; l->use_thread_stage = ctx->use_thread_stage; l->sort_shapes = ctx->sort_shapes; l->thread_min_regions = ctx->thread_min_regions;
+        l->dense_n = ctx->dense_n; l->thread_pop_budget = ctx->thread_pop_budget; l->thread_batch_min = ctx->thread_batch_min; l->use_spec_search = ctx->use_spec_search; l->use_thread_stage = ctx->use_thread_stage; l->sort_shapes = ctx->sort_shapes; l->thread_min_regions = ctx->thread_min_regions;
         for (auto &st : l->copy_streams) if (!st) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         l->up = l->copy_streams[0]; l->dn = l->copy_streams[1];
     }
