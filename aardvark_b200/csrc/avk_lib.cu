@@ -1879,7 +1879,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
         ctx->launches += 1;
     }
     const size_t spill_warp = 1u << 20, spill_half = (size_t)sm * 8 * spill_warp;
-    const u32 dense_cap = (u32)std::min<u64>(n, std::max<u64>(8192, n / 32));
+    const u32 dense_cap = (u32)std::min<u64>(n, std::max<u64>(65536, n / 16));   // slots of 3.6 KB; a list longer than this leaves its tail to the team stage
     // A list of hard clusters is solved in two launches: k_search_spec -- optimize_sequences with up to 32 queue pops in flight
     // and the exact-GT scoring of the equal-best results, one search per lane -- leaves the chosen solution in the cluster's
     // blob, and the team stage computes the metrics from it (or solves the cluster from scratch when the speculative search
