@@ -131,6 +131,9 @@ class RegionBatch:
         v0 = int(self.var_off[lo * k])
         v1 = int(self.var_off[hi * k])
         if v1 > v0:
+            ao = self.allele_off[v0:v1].astype(np.int64)
+            if ao.size > 1 and np.any(np.diff(ao) < 0):
+                raise ValueError("slice_regions needs an allele pool laid out in variant order (allele_off not monotone)")
             p0 = int(self.allele_off[v0])
             p1 = int(self.allele_off[v1 - 1]) + int(self.a0_len[v1 - 1]) + int(self.a1_len[v1 - 1])
         else:

@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU evidence: bash tools/gpu_call_multi.sh N   (gpurun --gpus N)
+# multi-GPU evidence: bash tools/gpu_calls/gpu_call_multi.sh N   (gpurun --gpus N)
 N=$1
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/m${N}_gpus.txt
