@@ -1320,10 +1320,18 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
         // it is not searched at all, and a search stops once it has used up what is left of the budget.
         // A solution with both haplotypes at 0 totals 0, which nothing later can beat and nothing earlier (>= 1) reaches:
         // the first such solution is the answer and no search is needed at all.
+        // "Nothing skipped" is read off the skipped variants' summed edit distance, which says nothing about a skipped variant
+        // whose ALT equals its REF (distance 0): in a cluster that holds such a record the zero-flip shortcuts are off (an
+        // incompatible no-op ALT cannot be kept, optimize_gt_alleles drops that child: exact_gt_optimizer.rs:293-305) and only
+        // the lower bound "ED or skip distance > 0 costs at least one flip" is used.
+        bool noop = false;
+#pragma unroll 1
+        for (int oi = lane; oi < n; oi += 32) noop = noop || LD32(vi(oi) + VI_ALTED) == 0u;
+        noop = __any_sync(AVK_FULL, noop);
         int best_total = 0x7fffffff;
         int lo = 0, hi = n_res;
 #pragma unroll 1
-        for (int ri = 0; ri < n_res; ++ri) {
+        for (int ri = 0; ri < n_res && !noop; ++ri) {
             int sum = 0;
 #pragma unroll 1
             for (int k = 0; k < 6; ++k) sum += LDI(res_num + (u32)(ri * 24 + 4 * k));
@@ -1333,9 +1341,10 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
         for (int ri = lo; ri < hi; ++ri) {
             const addr ra = res_alle + (u32)(ri * npad);
             const addr rnum = res_num + (u32)(ri * 24);
-            const bool zero0 = LDI(rnum) + LDI(rnum + 8) + LDI(rnum + 16) == 0;
-            const bool zero1 = LDI(rnum + 4) + LDI(rnum + 12) + LDI(rnum + 20) == 0;
-            if ((zero0 ? 0 : 1) + (zero1 ? 0 : 1) >= best_total) continue;
+            const int lb0 = LDI(rnum) + LDI(rnum + 8) + LDI(rnum + 16) == 0 ? 0 : 1;       // flips this haplotype costs at least
+            const int lb1 = LDI(rnum + 4) + LDI(rnum + 12) + LDI(rnum + 20) == 0 ? 0 : 1;
+            const bool zero0 = lb0 == 0 && !noop, zero1 = lb1 == 0 && !noop;                // ... and known to cost exactly none
+            if (lb0 + lb1 >= best_total) continue;
             int total = 0;
             bool lost = false;
 #pragma unroll 1
@@ -1348,7 +1357,7 @@ __device__ __noinline__ int RegionSolver<SMEM>::compare_score(u64 r, const avk_c
                     warp_copy<SMEM>(cur_obs + (u32)(h * npad), hap_alle, n);
                     __syncwarp();
                 } else {
-                    const int budget = best_total - total - ((h == 0 && !zero1) ? 1 : 0);
+                    const int budget = best_total - total - (h == 0 ? lb1 : 0);
                     rc = exact_gt(cur_obs + (u32)(h * npad), &errs, budget, cfg.exact_gt_max_expansions ? cfg.exact_gt_max_expansions : AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS);
                     if (rc) return rc;
                     lost = errs >= budget;

@@ -118,6 +118,7 @@ struct Shared {
     u32 truth_mask;
     u32 slot_types;                 // 4 bits per slot: variant type of metric-row slot k
     int N, nT, nQ, n_slots, wlen, mbf;
+    int has_noop;                   // some record's ALT equals its REF (alt_ed == 0)
     int qn, nres;
     u32 best, next_id;
     u32 spops;
@@ -508,6 +509,7 @@ static AVK_HD_NOINLINE bool load_cluster(Shared &S, const u8 *digest, int start,
     if ((end - start) + hdr[PH_SUM_L1 / 4] > 60000 || hdr[PH_SUM_ALLE / 4] > 60000) return false;   // logical offsets are 16-bit
     const u8 *recs = digest + PH_SIZE;
     u32 tm = 0;
+    int noop = 0;
     for (int k = 0; k < SP_MAXSLOT; ++k) S.type_bits[k] = 0;
     for (int i = 0; i < n; ++i) {
         const u32 *r = (const u32 *)(recs + (size_t)VI_SIZE * i);
@@ -515,6 +517,7 @@ static AVK_HD_NOINLINE bool load_cluster(Shared &S, const u8 *digest, int start,
         VarInfo v;
         v.pos = (u16)(r[VI_POS / 4] - (u32)start); v.aoff = (u16)r[VI_AOFF / 4];
         v.l0 = (u8)r[VI_L0 / 4]; v.l1 = (u8)r[VI_L1 / 4]; v.alted = (u8)r[VI_ALTED / 4];   // alt_ed <= max(l0, l1)
+        if (v.alted == 0) noop = 1;
         const u32 f = r[VI_FLAGS / 4];
         v.zyg = (u8)((f >> 8) & 0xff);
         S.var[i] = v;
@@ -523,7 +526,7 @@ static AVK_HD_NOINLINE bool load_cluster(Shared &S, const u8 *digest, int start,
         S.slot[i] = (u8)sl;
         if (sl < (u32)SP_MAXSLOT) S.type_bits[sl] |= 1u << i;
     }
-    S.truth_mask = tm;
+    S.truth_mask = tm; S.has_noop = noop;
     S.N = n; S.wlen = end - start; S.mbf = mbf;
     S.nT = hdr[PH_N0 / 4]; S.nQ = hdr[PH_N1 / 4]; S.n_slots = hdr[PH_NSLOTS / 4];
     S.slot_types = 0;
@@ -550,7 +553,9 @@ static AVK_HD inline void store_result(u8 *blob, int ri, const ResEnt &r, int n)
 // (result, haplotype) per lane, each an ordinary sequential best-first search in the lane's own queue (the code of the
 // thread solver's PC_X_* states).  A haplotype with ED 0 and nothing skipped scores 0 flips without a search, and the first
 // result with both haplotypes at 0 is the answer (RegionSolver::compare_score argues both).
-static AVK_HD inline bool hap_zero(const ResEnt &r, int h) { return h ? (r.ed2 + r.tvs2 + r.qvs2 == 0) : (r.ed1 + r.tvs1 + r.qvs1 == 0); }
+// (in a cluster that holds a record whose ALT equals its REF the summed skip distance does not tell whether a variant was
+// skipped: no shortcut there, see Solver::hap_zero in avk_thread_solver.cuh)
+static AVK_HD inline bool hap_zero(const Shared &S, const ResEnt &r, int h) { return !S.has_noop && (h ? (r.ed2 + r.tvs2 + r.qvs2 == 0) : (r.ed1 + r.tvs1 + r.qvs1 == 0)); }
 
 // longest common prefix from offset d0 of the two replayed sequences (DWFA with max ED 0, exact_gt_optimizer.rs:380)
 static AVK_HD_NOINLINE bool prefix(const View &V, Scratch &X, Counters &ctr, const Spec a, const Spec b, int d0, int *m, SeqInfo *ia_out, SeqInfo *ib_out) {
@@ -658,11 +663,11 @@ static AVK_HD_NOINLINE void exact_gt_lane(const View &V, Scratch &X, Counters &c
 // The searches to run: every non-zero haplotype of the results [lo, hi).  (Called after the search: its arrays alias.)
 static AVK_HD_NOINLINE void score_prepare(Shared &S, u32 xcap) {
     int lo = 0, hi = S.nres;
-    for (int i = 0; i < S.nres; ++i) if (hap_zero(S.res[i], 0) && hap_zero(S.res[i], 1)) { lo = i; hi = i + 1; break; }
+    for (int i = 0; i < S.nres; ++i) if (hap_zero(S, S.res[i], 0) && hap_zero(S, S.res[i], 1)) { lo = i; hi = i + 1; break; }
     int nt = 0;
     for (int ri = lo; ri < hi; ++ri)
         for (int h = 0; h < 2; ++h)
-            if (!hap_zero(S.res[ri], h)) { S.task_r[nt] = (u8)ri; S.task_h[nt] = (u8)h; nt += 1; }
+            if (!hap_zero(S, S.res[ri], h)) { S.task_r[nt] = (u8)ri; S.task_h[nt] = (u8)h; nt += 1; }
     S.n_tasks = nt; S.lo = lo; S.hi = hi; S.xpops = 0; S.xcap = xcap;
 }
 // First minimum of the summed errors (waffle_solver.rs:264-265).  false: a search was rejected.
@@ -673,7 +678,7 @@ static AVK_HD_NOINLINE bool score_combine(Shared &S) {
         int total = 0;
         u32 keep[2];
         for (int h = 0; h < 2; ++h) {
-            if (hap_zero(S.res[ri], h)) { keep[h] = h ? S.res[ri].a2 : S.res[ri].a1; continue; }
+            if (hap_zero(S, S.res[ri], h)) { keep[h] = h ? S.res[ri].a2 : S.res[ri].a1; continue; }
             const XOut &x = S.xout[t++];
             if (x.status) return false;
             total += x.errs; keep[h] = x.keep;

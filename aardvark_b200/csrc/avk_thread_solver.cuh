@@ -105,6 +105,7 @@ struct Cluster {
     int wlen, N, nT, nQ, mbf, n_slots;   // wlen = window length (end - start)
     u32 xcap;          // optimize_gt_alleles: node expansions allowed per call (AVK_ST_TIMEOUT beyond)
     u32 slot_types;    // 4 bits per slot: variant type of metric-row slot k
+    bool has_noop;     // some record's ALT equals its REF (alt_ed == 0)
 };
 
 // A sequence to build: HaplotypeTracker replay of `side` (0 truth, 1 query; 2 = the plain reference window) over the first
@@ -388,7 +389,7 @@ struct Solver {
         c.ref = contig + start; c.recs = digest + PH_SIZE; c.alle = c.recs + (size_t)VI_SIZE * n;
         c.xcap = xcap ? xcap : AVK_EXACT_GT_DEFAULT_MAX_EXPANSIONS;
         c.wlen = end - start; c.N = n; c.nT = hdr[PH_N0 / 4]; c.nQ = hdr[PH_N1 / 4]; c.mbf = mbf; c.n_slots = ns;
-        c.slot_types = 0;
+        c.slot_types = 0; c.has_noop = false;
         for (int s = 0; s < ns; ++s) c.slot_types |= (u32)digest[PH_SLOT_TYPE + s] << (4 * s);
         Work &W = w();
         u16 tm = 0;
@@ -399,6 +400,7 @@ struct Solver {
             VarInfo v;
             v.pos = (u16)(r[VI_POS / 4] - (u32)start); v.aoff = (u16)r[VI_AOFF / 4];
             v.l0 = (u8)r[VI_L0 / 4]; v.l1 = (u8)r[VI_L1 / 4]; v.alted = (u8)r[VI_ALTED / 4]; v.pad = 0;   // alt_ed <= max(l0, l1)
+            if (v.alted == 0) c.has_noop = true;
             W.var[i] = v;
             const u32 f = r[VI_FLAGS / 4];
             W.vtype[i] = (u8)(f & 0xff); W.zyg[i] = (u8)((f >> 8) & 0xff); W.slot[i] = (u8)(f >> 24);
@@ -423,7 +425,13 @@ struct Solver {
         task.kind = TK_PREFIX; task.a = a; task.b = b; task.d0 = d0; task.buf = 0; task.init = 0; task.src = 0; task.ed_in = 0;
         task.update = false; task.finalize = false;
     }
-    AVK_HD static bool hap_zero(const ResEnt &r, int hh) { return hh ? (r.ed2 + r.tvs2 + r.qvs2 == 0) : (r.ed1 + r.tvs1 + r.qvs1 == 0); }
+    // hap_lb: flips a result's haplotype costs at least (ED or skipped distance > 0: its zero-flip path cannot be exact).
+    // hap_zero: known to cost none -- ED 0 and nothing skipped.  "Nothing skipped" is read off the skipped variants' summed edit
+    // distance, which says nothing about a skipped variant whose ALT equals its REF (distance 0); an incompatible no-op ALT
+    // cannot be kept (optimize_gt_alleles drops that child, exact_gt_optimizer.rs:293-305), so in a cluster that holds such a
+    // record the shortcut is off and the search runs.
+    AVK_HD static int hap_lb(const ResEnt &r, int hh) { return (hh ? (r.ed2 + r.tvs2 + r.qvs2) : (r.ed1 + r.tvs1 + r.qvs1)) == 0 ? 0 : 1; }
+    AVK_HD bool hap_zero(const ResEnt &r, int hh) const { return hap_lb(r, hh) == 0 && !c.has_noop; }
 
     // ================================================================== the coroutine
     // Runs the cluster's control flow until it needs an alignment (returns with task.kind != TK_NONE) or the cluster is
@@ -565,13 +573,13 @@ struct Solver {
                 const ResEnt r = W.res[ri];
                 const bool z0 = hap_zero(r, 0), z1 = hap_zero(r, 1);
                 if (h == 0) {
-                    if ((z0 ? 0 : 1) + (z1 ? 0 : 1) >= best_total) { ri += 1; break; }
+                    if (hap_lb(r, 0) + hap_lb(r, 1) >= best_total) { ri += 1; break; }
                     total = 0; lost = false; keep0 = keep1 = 0;
                 }
                 if (h < 2 && !lost) {
                     const u32 ha = h ? r.a2 : r.a1;
                     if (h ? z1 : z0) { if (h) keep1 = ha; else keep0 = ha; h += 1; break; }
-                    budget = best_total - total - ((h == 0 && !z1) ? 1 : 0);
+                    budget = best_total - total - (h == 0 ? hap_lb(r, 1) : 0);
                     // optimize_gt_alleles (exact_gt_optimizer.rs:108-357) on this haplotype
                     hap_alt = ha; x_keep = 0;
                     x_next_id = 1; best_err = 0x7fffffff; have_best = false;

@@ -831,3 +831,62 @@ def test_vcf_ingest_vs_oracle(solver):
     _same_batch(built, host)
     cfg = CompareConfig(enable_sequences=False)
     assert solver.compare_batch(built, cfg).diff(orc.compare_batch(host, refs, compare_cfg(cfg))) == []
+
+
+def _random_adversarial_batch(n_clusters, seed):
+    """Clusters drawn like tests/test_properties.py: overlapping records, repeated positions, ALT == REF, every zygosity,
+    low-complexity windows; one window per cluster, laid end to end on one contig."""
+    from aardvark_b200.types import Coordinates, PhasedZygosity, Variant, VariantType
+    rng = np.random.default_rng(seed)
+    zygs = [PhasedZygosity.UnphasedHeterozygous, PhasedZygosity.PhasedHet01, PhasedZygosity.PhasedHet10, PhasedZygosity.HomozygousAlternate]
+    contig = bytearray()
+    regions = []
+    for r in range(n_clusters):
+        L = int(rng.integers(60, 160))
+        alphabet = [b"ACGT", b"AC", b"A"][int(rng.integers(0, 3))]
+        win = bytes(rng.choice(list(alphabet), size=L).astype(np.uint8))
+        base = len(contig)
+        contig += win
+        sides = []
+        for _ in range(2):
+            lst = []
+            for p in sorted(rng.integers(10, L - 20, size=int(rng.integers(0, 6))).tolist()):
+                l0 = int(rng.choice([1, 1, 1, 2, 3]))
+                a0 = win[p:p + l0]
+                kind = int(rng.integers(0, 4))
+                if kind == 0:
+                    a1 = bytes([int(rng.choice(list(b"ACGT")))]) + a0[1:]
+                elif kind == 1:
+                    a1 = a0[:1] + bytes(rng.choice(list(alphabet), size=int(rng.integers(1, 5))).astype(np.uint8))
+                elif kind == 2:
+                    a1 = a0[:1]
+                else:
+                    a1 = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(1, 4))).astype(np.uint8))
+                vt = (VariantType.Snv if len(a0) == 1 and len(a1) == 1 else VariantType.Insertion if len(a0) == 1 else
+                      VariantType.Deletion if len(a1) == 1 else VariantType.Indel)
+                lst.append((Variant(0, vt, base + p, a0, a1, max(len(a0), len(a1))), zygs[int(rng.integers(0, 4))]))
+            sides.append(lst)
+        if not sides[0] and not sides[1]:
+            continue
+        regions.append(CompareRegion(len(regions), Coordinates("c", base, base + L), [v for v, _ in sides[0]], [z for _, z in sides[0]],
+                                     [v for v, _ in sides[1]], [z for _, z in sides[1]]))
+    return np.frombuffer(bytes(contig), dtype=np.uint8).copy(), RegionBatch.from_compare_regions(regions, {"c": 0})
+
+
+def test_compare_random_adversarial_clusters_vs_oracle(solver):
+    """4000 randomly drawn clusters of adversarial shape through every pipeline variant: the default one (thread stage on in the
+    test suite), warp kernels only, and everything with three or more variants through the speculative solver."""
+    ref, batch = _random_adversarial_batch(4000, seed=2718)
+    for mbf in (50, 2):
+        cfg = CompareConfig(enable_sequences=False, max_branch_factor=mbf)
+        cpu = orc.compare_batch(batch, [ref], compare_cfg(cfg))
+        assert int((cpu.status[:batch.n_regions] == 0).sum()) > 0.9 * batch.n_regions
+        solver.set_reference([ref])
+        assert solver.compare_batch(batch, cfg).diff(cpu) == [], ("default", mbf)
+        for env in (dict(AVK_NO_THREAD_STAGE=1), dict(AVK_NO_THREAD_STAGE=1, AVK_DENSE_N=3), dict(AVK_DENSE_N=3, AVK_THREAD_POP_BUDGET=6)):
+            s = _solver_with_env(**env)
+            try:
+                s.set_reference([ref])
+                assert s.compare_batch(batch, cfg).diff(cpu) == [], (env, mbf)
+            finally:
+                s.close()
