@@ -833,7 +833,7 @@ def test_vcf_ingest_vs_oracle(solver):
     assert solver.compare_batch(built, cfg).diff(orc.compare_batch(host, refs, compare_cfg(cfg))) == []
 
 
-def _random_adversarial_batch(n_clusters, seed):
+def _random_adversarial_batch(n_clusters, seed, maxv=5, maxl0=3, maxins=4, wmax=160, k_inputs=2, p_copy=0.0):
     """Clusters drawn like tests/test_properties.py: overlapping records, repeated positions, ALT == REF, every zygosity,
     low-complexity windows; one window per cluster, laid end to end on one contig."""
     from aardvark_b200.types import Coordinates, PhasedZygosity, Variant, VariantType
@@ -842,22 +842,28 @@ def _random_adversarial_batch(n_clusters, seed):
     contig = bytearray()
     regions = []
     for r in range(n_clusters):
-        L = int(rng.integers(60, 160))
+        L = int(rng.integers(60, wmax))
         alphabet = [b"ACGT", b"AC", b"A"][int(rng.integers(0, 3))]
         win = bytes(rng.choice(list(alphabet), size=L).astype(np.uint8))
         base = len(contig)
         contig += win
         sides = []
-        for _ in range(2):
+        for k_in in range(k_inputs):
+            if k_in and rng.random() < p_copy:                 # merge inputs mostly agree: a copy of the first input, sometimes minus a record
+                lst = list(sides[0])
+                if lst and rng.random() < 0.3:
+                    lst.pop(int(rng.integers(0, len(lst))))
+                sides.append(lst)
+                continue
             lst = []
-            for p in sorted(rng.integers(10, L - 20, size=int(rng.integers(0, 6))).tolist()):
-                l0 = int(rng.choice([1, 1, 1, 2, 3]))
+            for p in sorted(rng.integers(10, L - 30, size=int(rng.integers(0, maxv + 1))).tolist()):
+                l0 = int(rng.integers(1, maxl0 + 1)) if rng.random() < 0.4 else 1
                 a0 = win[p:p + l0]
                 kind = int(rng.integers(0, 4))
                 if kind == 0:
                     a1 = bytes([int(rng.choice(list(b"ACGT")))]) + a0[1:]
                 elif kind == 1:
-                    a1 = a0[:1] + bytes(rng.choice(list(alphabet), size=int(rng.integers(1, 5))).astype(np.uint8))
+                    a1 = a0[:1] + bytes(rng.choice(list(alphabet), size=int(rng.integers(1, maxins + 1))).astype(np.uint8))
                 elif kind == 2:
                     a1 = a0[:1]
                 else:
@@ -866,17 +872,23 @@ def _random_adversarial_batch(n_clusters, seed):
                       VariantType.Deletion if len(a1) == 1 else VariantType.Indel)
                 lst.append((Variant(0, vt, base + p, a0, a1, max(len(a0), len(a1))), zygs[int(rng.integers(0, 4))]))
             sides.append(lst)
-        if not sides[0] and not sides[1]:
+        if not any(sides):
             continue
-        regions.append(CompareRegion(len(regions), Coordinates("c", base, base + L), [v for v, _ in sides[0]], [z for _, z in sides[0]],
-                                     [v for v, _ in sides[1]], [z for _, z in sides[1]]))
-    return np.frombuffer(bytes(contig), dtype=np.uint8).copy(), RegionBatch.from_compare_regions(regions, {"c": 0})
+        if k_inputs == 2:
+            regions.append(CompareRegion(len(regions), Coordinates("c", base, base + L), [v for v, _ in sides[0]], [z for _, z in sides[0]],
+                                         [v for v, _ in sides[1]], [z for _, z in sides[1]]))
+        else:
+            from aardvark_b200.types import MultiRegion
+            regions.append(MultiRegion(len(regions), Coordinates("c", base, base + L), [[v for v, _ in sd] for sd in sides], [[z for _, z in sd] for sd in sides]))
+    ref = np.frombuffer(bytes(contig), dtype=np.uint8).copy()
+    return ref, (RegionBatch.from_compare_regions(regions, {"c": 0}) if k_inputs == 2 else RegionBatch.from_multi_regions(regions, {"c": 0}))
 
 
-def test_compare_random_adversarial_clusters_vs_oracle(solver):
+@pytest.mark.parametrize("shape", [dict(seed=2718), dict(seed=31, maxv=8, maxl0=6, maxins=10, wmax=300)], ids=["small", "wide"])
+def test_compare_random_adversarial_clusters_vs_oracle(solver, shape):
     """4000 randomly drawn clusters of adversarial shape through every pipeline variant: the default one (thread stage on in the
     test suite), warp kernels only, and everything with three or more variants through the speculative solver."""
-    ref, batch = _random_adversarial_batch(4000, seed=2718)
+    ref, batch = _random_adversarial_batch(4000, **shape)
     for mbf in (50, 2):
         cfg = CompareConfig(enable_sequences=False, max_branch_factor=mbf)
         cpu = orc.compare_batch(batch, [ref], compare_cfg(cfg))
@@ -890,3 +902,16 @@ def test_compare_random_adversarial_clusters_vs_oracle(solver):
                 assert s.compare_batch(batch, cfg).diff(cpu) == [], (env, mbf)
             finally:
                 s.close()
+
+
+def test_merge_random_adversarial_clusters_vs_oracle(solver):
+    """solve_merge_region on randomly drawn clusters of four inputs that mostly agree (copies of the first input, sometimes
+    minus a record) or are drawn independently -- overlapping records, repeated positions, ALT == REF -- under every merge
+    configuration."""
+    ref, batch = _random_adversarial_batch(2500, seed=77, k_inputs=4, p_copy=0.7)
+    solver.set_reference([ref])
+    for cfg in (MergeConfig(majority_voting_enabled=True), MergeConfig(no_conflict_enabled=True), MergeConfig(conflict_selection=1), MergeConfig()):
+        gpu = solver.merge_batch(batch, cfg)
+        cpu = orc.merge_batch(batch, [ref], merge_cfg(cfg))
+        assert gpu.diff(cpu) == [], cfg
+    assert len(set(cpu.classification[:batch.n_regions].tolist())) >= 2
