@@ -819,6 +819,7 @@ __global__ void __launch_bounds__(128 * TEAMS_PER_CTA, 1) k_compare_team(DevBatc
 // (slot = index in X); the team stage that follows computes the metrics from it.  A cluster outside the fast path's limits
 // gets SPB_NONE in its slot and is solved from scratch by the team stage.
 enum { SPEC_WARPS = 8 };
+__device__ unsigned long long *g_spec_prof = nullptr;   // AVK_SPEC_PROFILE: per cluster {region, N, pops, load, search, score, metrics + commit} cycles
 struct SpecSink {
     const avk_sp::View &V;
     const DevCompareOut &out;
@@ -880,6 +881,7 @@ __global__ void __launch_bounds__(32 * SPEC_WARPS, 1) k_search_spec(DevBatch b, 
                   (int)cfg.max_branch_factor > 0;
         const u8 *digest = b.digest + b.digest_off[r];
         __syncwarp();
+        long long tp0 = clock64(), tp1 = tp0, tp2 = tp0, tp3 = tp0;
         if (ok) {
             if (lane == 0) ok = load_cluster(S, digest, (int)b.start[r], (int)b.end[r], (int)cfg.max_branch_factor);
             ok = __shfl_sync(AVK_FULL, ok, 0);
@@ -889,10 +891,15 @@ __global__ void __launch_bounds__(32 * SPEC_WARPS, 1) k_search_spec(DevBatch b, 
         if (ok) {
             View V;
             V.S = &S; V.ref = b.contig_ptr[c] + b.start[r]; V.recs = digest + PH_SIZE; V.alle = V.recs + (size_t)VI_SIZE * S.N;
-            if (search_warp(S, X, V, ctr)) {
+            tp1 = clock64();
+            const bool found_any = search_warp(S, X, V, ctr);
+            tp2 = clock64();
+            if (found_any) {
                 spops += S.spops;                                   // (warp-uniform reads of the shared state)
                 const int n = S.N, found = S.nres;
-                if (score_warp(S, X, V, ctr, xcap)) {
+                const bool scored = score_warp(S, X, V, ctr, xcap);
+                tp3 = clock64();
+                if (scored) {
                     xpops += S.xpops;
                     if (finish_here && metrics_warp(S, X, V, ctr)) {    // metrics + every output right here: nothing is left for the team stage
                         if (lane == 0) spec_commit(V, S, b, out, r, slot);
@@ -911,6 +918,12 @@ __global__ void __launch_bounds__(32 * SPEC_WARPS, 1) k_search_spec(DevBatch b, 
         }
         __syncwarp();
         if (lane == 0) *(int *)(blob + SPB_NRES) = nres;
+        if (g_spec_prof && lane == 0 && idx < 65536) {
+            unsigned long long *q = g_spec_prof + (size_t)idx * 8;
+            const long long tp4 = clock64();
+            q[0] = r; q[1] = ok ? (unsigned long long)S.N : 0ull; q[2] = S.spops; q[3] = (unsigned long long)(tp1 - tp0); q[4] = (unsigned long long)(tp2 - tp1);
+            q[5] = (unsigned long long)(tp3 - tp2); q[6] = (unsigned long long)(tp4 - tp3); q[7] = (unsigned long long)nres;
+        }
         __syncwarp();
     }
     if (t.work_out) {
@@ -1273,7 +1286,7 @@ struct avk_ctx {
     long long coop_arena0 = 256LL << 20, coop_arena1 = 2048LL << 20;
     int coop_cap_ints = 26000;
     int wide_b0 = 256;
-    DevBuf dense_blobs, dense_blobs2;
+    DevBuf dense_blobs, dense_blobs2, spec_prof;
     bool use_spec_search = true;    // AVK_NO_SPEC_SEARCH=1: the team stage searches the dense clusters itself (A/B timing)
     int thread_batch_min = 0;       // AVK_THREAD_BATCH_MIN (0 = default)
     int thread_pop_budget = 0;      // AVK_THREAD_POP_BUDGET (0: by batch size -- a launch ends with its slowest thread, and the fewer clusters a
@@ -1397,6 +1410,11 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     if (const char *s = getenv("AVK_THREAD_POP_BUDGET")) ctx->thread_pop_budget = std::max(1, atoi(s));
     if (const char *s = getenv("AVK_THREAD_BATCH_MIN")) ctx->thread_batch_min = std::min(32, std::max(1, atoi(s)));
     { const int v = getenv("AVK_PACKED_DWFA") ? atoi(getenv("AVK_PACKED_DWFA")) : 0; cudaMemcpyToSymbol(g_avk_packed_dwfa, &v, sizeof(int)); }
+    {   // AVK_SPEC_PROFILE=1: k_search_spec records per-cluster phase cycles (avk_spec_profile reads them back)
+        unsigned long long *pp = nullptr;
+        if (getenv("AVK_SPEC_PROFILE") && ensure(ctx, ctx->spec_prof, 65536 * 64) == AVK_OK) { pp = (unsigned long long *)ctx->spec_prof.p; cudaMemset(pp, 0, 65536 * 64); }
+        cudaMemcpyToSymbol(g_spec_prof, &pp, sizeof(pp));
+    }
     if (const char *s = getenv("AVK_NO_SHAPE_SORT")) ctx->sort_shapes = atoi(s) == 0;
     if (const char *s = getenv("AVK_THREAD_MIN_REGIONS")) ctx->thread_min_regions = (u64)std::max(0LL, atoll(s));
     if (const char *s = getenv("AVK_PIPELINE_BINS")) ctx->pipe_bins = std::max(-1, atoi(s));
@@ -1432,7 +1450,7 @@ extern "C" void avk_destroy(avk_ctx *ctx) {
                       &ctx->pos, &ctx->vtype, &ctx->zyg, &ctx->raw, &ctx->aoff, &ctx->l0, &ctx->l1, &ctx->pool, &ctx->alt_ed,
                       &ctx->status, &ctx->ed1, &ctx->ed2, &ctx->region_metrics, &ctx->type_mask, &ctx->vexp, &ctx->vobs, &ctx->vcls,
                       &ctx->totals, &ctx->tot_slots, &ctx->strat_off, &ctx->strat_idx, &ctx->strat_totals, &ctx->seq_off, &ctx->seq_len, &ctx->seq_pool,
-                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x, &ctx->fail_t, &ctx->fail_s, &ctx->shape_key, &ctx->dense_blobs, &ctx->dense_blobs2,
+                      &ctx->m_cls, &ctx->m_nidx, &ctx->m_idx, &ctx->m_rows, &ctx->m_perr, &ctx->m_tasks, &ctx->digest, &ctx->digest_sizes, &ctx->digest_offs, &ctx->scan_tmp, &ctx->blobs, &ctx->scratch, &ctx->arena, &ctx->arena2, &ctx->counters, &ctx->fail_a, &ctx->fail_b, &ctx->fail_c, &ctx->fail_d, &ctx->fail_h, &ctx->fail_w, &ctx->fail_x, &ctx->fail_t, &ctx->fail_s, &ctx->shape_key, &ctx->dense_blobs, &ctx->dense_blobs2, &ctx->spec_prof,
                       &ctx->work_ctr, &ctx->pair_a_off, &ctx->pair_b_off, &ctx->pair_a_len, &ctx->pair_b_len, &ctx->pair_ed, &ctx->pair_pool};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
@@ -3072,5 +3090,14 @@ extern "C" int avk_vcf_parse(avk_ctx *ctx, const uint8_t *text, uint64_t len, co
 #undef VDL
     CK(cudaStreamSynchronize(ctx->stream));
     out->n_variants = nv; out->allele_pool_len = nb;
+    return AVK_OK;
+}
+
+// diagnostics: per-cluster phase cycles of the LAST k_search_spec launches (AVK_SPEC_PROFILE=1); out = [n][8] u64
+extern "C" int avk_spec_profile(avk_ctx *ctx, unsigned long long *out, uint32_t n) {
+    if (!ctx || !out || !ctx->spec_prof.p) return AVK_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->spec_prof.p, (size_t)std::min<uint32_t>(n, 65536) * 64, cudaMemcpyDeviceToHost));
     return AVK_OK;
 }

@@ -258,7 +258,7 @@ static AVK_HD_NOINLINE int lcp(const View &V, const PSeq &A, int la, int x, cons
 // finalize (:183-198) if `finalize` on the wavefront `wf`, initialised per `init` (INIT_COPY: from `swf`; INIT_VALUE: one
 // diagonal at v0).  Sequences are built in this lane's scratch; the wavefronts may live in another lane's.  false: capacity exceeded.
 static AVK_HD_NOINLINE bool align(const View &V, Scratch &X, Counters &ctr, const Spec a, const Spec b, u16 *wf, int init, const u16 *swf, int ed_in, int v0,
-                                  bool update, bool finalize, int *ed_out, SeqInfo *ia_out, SeqInfo *ib_out) {
+                                  bool update, bool finalize, int *ed_out, SeqInfo *ia_out, SeqInfo *ib_out, int ed_cap = SP_EDCAP) {
     const Shared &S = *V.S;
     SeqInfo ia, ib;
     if (!replay(S, &X.seq[0], &ia, a) || !replay(S, &X.seq[1], &ib, b)) return false;
@@ -294,7 +294,7 @@ static AVK_HD_NOINLINE bool align(const View &V, Scratch &X, Counters &ctr, cons
             *ed_out = ed;
             return true;
         }
-        if (ed + 1 > SP_EDCAP) return false;
+        if (ed + 1 > ed_cap) { *ed_out = ed + 1; return false; }
         for (int i = n + 1; i >= 0; --i) {                     // increase_edit_distance() (:152-168): in place from the top
             int v = 0;
             if (i < n) v = wf[i];
@@ -783,10 +783,12 @@ static AVK_HD_NOINLINE bool metrics_walk(const View &V, Shared &S, bool collect)
     return ok;
 }
 // one of the listed alignments: wfa_ed of the two replayed sequences (finalize from an empty wavefront)
-static AVK_HD_NOINLINE void metrics_align(const View &V, Scratch &X, Counters &ctr, MTask &m) {
+// ed_cap < SP_EDCAP: a lane on its own gives up there (m.ok = 2) and the alignment is redone by the whole warp (metrics_align_warp)
+static AVK_HD_NOINLINE void metrics_align(const View &V, Scratch &X, Counters &ctr, MTask &m, int ed_cap = SP_EDCAP) {
     int ed = 0; SeqInfo ia, ib;
     const int n = V.S->N;
-    m.ok = align(V, X, ctr, spec(m.a_side, m.a_mask, n, true), spec(m.b_side, m.b_mask, n, true), X.wf[0], INIT_ZERO, nullptr, 0, 0, false, true, &ed, &ia, &ib) ? 1 : 0;
+    const bool ok = align(V, X, ctr, spec(m.a_side, m.a_mask, n, true), spec(m.b_side, m.b_mask, n, true), X.wf[0], INIT_ZERO, nullptr, 0, 0, false, true, &ed, &ia, &ib, ed_cap);
+    m.ok = ok ? 1 : ((ed_cap < SP_EDCAP && ed > ed_cap) ? 2 : 0);
     m.ed = (u32)ed;
 }
 
@@ -1020,6 +1022,57 @@ __device__ __noinline__ bool score_warp(Shared &S, Scratch &X, const View &V, Co
     return ok;
 }
 // final metrics after score_warp: S.bp filled, or false = outside the fast path's limits
+// wfa_ed of one listed alignment by the WHOLE warp: the lanes take the diagonals of a wavefront (a scalar lane needs (ED + 1)^2
+// sequential longest-common-prefix walks; with ED around 20 that is half a millisecond).  X0 = lane 0's scratch: sequences in
+// seq[0 / 1], wavefront ping-pong in wf[0 / 1].  Same recurrence and stop rule as align() with update == false, finalize == true.
+enum { SP_EDCAP_LANE = 6 };
+__device__ __noinline__ void metrics_align_warp(const View &V, Scratch &X0, Counters &ctr, MTask &m) {
+    const int lane = threadIdx.x & 31;
+    const Shared &S = *V.S;
+    const int n = S.N;
+    SeqInfo ia, ib;
+    bool built = true;
+    if (lane == 0) built = replay(S, &X0.seq[0], &ia, spec(m.a_side, m.a_mask, n, true)) && replay(S, &X0.seq[1], &ib, spec(m.b_side, m.b_mask, n, true));
+    built = __shfl_sync(0xffffffffu, (int)built, 0) != 0;
+    const int la = __shfl_sync(0xffffffffu, ia.len, 0), lb = __shfl_sync(0xffffffffu, ib.len, 0);
+    __syncwarp();
+    if (!built) { if (lane == 0) { m.ok = 0; m.ed = 0; } __syncwarp(); return; }
+    const PSeq &A = X0.seq[0], &B = X0.seq[1];
+    u16 *cur = X0.wf[0], *nxt = X0.wf[1];
+    if (lane == 0) cur[0] = 0;
+    __syncwarp();
+    int ed = 0;
+    bool ok = false;
+    for (;;) {
+        const int nd = 2 * ed + 1;
+        bool full = false;
+        int matched = 0;
+        for (int i = lane; i < nd; i += 32) {                      // extend() (dynamic_wfa.rs:94-130), one diagonal per lane
+            int d = cur[i];
+            int boff = d + ed - i;
+            if (boff < la && d < lb) { const int ext = lcp(V, A, la, boff, B, lb, d); d += ext; boff += ext; matched += ext; cur[i] = (u16)d; }
+            full = full || (boff >= la && d >= lb);
+        }
+        ctr.matched += (u64)matched;
+        if (lane == 0) ctr.cells += (u64)nd;
+        __syncwarp();
+        if (__any_sync(0xffffffffu, full)) { ok = true; break; }
+        if (ed + 1 > SP_EDCAP) break;
+        for (int i = lane; i < nd + 2; i += 32) {                  // increase_edit_distance() (:152-168) into the other buffer
+            int v = 0;
+            if (i < nd) v = cur[i];
+            if (i >= 1 && i - 1 < nd) v = max_i(v, cur[i - 1] + 1);
+            if (i >= 2 && i - 2 < nd) v = max_i(v, cur[i - 2] + 1);
+            nxt[i] = (u16)v;
+        }
+        __syncwarp();
+        u16 *t = cur; cur = nxt; nxt = t;
+        ed += 1;
+    }
+    if (lane == 0) { m.ok = ok ? 1 : 0; m.ed = (u32)ed; if (ok) ctr.alignments += 1; }
+    __syncwarp();
+}
+
 __device__ __noinline__ bool metrics_warp(Shared &S, Scratch &X, const View &V, Counters &ctr) {
     const int lane = threadIdx.x & 31;
     if (S.n_slots > SP_MAXSLOT) return false;
@@ -1029,9 +1082,13 @@ __device__ __noinline__ bool metrics_warp(Shared &S, Scratch &X, const View &V, 
     __syncwarp();
     if (!ok) return false;
     const int nt = S.n_mtasks;
-    for (int base = 0; base < nt; base += 32) {
-        if (base + lane < nt) metrics_align(V, X, ctr, S.mtask[base + lane]);
+    for (int base = 0; base < nt; base += 32) {                    // one alignment per lane, up to a small edit distance ...
+        if (base + lane < nt) metrics_align(V, X, ctr, S.mtask[base + lane], SP_EDCAP_LANE);
         __syncwarp();
+    }
+    for (int t = 0; t < nt; ++t) {                                 // ... and the few that go beyond it one after the other, 32 diagonals at a time
+        if (S.mtask[t].ok != 2) continue;                          // (warp-uniform: shared memory)
+        metrics_align_warp(V, (&X)[-lane], ctr, S.mtask[t]);
     }
     if (lane == 0) ok = metrics_walk(V, S, false);
     ok = __shfl_sync(0xffffffffu, ok, 0);
