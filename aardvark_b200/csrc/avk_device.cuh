@@ -347,7 +347,36 @@ __device__ __forceinline__ int coop_staged_cap16(int la, int lb, int cap_ints) {
     cap = min(cap, 2LL * (64000 - lb));
     return (int)max(cap, 0LL);
 }
-__device__ __noinline__ void coop_dwfa_body_staged() {
+// unaligned 32-bit read at a shared-window byte address (two aligned ld.shared + funnel shift); the address is the 32-bit
+// shared-space one so the reads stay LDS -- through a generic u8 pointer the compiler falls back to 64-bit generic loads
+__device__ __forceinline__ u32 lds4u_s(u32 saddr) {
+    u32 w0, w1;
+    const u32 a = saddr & ~3u;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
+    asm("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
+    return __funnelshift_r(w0, w1, (saddr & 3u) * 8u);
+}
+// equal leading bytes of a[ia..la) and b[ib..lb), ia < la && ib < lb, a/b shared-space addresses: four bases per step for every
+// lane alike (on unrelated sequence three diagonals in four end at the first base: a byte test first and a word loop for the
+// rest would leave the loop to a quarter of the lanes at the full issue cost)
+__device__ __forceinline__ int lcp_staged_w(u32 sa, int ia, int la, u32 sb, int ib, int lb) {
+    const int maxn = min(la - ia, lb - ib);
+    u32 pa = sa + (u32)ia, pb = sb + (u32)ib;
+    int k = 0;
+#pragma unroll 1
+    for (;;) {
+        const u32 x = lds4u_s(pa + k) ^ lds4u_s(pb + k);
+        if (x) { k += (__ffs(x) - 1) >> 3; break; }
+        k += 4;
+        if (k >= maxn) break;
+    }
+    return min(k, maxn);
+}
+// Wavefront entries are stored as offset + 1 with 0 = "no diagonal": two zero entries in front of each buffer and the zeroes
+// behind the old wavefront stand for the missing neighbours, so increase_edit_distance() (dynamic_wfa.rs:152-168) is three loads
+// and two max operations without a single bounds test.
+template <bool TO_FULL>
+__device__ __noinline__ void coop_dwfa_body_staged_t() {
     CoopJob &J = *(CoopJob *)avk_dyn_smem;
     const int tid = threadIdx.x, T = blockDim.x;
     VSeq<false> A, B;
@@ -356,57 +385,62 @@ __device__ __noinline__ void coop_dwfa_body_staged() {
     const int la = A.len, lb = B.len, max_ed = J.max_ed;
     u8 *sa = avk_dyn_smem + COOP_JOB_BYTES;
     u8 *sb = sa + ((la + 8 + 3) & ~3);
-    const int cap = coop_staged_cap16(la, lb, J.cap_ints);
-    unsigned short *cur = (unsigned short *)(sb + ((lb + 8 + 3) & ~3)), *nxt = cur + cap;
+    const int cap = coop_staged_cap16(la, lb, J.cap_ints) - 4;      // (two pad entries per buffer)
+    unsigned short *cur = (unsigned short *)(sb + ((lb + 8 + 3) & ~3)) + 2, *nxt = cur + cap + 2;
     const int e_cap = (cap - 3) / 2;
-    const bool to_full = J.to_full != 0;
     int *gw = (int *)(uintptr_t)J.wf;
     int e = J.ed, status = DWFA_OK;
+    const u32 sa_s = (u32)__cvta_generic_to_shared(sa), sb_s = (u32)__cvta_generic_to_shared(sb);
     coop_stage(sa, A);
     coop_stage(sb, B);
 #pragma unroll 1
-    for (int i = tid; i < 2 * e + 1; i += T) cur[i] = (unsigned short)gw[i];
+    for (int i = tid; i < 2 * cap + 4; i += T) cur[i - 2] = 0;       // both buffers and their pads (they are adjacent)
+    __syncthreads();
+#pragma unroll 1
+    for (int i = tid; i < 2 * e + 1; i += T) cur[i] = (unsigned short)(gw[i] + 1);
     __syncthreads();
     unsigned long long matched = 0, cells = 0;
-    bool flag = false;
+    u32 reached = 0;
 #pragma unroll 1
     for (int i = tid; i < 2 * e + 1; i += T) {           // extend() of the wavefront as it stands
-        int d = cur[i];
+        int d = (int)cur[i] - 1;
         int boff = d + e - i;
-        if (boff < la && d < lb) { const int ext = lcp_staged(sa, boff, la, sb, d, lb); d += ext; boff += ext; matched += ext; cur[i] = (unsigned short)d; }
-        flag = flag || (to_full ? (boff >= la && d >= lb) : (boff >= la || d >= lb));
+        if (boff < la && d < lb) { const int ext = lcp_staged_w(sa_s, boff, la, sb_s, d, lb); d += ext; boff += ext; matched += ext; cur[i] = (unsigned short)(d + 1); }
+        const u32 ra = boff >= la, rb = d >= lb;
+        reached |= TO_FULL ? (ra & rb) : (ra | rb);
     }
     cells += 2 * e + 1;
-    int stop = __syncthreads_or(flag);
+    int stop = __syncthreads_or(reached != 0u);
 #pragma unroll 1
     while (!stop) {
         e += 1;
         if (e > max_ed) { status = DWFA_MAX_ED; break; }                 // *ed stays incremented, wavefront not grown
         if (e > e_cap) { status = DWFA_COOP_SPILL; e -= 1; break; }      // does not fit shared memory: back to the warp path
-        const int n = 2 * e + 1, n_old = n - 2;
-        flag = false;
+        const int n = 2 * e + 1;
+        reached = 0;
 #pragma unroll 1
         for (int i = tid; i < n; i += T) {
-            int d = 0;                                                   // increase_edit_distance(): dynamic_wfa.rs:152-168
-            if (i < n_old) d = cur[i];
-            if (i >= 1 && i - 1 < n_old) d = max(d, (int)cur[i - 1] + 1);
-            if (i >= 2 && i - 2 < n_old) d = max(d, (int)cur[i - 2] + 1);
+            int d = (int)max((u32)cur[i], max((u32)cur[i - 1], (u32)cur[i - 2]) + 1u) - 1;   // increase_edit_distance()
             int boff = d + e - i;
-            if (boff < la && d < lb) { const int ext = lcp_staged(sa, boff, la, sb, d, lb); d += ext; boff += ext; matched += ext; }
-            nxt[i] = (unsigned short)d;
-            { const bool ra = boff >= la, rb = d >= lb; flag = flag | (to_full ? (ra & rb) : (ra | rb)); }
+            if (boff < la && d < lb) { const int ext = lcp_staged_w(sa_s, boff, la, sb_s, d, lb); d += ext; boff += ext; matched += ext; }
+            nxt[i] = (unsigned short)(d + 1);
+            const u32 ra = boff >= la, rb = d >= lb;
+            reached |= TO_FULL ? (ra & rb) : (ra | rb);
         }
         cells += n;
-        stop = __syncthreads_or(flag);
+        stop = __syncthreads_or(reached != 0u);
         unsigned short *t = cur; cur = nxt; nxt = t;
     }
     const int n_out = 2 * (status == DWFA_MAX_ED ? e - 1 : e) + 1;
 #pragma unroll 1
-    for (int i = tid; i < n_out; i += T) gw[i] = (int)cur[i];
+    for (int i = tid; i < n_out; i += T) gw[i] = (int)cur[i] - 1;
     if (matched) atomicAdd(&J.matched, matched);
     if (tid == 0) { J.ed = e; J.status = status; J.cells = cells; }
     __threadfence_block();
     __syncthreads();
+}
+__device__ __forceinline__ void coop_dwfa_body_staged() {
+    if (((CoopJob *)avk_dyn_smem)->to_full) coop_dwfa_body_staged_t<true>(); else coop_dwfa_body_staged_t<false>();
 }
 
 // ---- fastest path of the CTA-wide DWFA: 2-bit packed sequences, four diagonals per thread and trip ---------------------------------
