@@ -1308,6 +1308,12 @@ struct avk_ctx {
     // (copies then go on `stream`).  A sibling lane shares the owner's compute streams (own_streams == false).
     cudaStream_t up = nullptr, dn = nullptr;
     cudaStream_t copy_streams[2] = {nullptr, nullptr};   // created on first use, kept
+    // Concurrent lanes (compare_lanes): a large batch is cut into contiguous bins that are solved AT THE SAME TIME by sibling
+    // contexts of this device, each with its own streams and buffers and one host thread -- one bin's upload runs beside
+    // another's kernels, and the kernels of different bins fill each other's tails (a pass ends with its slowest clusters).
+    std::vector<avk_ctx *> lanes;   // lanes[0] == this context
+    int n_lanes = 0;                // AVK_LANES (0 or 1 = off, the default: measured, the bins' passes keep their fixed cost -- DESIGN.md section 5)
+    u64 lane_min_regions = 2000000; // AVK_LANE_MIN_REGIONS: smaller batches are solved in one piece
     cudaEvent_t ev_up = nullptr, ev_done = nullptr;
     bool own_streams = true;
 };
@@ -1417,6 +1423,8 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     }
     if (const char *s = getenv("AVK_NO_SHAPE_SORT")) ctx->sort_shapes = atoi(s) == 0;
     if (const char *s = getenv("AVK_THREAD_MIN_REGIONS")) ctx->thread_min_regions = (u64)std::max(0LL, atoll(s));
+    if (const char *s = getenv("AVK_LANES")) ctx->n_lanes = std::max(0, std::min(8, atoi(s)));
+    if (const char *s = getenv("AVK_LANE_MIN_REGIONS")) ctx->lane_min_regions = (u64)std::max(1LL, atoll(s));
     if (const char *s = getenv("AVK_PIPELINE_BINS")) ctx->pipe_bins = std::max(-1, atoi(s));
     if (const char *s = getenv("AVK_PIPELINE_BIN_REGIONS")) ctx->pipe_bin_regions = (u64)std::max(1LL, atoll(s));
     if (const char *s = getenv("AVK_PIPELINE_MIN_REGIONS")) ctx->pipe_min_regions = (u64)std::max(1LL, atoll(s));
@@ -1439,9 +1447,23 @@ extern "C" int avk_create(int device, avk_ctx **out) {
     return AVK_OK;
 }
 
+// A lane: a second context on the owner's device that reads the owner's reference and stratification tables and has its own
+// streams and batch / result buffers.  Several batches (whole call sets) are then in flight on the one GPU, one host thread per
+// context: one batch's copies run beside another's kernels, and the kernels of different batches fill each other's tails.
+extern "C" int avk_create_lane(avk_ctx *owner, avk_ctx **out) {
+    if (!owner || !out) return AVK_ERR_INVALID;
+    if (owner->ref_owner) { owner->err = "avk_create_lane: the owner is itself a lane"; return AVK_ERR_INVALID; }
+    const int rc = avk_create(owner->device, out);
+    if (rc != AVK_OK) { owner->err = "avk_create_lane: could not create the context"; return rc; }
+    (*out)->ref_owner = owner;
+    return AVK_OK;
+}
+
 extern "C" void avk_destroy(avk_ctx *ctx) {
     if (!ctx) return;
     for (auto &sb : ctx->sib) if (sb) { avk_destroy(sb); sb = nullptr; }
+    for (size_t i = 1; i < ctx->lanes.size(); ++i) avk_destroy(ctx->lanes[i]);
+    ctx->lanes.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &st : ctx->side) if (st) cudaStreamSynchronize(st);
@@ -1476,10 +1498,12 @@ extern "C" uint64_t avk_launch_count(const avk_ctx *ctx) {
     if (!ctx) return 0;
     uint64_t n = ctx->launches;
     for (const avk_ctx *sb : ctx->sib) if (sb) n += sb->launches;
+    for (size_t i = 1; i < ctx->lanes.size(); ++i) n += ctx->lanes[i]->launches;
     return n;
 }
 
 extern "C" int avk_set_reference(avk_ctx *ctx, uint32_t n_contigs, const uint8_t *const *seqs, const uint64_t *lens) {
+    if (ctx && ctx->ref_owner) { ctx->err = "a lane reads its owner's reference: call avk_set_reference on the owner"; return AVK_ERR_INVALID; }
     if (!ctx || (n_contigs && (!seqs || !lens))) return AVK_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     for (DevBuf &b : ctx->contig_bufs) if (b.p) cudaFree(b.p);
@@ -1500,6 +1524,7 @@ extern "C" int avk_set_reference(avk_ctx *ctx, uint32_t n_contigs, const uint8_t
 }
 
 extern "C" int avk_set_stratifications(avk_ctx *ctx, const avk_strat_intervals *in) {
+    if (ctx && ctx->ref_owner) { ctx->err = "a lane reads its owner's stratifications: call avk_set_stratifications on the owner"; return AVK_ERR_INVALID; }
     if (!ctx) return AVK_ERR_INVALID;
     if (!in || in->n_strata > 64 || (in->n_strata && in->n_contigs && !in->off)) { ctx->err = "avk_set_stratifications: at most 64 strata, non-null offsets"; return AVK_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
@@ -2072,8 +2097,9 @@ static int compare_launch(avk_ctx *ctx, const avk_compare_cfg *cfg, bool want_se
     if (rc != AVK_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (R.want_contain && n) {
-        k_strat_contain<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(R.db, n, ctx->st_n, ctx->st_contigs, (const u64 *)ctx->st_off.p,
-                                                                              (const u32 *)ctx->st_first.p, (const u32 *)ctx->st_pmax.p, (u64 *)ctx->st_mask.p);
+        const avk_ctx *so = ref_of(ctx);        // a lane reads its owner's interval tables
+        k_strat_contain<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(R.db, n, so->st_n, so->st_contigs, (const u64 *)so->st_off.p,
+                                                                              (const u32 *)so->st_first.p, (const u32 *)so->st_pmax.p, (u64 *)ctx->st_mask.p);
         ctx->launches += 1;
     }
     rc = run_compare_pipeline(ctx, R);
@@ -2206,7 +2232,7 @@ static int prepare_outputs_on_device(avk_ctx *ctx, const avk_compare_out *out, u
     }
     strata = strata_wanted(out);
     strat_dev = strata && !out->strat_off;
-    if ((strat_dev || out->containment) && (ctx->st_n == 0 || (strat_dev && ctx->st_n != out->n_strata) || ctx->st_contigs != (u32)ref_of(ctx)->contig_lens.size())) {
+    if ((strat_dev || out->containment) && (ref_of(ctx)->st_n == 0 || (strat_dev && ref_of(ctx)->st_n != out->n_strata) || ref_of(ctx)->st_contigs != (u32)ref_of(ctx)->contig_lens.size())) {
         ctx->err = "the device containment lookup needs avk_set_stratifications (same number of strata as n_strata, contigs as the reference)";
         return AVK_ERR_INVALID;
     }
@@ -2358,9 +2384,17 @@ static int compare_streamed(avk_ctx *ctx, const avk_region_batch *batch, const a
     return AVK_OK;
 }
 
+static int compare_lanes(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out, int n);
 extern "C" int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out) {
     if (!ctx) return AVK_ERR_INVALID;
     if (!batch) { ctx->err = "null batch"; return AVK_ERR_INVALID; }
+    const int want_lanes = ctx->n_lanes;
+    if (want_lanes > 1 && batch->n_regions >= ctx->lane_min_regions && !ctx->ref_owner && (ctx->pipe_bins == 0 || ctx->pipe_bins == 1)) {
+        if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
+        const int rc = validate_batch(ctx, batch, true);
+        if (rc != AVK_OK) return rc;
+        return compare_lanes(ctx, batch, cfg, out, want_lanes);
+    }
     if (ctx->pipe_bins != 0 && ctx->pipe_bins != 1 && batch->n_regions >= ctx->pipe_min_regions && !ctx->ref_owner) {
         const u64 n_bins = ctx->pipe_bins > 1 ? (u64)ctx->pipe_bins : std::min<u64>(16, (batch->n_regions + ctx->pipe_bin_regions / 2) / ctx->pipe_bin_regions);
         if (n_bins >= 2) {
@@ -2377,26 +2411,47 @@ extern "C" int avk_compare_batch(avk_ctx *ctx, const avk_region_batch *batch, co
 // Cost proxy per region: (variants + 1) * window + sum over variants of max(|allele0|, |allele1|)^2 (the SV tail is quadratic).
 // cuts[k] = first region of bin k: the first index whose cumulative cost reaches k/n of the total (bins are contiguous in
 // region_id order, so concatenating the bins' results restores the reference's output order, src/main.rs:271).
+static inline u64 region_cost(const avk_region_batch *b, u64 r) {
+    const u64 K = b->n_inputs, v0 = b->var_off[r * K], v1 = b->var_off[(r + 1) * K];
+    u64 c = (v1 - v0 + 1) * (u64)(b->end[r] > b->start[r] ? b->end[r] - b->start[r] : 0);
+    for (u64 v = v0; v < v1; ++v) { const u64 m = std::max(b->variants.a0_len[v], b->variants.a1_len[v]); c += m * m; }
+    return c;
+}
+// The sums are taken per chunk of 16 Ki regions (by several host threads when the batch is large: this runs inside the timed
+// call of the lane / multi-GPU entry points); a cut is then looked up in the chunk that holds it.
 extern "C" int avk_partition_regions(const avk_region_batch *b, uint32_t n_bins, uint64_t *cuts) {
     if (!b || !cuts || n_bins == 0) return AVK_ERR_INVALID;
-    const u64 n = b->n_regions, K = b->n_inputs;
-    std::vector<u64> cum(n + 1, 0);
-    for (u64 r = 0; r < n; ++r) {
-        const u64 v0 = b->var_off[r * K], v1 = b->var_off[(r + 1) * K];
-        u64 c = (v1 - v0 + 1) * (u64)(b->end[r] > b->start[r] ? b->end[r] - b->start[r] : 0);
-        for (u64 v = v0; v < v1; ++v) { const u64 m = std::max(b->variants.a0_len[v], b->variants.a1_len[v]); c += m * m; }
-        cum[r + 1] = cum[r] + c;
-    }
-    const unsigned __int128 total = cum[n];
+    const u64 n = b->n_regions, CH = 16384, n_ch = (n + CH - 1) / CH;
+    std::vector<u64> chunk(n_ch + 1, 0);
+    auto sum_chunks = [&](u64 c0, u64 c1) {
+        for (u64 c = c0; c < c1; ++c) {
+            u64 t = 0;
+            for (u64 r = c * CH, e = std::min(n, r + CH); r < e; ++r) t += region_cost(b, r);
+            chunk[c + 1] = t;
+        }
+    };
+    const u64 n_thr = n >= 500000 ? std::min<u64>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (n_thr > 1) {
+        std::vector<std::thread> th;
+        for (u64 t = 0; t < n_thr; ++t) th.emplace_back(sum_chunks, n_ch * t / n_thr, n_ch * (t + 1) / n_thr);
+        for (auto &t : th) t.join();
+    } else sum_chunks(0, n_ch);
+    for (u64 c = 0; c < n_ch; ++c) chunk[c + 1] += chunk[c];
+    const unsigned __int128 total = chunk[n_ch];
     cuts[0] = 0;
     for (uint32_t k = 1; k < n_bins; ++k) {
-        // first r with cum[r + 1] * n_bins >= total * k
-        u64 lo = 0, hi = n;
-        while (lo < hi) {
+        // first r with cum[r + 1] * n_bins >= total * k, cum[r + 1] = cost of regions [0, r]
+        u64 lo = 0, hi = n_ch;
+        while (lo < hi) {                                   // first chunk whose inclusive sum reaches the target
             const u64 m = (lo + hi) >> 1;
-            if ((unsigned __int128)cum[m + 1] * n_bins < total * k) lo = m + 1; else hi = m;
+            if ((unsigned __int128)chunk[m + 1] * n_bins < total * k) lo = m + 1; else hi = m;
         }
-        cuts[k] = std::max(lo, cuts[k - 1]);
+        u64 r = n;
+        if (lo < n_ch) {
+            u64 cum = chunk[lo];
+            for (r = lo * CH; r < n; ++r) { cum += region_cost(b, r); if ((unsigned __int128)cum * n_bins >= total * k) break; }
+        }
+        cuts[k] = std::max(std::min(r, n), cuts[k - 1]);
     }
     cuts[n_bins] = n;
     return AVK_OK;
@@ -2405,6 +2460,27 @@ extern "C" int avk_partition_regions(const avk_region_batch *b, uint32_t n_bins,
 // One host thread per context (= per GPU); bin k goes to ctxs[k].  Every device copies its slice of the results straight into
 // the caller's arrays at its bin offset -- the bins are contiguous, so on one node the "gather" is those copies -- and the
 // summary counters of the bins are added on the host.  Every context must hold the reference (avk_set_reference).
+static int compare_bins_concurrent(avk_ctx *const *ctxs, uint32_t n_ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out) {
+    avk_ctx *ctx = ctxs[0];
+    std::vector<u64> cuts(n_ctx + 1);
+    if (batch->n_regions && (!batch->variants.a0_len || !batch->variants.a1_len) && batch->variants.n_variants) { ctx->err = "null variant arrays"; return AVK_ERR_INVALID; }
+    avk_partition_regions(batch, n_ctx, cuts.data());
+    std::vector<BinTotals> bts(n_ctx);
+    std::vector<int> rcs(n_ctx, AVK_OK);
+    std::vector<std::thread> th;
+    auto work = [&](uint32_t k) {
+        if (!ctxs[k]) { rcs[k] = AVK_ERR_INVALID; return; }
+        rcs[k] = compare_bin(ctxs[k], batch, cuts[k], cuts[k + 1], cfg, out, bts[k]);
+    };
+    for (uint32_t k = 1; k < n_ctx; ++k) th.emplace_back(work, k);
+    work(0);                                                // the caller's thread takes the first bin
+    for (auto &t : th) t.join();
+    for (uint32_t k = 0; k < n_ctx; ++k)
+        if (rcs[k] != AVK_OK) { if (k && ctxs[k]) ctx->err = "bin " + std::to_string(k) + ": " + ctxs[k]->err; return rcs[k]; }
+    const bool strata = strata_wanted(out);
+    for (uint32_t k = 0; k < n_ctx; ++k) store_totals(out, bts[k], strata, k > 0);
+    return AVK_OK;
+}
 extern "C" int avk_compare_batch_multi(avk_ctx *const *ctxs, uint32_t n_ctx, const avk_region_batch *batch,
                                        const avk_compare_cfg *cfg, avk_compare_out *out) {
     if (!ctxs || n_ctx == 0 || !ctxs[0]) return AVK_ERR_INVALID;
@@ -2412,23 +2488,39 @@ extern "C" int avk_compare_batch_multi(avk_ctx *const *ctxs, uint32_t n_ctx, con
     if (!cfg || !out || !out->status) { ctx->err = "null cfg/out/status"; return AVK_ERR_INVALID; }
     int rc = validate_batch(ctx, batch, true);
     if (rc != AVK_OK) return rc;
-    std::vector<u64> cuts(n_ctx + 1);
-    if (batch->n_regions && (!batch->variants.a0_len || !batch->variants.a1_len) && batch->variants.n_variants) { ctx->err = "null variant arrays"; return AVK_ERR_INVALID; }
-    avk_partition_regions(batch, n_ctx, cuts.data());
-    std::vector<BinTotals> bts(n_ctx);
-    std::vector<int> rcs(n_ctx, AVK_OK);
-    std::vector<std::thread> th;
-    for (uint32_t k = 0; k < n_ctx; ++k)
-        th.emplace_back([&, k]() {
-            if (!ctxs[k]) { rcs[k] = AVK_ERR_INVALID; return; }
-            rcs[k] = compare_bin(ctxs[k], batch, cuts[k], cuts[k + 1], cfg, out, bts[k]);
-        });
-    for (auto &t : th) t.join();
-    for (uint32_t k = 0; k < n_ctx; ++k)
-        if (rcs[k] != AVK_OK) { if (k && ctxs[k]) ctx->err = "device " + std::to_string(k) + ": " + ctxs[k]->err; return rcs[k]; }
-    const bool strata = strata_wanted(out);
-    for (uint32_t k = 0; k < n_ctx; ++k) store_totals(out, bts[k], strata, k > 0);
+    return compare_bins_concurrent(ctxs, n_ctx, batch, cfg, out);
+}
+
+// One large batch on ONE GPU, as concurrent lanes: sibling contexts of this device (own streams and buffers, this context's
+// reference and stratification tables) take one contiguous bin each.  Measured on the whole-genome batch (3.95 M clusters):
+// see DESIGN.md section 5.
+static int ensure_lanes(avk_ctx *ctx, int n) {
+    if (ctx->lanes.empty()) ctx->lanes.push_back(ctx);
+    while ((int)ctx->lanes.size() < n) {
+        avk_ctx *l = nullptr;
+        const int rc = avk_create(ctx->device, &l);
+        if (rc != AVK_OK) { ctx->err = "compare lanes: could not create a sibling context"; return rc; }
+        l->ref_owner = ctx;
+        l->n_lanes = 1;
+        l->pipe_bins = 0;
+        ctx->lanes.push_back(l);
+    }
+    for (size_t i = 1; i < ctx->lanes.size(); ++i) {
+        avk_ctx *l = ctx->lanes[i];
+        l->dense_n = ctx->dense_n; l->thread_pop_budget = ctx->thread_pop_budget; l->thread_batch_min = ctx->thread_batch_min; l->use_spec_search = ctx->use_spec_search;
+        l->use_thread_stage = ctx->use_thread_stage; l->sort_shapes = ctx->sort_shapes; l->thread_min_regions = ctx->thread_min_regions;
+        l->coop_arena0 = ctx->coop_arena0; l->coop_arena1 = ctx->coop_arena1; l->coop_cap_ints = ctx->coop_cap_ints; l->wide_b0 = ctx->wide_b0;
+    }
     return AVK_OK;
+}
+static int compare_lanes(avk_ctx *ctx, const avk_region_batch *batch, const avk_compare_cfg *cfg, avk_compare_out *out, int n) {
+    int rc = ensure_lanes(ctx, n);
+    if (rc != AVK_OK) return rc;
+    rc = compare_bins_concurrent(ctx->lanes.data(), (uint32_t)n, batch, cfg, out);
+    ctx->have_batch = ctx->have_result = false;             // the owner holds one bin only: nothing "resident" to re-run or download
+    // the owner's timings describe the call: the longest device pass of the lanes
+    for (int i = 1; i < n; ++i) if (ctx->lanes[i]->last_ms[4] > ctx->last_ms[4]) for (int k = 0; k < 5; ++k) ctx->last_ms[k] = ctx->lanes[i]->last_ms[k];
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------ region builder

@@ -61,6 +61,7 @@ def load():
     vp = C.c_void_p
     lib.avk_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.avk_destroy.argtypes = [vp]
+    lib.avk_create_lane.argtypes = [vp, C.POINTER(vp)]
     lib.avk_last_error.restype = C.c_char_p
     lib.avk_last_error.argtypes = [vp]
     lib.avk_launch_count.restype = C.c_uint64
@@ -104,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "avk_wfa_ed_batch", "avk_compare_seq_offsets", "avk_compare_upload", "avk_compare_run_resident",
     "avk_compare_download", "avk_build_regions", "avk_build_regions_bed", "avk_regions_download", "avk_summary_write", "avk_vcf_records_write", "avk_vcf_parse", "avk_last_timings", "avk_last_work", "avk_launch_count", "avk_int_peak", "avk_last_tier_overflow", "avk_last_tier_ms",
     "avk_compare_batch_range", "avk_compare_batch_multi", "avk_merge_batch_multi", "avk_partition_regions", "avk_compare_upload_range",
-    "avk_compare_result_device", "avk_set_stratifications",
+    "avk_compare_result_device", "avk_set_stratifications", "avk_create_lane",
 ]
 
 
@@ -142,6 +143,16 @@ class Solver:
                            "(aardvark_b200 has no CPU fallback)")
         self.contig_index = {}
         self._contigs = []
+
+    def lane(self) -> "Solver":
+        """A second context on this solver's GPU that shares its resident reference and stratifications (avk_create_lane):
+        use one per host thread to keep several batches in flight.  Close the lanes before this solver."""
+        ln = Solver.__new__(Solver)
+        ln._lib = self._lib
+        ln._ctx = C.c_void_p()
+        self._check(self._lib.avk_create_lane(self._ctx, C.byref(ln._ctx)), "avk_create_lane")
+        ln.contig_index, ln._contigs, ln._owner = self.contig_index, self._contigs, self
+        return ln
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -326,6 +337,65 @@ class Solver:
         if isinstance(res, RegionError):
             raise res
         return res
+
+
+class SolverPool:
+    """Several batches in flight on ONE GPU: the owner context plus `n - 1` lanes (avk_create_lane), one host thread each.
+    `compare_batches` hands the batches to the contexts as they become free and returns the outputs in input order; the
+    calls are plain avk_compare_batch calls (ctypes releases the GIL), so results are those of Solver.compare_batch."""
+
+    def __init__(self, device: int = 0, n: int = 4):
+        self.owner = Solver(device)
+        self.solvers = [self.owner]
+        self._n = max(1, int(n))
+
+    def set_reference(self, contigs, names: Sequence[str] = None):
+        self.owner.set_reference(contigs, names)
+        for s in self.solvers[1:]:
+            s.contig_index, s._contigs = self.owner.contig_index, self.owner._contigs
+
+    def set_stratifications(self, strat):
+        self.owner.set_stratifications(strat)
+
+    def _grow(self):
+        while len(self.solvers) < self._n:
+            self.solvers.append(self.owner.lane())
+
+    def launch_count(self) -> int:
+        return sum(s.launch_count() for s in self.solvers)
+
+    def compare_batches(self, batches, cfg: CompareConfig = None, outs=None, **out_kwargs):
+        import threading
+        self._grow()
+        batches = list(batches)
+        outs = list(outs) if outs is not None else [None] * len(batches)
+        res, errs = [None] * len(batches), []
+        nxt, lock = [0], threading.Lock()
+
+        def work(s):
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= len(batches) or errs:
+                    return
+                try:
+                    res[i] = s.compare_batch(batches[i], cfg, out=outs[i], **out_kwargs)
+                except Exception as e:          # noqa: BLE001 - re-raised below on the caller's thread
+                    errs.append(e)
+        th = [threading.Thread(target=work, args=(s,)) for s in self.solvers[:max(1, min(self._n, len(batches)))]]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return res
+
+    def close(self):
+        for s in reversed(self.solvers):
+            s.close()
+        self.solvers = []
 
 
 class MultiSolver:

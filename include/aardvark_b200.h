@@ -254,6 +254,12 @@ typedef struct avk_ctx avk_ctx;
  * GPU (avk_compare_batch_multi); a context is used by one host thread at a time. */
 int avk_create(int device, avk_ctx **out);
 void avk_destroy(avk_ctx *ctx);
+/* A lane of `owner`: a context on the same device that reads the owner's resident reference and stratification tables
+ * (avk_set_reference / avk_set_stratifications on a lane are errors) and has its own streams and buffers.  With one host
+ * thread per context several batches -- e.g. the call sets of several samples against one truth set, the reference's
+ * one-process-per-sample use of src/main.rs -- are in flight on one GPU: copies of one overlap kernels of another and the
+ * passes fill each other's tails.  Destroy the lanes before the owner. */
+int avk_create_lane(avk_ctx *owner, avk_ctx **out);
 const char *avk_last_error(const avk_ctx *ctx);
 
 /* Replaces ReferenceGenome::from_fasta + get_full_chromosome

@@ -571,6 +571,79 @@ def test_pipelined_single_gpu_call_vs_unpipelined(solver):
         s.close()
 
 
+def test_concurrent_lanes_single_gpu_call_vs_one_piece(solver):
+    """avk_compare_batch on a large batch cuts it into contiguous bins that sibling contexts of the same GPU solve at the same
+    time (own streams, the owner's reference and stratification tables); the result must not depend on it.  The knobs lower
+    the size threshold so that a small batch takes that path, with host-side strata, device-side strata, totals only, and
+    result sequences."""
+    from aardvark_b200.batch import StratIntervals
+    ref, batch = synth.workload_chr20(scale=0.03, seed=31)
+    cfg = CompareConfig(enable_sequences=False)
+    solver.set_reference([ref])
+    strat_off = np.arange(batch.n_regions + 1, dtype=np.uint64)
+    strat_idx = (np.arange(batch.n_regions) % 2).astype(np.uint32)
+    plain = solver.compare_batch(batch, cfg, strat_off=strat_off, strat_idx=strat_idx, n_strata=2)
+    plain_tot = solver.compare_batch(batch, cfg, region_metrics=False)
+    L = len(ref)
+    strat = StratIntervals([[(0, 0, L // 3), (0, L // 2, L)], [(0, L // 4, 3 * L // 4)]], 1)
+    solver.set_stratifications(strat)
+    plain_dev = solver.compare_batch(batch, cfg, n_strata=2, device_strata=True, containment=True)
+    for lanes in (2, 5):
+        s = _solver_with_env(AVK_LANE_MIN_REGIONS=100, AVK_LANES=lanes)
+        try:
+            s.set_reference([ref])
+            assert s.compare_batch(batch, cfg, strat_off=strat_off, strat_idx=strat_idx, n_strata=2).diff(plain) == []
+            assert s.compare_batch(batch, cfg, region_metrics=False).diff(plain_tot) == []
+            s.set_stratifications(strat)
+            assert s.compare_batch(batch, cfg, n_strata=2, device_strata=True, containment=True).diff(plain_dev) == []
+            off, plen = seq_offsets(batch)
+            cs = CompareConfig(enable_sequences=True)
+            assert s.compare_batch(batch, cs, seq_off=off, seq_pool_len=plen).diff(solver.compare_batch(batch, cs, seq_off=off, seq_pool_len=plen)) == []
+            with pytest.raises(Exception):
+                s.run_resident(cfg)        # a lane call leaves nothing resident: loud, not one bin's worth of results
+        finally:
+            s.close()
+
+
+def test_solver_pool_batches_in_flight_vs_oracle():
+    """Several batches in flight on one GPU (avk_create_lane: lanes share the owner's reference and stratification tables, one
+    host thread per context): every batch's result equals the oracle's, whatever was running beside it; a lane refuses its
+    own reference; the resident entry points work on a lane."""
+    from aardvark_b200.batch import StratIntervals
+    from aardvark_b200.lib import SolverPool
+    ref, batch = synth.workload_chr20(scale=0.04, seed=37)
+    cfg = CompareConfig(enable_sequences=False)
+    n = batch.n_regions
+    cuts = [0, n // 7, n // 3, n // 2, (3 * n) // 4, n]
+    parts = [batch.slice_regions(cuts[i], cuts[i + 1]) for i in range(5)] * 3        # 15 calls over 4 contexts
+    L = len(ref)
+    strat = StratIntervals([[(0, 0, L // 3), (0, L // 2, L)], [(0, L // 4, 3 * L // 4)]], 1)
+    pool = SolverPool(0, 4)
+    try:
+        pool.set_reference([ref])
+        pool.set_stratifications(strat)
+        got = pool.compare_batches(parts, cfg, n_strata=2, device_strata=True, containment=True)
+        want = [None] * 5
+        for i, (b, g) in enumerate(zip(parts, got)):
+            if want[i % 5] is None:
+                o = orc.compare_batch(b, [ref], compare_cfg(cfg))
+                masks = orc.containments(b, strat)
+                want[i % 5] = (o, masks)
+            o, masks = want[i % 5]
+            assert g.diff(o) == [], i
+            assert np.array_equal(g.containment[:b.n_regions], masks)
+        lane = pool.solvers[1]
+        with pytest.raises(Exception):
+            lane.set_reference([ref])
+        lane.upload(parts[2])
+        lane.run_resident(cfg)
+        o = CompareOutputs(parts[2], region_metrics=False)
+        lane.download(o)
+        assert np.array_equal(o.ed1, want[2][0].ed1) and np.array_equal(o.var_class, want[2][0].var_class)
+    finally:
+        pool.close()
+
+
 def test_config0_golden_clusters_with_stratification(solver):
     """BASELINE configs[0] (the bundle does not exist: SURVEY 8d substitutes the unit-test clusters on contigs `mock` /
     `mock2` with test_data/example_stratification): the golden clusters, shifted onto both contigs, are solved with the
