@@ -1311,6 +1311,10 @@ struct avk_ctx {
     // Concurrent lanes (compare_lanes): a large batch is cut into contiguous bins that are solved AT THE SAME TIME by sibling
     // contexts of this device, each with its own streams and buffers and one host thread -- one bin's upload runs beside
     // another's kernels, and the kernels of different bins fill each other's tails (a pass ends with its slowest clusters).
+    bool many_in_flight = false;    // this context has lanes or is one (avk_create_lane): several passes share the GPU, so what counts is the work a
+                                    // pass costs, not how soon its slowest cluster ends -- the thread-per-cluster stage (the cheapest per cluster) then
+                                    // takes batches from thread_min_regions_lanes clusters up (AVK_THREAD_MIN_REGIONS overrides both thresholds)
+    u64 thread_min_regions_lanes = 100000;
     std::vector<avk_ctx *> lanes;   // lanes[0] == this context
     int n_lanes = 0;                // AVK_LANES (0 or 1 = off, the default: measured, the bins' passes keep their fixed cost -- DESIGN.md section 5)
     u64 lane_min_regions = 2000000; // AVK_LANE_MIN_REGIONS: smaller batches are solved in one piece
@@ -1422,7 +1426,7 @@ extern "C" int avk_create(int device, avk_ctx **out) {
         cudaMemcpyToSymbol(g_spec_prof, &pp, sizeof(pp));
     }
     if (const char *s = getenv("AVK_NO_SHAPE_SORT")) ctx->sort_shapes = atoi(s) == 0;
-    if (const char *s = getenv("AVK_THREAD_MIN_REGIONS")) ctx->thread_min_regions = (u64)std::max(0LL, atoll(s));
+    if (const char *s = getenv("AVK_THREAD_MIN_REGIONS")) ctx->thread_min_regions = ctx->thread_min_regions_lanes = (u64)std::max(0LL, atoll(s));
     if (const char *s = getenv("AVK_LANES")) ctx->n_lanes = std::max(0, std::min(8, atoi(s)));
     if (const char *s = getenv("AVK_LANE_MIN_REGIONS")) ctx->lane_min_regions = (u64)std::max(1LL, atoll(s));
     if (const char *s = getenv("AVK_PIPELINE_BINS")) ctx->pipe_bins = std::max(-1, atoi(s));
@@ -1456,6 +1460,7 @@ extern "C" int avk_create_lane(avk_ctx *owner, avk_ctx **out) {
     const int rc = avk_create(owner->device, out);
     if (rc != AVK_OK) { owner->err = "avk_create_lane: could not create the context"; return rc; }
     (*out)->ref_owner = owner;
+    (*out)->many_in_flight = owner->many_in_flight = true;
     return AVK_OK;
 }
 
@@ -1903,7 +1908,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
     const Stage S1 = {MODE_FUSED, true, 1, 27648, sm, 8}, G0 = {MODE_FUSED, false, 1, 2LL << 20, sm, 8};
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     u32 *LW = (u32 *)ctx->fail_h.p, *LA2 = (u32 *)ctx->fail_w.p, *LX = (u32 *)ctx->fail_x.p;
-    const bool thread_stage = ctx->use_thread_stage && n >= ctx->thread_min_regions;
+    const bool thread_stage = ctx->use_thread_stage && n >= (ctx->many_in_flight ? ctx->thread_min_regions_lanes : ctx->thread_min_regions);
     const int dense_n = ctx->dense_n ? ctx->dense_n : (thread_stage ? 10 : (n >= 250000 ? 8 : 6));
     // closed-form clusters; >= dense_n variants -> X (dense); the rest -> W
     u64 *keys = nullptr;
@@ -1957,7 +1962,7 @@ static int run_compare_pipeline(avk_ctx *ctx, const CompareRun &R) {
         u32 *LW2 = (u32 *)ctx->fail_t.p;
         TierArgs a = tier_args(ctx, keys ? (const u32 *)ctx->fail_s.p : LW, 12, 19, LW2, 13, sizeof(avk_ts::Work), nullptr);
         a.batch_min = ctx->thread_batch_min;
-        a.pop_budget = ctx->thread_pop_budget ? ctx->thread_pop_budget : (n >= 2500000 ? 64 : (n >= 1200000 ? 48 : 32));
+        a.pop_budget = ctx->thread_pop_budget ? ctx->thread_pop_budget : (n >= 2500000 ? 64 : (n >= 1200000 ? 48 : 32));   // (the same with passes in flight: measured)
         k_compare_thread<<<(unsigned)std::min<u64>((u64)sm, (n + THREAD_TPB - 1) / THREAD_TPB), THREAD_TPB, THREAD_TPB * sizeof(avk_ts::Work), ctx->side[0]>>>(R.db, R.out, R.cfg, a);
         ctx->launches += 1;
         const int rc = spec_then_team(LW2, 13, 22, 23, ctx->dense_blobs2, (u8 *)ctx->arena2.p + spill_half, ctx->side[0]);   // W2 -> B
