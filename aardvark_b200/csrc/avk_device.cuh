@@ -385,7 +385,7 @@ __device__ __noinline__ void coop_dwfa_body_staged_t() {
     const int la = A.len, lb = B.len, max_ed = J.max_ed;
     u8 *sa = avk_dyn_smem + COOP_JOB_BYTES;
     u8 *sb = sa + ((la + 8 + 3) & ~3);
-    const int cap = coop_staged_cap16(la, lb, J.cap_ints) - 4;      // (two pad entries per buffer)
+    const int cap = (coop_staged_cap16(la, lb, J.cap_ints) - 4) & ~1;      // (two pad entries per buffer; even: both buffers 4-byte aligned)
     unsigned short *cur = (unsigned short *)(sb + ((lb + 8 + 3) & ~3)) + 2, *nxt = cur + cap + 2;
     const int e_cap = (cap - 3) / 2;
     int *gw = (int *)(uintptr_t)J.wf;
@@ -418,14 +418,22 @@ __device__ __noinline__ void coop_dwfa_body_staged_t() {
         if (e > e_cap) { status = DWFA_COOP_SPILL; e -= 1; break; }      // does not fit shared memory: back to the warp path
         const int n = 2 * e + 1;
         reached = 0;
+        // two adjacent diagonals per thread: their five neighbours are two aligned 32-bit loads, increase_edit_distance() for
+        // both is one byte permute and three 16-bit-pair operations, and the two extensions are independent work for one thread
 #pragma unroll 1
-        for (int i = tid; i < n; i += T) {
-            int d = (int)max((u32)cur[i], max((u32)cur[i - 1], (u32)cur[i - 2]) + 1u) - 1;   // increase_edit_distance()
-            int boff = d + e - i;
-            if (boff < la && d < lb) { const int ext = lcp_staged_w(sa_s, boff, la, sb_s, d, lb); d += ext; boff += ext; matched += ext; }
-            nxt[i] = (unsigned short)(d + 1);
-            const u32 ra = boff >= la, rb = d >= lb;
-            reached |= TO_FULL ? (ra & rb) : (ra | rb);
+        for (int i = 2 * tid; i < n; i += 2 * T) {
+            const u32 w0 = *(const u32 *)(cur + i - 2), w1 = *(const u32 *)(cur + i);      // (cur[i-2], cur[i-1]), (cur[i], cur[i+1])
+            const u32 mid = __byte_perm(w0, w1, 0x5432);                                   // (cur[i-1], cur[i])
+            const u32 nv = __vmaxu2(w1, __vadd2(__vmaxu2(w0, mid), 0x00010001u));
+            const bool two = i + 1 < n;
+            int d0 = (int)(nv & 0xffffu) - 1, d1 = (int)(nv >> 16) - 1;
+            int b0 = d0 + e - i, b1 = d1 + e - i - 1;
+            if (b0 < la && d0 < lb) { const int ext = lcp_staged_w(sa_s, b0, la, sb_s, d0, lb); d0 += ext; b0 += ext; matched += ext; }
+            if (two && b1 < la && d1 < lb) { const int ext = lcp_staged_w(sa_s, b1, la, sb_s, d1, lb); d1 += ext; b1 += ext; matched += ext; }
+            if (two) *(u32 *)(nxt + i) = (u32)(d0 + 1) | ((u32)(d1 + 1) << 16);
+            else nxt[i] = (unsigned short)(d0 + 1);                                        // (entries behind the wavefront stay 0)
+            const u32 ra0 = b0 >= la, rb0 = d0 >= lb, ra1 = two && b1 >= la, rb1 = two && d1 >= lb;
+            reached |= TO_FULL ? ((ra0 & rb0) | (ra1 & rb1)) : (ra0 | rb0 | ra1 | rb1);
         }
         cells += n;
         stop = __syncthreads_or(reached != 0u);

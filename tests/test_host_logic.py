@@ -47,3 +47,37 @@ def test_callsets_table_round_trips_through_the_builder_oracle():
         assert pos.size > 0 and pos.min() >= b.start[k] and (pos + b.a0_len[vo[2 * k]:vo[2 * k + 2]]).max() <= b.end[k]
         if k:
             assert pos.min() >= b.end[k - 1]
+
+
+def _partition_restated(batch, n_bins):
+    """avk_partition_regions in numpy: cuts[k] = first region whose cumulative cost reaches k/n of the total."""
+    k = batch.n_inputs
+    vo = batch.var_off.astype(np.int64)
+    v0, v1 = vo[0:-1:k][:batch.n_regions], vo[k::k]
+    win = np.maximum(batch.end.astype(np.int64) - batch.start.astype(np.int64), 0)
+    m2 = np.maximum(batch.a0_len, batch.a1_len).astype(np.int64) ** 2
+    cs = np.concatenate([[0], np.cumsum(m2)])
+    cost = (v1 - v0 + 1) * win + (cs[v1] - cs[v0])
+    cum = np.cumsum(cost)
+    total = int(cum[-1]) if cum.size else 0
+    cuts = [0]
+    for j in range(1, n_bins):
+        r = int(np.searchsorted(cum * n_bins, total * j, side="left")) if cum.size else 0
+        cuts.append(max(min(r, batch.n_regions), cuts[-1]))
+    cuts.append(batch.n_regions)
+    return list(zip(cuts[:-1], cuts[1:]))
+
+
+def test_partition_matches_its_definition_small_and_threaded():
+    """The library sums the cost proxy per chunk of 16 Ki regions (several host threads from 500 k regions up) and looks a
+    cut up inside its chunk: same cuts as the one-pass definition, at sizes on both sides of the chunk and thread limits."""
+    _, small = synth.workload_chr20(scale=0.002, seed=5)
+    for n_bins in (1, 2, 3, 7, 64):
+        assert partition_regions(small, n_bins) == _partition_restated(small, n_bins)
+    _, mid = synth.workload_chr20(scale=0.3, seed=6)                 # ~35 k regions: several chunks, one thread
+    for n_bins in (2, 5, 8):
+        assert partition_regions(mid, n_bins) == _partition_restated(mid, n_bins)
+    big = RegionBatch.concat([mid] * 15)                              # > 500 k regions: the threaded path
+    assert big.n_regions >= 500000
+    for n_bins in (2, 3, 8):
+        assert partition_regions(big, n_bins) == _partition_restated(big, n_bins)
