@@ -3071,6 +3071,35 @@ extern "C" int avk_vcf_records_write(const avk_region_batch *batch, uint32_t sid
     return copy_text(avk_writers::vcf_records_text(batch, side, contig_names, var_class, var_expected, var_observed, lo, hi), buf, cap, len);
 }
 
+static int merge_view(const avk_region_batch *batch, const avk_merge_out *res, uint32_t n_contigs, bool need_contigs, avk_writers::MergeView &m) {
+    if (!batch || !res || !res->classification || !res->n_indices || !res->indices || batch->n_inputs == 0 || batch->n_inputs > 255) return AVK_ERR_INVALID;
+    m = {res->status, res->classification, res->n_indices, res->indices};
+    for (uint64_t r = 0; r < batch->n_regions; ++r) {
+        if (need_contigs && batch->contig[r] >= n_contigs) return AVK_ERR_INVALID;
+        if (res->n_indices[r] > batch->n_inputs) return AVK_ERR_INVALID;
+        for (uint8_t k = 0; k < res->n_indices[r]; ++k) if (res->indices[r * batch->n_inputs + k] >= batch->n_inputs) return AVK_ERR_INVALID;
+    }
+    return AVK_OK;
+}
+extern "C" int avk_merge_records_write(const avk_region_batch *batch, const avk_merge_out *result, const char *const *contig_names, uint32_t n_contigs,
+                                       const char *const *input_labels, uint64_t lo, uint64_t hi, char *buf, uint64_t cap, uint64_t *len) {
+    avk_writers::MergeView m;
+    if (!contig_names || !input_labels || merge_view(batch, result, n_contigs, true, m) != AVK_OK || lo > hi || hi > batch->n_regions) return AVK_ERR_INVALID;
+    return copy_text(avk_writers::merge_records_text(batch, contig_names, input_labels, m, lo, hi), buf, cap, len);
+}
+extern "C" int avk_merge_regions_write(const avk_region_batch *batch, const avk_merge_out *result, const char *const *contig_names, uint32_t n_contigs,
+                                       int passing, uint64_t lo, uint64_t hi, char *buf, uint64_t cap, uint64_t *len) {
+    avk_writers::MergeView m;
+    if (!contig_names || merge_view(batch, result, n_contigs, true, m) != AVK_OK || lo > hi || hi > batch->n_regions) return AVK_ERR_INVALID;
+    return copy_text(avk_writers::merge_regions_text(batch, contig_names, m, lo, hi, passing != 0), buf, cap, len);
+}
+extern "C" int avk_merge_summary_write(const avk_region_batch *batch, const avk_merge_out *result, const char *const *input_labels, int csv, int header,
+                                       char *buf, uint64_t cap, uint64_t *len) {
+    avk_writers::MergeView m;
+    if (!input_labels || merge_view(batch, result, 0, false, m) != AVK_OK) return AVK_ERR_INVALID;
+    return copy_text(avk_writers::merge_summary_text(batch, input_labels, m, csv ? ',' : '\t', header != 0), buf, cap, len);
+}
+
 // ---- VCF body text -> call-set table (avk_vcf.cuh) -----------------------------------------------------------
 struct LineStart {
     const u8 *t;

@@ -21,6 +21,11 @@ def _bind():
     lib.avk_vcf_records_write.argtypes = [C.POINTER(abi.RegionBatch), C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_uint8),
                                           C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, C.c_char_p, C.c_uint64,
                                           C.POINTER(C.c_uint64)]
+    t = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    names = C.POINTER(C.c_char_p)
+    lib.avk_merge_records_write.argtypes = [C.POINTER(abi.RegionBatch), C.POINTER(abi.MergeOut), names, C.c_uint32, names, C.c_uint64, C.c_uint64] + t
+    lib.avk_merge_regions_write.argtypes = [C.POINTER(abi.RegionBatch), C.POINTER(abi.MergeOut), names, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64] + t
+    lib.avk_merge_summary_write.argtypes = [C.POINTER(abi.RegionBatch), C.POINTER(abi.MergeOut), names, C.c_int, C.c_int] + t
     return lib
 
 
@@ -73,3 +78,34 @@ def vcf_record_lines(batch, side, contig_names, outputs, lo=0, hi=None):
     names = (C.c_char_p * len(contig_names))(*[n.encode() for n in contig_names])
     return _text(lambda buf, cap, n: lib.avk_vcf_records_write(C.byref(cb), side, names, len(contig_names), abi.ptr(outputs.var_class),
                                                                abi.ptr(outputs.var_expected), abi.ptr(outputs.var_observed), lo, hi, buf, cap, n))
+
+
+class VariantMerger:
+    """src/writers/variant_merger.rs + merge_summary.rs over a solved merge batch (MergeOutputs): the body of passing.vcf.gz,
+    regions.bed / failed_regions.bed and the merge summary table.  Formatting happens in the product library
+    (avk_merge_records_write / avk_merge_regions_write / avk_merge_summary_write, host C++)."""
+
+    def __init__(self, batch, outputs, contig_names, input_labels):
+        assert len(input_labels) == batch.n_inputs
+        self.batch, self.out = batch, outputs
+        self._cb, self._co = batch.to_c(), outputs.to_c()
+        self._names = (C.c_char_p * len(contig_names))(*[n.encode() for n in contig_names])
+        self._labels = (C.c_char_p * len(input_labels))(*[n.encode() for n in input_labels])
+        self._n_contigs = len(contig_names)
+
+    def passing_records(self, lo=0, hi=None):
+        lib = _bind()
+        hi = self.batch.n_regions if hi is None else hi
+        return _text(lambda buf, cap, n: lib.avk_merge_records_write(C.byref(self._cb), C.byref(self._co), self._names, self._n_contigs, self._labels,
+                                                                     lo, hi, buf, cap, n))
+
+    def regions_bed(self, passing=True, lo=0, hi=None):
+        lib = _bind()
+        hi = self.batch.n_regions if hi is None else hi
+        return _text(lambda buf, cap, n: lib.avk_merge_regions_write(C.byref(self._cb), C.byref(self._co), self._names, self._n_contigs,
+                                                                     1 if passing else 0, lo, hi, buf, cap, n))
+
+    def summary_text(self, csv=False, header=True):
+        lib = _bind()
+        return _text(lambda buf, cap, n: lib.avk_merge_summary_write(C.byref(self._cb), C.byref(self._co), self._labels, 1 if csv else 0,
+                                                                     1 if header else 0, buf, cap, n))

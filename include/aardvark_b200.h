@@ -394,6 +394,22 @@ int avk_vcf_records_write(const avk_region_batch *batch, uint32_t side, const ch
                           const uint8_t *var_class, const uint8_t *var_expected, const uint8_t *var_observed, uint64_t lo, uint64_t hi,
                           char *buf, uint64_t cap, uint64_t *len);
 
+/* The outputs of `aardvark merge` that are functions of avk_merge_out (host only; regions with status != 0 are skipped as
+ * src/main.rs:507-524 skips failed regions; `result->status` may be NULL = all solved):
+ * avk_merge_records_write: body lines of passing.vcf.gz (VariantMerger::write_variants, src/writers/variant_merger.rs:198-287)
+ *   for regions [lo, hi): the variants of the lowest passing input (input 0 for `identical`), INFO
+ *   SOURCES=<labels of the passing inputs>;MR=<identical|no_conflict|majority|conflict_select>, FORMAT GT:RI;
+ * avk_merge_regions_write: BED lines chrom, start, end, {reason}_{region_id} (write_region :294-309) of the passing
+ *   (passing != 0: regions.bed) or failed (failed_regions.bed) regions of [lo, hi);
+ * avk_merge_summary_write: MergeSummaryWriter (src/writers/merge_summary.rs:56-112): pass / fail variant counts per
+ *   (merge reason with its indices, variant type, input) in the reference's key order, e.g. `majority_0_2 Snv 1 ilmn 0 37810`. */
+int avk_merge_records_write(const avk_region_batch *batch, const avk_merge_out *result, const char *const *contig_names, uint32_t n_contigs,
+                            const char *const *input_labels, uint64_t lo, uint64_t hi, char *buf, uint64_t cap, uint64_t *len);
+int avk_merge_regions_write(const avk_region_batch *batch, const avk_merge_out *result, const char *const *contig_names, uint32_t n_contigs,
+                            int passing, uint64_t lo, uint64_t hi, char *buf, uint64_t cap, uint64_t *len);
+int avk_merge_summary_write(const avk_region_batch *batch, const avk_merge_out *result, const char *const *input_labels, int csv, int header,
+                            char *buf, uint64_t cap, uint64_t *len);
+
 int avk_compare_upload(avk_ctx *ctx, const avk_region_batch *batch);
 int avk_compare_upload_range(avk_ctx *ctx, const avk_region_batch *batch, uint64_t lo, uint64_t hi);
 int avk_compare_run_resident(avk_ctx *ctx, const avk_compare_cfg *cfg);
