@@ -1,0 +1,280 @@
+// avk_inflate.cuh -- BGZF block inflate for the VCF ingest ("parallel block inflate").
+//
+// The reference reads its inputs through noodles' bgzf reader (src/parsing/noodles_helper.rs:14-97, region_generation.rs:489-541),
+// i.e. through a DEFLATE library that is not part of the repository (noodles-bgzf -> flate2 / libdeflate, Cargo.lock).  What is
+// restated here is therefore the published format: RFC 1951 (DEFLATE), RFC 1952 (gzip member, CRC-32) and the BGZF section of the
+// SAM specification (gzip members of at most 64 KiB with a "BC" extra subfield holding the member size).  Parity is anchored on
+// zlib: tests/test_bgzf.py compares this decoder, built for the host, with Python's zlib on every block type.
+//
+// BGZF members are independent, so one thread inflates one member (at most 64 KiB of output); the host only walks the member
+// headers (12 + XLEN bytes each) to find the payloads and the output offsets.  Huffman codes are decoded canonically, bit by
+// bit, from per-thread count / symbol tables (~700 bytes of local memory): every lane of a warp runs the same short loop.
+// Host and device share the code (tests/inflate_host.cpp builds it with g++).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef AVK_HD
+#ifdef __CUDACC__
+#define AVK_HD __host__ __device__
+#else
+#define AVK_HD
+#endif
+#endif
+
+namespace avk_inflate {
+
+enum {
+    INF_OK = 0,
+    INF_E_INPUT = 1,        // ran out of input
+    INF_E_BTYPE = 2,        // block type 3
+    INF_E_STORED = 3,       // LEN != ~NLEN
+    INF_E_LENGTHS = 4,      // bad code-length data (repeat without a previous length, too many lengths, no end-of-block code)
+    INF_E_CODE = 5,         // over-subscribed code, or an incomplete one that is not the single-code case
+    INF_E_SYMBOL = 6,       // invalid literal/length or distance symbol
+    INF_E_DISTANCE = 7,     // distance reaches before the start of the output
+    INF_E_OUTPUT = 8,       // more output than the member's ISIZE
+    INF_E_SIZE = 9,         // less output than ISIZE
+    INF_E_CRC = 10          // CRC-32 of the output differs from the trailer's
+};
+
+struct Bits {
+    const uint8_t *p;
+    uint64_t n, pos;
+    uint64_t buf;
+    int cnt;
+    AVK_HD void init(const uint8_t *src, uint64_t len) { p = src; n = len; pos = 0; buf = 0; cnt = 0; }
+    // k <= 32.  A refill takes every byte that fits (the loads are independent of each other: one memory latency per ~7 bytes
+    // instead of one per byte); past the end of the input it shifts in zero bits -- a peek may look past it, over() tells
+    // whether bits that do not exist were CONSUMED.
+    AVK_HD void need(int k) {
+        if (cnt >= k) return;
+        while (cnt <= 56) {
+            const uint64_t b = pos < n ? p[pos] : 0;
+            pos += 1;
+            buf |= b << cnt;
+            cnt += 8;
+        }
+    }
+    AVK_HD uint32_t peek(int k) { need(k); return (uint32_t)(buf & ((1ull << k) - 1)); }
+    AVK_HD void drop(int k) { buf >>= k; cnt -= k; }
+    AVK_HD uint32_t get(int k) {
+        if (k == 0) return 0;
+        const uint32_t v = peek(k);
+        drop(k);
+        return v;
+    }
+    AVK_HD bool over() const { return pos * 8 - (uint64_t)cnt > n * 8; }      // more bits CONSUMED than the input holds
+    AVK_HD void align() { const int r = cnt & 7; buf >>= r; cnt -= r; }      // stored block: skip to the byte boundary
+};
+
+// canonical Huffman code: count[l] codes of length l, symbols in code order
+template <int NSYM>
+struct Huff {
+    uint16_t count[16];
+    uint16_t symbol[NSYM];
+    // > 0: incomplete, 0: complete, < 0: over-subscribed (RFC 1951 3.2.2)
+    AVK_HD int build(const uint8_t *len, int n) {
+        for (int l = 0; l < 16; ++l) count[l] = 0;
+        for (int s = 0; s < n; ++s) count[len[s]] += 1;
+        if (count[0] == n) return 0;                          // no codes at all: complete, but decoding anything fails
+        int left = 1;
+        for (int l = 1; l < 16; ++l) { left <<= 1; left -= count[l]; if (left < 0) return left; }
+        uint16_t offs[16];
+        offs[1] = 0;
+        for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
+        for (int s = 0; s < n; ++s) if (len[s]) symbol[offs[len[s]]++] = (uint16_t)s;
+        return left;
+    }
+    AVK_HD int decode(Bits &b) const {
+        int code = 0, first = 0, index = 0;
+        for (int l = 1; l < 16; ++l) {
+            code |= (int)b.get(1);
+            const int c = count[l];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c; first += c;
+            first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+};
+
+// First-level lookup: the next FAST bits of the stream (LSB first = the code's first bit in bit 0) -> (symbol << 4) | code length
+// for every code of at most FAST bits; 0 = a longer code, decoded bit by bit.
+template <int FAST>
+struct FastTab {
+    uint16_t e[1 << FAST];
+    template <int NSYM>
+    AVK_HD void build(const Huff<NSYM> &h) {
+        for (int i = 0; i < (1 << FAST); ++i) e[i] = 0;
+        int code = 0, index = 0;
+        for (int l = 1; l <= FAST; ++l) {
+            for (int k = 0; k < h.count[l]; ++k, ++code, ++index) {
+                int rev = 0;
+                for (int i = 0; i < l; ++i) rev |= ((code >> i) & 1) << (l - 1 - i);
+                const uint16_t v = (uint16_t)((h.symbol[index] << 4) | l);
+                for (int r = rev; r < (1 << FAST); r += 1 << l) e[r] = v;
+            }
+            code <<= 1;
+        }
+    }
+    template <int NSYM>
+    AVK_HD int decode(Bits &b, const Huff<NSYM> &h) const {
+        const uint16_t v = e[b.peek(FAST)];
+        if (v) { b.drop(v & 15); return v >> 4; }
+        return h.decode(b);
+    }
+};
+
+struct Tables {
+    Huff<288> lit;
+    Huff<30> dist;
+    FastTab<9> flit;
+    FastTab<7> fdist;
+    uint8_t len[320];
+};
+
+// length of literal/length symbol 257..285 and its extra bits; distance of symbol 0..29 and its extra bits (RFC 1951 3.2.5)
+AVK_HD inline int len_extra(int s) { return s < 265 || s == 285 ? 0 : (s - 261) >> 2; }
+AVK_HD inline int len_base(int s) { return s < 265 ? s - 254 : s == 285 ? 258 : ((4 + ((s - 265) & 3)) << len_extra(s)) + 3; }
+AVK_HD inline int dist_extra(int s) { return s < 4 ? 0 : (s >> 1) - 1; }
+AVK_HD inline int dist_base(int s) { return s < 4 ? s + 1 : ((2 + (s & 1)) << dist_extra(s)) + 1; }
+
+AVK_HD inline int fixed_tables(Tables &t) {
+    for (int s = 0; s < 144; ++s) t.len[s] = 8;
+    for (int s = 144; s < 256; ++s) t.len[s] = 9;
+    for (int s = 256; s < 280; ++s) t.len[s] = 7;
+    for (int s = 280; s < 288; ++s) t.len[s] = 8;
+    t.lit.build(t.len, 288);
+    for (int s = 0; s < 30; ++s) t.len[s] = 5;
+    t.dist.build(t.len, 30);
+    t.flit.build(t.lit); t.fdist.build(t.dist);
+    return INF_OK;
+}
+
+AVK_HD inline int dynamic_tables(Bits &b, Tables &t) {
+    const int nlen = (int)b.get(5) + 257, ndist = (int)b.get(5) + 1, ncode = (int)b.get(4) + 4;
+    if (nlen > 286 || ndist > 30) return INF_E_LENGTHS;
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint8_t cl[19];
+    for (int i = 0; i < 19; ++i) cl[i] = 0;
+    for (int i = 0; i < ncode; ++i) cl[order[i]] = (uint8_t)b.get(3);
+    Huff<19> clh;
+    if (clh.build(cl, 19) != 0) return INF_E_CODE;           // the code-length code must be complete
+    int i = 0;
+    while (i < nlen + ndist) {
+        const int s = clh.decode(b);
+        if (s < 0) return INF_E_SYMBOL;
+        if (s < 16) { t.len[i++] = (uint8_t)s; continue; }
+        int prev = 0, rep;
+        if (s == 16) { if (i == 0) return INF_E_LENGTHS; prev = t.len[i - 1]; rep = 3 + (int)b.get(2); }
+        else if (s == 17) rep = 3 + (int)b.get(3);
+        else rep = 11 + (int)b.get(7);
+        if (i + rep > nlen + ndist) return INF_E_LENGTHS;
+        while (rep--) t.len[i++] = (uint8_t)prev;
+    }
+    if (b.over()) return INF_E_INPUT;
+    if (t.len[256] == 0) return INF_E_LENGTHS;               // no end-of-block code
+    int left = t.lit.build(t.len, nlen);
+    if (left < 0 || (left > 0 && nlen - t.lit.count[0] != 1)) return INF_E_CODE;
+    left = t.dist.build(t.len + nlen, ndist);
+    if (left < 0 || (left > 0 && ndist - t.dist.count[0] != 1)) return INF_E_CODE;
+    t.flit.build(t.lit); t.fdist.build(t.dist);
+    return INF_OK;
+}
+
+// one raw DEFLATE stream -> out[0 .. *out_len); out_cap is the most it may produce
+AVK_HD inline int inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, uint64_t *out_len, Tables &t) {
+    Bits b;
+    b.init(in, in_len);
+    uint64_t o = 0;
+    int last;
+    do {
+        last = (int)b.get(1);
+        const int type = (int)b.get(2);
+        if (b.over()) return INF_E_INPUT;
+        if (type == 0) {
+            b.align();
+            const uint32_t len = b.get(16), nlen = b.get(16);
+            if (b.over()) return INF_E_INPUT;
+            if ((len ^ 0xffffu) != nlen) return INF_E_STORED;
+            if (o + len > out_cap) return INF_E_OUTPUT;
+            // the bit buffer holds whole bytes now: drain it, then copy straight from the input
+            uint32_t k = 0;
+            while (k < len && b.cnt >= 8) { out[o++] = (uint8_t)b.get(8); ++k; }
+            if (b.over()) return INF_E_INPUT;                  // (bytes past the end were drained)
+            if (k < len) {                                     // the buffer is empty now: pos is the stream position
+                if (b.pos + (len - k) > b.n) return INF_E_INPUT;
+                for (; k < len; ++k) out[o++] = b.p[b.pos++];
+            }
+            continue;
+        }
+        if (type == 3) return INF_E_BTYPE;
+        const int rc = type == 1 ? fixed_tables(t) : dynamic_tables(b, t);
+        if (rc != INF_OK) return rc;
+        for (;;) {
+            int s = t.flit.decode(b, t.lit);
+            if (s < 0) return b.over() ? INF_E_INPUT : INF_E_SYMBOL;
+            if (b.over()) return INF_E_INPUT;
+            if (s < 256) {
+                if (o >= out_cap) return INF_E_OUTPUT;
+                out[o++] = (uint8_t)s;
+                continue;
+            }
+            if (s == 256) break;
+            if (s > 285) return INF_E_SYMBOL;
+            const int len = len_base(s) + (int)b.get(len_extra(s));
+            const int ds = t.fdist.decode(b, t.dist);
+            if (ds < 0 || ds > 29) return b.over() ? INF_E_INPUT : INF_E_SYMBOL;
+            const uint64_t dist = (uint64_t)dist_base(ds) + b.get(dist_extra(ds));
+            if (b.over()) return INF_E_INPUT;
+            if (dist > o) return INF_E_DISTANCE;
+            if (o + (uint64_t)len > out_cap) return INF_E_OUTPUT;
+            for (int k = 0; k < len; ++k, ++o) out[o] = out[o - dist];      // byte by byte: the ranges may overlap (run-length case)
+        }
+    } while (!last);
+    *out_len = o;
+    return INF_OK;
+}
+
+// CRC-32 of RFC 1952 (reflected 0xEDB88320), table of 256 entries made by crc_table()
+AVK_HD inline uint32_t crc_entry(uint32_t i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+    return c;
+}
+AVK_HD inline uint32_t crc32(const uint32_t *tab, const uint8_t *p, uint64_t n) {
+    uint32_t c = 0xffffffffu;
+    for (uint64_t i = 0; i < n; ++i) c = tab[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+}
+
+// ---- BGZF member walk (host): SAM specification 4.1 ---------------------------------------------------------------------
+struct Member { uint64_t c_off; uint32_t c_len, isize, crc; uint64_t o_off; };
+// returns 0 and the member at byte `at` (next = offset of the following member), or a negative code: -1 truncated, -2 not a
+// gzip member with deflate + FEXTRA, -3 no BC subfield / inconsistent sizes
+inline int member_at(const uint8_t *gz, uint64_t n, uint64_t at, Member &m, uint64_t &next) {
+    if (at + 18 > n) return -1;
+    const uint8_t *h = gz + at;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return -2;
+    const uint32_t xlen = h[10] | ((uint32_t)h[11] << 8);
+    if (at + 12 + xlen > n) return -1;
+    int64_t bsize = -1;
+    for (uint32_t x = 0; x + 4 <= xlen;) {
+        const uint8_t *f = h + 12 + x;
+        const uint32_t slen = f[2] | ((uint32_t)f[3] << 8);
+        if (f[0] == 'B' && f[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (int64_t)(f[4] | ((uint32_t)f[5] << 8)) + 1;
+        x += 4 + slen;
+    }
+    if (bsize < 0 || (uint64_t)bsize < 12ull + xlen + 8 || (h[3] & ~4)) return -3;     // (no name / comment / header CRC in BGZF members)
+    if (at + (uint64_t)bsize > n) return -1;
+    const uint8_t *tr = h + bsize - 8;
+    m.c_off = at + 12 + xlen;
+    m.c_len = (uint32_t)(bsize - 12 - xlen - 8);
+    m.crc = tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+    m.isize = tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+    next = at + (uint64_t)bsize;
+    return 0;
+}
+
+}  // namespace avk_inflate

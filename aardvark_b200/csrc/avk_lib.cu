@@ -29,6 +29,7 @@
 #include "avk_thread_solver.cuh"
 #include "avk_writers.h"
 #include "avk_vcf.cuh"
+#include "avk_inflate.cuh"
 
 using namespace avk;
 
@@ -3139,22 +3140,22 @@ __global__ void __launch_bounds__(256) k_vcf_emit(const u8 *t, u64 len, const u6
         o += V.l0 + V.l1;
     }
 }
-extern "C" int avk_vcf_parse(avk_ctx *ctx, const uint8_t *text, uint64_t len, const char *const *contig_names, uint32_t n_contigs, uint32_t sample_index,
-                             int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code) {
-    if (!ctx) return AVK_ERR_INVALID;
-    if ((!text && len) || !out || !contig_names || n_contigs == 0 || len >= 0xfffffff0ull) { ctx->err = "avk_vcf_parse: bad arguments (text up to 4 GiB per call)"; return AVK_ERR_INVALID; }
+enum { V_TEXT, V_STARTS, V_NOUT, V_NBYTES, V_VOFF, V_BOFF, V_NAMES, V_MISC, V_C, V_POS, V_VT, V_ZY, V_RAW, V_AOFF, V_L0, V_L1, V_POOL, V_GZ, V_MEMBERS, V_MSTATUS };
+// `text` on the host (uploaded into rb[V_TEXT]) or, with text == NULL and len > 0, already in rb[V_TEXT] on the device
+static int vcf_parse_impl(avk_ctx *ctx, const uint8_t *text, uint64_t len, const char *const *contig_names, uint32_t n_contigs, uint32_t sample_index,
+                          int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code) {
+    if (!out || !contig_names || n_contigs == 0 || len >= 0xfffffff0ull) { ctx->err = "avk_vcf_parse: bad arguments (text up to 4 GiB per call)"; return AVK_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     if (error_line) *error_line = 0;
     if (error_code) *error_code = 0;
     out->n_variants = 0; out->allele_pool_len = 0;
     if (len == 0) return AVK_OK;
     DevBuf *rb = ctx->rb;   // the region builder's temporaries are free between its calls
-    enum { V_TEXT, V_STARTS, V_NOUT, V_NBYTES, V_VOFF, V_BOFF, V_NAMES, V_MISC, V_C, V_POS, V_VT, V_ZY, V_RAW, V_AOFF, V_L0, V_L1, V_POOL };
     u32 stride = 1;
     for (u32 c = 0; c < n_contigs; ++c) { if (!contig_names[c]) { ctx->err = "avk_vcf_parse: null contig name"; return AVK_ERR_INVALID; } stride = std::max<u32>(stride, (u32)strlen(contig_names[c]) + 1); }
     std::vector<char> names((size_t)stride * n_contigs, 0);
     for (u32 c = 0; c < n_contigs; ++c) strcpy(names.data() + (size_t)c * stride, contig_names[c]);
-    UPLOAD(rb[V_TEXT], text, len);
+    if (text) UPLOAD(rb[V_TEXT], text, len);
     UPLOAD(rb[V_NAMES], names.data(), names.size());
     ENSURE(rb[V_STARTS], 8 * (len / 2 + 2));                      // a line is at least one byte and its newline
     ENSURE(rb[V_MISC], 64);
@@ -3217,6 +3218,137 @@ extern "C" int avk_vcf_parse(avk_ctx *ctx, const uint8_t *text, uint64_t len, co
     CK(cudaStreamSynchronize(ctx->stream));
     out->n_variants = nv; out->allele_pool_len = nb;
     return AVK_OK;
+}
+extern "C" int avk_vcf_parse(avk_ctx *ctx, const uint8_t *text, uint64_t len, const char *const *contig_names, uint32_t n_contigs, uint32_t sample_index,
+                             int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!text && len) { ctx->err = "avk_vcf_parse: null text"; return AVK_ERR_INVALID; }
+    return vcf_parse_impl(ctx, text, len, contig_names, n_contigs, sample_index, enable_trimming, out, error_line, error_code);
+}
+
+// ---- BGZF inflate (avk_inflate.cuh): one thread per member ------------------------------------------------------
+// One warp per member: lane 0 decodes into a 64 KiB window in shared memory (Huffman tables and the CRC tables beside it: a
+// decoder is a chain of dependent loads, ~30 cycles each there against ~600 in global memory, where a match would read bytes the
+// same thread has just written), then the warp copies the window out with 16-byte stores.  The window starts at the output's
+// offset modulo 16 so that both sides of that copy are aligned.  Members that declare more than 64 KiB (legal gzip, not BGZF)
+// are decoded straight into global memory.
+enum { BGZF_WIN = 65536, BGZF_SMEM = BGZF_WIN + 16 + ((sizeof(avk_inflate::Tables) + 15) & ~15) + 4 * 256 * 4 };
+__global__ void __launch_bounds__(32) k_bgzf_inflate(const u8 *gz, const avk_inflate::Member *mem, u32 n_members, u8 *out, int verify_crc, u32 *status) {
+    u8 *win = avk_dyn_smem;
+    avk_inflate::Tables &tab = *(avk_inflate::Tables *)(avk_dyn_smem + BGZF_WIN + 16);
+    u32 *crc_t = (u32 *)(avk_dyn_smem + BGZF_WIN + 16 + ((sizeof(avk_inflate::Tables) + 15) & ~15));      // slicing by 4: T0..T3
+    const int lane = threadIdx.x;
+    for (u32 i = lane; i < 256; i += 32) crc_t[i] = avk_inflate::crc_entry(i);
+    __syncwarp();
+    for (int t = 1; t < 4; ++t) {
+        for (u32 i = lane; i < 256; i += 32) { const u32 p = crc_t[(t - 1) * 256 + i]; crc_t[t * 256 + i] = (p >> 8) ^ crc_t[p & 0xffu]; }
+        __syncwarp();
+    }
+    for (u32 k = blockIdx.x; k < n_members; k += gridDim.x) {
+        const avk_inflate::Member m = mem[k];
+        u8 *dst = out + m.o_off;
+        const bool windowed = m.isize <= BGZF_WIN;
+        const u32 pad = (u32)((uintptr_t)dst & 15u);
+        u8 *buf = windowed ? win + pad : dst;
+        int rc = 0;
+        uint64_t got = 0;
+        if (lane == 0) {
+            rc = avk_inflate::inflate(gz + m.c_off, m.c_len, buf, m.isize, &got, tab);
+            if (rc == avk_inflate::INF_OK && got != m.isize) rc = avk_inflate::INF_E_SIZE;
+            if (rc == avk_inflate::INF_OK && verify_crc) {
+                u32 c = 0xffffffffu;
+                u32 i = 0;
+                const u32 n = (u32)got;
+                while (i < n && ((uintptr_t)(buf + i) & 3u)) { c = crc_t[(c ^ buf[i]) & 0xffu] ^ (c >> 8); ++i; }
+                for (; i + 4 <= n; i += 4) {
+                    c ^= *(const u32 *)(buf + i);
+                    c = crc_t[768 + (c & 0xffu)] ^ crc_t[512 + ((c >> 8) & 0xffu)] ^ crc_t[256 + ((c >> 16) & 0xffu)] ^ crc_t[c >> 24];
+                }
+                for (; i < n; ++i) c = crc_t[(c ^ buf[i]) & 0xffu] ^ (c >> 8);
+                if ((c ^ 0xffffffffu) != m.crc) rc = avk_inflate::INF_E_CRC;
+            }
+            status[k] = (u32)rc;
+        }
+        rc = __shfl_sync(AVK_FULL, rc, 0);
+        __syncwarp();
+        if (rc == avk_inflate::INF_OK && windowed) {
+            const u32 n = m.isize;
+            const u32 head = min(n, (16u - pad) & 15u);
+            for (u32 i = lane; i < head; i += 32) dst[i] = buf[i];
+            const u32 body = (n - head) >> 4;
+            const uint4 *s4 = (const uint4 *)(buf + head);
+            uint4 *d4 = (uint4 *)(dst + head);
+            for (u32 i = lane; i < body; i += 32) d4[i] = s4[i];
+            for (u32 i = head + (body << 4) + lane; i < n; i += 32) dst[i] = buf[i];
+        }
+        __syncwarp();
+    }
+}
+// Walks the members on the host, uploads the file and inflates every member on the device into rb[V_TEXT]; *total = bytes.
+static int bgzf_inflate_device(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int verify_crc, uint64_t *total, std::vector<avk_inflate::Member> *members_out) {
+    std::vector<avk_inflate::Member> mem;
+    uint64_t at = 0, o = 0;
+    while (at < gz_len) {
+        avk_inflate::Member m;
+        uint64_t next = 0;
+        const int rc = avk_inflate::member_at(gz, gz_len, at, m, next);
+        if (rc != 0) {
+            ctx->err = "BGZF member " + std::to_string(mem.size()) + " at byte " + std::to_string(at) +
+                       (rc == -1 ? ": truncated" : rc == -2 ? ": not a gzip member with an extra field (plain gzip is not BGZF)" : ": no BC subfield / inconsistent sizes");
+            return AVK_ERR_INVALID;
+        }
+        m.o_off = o; o += m.isize;
+        if (m.isize) mem.push_back(m);                       // (empty members -- the EOF marker -- produce nothing)
+        at = next;
+    }
+    *total = o;
+    if (members_out) { *members_out = mem; return AVK_OK; }
+    if (o == 0) return AVK_OK;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf *rb = ctx->rb;
+    UPLOAD(rb[V_GZ], gz, gz_len);
+    UPLOAD(rb[V_MEMBERS], mem.data(), mem.size() * sizeof(avk_inflate::Member));
+    ENSURE(rb[V_MSTATUS], 4 * mem.size());
+    ENSURE(rb[V_TEXT], o);
+    const u32 n = (u32)mem.size();
+    CK(cudaFuncSetAttribute(k_bgzf_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BGZF_SMEM));      // (per device; cheap)
+    k_bgzf_inflate<<<std::min<u32>(n, 3u * (u32)ctx->sm_count), 32, BGZF_SMEM, ctx->stream>>>((const u8 *)rb[V_GZ].p, (const avk_inflate::Member *)rb[V_MEMBERS].p, n, (u8 *)rb[V_TEXT].p, verify_crc,
+                                                          (u32 *)rb[V_MSTATUS].p);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    std::vector<u32> st(n);
+    CK(cudaMemcpyAsync(st.data(), rb[V_MSTATUS].p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (u32 k = 0; k < n; ++k)
+        if (st[k] != 0) { ctx->err = "BGZF member with payload at byte " + std::to_string(mem[k].c_off) + " does not inflate (code " + std::to_string(st[k]) + ")"; return AVK_ERR_INVALID; }
+    return AVK_OK;
+}
+extern "C" int avk_bgzf_inflate(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int verify_crc, uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if ((!gz && gz_len) || !out_len) { ctx->err = "avk_bgzf_inflate: bad arguments"; return AVK_ERR_INVALID; }
+    uint64_t total = 0;
+    if (!out) {                                              // size query: the host walk only
+        std::vector<avk_inflate::Member> mem;
+        const int rc = bgzf_inflate_device(ctx, gz, gz_len, verify_crc, &total, &mem);
+        *out_len = total;
+        return rc;
+    }
+    int rc = bgzf_inflate_device(ctx, gz, gz_len, verify_crc, &total, nullptr);
+    *out_len = total;
+    if (rc != AVK_OK) return rc;
+    if (total > out_cap) { ctx->err = "avk_bgzf_inflate: output capacity too small"; return AVK_ERR_OOM; }
+    if (total) CK(cudaMemcpyAsync(out, ctx->rb[V_TEXT].p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AVK_OK;
+}
+extern "C" int avk_vcf_parse_bgzf(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int verify_crc, const char *const *contig_names, uint32_t n_contigs,
+                                  uint32_t sample_index, int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if (!gz && gz_len) { ctx->err = "avk_vcf_parse_bgzf: null input"; return AVK_ERR_INVALID; }
+    uint64_t total = 0;
+    const int rc = bgzf_inflate_device(ctx, gz, gz_len, verify_crc, &total, nullptr);
+    if (rc != AVK_OK) return rc;
+    return vcf_parse_impl(ctx, nullptr, total, contig_names, n_contigs, sample_index, enable_trimming, out, error_line, error_code);   // the text never leaves the device
 }
 
 // diagnostics: per-cluster phase cycles of the LAST k_search_spec launches (AVK_SPEC_PROFILE=1); out = [n][8] u64

@@ -378,6 +378,17 @@ typedef struct {
 int avk_vcf_parse(avk_ctx *ctx, const uint8_t *text, uint64_t len, const char *const *contig_names, uint32_t n_contigs, uint32_t sample_index,
                   int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code);
 
+/* ---- BGZF inflate (SURVEY 8f N2 "parallel block inflate"; replaces the bgzf reader behind noodles_helper.rs:14-97 for a
+ * whole file).  BGZF members (SAM specification 4.1: gzip members of at most 64 KiB with a BC extra subfield) are independent:
+ * the host walks the member headers, one device thread inflates one member (RFC 1951 restated in csrc/avk_inflate.cuh) and,
+ * with verify_crc != 0, checks its CRC-32 against the trailer.  A plain gzip file, a truncated file or a member that does not
+ * inflate fails the call (avk_last_error names the member).
+ * avk_bgzf_inflate: out == NULL -> *out_len = inflated size (host walk only); else the text is copied to `out`.
+ * avk_vcf_parse_bgzf = avk_bgzf_inflate + avk_vcf_parse without the text leaving the device ('#' lines are skipped). */
+int avk_bgzf_inflate(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int verify_crc, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+int avk_vcf_parse_bgzf(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int verify_crc, const char *const *contig_names, uint32_t n_contigs,
+                       uint32_t sample_index, int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code);
+
 /* ---- writers: host-side text of what the kernels counted.  buf == NULL: *len receives the size needed.
  * avk_summary_write: the rows SummaryWriter::write_summary (src/writers/summary.rs:166-221, :243-420) emits for ONE
  * GroupTypeMetrics table -- `totals` = avk_compare_out::totals for region_label "ALL", or row s of strat_totals for the

@@ -1,0 +1,37 @@
+// Host build of the BGZF inflate the device runs (aardvark_b200/csrc/avk_inflate.cuh): tests/test_bgzf.py compares it with zlib.
+#include <cstring>
+#include <vector>
+
+#include "../aardvark_b200/csrc/avk_inflate.cuh"
+
+using namespace avk_inflate;
+
+extern "C" int inf_raw(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_len) {
+    static thread_local Tables t;
+    *out_len = 0;
+    return inflate(in, n, out, cap, out_len, t);
+}
+
+// whole BGZF file -> out; returns 0, or 1000 * (member index + 1) + code (member walk errors: code 100 - rc)
+extern "C" int inf_bgzf(const uint8_t *gz, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_len, int verify) {
+    static thread_local Tables t;
+    uint32_t tab[256];
+    for (uint32_t i = 0; i < 256; ++i) tab[i] = crc_entry(i);
+    uint64_t at = 0, o = 0;
+    int k = 0;
+    while (at < n) {
+        Member m;
+        uint64_t next = 0;
+        const int rc = member_at(gz, n, at, m, next);
+        if (rc != 0) return 1000 * (k + 1) + 100 - rc;
+        if (o + m.isize > cap) return 1000 * (k + 1) + INF_E_OUTPUT;
+        uint64_t got = 0;
+        const int e = inflate(gz + m.c_off, m.c_len, out + o, m.isize, &got, t);
+        if (e != INF_OK) return 1000 * (k + 1) + e;
+        if (got != m.isize) return 1000 * (k + 1) + INF_E_SIZE;
+        if (verify && crc32(tab, out + o, got) != m.crc) return 1000 * (k + 1) + INF_E_CRC;
+        o += got; at = next; ++k;
+    }
+    *out_len = o;
+    return 0;
+}

@@ -1,0 +1,191 @@
+"""BGZF inflate.  The reference inflates through noodles-bgzf (flate2 / libdeflate; not in the repository), so
+parity is anchored on zlib: the decoder the device runs (aardvark_b200/csrc/avk_inflate.cuh), built here for the host by
+tests/inflate_host.cpp, must reproduce what Python's zlib produces -- stored, fixed-Huffman and dynamic-Huffman blocks, streams
+of several blocks, the degenerate codes (one distance code, no distance codes), empty members -- and must reject damaged input."""
+import ctypes as C
+import os
+import random
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libinflate_host.so")
+SRCS = [os.path.join(HERE, "inflate_host.cpp"), os.path.join(HERE, "..", "aardvark_b200", "csrc", "avk_inflate.cuh")]
+
+
+def inf_lib():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(s) for s in SRCS):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", SO, SRCS[0]])
+    lib = C.CDLL(SO)
+    lib.inf_raw.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.inf_bgzf.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+    return lib
+
+
+def raw_inflate(data: bytes, cap: int):
+    out = C.create_string_buffer(max(cap, 1))
+    n = C.c_uint64(0)
+    rc = inf_lib().inf_raw(data, len(data), out, cap, C.byref(n))
+    return rc, out.raw[:n.value]
+
+
+def deflate_raw(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY):
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+    return c.compress(data) + c.flush()
+
+
+def bgzf_member(chunk: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, extra=b"") -> bytes:
+    """One BGZF member (SAM spec 4.1); `extra`: further subfields in front of BC (allowed by the format)."""
+    cdata = deflate_raw(chunk, level, strategy)
+    xlen = 6 + len(extra)
+    bsize = 12 + xlen + len(cdata) + 8 - 1
+    assert bsize < 65536
+    return (b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", xlen) + extra + b"BC" + struct.pack("<HH", 2, bsize) + cdata
+            + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+
+
+BGZF_EOF = bgzf_member(b"")
+
+
+def bgzf_compress(data: bytes, level=6, block=0xff00, strategy=zlib.Z_DEFAULT_STRATEGY, eof=True) -> bytes:
+    out = b"".join(bgzf_member(data[i:i + block], level, strategy) for i in range(0, len(data), block))
+    return out + (BGZF_EOF if eof else b"")
+
+
+def bgzf_inflate_host(gz: bytes, cap: int, verify=1):
+    out = C.create_string_buffer(max(cap, 1))
+    n = C.c_uint64(0)
+    rc = inf_lib().inf_bgzf(gz, len(gz), out, cap, C.byref(n), verify)
+    return rc, out.raw[:n.value]
+
+
+def _texts():
+    rnd = random.Random(7)
+    vcf = b"".join(b"chr%d\t%d\t.\t%s\t%s\t.\tPASS\tSVTYPE=INS\tGT:AD\t0|1:%d,%d\n" % (rnd.randint(1, 22), rnd.randint(1, 10**8), rnd.choice([b"A", b"ACGT", b"G"]),
+                   rnd.choice([b"T", b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTT", b"C"]), rnd.randint(0, 60), rnd.randint(0, 60)) for _ in range(3000))
+    return {
+        "empty": b"",
+        "one": b"A",
+        "run": b"A" * 70000,                                      # one distance code, matches overlapping their source
+        "two_symbols": b"ABABABABAB" * 500,
+        "text": vcf,
+        "random": bytes(rnd.getrandbits(8) for _ in range(40000)),   # incompressible: zlib stores it
+        "acgt": bytes(rnd.choice(b"ACGT") for _ in range(100000)),   # literals only in practice: few or no distance codes
+        "far": bytes(rnd.getrandbits(8) for _ in range(32768)) * 2 + b"tail",   # matches at the maximum distance
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_texts()))
+@pytest.mark.parametrize("level,strategy", [(0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                                            (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)])
+def test_raw_deflate_streams_vs_zlib(name, level, strategy):
+    data = _texts()[name]
+    comp = deflate_raw(data, level, strategy)
+    assert zlib.decompress(comp, -15) == data
+    rc, out = raw_inflate(comp, len(data))
+    assert rc == 0 and out == data
+
+
+def test_stream_of_many_blocks_and_flush_points():
+    """Z_FULL_FLUSH / Z_SYNC_FLUSH insert empty stored blocks and restart the codes: several blocks of every type in one stream."""
+    rnd = random.Random(3)
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    parts, data = [], b""
+    for i in range(40):
+        chunk = bytes(rnd.choice(b"ACGT\n\t01|/") for _ in range(rnd.randint(0, 3000))) if i % 3 else bytes(rnd.getrandbits(8) for _ in range(rnd.randint(0, 500)))
+        data += chunk
+        parts.append(c.compress(chunk) + c.flush(zlib.Z_FULL_FLUSH if i % 2 else zlib.Z_SYNC_FLUSH))
+    comp = b"".join(parts) + c.flush()
+    rc, out = raw_inflate(comp, len(data))
+    assert rc == 0 and out == data
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.binary(max_size=5000), st.sampled_from([0, 1, 6, 9]), st.sampled_from([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED]))
+def test_raw_deflate_property(data, level, strategy):
+    rc, out = raw_inflate(deflate_raw(data, level, strategy), len(data))
+    assert rc == 0 and out == data
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.sampled_from([b"A", b"C", b"G", b"T", b"\t", b"\n", b"0|1", b"chr1", b"PASS"]), max_size=4000), st.integers(1, 5000))
+def test_bgzf_property(tokens, block):
+    data = b"".join(tokens)
+    rc, out = bgzf_inflate_host(bgzf_compress(data, 6, block), len(data))
+    assert rc == 0 and out == data
+
+
+def test_bgzf_file_layout():
+    data = _texts()["text"]
+    gz = bgzf_compress(data, 6)
+    assert zlib.decompress(gz, 31) == data[:0xff00]                 # (each member is a gzip member)
+    rc, out = bgzf_inflate_host(gz, len(data))
+    assert rc == 0 and out == data
+    # extra subfields before BC, no EOF marker, members of one byte
+    gz2 = bgzf_member(b"hello ", extra=b"XY" + struct.pack("<H", 3) + b"abc") + bgzf_member(b"") + bgzf_member(b"w") + bgzf_member(b"orld")
+    rc, out = bgzf_inflate_host(gz2, 64)
+    assert rc == 0 and out == b"hello world"
+    assert bgzf_inflate_host(b"", 8) == (0, b"")
+
+
+def test_damaged_input_is_rejected():
+    data = _texts()["text"][:20000]
+    gz = bytearray(bgzf_compress(data, 6))
+    rc, _ = bgzf_inflate_host(bytes(gz[:-40]), len(data))            # truncated inside the EOF member
+    assert rc != 0
+    bad = bytearray(gz); bad[len(gz) // 2] ^= 0x55                   # a flipped payload byte: some decode error or the CRC
+    rc, _ = bgzf_inflate_host(bytes(bad), len(data))
+    assert rc != 0
+    plain_gzip = zlib.compressobj(6, zlib.DEFLATED, 31)
+    g = plain_gzip.compress(data) + plain_gzip.flush()
+    rc, _ = bgzf_inflate_host(g, len(data))                          # a gzip file that is not BGZF (no FEXTRA / BC)
+    assert rc % 1000 in (102, 103)
+    # raw streams: block type 3, stored length mismatch, distance before the start, input that ends early
+    assert raw_inflate(bytes([0b111]), 16)[0] == 2
+    assert raw_inflate(bytes([0b001, 5, 0, 0, 0]), 16)[0] == 3
+    comp = deflate_raw(b"abcabcabcabc" * 10, 6, zlib.Z_FIXED)
+    assert raw_inflate(comp[:len(comp) // 2], 200)[0] == 1
+    assert raw_inflate(comp, 10)[0] == 8                              # more output than the caller allows
+    # fixed block: literal 'a', then length 3 at distance 2 with one byte of history
+    stream = _fixed_stream([("lit", ord("a")), ("match", 3, 2), ("end",)])
+    assert raw_inflate(stream, 16)[0] == 7
+
+
+def _fixed_stream(ops):
+    """Assemble a final fixed-Huffman block from literals / matches (RFC 1951 3.2.6) -- Huffman codes MSB first, extra bits LSB first."""
+    bits = []
+    def put_code(code, n):
+        bits.extend((code >> (n - 1 - i)) & 1 for i in range(n))
+    def put_extra(v, n):
+        bits.extend((v >> i) & 1 for i in range(n))
+    def lit(s):
+        if s < 144: put_code(0x30 + s, 8)
+        elif s < 256: put_code(0x190 + s - 144, 9)
+        elif s < 280: put_code(s - 256, 7)
+        else: put_code(0xc0 + s - 280, 8)
+    put_extra(1, 1); put_extra(1, 2)                                 # BFINAL = 1, BTYPE = 01
+    for op in ops:
+        if op[0] == "lit":
+            lit(op[1])
+        elif op[0] == "end":
+            lit(256)
+        else:
+            _, length, dist = op
+            assert 3 <= length <= 10 and 1 <= dist <= 4              # symbols without extra bits
+            lit(254 + length)
+            put_code(dist - 1, 5)
+    while len(bits) % 8:
+        bits.append(0)
+    return bytes(sum(b << i for i, b in enumerate(bits[k:k + 8])) for k in range(0, len(bits), 8))
+
+
+def test_hand_assembled_fixed_block():
+    s = _fixed_stream([("lit", ord("a")), ("lit", ord("b")), ("match", 4, 2), ("match", 3, 1), ("end",)])
+    assert zlib.decompress(s, -15) == b"abababbbb"
+    assert raw_inflate(s, 16) == (0, b"abababbbb")

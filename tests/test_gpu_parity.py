@@ -906,6 +906,63 @@ def test_vcf_ingest_vs_oracle(solver):
     assert solver.compare_batch(built, cfg).diff(orc.compare_batch(host, refs, compare_cfg(cfg))) == []
 
 
+def test_bgzf_inflate_device_vs_zlib(solver):
+    """avk_bgzf_inflate (one thread per BGZF member, CRC-32 checked on the device) against the original bytes that Python's
+    zlib compressed: every block type and strategy of tests/test_bgzf.py, members of very different sizes in one file, the
+    EOF marker, extra subfields; plain gzip, a truncated file and a flipped payload bit fail the call."""
+    import zlib
+    import test_bgzf as B
+    from aardvark_b200.ingest import bgzf_inflate
+    from aardvark_b200.lib import AvkError
+    texts = B._texts()
+    for name, data in sorted(texts.items()):
+        for level, strategy in ((0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY)):
+            gz = B.bgzf_compress(data, level, 0xff00 if level else 0xf000, strategy)
+            assert bgzf_inflate(solver, gz) == data, (name, level, strategy)
+    big = (texts["text"] + texts["acgt"] + texts["random"]) * 6                 # ~2.3 MB, 40 members: more than one CTA of threads
+    for block in (0xff00, 4093, 257):
+        assert bgzf_inflate(solver, B.bgzf_compress(big[:300000] if block == 257 else big, 6, block)) == (big[:300000] if block == 257 else big)
+    gz2 = B.bgzf_member(b"hello ", extra=b"XY" + (3).to_bytes(2, "little") + b"abc") + B.bgzf_member(b"") + B.bgzf_member(b"w") + B.bgzf_member(b"orld")
+    assert bgzf_inflate(solver, gz2) == b"hello world"
+    assert bgzf_inflate(solver, b"") == b"" and bgzf_inflate(solver, B.BGZF_EOF) == b""
+    gz = bytearray(B.bgzf_compress(texts["text"], 6))
+    with pytest.raises(AvkError, match="truncated"):
+        bgzf_inflate(solver, bytes(gz[:-40]))
+    bad = bytearray(gz); bad[len(gz) // 2] ^= 0x55
+    with pytest.raises(AvkError, match="does not inflate|BGZF member"):
+        bgzf_inflate(solver, bytes(bad))
+    tr = bytearray(gz); tr[len(B.bgzf_member(texts["text"][:0xff00])) - 8] ^= 1      # the first member's CRC field
+    with pytest.raises(AvkError, match="code 10"):
+        bgzf_inflate(solver, bytes(tr))
+    assert bgzf_inflate(solver, bytes(tr), verify_crc=False) == texts["text"]
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    with pytest.raises(AvkError, match="not BGZF"):
+        bgzf_inflate(solver, c.compress(texts["text"]) + c.flush())
+
+
+def test_vcf_parse_bgzf_vs_plain_text(solver):
+    """avk_vcf_parse_bgzf = inflate + parse with the text staying on the device: the same table as avk_vcf_parse on the plain
+    text (header lines skipped), for the hand-made records and for a synthetic call set of several members."""
+    import test_bgzf as B
+    import test_vcf_ingest as T
+    from aardvark_b200.ingest import parse_vcf_bgzf, parse_vcf_text
+    from aardvark_b200.lib import AvkError
+    names = ["chr1", "chr2"]
+    for sample, trim, block in ((0, True, 0xff00), (1, False, 97)):         # 97-byte members: records straddle member boundaries
+        assert parse_vcf_bgzf(solver, B.bgzf_compress(T.TEXT, 6, block), names, sample, trim).records() == parse_vcf_text(solver, T.TEXT, names, sample, trim).records()
+    recs = []
+    for c, L in enumerate((400_000, 250_000)):
+        ref, (truth, _q) = synth.callsets_compare(L, synth.SynthParams(n_variants=L // 150), seed=700 + c)
+        recs += [(c, pos, a0, a1, z, t, raw) for (pos, a0, a1, z, t, raw) in truth]
+    text = _vcf_text(recs, names)
+    assert len(text) > 2 * 0xff00                                        # three members
+    tab = parse_vcf_bgzf(solver, B.bgzf_compress(text, 6), names, 0, True)
+    assert tab.records() == recs
+    with pytest.raises(AvkError, match="record 3 cannot be parsed"):
+        parse_vcf_bgzf(solver, B.bgzf_compress(T.HEADER + T.LINES[0] + b"\n" + b"chr1\t5\t.\tA\tG\t.\t.\t.\tDP\t3\t4\n"), names)
+    assert parse_vcf_bgzf(solver, B.BGZF_EOF, names).n_variants == 0
+
+
 def _random_adversarial_batch(n_clusters, seed, maxv=5, maxl0=3, maxins=4, wmax=160, k_inputs=2, p_copy=0.0):
     """Clusters drawn like tests/test_properties.py: overlapping records, repeated positions, ALT == REF, every zygosity,
     low-complexity windows; one window per cluster, laid end to end on one contig."""
