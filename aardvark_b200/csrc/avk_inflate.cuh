@@ -6,10 +6,11 @@
 // SAM specification (gzip members of at most 64 KiB with a "BC" extra subfield holding the member size).  Parity is anchored on
 // zlib: tests/test_bgzf.py compares this decoder, built for the host, with Python's zlib on every block type.
 //
-// BGZF members are independent, so one thread inflates one member (at most 64 KiB of output); the host only walks the member
-// headers (12 + XLEN bytes each) to find the payloads and the output offsets.  Huffman codes are decoded canonically, bit by
-// bit, from per-thread count / symbol tables (~700 bytes of local memory): every lane of a warp runs the same short loop.
-// Host and device share the code (tests/inflate_host.cpp builds it with g++).
+// BGZF members are independent: the host only walks the member headers (12 + XLEN bytes each) to find the payloads and the
+// output offsets, and k_bgzf_inflate (avk_lib.cu) gives every member a warp -- lane 0 runs inflate() below into a 64 KiB window
+// in shared memory, where its tables live too, and the warp writes the window out.  Huffman codes are decoded through a
+// first-level table (9 bits for literals / lengths, 7 for distances) and canonically, bit by bit, beyond it.
+// Host and device share this code (tests/inflate_host.cpp builds it with g++).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
