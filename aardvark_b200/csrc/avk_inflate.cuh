@@ -250,6 +250,118 @@ AVK_HD inline uint32_t crc32(const uint32_t *tab, const uint8_t *p, uint64_t n) 
     return c ^ 0xffffffffu;
 }
 
+// slicing by 4: t4 = T0..T3 (1024 entries), T_k[i] = CRC of byte i followed by k zero bytes
+AVK_HD inline void crc_tables4(uint32_t *t4) {
+    for (uint32_t i = 0; i < 256; ++i) t4[i] = crc_entry(i);
+    for (int t = 1; t < 4; ++t) for (uint32_t i = 0; i < 256; ++i) { const uint32_t p = t4[(t - 1) * 256 + i]; t4[t * 256 + i] = (p >> 8) ^ t4[p & 0xffu]; }
+}
+AVK_HD inline uint32_t crc32_4(const uint32_t *t4, const uint8_t *buf, uint32_t n) {
+    uint32_t c = 0xffffffffu, i = 0;
+    while (i < n && ((uintptr_t)(buf + i) & 3u)) { c = t4[(c ^ buf[i]) & 0xffu] ^ (c >> 8); ++i; }
+    for (; i + 4 <= n; i += 4) {
+        c ^= *(const uint32_t *)(buf + i);                                                  // (little endian)
+        c = t4[768 + (c & 0xffu)] ^ t4[512 + ((c >> 8) & 0xffu)] ^ t4[256 + ((c >> 16) & 0xffu)] ^ t4[c >> 24];
+    }
+    for (; i < n; ++i) c = t4[(c ^ buf[i]) & 0xffu] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+}
+
+// ---- the other direction: one BGZF member's payload from at most 0xff00 bytes ------------------------------------------------
+// (the reference compresses truth.vcf.gz / query.vcf.gz / passing.vcf.gz through noodles' multithreaded bgzf
+// writer, src/writers/compare_parallel.rs:25-214, variant_merger.rs:124-147.  Any valid DEFLATE stream is a valid member: the
+// bytes differ from the reference's compressor's, the inflated content does not.)  One final block with the fixed Huffman
+// codes (RFC 1951 3.2.6) over a greedy LZ77 parse: a hash of the next three bytes remembers the last position they were seen
+// at; a stored block when that does not pay (so a member never exceeds 64 KiB).
+enum { DEFLATE_CHUNK = 0xff00, DEFLATE_HASH_BITS = 12, DEFLATE_MAX_OUT = DEFLATE_CHUNK + 5 };
+
+struct BitWriter {
+    uint8_t *p;
+    uint32_t cap, pos;
+    uint64_t buf;
+    int cnt;
+    bool full;
+    AVK_HD void init(uint8_t *dst, uint32_t n) { p = dst; cap = n; pos = 0; buf = 0; cnt = 0; full = false; }
+    AVK_HD void put(uint32_t v, int k) {                       // k <= 24 bits, LSB first
+        buf |= (uint64_t)v << cnt; cnt += k;
+        while (cnt >= 8) { if (pos < cap) p[pos] = (uint8_t)buf; else full = true; pos += 1; buf >>= 8; cnt -= 8; }
+    }
+    AVK_HD void huff(uint32_t code, int k) {                   // Huffman codes go in most-significant bit first
+        uint32_t r = 0;
+        for (int i = 0; i < k; ++i) r |= ((code >> i) & 1u) << (k - 1 - i);
+        put(r, k);
+    }
+    AVK_HD void finish() { if (cnt > 0) put(0, 8 - cnt); }
+};
+AVK_HD inline void put_litlen(BitWriter &w, int s) {           // fixed code of literal/length symbol s
+    if (s < 144) w.huff(0x30 + s, 8);
+    else if (s < 256) w.huff(0x190 + s - 144, 9);
+    else if (s < 280) w.huff(s - 256, 7);
+    else w.huff(0xc0 + s - 280, 8);
+}
+AVK_HD inline int msb_index(uint32_t v) { int m = 0; while (v >>= 1) ++m; return m; }
+AVK_HD inline void put_match(BitWriter &w, int len, int dist) {
+    int s;
+    if (len <= 10) s = 254 + len;
+    else if (len == 258) s = 285;
+    else { const int l = len - 3, e = msb_index((uint32_t)l) - 2; s = 261 + 4 * e + ((l >> e) & 3); }
+    put_litlen(w, s);
+    w.put((uint32_t)(len - len_base(s)), len_extra(s));
+    const int d = dist - 1;
+    int ds;
+    if (d < 4) ds = d;
+    else { const int m = msb_index((uint32_t)d); ds = 2 * m + ((d >> (m - 1)) & 1); }
+    w.huff((uint32_t)ds, 5);
+    w.put((uint32_t)(dist - dist_base(ds)), dist_extra(ds));
+}
+// head: 1 << DEFLATE_HASH_BITS entries.  Returns the payload length (<= n + 5).
+AVK_HD inline uint32_t deflate_member(const uint8_t *in, uint32_t n, uint8_t *out, uint16_t *head) {
+    for (int i = 0; i < (1 << DEFLATE_HASH_BITS); ++i) head[i] = 0xffff;
+    BitWriter w;
+    w.init(out, n + 4);                                        // anything longer loses to a stored block
+    w.put(1, 1); w.put(1, 2);                                  // BFINAL = 1, BTYPE = 01
+    uint32_t i = 0;
+    while (i < n && !w.full) {
+        int len = 0, dist = 0;
+        if (i + 3 <= n) {
+            const uint32_t h = (((uint32_t)in[i] << 16 | (uint32_t)in[i + 1] << 8 | in[i + 2]) * 2654435761u) >> (32 - DEFLATE_HASH_BITS);
+            const uint32_t cand = head[h];
+            head[h] = (uint16_t)i;
+            if (cand != 0xffff && i - cand <= 32768u) {
+                const int lim = (int)(n - i < 258u ? n - i : 258u);
+                while (len < lim && in[cand + len] == in[i + len]) ++len;
+                dist = (int)(i - cand);
+            }
+        }
+        if (len >= 3) {
+            put_match(w, len, dist);
+            if (len <= 16)                                     // remember the positions inside short matches too
+                for (uint32_t j = i + 1; j < i + (uint32_t)len && j + 3 <= n; ++j)
+                    head[(((uint32_t)in[j] << 16 | (uint32_t)in[j + 1] << 8 | in[j + 2]) * 2654435761u) >> (32 - DEFLATE_HASH_BITS)] = (uint16_t)j;
+            i += (uint32_t)len;
+        } else {
+            put_litlen(w, in[i]);
+            i += 1;
+        }
+    }
+    put_litlen(w, 256);
+    w.finish();
+    if (!w.full && w.pos < n + 5) return w.pos;
+    // stored: BFINAL = 1, BTYPE = 00, padding, LEN, NLEN, bytes
+    out[0] = 1; out[1] = (uint8_t)n; out[2] = (uint8_t)(n >> 8); out[3] = (uint8_t)~n; out[4] = (uint8_t)(~n >> 8);
+    for (uint32_t k = 0; k < n; ++k) out[5 + k] = in[k];
+    return n + 5;
+}
+// the 18 bytes in front of a member's payload and the 8 behind it (SAM specification 4.1); bsize = total member size
+AVK_HD inline void member_header(uint8_t *h, uint32_t payload_len) {
+    const uint32_t bsize = 18 + payload_len + 8 - 1;
+    const uint8_t fixed[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    for (int i = 0; i < 16; ++i) h[i] = fixed[i];
+    h[16] = (uint8_t)bsize; h[17] = (uint8_t)(bsize >> 8);
+}
+AVK_HD inline void member_trailer(uint8_t *t, uint32_t crc, uint32_t isize) {
+    for (int i = 0; i < 4; ++i) { t[i] = (uint8_t)(crc >> (8 * i)); t[4 + i] = (uint8_t)(isize >> (8 * i)); }
+}
+
 // ---- BGZF member walk (host): SAM specification 4.1 ---------------------------------------------------------------------
 struct Member { uint64_t c_off; uint32_t c_len, isize, crc; uint64_t o_off; };
 // returns 0 and the member at byte `at` (next = offset of the following member), or a negative code: -1 truncated, -2 not a

@@ -3341,6 +3341,92 @@ extern "C" int avk_bgzf_inflate(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len
     CK(cudaStreamSynchronize(ctx->stream));
     return AVK_OK;
 }
+// ---- BGZF compression of the text outputs (avk_inflate.cuh::deflate_member): one warp per 0xff00-byte chunk ---------
+// The chunk is staged in shared memory by the whole warp; lane 0 runs the LZ77 parse over it (its hash table is in shared memory
+// too) and writes the payload into the chunk's slot of a scratch buffer; k_bgzf_pack then lays header, payload and trailer of
+// every member end to end (the offsets are the prefix sums of the payload lengths, taken on the host).
+enum { BGZF_DEF_SMEM = avk_inflate::DEFLATE_CHUNK + 2 * (1 << avk_inflate::DEFLATE_HASH_BITS) + 4 * 256 * 4, BGZF_PAY_STRIDE = 65536 };
+__global__ void __launch_bounds__(32) k_bgzf_deflate(const u8 *text, u64 len, u32 n_chunks, u8 *pay, u32 *c_len, u32 *crc) {
+    u8 *win = avk_dyn_smem;
+    uint16_t *head = (uint16_t *)(avk_dyn_smem + avk_inflate::DEFLATE_CHUNK);
+    u32 *crc_t = (u32 *)(avk_dyn_smem + avk_inflate::DEFLATE_CHUNK + 2 * (1 << avk_inflate::DEFLATE_HASH_BITS));
+    const int lane = threadIdx.x;
+    for (u32 i = lane; i < 256; i += 32) crc_t[i] = avk_inflate::crc_entry(i);
+    __syncwarp();
+    for (int t = 1; t < 4; ++t) {
+        for (u32 i = lane; i < 256; i += 32) { const u32 p = crc_t[(t - 1) * 256 + i]; crc_t[t * 256 + i] = (p >> 8) ^ crc_t[p & 0xffu]; }
+        __syncwarp();
+    }
+    for (u32 k = blockIdx.x; k < n_chunks; k += gridDim.x) {
+        const u64 at = (u64)k * avk_inflate::DEFLATE_CHUNK;
+        const u32 n = (u32)min((u64)avk_inflate::DEFLATE_CHUNK, len - at);
+        const u8 *src = text + at;                               // chunk starts are multiples of 0xff00: 16-byte aligned in a cudaMalloc'd buffer
+        const u32 body = n >> 4;
+        for (u32 i = lane; i < body; i += 32) ((uint4 *)win)[i] = ((const uint4 *)src)[i];
+        for (u32 i = (body << 4) + lane; i < n; i += 32) win[i] = src[i];
+        __syncwarp();
+        if (lane == 0) {
+            c_len[k] = avk_inflate::deflate_member(win, n, pay + (u64)k * BGZF_PAY_STRIDE, head);
+            crc[k] = avk_inflate::crc32_4(crc_t, win, n);
+        }
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(128) k_bgzf_pack(const u8 *pay, const u32 *c_len, const u32 *crc, const u64 *m_off, u64 len, u32 n_chunks, u8 *out) {
+    const u32 k = blockIdx.x;                                    // member k; member n_chunks is the EOF marker
+    u8 *dst = out + m_off[k];
+    if (k == n_chunks) {
+        if (threadIdx.x == 0) { avk_inflate::member_header(dst, 2); dst[18] = 3; dst[19] = 0; avk_inflate::member_trailer(dst + 20, 0, 0); }
+        return;
+    }
+    const u32 c = c_len[k];
+    const u64 at = (u64)k * avk_inflate::DEFLATE_CHUNK;
+    if (threadIdx.x == 0) {
+        avk_inflate::member_header(dst, c);
+        avk_inflate::member_trailer(dst + 18 + c, crc[k], (u32)min((u64)avk_inflate::DEFLATE_CHUNK, len - at));
+    }
+    const u8 *src = pay + (u64)k * BGZF_PAY_STRIDE;
+    for (u32 i = threadIdx.x; i < c; i += blockDim.x) dst[18 + i] = src[i];
+}
+extern "C" int avk_bgzf_compress(avk_ctx *ctx, const uint8_t *text, uint64_t len, uint8_t *out, uint64_t cap, uint64_t *out_len) {
+    if (!ctx) return AVK_ERR_INVALID;
+    if ((!text && len) || !out_len) { ctx->err = "avk_bgzf_compress: bad arguments"; return AVK_ERR_INVALID; }
+    const u64 n_chunks = (len + avk_inflate::DEFLATE_CHUNK - 1) / avk_inflate::DEFLATE_CHUNK;
+    if (n_chunks >= 0x7fffffffull) { ctx->err = "avk_bgzf_compress: text too long for one call"; return AVK_ERR_INVALID; }
+    if (!out) { *out_len = len + 31 * n_chunks + 28; return AVK_OK; }        // upper bound: every chunk stored
+    CK(cudaSetDevice(ctx->device));
+    DevBuf *rb = ctx->rb;
+    enum { C_TEXT = V_TEXT, C_PAY = V_GZ, C_LEN = V_NOUT, C_CRC = V_NBYTES, C_OFF = V_STARTS, C_OUT = V_POOL };
+    std::vector<u64> m_off(n_chunks + 2, 0);
+    std::vector<u32> c_len(n_chunks);
+    if (n_chunks) {
+        UPLOAD(rb[C_TEXT], text, len);
+        ENSURE(rb[C_PAY], n_chunks * (u64)BGZF_PAY_STRIDE);
+        ENSURE(rb[C_LEN], 4 * n_chunks); ENSURE(rb[C_CRC], 4 * n_chunks);
+        CK(cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BGZF_DEF_SMEM));
+        k_bgzf_deflate<<<(unsigned)std::min<u64>(n_chunks, 2ull * ctx->sm_count), 32, BGZF_DEF_SMEM, ctx->stream>>>((const u8 *)rb[C_TEXT].p, len, (u32)n_chunks, (u8 *)rb[C_PAY].p,
+                                                                                                                   (u32 *)rb[C_LEN].p, (u32 *)rb[C_CRC].p);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c_len.data(), rb[C_LEN].p, 4 * n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (u64 k = 0; k < n_chunks; ++k) m_off[k + 1] = m_off[k] + 18 + c_len[k] + 8;
+    m_off[n_chunks + 1] = m_off[n_chunks] + 28;
+    const u64 total = m_off[n_chunks + 1];
+    *out_len = total;
+    if (total > cap) { ctx->err = "avk_bgzf_compress: output capacity too small"; return AVK_ERR_OOM; }
+    UPLOAD(rb[C_OFF], m_off.data(), 8 * m_off.size());
+    ENSURE(rb[C_OUT], total);
+    k_bgzf_pack<<<(unsigned)(n_chunks + 1), 128, 0, ctx->stream>>>((const u8 *)rb[C_PAY].p, (const u32 *)rb[C_LEN].p, (const u32 *)rb[C_CRC].p, (const u64 *)rb[C_OFF].p, len,
+                                                                    (u32)n_chunks, (u8 *)rb[C_OUT].p);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, rb[C_OUT].p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AVK_OK;
+}
+
 extern "C" int avk_vcf_parse_bgzf(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int verify_crc, const char *const *contig_names, uint32_t n_contigs,
                                   uint32_t sample_index, int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code) {
     if (!ctx) return AVK_ERR_INVALID;

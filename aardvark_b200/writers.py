@@ -109,3 +109,14 @@ class VariantMerger:
         lib = _bind()
         return _text(lambda buf, cap, n: lib.avk_merge_summary_write(C.byref(self._cb), C.byref(self._co), self._labels, 1 if csv else 0,
                                                                      1 if header else 0, buf, cap, n))
+
+
+def bgzf_compress(solver, text: bytes) -> bytes:
+    """avk_bgzf_compress: text -> a complete BGZF file (EOF marker included), compressed on the device."""
+    lib = solver._lib
+    lib.avk_bgzf_compress.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    n = C.c_uint64(0)
+    solver._check(lib.avk_bgzf_compress(solver._ctx, text, len(text), None, 0, C.byref(n)), "avk_bgzf_compress")
+    buf = C.create_string_buffer(int(n.value) + 1)
+    solver._check(lib.avk_bgzf_compress(solver._ctx, text, len(text), buf, int(n.value), C.byref(n)), "avk_bgzf_compress")
+    return buf.raw[:int(n.value)]

@@ -389,6 +389,13 @@ int avk_bgzf_inflate(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int verif
 int avk_vcf_parse_bgzf(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int verify_crc, const char *const *contig_names, uint32_t n_contigs,
                        uint32_t sample_index, int enable_trimming, avk_vcf_out *out, uint64_t *error_line, int32_t *error_code);
 
+/* avk_bgzf_compress (the BGZF compression behind truth.vcf.gz / query.vcf.gz / passing.vcf.gz and the BED outputs,
+ * src/writers/compare_parallel.rs:25-214, variant_merger.rs:124-147): text -> a complete BGZF file (members of 0xff00 input
+ * bytes + the EOF marker), one warp per member: fixed-Huffman DEFLATE over a greedy LZ77 parse, a stored block where that does
+ * not pay.  The bytes differ from the reference's compressor's (any valid DEFLATE stream is a valid member); the inflated
+ * content, member sizes and CRCs are what zlib / htslib expect.  out == NULL -> *out_len = an upper bound of the size. */
+int avk_bgzf_compress(avk_ctx *ctx, const uint8_t *text, uint64_t len, uint8_t *out, uint64_t cap, uint64_t *out_len);
+
 /* ---- writers: host-side text of what the kernels counted.  buf == NULL: *len receives the size needed.
  * avk_summary_write: the rows SummaryWriter::write_summary (src/writers/summary.rs:166-221, :243-420) emits for ONE
  * GroupTypeMetrics table -- `totals` = avk_compare_out::totals for region_label "ALL", or row s of strat_totals for the

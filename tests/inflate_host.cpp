@@ -35,3 +35,27 @@ extern "C" int inf_bgzf(const uint8_t *gz, uint64_t n, uint8_t *out, uint64_t ca
     *out_len = o;
     return 0;
 }
+
+// text -> BGZF file (members of DEFLATE_CHUNK bytes + the EOF marker) with the compressor the device runs; returns the length
+extern "C" uint64_t def_bgzf(const uint8_t *text, uint64_t n, uint8_t *out, uint64_t cap) {
+    static thread_local uint16_t head[1 << DEFLATE_HASH_BITS];
+    uint32_t t4[1024];
+    crc_tables4(t4);
+    uint64_t o = 0;
+    std::vector<uint8_t> pay(DEFLATE_MAX_OUT + 8);
+    for (uint64_t at = 0; at < n; at += DEFLATE_CHUNK) {
+        const uint32_t len = (uint32_t)(n - at < DEFLATE_CHUNK ? n - at : DEFLATE_CHUNK);
+        const uint32_t c = deflate_member(text + at, len, pay.data(), head);
+        if (o + 18 + c + 8 > cap) return 0;
+        member_header(out + o, c);
+        memcpy(out + o + 18, pay.data(), c);
+        member_trailer(out + o + 18 + c, crc32_4(t4, text + at, len), len);
+        o += 18 + c + 8;
+    }
+    const uint32_t c = deflate_member(text, 0, pay.data(), head);      // EOF marker: an empty member
+    if (o + 18 + c + 8 > cap) return 0;
+    member_header(out + o, c);
+    memcpy(out + o + 18, pay.data(), c);
+    member_trailer(out + o + 18 + c, 0, 0);
+    return o + 18 + c + 8;
+}

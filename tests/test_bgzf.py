@@ -25,6 +25,8 @@ def inf_lib():
     lib = C.CDLL(SO)
     lib.inf_raw.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.inf_bgzf.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+    lib.def_bgzf.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    lib.def_bgzf.restype = C.c_uint64
     return lib
 
 
@@ -189,3 +191,74 @@ def test_hand_assembled_fixed_block():
     s = _fixed_stream([("lit", ord("a")), ("lit", ord("b")), ("match", 4, 2), ("match", 3, 1), ("end",)])
     assert zlib.decompress(s, -15) == b"abababbbb"
     assert raw_inflate(s, 16) == (0, b"abababbbb")
+
+
+# ---- compression: any valid BGZF will do; what is pinned is that zlib (and our own inflate) give the text back ------------------
+
+def gunzip_members(gz: bytes) -> bytes:
+    out, buf = [], gz
+    while buf:
+        d = zlib.decompressobj(31)
+        out.append(d.decompress(buf))
+        assert d.eof
+        buf = d.unused_data
+    return b"".join(out)
+
+
+def bgzf_compress_host(text: bytes) -> bytes:
+    cap = len(text) + (len(text) // 0xff00 + 2) * 64
+    out = C.create_string_buffer(cap)
+    n = inf_lib().def_bgzf(text, len(text), out, cap)
+    assert n > 0
+    return out.raw[:n]
+
+
+def check_bgzf_layout(gz: bytes, text: bytes):
+    """members of at most 64 KiB with the BC subfield, the sizes and CRCs of the chunks, the 28-byte EOF marker at the end"""
+    at, chunks = 0, []
+    while at < len(gz):
+        assert gz[at:at + 4] == b"\x1f\x8b\x08\x04" and gz[at + 10:at + 16] == b"\x06\x00BC\x02\x00"
+        bsize = struct.unpack("<H", gz[at + 16:at + 18])[0] + 1
+        crc, isize = struct.unpack("<II", gz[at + bsize - 8:at + bsize])
+        chunks.append((crc, isize))
+        at += bsize
+    assert at == len(gz)
+    assert chunks[-1] == (0, 0) and gz[-28:] == BGZF_EOF
+    want = [(zlib.crc32(text[i:i + 0xff00]) & 0xffffffff, len(text[i:i + 0xff00])) for i in range(0, len(text), 0xff00)]
+    assert chunks[:-1] == want
+
+
+@pytest.mark.parametrize("name", sorted(_texts()))
+def test_bgzf_compress_round_trip(name):
+    text = _texts()[name] * (3 if name in ("text", "acgt") else 1)
+    gz = bgzf_compress_host(text)
+    check_bgzf_layout(gz, text)
+    assert gunzip_members(gz) == text                                 # zlib reads it
+    rc, out = bgzf_inflate_host(gz, len(text))                        # and so does the decoder above
+    assert rc == 0 and out == text
+    if name == "text":
+        assert len(gz) < len(text) // 2                               # VCF text: the LZ77 parse finds the repeats
+    if name == "random":
+        assert len(gz) <= len(text) + 5 + 26 + 28                     # incompressible: one stored member + EOF
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.one_of(st.binary(max_size=3000), st.lists(st.sampled_from([b"A", b"C", b"chr1\t", b"0|1", b"\n", b"PASS", b"\xff\xfe"]), max_size=3000).map(b"".join)))
+def test_bgzf_compress_property(data):
+    gz = bgzf_compress_host(data)
+    assert gunzip_members(gz) == data
+    check_bgzf_layout(gz, data)
+
+
+def test_bgzf_compress_long_matches_and_lengths():
+    """every match length 3..258 and distances across the code boundaries: runs and periodic text"""
+    rnd = random.Random(11)
+    parts = []
+    for length in list(range(3, 40)) + [57, 58, 59, 113, 114, 115, 130, 131, 226, 227, 257, 258, 259, 300]:
+        seed = bytes(rnd.getrandbits(8) for _ in range(6))
+        parts.append(seed + bytes(rnd.choice(b"ACGT") for _ in range(rnd.choice([1, 2, 5, 30, 200, 1500]))) + (seed * 60)[:length])
+    text = b"".join(parts)
+    assert gunzip_members(bgzf_compress_host(text)) == text
+    far = bytes(rnd.getrandbits(8) for _ in range(300)) + bytes(rnd.choice(b"AC") for _ in range(32768 - 300)) + b"tail"
+    far = far + far[:300]                                             # a repeat exactly 32768 back, and one just beyond the window
+    assert gunzip_members(bgzf_compress_host(far)) == far
