@@ -269,10 +269,11 @@ AVK_HD inline uint32_t crc32_4(const uint32_t *t4, const uint8_t *buf, uint32_t 
 // ---- the other direction: one BGZF member's payload from at most 0xff00 bytes ------------------------------------------------
 // (the reference compresses truth.vcf.gz / query.vcf.gz / passing.vcf.gz through noodles' multithreaded bgzf
 // writer, src/writers/compare_parallel.rs:25-214, variant_merger.rs:124-147.  Any valid DEFLATE stream is a valid member: the
-// bytes differ from the reference's compressor's, the inflated content does not.)  One final block with the fixed Huffman
-// codes (RFC 1951 3.2.6) over a greedy LZ77 parse: a hash of the next three bytes remembers the last position they were seen
-// at; a stored block when that does not pay (so a member never exceeds 64 KiB).
-enum { DEFLATE_CHUNK = 0xff00, DEFLATE_HASH_BITS = 12, DEFLATE_MAX_OUT = DEFLATE_CHUNK + 5 };
+// bytes differ from the reference's compressor's, the inflated content does not.)  One final block over a greedy LZ77 parse --
+// a hash of the next three bytes remembers the last position they were seen at.  The parse runs twice: once to count the
+// symbols, from which length-limited Huffman codes are built (RFC 1951 3.2.7, dynamic block), once to emit; tiny inputs take
+// the fixed codes (3.2.6), and a stored block replaces whatever does not pay, so a member never exceeds 64 KiB.
+enum { DEFLATE_CHUNK = 0xff00, DEFLATE_HASH_BITS = 12, DEFLATE_MAX_OUT = DEFLATE_CHUNK + 5, DEFLATE_DYN_MIN = 128 };
 
 struct BitWriter {
     uint8_t *p;
@@ -285,45 +286,134 @@ struct BitWriter {
         buf |= (uint64_t)v << cnt; cnt += k;
         while (cnt >= 8) { if (pos < cap) p[pos] = (uint8_t)buf; else full = true; pos += 1; buf >>= 8; cnt -= 8; }
     }
-    AVK_HD void huff(uint32_t code, int k) {                   // Huffman codes go in most-significant bit first
-        uint32_t r = 0;
-        for (int i = 0; i < k; ++i) r |= ((code >> i) & 1u) << (k - 1 - i);
-        put(r, k);
-    }
     AVK_HD void finish() { if (cnt > 0) put(0, 8 - cnt); }
 };
-AVK_HD inline void put_litlen(BitWriter &w, int s) {           // fixed code of literal/length symbol s
-    if (s < 144) w.huff(0x30 + s, 8);
-    else if (s < 256) w.huff(0x190 + s - 144, 9);
-    else if (s < 280) w.huff(s - 256, 7);
-    else w.huff(0xc0 + s - 280, 8);
+AVK_HD inline uint32_t bit_reverse(uint32_t code, int k) {     // Huffman codes go into the stream most-significant bit first
+    uint32_t r = 0;
+    for (int i = 0; i < k; ++i) r |= ((code >> i) & 1u) << (k - 1 - i);
+    return r;
 }
 AVK_HD inline int msb_index(uint32_t v) { int m = 0; while (v >>= 1) ++m; return m; }
-AVK_HD inline void put_match(BitWriter &w, int len, int dist) {
-    int s;
-    if (len <= 10) s = 254 + len;
-    else if (len == 258) s = 285;
-    else { const int l = len - 3, e = msb_index((uint32_t)l) - 2; s = 261 + 4 * e + ((l >> e) & 3); }
-    put_litlen(w, s);
-    w.put((uint32_t)(len - len_base(s)), len_extra(s));
-    const int d = dist - 1;
-    int ds;
-    if (d < 4) ds = d;
-    else { const int m = msb_index((uint32_t)d); ds = 2 * m + ((d >> (m - 1)) & 1); }
-    w.huff((uint32_t)ds, 5);
-    w.put((uint32_t)(dist - dist_base(ds)), dist_extra(ds));
+AVK_HD inline int len_symbol(int len) {
+    if (len <= 10) return 254 + len;
+    if (len == 258) return 285;
+    const int l = len - 3, e = msb_index((uint32_t)l) - 2;
+    return 261 + 4 * e + ((l >> e) & 3);
 }
-// head: 1 << DEFLATE_HASH_BITS entries.  Returns the payload length (<= n + 5).
-AVK_HD inline uint32_t deflate_member(const uint8_t *in, uint32_t n, uint8_t *out, uint16_t *head) {
+AVK_HD inline int dist_symbol(int dist) {
+    const int d = dist - 1;
+    if (d < 4) return d;
+    const int m = msb_index((uint32_t)d);
+    return 2 * m + ((d >> (m - 1)) & 1);
+}
+
+// everything deflate_member needs besides its input and output (shared memory on the device)
+struct DeflateWork {
+    uint16_t head[1 << DEFLATE_HASH_BITS];
+    uint32_t lfreq[286], dfreq[30], cfreq[19];
+    uint16_t lcode[286], dcode[30], ccode[19];         // bit-reversed canonical codes
+    uint8_t llen[286], dlen[30], clen[19];
+    uint8_t seq[316 + 4];                               // code lengths of both alphabets, in order
+    uint32_t weight[2 * 286];                           // Huffman construction: leaves then internal nodes
+    uint16_t parent[2 * 286];
+};
+
+// Code lengths of an optimal prefix code for freq[0..n), at most `limit` bits: the two lightest live nodes are merged until one
+// is left (n <= 286: a quadratic scan is cheap); if the tree comes out deeper than the limit the weights are halved (rounding
+// up, so used symbols stay used) and it is built again.  One used symbol gets one bit.
+AVK_HD inline void huff_lengths(DeflateWork &w, const uint32_t *freq, int n, int limit, uint8_t *len) {
+    int shift = 0;
+    for (;;) {
+        int live = 0;
+        for (int i = 0; i < n; ++i) {
+            w.weight[i] = freq[i] ? ((freq[i] - 1) >> shift) + 1 : 0;
+            w.parent[i] = 0xffff;
+            if (freq[i]) ++live;
+        }
+        if (live == 0) { for (int i = 0; i < n; ++i) len[i] = 0; return; }
+        if (live == 1) { for (int i = 0; i < n; ++i) len[i] = freq[i] ? 1 : 0; return; }
+        int nodes = n;
+        while (live > 1) {
+            int a = -1, b = -1;                          // lightest, second lightest among the nodes without a parent
+            for (int i = 0; i < nodes; ++i) {
+                if (w.parent[i] != 0xffff || w.weight[i] == 0) continue;
+                if (a < 0 || w.weight[i] < w.weight[a]) { b = a; a = i; }
+                else if (b < 0 || w.weight[i] < w.weight[b]) b = i;
+            }
+            w.weight[nodes] = w.weight[a] + w.weight[b];
+            w.parent[nodes] = 0xffff;
+            w.parent[a] = w.parent[b] = (uint16_t)nodes;
+            nodes += 1; live -= 1;
+        }
+        int deepest = 0;
+        for (int i = 0; i < n; ++i) {
+            int d = 0;
+            if (freq[i]) for (int j = i; w.parent[j] != 0xffff; j = w.parent[j]) ++d;
+            len[i] = (uint8_t)d;
+            if (d > deepest) deepest = d;
+        }
+        if (deepest <= limit) return;
+        shift += 1;
+    }
+}
+// canonical codes of RFC 1951 3.2.2 from the lengths, stored bit-reversed
+AVK_HD inline void huff_codes(const uint8_t *len, int n, uint16_t *code) {
+    int count[16], next[16];
+    for (int l = 0; l < 16; ++l) count[l] = 0;
+    for (int i = 0; i < n; ++i) count[len[i]] += 1;
+    count[0] = 0;
+    int c = 0;
+    for (int l = 1; l < 16; ++l) { c = (c + count[l - 1]) << 1; next[l] = c; }
+    for (int i = 0; i < n; ++i) code[i] = len[i] ? (uint16_t)bit_reverse((uint32_t)next[len[i]]++, len[i]) : 0;
+}
+
+struct CountSink {
+    DeflateWork &w;
+    AVK_HD bool stop() const { return false; }
+    AVK_HD void lit(int b) { w.lfreq[b] += 1; }
+    AVK_HD void match(int len, int dist) { w.lfreq[len_symbol(len)] += 1; w.dfreq[dist_symbol(dist)] += 1; }
+};
+struct EmitSink {                                       // with the codes in w (dynamic block)
+    DeflateWork &w;
+    BitWriter &o;
+    AVK_HD bool stop() const { return o.full; }
+    AVK_HD void lit(int b) { o.put(w.lcode[b], w.llen[b]); }
+    AVK_HD void match(int len, int dist) {
+        const int s = len_symbol(len), ds = dist_symbol(dist);
+        o.put(w.lcode[s], w.llen[s]);
+        o.put((uint32_t)(len - len_base(s)), len_extra(s));
+        o.put(w.dcode[ds], w.dlen[ds]);
+        o.put((uint32_t)(dist - dist_base(ds)), dist_extra(ds));
+    }
+};
+AVK_HD inline void put_fixed_litlen(BitWriter &o, int s) {
+    if (s < 144) o.put(bit_reverse(0x30 + s, 8), 8);
+    else if (s < 256) o.put(bit_reverse(0x190 + s - 144, 9), 9);
+    else if (s < 280) o.put(bit_reverse(s - 256, 7), 7);
+    else o.put(bit_reverse(0xc0 + s - 280, 8), 8);
+}
+struct FixedSink {
+    BitWriter &o;
+    AVK_HD bool stop() const { return o.full; }
+    AVK_HD void lit(int b) { put_fixed_litlen(o, b); }
+    AVK_HD void match(int len, int dist) {
+        const int s = len_symbol(len), ds = dist_symbol(dist);
+        put_fixed_litlen(o, s);
+        o.put((uint32_t)(len - len_base(s)), len_extra(s));
+        o.put(bit_reverse((uint32_t)ds, 5), 5);
+        o.put((uint32_t)(dist - dist_base(ds)), dist_extra(ds));
+    }
+};
+AVK_HD inline uint32_t hash3(const uint8_t *p) { return (((uint32_t)p[0] << 16 | (uint32_t)p[1] << 8 | p[2]) * 2654435761u) >> (32 - DEFLATE_HASH_BITS); }
+// the greedy parse: deterministic, so the counting pass and the emitting pass see the same literals and matches
+template <class Sink>
+AVK_HD inline void lz_parse(const uint8_t *in, uint32_t n, uint16_t *head, Sink &sink) {
     for (int i = 0; i < (1 << DEFLATE_HASH_BITS); ++i) head[i] = 0xffff;
-    BitWriter w;
-    w.init(out, n + 4);                                        // anything longer loses to a stored block
-    w.put(1, 1); w.put(1, 2);                                  // BFINAL = 1, BTYPE = 01
     uint32_t i = 0;
-    while (i < n && !w.full) {
+    while (i < n && !sink.stop()) {
         int len = 0, dist = 0;
         if (i + 3 <= n) {
-            const uint32_t h = (((uint32_t)in[i] << 16 | (uint32_t)in[i + 1] << 8 | in[i + 2]) * 2654435761u) >> (32 - DEFLATE_HASH_BITS);
+            const uint32_t h = hash3(in + i);
             const uint32_t cand = head[h];
             head[h] = (uint16_t)i;
             if (cand != 0xffff && i - cand <= 32768u) {
@@ -333,19 +423,85 @@ AVK_HD inline uint32_t deflate_member(const uint8_t *in, uint32_t n, uint8_t *ou
             }
         }
         if (len >= 3) {
-            put_match(w, len, dist);
+            sink.match(len, dist);
             if (len <= 16)                                     // remember the positions inside short matches too
-                for (uint32_t j = i + 1; j < i + (uint32_t)len && j + 3 <= n; ++j)
-                    head[(((uint32_t)in[j] << 16 | (uint32_t)in[j + 1] << 8 | in[j + 2]) * 2654435761u) >> (32 - DEFLATE_HASH_BITS)] = (uint16_t)j;
+                for (uint32_t j = i + 1; j < i + (uint32_t)len && j + 3 <= n; ++j) head[hash3(in + j)] = (uint16_t)j;
             i += (uint32_t)len;
         } else {
-            put_litlen(w, in[i]);
+            sink.lit(in[i]);
             i += 1;
         }
     }
-    put_litlen(w, 256);
-    w.finish();
-    if (!w.full && w.pos < n + 5) return w.pos;
+}
+// header of a dynamic block (3.2.7): HLIT, HDIST, HCLEN, the code-length code, then both alphabets' lengths run-length coded
+AVK_HD inline void put_dynamic_header(DeflateWork &w, BitWriter &o) {
+    int hlit = 286, hdist = 30;
+    while (hlit > 257 && w.llen[hlit - 1] == 0) --hlit;
+    while (hdist > 1 && w.dlen[hdist - 1] == 0) --hdist;
+    const int total = hlit + hdist;
+    for (int i = 0; i < hlit; ++i) w.seq[i] = w.llen[i];
+    for (int i = 0; i < hdist; ++i) w.seq[hlit + i] = w.dlen[i];
+    // two passes over the same run-length tokenisation: count, then emit
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0) for (int i = 0; i < 19; ++i) w.cfreq[i] = 0;
+        else {
+            huff_lengths(w, w.cfreq, 19, 7, w.clen);
+            huff_codes(w.clen, 19, w.ccode);
+            const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+            int hclen = 19;
+            while (hclen > 4 && w.clen[order[hclen - 1]] == 0) --hclen;
+            o.put((uint32_t)(hlit - 257), 5); o.put((uint32_t)(hdist - 1), 5); o.put((uint32_t)(hclen - 4), 4);
+            for (int i = 0; i < hclen; ++i) o.put(w.clen[order[i]], 3);
+        }
+        int i = 0;
+        while (i < total) {
+            const int v = w.seq[i];
+            int run = 1;
+            while (i + run < total && w.seq[i + run] == v) ++run;
+            int sym, extra = 0, ebits = 0, used;
+            if (v == 0 && run >= 11) { used = run < 138 ? run : 138; sym = 18; extra = used - 11; ebits = 7; }
+            else if (v == 0 && run >= 3) { used = run; sym = 17; extra = used - 3; ebits = 3; }
+            else { used = 1; sym = v; }                                  // the length itself; repeats of a non-zero one follow as 16s
+            if (pass == 0) w.cfreq[sym] += 1; else { o.put(w.ccode[sym], w.clen[sym]); o.put((uint32_t)extra, ebits); }
+            i += used;
+            if (v != 0 && sym == v) {                                     // repeats of a non-zero length: 16 copies the previous one 3..6 times
+                int left = run - 1;
+                while (left >= 3) {
+                    const int r = left < 6 ? left : 6;
+                    if (pass == 0) w.cfreq[16] += 1; else { o.put(w.ccode[16], w.clen[16]); o.put((uint32_t)(r - 3), 2); }
+                    left -= r; i += r;
+                }
+            }
+        }
+    }
+}
+// Returns the payload length (<= n + 5).
+AVK_HD inline uint32_t deflate_member(const uint8_t *in, uint32_t n, uint8_t *out, DeflateWork &w) {
+    BitWriter o;
+    o.init(out, n + 4);                                        // anything longer loses to a stored block
+    if (n < DEFLATE_DYN_MIN) {
+        o.put(1, 1); o.put(1, 2);                              // BFINAL = 1, BTYPE = 01
+        FixedSink fs{o};
+        lz_parse(in, n, w.head, fs);
+        put_fixed_litlen(o, 256);
+    } else {
+        for (int i = 0; i < 286; ++i) w.lfreq[i] = 0;
+        for (int i = 0; i < 30; ++i) w.dfreq[i] = 0;
+        w.lfreq[256] = 1;
+        CountSink cs{w};
+        lz_parse(in, n, w.head, cs);
+        huff_lengths(w, w.lfreq, 286, 15, w.llen);
+        huff_lengths(w, w.dfreq, 30, 15, w.dlen);
+        huff_codes(w.llen, 286, w.lcode);
+        huff_codes(w.dlen, 30, w.dcode);
+        o.put(1, 1); o.put(2, 2);                              // BFINAL = 1, BTYPE = 10
+        put_dynamic_header(w, o);
+        EmitSink es{w, o};
+        lz_parse(in, n, w.head, es);
+        o.put(w.lcode[256], w.llen[256]);
+    }
+    o.finish();
+    if (!o.full && o.pos < n + 5) return o.pos;
     // stored: BFINAL = 1, BTYPE = 00, padding, LEN, NLEN, bytes
     out[0] = 1; out[1] = (uint8_t)n; out[2] = (uint8_t)(n >> 8); out[3] = (uint8_t)~n; out[4] = (uint8_t)(~n >> 8);
     for (uint32_t k = 0; k < n; ++k) out[5 + k] = in[k];

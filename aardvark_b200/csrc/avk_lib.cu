@@ -3342,14 +3342,14 @@ extern "C" int avk_bgzf_inflate(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len
     return AVK_OK;
 }
 // ---- BGZF compression of the text outputs (avk_inflate.cuh::deflate_member): one warp per 0xff00-byte chunk ---------
-// The chunk is staged in shared memory by the whole warp; lane 0 runs the LZ77 parse over it (its hash table is in shared memory
-// too) and writes the payload into the chunk's slot of a scratch buffer; k_bgzf_pack then lays header, payload and trailer of
+// The chunk is staged in shared memory by the whole warp; lane 0 runs the two LZ77 passes over it (hash table, symbol counts and
+// Huffman codes are in shared memory too) and writes the payload into the chunk's slot of a scratch buffer; k_bgzf_pack then lays header, payload and trailer of
 // every member end to end (the offsets are the prefix sums of the payload lengths, taken on the host).
-enum { BGZF_DEF_SMEM = avk_inflate::DEFLATE_CHUNK + 2 * (1 << avk_inflate::DEFLATE_HASH_BITS) + 4 * 256 * 4, BGZF_PAY_STRIDE = 65536 };
+enum { BGZF_DEF_WORK = (sizeof(avk_inflate::DeflateWork) + 15) & ~15, BGZF_DEF_SMEM = avk_inflate::DEFLATE_CHUNK + BGZF_DEF_WORK + 4 * 256 * 4, BGZF_PAY_STRIDE = 65536 };
 __global__ void __launch_bounds__(32) k_bgzf_deflate(const u8 *text, u64 len, u32 n_chunks, u8 *pay, u32 *c_len, u32 *crc) {
     u8 *win = avk_dyn_smem;
-    uint16_t *head = (uint16_t *)(avk_dyn_smem + avk_inflate::DEFLATE_CHUNK);
-    u32 *crc_t = (u32 *)(avk_dyn_smem + avk_inflate::DEFLATE_CHUNK + 2 * (1 << avk_inflate::DEFLATE_HASH_BITS));
+    avk_inflate::DeflateWork &work = *(avk_inflate::DeflateWork *)(avk_dyn_smem + avk_inflate::DEFLATE_CHUNK);      // hash table, symbol counts, codes
+    u32 *crc_t = (u32 *)(avk_dyn_smem + avk_inflate::DEFLATE_CHUNK + BGZF_DEF_WORK);
     const int lane = threadIdx.x;
     for (u32 i = lane; i < 256; i += 32) crc_t[i] = avk_inflate::crc_entry(i);
     __syncwarp();
@@ -3366,7 +3366,7 @@ __global__ void __launch_bounds__(32) k_bgzf_deflate(const u8 *text, u64 len, u3
         for (u32 i = (body << 4) + lane; i < n; i += 32) win[i] = src[i];
         __syncwarp();
         if (lane == 0) {
-            c_len[k] = avk_inflate::deflate_member(win, n, pay + (u64)k * BGZF_PAY_STRIDE, head);
+            c_len[k] = avk_inflate::deflate_member(win, n, pay + (u64)k * BGZF_PAY_STRIDE, work);
             crc[k] = avk_inflate::crc32_4(crc_t, win, n);
         }
         __syncwarp();

@@ -391,7 +391,7 @@ int avk_vcf_parse_bgzf(avk_ctx *ctx, const uint8_t *gz, uint64_t gz_len, int ver
 
 /* avk_bgzf_compress (the BGZF compression behind truth.vcf.gz / query.vcf.gz / passing.vcf.gz and the BED outputs,
  * src/writers/compare_parallel.rs:25-214, variant_merger.rs:124-147): text -> a complete BGZF file (members of 0xff00 input
- * bytes + the EOF marker), one warp per member: fixed-Huffman DEFLATE over a greedy LZ77 parse, a stored block where that does
+ * bytes + the EOF marker), one warp per member: dynamic-Huffman DEFLATE over a greedy LZ77 parse, a stored block where that does
  * not pay.  The bytes differ from the reference's compressor's (any valid DEFLATE stream is a valid member); the inflated
  * content, member sizes and CRCs are what zlib / htslib expect.  out == NULL -> *out_len = an upper bound of the size. */
 int avk_bgzf_compress(avk_ctx *ctx, const uint8_t *text, uint64_t len, uint8_t *out, uint64_t cap, uint64_t *out_len);

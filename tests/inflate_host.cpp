@@ -38,7 +38,7 @@ extern "C" int inf_bgzf(const uint8_t *gz, uint64_t n, uint8_t *out, uint64_t ca
 
 // text -> BGZF file (members of DEFLATE_CHUNK bytes + the EOF marker) with the compressor the device runs; returns the length
 extern "C" uint64_t def_bgzf(const uint8_t *text, uint64_t n, uint8_t *out, uint64_t cap) {
-    static thread_local uint16_t head[1 << DEFLATE_HASH_BITS];
+    static thread_local DeflateWork head;
     uint32_t t4[1024];
     crc_tables4(t4);
     uint64_t o = 0;
@@ -58,4 +58,10 @@ extern "C" uint64_t def_bgzf(const uint8_t *text, uint64_t n, uint8_t *out, uint
     memcpy(out + o + 18, pay.data(), c);
     member_trailer(out + o + 18 + c, 0, 0);
     return o + 18 + c + 8;
+}
+
+// the length-limited Huffman construction on its own: lengths for freq[0..n) with at most `limit` bits
+extern "C" void def_huff_lengths(const uint32_t *freq, int n, int limit, uint8_t *len) {
+    static thread_local DeflateWork w;
+    huff_lengths(w, freq, n, limit, len);
 }

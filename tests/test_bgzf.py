@@ -27,6 +27,7 @@ def inf_lib():
     lib.inf_bgzf.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
     lib.def_bgzf.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
     lib.def_bgzf.restype = C.c_uint64
+    lib.def_huff_lengths.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(C.c_uint8)]
     return lib
 
 
@@ -262,3 +263,66 @@ def test_bgzf_compress_long_matches_and_lengths():
     far = bytes(rnd.getrandbits(8) for _ in range(300)) + bytes(rnd.choice(b"AC") for _ in range(32768 - 300)) + b"tail"
     far = far + far[:300]                                             # a repeat exactly 32768 back, and one just beyond the window
     assert gunzip_members(bgzf_compress_host(far)) == far
+
+
+def _huff_lengths(freq, limit):
+    f = np.asarray(freq, dtype=np.uint32)
+    out = np.zeros(f.size, dtype=np.uint8)
+    inf_lib().def_huff_lengths(f.ctypes.data_as(C.POINTER(C.c_uint32)), f.size, limit, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out.tolist()
+
+
+def _optimal_cost(freq):
+    import heapq
+    h = [f for f in freq if f]
+    if len(h) < 2:
+        return sum(h)
+    heapq.heapify(h)
+    cost = 0
+    while len(h) > 1:
+        a, b = heapq.heappop(h), heapq.heappop(h)
+        cost += a + b
+        heapq.heappush(h, a + b)
+    return cost
+
+
+def test_huffman_lengths_are_prefix_codes_within_the_limit():
+    rnd = random.Random(2)
+    fib = [1, 1]
+    while len(fib) < 40:
+        fib.append(fib[-1] + fib[-2])
+    cases = [[rnd.randint(0, 1000) for _ in range(286)], [rnd.choice([0, 0, 0, 5]) for _ in range(286)], fib[:30], fib[:19], fib[:25] + [0] * 200,
+             [1] * 286, [0] * 29 + [7], [3, 0, 9], [2 ** k for k in range(19)], [0] * 30]
+    for freq in cases:
+        n = len(freq)
+        limit = 7 if n == 19 else 15
+        lens = _huff_lengths(freq, limit)
+        used = [l for f, l in zip(freq, lens) if f]
+        assert all(l == 0 for f, l in zip(freq, lens) if not f)
+        assert all(1 <= l <= limit for l in used)
+        if len(used) > 1:
+            assert sum(2.0 ** -l for l in used) == 1.0                 # a complete prefix code (what zlib's inflate insists on)
+        cost = sum(f * l for f, l in zip(freq, lens))
+        opt = _optimal_cost(freq)
+        if len(used) > 1 and max(_huff_lengths(freq, 64)) <= limit:
+            assert cost == opt                                         # no limit in play: optimal
+        elif len(used) > 1:
+            assert opt <= cost <= 1.1 * opt + len(used)                # the halving heuristic costs little
+
+
+def test_bgzf_compress_skewed_symbols_hit_the_length_limit():
+    """byte k occurs F(k) times and no three-byte window repeats often enough to hide that: codes deeper than 15 bits are limited"""
+    rnd = random.Random(9)
+    fib = [1, 1]
+    while len(fib) < 22:
+        fib.append(fib[-1] + fib[-2])
+    data = bytearray()
+    for k, f in enumerate(fib):
+        data += bytes([k + 65]) * f
+    data = bytes(data)
+    perm = list(data)
+    rnd.shuffle(perm)
+    for text in (data, bytes(perm)):
+        gz = bgzf_compress_host(text)
+        assert gunzip_members(gz) == text
+        check_bgzf_layout(gz, text)
