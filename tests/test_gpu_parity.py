@@ -986,6 +986,62 @@ def test_vcf_parse_bgzf_vs_plain_text(solver):
     assert parse_vcf_bgzf(solver, B.BGZF_EOF, names).n_variants == 0
 
 
+def test_pipeline_bgzf_vcf_in_bgzf_outputs_out(solver):
+    """The whole chain a host would run for `aardvark compare`, every stage on the device: two BGZF-compressed VCFs ->
+    avk_vcf_parse_bgzf -> avk_build_regions_bed (two contigs, BED confidence regions) -> avk_compare_batch with device-side
+    stratification -> summary rows and labelled VCF records -> avk_bgzf_compress.  Checked against the oracle's own chain on the
+    plain text (vcf_parse -> build_regions_bed -> compare_batch): same batch, same results, same summary text; the compressed
+    outputs inflate (zlib) to exactly the record lines."""
+    import test_bgzf as B
+    from aardvark_b200.batch import BedIntervals, CallSets, StratIntervals
+    from aardvark_b200.ingest import parse_vcf_bgzf
+    from aardvark_b200.writers import SummaryWriter, bgzf_compress, vcf_record_lines
+    names = ["chrA", "chrB"]
+    refs, sides = [], [[], []]
+    for c, L in enumerate((120_000, 60_000)):
+        p = synth.SynthParams(n_variants=L // 120, sv_events=2 if c == 0 else 0, sv_min=60, sv_max=300)
+        ref, (truth, query) = synth.callsets_compare(L, p, seed=900 + c)
+        refs.append(ref)
+        for k, lst in enumerate((truth, query)):
+            sides[k] += [(c, pos, a0, a1, z, t, raw) for (pos, a0, a1, z, t, raw) in lst]
+    texts = [_vcf_text(recs, names) for recs in sides]
+    bed = BedIntervals([[(1_000, 50_000), (52_000, 118_000)], [(0, 59_000)]])
+    strat = StratIntervals([[(0, 0, 40_000), (1, 10_000, 30_000)], [(0, 30_000, 120_000)]], 2)
+    # device chain
+    solver.set_reference(refs)
+    solver.set_stratifications(strat)
+    parsed = [parse_vcf_bgzf(solver, B.bgzf_compress(t, 6, 0x4000), names, 0, True) for t in texts]
+    cs = CallSets([[r[1:] for r in tab.records()] for tab in parsed], contigs=[[r[0] for r in tab.records()] for tab in parsed])
+    built = solver.build_regions(cs, 0, 50, bed=bed)
+    cfg = CompareConfig(enable_sequences=False)
+    gpu = solver.compare_batch(built, cfg, n_strata=2, device_strata=True, containment=True)
+    # oracle chain on the plain text
+    o_tabs = [orc.vcf_parse(t, names, 0, True)[0] for t in texts]
+    o_cs = CallSets([[r[1:] for r in tab.records()] for tab in o_tabs], contigs=[[r[0] for r in tab.records()] for tab in o_tabs])
+    host = orc.build_regions_bed(o_cs, [r.size for r in refs], 50, bed)
+    _same_batch(built, host)
+    masks = orc.containments(host, strat)
+    from aardvark_b200.batch import masks_to_membership
+    so, si = masks_to_membership(masks)
+    cpu = orc.compare_batch(host, refs, compare_cfg(cfg), strat_off=so, strat_idx=si, n_strata=2)
+    assert gpu.diff(cpu) == []
+    assert np.array_equal(gpu.containment[:host.n_regions], masks)
+    sw = SummaryWriter("pipeline", strat_labels=["low", "high"])
+    assert sw.summary_text(gpu.totals, gpu.strat_totals) == sw.summary_text(cpu.totals, cpu.strat_totals)
+    for side in (0, 1):
+        lines = vcf_record_lines(built, side, names, gpu).encode()
+        assert lines == vcf_record_lines(host, side, names, cpu).encode() and lines.count(b"\n") == len(sides[side]) - _dropped(sides[side], bed)
+        gz = bgzf_compress(solver, lines)
+        B.check_bgzf_layout(gz, lines)
+        assert B.gunzip_members(gz) == lines
+
+
+def _dropped(records, bed_obj):
+    """records outside every BED interval (or overlapping a boundary) never reach a region"""
+    ivs = {0: [(1_000, 50_000), (52_000, 118_000)], 1: [(0, 59_000)]}
+    return sum(1 for (c, pos, a0, *_r) in records if not any(s <= pos and pos + len(a0) <= e for (s, e) in ivs[c]))
+
+
 def _random_adversarial_batch(n_clusters, seed, maxv=5, maxl0=3, maxins=4, wmax=160, k_inputs=2, p_copy=0.0):
     """Clusters drawn like tests/test_properties.py: overlapping records, repeated positions, ALT == REF, every zygosity,
     low-complexity windows; one window per cluster, laid end to end on one contig."""
