@@ -87,6 +87,7 @@ extern "C" int sp_solve_batch(const avk_region_batch *b, const uint8_t *const *c
     for (int k = 0; k < 4; ++k) stats[k] = 0;
     for (uint64_t r = 0; r < b->n_regions; ++r) {
         rejected[r] = 1;
+        if (cfg->enable_exact_shortcut || cfg->enable_sequences) continue;     // as k_search_spec: those clusters go to the warp solver
         const uint64_t nv = b->var_off[r * 2 + 2] - b->var_off[r * 2];
         if (nv < min_n) continue;
         stats[0] += 1;
