@@ -309,7 +309,7 @@ AVK_HD inline int dist_symbol(int dist) {
 
 // everything deflate_member needs besides its input and output (shared memory on the device)
 struct DeflateWork {
-    uint16_t head[1 << DEFLATE_HASH_BITS];
+    uint16_t head[2 << DEFLATE_HASH_BITS];             // two most recent positions per hash bucket
     uint32_t lfreq[286], dfreq[30], cfreq[19];
     uint16_t lcode[286], dcode[30], ccode[19];         // bit-reversed canonical codes
     uint8_t llen[286], dlen[30], clen[19];
@@ -405,32 +405,49 @@ struct FixedSink {
     }
 };
 AVK_HD inline uint32_t hash3(const uint8_t *p) { return (((uint32_t)p[0] << 16 | (uint32_t)p[1] << 8 | p[2]) * 2654435761u) >> (32 - DEFLATE_HASH_BITS); }
-// the greedy parse: deterministic, so the counting pass and the emitting pass see the same literals and matches
+// Longest match for position i among the two most recent positions with the same hash (most recent first: on a tie the nearer
+// one, whose distance costs fewer bits, wins); remembers i.
+AVK_HD inline void lz_find(const uint8_t *in, uint32_t n, uint16_t *head, uint32_t i, int &len, int &dist) {
+    len = 0; dist = 0;
+    if (i + 3 > n) return;
+    uint16_t *b = head + 2 * hash3(in + i);
+    const int lim = (int)(n - i < 258u ? n - i : 258u);
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t cand = b[k];
+        if (cand == 0xffff || i - cand > 32768u) continue;
+        int l = 0;
+        while (l < lim && in[cand + l] == in[i + l]) ++l;
+        if (l > len) { len = l; dist = (int)(i - cand); }
+    }
+    b[1] = b[0]; b[0] = (uint16_t)i;
+}
+AVK_HD inline void lz_remember(const uint8_t *in, uint32_t n, uint16_t *head, uint32_t j) {
+    if (j + 3 > n) return;
+    uint16_t *b = head + 2 * hash3(in + j);
+    b[1] = b[0]; b[0] = (uint16_t)j;
+}
+// The LZ77 parse, greedy with one step of lazy evaluation (a short match gives way to a longer one starting at the next byte).
+// It is deterministic, so the counting pass and the emitting pass see the same literals and matches.
 template <class Sink>
 AVK_HD inline void lz_parse(const uint8_t *in, uint32_t n, uint16_t *head, Sink &sink) {
-    for (int i = 0; i < (1 << DEFLATE_HASH_BITS); ++i) head[i] = 0xffff;
+    for (int i = 0; i < 2 * (1 << DEFLATE_HASH_BITS); ++i) head[i] = 0xffff;
     uint32_t i = 0;
+    int len = 0, dist = 0;
+    bool have = false;
     while (i < n && !sink.stop()) {
-        int len = 0, dist = 0;
-        if (i + 3 <= n) {
-            const uint32_t h = hash3(in + i);
-            const uint32_t cand = head[h];
-            head[h] = (uint16_t)i;
-            if (cand != 0xffff && i - cand <= 32768u) {
-                const int lim = (int)(n - i < 258u ? n - i : 258u);
-                while (len < lim && in[cand + len] == in[i + len]) ++len;
-                dist = (int)(i - cand);
-            }
+        if (!have) lz_find(in, n, head, i, len, dist);
+        have = false;
+        if (len < 3) { sink.lit(in[i]); i += 1; continue; }
+        bool next_known = false;
+        if (len < 32 && i + 1 < n) {
+            int len2, dist2;
+            lz_find(in, n, head, i + 1, len2, dist2);
+            next_known = true;
+            if (len2 > len) { sink.lit(in[i]); i += 1; len = len2; dist = dist2; have = true; continue; }
         }
-        if (len >= 3) {
-            sink.match(len, dist);
-            if (len <= 16)                                     // remember the positions inside short matches too
-                for (uint32_t j = i + 1; j < i + (uint32_t)len && j + 3 <= n; ++j) head[hash3(in + j)] = (uint16_t)j;
-            i += (uint32_t)len;
-        } else {
-            sink.lit(in[i]);
-            i += 1;
-        }
+        sink.match(len, dist);
+        if (len <= 16) for (uint32_t j = i + (next_known ? 2 : 1); j < i + (uint32_t)len; ++j) lz_remember(in, n, head, j);   // positions inside short matches
+        i += (uint32_t)len;
     }
 }
 // header of a dynamic block (3.2.7): HLIT, HDIST, HCLEN, the code-length code, then both alphabets' lengths run-length coded
