@@ -269,8 +269,9 @@ AVK_HD inline uint32_t crc32_4(const uint32_t *t4, const uint8_t *buf, uint32_t 
 // ---- the other direction: one BGZF member's payload from at most 0xff00 bytes ------------------------------------------------
 // (the reference compresses truth.vcf.gz / query.vcf.gz / passing.vcf.gz through noodles' multithreaded bgzf
 // writer, src/writers/compare_parallel.rs:25-214, variant_merger.rs:124-147.  Any valid DEFLATE stream is a valid member: the
-// bytes differ from the reference's compressor's, the inflated content does not.)  One final block over a greedy LZ77 parse --
-// a hash of the next three bytes remembers the last position they were seen at.  The parse runs twice: once to count the
+// bytes differ from the reference's compressor's, the inflated content does not.)  One final block over an LZ77 parse -- a hash
+// of the next three bytes remembers the last two positions they were seen at; a short match gives way to a longer one that
+// starts at the next byte.  The parse runs twice: once to count the
 // symbols, from which length-limited Huffman codes are built (RFC 1951 3.2.7, dynamic block), once to emit; tiny inputs take
 // the fixed codes (3.2.6), and a stored block replaces whatever does not pay, so a member never exceeds 64 KiB.
 enum { DEFLATE_CHUNK = 0xff00, DEFLATE_HASH_BITS = 12, DEFLATE_MAX_OUT = DEFLATE_CHUNK + 5, DEFLATE_DYN_MIN = 128 };
