@@ -258,7 +258,8 @@ void avk_destroy(avk_ctx *ctx);
  * (avk_set_reference / avk_set_stratifications on a lane are errors) and has its own streams and buffers.  With one host
  * thread per context several batches -- e.g. the call sets of several samples against one truth set, the reference's
  * one-process-per-sample use of src/main.rs -- are in flight on one GPU: copies of one overlap kernels of another and the
- * passes fill each other's tails.  Destroy the lanes before the owner. */
+ * passes fill each other's tails.  Destroy the lanes before the owner, and do not replace the owner's reference or
+ * stratifications while a lane has a call in flight. */
 int avk_create_lane(avk_ctx *owner, avk_ctx **out);
 const char *avk_last_error(const avk_ctx *ctx);
 
