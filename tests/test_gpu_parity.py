@@ -1113,6 +1113,23 @@ def test_compare_random_adversarial_clusters_vs_oracle(solver, shape):
                 s.close()
 
 
+def test_compare_random_adversarial_clusters_exact_shortcut_and_sequences_vs_oracle(solver):
+    """The configurations that bypass the fast kernels (enable_exact_shortcut: waffle_solver.rs:171-199; enable_sequences: the
+    sequence bundle) on adversarial clusters whose query side is mostly a copy of the truth side, so that the shortcut fires --
+    including copies that contain ALT == REF records, repeated positions and overlapping records."""
+    ref, batch = _random_adversarial_batch(2500, seed=99, k_inputs=2, p_copy=0.6)
+    solver.set_reference([ref])
+    off, plen = seq_offsets(batch)
+    for mbf in (50, 2):
+        for shortcut in (True, False):
+            cfg = CompareConfig(enable_sequences=False, enable_exact_shortcut=shortcut, max_branch_factor=mbf)
+            cpu = orc.compare_batch(batch, [ref], compare_cfg(cfg))
+            assert solver.compare_batch(batch, cfg).diff(cpu) == [], (mbf, shortcut)
+        cs = CompareConfig(enable_sequences=True, enable_exact_shortcut=True, max_branch_factor=mbf)
+        cpu = orc.compare_batch(batch, [ref], compare_cfg(cs), seq_off=off, seq_pool_len=plen)
+        assert solver.compare_batch(batch, cs, seq_off=off, seq_pool_len=plen).diff(cpu) == [], (mbf, "sequences")
+
+
 def test_merge_random_adversarial_clusters_vs_oracle(solver):
     """solve_merge_region on randomly drawn clusters of four inputs that mostly agree (copies of the first input, sometimes
     minus a record) or are drawn independently -- overlapping records, repeated positions, ALT == REF -- under every merge
