@@ -453,6 +453,9 @@ int avk_compare_result_device(avk_ctx *ctx, avk_compare_dev_view *view);
  * [3] finalize/reduce, [4] total. */
 int avk_last_timings(avk_ctx *ctx, float *ms5);
 int avk_last_work(avk_ctx *ctx, avk_work_counters *out);
+/* Diagnostics: with AVK_SPEC_PROFILE=1 in the environment k_search_spec records per-cluster phase clocks (64 bytes per
+ * cluster, up to 65536 clusters); this copies the first n 64-bit words back (tools/spec_profile.py). */
+int avk_spec_profile(avk_ctx *ctx, unsigned long long *out, uint32_t n);
 /* Diagnostics: clusters that overflowed workspace tiers 0, 1, 2 in the last run. */
 int avk_last_tier_overflow(avk_ctx *ctx, uint32_t *out3);
 /* Diagnostics: device milliseconds spent in workspace tiers 0, 1, 2 in the last run. */
